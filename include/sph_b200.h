@@ -1,0 +1,182 @@
+/*
+ * sph_b200 -- C ABI of the B200-native TinySPH compute-rank timestep.
+ *
+ * Plain C: pointers and sizes only, no CUDA or torch types.  The library behind
+ * it (sph_b200/csrc -> libsph_b200.so) is hand-written CUDA for sm_100a and has
+ * NO CPU fallback: every entry point returns SPH_ERR_CUDA when no device is
+ * usable.
+ *
+ * Each entry point cites the reference interface it replaces
+ * (paths under AdamSimpson/SPH `src/`).  The reference-named wrappers
+ * (apply_gravity, hash_fluid, ... with the reference's own signatures) are in
+ * include/sph_ref_api.h and are implemented on top of this header.
+ *
+ * Data model: the reference passes a host AoS (`fluid_particle`, 52 bytes) plus
+ * a pointer-array view into every call (fluid.h:112-126).  Here the state is
+ * resident on the device as cell-sorted SoA float2 arrays; the host AoS is a
+ * mirror that is filled only on request (sph_download / sph_pack_coords).
+ */
+#ifndef SPH_B200_H
+#define SPH_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- records, bit-for-bit the reference's (fluid.h:56-106) ---- */
+
+/* == struct FLUID_PARTICLE (fluid.h:56-70): 52 bytes, id @48 */
+typedef struct sph_particle {
+    float x_prev, y_prev;
+    float x, y;
+    float v_x, v_y;
+    float a_x, a_y;               /* dead fields in the reference (fluid.c:763-764) */
+    float density, density_near;
+    float pressure, pressure_near;
+    int id;                       /* local index in the pointer array */
+} sph_particle;
+
+/* == struct TUNABLE_PARAMETERS (fluid.h:78-97): 64 bytes */
+typedef struct sph_tunable {
+    float rest_density;
+    float smoothing_radius;
+    float g;
+    float k;
+    float k_near;
+    float k_spring;
+    float sigma;
+    float beta;
+    float time_step;
+    float node_start_x;
+    float node_end_x;
+    float mover_center_x;
+    float mover_center_y;
+    float mover_width;
+    float mover_height;
+    char mover_type;              /* SPH_SPHERE_MOVER / SPH_RECTANGLE_MOVER (fluid.h:48-49) */
+    char kill_sim;
+    char active;
+} sph_tunable;
+
+/* == struct PARAM (fluid.h:100-106): 80 bytes, counts @64.. */
+typedef struct sph_param {
+    sph_tunable tunable_params;
+    int number_fluid_particles_global;
+    int number_fluid_particles_local;
+    int max_fluid_particle_index;
+    int number_halo_particles;
+} sph_param;
+
+#define SPH_SPHERE_MOVER 0
+#define SPH_RECTANGLE_MOVER 1
+
+/* reference capacities (fluid.c:174-175): detected, see sph_status */
+#define SPH_REF_MAX_BUCKET 100
+#define SPH_REF_MAX_NEIGHBORS 400
+
+/* ---- errors ---- */
+enum {
+    SPH_OK = 0,
+    SPH_ERR_CUDA = 1,        /* CUDA runtime error or no device: never falls back to the CPU */
+    SPH_ERR_ARG = 2,
+    SPH_ERR_CAPACITY = 3,    /* particle / message capacity exceeded */
+    SPH_ERR_STATE = 4
+};
+
+typedef struct sph_ctx sph_ctx;
+
+typedef struct sph_config {
+    float tank_w, tank_h;    /* boundary_global.max_x / max_y; min is 0 (fluid.c:117-127) */
+    float h;                 /* smoothing radius == hash grid spacing (fluid.c:159,176) */
+    int capacity;            /* max resident particles on this device (local + halo) */
+    int msg_capacity;        /* max particles in one neighbour message (halo or migrants) */
+    int device;              /* CUDA device ordinal */
+    int rank, nranks;        /* slab index / number of slabs; nranks == 1: no exchange */
+    float halo_width;        /* ghost-layer width in units of h; 0 -> default 2.0 */
+    void *stream;            /* cudaStream_t to run on, or NULL for a private stream */
+} sph_config;
+
+/* what the reference silently drops (hash.c:160-165, :188-197, :223-232) is counted here */
+typedef struct sph_status {
+    int n_local, n_halo;
+    int max_bucket;              /* largest cell population seen by the last sort */
+    int bucket_overflow;         /* cells above SPH_REF_MAX_BUCKET (reference would drop particles) */
+    int neighbor_overflow;       /* particles with > SPH_REF_MAX_NEIGHBORS forward neighbours */
+    int capacity_overflow;       /* particles dropped because `capacity` was exceeded (fatal) */
+    int msg_overflow;            /* particles that did not fit a neighbour message (fatal) */
+    int migrated_left, migrated_right;   /* last step */
+    long long steps;
+} sph_status;
+
+/* ---- lifecycle (the reference allocates everything in start_simulation, fluid.c:178-233) ---- */
+int sph_create(const sph_config *cfg, sph_ctx **out);
+void sph_destroy(sph_ctx *ctx);
+const char *sph_last_error(const sph_ctx *ctx);
+int sph_synchronize(sph_ctx *ctx);
+int sph_get_status(sph_ctx *ctx, sph_status *out);
+
+/* ---- parameters ---- */
+/* Full tunable block, as the render rank scatters it (fluid.c:293-294). Stream-ordered. */
+int sph_set_params(sph_ctx *ctx, const sph_tunable *t);
+/* Parameters that take effect between position prediction and migration of the NEXT
+ * advect stage, which is where the reference's MPI_Scatterv lands (fluid.c:279-310). */
+int sph_queue_params(sph_ctx *ctx, const sph_tunable *t);
+/* Slab edges only (node_start_x / node_end_x); used by migration and halo selection. */
+int sph_set_edges(sph_ctx *ctx, float node_start_x, float node_end_x);
+
+/* ---- state ---- */
+/* Host AoS -> device SoA, then bins by cell so the first viscosity pass has its
+ * neighbour structure (the reference starts with empty lists, fluid.c:202; velocities are
+ * zero there so both give no impulse).  uid may be NULL (uid = index). */
+int sph_upload(sph_ctx *ctx, const sph_particle *aos, const uint32_t *uid, int n);
+#define SPH_ORDER_UID 0      /* ascending uid == the reference's pointer order on one rank */
+#define SPH_ORDER_CELL 1     /* device order: row-major cell, then uid == bucket order */
+/* Device SoA -> host AoS (local particles; halo too if include_halo). Returns count or <0. */
+int sph_download(sph_ctx *ctx, sph_particle *aos, uint32_t *uid, int order, int include_halo);
+
+/* ---- stages: each is the gather form of the named reference functions ---- */
+/* apply_gravity (fluid.c:398) + viscosity_impluses (:416) + predict_positions (:507) incl.
+ * boundaryConditions (:656) + identify_oob_particles (:481): one fused kernel. */
+int sph_advect(sph_ctx *ctx);
+/* hash_fluid pass 1 (hash.c:148-166) + hash_halo insertion (hash.c:51): counting sort by
+ * hash_val (hash.c:35); completes the binning started inside advect/relax. */
+int sph_sort(sph_ctx *ctx);
+/* calculate_density over hash_fluid/hash_halo pairs (fluid.c:527, hash.c:190-228, :106-110) */
+int sph_density(sph_ctx *ctx);
+/* double_density_relaxation (fluid.c:541) + updateVelocities (:642) incl. boundaryConditions */
+int sph_relax(sph_ctx *ctx);
+/* n iterations of the loop at fluid.c:270-348 on one slab with no neighbours (nranks == 1);
+ * replayed from a CUDA graph. */
+int sph_step(sph_ctx *ctx, int n);
+
+/* ---- slab exchange (communication.c:120-450): device-side message buffers ---- */
+/* Message layout: 16-byte header {int n_migrants, n_halo, 0, 0} then records.  The
+ * pack is fused into advect/relax, the unpack into sort; a transport only moves bytes.
+ * which = 0: after advect (migrants + predicted-position halo), 1: after relax (pos+vel halo). */
+int sph_exchange_buffers(sph_ctx *ctx, int which, void **send_left, void **recv_left,
+                         void **send_right, void **recv_right, size_t *bytes);
+/* Mark a neighbour as absent for the coming sort (edge slabs): its recv buffer is ignored. */
+int sph_set_neighbors(sph_ctx *ctx, int has_left, int has_right);
+
+/* ---- parity / inspection ---- */
+/* per local particle: uid and hash_val cell id in the reference's GLOBAL grid numbering */
+int sph_get_cells(sph_ctx *ctx, uint32_t *uid, uint32_t *cell, int cap);
+/* every pair (uid_a < uid_b) with unfused r2 <= h2 among resident particles: the symmetric
+ * closure of the reference's forward lists (hash.c:185,221,99). Returns pair count or <0. */
+long long sph_get_pairs(sph_ctx *ctx, uint64_t *pairs, long long cap);
+/* forward-neighbour count per local particle under the reference's ownership rule */
+int sph_get_forward_counts(sph_ctx *ctx, uint32_t *uid, int *count, int cap);
+
+/* ---- render feed (fluid.c:354-365): int16 pixel-range coordinates of local particles ---- */
+int sph_pack_coords(sph_ctx *ctx, int16_t *xy_pairs, int cap);
+
+/* kernels launched since the context was created (bench bookkeeping) */
+long long sph_launch_count(const sph_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
