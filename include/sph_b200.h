@@ -173,6 +173,13 @@ int sph_get_forward_counts(sph_ctx *ctx, uint32_t *uid, int *count, int cap);
 /* ---- render feed (fluid.c:354-365): int16 pixel-range coordinates of local particles ---- */
 int sph_pack_coords(sph_ctx *ctx, int16_t *xy_pairs, int cap);
 
+/* ---- one render frame of the compute rank (the loop body at fluid.c:270-372, `steps` times) ----
+ * `t` (may be NULL) is the block the render rank scatters; it lands in the LAST sub-step between
+ * position prediction and migration (fluid.c:293-294).  Afterwards the int16 coordinate feed
+ * (fluid.c:354-365) is copied into the HOST buffer xy_pairs (may be NULL).  nranks == 1 only.
+ * Returns the local particle count or a negative error. */
+int sph_run_frame(sph_ctx *ctx, const sph_tunable *t, int steps, int16_t *xy_pairs, int cap);
+
 /* kernels launched since the context was created (bench bookkeeping) */
 long long sph_launch_count(const sph_ctx *ctx);
 

@@ -1,0 +1,221 @@
+"""sph_b200 -- B200-native TinySPH compute-rank timestep.
+
+Python is plumbing here: this module binds the C ABI in include/sph_b200.h
+(libsph_b200.so, hand-written CUDA for sm_100a) with ctypes so that tests, bench.py and the
+multi-rank driver (sph_b200.slab) can call it.  There is NO CPU fallback: importing works
+without a GPU (so the symbol table can be checked), but creating a Context without the built
+library or without a CUDA device raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libsph_b200.so")
+
+# == struct FLUID_PARTICLE (fluid.h:56-70), 52 bytes
+PARTICLE = np.dtype([("x_prev", "f4"), ("y_prev", "f4"), ("x", "f4"), ("y", "f4"),
+                     ("v_x", "f4"), ("v_y", "f4"), ("a_x", "f4"), ("a_y", "f4"),
+                     ("density", "f4"), ("density_near", "f4"),
+                     ("pressure", "f4"), ("pressure_near", "f4"), ("id", "i4")])
+
+ORDER_UID, ORDER_CELL = 0, 1
+HALO_BIT = 0x80000000
+UID_MASK = 0x7FFFFFFF
+
+
+class Tunable(C.Structure):
+    """== struct TUNABLE_PARAMETERS (fluid.h:78-97), 64 bytes."""
+    _fields_ = [(n, C.c_float) for n in (
+        "rest_density", "smoothing_radius", "g", "k", "k_near", "k_spring", "sigma", "beta",
+        "time_step", "node_start_x", "node_end_x", "mover_center_x", "mover_center_y",
+        "mover_width", "mover_height")] + [("mover_type", C.c_char), ("kill_sim", C.c_char),
+                                           ("active", C.c_char)]
+
+    def copy(self):
+        t = Tunable()
+        C.memmove(C.byref(t), C.byref(self), C.sizeof(Tunable))
+        return t
+
+
+class Config(C.Structure):
+    """== sph_config."""
+    _fields_ = [("tank_w", C.c_float), ("tank_h", C.c_float), ("h", C.c_float),
+                ("capacity", C.c_int), ("msg_capacity", C.c_int), ("device", C.c_int),
+                ("rank", C.c_int), ("nranks", C.c_int), ("halo_width", C.c_float),
+                ("stream", C.c_void_p)]
+
+
+class Status(C.Structure):
+    """== sph_status."""
+    _fields_ = [(n, C.c_int) for n in (
+        "n_local", "n_halo", "max_bucket", "bucket_overflow", "neighbor_overflow",
+        "capacity_overflow", "msg_overflow", "migrated_left", "migrated_right")] + [("steps", C.c_longlong)]
+
+
+# every symbol include/sph_b200.h declares
+C_ABI_SYMBOLS = (
+    "sph_create", "sph_destroy", "sph_last_error", "sph_synchronize", "sph_get_status",
+    "sph_set_params", "sph_queue_params", "sph_set_edges", "sph_upload", "sph_download",
+    "sph_advect", "sph_sort", "sph_density", "sph_relax", "sph_step", "sph_exchange_buffers",
+    "sph_set_neighbors", "sph_get_cells", "sph_get_pairs", "sph_get_forward_counts",
+    "sph_pack_coords", "sph_launch_count", "sph_run_frame",
+)
+
+_lib = None
+
+
+class SphError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load libsph_b200.so; raises when it has not been built (no fallback of any kind)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise SphError(f"{LIB_PATH} is missing: build it with `python -m sph_b200.build` "
+                           "(nvcc, sm_100a). sph_b200 has no CPU path.")
+        L = C.CDLL(LIB_PATH)
+        L.sph_last_error.restype = C.c_char_p
+        L.sph_last_error.argtypes = [C.c_void_p]
+        L.sph_launch_count.restype = C.c_longlong
+        L.sph_launch_count.argtypes = [C.c_void_p]
+        L.sph_get_pairs.restype = C.c_longlong
+        L.sph_get_pairs.argtypes = [C.c_void_p, C.c_void_p, C.c_longlong]
+        L.sph_set_edges.argtypes = [C.c_void_p, C.c_float, C.c_float]
+        L.sph_create.argtypes = [C.POINTER(Config), C.POINTER(C.c_void_p)]
+        for name in ("sph_destroy", "sph_synchronize", "sph_advect", "sph_sort", "sph_density", "sph_relax"):
+            getattr(L, name).argtypes = [C.c_void_p]
+        L.sph_step.argtypes = [C.c_void_p, C.c_int]
+        L.sph_set_params.argtypes = [C.c_void_p, C.POINTER(Tunable)]
+        L.sph_queue_params.argtypes = [C.c_void_p, C.POINTER(Tunable)]
+        L.sph_get_status.argtypes = [C.c_void_p, C.POINTER(Status)]
+        L.sph_upload.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.sph_download.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+        L.sph_set_neighbors.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.sph_get_cells.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.sph_get_forward_counts.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.sph_pack_coords.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        L.sph_run_frame.argtypes = [C.c_void_p, C.POINTER(Tunable), C.c_int, C.c_void_p, C.c_int]
+        L.sph_exchange_buffers.argtypes = [C.c_void_p, C.c_int] + [C.POINTER(C.c_void_p)] * 4 + [C.POINTER(C.c_size_t)]
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Context:
+    """One slab of the simulation resident on one GPU (sph_ctx)."""
+
+    def __init__(self, tank_w, tank_h, h, capacity, msg_capacity=1, device=0, rank=0, nranks=1,
+                 halo_width=2.0, stream=None):
+        self.L = lib()
+        self.capacity = int(capacity)
+        self.cfg = Config(tank_w, tank_h, h, int(capacity), int(msg_capacity), device, rank, nranks,
+                          halo_width, stream)
+        self.h = C.c_void_p()
+        rc = self.L.sph_create(C.byref(self.cfg), C.byref(self.h))
+        if rc != 0:
+            msg = self.L.sph_last_error(self.h).decode() if self.h else "sph_create failed"
+            if self.h:
+                self.L.sph_destroy(self.h)
+                self.h = None
+            raise SphError(f"sph_create -> {rc}: {msg}")
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.sph_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def _ck(self, rc, what):
+        if rc != 0:
+            raise SphError(f"{what} -> {rc}: {self.L.sph_last_error(self.h).decode()}")
+
+    def set_params(self, t): self._ck(self.L.sph_set_params(self.h, C.byref(t)), "sph_set_params")
+    def queue_params(self, t): self._ck(self.L.sph_queue_params(self.h, C.byref(t)), "sph_queue_params")
+    def set_edges(self, s, e): self._ck(self.L.sph_set_edges(self.h, s, e), "sph_set_edges")
+    def set_neighbors(self, l, r): self._ck(self.L.sph_set_neighbors(self.h, int(l), int(r)), "sph_set_neighbors")
+    def synchronize(self): self._ck(self.L.sph_synchronize(self.h), "sph_synchronize")
+
+    def upload(self, aos, uid=None):
+        aos = np.ascontiguousarray(aos, PARTICLE)
+        u = None if uid is None else np.ascontiguousarray(uid, "u4")
+        self._ck(self.L.sph_upload(self.h, _p(aos), None if u is None else _p(u), len(aos)), "sph_upload")
+
+    def download(self, order=ORDER_UID, include_halo=False):
+        a = np.zeros(self.capacity, PARTICLE)
+        u = np.zeros(self.capacity, "u4")
+        n = self.L.sph_download(self.h, _p(a), _p(u), order, int(include_halo))
+        if n < 0:
+            self._ck(-n, "sph_download")
+        return a[:n].copy(), u[:n].copy()
+
+    def advect(self): self._ck(self.L.sph_advect(self.h), "sph_advect")
+    def sort(self): self._ck(self.L.sph_sort(self.h), "sph_sort")
+    def density(self): self._ck(self.L.sph_density(self.h), "sph_density")
+    def relax(self): self._ck(self.L.sph_relax(self.h), "sph_relax")
+    def step(self, n=1): self._ck(self.L.sph_step(self.h, int(n)), "sph_step")
+
+    def run_frame(self, tunable, steps, coords_out):
+        """One render frame (fluid.c:270-372): `steps` sub-steps, the parameter scatter landing in
+        the last one, then the int16 coordinate feed into `coords_out` (host array). Returns n_local."""
+        n = self.L.sph_run_frame(self.h, C.byref(tunable) if tunable is not None else None, int(steps),
+                                 _p(coords_out) if coords_out is not None else None,
+                                 0 if coords_out is None else coords_out.size // 2)
+        if n < 0:
+            self._ck(-n, "sph_run_frame")
+        return n
+
+    def status(self):
+        s = Status()
+        self._ck(self.L.sph_get_status(self.h, C.byref(s)), "sph_get_status")
+        return s
+
+    def exchange_pointers(self, which):
+        """Device pointers (send_left, recv_left, send_right, recv_right) and message bytes."""
+        ptr = [C.c_void_p() for _ in range(4)]
+        nb = C.c_size_t()
+        self._ck(self.L.sph_exchange_buffers(self.h, which, *[C.byref(p) for p in ptr], C.byref(nb)),
+                 "sph_exchange_buffers")
+        return [p.value for p in ptr], nb.value
+
+    def cells(self):
+        u = np.zeros(self.capacity, "u4"); c = np.zeros(self.capacity, "u4")
+        n = self.L.sph_get_cells(self.h, _p(u), _p(c), self.capacity)
+        if n < 0:
+            self._ck(-n, "sph_get_cells")
+        return u[:n].copy(), c[:n].copy()
+
+    def pairs(self):
+        n = self.L.sph_get_pairs(self.h, None, 0)
+        if n < 0:
+            self._ck(int(-n), "sph_get_pairs")
+        out = np.zeros(max(int(n), 1), "u8")
+        n = self.L.sph_get_pairs(self.h, _p(out), len(out))
+        if n < 0:
+            self._ck(int(-n), "sph_get_pairs")
+        return np.sort(out[:n])
+
+    def forward_counts(self):
+        u = np.zeros(self.capacity, "u4"); c = np.zeros(self.capacity, "i4")
+        n = self.L.sph_get_forward_counts(self.h, _p(u), _p(c), self.capacity)
+        if n < 0:
+            self._ck(-n, "sph_get_forward_counts")
+        return u[:n].copy(), c[:n].copy()
+
+    def pack_coords(self):
+        xy = np.zeros(2 * self.capacity, "i2")
+        n = self.L.sph_pack_coords(self.h, _p(xy), self.capacity)
+        if n < 0:
+            self._ck(-n, "sph_pack_coords")
+        return xy[:2 * n].reshape(n, 2).copy()
+
+    @property
+    def launches(self):
+        return int(self.L.sph_launch_count(self.h))

@@ -1,0 +1,624 @@
+// C-ABI of the B200-native TinySPH compute-rank timestep (include/sph_b200.h).
+// Host side of the CUDA library: context, buffers, stage launches, CUDA-graph step loop.
+// There is no CPU path in this file: every failure to reach the GPU is SPH_ERR_CUDA.
+#include "../../include/sph_b200.h"
+#include "sph_kernels.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+enum { ST_READY = 0, ST_ADVECTED, ST_SORTED1, ST_DENSITY, ST_RELAXED };
+
+struct sph_ctx {
+    sph_config cfg;
+    cudaStream_t stream;
+    bool own_stream;
+    DevParams hp;            // host shadow of *dp, always describing the state after all launched work
+    DevParams *dp;
+    sph_tunable tun, queued;
+    bool have_queued;
+    int *counters;
+    // rotating SoA buffers: see the role table in launch_* below
+    float2 *P[4];
+    float2 *Q[3];
+    uint32_t *U[2];
+    float2 *dens;
+    int *cnt, *cell_start, *t_key, *t_slot, *ord_src;
+    uint32_t *ord_uid;
+    unsigned long long *tile_state;
+    unsigned char *send[2], *recv[2];
+    short2 *coords;
+    int stage;
+    int grid;
+    int size_x, size_y;
+    cudaGraphExec_t graph;
+    bool graph_ready;
+    long long launches;
+    long long steps;
+    char err[256];
+};
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            snprintf(ctx->err, sizeof ctx->err, "%s:%d %s: %s", __FILE__, __LINE__, #call,         \
+                     cudaGetErrorString(e_));                                                      \
+            return SPH_ERR_CUDA;                                                                   \
+        }                                                                                          \
+    } while (0)
+
+static int fail(sph_ctx *ctx, int code, const char *msg)
+{
+    snprintf(ctx->err, sizeof ctx->err, "%s", msg);
+    return code;
+}
+
+// window of grid columns a slab can touch: slab + ghost layer + one spare column
+static void compute_window(const sph_ctx *ctx, float edge_start, float edge_end, int *gx0, int *wx)
+{
+    if (ctx->cfg.nranks <= 1) { *gx0 = 0; *wx = ctx->size_x; return; }
+    float w = ctx->cfg.halo_width * ctx->cfg.h;
+    int lo = (int)floorf((edge_start - w) / ctx->cfg.h) - 1;
+    int hi = (int)floorf((edge_end + w) / ctx->cfg.h) + 1;
+    lo = std::max(lo, 0);
+    hi = std::min(hi, ctx->size_x - 1);
+    hi = std::max(hi, lo);
+    *gx0 = lo;
+    *wx = hi - lo + 1;
+}
+
+static void fill_phys(DevParams &P, const sph_tunable &t)
+{
+    P.rest_density = t.rest_density; P.h = t.smoothing_radius; P.g = t.g; P.k = t.k; P.k_near = t.k_near;
+    P.k_spring = t.k_spring; P.sigma = t.sigma; P.beta = t.beta; P.dt = t.time_step;
+    P.mover_cx = t.mover_center_x; P.mover_cy = t.mover_center_y; P.mover_w = t.mover_width;
+    P.mover_h = t.mover_height; P.mover_type = (int)t.mover_type;
+}
+
+static void fill_edges(sph_ctx *ctx, float s, float e)
+{
+    ctx->hp.edge_start = s; ctx->hp.edge_end = e;
+    compute_window(ctx, s, e, &ctx->hp.gx0_new, &ctx->hp.wx_new);
+}
+
+static int push_params(sph_ctx *ctx)
+{
+    // pageable source: the runtime stages the 128 bytes before returning, so hp may change right away
+    CK(cudaMemcpyAsync(ctx->dp, &ctx->hp, sizeof(DevParams), cudaMemcpyHostToDevice, ctx->stream));
+    return SPH_OK;
+}
+
+extern "C" int sph_create(const sph_config *cfg, sph_ctx **out)
+{
+    if (!cfg || !out || cfg->capacity <= 0 || cfg->h <= 0.0f || cfg->nranks < 1) return SPH_ERR_ARG;
+    sph_ctx *ctx = new sph_ctx();
+    memset(ctx, 0, sizeof *ctx);
+    *out = ctx;
+    ctx->cfg = *cfg;
+    if (ctx->cfg.halo_width <= 0.0f) ctx->cfg.halo_width = 2.0f;
+    if (ctx->cfg.msg_capacity <= 0) ctx->cfg.msg_capacity = 1;
+    int ndev = 0;
+    CK(cudaGetDeviceCount(&ndev));
+    if (ndev == 0) return fail(ctx, SPH_ERR_CUDA, "no CUDA device: sph_b200 has no CPU path");
+    CK(cudaSetDevice(cfg->device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, cfg->device));
+    if (cfg->stream) { ctx->stream = (cudaStream_t)cfg->stream; ctx->own_stream = false; }
+    else { CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)); ctx->own_stream = true; }
+
+    ctx->size_x = (int)ceil((cfg->tank_w - 0.0f) / cfg->h);      // fluid.c:214-215
+    ctx->size_y = (int)ceil((cfg->tank_h - 0.0f) / cfg->h);
+    const size_t cap = (size_t)cfg->capacity;
+    const size_t ncell_max = (size_t)ctx->size_x * ctx->size_y;
+    ctx->grid = std::min<int>((int)((cap + SPH_THREADS - 1) / SPH_THREADS), prop.multiProcessorCount * 8);
+
+    for (int i = 0; i < 4; i++) CK(cudaMalloc(&ctx->P[i], cap * sizeof(float2)));
+    for (int i = 0; i < 3; i++) CK(cudaMalloc(&ctx->Q[i], cap * sizeof(float2)));
+    for (int i = 0; i < 2; i++) CK(cudaMalloc(&ctx->U[i], cap * sizeof(uint32_t)));
+    CK(cudaMalloc(&ctx->dens, cap * sizeof(float2)));
+    CK(cudaMalloc(&ctx->cnt, (ncell_max + 1) * sizeof(int)));
+    CK(cudaMalloc(&ctx->cell_start, (ncell_max + 1) * sizeof(int)));
+    CK(cudaMalloc(&ctx->t_key, cap * sizeof(int)));
+    CK(cudaMalloc(&ctx->t_slot, cap * sizeof(int)));
+    CK(cudaMalloc(&ctx->ord_src, cap * sizeof(int)));
+    CK(cudaMalloc(&ctx->ord_uid, cap * sizeof(uint32_t)));
+    CK(cudaMalloc(&ctx->coords, cap * sizeof(short2)));
+    const size_t ntiles_max = (ncell_max + SCAN_TILE - 1) / SCAN_TILE + 1;
+    CK(cudaMalloc(&ctx->tile_state, ntiles_max * sizeof(unsigned long long)));
+    CK(cudaMemset(ctx->tile_state, 0, ntiles_max * sizeof(unsigned long long)));
+    CK(cudaMemset(ctx->cnt, 0, (ncell_max + 1) * sizeof(int)));
+    CK(cudaMemset(ctx->cell_start, 0, (ncell_max + 1) * sizeof(int)));
+    CK(cudaMalloc(&ctx->counters, CN_COUNT * sizeof(int)));
+    CK(cudaMemset(ctx->counters, 0, CN_COUNT * sizeof(int)));
+    int one = 1;
+    CK(cudaMemcpy(ctx->counters + CN_EPOCH, &one, sizeof(int), cudaMemcpyHostToDevice));
+    const size_t mb = msg_bytes_full(ctx->cfg.msg_capacity);
+    for (int s = 0; s < 2; s++) {
+        CK(cudaMalloc(&ctx->send[s], mb));
+        CK(cudaMalloc(&ctx->recv[s], mb));
+        CK(cudaMemset(ctx->send[s], 0, mb));
+        CK(cudaMemset(ctx->recv[s], 0, mb));
+    }
+    CK(cudaMalloc(&ctx->dp, sizeof(DevParams)));
+
+    DevParams &P = ctx->hp;
+    P.tank_w = cfg->tank_w; P.tank_h = cfg->tank_h; P.cell_h = cfg->h;
+    P.size_x = ctx->size_x; P.size_y = ctx->size_y;
+    P.halo_w = ctx->cfg.halo_width * cfg->h;
+    P.has_left = cfg->rank > 0; P.has_right = cfg->rank < cfg->nranks - 1; P.nranks = cfg->nranks;
+    P.cap = cfg->capacity; P.msg_cap = ctx->cfg.msg_capacity;
+    P.h = cfg->h; P.dt = 1.0f / 120.0f; P.mover_type = -1;
+    fill_edges(ctx, 0.0f, cfg->tank_w);
+    P.gx0 = P.gx0_new; P.wx = P.wx_new;
+    int rc = push_params(ctx);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->stage = ST_READY;
+    return SPH_OK;
+}
+
+extern "C" void sph_destroy(sph_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->graph_ready) cudaGraphExecDestroy(ctx->graph);
+    for (int i = 0; i < 4; i++) cudaFree(ctx->P[i]);
+    for (int i = 0; i < 3; i++) cudaFree(ctx->Q[i]);
+    for (int i = 0; i < 2; i++) cudaFree(ctx->U[i]);
+    cudaFree(ctx->dens); cudaFree(ctx->cnt); cudaFree(ctx->cell_start); cudaFree(ctx->t_key);
+    cudaFree(ctx->t_slot); cudaFree(ctx->ord_src); cudaFree(ctx->ord_uid); cudaFree(ctx->coords);
+    cudaFree(ctx->tile_state); cudaFree(ctx->counters); cudaFree(ctx->dp);
+    for (int s = 0; s < 2; s++) { cudaFree(ctx->send[s]); cudaFree(ctx->recv[s]); }
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+extern "C" const char *sph_last_error(const sph_ctx *ctx) { return ctx ? ctx->err : "null context"; }
+extern "C" long long sph_launch_count(const sph_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" int sph_synchronize(sph_ctx *ctx)
+{
+    CK(cudaStreamSynchronize(ctx->stream));
+    return SPH_OK;
+}
+
+extern "C" int sph_set_params(sph_ctx *ctx, const sph_tunable *t)
+{
+    if (!ctx || !t) return SPH_ERR_ARG;
+    ctx->tun = *t;
+    fill_phys(ctx->hp, *t);
+    fill_edges(ctx, t->node_start_x, t->node_end_x);
+    return push_params(ctx);
+}
+
+extern "C" int sph_queue_params(sph_ctx *ctx, const sph_tunable *t)
+{
+    if (!ctx || !t) return SPH_ERR_ARG;
+    ctx->queued = *t;
+    ctx->have_queued = true;
+    return SPH_OK;
+}
+
+extern "C" int sph_set_edges(sph_ctx *ctx, float s, float e)
+{
+    if (!ctx) return SPH_ERR_ARG;
+    ctx->tun.node_start_x = s; ctx->tun.node_end_x = e;
+    fill_edges(ctx, s, e);
+    return push_params(ctx);
+}
+
+extern "C" int sph_set_neighbors(sph_ctx *ctx, int has_left, int has_right)
+{
+    if (!ctx) return SPH_ERR_ARG;
+    ctx->hp.has_left = has_left; ctx->hp.has_right = has_right;
+    return push_params(ctx);
+}
+
+extern "C" int sph_exchange_buffers(sph_ctx *ctx, int which, void **sl, void **rl, void **sr, void **rr, size_t *bytes)
+{
+    if (!ctx) return SPH_ERR_ARG;
+    if (sl) *sl = ctx->send[0];
+    if (rl) *rl = ctx->recv[0];
+    if (sr) *sr = ctx->send[1];
+    if (rr) *rr = ctx->recv[1];
+    if (bytes) *bytes = which == 0 ? msg_bytes_full(ctx->cfg.msg_capacity) : msg_bytes_halo1(ctx->cfg.msg_capacity);
+    return SPH_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// stage launches.  Buffer roles (period-1 rotation, so one captured graph is a whole step):
+//   READY    : pos P0, vel Q0, uid U0 (cell-sorted)
+//   advect   : reads P0,Q0,U0            writes predicted pos P1 (source order)
+//   sort 1   : src (P1, prev=P0, U0)     dst (P2, prev Q1, U1)
+//   density  : reads P2                  writes dens
+//   relax    : reads P2,Q1,U1,dens       writes relaxed pos P3, vel Q2 (source order)
+//   sort 2   : src (P3, Q2, U1)          dst (P0, Q0, U0)
+// ------------------------------------------------------------------------------------------
+static int launch_sort(sph_ctx *ctx, int which, bool with_unpack = true)
+{
+    float2 *sp = which == 0 ? ctx->P[1] : ctx->P[3];
+    float2 *sq = which == 0 ? ctx->P[0] : ctx->Q[2];
+    uint32_t *su = which == 0 ? ctx->U[0] : ctx->U[1];
+    float2 *dp = which == 0 ? ctx->P[2] : ctx->P[0];
+    float2 *dq = which == 0 ? ctx->Q[1] : ctx->Q[0];
+    uint32_t *du = which == 0 ? ctx->U[1] : ctx->U[0];
+    if (ctx->cfg.nranks > 1 && with_unpack) {
+        k_unpack<<<ctx->grid, SPH_THREADS, 0, ctx->stream>>>(ctx->dp, ctx->counters, which, ctx->recv[0], ctx->recv[1],
+                                                             sp, sq, su, ctx->cnt, ctx->t_key, ctx->t_slot);
+        ctx->launches++;
+    }
+    const int ncell = ctx->hp.wx_new * ctx->size_y;
+    const int ntiles = (ncell + SCAN_TILE - 1) / SCAN_TILE;
+    k_scan<<<ntiles, SPH_THREADS, 0, ctx->stream>>>(ctx->dp, ctx->counters, ctx->cnt, ctx->cell_start, ctx->tile_state,
+                                                    ctx->cfg.nranks > 1 ? ctx->send[0] : nullptr,
+                                                    ctx->cfg.nranks > 1 ? ctx->send[1] : nullptr);
+    k_scatter<<<ctx->grid, SPH_THREADS, 0, ctx->stream>>>(ctx->counters, ctx->cell_start, ctx->t_key, ctx->t_slot, su,
+                                                          ctx->ord_uid, ctx->ord_src);
+    k_reorder<<<ctx->grid, SPH_THREADS, 0, ctx->stream>>>(ctx->dp, ctx->counters, ctx->cell_start, ctx->t_key,
+                                                          ctx->ord_uid, ctx->ord_src, sp, sq, dp, dq, du);
+    ctx->launches += 3;
+    ctx->hp.gx0 = ctx->hp.gx0_new;     // the scan kernel did the same on the device
+    ctx->hp.wx = ctx->hp.wx_new;
+    CK(cudaGetLastError());
+    return SPH_OK;
+}
+
+static int launch_advect(sph_ctx *ctx)
+{
+    k_advect<<<ctx->grid, SPH_THREADS, 0, ctx->stream>>>(ctx->dp, ctx->counters, ctx->P[0], ctx->Q[0], ctx->U[0],
+                                                         ctx->cell_start, ctx->P[1], ctx->cnt, ctx->t_key, ctx->t_slot,
+                                                         ctx->send[0], ctx->send[1]);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return SPH_OK;
+}
+
+static int launch_density(sph_ctx *ctx)
+{
+    k_density<<<ctx->grid, SPH_THREADS, 0, ctx->stream>>>(ctx->dp, ctx->counters, ctx->P[2], ctx->cell_start, ctx->dens);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return SPH_OK;
+}
+
+static int launch_relax(sph_ctx *ctx)
+{
+    k_relax<<<ctx->grid, SPH_THREADS, 0, ctx->stream>>>(ctx->dp, ctx->counters, ctx->P[2], ctx->Q[1], ctx->U[1], ctx->dens,
+                                                        ctx->cell_start, ctx->P[3], ctx->Q[2], ctx->cnt, ctx->t_key,
+                                                        ctx->t_slot, ctx->send[0], ctx->send[1]);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return SPH_OK;
+}
+
+extern "C" int sph_advect(sph_ctx *ctx)
+{
+    if (!ctx) return SPH_ERR_ARG;
+    if (ctx->stage != ST_READY) return fail(ctx, SPH_ERR_STATE, "sph_advect: state is not at a step boundary");
+    int rc;
+    if (ctx->have_queued) {
+        // the scatter from the render rank lands between prediction and migration (fluid.c:279-310):
+        // new slab edges first (only the classification at the end of the kernel reads them) ...
+        fill_edges(ctx, ctx->queued.node_start_x, ctx->queued.node_end_x);
+        if ((rc = push_params(ctx))) return rc;
+    }
+    if ((rc = launch_advect(ctx))) return rc;
+    if (ctx->have_queued) {
+        // ... then everything else, for the stages after the prediction
+        ctx->have_queued = false;
+        if ((rc = sph_set_params(ctx, &ctx->queued))) return rc;
+    }
+    ctx->stage = ST_ADVECTED;
+    return SPH_OK;
+}
+
+extern "C" int sph_sort(sph_ctx *ctx)
+{
+    if (!ctx) return SPH_ERR_ARG;
+    int rc;
+    if (ctx->stage == ST_ADVECTED) { if ((rc = launch_sort(ctx, 0))) return rc; ctx->stage = ST_SORTED1; }
+    else if (ctx->stage == ST_RELAXED) { if ((rc = launch_sort(ctx, 1))) return rc; ctx->stage = ST_READY; ctx->steps++; }
+    else return fail(ctx, SPH_ERR_STATE, "sph_sort: nothing to sort");
+    return SPH_OK;
+}
+
+extern "C" int sph_density(sph_ctx *ctx)
+{
+    if (!ctx) return SPH_ERR_ARG;
+    if (ctx->stage != ST_SORTED1) return fail(ctx, SPH_ERR_STATE, "sph_density: call after the first sort");
+    int rc = launch_density(ctx);
+    if (rc) return rc;
+    ctx->stage = ST_DENSITY;
+    return SPH_OK;
+}
+
+extern "C" int sph_relax(sph_ctx *ctx)
+{
+    if (!ctx) return SPH_ERR_ARG;
+    if (ctx->stage != ST_DENSITY) return fail(ctx, SPH_ERR_STATE, "sph_relax: call after sph_density");
+    int rc = launch_relax(ctx);
+    if (rc) return rc;
+    ctx->stage = ST_RELAXED;
+    return SPH_OK;
+}
+
+static int launch_step(sph_ctx *ctx)
+{
+    int rc;
+    if ((rc = launch_advect(ctx))) return rc;
+    if ((rc = launch_sort(ctx, 0))) return rc;
+    if ((rc = launch_density(ctx))) return rc;
+    if ((rc = launch_relax(ctx))) return rc;
+    if ((rc = launch_sort(ctx, 1))) return rc;
+    return SPH_OK;
+}
+
+extern "C" int sph_step(sph_ctx *ctx, int n)
+{
+    if (!ctx || n < 0) return SPH_ERR_ARG;
+    if (ctx->cfg.nranks != 1) return fail(ctx, SPH_ERR_STATE, "sph_step: slabs with neighbours step stage by stage");
+    if (ctx->stage != ST_READY) return fail(ctx, SPH_ERR_STATE, "sph_step: state is not at a step boundary");
+    int rc;
+    for (int s = 0; s < n; s++) {
+        if (ctx->have_queued) {           // parameter change inside this step: run it stage by stage
+            if ((rc = sph_advect(ctx)) || (rc = sph_sort(ctx)) || (rc = sph_density(ctx)) ||
+                (rc = sph_relax(ctx)) || (rc = sph_sort(ctx))) return rc;
+            continue;
+        }
+        if (!ctx->graph_ready) {
+            cudaGraph_t g;
+            long long before = ctx->launches;
+            CK(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+            rc = launch_step(ctx);
+            cudaError_t e = cudaStreamEndCapture(ctx->stream, &g);
+            ctx->launches = before;
+            if (rc) return rc;
+            CK(e);
+            CK(cudaGraphInstantiate(&ctx->graph, g, 0));
+            CK(cudaGraphDestroy(g));
+            ctx->graph_ready = true;
+        }
+        CK(cudaGraphLaunch(ctx->graph, ctx->stream));
+        ctx->launches += 9;
+        ctx->steps++;
+    }
+    return SPH_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// state transfer
+// ------------------------------------------------------------------------------------------
+extern "C" int sph_upload(sph_ctx *ctx, const sph_particle *aos, const uint32_t *uid, int n)
+{
+    if (!ctx || (!aos && n > 0) || n < 0) return SPH_ERR_ARG;
+    if (n > ctx->cfg.capacity) return fail(ctx, SPH_ERR_CAPACITY, "sph_upload: more particles than capacity");
+    std::vector<float2> p(n), v(n);
+    std::vector<uint32_t> u(n);
+    for (int i = 0; i < n; i++) {
+        p[i] = make_float2(aos[i].x, aos[i].y);
+        v[i] = make_float2(aos[i].v_x, aos[i].v_y);
+        u[i] = uid ? (uid[i] & SPH_UID_MASK) : (uint32_t)i;
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    // enter the pipeline where sort 2 does: source arrays P3 / Q2 / U1
+    CK(cudaMemcpyAsync(ctx->P[3], p.data(), n * sizeof(float2), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->Q[2], v.data(), n * sizeof(float2), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->U[1], u.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    int zero[CN_COUNT] = {0};
+    zero[CN_NTOT] = n;
+    int epoch = 0;
+    CK(cudaMemcpy(&epoch, ctx->counters + CN_EPOCH, sizeof(int), cudaMemcpyDeviceToHost));
+    zero[CN_EPOCH] = epoch;
+    CK(cudaMemcpyAsync(ctx->counters, zero, sizeof zero, cudaMemcpyHostToDevice, ctx->stream));
+    const size_t ncell_max = (size_t)ctx->size_x * ctx->size_y;
+    CK(cudaMemsetAsync(ctx->cnt, 0, (ncell_max + 1) * sizeof(int), ctx->stream));
+    int rc = push_params(ctx);
+    if (rc) return rc;
+    k_bin_upload<<<ctx->grid, SPH_THREADS, 0, ctx->stream>>>(ctx->dp, ctx->counters, ctx->P[3], ctx->cnt, ctx->t_key, ctx->t_slot);
+    ctx->launches++;
+    // no neighbour messages belong to an upload: skip the unpack kernel
+    if ((rc = launch_sort(ctx, 1, false))) return rc;
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->stage = ST_READY;
+    return SPH_OK;
+}
+
+static int read_counters(sph_ctx *ctx, int *c)
+{
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaMemcpy(c, ctx->counters, CN_COUNT * sizeof(int), cudaMemcpyDeviceToHost));
+    return SPH_OK;
+}
+
+// which sorted arrays hold the resident state at this stage
+static int current_arrays(sph_ctx *ctx, float2 **pos, float2 **q, uint32_t **uid, bool *q_is_prev)
+{
+    if (ctx->stage == ST_READY) { *pos = ctx->P[0]; *q = ctx->Q[0]; *uid = ctx->U[0]; *q_is_prev = false; return SPH_OK; }
+    if (ctx->stage == ST_SORTED1 || ctx->stage == ST_DENSITY) { *pos = ctx->P[2]; *q = ctx->Q[1]; *uid = ctx->U[1]; *q_is_prev = true; return SPH_OK; }
+    return fail(ctx, SPH_ERR_STATE, "state is between a producing kernel and its sort: call sph_sort first");
+}
+
+extern "C" int sph_download(sph_ctx *ctx, sph_particle *aos, uint32_t *uid_out, int order, int include_halo)
+{
+    if (!ctx || !aos) return -SPH_ERR_ARG;
+    int c[CN_COUNT];
+    if (read_counters(ctx, c)) return -SPH_ERR_CUDA;
+    float2 *dpos, *dq; uint32_t *duid; bool q_is_prev;
+    if (current_arrays(ctx, &dpos, &dq, &duid, &q_is_prev)) return -SPH_ERR_STATE;
+    const int n = c[CN_NTOT];
+    std::vector<float2> p(n), q(n), d(n);
+    std::vector<uint32_t> u(n);
+    auto cp = [&](void *dst, const void *src, size_t bytes) { return cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost); };
+    if (n > 0) {
+        if (cp(p.data(), dpos, n * sizeof(float2)) || cp(q.data(), dq, n * sizeof(float2)) ||
+            cp(u.data(), duid, n * sizeof(uint32_t))) { fail(ctx, SPH_ERR_CUDA, "download copy failed"); return -SPH_ERR_CUDA; }
+        if (ctx->stage == ST_DENSITY && cp(d.data(), ctx->dens, n * sizeof(float2))) { fail(ctx, SPH_ERR_CUDA, "download copy failed"); return -SPH_ERR_CUDA; }
+    }
+    std::vector<int> idx;
+    idx.reserve(n);
+    for (int i = 0; i < n; i++) if (include_halo || !(u[i] & SPH_HALO_BIT)) idx.push_back(i);
+    if (order == SPH_ORDER_UID)
+        std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) { return (u[a] & SPH_UID_MASK) < (u[b] & SPH_UID_MASK); });
+    for (size_t k = 0; k < idx.size(); k++) {
+        const int i = idx[k];
+        sph_particle &o = aos[k];
+        memset(&o, 0, sizeof o);
+        o.x = p[i].x; o.y = p[i].y;
+        if (q_is_prev) { o.x_prev = q[i].x; o.y_prev = q[i].y; }
+        else { o.x_prev = p[i].x; o.y_prev = p[i].y; o.v_x = q[i].x; o.v_y = q[i].y; }
+        if (ctx->stage == ST_DENSITY) {
+            o.density = d[i].x; o.density_near = d[i].y;
+            o.pressure = ctx->tun.k * (d[i].x - ctx->tun.rest_density);     // fluid.c:563-564
+            o.pressure_near = ctx->tun.k_near * d[i].y;
+        }
+        o.id = (int)k;
+        if (uid_out) uid_out[k] = u[i];
+    }
+    return (int)idx.size();
+}
+
+extern "C" int sph_get_status(sph_ctx *ctx, sph_status *out)
+{
+    if (!ctx || !out) return SPH_ERR_ARG;
+    int c[CN_COUNT];
+    int rc = read_counters(ctx, c);
+    if (rc) return rc;
+    memset(out, 0, sizeof *out);
+    out->n_local = c[CN_NLOCAL];
+    out->n_halo = c[CN_NTOT] - c[CN_NLOCAL];
+    out->max_bucket = c[CN_MAX_BUCKET];
+    out->bucket_overflow = c[CN_BUCKET_OVER];
+    out->neighbor_overflow = c[CN_NEIGH_OVER];
+    out->capacity_overflow = c[CN_CAP_OVER];
+    out->msg_overflow = c[CN_MSG_OVER];
+    if (ctx->cfg.nranks > 1) {
+        int hl[2] = {0, 0}, hr[2] = {0, 0};
+        CK(cudaMemcpy(hl, ctx->send[0], sizeof hl, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(hr, ctx->send[1], sizeof hr, cudaMemcpyDeviceToHost));
+        out->migrated_left = hl[0]; out->migrated_right = hr[0];
+    }
+    out->steps = ctx->steps;
+    return SPH_OK;
+}
+
+extern "C" int sph_pack_coords(sph_ctx *ctx, int16_t *xy, int cap)
+{
+    if (!ctx || !xy) return -SPH_ERR_ARG;
+    float2 *dpos, *dq; uint32_t *duid; bool q_is_prev;
+    if (current_arrays(ctx, &dpos, &dq, &duid, &q_is_prev)) return -SPH_ERR_STATE;
+    auto bail = [&](cudaError_t e) { snprintf(ctx->err, sizeof ctx->err, "pack_coords: %s", cudaGetErrorString(e)); return -SPH_ERR_CUDA; };
+    cudaError_t e;
+    if ((e = cudaMemsetAsync(ctx->counters + CN_COORDS, 0, sizeof(int), ctx->stream))) return bail(e);
+    k_pack_coords<<<ctx->grid, SPH_THREADS, 0, ctx->stream>>>(ctx->dp, ctx->counters, dpos, duid, ctx->coords, ctx->cfg.capacity);
+    ctx->launches++;
+    int c[CN_COUNT];
+    if ((e = cudaMemcpyAsync(c, ctx->counters, sizeof c, cudaMemcpyDeviceToHost, ctx->stream))) return bail(e);
+    if ((e = cudaStreamSynchronize(ctx->stream))) return bail(e);
+    const int n = c[CN_NLOCAL];
+    const int m = std::min(n, cap);
+    if (m > 0) {
+        if ((e = cudaMemcpyAsync(xy, ctx->coords, (size_t)m * sizeof(short2), cudaMemcpyDeviceToHost, ctx->stream))) return bail(e);
+        if ((e = cudaStreamSynchronize(ctx->stream))) return bail(e);
+    }
+    return n;
+}
+
+extern "C" int sph_run_frame(sph_ctx *ctx, const sph_tunable *t, int steps, int16_t *xy, int cap)
+{
+    if (!ctx || steps < 1) return -SPH_ERR_ARG;
+    int rc;
+    if ((rc = sph_step(ctx, steps - 1))) return -rc;
+    if (t && (rc = sph_queue_params(ctx, t))) return -rc;
+    if ((rc = sph_step(ctx, 1))) return -rc;
+    if (xy) return sph_pack_coords(ctx, xy, cap);
+    int c[CN_COUNT];
+    if ((rc = read_counters(ctx, c))) return -rc;
+    return c[CN_NLOCAL];
+}
+
+extern "C" int sph_get_cells(sph_ctx *ctx, uint32_t *uid, uint32_t *cell, int cap)
+{
+    if (!ctx || !uid || !cell) return -SPH_ERR_ARG;
+    float2 *dpos, *dq; uint32_t *duid; bool q_is_prev;
+    if (current_arrays(ctx, &dpos, &dq, &duid, &q_is_prev)) return -SPH_ERR_STATE;
+    int c[CN_COUNT];
+    if (read_counters(ctx, c)) return -SPH_ERR_CUDA;
+    const int n = c[CN_NTOT];
+    uint32_t *dcell = (uint32_t *)ctx->ord_uid;      // scratch: free between sorts
+    k_export_cells<<<ctx->grid, SPH_THREADS, 0, ctx->stream>>>(ctx->dp, ctx->counters, dpos, dcell);
+    ctx->launches++;
+    std::vector<uint32_t> hu(n), hc(n);
+    if (n > 0) {
+        if (cudaMemcpyAsync(hc.data(), dcell, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream) ||
+            cudaMemcpyAsync(hu.data(), duid, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream) ||
+            cudaStreamSynchronize(ctx->stream)) { fail(ctx, SPH_ERR_CUDA, "get_cells copy failed"); return -SPH_ERR_CUDA; }
+    }
+    int m = 0;
+    for (int i = 0; i < n; i++) {
+        if (hu[i] & SPH_HALO_BIT) continue;
+        if (m < cap) { uid[m] = hu[i]; cell[m] = hc[i]; }
+        m++;
+    }
+    return m;
+}
+
+static long long export_pairs(sph_ctx *ctx, uint64_t *pairs, long long cap, uint32_t *uid, int *count, int count_cap)
+{
+    float2 *dpos, *dq; uint32_t *duid; bool q_is_prev;
+    if (current_arrays(ctx, &dpos, &dq, &duid, &q_is_prev)) return -SPH_ERR_STATE;
+    int c[CN_COUNT];
+    if (read_counters(ctx, c)) return -SPH_ERR_CUDA;
+    const int n = c[CN_NTOT];
+    unsigned long long *dpairs = nullptr, *dn = nullptr;
+    int *dfwd = nullptr;
+    long long result = -SPH_ERR_CUDA;
+    unsigned long long np = 0;
+    do {
+        if (cudaMalloc(&dn, sizeof(unsigned long long)) || cudaMemset(dn, 0, sizeof(unsigned long long))) break;
+        if (pairs && cap > 0 && cudaMalloc(&dpairs, (size_t)cap * sizeof(unsigned long long))) break;
+        if (count && cudaMalloc(&dfwd, (size_t)std::max(n, 1) * sizeof(int))) break;
+        // count-only calls still need a non-null marker so the kernel counts pairs
+        unsigned long long *pairs_arg = (pairs || !count) ? (dpairs ? dpairs : (unsigned long long *)dn) : nullptr;
+        k_export_pairs<<<ctx->grid, SPH_THREADS, 0, ctx->stream>>>(ctx->dp, ctx->counters, dpos, duid, ctx->cell_start,
+                                                                   pairs_arg, dpairs ? (unsigned long long)cap : 0ull, dn, dfwd);
+        ctx->launches++;
+        if (cudaStreamSynchronize(ctx->stream)) break;
+        if (cudaMemcpy(&np, dn, sizeof np, cudaMemcpyDeviceToHost)) break;
+        if (dpairs && cudaMemcpy(pairs, dpairs, (size_t)std::min<unsigned long long>(np, (unsigned long long)cap) * sizeof(uint64_t), cudaMemcpyDeviceToHost)) break;
+        if (count) {
+            std::vector<int> hf(n);
+            std::vector<uint32_t> hu(n);
+            if (n > 0 && (cudaMemcpy(hf.data(), dfwd, n * sizeof(int), cudaMemcpyDeviceToHost) ||
+                          cudaMemcpy(hu.data(), duid, n * sizeof(uint32_t), cudaMemcpyDeviceToHost))) break;
+            int m = 0;
+            for (int i = 0; i < n; i++) {
+                if (hu[i] & SPH_HALO_BIT) continue;
+                if (m < count_cap) { uid[m] = hu[i]; count[m] = hf[i]; }
+                m++;
+            }
+            result = m;
+        } else {
+            result = (long long)np;
+        }
+    } while (0);
+    if (result < 0) fail(ctx, SPH_ERR_CUDA, "export_pairs: CUDA failure");
+    cudaFree(dpairs); cudaFree(dn); cudaFree(dfwd);
+    return result;
+}
+
+extern "C" long long sph_get_pairs(sph_ctx *ctx, uint64_t *pairs, long long cap)
+{
+    if (!ctx) return -SPH_ERR_ARG;
+    return export_pairs(ctx, pairs, pairs ? cap : 0, nullptr, nullptr, 0);
+}
+
+extern "C" int sph_get_forward_counts(sph_ctx *ctx, uint32_t *uid, int *count, int cap)
+{
+    if (!ctx || !uid || !count) return -SPH_ERR_ARG;
+    return (int)export_pairs(ctx, nullptr, 0, uid, count, cap);
+}

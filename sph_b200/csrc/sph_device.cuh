@@ -1,0 +1,103 @@
+// Device-side definitions shared by the kernels and the C-ABI layer.
+// sm_100a only.  Citations are to AdamSimpson/SPH `src/`.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define SPH_HALO_BIT 0x80000000u
+#define SPH_UID_MASK 0x7fffffffu
+#define SPH_KEY_DROP (-1)
+#define SPH_KEY_EMIG (1 << 30)            // entry stays resident but becomes a ghost of its new owner
+#define SPH_KEY_MASK (SPH_KEY_EMIG - 1)
+
+// Everything a kernel needs to know, resident in device memory so that a captured CUDA
+// graph keeps working when the render rank changes parameters (fluid.c:293-294).
+struct DevParams {
+    // physics: struct TUNABLE_PARAMETERS (fluid.h:78-97)
+    float rest_density, h, g, k, k_near, k_spring, sigma, beta, dt;
+    float mover_cx, mover_cy, mover_w, mover_h;
+    int mover_type;
+    // tank (AABB min is 0: fluid.c:117) and hash grid (fluid.c:176,214-215)
+    float tank_w, tank_h, cell_h;
+    int size_x, size_y;
+    // slab (communication.c): edges, ghost-layer width, neighbours present
+    float edge_start, edge_end, halo_w;
+    int has_left, has_right, nranks;
+    // window of grid columns the sorted arrays cover now / will cover after the next sort
+    int gx0, wx;
+    int gx0_new, wx_new;
+    int cap, msg_cap;
+};
+
+// device-side counters (ints); indices below
+enum {
+    CN_NTOT = 0,        // resident entries in the sorted arrays
+    CN_EXTRA,           // entries appended by the unpack kernel for the coming sort
+    CN_NSRC,            // entries the scatter kernel must visit (written by the scan)
+    CN_NLOCAL,          // non-ghost entries after the last sort (accumulated by reorder)
+    CN_MAX_BUCKET, CN_BUCKET_OVER, CN_NEIGH_OVER, CN_CAP_OVER, CN_MSG_OVER,
+    CN_TICKET, CN_DONE, // scan bookkeeping
+    CN_COORDS,          // pack_coords compaction cursor
+    CN_EPOCH,           // scan epoch (so tile flags never need clearing)
+    CN_COUNT = 16
+};
+
+// neighbour message: 16-byte header {n_migrants, n_halo, 0, 0} then SoA sections sized by msg_cap
+__host__ __device__ inline size_t msg_bytes_full(int m) { return 16 + (size_t)m * 32; }
+__host__ __device__ inline size_t msg_bytes_halo1(int m) { return 16 + (size_t)m * 20; }
+__device__ __forceinline__ int *msg_hdr(unsigned char *b) { return (int *)b; }
+__device__ __forceinline__ float2 *msg_a(unsigned char *b) { return (float2 *)(b + 16); }                       // migrant pos / halo-1 pos
+__device__ __forceinline__ float2 *msg_b(unsigned char *b, int m) { return (float2 *)(b + 16 + (size_t)m * 8); } // migrant prev / halo-1 vel
+__device__ __forceinline__ uint32_t *msg_u(unsigned char *b, int m) { return (uint32_t *)(b + 16 + (size_t)m * 16); }
+__device__ __forceinline__ float2 *msg_hp(unsigned char *b, int m) { return (float2 *)(b + 16 + (size_t)m * 20); } // halo-0 pos
+__device__ __forceinline__ uint32_t *msg_hu(unsigned char *b, int m) { return (uint32_t *)(b + 16 + (size_t)m * 28); }
+
+// hash_val (hash.c:35-47): IEEE fp32 divide, floor; kept as two coordinates
+__device__ __forceinline__ int cell_coord(float v, float cell_h) { return (int)floorf(__fdiv_rn(v, cell_h)); }
+
+// unfused squared distance: the list cut-off r2 <= h2 must match hash.c:185,221,99 bit for bit
+__device__ __forceinline__ float dist2(float dx, float dy) { return __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)); }
+
+// checkVelocity (fluid.c:613-625)
+__device__ __forceinline__ float clamp5(float v) { return v > 5.0f ? 5.0f : (v < -5.0f ? -5.0f : v); }
+
+// boundaryConditions (fluid.c:656-744)
+__device__ __forceinline__ float2 boundary(float2 p, const DevParams &P)
+{
+    float x = p.x, y = p.y;
+    if (P.mover_type == 0) {                                        // sphere: :663-685
+        float radius = P.mover_w * 0.5f;
+        float ddx = x - P.mover_cx, ddy = y - P.mover_cy;
+        float d2 = dist2(ddx, ddy);
+        if (d2 <= __fmul_rn(radius, radius) && d2 > 0.0f) {
+            float d = __fsqrt_rn(d2);
+            float nx = __fdiv_rn(P.mover_cx - x, d);
+            float ny = __fdiv_rn(P.mover_cy - y, d);
+            float pen = radius - d;
+            x = __fsub_rn(x, __fmul_rn(pen, nx));
+            y = __fsub_rn(y, __fmul_rn(pen, ny));
+        }
+    } else if (P.mover_type == 1) {                                 // rectangle: :688-727
+        float hw = P.mover_w * 0.5f, hh = P.mover_h * 0.5f;
+        float rx = x - P.mover_cx, ry = y - P.mover_cy;
+        float ax = fabsf(rx), ay = fabsf(ry);
+        if (ax < hw && ay < hh) {
+            float penx = hw - ax, peny = hh - ay;
+            if (penx < peny) { if (rx < 0.0f) x -= penx; else x += penx; }
+            else             { if (ry < 0.0f) y -= peny; else y += peny; }
+        }
+    }
+    if (x < 0.0f) x = 0.0f; else if (x > P.tank_w) x = P.tank_w - 0.001f;   // :732-743
+    if (y < 0.0f) y = 0.0f; else if (y > P.tank_h) y = P.tank_h - 0.001f;
+    return make_float2(x, y);
+}
+
+// key of a position in the NEW window (the one the coming sort will use), or DROP
+__device__ __forceinline__ int window_key_new(float2 p, const DevParams &P)
+{
+    int gx = cell_coord(p.x, P.cell_h) - P.gx0_new;
+    int gy = cell_coord(p.y, P.cell_h);
+    if (gx < 0 || gx >= P.wx_new || gy < 0 || gy >= P.size_y) return SPH_KEY_DROP;
+    return gy * P.wx_new + gx;
+}

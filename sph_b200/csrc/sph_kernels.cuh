@@ -1,0 +1,596 @@
+// Kernels of the B200-native TinySPH compute-rank timestep (sm_100a).
+//
+// State is cell-sorted SoA (float2 position, float2 velocity-or-previous-position, u32 uid with
+// a ghost flag).  Cells are the reference's hash cells (hash.c:35-47) numbered row-major inside
+// the slab's window of grid columns, so the 3x3 neighbourhood of a particle is THREE CONTIGUOUS
+// INDEX RANGES (rows gy-1, gy, gy+1; columns gx-1..gx+1 are adjacent in memory).
+//
+// The reference's symmetric pair scatter (fluid.c:461-471, :598-607) is a gather here: every
+// particle sums the contributions of all particles within h, in a fixed order (row, then sorted
+// index == ascending uid inside a cell), so there are no atomics on the pair loops and results
+// are bit-reproducible and independent of the slab decomposition.
+#pragma once
+
+#include "sph_device.cuh"
+
+#define SPH_THREADS 256
+
+// -------------------------------------------------------------------------------------------
+// neighbourhood iteration: rows gy-1..gy+1, columns gx-1..gx+1 of the CURRENT window
+// -------------------------------------------------------------------------------------------
+struct Rows { int b[3], e[3]; };
+
+__device__ __forceinline__ Rows candidate_rows(float2 p, const DevParams &P, const int *__restrict__ cell_start)
+{
+    Rows r;
+    int gx = cell_coord(p.x, P.cell_h) - P.gx0;
+    int gy = cell_coord(p.y, P.cell_h);
+    gx = min(max(gx, 0), P.wx - 1);
+    gy = min(max(gy, 0), P.size_y - 1);
+    int c0 = max(gx - 1, 0), c1 = min(gx + 1, P.wx - 1);
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+        int row = gy + d - 1;
+        if (row < 0 || row >= P.size_y) { r.b[d] = 0; r.e[d] = 0; continue; }
+        r.b[d] = __ldg(&cell_start[row * P.wx + c0]);
+        r.e[d] = __ldg(&cell_start[row * P.wx + c1 + 1]);
+    }
+    return r;
+}
+
+// bin a freshly produced position for the coming sort: key, arrival slot, cell population
+__device__ __forceinline__ void bin_position(int i, float2 p, int extra_bits, const DevParams &P,
+                                             int *__restrict__ cnt, int *__restrict__ t_key,
+                                             int *__restrict__ t_slot, int *__restrict__ counters)
+{
+    int key = window_key_new(p, P);
+    if (key == SPH_KEY_DROP) {                 // left the window: cannot happen with a sane ghost width
+        atomicAdd(&counters[CN_CAP_OVER], 1);
+        t_key[i] = SPH_KEY_DROP;
+        return;
+    }
+    t_slot[i] = atomicAdd(&cnt[key], 1);
+    t_key[i] = key | extra_bits;
+}
+
+// -------------------------------------------------------------------------------------------
+// K1  apply_gravity (fluid.c:398) + viscosity_impluses (:416) + predict_positions (:507)
+//     + boundaryConditions (:656) + identify_oob_particles (:481) + ghost selection
+//     (communication.c:134-141) + first half of hash_fluid pass 1 (hash.c:153-166)
+// -------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(SPH_THREADS)
+k_advect(const DevParams *__restrict__ Pp, int *__restrict__ counters,
+         const float2 *__restrict__ pos, const float2 *__restrict__ vel, const uint32_t *__restrict__ uid,
+         const int *__restrict__ cell_start,
+         float2 *__restrict__ pos_pred, int *__restrict__ cnt, int *__restrict__ t_key, int *__restrict__ t_slot,
+         unsigned char *send_l, unsigned char *send_r)
+{
+    const DevParams P = *Pp;
+    const int n = counters[CN_NTOT];
+    const float dt = P.dt;
+    const float gdt = (-P.g) * dt;
+    const float h_recip = __fdiv_rn(1.0f, P.h);
+    const float h2 = __fmul_rn(P.h, P.h);
+    if (blockIdx.x == 0 && threadIdx.x == 0) counters[CN_MAX_BUCKET] = 0;
+
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t u = uid[i];
+        if (u & SPH_HALO_BIT) { t_key[i] = SPH_KEY_DROP; continue; }   // ghosts are replaced every exchange
+        const float2 p = pos[i];
+        const float2 v0 = vel[i];
+        const float vix = v0.x, viy = v0.y + gdt;                      // apply_gravity
+        float vx = vix, vy = viy;
+        const Rows R = candidate_rows(p, P, cell_start);
+#pragma unroll
+        for (int d = 0; d < 3; d++) {
+            for (int j = R.b[d]; j < R.e[d]; j++) {
+                const float2 q = pos[j];
+                const float dx = q.x - p.x, dy = q.y - p.y;
+                const float r2 = dist2(dx, dy);
+                if (r2 > h2 || j == i) continue;                        // list membership
+                const float2 vq = vel[j];
+                const float r = __fsqrt_rn(r2);
+                const float r_recip = __fdiv_rn(1.0f, r);
+                const float ratio = r * h_recip;
+                const float u_in = ((vix - vq.x) * dx + (viy - (vq.y + gdt)) * dy) * r_recip;
+                if (u_in > 0.0f) {                                      // fluid.c:451-462 (r == 0 gives NaN: skipped)
+                    const float imp = dt * (1.0f - ratio) * (P.sigma * u_in + P.beta * u_in * u_in);
+                    const float ix = clamp5(imp * dx * r_recip);
+                    const float iy = clamp5(imp * dy * r_recip);
+                    vx -= ix * 0.5f;
+                    vy -= iy * 0.5f;
+                }
+            }
+        }
+        float2 np = make_float2(p.x + vx * dt, p.y + vy * dt);          // fluid.c:517-518
+        np = boundary(np, P);
+        pos_pred[i] = np;
+
+        int extra = 0;
+        if (P.nranks > 1) {
+            // identify_oob_particles: strict < start / > end (fluid.c:494-497)
+            unsigned char *dst = nullptr;
+            if (np.x < P.edge_start && P.has_left) dst = send_l;
+            else if (np.x > P.edge_end && P.has_right) dst = send_r;
+            if (dst) {
+                int k = atomicAdd(&msg_hdr(dst)[0], 1);
+                if (k < P.msg_cap) {
+                    msg_a(dst)[k] = np;
+                    msg_b(dst, P.msg_cap)[k] = p;                       // x_prev travels with the migrant
+                    msg_u(dst, P.msg_cap)[k] = u;
+                    extra = SPH_KEY_EMIG;
+                } else {
+                    atomicAdd(&counters[CN_MSG_OVER], 1);
+                }
+            } else {
+                // ghost layer: widened to halo_w and tested per side (communication.c:137-140 uses h, else-if)
+                if (P.has_left && np.x - P.edge_start <= P.halo_w) {
+                    int k = atomicAdd(&msg_hdr(send_l)[1], 1);
+                    if (k < P.msg_cap) { msg_hp(send_l, P.msg_cap)[k] = np; msg_hu(send_l, P.msg_cap)[k] = u; }
+                    else atomicAdd(&counters[CN_MSG_OVER], 1);
+                }
+                if (P.has_right && P.edge_end - np.x <= P.halo_w) {
+                    int k = atomicAdd(&msg_hdr(send_r)[1], 1);
+                    if (k < P.msg_cap) { msg_hp(send_r, P.msg_cap)[k] = np; msg_hu(send_r, P.msg_cap)[k] = u; }
+                    else atomicAdd(&counters[CN_MSG_OVER], 1);
+                }
+            }
+        }
+        bin_position(i, np, extra, P, cnt, t_key, t_slot, counters);
+    }
+}
+
+// -------------------------------------------------------------------------------------------
+// K2  unpack neighbour messages into the source arrays and bin them (hash_halo, hash.c:51;
+//     the receive side of transferOOBParticles, communication.c:340-358).  Slab mode only.
+//     which == 0: migrants (pos, prev) become locals, ghosts carry a position only.
+//     which == 1: ghosts carry position + velocity.
+// -------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(SPH_THREADS)
+k_unpack(const DevParams *__restrict__ Pp, int *__restrict__ counters, int which,
+         unsigned char *recv_l, unsigned char *recv_r,
+         float2 *__restrict__ src_pos, float2 *__restrict__ src_q, uint32_t *__restrict__ src_uid,
+         int *__restrict__ cnt, int *__restrict__ t_key, int *__restrict__ t_slot)
+{
+    const DevParams P = *Pp;
+    const int base = counters[CN_NTOT];
+    int n_mig[2] = {0, 0}, n_halo[2] = {0, 0};
+    unsigned char *buf[2] = {recv_l, recv_r};
+    const int present[2] = {P.has_left, P.has_right};
+    for (int s = 0; s < 2; s++) {
+        if (!present[s]) continue;
+        n_mig[s] = which == 0 ? min(msg_hdr(buf[s])[0], P.msg_cap) : 0;
+        n_halo[s] = min(msg_hdr(buf[s])[1], P.msg_cap);
+    }
+    const int total = n_mig[0] + n_halo[0] + n_mig[1] + n_halo[1];
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        int fit = min(total, max(P.cap - base, 0));
+        counters[CN_EXTRA] = fit;
+        if (fit < total) atomicAdd(&counters[CN_CAP_OVER], total - fit);
+    }
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+        const int idx = base + t;
+        if (idx >= P.cap) break;
+        int k = t, s = 0, is_mig = 0;
+        if (k < n_mig[0]) { s = 0; is_mig = 1; }
+        else if ((k -= n_mig[0]) < n_halo[0]) { s = 0; }
+        else if ((k -= n_halo[0]) < n_mig[1]) { s = 1; is_mig = 1; }
+        else { k -= n_mig[1]; s = 1; }
+        float2 p, q;
+        uint32_t u;
+        if (which == 0 && !is_mig) {
+            p = msg_hp(buf[s], P.msg_cap)[k];
+            q = make_float2(0.0f, 0.0f);
+            u = msg_hu(buf[s], P.msg_cap)[k] | SPH_HALO_BIT;
+        } else {
+            p = msg_a(buf[s])[k];
+            q = msg_b(buf[s], P.msg_cap)[k];
+            u = msg_u(buf[s], P.msg_cap)[k];
+            u = is_mig ? (u & SPH_UID_MASK) : (u | SPH_HALO_BIT);
+        }
+        src_pos[idx] = p;
+        src_q[idx] = q;
+        src_uid[idx] = u;
+        bin_position(idx, p, 0, P, cnt, t_key, t_slot, counters);
+    }
+}
+
+// -------------------------------------------------------------------------------------------
+// K3  exclusive prefix sum of the cell populations -> cell_start (single pass, decoupled
+//     look-back, warp-shuffle scans).  Also clears the populations for the next sort, records
+//     the largest bucket (the reference silently drops above 100: hash.c:160-165) and
+//     publishes the new entry counts.
+// -------------------------------------------------------------------------------------------
+#define SCAN_ITEMS 8
+#define SCAN_TILE (SPH_THREADS * SCAN_ITEMS)
+
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_u64(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+__global__ void __launch_bounds__(SPH_THREADS)
+k_scan(DevParams *__restrict__ Pp, int *__restrict__ counters, int *__restrict__ cnt, int *__restrict__ cell_start,
+       unsigned long long *__restrict__ tile_state, unsigned char *send_l, unsigned char *send_r)
+{
+    __shared__ int s_tile;
+    __shared__ int s_warp[SPH_THREADS / 32];
+    __shared__ int s_prefix;
+    const int ncell = Pp->wx_new * Pp->size_y;
+    const int ntiles = (ncell + SCAN_TILE - 1) / SCAN_TILE;
+    const unsigned epoch = (unsigned)counters[CN_EPOCH];
+    if (threadIdx.x == 0) s_tile = atomicAdd(&counters[CN_TICKET], 1);
+    __syncthreads();
+    const int tile = s_tile;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int base = tile * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+
+    int v[SCAN_ITEMS];
+    int sum = 0, mx = 0, over = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) {
+        int idx = base + k;
+        v[k] = idx < ncell ? cnt[idx] : 0;
+        if (idx < ncell) cnt[idx] = 0;
+        sum += v[k];
+        mx = max(mx, v[k]);
+        over += v[k] > 100;
+    }
+    // warp inclusive scan of the thread sums
+    int inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, 16)); over += __shfl_xor_sync(0xffffffffu, over, 16);
+    mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, 8));  over += __shfl_xor_sync(0xffffffffu, over, 8);
+    mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, 4));  over += __shfl_xor_sync(0xffffffffu, over, 4);
+    mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, 2));  over += __shfl_xor_sync(0xffffffffu, over, 2);
+    mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, 1));  over += __shfl_xor_sync(0xffffffffu, over, 1);
+    if (lane == 31) s_warp[warp] = inc;
+    if (lane == 0) {
+        if (mx > 0) atomicMax(&counters[CN_MAX_BUCKET], mx);
+        if (over > 0) atomicAdd(&counters[CN_BUCKET_OVER], over);
+    }
+    __syncthreads();
+    int warp_off = 0, block_total = 0;
+#pragma unroll
+    for (int w = 0; w < SPH_THREADS / 32; w++) {
+        int s = s_warp[w];
+        if (w < warp) warp_off += s;
+        block_total += s;
+    }
+    // publish this tile, look back for the exclusive prefix (one warp)
+    if (warp == 0) {
+        const unsigned long long tag = (unsigned long long)epoch << 34;
+        if (lane == 0) {
+            unsigned long long st = tag | ((unsigned long long)(tile == 0 ? 2 : 1) << 32) | (unsigned)block_total;
+            st_release_u64(&tile_state[tile], st);
+        }
+        int prefix = 0;
+        int look = tile - 1;
+        while (look >= 0) {
+            int idx = look - lane;
+            unsigned long long st = 0;
+            int status = 0;
+            if (idx >= 0) {
+                do {
+                    st = ld_acquire_u64(&tile_state[idx]);
+                    status = ((st >> 34) == epoch) ? (int)((st >> 32) & 3) : 0;
+                } while (status == 0);
+            } else {
+                status = 2;      // before tile 0: an inclusive prefix of zero
+            }
+            unsigned incl_mask = __ballot_sync(0xffffffffu, status == 2);
+            // nearest predecessor with an inclusive value; none in this window -> take all 32 aggregates
+            int last = incl_mask ? __ffs(incl_mask) - 1 : 31;
+            int val = (idx >= 0 && lane <= last) ? (int)(unsigned)st : 0;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) val += __shfl_xor_sync(0xffffffffu, val, o);
+            prefix += val;
+            if (incl_mask) break;
+            look -= 32;
+        }
+        if (lane == 0) {
+            s_prefix = prefix;
+            if (tile != 0) {
+                unsigned long long st = tag | (2ull << 32) | (unsigned)(prefix + block_total);
+                st_release_u64(&tile_state[tile], st);
+            }
+        }
+    }
+    __syncthreads();
+    int run = s_prefix + warp_off + (inc - sum);
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) {
+        int idx = base + k;
+        if (idx < ncell) cell_start[idx] = run;
+        run += v[k];
+    }
+    if (tile == ntiles - 1 && threadIdx.x == SPH_THREADS - 1) {
+        const int total = s_prefix + block_total;
+        cell_start[ncell] = total;
+        counters[CN_NSRC] = counters[CN_NTOT] + counters[CN_EXTRA];
+        counters[CN_EXTRA] = 0;
+        counters[CN_NTOT] = total;
+        counters[CN_NLOCAL] = 0;
+        // the sorted arrays are about to be rebuilt for the new window
+        Pp->gx0 = Pp->gx0_new;
+        Pp->wx = Pp->wx_new;
+        // send buffers are free again: the messages they held were consumed before this sort
+        if (send_l) { msg_hdr(send_l)[0] = 0; msg_hdr(send_l)[1] = 0; }
+        if (send_r) { msg_hdr(send_r)[0] = 0; msg_hdr(send_r)[1] = 0; }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(&counters[CN_DONE], 1) == ntiles - 1) {   // last tile out resets the bookkeeping
+            counters[CN_TICKET] = 0;
+            counters[CN_DONE] = 0;
+            counters[CN_EPOCH] = (int)((epoch + 1) & 0x3fffffffu);
+        }
+    }
+}
+
+// -------------------------------------------------------------------------------------------
+// K4  scatter (uid, source index) to cell_start[key] + arrival slot.  Arrival order inside a
+//     cell is whatever the atomics produced; K5 makes it canonical.
+// -------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(SPH_THREADS)
+k_scatter(const int *__restrict__ counters, const int *__restrict__ cell_start,
+          const int *__restrict__ t_key, const int *__restrict__ t_slot, const uint32_t *__restrict__ src_uid,
+          uint32_t *__restrict__ ord_uid, int *__restrict__ ord_src)
+{
+    const int n = counters[CN_NSRC];
+    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) {
+        const int key = t_key[s];
+        if (key == SPH_KEY_DROP) continue;
+        const int d = cell_start[key & SPH_KEY_MASK] + t_slot[s];
+        uint32_t u = src_uid[s];
+        if (key & SPH_KEY_EMIG) u |= SPH_HALO_BIT;
+        ord_uid[d] = u;
+        ord_src[d] = s;
+    }
+}
+
+// -------------------------------------------------------------------------------------------
+// K5  canonical order inside each cell (ascending uid == the reference's bucket order on one
+//     rank, hash.c:160-163 inserts in pointer order) and the physical reorder of the payload.
+// -------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(SPH_THREADS)
+k_reorder(const DevParams *__restrict__ Pp, int *__restrict__ counters, const int *__restrict__ cell_start,
+          const int *__restrict__ t_key, const uint32_t *__restrict__ ord_uid, const int *__restrict__ ord_src,
+          const float2 *__restrict__ src_pos, const float2 *__restrict__ src_q,
+          float2 *__restrict__ dst_pos, float2 *__restrict__ dst_q, uint32_t *__restrict__ dst_uid)
+{
+    const int n = counters[CN_NTOT];
+    int locals = 0;
+    for (int d = blockIdx.x * blockDim.x + threadIdx.x; d < n; d += gridDim.x * blockDim.x) {
+        const int s = ord_src[d];
+        const uint32_t u = ord_uid[d];
+        const int key = t_key[s] & SPH_KEY_MASK;
+        const int b = cell_start[key], e = cell_start[key + 1];
+        const uint32_t um = u & SPH_UID_MASK;
+        int rank = 0;
+        for (int k = b; k < e; k++) rank += (ord_uid[k] & SPH_UID_MASK) < um;
+        const int dst = b + rank;
+        dst_pos[dst] = src_pos[s];
+        dst_q[dst] = src_q[s];
+        dst_uid[dst] = u;
+        locals += !(u & SPH_HALO_BIT);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) locals += __shfl_xor_sync(0xffffffffu, locals, o);
+    if ((threadIdx.x & 31) == 0 && locals) atomicAdd(&counters[CN_NLOCAL], locals);
+}
+
+// -------------------------------------------------------------------------------------------
+// K6  calculate_density (fluid.c:527-539) over every pair within h, as a gather.
+//     Output: (density, density_near) per resident entry, ghosts included (their pressure is
+//     needed by the relaxation of the locals next to them, fluid.c:560-565).
+// -------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(SPH_THREADS)
+k_density(const DevParams *__restrict__ Pp, int *__restrict__ counters,
+          const float2 *__restrict__ pos, const int *__restrict__ cell_start, float2 *__restrict__ dens)
+{
+    const DevParams P = *Pp;
+    const int n = counters[CN_NTOT];
+    const float h_recip = __fdiv_rn(1.0f, P.h);
+    const float h2 = __fmul_rn(P.h, P.h);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float2 p = pos[i];
+        float d = 0.0f, dn = 0.0f;
+        int nn = 0;
+        const Rows R = candidate_rows(p, P, cell_start);
+#pragma unroll
+        for (int dd = 0; dd < 3; dd++) {
+            for (int j = R.b[dd]; j < R.e[dd]; j++) {
+                const float2 q = pos[j];
+                const float dx = q.x - p.x, dy = q.y - p.y;
+                const float r2 = dist2(dx, dy);
+                if (r2 > h2 || j == i) continue;
+                nn++;
+                const float ratio = __fsqrt_rn(r2) * h_recip;
+                if (ratio < 1.0f) {
+                    const float omr = 1.0f - ratio;
+                    const float omr2 = omr * omr;
+                    d += omr2;
+                    dn += omr2 * omr;
+                }
+            }
+        }
+        dens[i] = make_float2(d, dn);
+        // a forward list cannot exceed the full neighbour count: cheap, conservative detection
+        // of the reference's 400-entry cap (hash.c:188,223)
+        if (nn > 400) atomicAdd(&counters[CN_NEIGH_OVER], 1);
+    }
+}
+
+// -------------------------------------------------------------------------------------------
+// K7  double_density_relaxation (fluid.c:541-611) as a gather + updateVelocities (:642-653)
+//     incl. boundaryConditions + second ghost selection (fluid.c:337) + binning for the re-hash
+//     (fluid.c:341).
+// -------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(SPH_THREADS)
+k_relax(const DevParams *__restrict__ Pp, int *__restrict__ counters,
+        const float2 *__restrict__ pos, const float2 *__restrict__ prev, const uint32_t *__restrict__ uid,
+        const float2 *__restrict__ dens, const int *__restrict__ cell_start,
+        float2 *__restrict__ pos_out, float2 *__restrict__ vel_out,
+        int *__restrict__ cnt, int *__restrict__ t_key, int *__restrict__ t_slot,
+        unsigned char *send_l, unsigned char *send_r)
+{
+    const DevParams P = *Pp;
+    const int n = counters[CN_NTOT];
+    const float dt = P.dt, dt2 = dt * dt;
+    const float h = P.h;
+    const float h_recip = __fdiv_rn(1.0f, h);
+    const float h2 = __fmul_rn(h, h);
+    if (blockIdx.x == 0 && threadIdx.x == 0) counters[CN_MAX_BUCKET] = 0;
+
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t u = uid[i];
+        if (u & SPH_HALO_BIT) { t_key[i] = SPH_KEY_DROP; continue; }
+        const float2 p = pos[i];
+        const float2 di = dens[i];
+        const float pp = P.k * (di.x - P.rest_density);        // fluid.c:563-564
+        const float ppn = P.k_near * di.y;
+        float x = p.x, y = p.y;
+        const int gxi = cell_coord(p.x, P.cell_h), gyi = cell_coord(p.y, P.cell_h);
+        const Rows R = candidate_rows(p, P, cell_start);
+#pragma unroll
+        for (int d = 0; d < 3; d++) {
+            for (int j = R.b[d]; j < R.e[d]; j++) {
+                const float2 q = pos[j];
+                const float dx = q.x - p.x, dy = q.y - p.y;
+                const float r2 = dist2(dx, dy);
+                if (r2 > h2 || j == i) continue;
+                const float r = __fsqrt_rn(r2);
+                const float ratio = r * h_recip;
+                if (r <= 0.000001f) {
+                    // coincident particles: only the list owner is nudged (fluid.c:583-586); owner =
+                    // earlier bucket slot in the same cell, else the cell whose forward stencil
+                    // (0,+1),(1,-1),(1,0),(1,+1) holds the other (hash.c:178-224)
+                    const int gxj = cell_coord(q.x, P.cell_h), gyj = cell_coord(q.y, P.cell_h);
+                    const bool owner = (gxi == gxj && gyi == gyj) ? (i < j) : (gxi != gxj ? gxi < gxj : gyi < gyj);
+                    if (owner) { x += 0.000001f; y += 0.000001f; }
+                }
+                if (ratio < 1.0f && r > 0.0f) {
+                    const float2 dj = dens[j];
+                    const float pq = P.k * (dj.x - P.rest_density);
+                    const float pqn = P.k_near * dj.y;
+                    const float omr = 1.0f - ratio;
+                    const float r_recip = __fdiv_rn(1.0f, r);
+                    // fluid.c:591; the reference's fp64 tail is evaluated in fp32 here (<= 1 ulp of D)
+                    const float D = dt2 * ((pp + pq) * omr + (ppn + pqn) * omr * omr + P.k_spring * (h - r) * 0.5f);
+                    x -= D * dx * r_recip;
+                    y -= D * dy * r_recip;
+                }
+            }
+        }
+        float2 np = boundary(make_float2(x, y), P);                     // fluid.c:649
+        const float2 pv = prev[i];
+        const float2 v = make_float2(clamp5(__fdiv_rn(np.x - pv.x, dt)), clamp5(__fdiv_rn(np.y - pv.y, dt)));
+        pos_out[i] = np;
+        vel_out[i] = v;
+        if (P.nranks > 1) {
+            if (P.has_left && np.x - P.edge_start <= P.halo_w) {
+                int k = atomicAdd(&msg_hdr(send_l)[1], 1);
+                if (k < P.msg_cap) { msg_a(send_l)[k] = np; msg_b(send_l, P.msg_cap)[k] = v; msg_u(send_l, P.msg_cap)[k] = u; }
+                else atomicAdd(&counters[CN_MSG_OVER], 1);
+            }
+            if (P.has_right && P.edge_end - np.x <= P.halo_w) {
+                int k = atomicAdd(&msg_hdr(send_r)[1], 1);
+                if (k < P.msg_cap) { msg_a(send_r)[k] = np; msg_b(send_r, P.msg_cap)[k] = v; msg_u(send_r, P.msg_cap)[k] = u; }
+                else atomicAdd(&counters[CN_MSG_OVER], 1);
+            }
+        }
+        bin_position(i, np, 0, P, cnt, t_key, t_slot, counters);
+    }
+}
+
+// -------------------------------------------------------------------------------------------
+// upload helper: bin freshly uploaded particles (sph_upload)
+// -------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(SPH_THREADS)
+k_bin_upload(const DevParams *__restrict__ Pp, int *__restrict__ counters, const float2 *__restrict__ pos,
+             int *__restrict__ cnt, int *__restrict__ t_key, int *__restrict__ t_slot)
+{
+    const DevParams P = *Pp;
+    const int n = counters[CN_NTOT];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        bin_position(i, pos[i], 0, P, cnt, t_key, t_slot, counters);
+}
+
+// -------------------------------------------------------------------------------------------
+// render feed (fluid.c:358-361): (2x/max_x - 1) * SHRT_MAX, truncated to int16
+// -------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(SPH_THREADS)
+k_pack_coords(const DevParams *__restrict__ Pp, int *__restrict__ counters, const float2 *__restrict__ pos,
+              const uint32_t *__restrict__ uid, short2 *__restrict__ out, int cap)
+{
+    const DevParams P = *Pp;
+    const int n = counters[CN_NTOT];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        if (uid[i] & SPH_HALO_BIT) continue;
+        int k = P.nranks > 1 ? atomicAdd(&counters[CN_COORDS], 1) : i;
+        if (k >= cap) continue;
+        const float2 p = pos[i];
+        float fx = __fmul_rn(__fsub_rn(__fdiv_rn(__fmul_rn(2.0f, p.x), P.tank_w), 1.0f), 32767.0f);
+        float fy = __fmul_rn(__fsub_rn(__fdiv_rn(__fmul_rn(2.0f, p.y), P.tank_h), 1.0f), 32767.0f);
+        out[k] = make_short2((short)fx, (short)fy);
+    }
+}
+
+// -------------------------------------------------------------------------------------------
+// parity / inspection kernels (not on the hot path)
+// -------------------------------------------------------------------------------------------
+__global__ void k_export_cells(const DevParams *__restrict__ Pp, const int *__restrict__ counters,
+                               const float2 *__restrict__ pos, uint32_t *__restrict__ cell)
+{
+    const DevParams P = *Pp;
+    const int n = counters[CN_NTOT];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        unsigned gx = (unsigned)cell_coord(pos[i].x, P.cell_h), gy = (unsigned)cell_coord(pos[i].y, P.cell_h);
+        cell[i] = gy * (unsigned)P.size_x + gx;             // global numbering of hash_val (hash.c:44)
+    }
+}
+
+__global__ void k_export_pairs(const DevParams *__restrict__ Pp, const int *__restrict__ counters,
+                               const float2 *__restrict__ pos, const uint32_t *__restrict__ uid,
+                               const int *__restrict__ cell_start, unsigned long long *__restrict__ pairs,
+                               unsigned long long cap, unsigned long long *__restrict__ n_pairs,
+                               int *__restrict__ fwd_count)
+{
+    const DevParams P = *Pp;
+    const int n = counters[CN_NTOT];
+    const float h2 = __fmul_rn(P.h, P.h);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float2 p = pos[i];
+        const uint32_t ui = uid[i] & SPH_UID_MASK;
+        const int gxi = cell_coord(p.x, P.cell_h), gyi = cell_coord(p.y, P.cell_h);
+        int fwd = 0;
+        const Rows R = candidate_rows(p, P, cell_start);
+        for (int d = 0; d < 3; d++)
+            for (int j = R.b[d]; j < R.e[d]; j++) {
+                if (j == i) continue;
+                const float2 q = pos[j];
+                if (dist2(p.x - q.x, p.y - q.y) > h2) continue;
+                const uint32_t uj = uid[j] & SPH_UID_MASK;
+                if (uj > ui && pairs) {
+                    unsigned long long k = atomicAdd(n_pairs, 1ull);
+                    if (k < cap) pairs[k] = ((unsigned long long)ui << 32) | uj;
+                }
+                const int gxj = cell_coord(q.x, P.cell_h), gyj = cell_coord(q.y, P.cell_h);
+                const bool owner = (gxi == gxj && gyi == gyj) ? (i < j) : (gxi != gxj ? gxi < gxj : gyi < gyj);
+                if ((uid[j] & SPH_HALO_BIT) || owner) fwd++;
+            }
+        if (fwd_count) fwd_count[i] = fwd;
+    }
+}

@@ -1,0 +1,42 @@
+"""The C-ABI library builds for sm_100a, loads, and exports every symbol include/sph_b200.h
+declares.  No compute calls here (no GPU in this container); on a box without a device the
+library must refuse loudly instead of falling back to anything."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+
+def test_library_exports_every_declared_symbol(built_lib):
+    import sph_b200
+    L = C.CDLL(built_lib)
+    hdr = open(os.path.join(os.path.dirname(built_lib), "..", "include", "sph_b200.h")).read()
+    declared = set(re.findall(r"\b(sph_[a-z_]+)\s*\(", hdr))
+    assert declared == set(sph_b200.C_ABI_SYMBOLS), declared ^ set(sph_b200.C_ABI_SYMBOLS)
+    for name in declared:
+        assert hasattr(L, name), name
+
+
+def test_record_layouts_match_reference():
+    import sph_b200
+    assert sph_b200.PARTICLE.itemsize == 52 and sph_b200.PARTICLE.fields["id"][1] == 48       # fluid.h:56-70
+    assert C.sizeof(sph_b200.Tunable) == 64                                                   # fluid.h:78-97
+    assert sph_b200.Tunable.mover_type.offset == 60
+
+
+def test_no_cpu_fallback(built_lib):
+    """Without a CUDA device sph_create must fail with SPH_ERR_CUDA (1) and say why."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    import sph_b200
+    with pytest.raises(sph_b200.SphError) as e:
+        sph_b200.Context(15.0, 8.4375, 0.58, 2048)
+    assert "-> 1" in str(e.value)
+
+
+def test_sass_is_sm100a(built_lib):
+    import subprocess
+    out = subprocess.run(["cuobjdump", "-lelf", built_lib], capture_output=True, text=True).stdout
+    assert "sm_100a" in out

@@ -1,0 +1,180 @@
+"""CUDA path (through the C ABI, libsph_b200.so) against the reference's golden vectors and against
+the gather oracle.  Run on the B200 box: pytest -m gpu."""
+import numpy as np
+import pytest
+
+import parity_checks as pc
+from common import load_golden, random_state, ulp32
+from oracle.oracle import GatherOracle, default_tunable, lattice, make_problem
+
+pytestmark = pytest.mark.gpu
+
+CASES = [("default1508", 100), ("default1508", 400), ("goo_rect1508", 300), ("block3000", 150),
+         ("zerog1508", 200), ("gas1508", 200)]
+
+
+def make(tank_w, tank_h, h, capacity):
+    import sph_b200
+    return sph_b200.Context(tank_w, tank_h, h, capacity)
+
+
+def make_oracle(tank_w, tank_h, h, capacity):
+    return GatherOracle(tank_w, tank_h, h, capacity)
+
+
+def as_sph(t):
+    """oracle.Tunable -> sph_b200.Tunable (same 64-byte layout)."""
+    import ctypes as C
+    import sph_b200
+    o = sph_b200.Tunable()
+    C.memmove(C.byref(o), C.byref(t), 64)
+    return o
+
+
+class Cuda:
+    """Adapter so parity_checks can hand oracle.Tunable blocks to the CUDA context."""
+
+    def __init__(self, *a):
+        self.c = make(*a)
+
+    def set_params(self, t): self.c.set_params(as_sph(t))
+    def queue_params(self, t): self.c.queue_params(as_sph(t))
+
+    def __getattr__(self, k):
+        return getattr(self.c, k)
+
+
+def mk(*a):
+    return Cuda(*a)
+
+
+@pytest.mark.parametrize("name,warm", CASES)
+def test_binning_and_neighbour_sets_bit_exact(built_lib, name, warm):
+    pc.check_binning_and_neighbours_exact(mk, name, warm)
+
+
+@pytest.mark.parametrize("name,warm", CASES)
+def test_one_step_within_tolerance_of_reference(built_lib, name, warm):
+    pc.check_stages_vs_reference(mk, name, warm)
+
+
+@pytest.mark.parametrize("name,warm", CASES)
+def test_density_on_reference_positions(built_lib, name, warm):
+    pc.check_density_exact_positions(mk, name, warm)
+
+
+@pytest.mark.parametrize("name,warm", CASES)
+def test_rounding_level_agreement_with_gather_oracle(built_lib, name, warm):
+    pc.check_tight_vs_gather_oracle(mk, make_oracle, name, warm, steps=3)
+
+
+@pytest.mark.parametrize("name,warm", CASES[:2])
+def test_ten_steps_bounded(built_lib, name, warm):
+    pc.check_ten_steps_bounded(mk, name, warm)
+
+
+def test_long_run_statistics_default(built_lib):
+    a, _ = lattice(make_problem(1500))
+    pc.check_long_run_statistics(mk, "default1508", a, dens_make=make_oracle)
+
+
+def test_graph_step_equals_staged_and_is_deterministic(built_lib):
+    z, t, tank_w, tank_h, h, _ = load_golden("default1508")
+    st = z["w400_state"]
+    outs = []
+    for mode in ("graph", "staged", "graph"):
+        b = mk(tank_w, tank_h, h, len(st) + 64)
+        b.set_params(t); b.upload(st)
+        if mode == "graph":
+            b.step(25)
+        else:
+            for _ in range(25):
+                b.advect(); b.sort(); b.density(); b.relax(); b.sort()
+        outs.append(b.download()[0])
+    for f in ("x", "y", "v_x", "v_y"):
+        assert np.array_equal(outs[0][f].view("u4"), outs[1][f].view("u4"))
+        assert np.array_equal(outs[0][f].view("u4"), outs[2][f].view("u4"))
+
+
+def test_queued_params_land_between_predict_and_relax(built_lib):
+    """fluid.c:279-310: the scatter changes the mover between the two boundaryConditions calls."""
+    z, t, tank_w, tank_h, h, _ = load_golden("default1508")
+    st = z["w400_state"]
+    t2 = t.copy(); t2.mover_center_x = 0.3 * tank_w; t2.mover_center_y = 0.1 * tank_h; t2.k = 0.3
+    b = mk(tank_w, tank_h, h, len(st) + 64); o = make_oracle(tank_w, tank_h, h, len(st) + 64)
+    for x in (b, o):
+        x.set_params(t); x.upload(st); x.queue_params(t2); x.step(2)
+    a, _ = b.download(); r, _ = o.download()
+    tol = 64 * ulp32(tank_w)
+    assert np.abs(a["x"] - r["x"]).max() <= tol and np.abs(a["y"] - r["y"]).max() <= tol
+
+
+def test_edge_cases(built_lib):
+    z, t, tank_w, tank_h, h, _ = load_golden("default1508")
+    # empty
+    b = mk(tank_w, tank_h, h, 64); b.set_params(t); b.upload(np.zeros(0, random_state(1, 1, 1, 0).dtype)); b.step(2)
+    assert len(b.download()[0]) == 0 and len(b.pairs()) == 0
+    # one particle: free fall, then rests on the floor at y == 0 exactly (fluid.c:738-740)
+    one = random_state(1, tank_w, tank_h, 1); one["x"] = 1.0; one["y"] = 0.01; one["v_x"] = 0; one["v_y"] = 0
+    b = mk(tank_w, tank_h, h, 64); b.set_params(t); b.upload(one); b.step(50)
+    a, _ = b.download()
+    assert a["y"][0] == 0.0 and a["x"][0] == 1.0
+    # hostile soup: coincident pairs, corner pile-up, particles exactly on the max walls
+    a = random_state(1500, tank_w, tank_h, seed=3, clustered=True)
+    a[10] = a[11]; a[12]["x"] = a[12]["y"] = a[13]["x"] = a[13]["y"] = 0.0
+    a[14]["x"] = tank_w; a[15]["y"] = tank_h
+    a["id"] = np.arange(len(a))
+    b = mk(tank_w, tank_h, h, 2048); o = make_oracle(tank_w, tank_h, h, 2048)
+    for x in (b, o):
+        x.set_params(t); x.upload(a)
+    assert np.array_equal(b.pairs(), o.pairs())
+    ub, cb = b.cells(); uo, co = o.cells()
+    assert np.array_equal(ub, uo) and np.array_equal(cb, co)          # same device order, same cells
+    b.step(1); o.step(1)
+    x, _ = b.download(); y, _ = o.download()
+    ok = np.isfinite(y["x"]) & np.isfinite(y["y"])
+    assert np.array_equal(np.isfinite(x["x"]), np.isfinite(y["x"]))
+    assert np.abs(x["x"][ok] - y["x"][ok]).max() <= 1e-4 and np.abs(x["y"][ok] - y["y"][ok]).max() <= 1e-4
+    s = b.status()
+    assert s.capacity_overflow == 0 and s.n_local == 1500
+
+
+def test_pack_coords_matches_reference_formula(built_lib):
+    z, t, tank_w, tank_h, h, _ = load_golden("default1508")
+    st = z["w400_state"]
+    b = mk(tank_w, tank_h, h, len(st) + 64); o = make_oracle(tank_w, tank_h, h, len(st) + 64)
+    for x in (b, o):
+        x.set_params(t); x.upload(st)
+    assert np.array_equal(b.pack_coords(), o.pack_coords())
+
+
+@pytest.mark.parametrize("n_request", [100_000, 1_000_000])
+def test_full_size_properties(built_lib, n_request):
+    """BASELINE.json sizes: properties that do not need the oracle to finish -- the sort is a
+    permutation, cells are sorted, particles stay in the tank, nothing overflows -- plus a sampled
+    neighbour-set and one-step comparison against the gather oracle at 100k."""
+    prob = make_problem(n_request, tank_w=15.0 * np.sqrt(n_request / 1500.0), water_frac=0.5)
+    a, uid = lattice(prob)
+    t = default_tunable(prob["h"], prob["tank_w"], prob["tank_h"])
+    b = mk(prob["tank_w"], prob["tank_h"], prob["h"], len(a) + 1024)
+    b.set_params(t); b.upload(a, uid)
+    b.step(60)
+    out, u = b.download()
+    assert np.array_equal(u, np.sort(uid))                                   # nobody lost, nobody duplicated
+    assert np.all((out["x"] >= 0) & (out["x"] <= prob["tank_w"]) & (out["y"] >= 0) & (out["y"] <= prob["tank_h"]))
+    assert np.all(np.abs(out["v_x"]) <= 5.0) and np.all(np.abs(out["v_y"]) <= 5.0)   # fluid.c:613-625
+    du, dc = b.cells()
+    assert np.all(np.diff(dc.astype("i8")) >= 0)                             # device order is cell order
+    s = b.status()
+    assert s.capacity_overflow == 0 and s.bucket_overflow == 0 and s.neighbor_overflow == 0
+    assert s.n_local == len(a) and s.n_halo == 0
+    if n_request <= 100_000:
+        o = make_oracle(prob["tank_w"], prob["tank_h"], prob["h"], len(a) + 1024)
+        o.set_params(t); o.upload(out, u)
+        b2 = mk(prob["tank_w"], prob["tank_h"], prob["h"], len(a) + 1024)
+        b2.set_params(t); b2.upload(out, u)
+        assert np.array_equal(b2.pairs(), o.pairs())
+        b2.step(1); o.step(1)
+        x, _ = b2.download(); y, _ = o.download()
+        tol = 16 * ulp32(prob["tank_w"])
+        assert np.abs(x["x"] - y["x"]).max() <= tol and np.abs(x["y"] - y["y"]).max() <= tol
