@@ -1,0 +1,383 @@
+#!/usr/bin/env python
+"""bench.py -- particle-steps/s of the TinySPH compute-rank timestep on B200.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--n PARTICLES]
+
+Workload (BASELINE.json configs[1]): 2-D dam-break block, 1 M particles per GPU, default fluid
+preset 'x', lattice spacing and h of the reference (s0 = 0.2905, h = 0.5809), tank scaled so the
+water block (left half, full height) holds N particles; mover sphere (diameter 2/15 W) parked in
+the dry half at (0.75 W, 0.35 H).  A "step" is one iteration of the loop at fluid.c:270-372
+(dt = 1/120).  Weak scaling: N GPUs -> N x 1 M particles in N x-slabs.
+
+One JSON line on stdout (rank 0).  Keys beyond the base contract:
+  roofline      dominant kernel vs the measured HBM peak, algorithmic bytes
+  cpu_baseline  the unmodified reference (oracle/_ref/sph_ref_run) on this box's host cores
+  e2e           frames through sph_run_frame: parameter block H2D + 4 steps + int16 coords D2H
+"""
+import argparse
+import json
+import os
+import re
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ALG_BYTES = {            # algorithmic bytes per particle per launch
+    "advect": 24, "sort": 48 + 8 + 4, "density": 16, "relax": 40, "step": 200,
+}
+HBM_FALLBACK_GBS = 6650.0
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured"
+    return HBM_FALLBACK_GBS, "fallback"
+
+
+def problem_dims(n, water_frac):
+    import numpy as np
+    tank_w = 15.0 * float(np.sqrt(n / (1500.0 * water_frac)))
+    return tank_w
+
+
+class ClockSampler:
+    """nvidia-smi clocks during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        if not self.p:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        out = self.p.communicate()[0]
+        sm, mx, reasons = [], None, set()
+        for line in out.splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx = float(f[2])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / CPU baseline: the unmodified reference on the host cores
+# ------------------------------------------------------------------------------------------------
+def run_reference_cpu(n, water_frac, steps, warmup, ranks=None, budget_s=150.0):
+    """Runs oracle/_ref/sph_ref_run (reference TUs compiled unmodified + mini-MPI).  Falls back to the
+    C restatement (oracle port, 1 core) when the reference binary is absent.  Sample is bounded so the
+    run stays within `budget_s`."""
+    from oracle.oracle import ref_binary
+    cores = os.cpu_count() or 1
+    exe = ref_binary()
+    if exe:
+        ranks = ranks or max(1, min(cores, 64))
+        est_rate = 0.5e6 * ranks                       # particle-steps/s, conservative
+        n_s = int(min(n, max(20000, est_rate * budget_s / max(steps + warmup, 1))))
+        tank_w = problem_dims(n_s, water_frac)
+        cmd = [exe, "--ranks", str(ranks), "--n", str(n_s), "--tank-w", f"{tank_w:.6f}",
+               "--tank-h", f"{tank_w * 9.0 / 16.0:.6f}", "--water-frac", str(water_frac),
+               "--mover-x-frac", "0.75", "--steps", str(steps), "--warmup", str(warmup), "--balance", "1"]
+        t0 = time.time()
+        out = subprocess.run(cmd, capture_output=True, text=True, timeout=budget_s * 4)
+        line = [l for l in out.stdout.splitlines() if l.startswith("{")]
+        if out.returncode != 0 or not line:
+            raise RuntimeError(f"sph_ref_run failed rc={out.returncode}: {out.stderr[-400:]}")
+        r = json.loads(line[-1])
+        return {"value": r["particle_steps_per_s"], "unit": "particle-steps/s", "cores": ranks, "kind": "reference",
+                "sample": f"{r['n_global']} particles x {steps} steps (+{warmup} warm-up) from the lattice, "
+                          f"{ranks} compute ranks over mini-MPI, load balancer on, host has {cores} cores, "
+                          f"wall {time.time() - t0:.1f}s",
+                "ms_per_step": 1e3 * r["seconds"] / max(steps, 1), "n_particles": r["n_global"]}
+    # oracle port: single core
+    import ctypes as C
+    from oracle.oracle import SeqOracle, default_tunable, lattice, make_problem
+    n_s = int(min(n, 200000))
+    prob = make_problem(n_s, tank_w=problem_dims(n_s, water_frac), water_frac=water_frac)
+    a, _ = lattice(prob)
+    t = default_tunable(prob["h"], prob["tank_w"], prob["tank_h"]); t.mover_center_x = 0.75 * prob["tank_w"]
+    seq = SeqOracle(len(a) + 8, prob["tank_w"], prob["tank_h"], t)
+    seq.load(a)
+    for _ in range(warmup):
+        seq.step()
+    t0 = time.time()
+    for _ in range(steps):
+        seq.step()
+    dt = time.time() - t0
+    return {"value": len(a) * steps / dt, "unit": "particle-steps/s", "cores": 1, "kind": "port",
+            "sample": f"{len(a)} particles x {steps} steps from the lattice, oracle/sph_oracle.c orc_seq_step",
+            "ms_per_step": 1e3 * dt / max(steps, 1), "n_particles": len(a)}
+
+
+def main_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    n = args.n * args.gpus
+    r = run_reference_cpu(n, args.water_frac, args.steps, args.warmup)
+    line = {
+        "impl": "reference", "metric": "particle-steps/sec", "value": r["value"], "unit": "particle-steps/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"2D dam-break block, {n} particles requested ({r['n_particles']} in the bounded sample), "
+                               "preset x, CPU reference", "water_frac": args.water_frac},
+        "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": r["value"], "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def main_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import sph_b200
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; sph_b200 has no CPU path")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("bench.py --gpus N>1 must be launched with torch.distributed.run (one rank per GPU)")
+    peak, peak_kind = measured_peak()
+
+    n_global_req = args.n * world
+    tank_w = problem_dims(n_global_req, args.water_frac)
+    prob = sph_b200.make_problem(n_global_req, tank_w=tank_w, water_frac=args.water_frac, nranks=world)
+    t = sph_b200.default_params(prob["h"], prob["tank_w"], prob["tank_h"], args.preset)
+    t.mover_center_x = 0.75 * prob["tank_w"]
+    stream = torch.cuda.Stream()
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.cuda.stream(stream):
+        if world == 1:
+            sim = SingleGpu(sph_b200, prob, t, stream, args)
+        else:
+            from sph_b200.slab import SlabRunner
+            sim = SlabRunner(prob, t, rank, world, stream, capacity_factor=2.0)
+        sim.init_lattice()
+        sim.run(args.preroll)
+        sim.run(args.warmup)
+        barrier()
+        launches0 = sim.launches
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        # ---- timed region: K steps, L2 flushed between steps, device time per step from CUDA events
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        wall0 = time.perf_counter()
+        for k in range(args.steps):
+            flush_buf.zero_()
+            ev[k][0].record(stream)
+            sim.run(1)
+            ev[k][1].record(stream)
+        barrier()
+        wall = time.perf_counter() - wall0
+        clocks = sampler.stop()
+        launches = sim.launches - launches0
+        step_ms = [a.elapsed_time(b) for a, b in ev]
+        total_ms = float(sum(step_ms))
+        # ---- the same K steps back to back, state L2-resident (informational)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record(stream); sim.run(args.steps); e1.record(stream)
+        barrier()
+        b2b_ms = e0.elapsed_time(e1)
+        # ---- per-stage device times for the roofline (stage API, flushed between steps)
+        stage_ms = sim.stage_times(min(args.steps, 20), flush_buf)
+        # ---- end to end through the frame call with host buffers
+        e2e = sim.e2e(max(3, args.steps // 4), flush_buf)
+        stats = sim.stats()
+
+    if world > 1:
+        tmax = torch.tensor([total_ms, b2b_ms, e2e["seconds"]], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        total_ms, b2b_ms, e2e_s = [float(x) for x in tmax.tolist()]
+        e2e["seconds"] = e2e_s
+        cnt = torch.tensor([stats["n_local"], launches], device="cuda", dtype=torch.float64)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+        n_global = int(cnt[0].item()); launches = int(cnt[1].item())
+    else:
+        n_global = stats["n_local"]
+
+    if rank == 0:
+        ms_per_step = total_ms / args.steps
+        value = n_global * args.steps / (total_ms * 1e-3)
+        dom = max(stage_ms, key=lambda k: stage_ms[k])
+        n_per_launch = stats["n_local"] + stats["n_halo"]
+        dom_key = "sort" if dom.startswith("sort") else dom
+        achieved = ALG_BYTES[dom_key] * n_per_launch / (stage_ms[dom] * 1e-3) / 1e9
+        step_gbs = ALG_BYTES["step"] * n_global / world / (ms_per_step * 1e-3) / 1e9
+        line = {
+            "metric": "particle-steps/sec", "value": value, "unit": "particle-steps/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {
+                "workload": f"2D dam-break block, {n_global} particles ({args.n} requested per GPU), preset {args.preset}, "
+                            f"h={prob['h']:.6f}, tank {prob['tank_w']:.1f}x{prob['tank_h']:.1f}, {world} x-slab(s)",
+                "state": f"{args.preroll} pre-roll steps + {args.warmup} warm-up steps from the lattice",
+                "mean_neighbours_per_particle": stats["mean_neighbours"], "max_bucket": stats["max_bucket"],
+                "l2": "flushed between timed steps (256 MiB write, outside the per-step CUDA-event brackets)",
+                "l2_resident_value": n_global * args.steps / (b2b_ms * 1e-3),
+                "l2_resident_ms_per_step": b2b_ms / args.steps,
+                "wall_s_timed_region": wall,
+                "stage_ms": stage_ms,
+                "step_hbm_frac": step_gbs / peak,
+                "parallelism": f"slab{world}",
+            },
+            "roofline": {"bound": "hbm", "kernel": sim.kernel_name(dom), "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_kind,
+                         "algorithmic_bytes_per_particle": ALG_BYTES[dom_key]},
+            "clocks": clocks,
+            "e2e": {"value": n_global * e2e["steps"] / e2e["seconds"], "unit": "particle-steps/s",
+                    "h2d_bytes_per_step": e2e["h2d_per_step"], "d2h_bytes_per_step": e2e["d2h_per_step"],
+                    "protocol": "per frame: 64-byte parameter block H2D, 4 steps, int16 (x,y) per particle D2H "
+                                "into pinned host memory (fluid.c:293-294, :354-365)"},
+            "gpu_launches": launches,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            try:
+                r = run_reference_cpu(args.n, args.water_frac, steps=args.cpu_steps, warmup=2, budget_s=40.0)
+                line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            except Exception as e:  # the baseline is reported, never fatal
+                line["cpu_baseline"] = {"value": None, "unit": "particle-steps/s", "cores": 0, "kind": "reference",
+                                        "sample": f"failed: {e}"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+class SingleGpu:
+    """One GPU, one slab, whole tank: sph_step from a CUDA graph."""
+
+    def __init__(self, sph, prob, t, stream, args):
+        import numpy as np
+        self.sph, self.prob, self.t = sph, prob, t
+        self.np = np
+        self.stream = stream
+        self.cap = prob["n_global"] + 4096
+        self.ctx = sph.Context(prob["tank_w"], prob["tank_h"], prob["h"], self.cap, stream=stream.cuda_stream)
+        self.ctx.set_params(t)
+
+    @property
+    def launches(self):
+        return self.ctx.launches
+
+    def init_lattice(self):
+        a, uid = self.sph.lattice(self.prob)
+        self.ctx.upload(a, uid)
+
+    def run(self, n):
+        if n > 0:
+            self.ctx.step(n)
+
+    def stage_times(self, nsteps, flush_buf):
+        import torch
+        names = ("advect", "sort1", "density", "relax", "sort2")
+        acc = {k: 0.0 for k in names}
+        c = self.ctx
+        for _ in range(nsteps):
+            flush_buf.zero_()
+            evs = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
+            evs[0].record(self.stream); c.advect()
+            evs[1].record(self.stream); c.sort()
+            evs[2].record(self.stream); c.density()
+            evs[3].record(self.stream); c.relax()
+            evs[4].record(self.stream); c.sort()
+            evs[5].record(self.stream)
+            torch.cuda.synchronize()
+            for i, k in enumerate(names):
+                acc[k] += evs[i].elapsed_time(evs[i + 1])
+        return {k: v / nsteps for k, v in acc.items()}
+
+    def kernel_name(self, stage):
+        return {"advect": "k_advect", "density": "k_density", "relax": "k_relax",
+                "sort1": "k_scan+k_scatter+k_reorder", "sort2": "k_scan+k_scatter+k_reorder"}[stage]
+
+    def e2e(self, frames, flush_buf):
+        import torch
+        coords = torch.empty(2 * self.cap, dtype=torch.int16).pin_memory()
+        xy = coords.numpy()
+        for _ in range(2):
+            self.ctx.run_frame(self.t, 4, xy)
+        torch.cuda.synchronize()
+        secs = 0.0
+        n = 0
+        for _ in range(frames):
+            flush_buf.zero_()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            n = self.ctx.run_frame(self.t, 4, xy)      # returns after the coordinates are in host memory
+            secs += time.perf_counter() - t0
+        return {"seconds": secs, "steps": 4 * frames, "h2d_per_step": 64 / 4, "d2h_per_step": 4 * n / 4}
+
+    def stats(self):
+        s = self.ctx.status()
+        npairs = self.ctx.L.sph_get_pairs(self.ctx.h, None, 0)
+        return {"n_local": s.n_local, "n_halo": s.n_halo, "max_bucket": s.max_bucket,
+                "mean_neighbours": 2.0 * npairs / max(s.n_local, 1)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=1_000_000, help="particles per GPU")
+    ap.add_argument("--preroll", type=int, default=1000, help="untimed steps before warm-up (state preparation)")
+    ap.add_argument("--water-frac", type=float, default=0.5)
+    ap.add_argument("--preset", default="x")
+    ap.add_argument("--cpu-steps", type=int, default=10)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        return main_reference(args)
+    return main_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,53 @@
+/*
+ * sph_host -- C host layer of sph_b200: the start-up geometry, parameter model and slab
+ * load balancer of the TinySPH compute path, in plain C99 (no CUDA types).  Linked into
+ * libsph_b200.so next to the CUDA library; it prepares inputs for, and steers, the entry points
+ * of sph_b200.h.  Citations: AdamSimpson/SPH `src/`.
+ */
+#ifndef SPH_HOST_H
+#define SPH_HOST_H
+
+#include "sph_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* initial particle spacing: sqrt(water area / N) as fluid.c:141-144 computes it */
+float sph_host_spacing(float water_w, float water_h, int n_request);
+
+/* hard-coded start-up parameters of start_simulation (fluid.c:88-107, :159), mover parked at
+ * (0.5 W, 0.35 H) with diameter 2/15 W (the reference leaves the centre uninitialised) */
+void sph_host_default_params(sph_tunable *t, float h, float tank_w, float tank_h);
+
+/* fluid presets of the game-pad buttons: 'x' water, 'y' goo, 'a' zero-g, 'b' spring gas
+ * (controls.c:344-401). Returns 0 on success. */
+int sph_host_preset(sph_tunable *t, char which);
+
+/* partitionProblem (geometry.c:101-160) for all ranks at once: equal lattice columns, remainder
+ * to the left ranks, first/last slab clamped to the tank. Returns N_global actually used
+ * (geometry.c:152-156). */
+int sph_host_partition(float tank_w, float water_min_x, float water_max_x, float water_min_y,
+                       float water_max_y, float spacing, int nranks,
+                       int *start_col, int *ncols, float *start_x, float *end_x);
+
+/* constructFluidVolume (geometry.c:29-59) + initParticles (fluid.c:747-768) for one slab's
+ * columns; uid = row * total_cols + column. Returns the number of particles written. */
+int sph_host_lattice(float water_min_x, float water_min_y, float water_max_y, float spacing,
+                     int start_col, int ncols, int total_cols, sph_particle *out, uint32_t *uid);
+
+/* check_partition_left (renderer.c:427-477): nudge interior slab edges by h/8 toward equal
+ * particle counts; dead band even/15, minimum slab width 2h. `counts` are whatever the caller
+ * uses consistently on both sides of the ratio (the reference passes coordinate counts,
+ * renderer.c:280,290). */
+void sph_host_balance(sph_tunable *master, int nactive, const int *counts, int total);
+
+/* remove_partition / add_partition (controls.c:405-455): park the last active slab outside the
+ * tank / split the last active slab in half. Return the new number of active slabs. */
+int sph_host_remove_partition(sph_tunable *master, int nactive);
+int sph_host_add_partition(sph_tunable *master, int nactive, int nranks);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -310,7 +310,7 @@ void refh_balance(tunable_parameters *master, int nactive, const int *counts, in
 
 typedef struct {
     int ranks, n, steps, warmup, balance, quiet;
-    float tank_w, tank_h, water_frac;
+    float tank_w, tank_h, water_frac, mover_x_frac, mover_y_frac;
     const char *dump;
 } cli_t;
 
@@ -336,7 +336,7 @@ static int run_rank(int rank, const cli_t *c)
     cfg.water_min_x = 0.0f; cfg.water_max_x = c->tank_w * c->water_frac;
     cfg.water_min_y = 0.0f; cfg.water_max_y = c->tank_h;
     cfg.mover_w = cfg.mover_h = 2.0f * c->tank_w / 15.0f;
-    cfg.mover_cx = 0.5f * c->tank_w; cfg.mover_cy = 0.35f * c->tank_h;
+    cfg.mover_cx = c->mover_x_frac * c->tank_w; cfg.mover_cy = c->mover_y_frac * c->tank_h;
     cfg.mover_type = SPHERE_MOVER;
     cfg.steps_per_frame = 4;
     cfg.cap_factor = 2;
@@ -422,6 +422,8 @@ int main(int argc, char **argv)
     c.tank_w = (float)arg_f(argc, argv, "--tank-w", 15.0);
     c.tank_h = (float)arg_f(argc, argv, "--tank-h", 15.0 * 9.0 / 16.0);
     c.water_frac = (float)arg_f(argc, argv, "--water-frac", 1.0);
+    c.mover_x_frac = (float)arg_f(argc, argv, "--mover-x-frac", 0.5);
+    c.mover_y_frac = (float)arg_f(argc, argv, "--mover-y-frac", 0.35);
     c.dump = arg_s(argc, argv, "--dump", NULL);
     size_t ring = (size_t)arg_f(argc, argv, "--ring-mb", 64) << 20;
     if (mini_mpi_world_create(c.ranks, ring) != 0) { fprintf(stderr, "world create failed\n"); return 1; }

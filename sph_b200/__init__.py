@@ -219,3 +219,73 @@ class Context:
     @property
     def launches(self):
         return int(self.L.sph_launch_count(self.h))
+
+
+# ------------------------------------------------------------------------------------------------
+# C host layer (include/sph_host.h): start-up geometry, parameter model, slab load balancer
+# ------------------------------------------------------------------------------------------------
+HOST_SYMBOLS = ("sph_host_spacing", "sph_host_default_params", "sph_host_preset", "sph_host_partition",
+                "sph_host_lattice", "sph_host_balance", "sph_host_remove_partition", "sph_host_add_partition")
+
+
+def _host():
+    L = lib()
+    if not getattr(L, "_host_ready", False):
+        L.sph_host_spacing.restype = C.c_float
+        L.sph_host_spacing.argtypes = [C.c_float, C.c_float, C.c_int]
+        L.sph_host_default_params.argtypes = [C.POINTER(Tunable), C.c_float, C.c_float, C.c_float]
+        L.sph_host_preset.argtypes = [C.POINTER(Tunable), C.c_char]
+        L.sph_host_partition.argtypes = [C.c_float] * 6 + [C.c_int] + [C.c_void_p] * 4
+        L.sph_host_lattice.argtypes = [C.c_float] * 4 + [C.c_int] * 3 + [C.c_void_p] * 2
+        L.sph_host_balance.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+        L.sph_host_remove_partition.argtypes = [C.c_void_p, C.c_int]
+        L.sph_host_add_partition.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L._host_ready = True
+    return L
+
+
+def default_params(h, tank_w, tank_h, preset="x"):
+    t = Tunable()
+    L = _host()
+    L.sph_host_default_params(C.byref(t), h, tank_w, tank_h)
+    if L.sph_host_preset(C.byref(t), preset.encode()) != 0:
+        raise ValueError(f"unknown preset {preset!r}")
+    return t
+
+
+def make_problem(n_request, tank_w=15.0, aspect=16.0 / 9.0, water_frac=1.0, nranks=1):
+    """Geometry of start_simulation (fluid.c:116-159) for a tank scaled to n_request particles."""
+    L = _host()
+    tank_w = float(np.float32(tank_w))
+    tank_h = float(np.float32(np.float32(tank_w) / np.float32(aspect)))
+    water_w = float(np.float32(np.float32(tank_w) * np.float32(water_frac)))
+    spacing = float(L.sph_host_spacing(water_w, tank_h, int(n_request)))
+    sc = np.zeros(nranks, "i4"); nc = np.zeros(nranks, "i4")
+    sx = np.zeros(nranks, "f4"); ex = np.zeros(nranks, "f4")
+    n_global = L.sph_host_partition(tank_w, 0.0, water_w, 0.0, tank_h, spacing, nranks, _p(sc), _p(nc), _p(sx), _p(ex))
+    return dict(tank_w=tank_w, tank_h=tank_h, water_w=water_w, spacing=spacing,
+                h=float(np.float32(2.0) * np.float32(spacing)), n_global=int(n_global), total_cols=int(nc.sum()),
+                slabs=[(int(sc[r]), int(nc[r]), float(sx[r]), float(ex[r])) for r in range(nranks)])
+
+
+def lattice(prob, rank=0):
+    """Initial particles of one slab (geometry.c:29-59) with persistent uids."""
+    L = _host()
+    sc, nc, _, _ = prob["slabs"][rank]
+    rows = int(np.floor(np.float32(prob["tank_h"]) / np.float32(prob["spacing"])))
+    a = np.zeros(nc * rows, PARTICLE); uid = np.zeros(nc * rows, "u4")
+    n = L.sph_host_lattice(0.0, 0.0, prob["tank_h"], prob["spacing"], sc, nc, prob["total_cols"], _p(a), _p(uid))
+    assert n == len(a)
+    return a, uid
+
+
+def balance(edges, counts, h):
+    """check_partition_left (renderer.c:427-477) on a list of (start_x, end_x); returns the new list."""
+    L = _host()
+    n = len(edges)
+    m = (Tunable * n)()
+    for r, (s, e) in enumerate(edges):
+        m[r].smoothing_radius = h; m[r].node_start_x = s; m[r].node_end_x = e
+    c = np.asarray(counts, "i4")
+    L.sph_host_balance(m, n, _p(c), int(c.sum()))
+    return [(float(m[r].node_start_x), float(m[r].node_end_x)) for r in range(n)]

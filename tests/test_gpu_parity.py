@@ -153,9 +153,10 @@ def test_full_size_properties(built_lib, n_request):
     """BASELINE.json sizes: properties that do not need the oracle to finish -- the sort is a
     permutation, cells are sorted, particles stay in the tank, nothing overflows -- plus a sampled
     neighbour-set and one-step comparison against the gather oracle at 100k."""
-    prob = make_problem(n_request, tank_w=15.0 * np.sqrt(n_request / 1500.0), water_frac=0.5)
+    prob = make_problem(n_request, tank_w=15.0 * np.sqrt(n_request / (1500.0 * 0.5)), water_frac=0.5)
     a, uid = lattice(prob)
     t = default_tunable(prob["h"], prob["tank_w"], prob["tank_h"])
+    t.mover_center_x = 0.75 * prob["tank_w"]      # parked in the dry half: no pile-up on its arc at t=0
     b = mk(prob["tank_w"], prob["tank_h"], prob["h"], len(a) + 1024)
     b.set_params(t); b.upload(a, uid)
     b.step(60)
