@@ -20,6 +20,17 @@
 // -------------------------------------------------------------------------------------------
 struct Rows { int b[3], e[3]; };
 
+// r and 1/r from the (exact, unfused) squared distance with one MUFU.RSQ instead of the IEEE sqrt +
+// divide sequences (~18 instructions).  Only the pair PHYSICS uses these; list membership is decided
+// on r2 itself, so neighbour sets stay bit-exact.  Relative error ~2^-22: orders of magnitude below
+// the stated parity tolerance.  r2 == 0 (coincident particles) gives r = 0, 1/r = +inf like the
+// reference's 1.0f/r.
+__device__ __forceinline__ void r_and_recip(float r2, float &r, float &r_recip)
+{
+    r_recip = rsqrtf(r2);
+    r = r2 > 0.0f ? r2 * r_recip : 0.0f;
+}
+
 __device__ __forceinline__ Rows candidate_rows(float2 p, const DevParams &P, const int *__restrict__ cell_start)
 {
     Rows r;
@@ -58,7 +69,7 @@ __device__ __forceinline__ void bin_position(int i, float2 p, int extra_bits, co
 //     + boundaryConditions (:656) + identify_oob_particles (:481) + ghost selection
 //     (communication.c:134-141) + first half of hash_fluid pass 1 (hash.c:153-166)
 // -------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(SPH_THREADS)
+__global__ void __launch_bounds__(SPH_THREADS, 4)
 k_advect(const DevParams *__restrict__ Pp, int *__restrict__ counters,
          const float2 *__restrict__ pos, const float2 *__restrict__ vel, const uint32_t *__restrict__ uid,
          const int *__restrict__ cell_start,
@@ -83,14 +94,17 @@ k_advect(const DevParams *__restrict__ Pp, int *__restrict__ counters,
         const Rows R = candidate_rows(p, P, cell_start);
 #pragma unroll
         for (int d = 0; d < 3; d++) {
+#pragma unroll 4
             for (int j = R.b[d]; j < R.e[d]; j++) {
                 const float2 q = pos[j];
                 const float dx = q.x - p.x, dy = q.y - p.y;
                 const float r2 = dist2(dx, dy);
-                if (r2 > h2 || j == i) continue;                        // list membership
+                if (r2 > h2) continue;                                  // list membership
+                // (the particle itself, r2 == 0, falls out below: 0 * inf = NaN fails u > 0, as does
+                //  any coincident neighbour in the reference, fluid.c:446-451)
                 const float2 vq = vel[j];
-                const float r = __fsqrt_rn(r2);
-                const float r_recip = __fdiv_rn(1.0f, r);
+                float r, r_recip;
+                r_and_recip(r2, r, r_recip);
                 const float ratio = r * h_recip;
                 const float u_in = ((vix - vq.x) * dx + (viy - (vq.y + gdt)) * dy) * r_recip;
                 if (u_in > 0.0f) {                                      // fluid.c:451-462 (r == 0 gives NaN: skipped)
@@ -411,13 +425,17 @@ k_density(const DevParams *__restrict__ Pp, int *__restrict__ counters,
         const Rows R = candidate_rows(p, P, cell_start);
 #pragma unroll
         for (int dd = 0; dd < 3; dd++) {
+#pragma unroll 4
             for (int j = R.b[dd]; j < R.e[dd]; j++) {
                 const float2 q = pos[j];
                 const float dx = q.x - p.x, dy = q.y - p.y;
                 const float r2 = dist2(dx, dy);
-                if (r2 > h2 || j == i) continue;
+                if (r2 > h2) continue;
+                if (r2 == 0.0f && j == i) continue;                     // self; coincident others do count (ratio 0)
                 nn++;
-                const float ratio = __fsqrt_rn(r2) * h_recip;
+                float r, r_recip;
+                r_and_recip(r2, r, r_recip);
+                const float ratio = r * h_recip;
                 if (ratio < 1.0f) {
                     const float omr = 1.0f - ratio;
                     const float omr2 = omr * omr;
@@ -438,7 +456,7 @@ k_density(const DevParams *__restrict__ Pp, int *__restrict__ counters,
 //     incl. boundaryConditions + second ghost selection (fluid.c:337) + binning for the re-hash
 //     (fluid.c:341).
 // -------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(SPH_THREADS)
+__global__ void __launch_bounds__(SPH_THREADS, 4)
 k_relax(const DevParams *__restrict__ Pp, int *__restrict__ counters,
         const float2 *__restrict__ pos, const float2 *__restrict__ prev, const uint32_t *__restrict__ uid,
         const float2 *__restrict__ dens, const int *__restrict__ cell_start,
@@ -466,14 +484,16 @@ k_relax(const DevParams *__restrict__ Pp, int *__restrict__ counters,
         const Rows R = candidate_rows(p, P, cell_start);
 #pragma unroll
         for (int d = 0; d < 3; d++) {
+#pragma unroll 4
             for (int j = R.b[d]; j < R.e[d]; j++) {
                 const float2 q = pos[j];
                 const float dx = q.x - p.x, dy = q.y - p.y;
                 const float r2 = dist2(dx, dy);
-                if (r2 > h2 || j == i) continue;
-                const float r = __fsqrt_rn(r2);
+                if (r2 > h2) continue;
+                float r, r_recip;
+                r_and_recip(r2, r, r_recip);
                 const float ratio = r * h_recip;
-                if (r <= 0.000001f) {
+                if (r <= 0.000001f && j != i) {
                     // coincident particles: only the list owner is nudged (fluid.c:583-586); owner =
                     // earlier bucket slot in the same cell, else the cell whose forward stencil
                     // (0,+1),(1,-1),(1,0),(1,+1) holds the other (hash.c:178-224)
@@ -486,7 +506,6 @@ k_relax(const DevParams *__restrict__ Pp, int *__restrict__ counters,
                     const float pq = P.k * (dj.x - P.rest_density);
                     const float pqn = P.k_near * dj.y;
                     const float omr = 1.0f - ratio;
-                    const float r_recip = __fdiv_rn(1.0f, r);
                     // fluid.c:591; the reference's fp64 tail is evaluated in fp32 here (<= 1 ulp of D)
                     const float D = dt2 * ((pp + pq) * omr + (ppn + pqn) * omr * omr + P.k_spring * (h - r) * 0.5f);
                     x -= D * dx * r_recip;

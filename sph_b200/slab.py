@@ -1,0 +1,190 @@
+"""Multi-rank driver: one process per GPU, one x-slab per process (communication.c's design).
+
+torch.distributed is the plumbing (NCCL on the GPU box, gloo in the CPU tests): it moves the
+fixed-size neighbour messages whose packing is fused into the advect/relax kernels and whose
+unpacking is fused into the sort (include/sph_b200.h, "slab exchange").  Per step:
+
+    advect -> exchange 0 (migrants + predicted-position ghosts) -> sort -> density -> relax
+           -> exchange 1 (relaxed position + velocity ghosts)   -> sort
+
+which replaces transferOOBParticles + 2 x start/finishHaloExchange + 2 x hash_halo
+(fluid.c:310-348).  Once per frame (every `steps_per_frame` steps, at the sub-step where the
+reference's MPI_Scatterv lands, fluid.c:293-294) all ranks share their particle counts and run the
+reference's edge balancer (renderer.c:427-477) on identical inputs, so every rank derives the same
+new edges without a coordinator.
+"""
+import time
+
+import numpy as np
+
+
+class _CudaBytes:
+    """Zero-copy view of a device pointer for torch.as_tensor."""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+
+class SlabRunner:
+    def __init__(self, prob, tunable, rank, world, stream=None, capacity_factor=2.0, backend=None,
+                 msg_capacity=None, steps_per_frame=4, balance=True, group=None):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.prob, self.rank, self.world, self.group = prob, rank, world, group
+        self.steps_per_frame, self.do_balance = steps_per_frame, balance
+        self.sub_step = 0
+        self.stream = stream
+        self.t = tunable.copy()
+        self.edges = [(s, e) for (_, _, s, e) in prob["slabs"]]
+        self.t.node_start_x, self.t.node_end_x = self.edges[rank]
+        n_slab = max(nc for (_, nc, _, _) in prob["slabs"]) * int(np.floor(np.float32(prob["tank_h"]) / np.float32(prob["spacing"])))
+        rows = int(np.floor(np.float32(prob["tank_h"]) / np.float32(prob["spacing"])))
+        # ghost layer 2h wide = ~4 lattice columns at rest; settle-time compression and migrants: x6
+        self.msg_capacity = int(msg_capacity or max(4096, 6 * 5 * rows))
+        self.capacity = int(capacity_factor * n_slab) + 4 * self.msg_capacity
+        if backend is None:
+            import sph_b200
+            self.sph = sph_b200
+            self.ctx = sph_b200.Context(prob["tank_w"], prob["tank_h"], prob["h"], self.capacity,
+                                        msg_capacity=self.msg_capacity, device=torch.cuda.current_device(),
+                                        rank=rank, nranks=world,
+                                        stream=stream.cuda_stream if stream is not None else None)
+            self.cuda = True
+        else:
+            self.ctx = backend(prob["tank_w"], prob["tank_h"], prob["h"], self.capacity, self.msg_capacity, rank, world)
+            self.cuda = False
+        self.ctx.set_params(self.t)
+        self.has_left, self.has_right = rank > 0, rank < world - 1
+        self._bufs = {}
+        self.counts = None
+        self.exchange_s = 0.0
+
+    # -------------------------------------------------------------------------------- plumbing
+    def _buffers(self, which):
+        if which not in self._bufs:
+            torch = self.torch
+            if self.cuda:
+                ptrs, nb = self.ctx.exchange_pointers(which)
+                self._bufs[which] = [torch.as_tensor(_CudaBytes(p, nb), device="cuda") for p in ptrs]
+            else:
+                self._bufs[which] = [torch.from_numpy(a) for a in self.ctx.exchange_buffers(which)]
+        return self._bufs[which]
+
+    def exchange(self, which):
+        dist = self.dist
+        send_l, recv_l, send_r, recv_r = self._buffers(which)
+        ops = []
+        if self.has_right:
+            ops += [dist.P2POp(dist.isend, send_r, self.rank + 1, self.group),
+                    dist.P2POp(dist.irecv, recv_r, self.rank + 1, self.group)]
+        if self.has_left:
+            ops += [dist.P2POp(dist.isend, send_l, self.rank - 1, self.group),
+                    dist.P2POp(dist.irecv, recv_l, self.rank - 1, self.group)]
+        if ops:
+            for r in dist.batch_isend_irecv(ops):
+                r.wait()
+
+    def gather_counts(self):
+        torch, dist = self.torch, self.dist
+        n = self.ctx.status().n_local
+        dev = "cuda" if self.cuda else "cpu"
+        mine = torch.tensor([n], dtype=torch.int32, device=dev)
+        out = [torch.zeros(1, dtype=torch.int32, device=dev) for _ in range(self.world)]
+        dist.all_gather(out, mine, group=self.group)
+        return [int(x.item()) for x in out]
+
+    def rebalance(self):
+        """check_partition_left on identical inputs on every rank; the new edges are queued so that they
+        land between prediction and migration of the coming step (fluid.c:293-310)."""
+        import sph_b200
+        counts = self.gather_counts()
+        self.counts = counts
+        # the reference feeds coordinate counts (2 per particle) on both sides of the ratio (renderer.c:280,290)
+        self.edges = sph_b200.balance(self.edges, [2 * c for c in counts], self.prob["h"])
+        self.t.node_start_x, self.t.node_end_x = self.edges[self.rank]
+        self.ctx.queue_params(self.t)
+
+    # -------------------------------------------------------------------------------- simulation
+    def init_lattice(self):
+        if self.cuda:
+            a, uid = self.sph.lattice(self.prob, self.rank)
+        else:
+            import sph_b200
+            a, uid = sph_b200.lattice(self.prob, self.rank)
+        self.ctx.upload(a, uid)
+
+    def step_once(self):
+        if self.do_balance and self.world > 1 and self.sub_step == self.steps_per_frame - 1:
+            self.rebalance()
+        c = self.ctx
+        c.advect()
+        self.exchange(0)
+        c.sort()
+        c.density()
+        c.relax()
+        self.exchange(1)
+        c.sort()
+        self.sub_step = (self.sub_step + 1) % self.steps_per_frame
+
+    def run(self, n):
+        for _ in range(n):
+            self.step_once()
+
+    # -------------------------------------------------------------------------------- bench hooks
+    @property
+    def launches(self):
+        return self.ctx.launches
+
+    def stage_times(self, nsteps, flush_buf):
+        torch = self.torch
+        names = ("advect", "exchange0", "sort1", "density", "relax", "exchange1", "sort2")
+        acc = {k: 0.0 for k in names}
+        c = self.ctx
+        for _ in range(nsteps):
+            flush_buf.zero_()
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(8)]
+            ev[0].record(self.stream); c.advect()
+            ev[1].record(self.stream); self.exchange(0)
+            ev[2].record(self.stream); c.sort()
+            ev[3].record(self.stream); c.density()
+            ev[4].record(self.stream); c.relax()
+            ev[5].record(self.stream); self.exchange(1)
+            ev[6].record(self.stream); c.sort()
+            ev[7].record(self.stream)
+            torch.cuda.synchronize()
+            for i, k in enumerate(names):
+                acc[k] += ev[i].elapsed_time(ev[i + 1])
+        out = {k: v / nsteps for k, v in acc.items()}
+        self._exchange_ms = out.pop("exchange0") + out.pop("exchange1")
+        out["exchange"] = self._exchange_ms
+        return {k: v for k, v in out.items()}
+
+    def kernel_name(self, stage):
+        return {"advect": "k_advect", "density": "k_density", "relax": "k_relax", "exchange": "nccl send/recv",
+                "sort1": "k_unpack+k_scan+k_scatter+k_reorder", "sort2": "k_unpack+k_scan+k_scatter+k_reorder"}[stage]
+
+    def e2e(self, frames, flush_buf):
+        """Frames with host buffers: parameter block H2D (queued, lands at the last sub-step), 4 steps, the
+        slab's int16 coordinates D2H into pinned memory (fluid.c:354-365)."""
+        torch = self.torch
+        coords = torch.empty(2 * self.capacity, dtype=torch.int16).pin_memory().numpy()
+        secs, n = 0.0, 0
+        for f in range(frames + 1):
+            flush_buf.zero_()
+            torch.cuda.synchronize()
+            self.dist.barrier()
+            t0 = time.perf_counter()
+            self.run(self.steps_per_frame)
+            n = self.ctx.L.sph_pack_coords(self.ctx.h, coords.ctypes.data, self.capacity)
+            if f > 0:
+                secs += time.perf_counter() - t0
+        return {"seconds": secs, "steps": self.steps_per_frame * frames, "h2d_per_step": 64 / self.steps_per_frame,
+                "d2h_per_step": 4 * n / self.steps_per_frame}
+
+    def stats(self):
+        s = self.ctx.status()
+        npairs = self.ctx.L.sph_get_pairs(self.ctx.h, None, 0) if self.cuda else 0
+        return {"n_local": s.n_local, "n_halo": s.n_halo, "max_bucket": s.max_bucket,
+                "mean_neighbours": 2.0 * npairs / max(s.n_local + s.n_halo, 1),
+                "capacity_overflow": s.capacity_overflow, "msg_overflow": s.msg_overflow}

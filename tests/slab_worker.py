@@ -1,0 +1,44 @@
+"""One rank of the CPU (gloo) slab test: the multi-rank driver sph_b200.slab.SlabRunner with the gather
+oracle standing in for the CUDA library.  Launched by test_slab_gloo.py, one process per rank."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    import torch.distributed as dist
+
+    from oracle.oracle import GatherOracle, default_tunable, make_problem
+    from sph_b200.slab import SlabRunner
+
+    out, n_req, steps, balance = sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4])
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    prob = make_problem(n_req, nranks=world)
+    t = default_tunable(prob["h"], prob["tank_w"], prob["tank_h"])
+
+    def backend(tw, th, h, cap, msg, r, w):
+        return GatherOracle(tw, th, h, cap, msg, r, w)
+
+    sim = SlabRunner(prob, t, rank, world, backend=backend, balance=bool(balance))
+    sim.init_lattice()
+    history = []
+    for s in range(steps):
+        sim.step_once()
+        if s % 20 == 19:
+            st = sim.ctx.status()
+            history.append((st.n_local, st.n_halo, sim.edges[rank][0], sim.edges[rank][1]))
+    a, uid = sim.ctx.download()
+    st = sim.ctx.status()
+    np.savez(f"{out}.rank{rank}.npz", state=a, uid=uid, history=np.array(history, "f8"),
+             overflow=np.array([st.capacity_overflow, st.msg_overflow]), edges=np.array(sim.edges, "f8"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
