@@ -30,7 +30,7 @@ def build(force=False, verbose=False):
     objs = []
     for src in hc:
         o = os.path.join(bdir, os.path.basename(src) + ".o")
-        subprocess.check_call(["gcc", "-std=gnu99", "-O2", "-fPIC", "-Wall", "-I", inc, "-c", src, "-o", o])
+        subprocess.check_call(["gcc", "-std=gnu99", "-O2", "-ffp-contract=off", "-fPIC", "-Wall", "-I", inc, "-c", src, "-o", o])
         objs.append(o)
     cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-I", inc, "-shared", "-o", out] + cu + objs
     subprocess.check_call(cmd)

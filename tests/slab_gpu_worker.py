@@ -1,0 +1,52 @@
+"""One rank of the multi-GPU slab test (NCCL): dam-break block, migration + ghosts + rebalancing.
+Rank 0 also runs the same problem on one GPU alone for the bit-for-bit comparison."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+
+    import sph_b200
+    from sph_b200.slab import SlabRunner
+
+    out, n_req, steps = sys.argv[1], int(sys.argv[2]), int(sys.argv[3])
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
+    dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ["LOCAL_RANK"])))
+    tank_w = 15.0 * float(np.sqrt(n_req / (1500.0 * 0.5)))
+    prob = sph_b200.make_problem(n_req, tank_w=tank_w, water_frac=0.5, nranks=world)
+    t = sph_b200.default_params(prob["h"], prob["tank_w"], prob["tank_h"])
+    t.mover_center_x = 0.4 * prob["tank_w"]          # in the path of the collapsing block
+    stream = torch.cuda.Stream()
+    with torch.cuda.stream(stream):
+        sim = SlabRunner(prob, t, rank, world, stream)
+        sim.init_lattice()
+        sim.run(steps)
+        a, uid = sim.ctx.download()
+        st = sim.ctx.status()
+    np.savez(f"{out}.rank{rank}.npz", state=a, uid=uid, overflow=np.array([st.capacity_overflow, st.msg_overflow]),
+             edges=np.array(sim.edges, "f8"))
+    if rank == 0:
+        p1 = sph_b200.make_problem(n_req, tank_w=tank_w, water_frac=0.5, nranks=1)
+        ctx = sph_b200.Context(p1["tank_w"], p1["tank_h"], p1["h"], p1["n_global"] + 64)
+        t1 = sph_b200.default_params(p1["h"], p1["tank_w"], p1["tank_h"]); t1.mover_center_x = 0.4 * p1["tank_w"]
+        ctx.set_params(t1)
+        a1, u1 = sph_b200.lattice(p1)
+        ctx.upload(a1, u1)
+        ctx.step(steps)
+        s1, su = ctx.download()
+        np.savez(f"{out}.single.npz", state=s1, uid=su)
+        print("edges", sim.edges, "counts", sim.counts)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
