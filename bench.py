@@ -178,6 +178,11 @@ def main_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries exactly one JSON line: libraries that chat on fd 1 (NCCL prints its version there)
+    # are sent to stderr until the result is printed
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; sph_b200 has no CPU path")
     torch.cuda.set_device(local_rank)
@@ -295,7 +300,10 @@ def main_ours(args):
             except Exception as e:  # the baseline is reported, never fatal
                 line["cpu_baseline"] = {"value": None, "unit": "particle-steps/s", "cores": 0, "kind": "reference",
                                         "sample": f"failed: {e}"}
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -118,6 +118,10 @@ const char *sph_last_error(const sph_ctx *ctx);
 int sph_synchronize(sph_ctx *ctx);
 int sph_get_status(sph_ctx *ctx, sph_status *out);
 
+/* Stream-ordered copy of the local particle count (one int) to DEVICE memory, without synchronising:
+ * what a multi-rank driver all-gathers once per frame for the edge balancer (renderer.c:280,290). */
+int sph_copy_n_local(sph_ctx *ctx, void *device_dst);
+
 /* ---- parameters ---- */
 /* Full tunable block, as the render rank scatters it (fluid.c:293-294). Stream-ordered. */
 int sph_set_params(sph_ctx *ctx, const sph_tunable *t);
@@ -160,6 +164,14 @@ int sph_exchange_buffers(sph_ctx *ctx, int which, void **send_left, void **recv_
                          void **send_right, void **recv_right, size_t *bytes);
 /* Mark a neighbour as absent for the coming sort (edge slabs): its recv buffer is ignored. */
 int sph_set_neighbors(sph_ctx *ctx, int has_left, int has_right);
+
+/* Peer-memory transport (one process per GPU on one NVLink/NVSwitch box).  Each rank publishes the
+ * 64-byte cudaIpc handle of its exchange block; after sph_p2p_connect the pack code of advect/relax
+ * stores outgoing records straight into the neighbour's block and releases an arrival flag, and the
+ * sort waits for the neighbours' flags on the device.  No transport calls, no host synchronisation:
+ * sph_step() then works for slabs too (one CUDA graph per step).  Pass NULL for an absent side. */
+int sph_p2p_local_handle(sph_ctx *ctx, void *handle64);
+int sph_p2p_connect(sph_ctx *ctx, const void *left_handle64, const void *right_handle64);
 
 /* ---- parity / inspection ---- */
 /* per local particle: uid and hash_val cell id in the reference's GLOBAL grid numbering */

@@ -60,7 +60,7 @@ C_ABI_SYMBOLS = (
     "sph_set_params", "sph_queue_params", "sph_set_edges", "sph_upload", "sph_download",
     "sph_advect", "sph_sort", "sph_density", "sph_relax", "sph_step", "sph_exchange_buffers",
     "sph_set_neighbors", "sph_get_cells", "sph_get_pairs", "sph_get_forward_counts",
-    "sph_pack_coords", "sph_launch_count", "sph_run_frame",
+    "sph_pack_coords", "sph_launch_count", "sph_run_frame", "sph_p2p_local_handle", "sph_p2p_connect", "sph_copy_n_local",
 )
 
 _lib = None
@@ -99,6 +99,9 @@ def lib():
         L.sph_get_forward_counts.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         L.sph_pack_coords.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         L.sph_run_frame.argtypes = [C.c_void_p, C.POINTER(Tunable), C.c_int, C.c_void_p, C.c_int]
+        L.sph_copy_n_local.argtypes = [C.c_void_p, C.c_void_p]
+        L.sph_p2p_local_handle.argtypes = [C.c_void_p, C.c_void_p]
+        L.sph_p2p_connect.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.sph_exchange_buffers.argtypes = [C.c_void_p, C.c_int] + [C.POINTER(C.c_void_p)] * 4 + [C.POINTER(C.c_size_t)]
         _lib = L
     return _lib
@@ -184,6 +187,20 @@ class Context:
         self._ck(self.L.sph_exchange_buffers(self.h, which, *[C.byref(p) for p in ptr], C.byref(nb)),
                  "sph_exchange_buffers")
         return [p.value for p in ptr], nb.value
+
+    def copy_n_local(self, device_ptr):
+        self._ck(self.L.sph_copy_n_local(self.h, device_ptr), "sph_copy_n_local")
+
+    def p2p_handle(self):
+        """64-byte cudaIpc handle of this rank's exchange block."""
+        buf = C.create_string_buffer(64)
+        self._ck(self.L.sph_p2p_local_handle(self.h, buf), "sph_p2p_local_handle")
+        return bytes(buf.raw)
+
+    def p2p_connect(self, left, right):
+        l = C.create_string_buffer(left, 64) if left else None
+        r = C.create_string_buffer(right, 64) if right else None
+        self._ck(self.L.sph_p2p_connect(self.h, l, r), "sph_p2p_connect")
 
     def cells(self):
         u = np.zeros(self.capacity, "u4"); c = np.zeros(self.capacity, "u4")

@@ -31,6 +31,9 @@ struct sph_ctx {
     uint32_t *ord_uid;
     unsigned long long *tile_state;
     unsigned char *send[2], *recv[2];
+    unsigned char *xchg;             // exchange block for peer-memory mode (flags + 8 message buffers)
+    void *peer[2];                   // neighbours' exchange blocks mapped with cudaIpcOpenMemHandle
+    int scan_grid;                   // tiles of the widest possible window
     short2 *coords;
     int stage;
     int grid;
@@ -144,6 +147,9 @@ extern "C" int sph_create(const sph_config *cfg, sph_ctx **out)
         CK(cudaMemset(ctx->send[s], 0, mb));
         CK(cudaMemset(ctx->recv[s], 0, mb));
     }
+    CK(cudaMalloc(&ctx->xchg, xchg_bytes(ctx->cfg.msg_capacity)));
+    CK(cudaMemset(ctx->xchg, 0, xchg_bytes(ctx->cfg.msg_capacity)));
+    ctx->scan_grid = (int)((ncell_max + SCAN_TILE - 1) / SCAN_TILE);
     CK(cudaMalloc(&ctx->dp, sizeof(DevParams)));
 
     DevParams &P = ctx->hp;
@@ -152,6 +158,7 @@ extern "C" int sph_create(const sph_config *cfg, sph_ctx **out)
     P.halo_w = ctx->cfg.halo_width * cfg->h;
     P.has_left = cfg->rank > 0; P.has_right = cfg->rank < cfg->nranks - 1; P.nranks = cfg->nranks;
     P.cap = cfg->capacity; P.msg_cap = ctx->cfg.msg_capacity;
+    P.p2p = 0; P.xchg_base = (unsigned long long)ctx->xchg; P.remote_base[0] = P.remote_base[1] = 0;
     P.h = cfg->h; P.dt = 1.0f / 120.0f; P.mover_type = -1;
     fill_edges(ctx, 0.0f, cfg->tank_w);
     P.gx0 = P.gx0_new; P.wx = P.wx_new;
@@ -174,6 +181,8 @@ extern "C" void sph_destroy(sph_ctx *ctx)
     cudaFree(ctx->t_slot); cudaFree(ctx->ord_src); cudaFree(ctx->ord_uid); cudaFree(ctx->coords);
     cudaFree(ctx->tile_state); cudaFree(ctx->counters); cudaFree(ctx->dp);
     for (int s = 0; s < 2; s++) { cudaFree(ctx->send[s]); cudaFree(ctx->recv[s]); }
+    for (int s = 0; s < 2; s++) if (ctx->peer[s]) cudaIpcCloseMemHandle(ctx->peer[s]);
+    cudaFree(ctx->xchg);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -231,6 +240,36 @@ extern "C" int sph_exchange_buffers(sph_ctx *ctx, int which, void **sl, void **r
 }
 
 // ------------------------------------------------------------------------------------------
+// peer-memory exchange: neighbours map each other's exchange block (cudaIpc) and the pack code in
+// k_advect / k_relax stores outgoing records straight into it over NVLink
+// ------------------------------------------------------------------------------------------
+extern "C" int sph_p2p_local_handle(sph_ctx *ctx, void *handle64)
+{
+    if (!ctx || !handle64) return SPH_ERR_ARG;
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, ctx->xchg));
+    static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    memcpy(handle64, &h, 64);
+    return SPH_OK;
+}
+
+extern "C" int sph_p2p_connect(sph_ctx *ctx, const void *left_handle64, const void *right_handle64)
+{
+    if (!ctx) return SPH_ERR_ARG;
+    const void *hs[2] = {left_handle64, right_handle64};
+    for (int s = 0; s < 2; s++) {
+        if (!hs[s]) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, hs[s], 64);
+        CK(cudaIpcOpenMemHandle(&ctx->peer[s], h, cudaIpcMemLazyEnablePeerAccess));
+        ctx->hp.remote_base[s] = (unsigned long long)ctx->peer[s];
+    }
+    ctx->hp.p2p = 1;
+    if (ctx->graph_ready) { cudaGraphExecDestroy(ctx->graph); ctx->graph_ready = false; }
+    return push_params(ctx);
+}
+
+// ------------------------------------------------------------------------------------------
 // stage launches.  Buffer roles (period-1 rotation, so one captured graph is a whole step):
 //   READY    : pos P0, vel Q0, uid U0 (cell-sorted)
 //   advect   : reads P0,Q0,U0            writes predicted pos P1 (source order)
@@ -248,15 +287,16 @@ static int launch_sort(sph_ctx *ctx, int which, bool with_unpack = true)
     float2 *dq = which == 0 ? ctx->Q[1] : ctx->Q[0];
     uint32_t *du = which == 0 ? ctx->U[1] : ctx->U[0];
     if (ctx->cfg.nranks > 1 && with_unpack) {
-        k_unpack<<<ctx->grid, SPH_THREADS, 0, ctx->stream>>>(ctx->dp, ctx->counters, which, ctx->recv[0], ctx->recv[1],
+        k_unpack<<<ctx->grid, SPH_THREADS, 0, ctx->stream>>>(ctx->dp, ctx->counters, which, ctx->send[0], ctx->send[1],
+                                                             ctx->recv[0], ctx->recv[1],
                                                              sp, sq, su, ctx->cnt, ctx->t_key, ctx->t_slot);
         ctx->launches++;
     }
-    const int ncell = ctx->hp.wx_new * ctx->size_y;
-    const int ntiles = (ncell + SCAN_TILE - 1) / SCAN_TILE;
-    k_scan<<<ntiles, SPH_THREADS, 0, ctx->stream>>>(ctx->dp, ctx->counters, ctx->cnt, ctx->cell_start, ctx->tile_state,
-                                                    ctx->cfg.nranks > 1 ? ctx->send[0] : nullptr,
-                                                    ctx->cfg.nranks > 1 ? ctx->send[1] : nullptr);
+    // grid sized for the widest window: a captured graph survives moving slab edges
+    k_scan<<<ctx->scan_grid, SPH_THREADS, 0, ctx->stream>>>(ctx->dp, ctx->counters, ctx->cnt, ctx->cell_start, ctx->tile_state,
+                                                            ctx->cfg.nranks > 1 ? ctx->send[0] : nullptr,
+                                                            ctx->cfg.nranks > 1 ? ctx->send[1] : nullptr,
+                                                            (which == 1 && with_unpack) ? 1 : 0);
     k_scatter<<<ctx->grid, SPH_THREADS, 0, ctx->stream>>>(ctx->counters, ctx->cell_start, ctx->t_key, ctx->t_slot, su,
                                                           ctx->ord_uid, ctx->ord_src);
     k_reorder<<<ctx->grid, SPH_THREADS, 0, ctx->stream>>>(ctx->dp, ctx->counters, ctx->cell_start, ctx->t_key,
@@ -361,7 +401,8 @@ static int launch_step(sph_ctx *ctx)
 extern "C" int sph_step(sph_ctx *ctx, int n)
 {
     if (!ctx || n < 0) return SPH_ERR_ARG;
-    if (ctx->cfg.nranks != 1) return fail(ctx, SPH_ERR_STATE, "sph_step: slabs with neighbours step stage by stage");
+    if (ctx->cfg.nranks != 1 && !ctx->hp.p2p)
+        return fail(ctx, SPH_ERR_STATE, "sph_step: slabs need sph_p2p_connect (or step stage by stage around a transport)");
     if (ctx->stage != ST_READY) return fail(ctx, SPH_ERR_STATE, "sph_step: state is not at a step boundary");
     int rc;
     for (int s = 0; s < n; s++) {
@@ -384,7 +425,7 @@ extern "C" int sph_step(sph_ctx *ctx, int n)
             ctx->graph_ready = true;
         }
         CK(cudaGraphLaunch(ctx->graph, ctx->stream));
-        ctx->launches += 9;
+        ctx->launches += ctx->cfg.nranks > 1 ? 11 : 9;
         ctx->steps++;
     }
     return SPH_OK;
@@ -417,6 +458,8 @@ extern "C" int sph_upload(sph_ctx *ctx, const sph_particle *aos, const uint32_t 
     CK(cudaMemcpyAsync(ctx->counters, zero, sizeof zero, cudaMemcpyHostToDevice, ctx->stream));
     const size_t ncell_max = (size_t)ctx->size_x * ctx->size_y;
     CK(cudaMemsetAsync(ctx->cnt, 0, (ncell_max + 1) * sizeof(int), ctx->stream));
+    CK(cudaMemsetAsync(ctx->xchg, 0, SPH_XCHG_HDR, ctx->stream));      // message sequence numbers restart
+    for (int s = 0; s < 2; s++) CK(cudaMemsetAsync(ctx->send[s], 0, 16, ctx->stream));
     int rc = push_params(ctx);
     if (rc) return rc;
     k_bin_upload<<<ctx->grid, SPH_THREADS, 0, ctx->stream>>>(ctx->dp, ctx->counters, ctx->P[3], ctx->cnt, ctx->t_key, ctx->t_slot);
@@ -480,6 +523,13 @@ extern "C" int sph_download(sph_ctx *ctx, sph_particle *aos, uint32_t *uid_out, 
         if (uid_out) uid_out[k] = u[i];
     }
     return (int)idx.size();
+}
+
+extern "C" int sph_copy_n_local(sph_ctx *ctx, void *device_dst)
+{
+    if (!ctx || !device_dst) return SPH_ERR_ARG;
+    CK(cudaMemcpyAsync(device_dst, ctx->counters + CN_NLOCAL, sizeof(int), cudaMemcpyDeviceToDevice, ctx->stream));
+    return SPH_OK;
 }
 
 extern "C" int sph_get_status(sph_ctx *ctx, sph_status *out)

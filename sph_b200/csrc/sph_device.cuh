@@ -28,6 +28,11 @@ struct DevParams {
     int gx0, wx;
     int gx0_new, wx_new;
     int cap, msg_cap;
+    // peer-memory exchange (NVLink): this rank's exchange block and the neighbours' blocks as mapped
+    // into this process (cudaIpc); 0 = use the local send/recv buffers and an external transport
+    int p2p;
+    unsigned long long xchg_base;
+    unsigned long long remote_base[2];
 };
 
 // device-side counters (ints); indices below
@@ -40,6 +45,8 @@ enum {
     CN_TICKET, CN_DONE, // scan bookkeeping
     CN_COORDS,          // pack_coords compaction cursor
     CN_EPOCH,           // scan epoch (so tile flags never need clearing)
+    CN_STEP,            // completed steps (message sequence numbers and buffer parity)
+    CN_PUB,             // blocks that finished packing (last one publishes the message)
     CN_COUNT = 16
 };
 
@@ -52,6 +59,31 @@ __device__ __forceinline__ float2 *msg_b(unsigned char *b, int m) { return (floa
 __device__ __forceinline__ uint32_t *msg_u(unsigned char *b, int m) { return (uint32_t *)(b + 16 + (size_t)m * 16); }
 __device__ __forceinline__ float2 *msg_hp(unsigned char *b, int m) { return (float2 *)(b + 16 + (size_t)m * 20); } // halo-0 pos
 __device__ __forceinline__ uint32_t *msg_hu(unsigned char *b, int m) { return (uint32_t *)(b + 16 + (size_t)m * 28); }
+
+// Exchange block of one rank (peer-memory mode): 4 arrival flags, then one message buffer per
+// (side it arrives from, which exchange, step parity).  Double buffering by step parity is enough:
+// a neighbour can only be one exchange ahead, because each of its sorts waits for this rank's message.
+#define SPH_XCHG_HDR 256
+__host__ __device__ inline size_t xchg_msg_stride(int m) { return (msg_bytes_full(m) + 255) & ~(size_t)255; }
+__host__ __device__ inline size_t xchg_offset(int side, int which, int parity, int m)
+{
+    return SPH_XCHG_HDR + (size_t)((side * 2 + which) * 2 + parity) * xchg_msg_stride(m);
+}
+__host__ __device__ inline size_t xchg_bytes(int m) { return SPH_XCHG_HDR + 8 * xchg_msg_stride(m); }
+__device__ __forceinline__ int *xchg_flag(unsigned long long base, int side, int which)
+{
+    return (int *)(base + (size_t)(side * 2 + which) * 16);
+}
+__device__ __forceinline__ int ld_acquire_sys(const int *p)
+{
+    int v;
+    asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(int *p, int v)
+{
+    asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 
 // hash_val (hash.c:35-47): IEEE fp32 divide, floor; kept as two coordinates
 __device__ __forceinline__ int cell_coord(float v, float cell_h) { return (int)floorf(__fdiv_rn(v, cell_h)); }

@@ -49,6 +49,70 @@ __device__ __forceinline__ Rows candidate_rows(float2 p, const DevParams &P, con
     return r;
 }
 
+
+// -------------------------------------------------------------------------------------------
+// Peer-memory exchange.  The compute kernels (k_advect, k_relax) append outgoing records to a compact
+// LOCAL message; the first kernel of the following sort (k_unpack) then (1) copies that message into
+// the neighbour GPU's exchange block over NVLink with coalesced stores spread over the whole grid,
+// (2) the last block to finish releases the neighbour's arrival flag with system scope, and (3) every
+// block waits for this rank's own arrival flags before unpacking.  Both neighbours send before they
+// wait, so there is no deadlock; nothing goes through the host or a collective library.
+// (Storing each record remotely from inside the compute kernels was tried first: the scattered 8-byte
+// NVLink stores lengthened k_advect/k_relax by 30-45 us.)
+// -------------------------------------------------------------------------------------------
+__device__ __forceinline__ void copy_words(unsigned char *dst, const unsigned char *src, size_t off, int nwords,
+                                           int gtid, int gstride, bool &wrote)
+{
+    const int *s = (const int *)(src + off);
+    int *d = (int *)(dst + off);
+    for (int w = gtid; w < nwords; w += gstride) { d[w] = s[w]; wrote = true; }
+}
+
+__device__ __forceinline__ void send_messages(const DevParams &P, int *counters, int which, int step,
+                                              unsigned char *send_l, unsigned char *send_r)
+{
+    unsigned char *local[2] = {send_l, send_r};
+    const int present[2] = {P.has_left, P.has_right};
+    const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gstride = gridDim.x * blockDim.x;
+    const int m = P.msg_cap;
+    bool wrote = false;
+    for (int s = 0; s < 2; s++) {
+        if (!present[s]) continue;
+        // it arrives at the neighbour from the opposite side
+        unsigned char *remote = (unsigned char *)(P.remote_base[s] + xchg_offset(1 - s, which, step & 1, m));
+        const int n_mig = which == 0 ? min(msg_hdr(local[s])[0], m) : 0;
+        const int n_halo = min(msg_hdr(local[s])[1], m);
+        if (which == 0) {
+            copy_words(remote, local[s], 16, n_mig * 2, gtid, gstride, wrote);                      // migrant pos
+            copy_words(remote, local[s], 16 + (size_t)m * 8, n_mig * 2, gtid, gstride, wrote);      // migrant x_prev
+            copy_words(remote, local[s], 16 + (size_t)m * 16, n_mig, gtid, gstride, wrote);         // migrant uid
+            copy_words(remote, local[s], 16 + (size_t)m * 20, n_halo * 2, gtid, gstride, wrote);    // ghost pos
+            copy_words(remote, local[s], 16 + (size_t)m * 28, n_halo, gtid, gstride, wrote);        // ghost uid
+        } else {
+            copy_words(remote, local[s], 16, n_halo * 2, gtid, gstride, wrote);                     // ghost pos
+            copy_words(remote, local[s], 16 + (size_t)m * 8, n_halo * 2, gtid, gstride, wrote);     // ghost vel
+            copy_words(remote, local[s], 16 + (size_t)m * 16, n_halo, gtid, gstride, wrote);        // ghost uid
+        }
+    }
+    // only blocks that stored remotely pay for a system-scope fence
+    const int any = __syncthreads_or(wrote ? 1 : 0);
+    if (threadIdx.x == 0) {
+        if (any) __threadfence_system(); else __threadfence();
+        if (atomicAdd(&counters[CN_PUB], 1) == (int)gridDim.x - 1) {
+            counters[CN_PUB] = 0;
+            __threadfence_system();
+            for (int s = 0; s < 2; s++) {
+                if (!present[s]) continue;
+                int *rh = msg_hdr((unsigned char *)(P.remote_base[s] + xchg_offset(1 - s, which, step & 1, m)));
+                rh[0] = which == 0 ? min(msg_hdr(local[s])[0], m) : 0;
+                rh[1] = min(msg_hdr(local[s])[1], m);
+                __threadfence_system();
+                st_release_sys(xchg_flag(P.remote_base[s], 1 - s, which), 2 * step + which + 1);
+            }
+        }
+    }
+}
+
 // bin a freshly produced position for the coming sort: key, arrival slot, cell population
 __device__ __forceinline__ void bin_position(int i, float2 p, int extra_bits, const DevParams &P,
                                              int *__restrict__ cnt, int *__restrict__ t_key,
@@ -162,7 +226,7 @@ k_advect(const DevParams *__restrict__ Pp, int *__restrict__ counters,
 // -------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(SPH_THREADS)
 k_unpack(const DevParams *__restrict__ Pp, int *__restrict__ counters, int which,
-         unsigned char *recv_l, unsigned char *recv_r,
+         unsigned char *send_l, unsigned char *send_r, unsigned char *recv_l, unsigned char *recv_r,
          float2 *__restrict__ src_pos, float2 *__restrict__ src_q, uint32_t *__restrict__ src_uid,
          int *__restrict__ cnt, int *__restrict__ t_key, int *__restrict__ t_slot)
 {
@@ -171,10 +235,35 @@ k_unpack(const DevParams *__restrict__ Pp, int *__restrict__ counters, int which
     int n_mig[2] = {0, 0}, n_halo[2] = {0, 0};
     unsigned char *buf[2] = {recv_l, recv_r};
     const int present[2] = {P.has_left, P.has_right};
+    if (P.p2p) {
+        const int step = counters[CN_STEP];
+        send_messages(P, counters, which, step, send_l, send_r);
+        // wait for the neighbours' messages of this exchange: they were stored into this rank's
+        // exchange block by the neighbours' k_unpack; the flag is released after the payload
+        __shared__ int s_ok[2];
+        if (threadIdx.x < 2) {
+            const int s = threadIdx.x;
+            int ok = 1;
+            if (present[s]) {
+                const int *flag = xchg_flag(P.xchg_base, s, which);
+                const long long t0 = clock64();
+                while (ld_acquire_sys(flag) < 2 * step + which + 1) {
+                    if (clock64() - t0 > 20000000000LL) { ok = 0; break; }     // ~10 s: neighbour lost
+                    __nanosleep(200);
+                }
+            }
+            s_ok[s] = ok;
+        }
+        __syncthreads();
+        for (int s = 0; s < 2; s++) {
+            buf[s] = (unsigned char *)(P.xchg_base + xchg_offset(s, which, step & 1, P.msg_cap));
+            if (!s_ok[s]) { buf[s] = recv_l; if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&counters[CN_MSG_OVER], 1 << 20); }
+        }
+    }
     for (int s = 0; s < 2; s++) {
         if (!present[s]) continue;
-        n_mig[s] = which == 0 ? min(msg_hdr(buf[s])[0], P.msg_cap) : 0;
-        n_halo[s] = min(msg_hdr(buf[s])[1], P.msg_cap);
+        n_mig[s] = which == 0 ? min(ld_acquire_sys(&msg_hdr(buf[s])[0]), P.msg_cap) : 0;
+        n_halo[s] = min(ld_acquire_sys(&msg_hdr(buf[s])[1]), P.msg_cap);
     }
     const int total = n_mig[0] + n_halo[0] + n_mig[1] + n_halo[1];
     if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -231,7 +320,7 @@ __device__ __forceinline__ void st_release_u64(unsigned long long *p, unsigned l
 
 __global__ void __launch_bounds__(SPH_THREADS)
 k_scan(DevParams *__restrict__ Pp, int *__restrict__ counters, int *__restrict__ cnt, int *__restrict__ cell_start,
-       unsigned long long *__restrict__ tile_state, unsigned char *send_l, unsigned char *send_r)
+       unsigned long long *__restrict__ tile_state, unsigned char *send_l, unsigned char *send_r, int end_of_step)
 {
     __shared__ int s_tile;
     __shared__ int s_warp[SPH_THREADS / 32];
@@ -242,6 +331,15 @@ k_scan(DevParams *__restrict__ Pp, int *__restrict__ counters, int *__restrict__
     if (threadIdx.x == 0) s_tile = atomicAdd(&counters[CN_TICKET], 1);
     __syncthreads();
     const int tile = s_tile;
+    // the grid is sized for the widest window a slab can have; surplus blocks only check out
+    if (tile >= ntiles) {
+        if (threadIdx.x == 0 && atomicAdd(&counters[CN_DONE], 1) == (int)gridDim.x - 1) {
+            counters[CN_TICKET] = 0;
+            counters[CN_DONE] = 0;
+            counters[CN_EPOCH] = (int)((epoch + 1) & 0x3fffffffu);
+        }
+        return;
+    }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int base = tile * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
 
@@ -341,11 +439,12 @@ k_scan(DevParams *__restrict__ Pp, int *__restrict__ counters, int *__restrict__
         // send buffers are free again: the messages they held were consumed before this sort
         if (send_l) { msg_hdr(send_l)[0] = 0; msg_hdr(send_l)[1] = 0; }
         if (send_r) { msg_hdr(send_r)[0] = 0; msg_hdr(send_r)[1] = 0; }
+        if (end_of_step) counters[CN_STEP] += 1;
     }
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();
-        if (atomicAdd(&counters[CN_DONE], 1) == ntiles - 1) {   // last tile out resets the bookkeeping
+        if (atomicAdd(&counters[CN_DONE], 1) == (int)gridDim.x - 1) {   // last block out resets the bookkeeping
             counters[CN_TICKET] = 0;
             counters[CN_DONE] = 0;
             counters[CN_EPOCH] = (int)((epoch + 1) & 0x3fffffffu);

@@ -27,13 +27,15 @@ class _CudaBytes:
 
 class SlabRunner:
     def __init__(self, prob, tunable, rank, world, stream=None, capacity_factor=2.0, backend=None,
-                 msg_capacity=None, steps_per_frame=4, balance=True, group=None):
+                 msg_capacity=None, steps_per_frame=4, balance=True, group=None, transport="p2p",
+                 async_counts=True):
         import torch
         import torch.distributed as dist
         self.torch, self.dist = torch, dist
         self.prob, self.rank, self.world, self.group = prob, rank, world, group
         self.steps_per_frame, self.do_balance = steps_per_frame, balance
         self.sub_step = 0
+        self.async_counts = async_counts
         self.stream = stream
         self.t = tunable.copy()
         self.edges = [(s, e) for (_, _, s, e) in prob["slabs"]]
@@ -56,6 +58,14 @@ class SlabRunner:
             self.cuda = False
         self.ctx.set_params(self.t)
         self.has_left, self.has_right = rank > 0, rank < world - 1
+        # "p2p": neighbours map each other's exchange block (cudaIpc) and the kernels store messages
+        # straight into it over NVLink; "collective": torch.distributed send/recv moves the buffers
+        self.transport = transport if (self.cuda and world > 1) else "collective"
+        if self.transport == "p2p":
+            handles = [None] * world
+            dist.all_gather_object(handles, self.ctx.p2p_handle(), group=group)
+            self.ctx.p2p_connect(handles[rank - 1] if self.has_left else None,
+                                 handles[rank + 1] if self.has_right else None)
         self._bufs = {}
         self.counts = None
         self.exchange_s = 0.0
@@ -94,11 +104,33 @@ class SlabRunner:
         dist.all_gather(out, mine, group=self.group)
         return [int(x.item()) for x in out]
 
+    def sample_counts_async(self):
+        """End of a frame: all-gather the slab populations WITHOUT stalling the host.  The result is used
+        one frame later, which is the reference's own timing: its render rank balances on the counts of
+        the coordinate messages of the previous frame (renderer.c:268-290)."""
+        torch, dist = self.torch, self.dist
+        if not hasattr(self, "_cnt_mine"):
+            self._cnt_mine = torch.zeros(1, dtype=torch.int32, device="cuda")
+            self._cnt_all = torch.zeros(self.world, dtype=torch.int32, device="cuda")
+            self._cnt_host = torch.zeros(self.world, dtype=torch.int32).pin_memory()
+            self._cnt_event = torch.cuda.Event()
+        self.ctx.copy_n_local(self._cnt_mine.data_ptr())
+        dist.all_gather_into_tensor(self._cnt_all, self._cnt_mine, group=self.group)
+        self._cnt_host.copy_(self._cnt_all, non_blocking=True)
+        self._cnt_event.record(self.stream)
+        self._cnt_pending = True
+
     def rebalance(self):
         """check_partition_left on identical inputs on every rank; the new edges are queued so that they
         land between prediction and migration of the coming step (fluid.c:293-310)."""
         import sph_b200
-        counts = self.gather_counts()
+        if self.cuda and self.async_counts:
+            if not getattr(self, "_cnt_pending", False):
+                return                                  # first frame: nothing sampled yet
+            self._cnt_event.synchronize()               # recorded a frame ago: already complete
+            counts = [int(c) for c in self._cnt_host.tolist()]
+        else:
+            counts = self.gather_counts()
         self.counts = counts
         # the reference feeds coordinate counts (2 per particle) on both sides of the ratio (renderer.c:280,290)
         self.edges = sph_b200.balance(self.edges, [2 * c for c in counts], self.prob["h"])
@@ -113,11 +145,21 @@ class SlabRunner:
             import sph_b200
             a, uid = sph_b200.lattice(self.prob, self.rank)
         self.ctx.upload(a, uid)
+        if self.world > 1:
+            if self.cuda:
+                self.torch.cuda.synchronize()
+            self.dist.barrier(group=self.group)       # message sequence numbers restart together
 
     def step_once(self):
         if self.do_balance and self.world > 1 and self.sub_step == self.steps_per_frame - 1:
             self.rebalance()
         c = self.ctx
+        if self.transport == "p2p":
+            c.step(1)                                  # one CUDA graph; the exchange happens inside the kernels
+            if self.do_balance and self.async_counts and self.sub_step == self.steps_per_frame - 1:
+                self.sample_counts_async()
+            self.sub_step = (self.sub_step + 1) % self.steps_per_frame
+            return
         c.advect()
         self.exchange(0)
         c.sort()
@@ -125,6 +167,8 @@ class SlabRunner:
         c.relax()
         self.exchange(1)
         c.sort()
+        if self.do_balance and self.cuda and self.async_counts and self.world > 1 and self.sub_step == self.steps_per_frame - 1:
+            self.sample_counts_async()
         self.sub_step = (self.sub_step + 1) % self.steps_per_frame
 
     def run(self, n):
@@ -141,15 +185,16 @@ class SlabRunner:
         names = ("advect", "exchange0", "sort1", "density", "relax", "exchange1", "sort2")
         acc = {k: 0.0 for k in names}
         c = self.ctx
+        x = (lambda w: None) if self.transport == "p2p" else self.exchange
         for _ in range(nsteps):
             flush_buf.zero_()
             ev = [torch.cuda.Event(enable_timing=True) for _ in range(8)]
             ev[0].record(self.stream); c.advect()
-            ev[1].record(self.stream); self.exchange(0)
+            ev[1].record(self.stream); x(0)
             ev[2].record(self.stream); c.sort()
             ev[3].record(self.stream); c.density()
             ev[4].record(self.stream); c.relax()
-            ev[5].record(self.stream); self.exchange(1)
+            ev[5].record(self.stream); x(1)
             ev[6].record(self.stream); c.sort()
             ev[7].record(self.stream)
             torch.cuda.synchronize()
@@ -161,7 +206,8 @@ class SlabRunner:
         return {k: v for k, v in out.items()}
 
     def kernel_name(self, stage):
-        return {"advect": "k_advect", "density": "k_density", "relax": "k_relax", "exchange": "nccl send/recv",
+        return {"advect": "k_advect", "density": "k_density", "relax": "k_relax",
+                "exchange": "peer stores inside k_advect/k_relax" if self.transport == "p2p" else "nccl send/recv",
                 "sort1": "k_unpack+k_scan+k_scatter+k_reorder", "sort2": "k_unpack+k_scan+k_scatter+k_reorder"}[stage]
 
     def e2e(self, frames, flush_buf):

@@ -17,6 +17,7 @@ def main():
     from sph_b200.slab import SlabRunner
 
     out, n_req, steps = sys.argv[1], int(sys.argv[2]), int(sys.argv[3])
+    transport = sys.argv[4] if len(sys.argv) > 4 else "p2p"
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
     dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ["LOCAL_RANK"])))
@@ -26,7 +27,7 @@ def main():
     t.mover_center_x = 0.4 * prob["tank_w"]          # in the path of the collapsing block
     stream = torch.cuda.Stream()
     with torch.cuda.stream(stream):
-        sim = SlabRunner(prob, t, rank, world, stream)
+        sim = SlabRunner(prob, t, rank, world, stream, transport=transport)
         sim.init_lattice()
         sim.run(steps)
         a, uid = sim.ctx.download()

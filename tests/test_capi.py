@@ -12,7 +12,7 @@ def test_library_exports_every_declared_symbol(built_lib):
     import sph_b200
     L = C.CDLL(built_lib)
     hdr = open(os.path.join(os.path.dirname(built_lib), "..", "include", "sph_b200.h")).read()
-    declared = set(re.findall(r"\b(sph_[a-z_]+)\s*\(", hdr))
+    declared = set(re.findall(r"\b(sph_[a-z0-9_]+)\s*\(", hdr))
     assert declared == set(sph_b200.C_ABI_SYMBOLS), declared ^ set(sph_b200.C_ABI_SYMBOLS)
     for name in declared:
         assert hasattr(L, name), name

@@ -20,11 +20,13 @@ def ngpus():
 
 
 @pytest.mark.skipif(ngpus() < 2, reason="needs 2 GPUs")
-@pytest.mark.parametrize("world", [2])
-def test_two_gpu_slabs_match_single_gpu_bit_for_bit(tmp_path, built_lib, world):
+@pytest.mark.parametrize("world,transport", [(2, "p2p"), (2, "collective"), (4, "p2p"), (8, "p2p")])
+def test_two_gpu_slabs_match_single_gpu_bit_for_bit(tmp_path, built_lib, world, transport):
+    if ngpus() < world:
+        pytest.skip(f"needs {world} GPUs")
     base = str(tmp_path / "slab")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
-           "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.join(HERE, "slab_gpu_worker.py"), base, "20000", "240"]
+           "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.join(HERE, "slab_gpu_worker.py"), base, "40000", "240", transport]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-4000:]
     parts = [np.load(f"{base}.rank{r}.npz") for r in range(world)]

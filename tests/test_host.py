@@ -17,7 +17,7 @@ def test_host_symbols_exported(built_lib):
         assert hasattr(L, s)
     hdr = open(os.path.join(os.path.dirname(built_lib), "..", "include", "sph_host.h")).read()
     import re
-    assert set(re.findall(r"\b(sph_host_[a-z_]+)\s*\(", hdr)) == set(sph_b200.HOST_SYMBOLS)
+    assert set(re.findall(r"\b(sph_host_[a-z0-9_]+)\s*\(", hdr)) == set(sph_b200.HOST_SYMBOLS)
 
 
 def test_partition_matches_reference_golden(built_lib):
