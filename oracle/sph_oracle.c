@@ -633,7 +633,8 @@ void orc_g_advect(orc_g *g)
             if (g->has_right && g->edge_end - x <= w) g_pack_halo0(g, 1, x, y, g->tuid[i]);
         }
         g->tkey[i] = g_key(g, x, y);
-        if (g->tkey[i] == KEY_DROP) g->st.capacity_overflow++;
+        /* an emigrant pushed out of this slab's window (mover) is simply not kept as a ghost */
+        if (g->tkey[i] == KEY_DROP && !(g->tuid[i] & HALO_BIT)) g->st.capacity_overflow++;
     }
     g->stage = ST_ADVECTED;
 }

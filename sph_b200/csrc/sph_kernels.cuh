@@ -119,8 +119,11 @@ __device__ __forceinline__ void bin_position(int i, float2 p, int extra_bits, co
                                              int *__restrict__ t_slot, int *__restrict__ counters)
 {
     int key = window_key_new(p, P);
-    if (key == SPH_KEY_DROP) {                 // left the window: cannot happen with a sane ghost width
-        atomicAdd(&counters[CN_CAP_OVER], 1);
+    if (key == SPH_KEY_DROP) {
+        // Outside this slab's window.  For an emigrant that is fine: it has been handed to its new owner
+        // and is too far away to matter as a ghost (a mover can push a particle several cells at once).
+        // For anything else the particle would be lost: counted, and fatal for the caller.
+        if (!(extra_bits & SPH_KEY_EMIG)) atomicAdd(&counters[CN_CAP_OVER], 1);
         t_key[i] = SPH_KEY_DROP;
         return;
     }

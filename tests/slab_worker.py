@@ -16,10 +16,16 @@ def main():
     from sph_b200.slab import SlabRunner
 
     out, n_req, steps, balance = sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4])
+    block = len(sys.argv) > 5 and sys.argv[5] == "block"
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    prob = make_problem(n_req, nranks=world)
-    t = default_tunable(prob["h"], prob["tank_w"], prob["tank_h"])
+    if block:   # dam-break block in the left half, mover sphere straddling a slab edge inside the water
+        prob = make_problem(n_req, tank_w=15.0 * float(np.sqrt(n_req / 750.0)), water_frac=0.5, nranks=world)
+        t = default_tunable(prob["h"], prob["tank_w"], prob["tank_h"])
+        t.mover_center_x = 0.4 * prob["tank_w"]
+    else:
+        prob = make_problem(n_req, nranks=world)
+        t = default_tunable(prob["h"], prob["tank_w"], prob["tank_h"])
 
     def backend(tw, th, h, cap, msg, r, w):
         return GatherOracle(tw, th, h, cap, msg, r, w)
