@@ -27,6 +27,7 @@ struct sph_ctx {
     float2 *Q[3];
     uint32_t *U[2];
     float2 *dens;
+    unsigned long long *nmask;       // 3 x capacity: per-row acceptance masks from k_density for k_relax
     int *cnt, *cell_start, *t_key, *t_slot, *ord_src;
     uint32_t *ord_uid;
     unsigned long long *tile_state;
@@ -124,6 +125,7 @@ extern "C" int sph_create(const sph_config *cfg, sph_ctx **out)
     for (int i = 0; i < 3; i++) CK(cudaMalloc(&ctx->Q[i], cap * sizeof(float2)));
     for (int i = 0; i < 2; i++) CK(cudaMalloc(&ctx->U[i], cap * sizeof(uint32_t)));
     CK(cudaMalloc(&ctx->dens, cap * sizeof(float2)));
+    CK(cudaMalloc(&ctx->nmask, 3 * cap * sizeof(unsigned long long)));
     CK(cudaMalloc(&ctx->cnt, (ncell_max + 1) * sizeof(int)));
     CK(cudaMalloc(&ctx->cell_start, (ncell_max + 1) * sizeof(int)));
     CK(cudaMalloc(&ctx->t_key, cap * sizeof(int)));
@@ -177,7 +179,7 @@ extern "C" void sph_destroy(sph_ctx *ctx)
     for (int i = 0; i < 4; i++) cudaFree(ctx->P[i]);
     for (int i = 0; i < 3; i++) cudaFree(ctx->Q[i]);
     for (int i = 0; i < 2; i++) cudaFree(ctx->U[i]);
-    cudaFree(ctx->dens); cudaFree(ctx->cnt); cudaFree(ctx->cell_start); cudaFree(ctx->t_key);
+    cudaFree(ctx->dens); cudaFree(ctx->nmask); cudaFree(ctx->cnt); cudaFree(ctx->cell_start); cudaFree(ctx->t_key);
     cudaFree(ctx->t_slot); cudaFree(ctx->ord_src); cudaFree(ctx->ord_uid); cudaFree(ctx->coords);
     cudaFree(ctx->tile_state); cudaFree(ctx->counters); cudaFree(ctx->dp);
     for (int s = 0; s < 2; s++) { cudaFree(ctx->send[s]); cudaFree(ctx->recv[s]); }
@@ -320,7 +322,7 @@ static int launch_advect(sph_ctx *ctx)
 
 static int launch_density(sph_ctx *ctx)
 {
-    k_density<<<ctx->grid, SPH_THREADS, 0, ctx->stream>>>(ctx->dp, ctx->counters, ctx->P[2], ctx->cell_start, ctx->dens);
+    k_density<<<ctx->grid, SPH_THREADS, 0, ctx->stream>>>(ctx->dp, ctx->counters, ctx->P[2], ctx->cell_start, ctx->dens, ctx->nmask);
     ctx->launches++;
     CK(cudaGetLastError());
     return SPH_OK;
@@ -329,7 +331,7 @@ static int launch_density(sph_ctx *ctx)
 static int launch_relax(sph_ctx *ctx)
 {
     k_relax<<<ctx->grid, SPH_THREADS, 0, ctx->stream>>>(ctx->dp, ctx->counters, ctx->P[2], ctx->Q[1], ctx->U[1], ctx->dens,
-                                                        ctx->cell_start, ctx->P[3], ctx->Q[2], ctx->cnt, ctx->t_key,
+                                                        ctx->cell_start, ctx->nmask, ctx->P[3], ctx->Q[2], ctx->cnt, ctx->t_key,
                                                         ctx->t_slot, ctx->send[0], ctx->send[1]);
     ctx->launches++;
     CK(cudaGetLastError());

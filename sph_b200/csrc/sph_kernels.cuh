@@ -514,7 +514,8 @@ k_reorder(const DevParams *__restrict__ Pp, int *__restrict__ counters, const in
 // -------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(SPH_THREADS)
 k_density(const DevParams *__restrict__ Pp, int *__restrict__ counters,
-          const float2 *__restrict__ pos, const int *__restrict__ cell_start, float2 *__restrict__ dens)
+          const float2 *__restrict__ pos, const int *__restrict__ cell_start, float2 *__restrict__ dens,
+          unsigned long long *__restrict__ nmask)
 {
     const DevParams P = *Pp;
     const int n = counters[CN_NTOT];
@@ -527,13 +528,18 @@ k_density(const DevParams *__restrict__ Pp, int *__restrict__ counters,
         const Rows R = candidate_rows(p, P, cell_start);
 #pragma unroll
         for (int dd = 0; dd < 3; dd++) {
+            // acceptance mask of this row's first 64 candidates: k_relax works on the same positions and
+            // the same ranges, so it iterates these bits instead of repeating ~60 distance tests
+            unsigned long long m = 0ull;
+            const int b = R.b[dd];
 #pragma unroll 4
-            for (int j = R.b[dd]; j < R.e[dd]; j++) {
+            for (int j = b; j < R.e[dd]; j++) {
                 const float2 q = pos[j];
                 const float dx = q.x - p.x, dy = q.y - p.y;
                 const float r2 = dist2(dx, dy);
                 if (r2 > h2) continue;
                 if (r2 == 0.0f && j == i) continue;                     // self; coincident others do count (ratio 0)
+                if (j - b < 64) m |= 1ull << (j - b);
                 nn++;
                 float r, r_recip;
                 r_and_recip(r2, r, r_recip);
@@ -545,6 +551,7 @@ k_density(const DevParams *__restrict__ Pp, int *__restrict__ counters,
                     dn += omr2 * omr;
                 }
             }
+            nmask[(size_t)dd * P.cap + i] = m;
         }
         dens[i] = make_float2(d, dn);
         // a forward list cannot exceed the full neighbour count: cheap, conservative detection
@@ -562,6 +569,7 @@ __global__ void __launch_bounds__(SPH_THREADS, 4)
 k_relax(const DevParams *__restrict__ Pp, int *__restrict__ counters,
         const float2 *__restrict__ pos, const float2 *__restrict__ prev, const uint32_t *__restrict__ uid,
         const float2 *__restrict__ dens, const int *__restrict__ cell_start,
+        const unsigned long long *__restrict__ nmask,
         float2 *__restrict__ pos_out, float2 *__restrict__ vel_out,
         int *__restrict__ cnt, int *__restrict__ t_key, int *__restrict__ t_slot,
         unsigned char *send_l, unsigned char *send_r)
@@ -584,35 +592,48 @@ k_relax(const DevParams *__restrict__ Pp, int *__restrict__ counters,
         float x = p.x, y = p.y;
         const int gxi = cell_coord(p.x, P.cell_h), gyi = cell_coord(p.y, P.cell_h);
         const Rows R = candidate_rows(p, P, cell_start);
+        // pair physics for one listed neighbour (membership r2 <= h2, j != i already established)
+        auto pair = [&](int j) {
+            const float2 q = pos[j];
+            const float dx = q.x - p.x, dy = q.y - p.y;
+            float r, r_recip;
+            r_and_recip(dist2(dx, dy), r, r_recip);
+            const float ratio = r * h_recip;
+            if (r <= 0.000001f) {
+                // coincident particles: only the list owner is nudged (fluid.c:583-586); owner =
+                // earlier bucket slot in the same cell, else the cell whose forward stencil
+                // (0,+1),(1,-1),(1,0),(1,+1) holds the other (hash.c:178-224)
+                const int gxj = cell_coord(q.x, P.cell_h), gyj = cell_coord(q.y, P.cell_h);
+                const bool owner = (gxi == gxj && gyi == gyj) ? (i < j) : (gxi != gxj ? gxi < gxj : gyi < gyj);
+                if (owner) { x += 0.000001f; y += 0.000001f; }
+            }
+            if (ratio < 1.0f && r > 0.0f) {
+                const float2 dj = dens[j];
+                const float pq = P.k * (dj.x - P.rest_density);
+                const float pqn = P.k_near * dj.y;
+                const float omr = 1.0f - ratio;
+                // fluid.c:591; the reference's fp64 tail is evaluated in fp32 here (<= 1 ulp of D)
+                const float D = dt2 * ((pp + pq) * omr + (ppn + pqn) * omr * omr + P.k_spring * (h - r) * 0.5f);
+                x -= D * dx * r_recip;
+                y -= D * dy * r_recip;
+            }
+        };
 #pragma unroll
         for (int d = 0; d < 3; d++) {
-#pragma unroll 4
-            for (int j = R.b[d]; j < R.e[d]; j++) {
+            // the lists were built by k_density on these same positions: walk its acceptance bits
+            // (candidate order, so the order of summation is unchanged) ...
+            const int b = R.b[d];
+            unsigned long long m = nmask[(size_t)d * P.cap + i];
+            while (m) {
+                const int k = __ffsll((long long)m) - 1;
+                m &= m - 1;
+                pair(b + k);
+            }
+            // ... and test the rare candidates beyond the 64 a mask covers
+            for (int j = b + 64; j < R.e[d]; j++) {
                 const float2 q = pos[j];
-                const float dx = q.x - p.x, dy = q.y - p.y;
-                const float r2 = dist2(dx, dy);
-                if (r2 > h2) continue;
-                float r, r_recip;
-                r_and_recip(r2, r, r_recip);
-                const float ratio = r * h_recip;
-                if (r <= 0.000001f && j != i) {
-                    // coincident particles: only the list owner is nudged (fluid.c:583-586); owner =
-                    // earlier bucket slot in the same cell, else the cell whose forward stencil
-                    // (0,+1),(1,-1),(1,0),(1,+1) holds the other (hash.c:178-224)
-                    const int gxj = cell_coord(q.x, P.cell_h), gyj = cell_coord(q.y, P.cell_h);
-                    const bool owner = (gxi == gxj && gyi == gyj) ? (i < j) : (gxi != gxj ? gxi < gxj : gyi < gyj);
-                    if (owner) { x += 0.000001f; y += 0.000001f; }
-                }
-                if (ratio < 1.0f && r > 0.0f) {
-                    const float2 dj = dens[j];
-                    const float pq = P.k * (dj.x - P.rest_density);
-                    const float pqn = P.k_near * dj.y;
-                    const float omr = 1.0f - ratio;
-                    // fluid.c:591; the reference's fp64 tail is evaluated in fp32 here (<= 1 ulp of D)
-                    const float D = dt2 * ((pp + pq) * omr + (ppn + pqn) * omr * omr + P.k_spring * (h - r) * 0.5f);
-                    x -= D * dx * r_recip;
-                    y -= D * dy * r_recip;
-                }
+                if (dist2(q.x - p.x, q.y - p.y) > h2 || j == i) continue;
+                pair(j);
             }
         }
         float2 np = boundary(make_float2(x, y), P);                     // fluid.c:649
