@@ -220,6 +220,8 @@ def main_ours(args):
         sim.run(args.warmup)
         barrier()
         launches0 = sim.launches
+        if os.environ.get("SPH_PROFILE"):      # ncu --profile-from-start off: instrument the timed region only
+            torch.cuda.profiler.start()
         # ---- timed region: K steps, L2 flushed between steps, device time per step from CUDA events
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
         wall0 = time.perf_counter()
@@ -231,6 +233,8 @@ def main_ours(args):
         barrier()
         wall = time.perf_counter() - wall0
         launches = sim.launches - launches0
+        if os.environ.get("SPH_PROFILE"):
+            torch.cuda.profiler.stop()
         step_ms = [a.elapsed_time(b) for a, b in ev]
         total_ms = float(sum(step_ms))
         # ---- the same K steps back to back, state L2-resident (informational)

@@ -302,12 +302,16 @@ k_unpack(const DevParams *__restrict__ Pp, int *__restrict__ counters, int which
 }
 
 // -------------------------------------------------------------------------------------------
-// K3  exclusive prefix sum of the cell populations -> cell_start (single pass, decoupled
-//     look-back, warp-shuffle scans).  Also clears the populations for the next sort, records
-//     the largest bucket (the reference silently drops above 100: hash.c:160-165) and
-//     publishes the new entry counts.
+// K3  exclusive prefix sum of the cell populations -> cell_start, one pass.
+//     Every tile (8192 cells) publishes its total; a tile's offset is the sum of ALL preceding
+//     totals, read directly.  All tiles of a launch are co-resident (a few hundred blocks at most)
+//     and take their tile index from a ticket, so every predecessor is already running: there is one
+//     round of waiting instead of the chained look-back of the first version, whose ~8 sequential
+//     L2 round trips made this kernel 20 us for 2 MB of data (profiles/r1_masks_full.csv).
+//     Also clears the populations for the next sort, records the largest bucket (the reference
+//     silently drops above 100: hash.c:160-165) and publishes the new entry counts.
 // -------------------------------------------------------------------------------------------
-#define SCAN_ITEMS 8
+#define SCAN_ITEMS 32
 #define SCAN_TILE (SPH_THREADS * SCAN_ITEMS)
 
 __device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long *p)
@@ -344,31 +348,39 @@ k_scan(DevParams *__restrict__ Pp, int *__restrict__ counters, int *__restrict__
         return;
     }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int base = tile * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+    const int base = tile * SCAN_TILE + threadIdx.x * SCAN_ITEMS;     // 32 consecutive cells = 128 bytes per thread
 
     int v[SCAN_ITEMS];
     int sum = 0, mx = 0, over = 0;
+    if (base + SCAN_ITEMS <= ncell) {
+        const int4 *src = reinterpret_cast<const int4 *>(cnt + base);
+        int4 *dstz = reinterpret_cast<int4 *>(cnt + base);
 #pragma unroll
-    for (int k = 0; k < SCAN_ITEMS; k++) {
-        int idx = base + k;
-        v[k] = idx < ncell ? cnt[idx] : 0;
-        if (idx < ncell) cnt[idx] = 0;
-        sum += v[k];
-        mx = max(mx, v[k]);
-        over += v[k] > 100;
+        for (int k = 0; k < SCAN_ITEMS / 4; k++) {
+            const int4 q = src[k];
+            v[4 * k] = q.x; v[4 * k + 1] = q.y; v[4 * k + 2] = q.z; v[4 * k + 3] = q.w;
+        }
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS / 4; k++) dstz[k] = make_int4(0, 0, 0, 0);
+    } else {
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; k++) {
+            const int idx = base + k;
+            v[k] = idx < ncell ? cnt[idx] : 0;
+            if (idx < ncell) cnt[idx] = 0;
+        }
     }
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) { sum += v[k]; mx = max(mx, v[k]); over += v[k] > 100; }
     // warp inclusive scan of the thread sums
     int inc = sum;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-        int t = __shfl_up_sync(0xffffffffu, inc, o);
+        const int t = __shfl_up_sync(0xffffffffu, inc, o);
         if (lane >= o) inc += t;
     }
-    mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, 16)); over += __shfl_xor_sync(0xffffffffu, over, 16);
-    mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, 8));  over += __shfl_xor_sync(0xffffffffu, over, 8);
-    mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, 4));  over += __shfl_xor_sync(0xffffffffu, over, 4);
-    mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, 2));  over += __shfl_xor_sync(0xffffffffu, over, 2);
-    mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, 1));  over += __shfl_xor_sync(0xffffffffu, over, 1);
+    mx = __reduce_max_sync(0xffffffffu, mx);
+    over = __reduce_add_sync(0xffffffffu, over);
     if (lane == 31) s_warp[warp] = inc;
     if (lane == 0) {
         if (mx > 0) atomicMax(&counters[CN_MAX_BUCKET], mx);
@@ -378,56 +390,43 @@ k_scan(DevParams *__restrict__ Pp, int *__restrict__ counters, int *__restrict__
     int warp_off = 0, block_total = 0;
 #pragma unroll
     for (int w = 0; w < SPH_THREADS / 32; w++) {
-        int s = s_warp[w];
-        if (w < warp) warp_off += s;
-        block_total += s;
+        const int sw = s_warp[w];
+        if (w < warp) warp_off += sw;
+        block_total += sw;
     }
-    // publish this tile, look back for the exclusive prefix (one warp)
+    // publish this tile's total, then add up every preceding tile's total (one warp)
     if (warp == 0) {
-        const unsigned long long tag = (unsigned long long)epoch << 34;
-        if (lane == 0) {
-            unsigned long long st = tag | ((unsigned long long)(tile == 0 ? 2 : 1) << 32) | (unsigned)block_total;
-            st_release_u64(&tile_state[tile], st);
-        }
+        const unsigned long long tag = (unsigned long long)epoch << 32;
+        if (lane == 0) st_release_u64(&tile_state[tile], tag | (unsigned)block_total);
         int prefix = 0;
-        int look = tile - 1;
-        while (look >= 0) {
-            int idx = look - lane;
-            unsigned long long st = 0;
-            int status = 0;
-            if (idx >= 0) {
-                do {
-                    st = ld_acquire_u64(&tile_state[idx]);
-                    status = ((st >> 34) == epoch) ? (int)((st >> 32) & 3) : 0;
-                } while (status == 0);
-            } else {
-                status = 2;      // before tile 0: an inclusive prefix of zero
-            }
-            unsigned incl_mask = __ballot_sync(0xffffffffu, status == 2);
-            // nearest predecessor with an inclusive value; none in this window -> take all 32 aggregates
-            int last = incl_mask ? __ffs(incl_mask) - 1 : 31;
-            int val = (idx >= 0 && lane <= last) ? (int)(unsigned)st : 0;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) val += __shfl_xor_sync(0xffffffffu, val, o);
-            prefix += val;
-            if (incl_mask) break;
-            look -= 32;
+        for (int idx = lane; idx < tile; idx += 32) {
+            unsigned long long st;
+            do { st = ld_acquire_u64(&tile_state[idx]); } while ((unsigned)(st >> 32) != epoch);
+            prefix += (int)(unsigned)st;
         }
-        if (lane == 0) {
-            s_prefix = prefix;
-            if (tile != 0) {
-                unsigned long long st = tag | (2ull << 32) | (unsigned)(prefix + block_total);
-                st_release_u64(&tile_state[tile], st);
-            }
-        }
+        prefix = __reduce_add_sync(0xffffffffu, prefix);
+        if (lane == 0) s_prefix = prefix;
     }
     __syncthreads();
     int run = s_prefix + warp_off + (inc - sum);
+    if (base + SCAN_ITEMS <= ncell) {
+        int4 *dst = reinterpret_cast<int4 *>(cell_start + base);
 #pragma unroll
-    for (int k = 0; k < SCAN_ITEMS; k++) {
-        int idx = base + k;
-        if (idx < ncell) cell_start[idx] = run;
-        run += v[k];
+        for (int k = 0; k < SCAN_ITEMS / 4; k++) {
+            int4 o;
+            o.x = run; run += v[4 * k];
+            o.y = run; run += v[4 * k + 1];
+            o.z = run; run += v[4 * k + 2];
+            o.w = run; run += v[4 * k + 3];
+            dst[k] = o;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; k++) {
+            const int idx = base + k;
+            if (idx < ncell) cell_start[idx] = run;
+            run += v[k];
+        }
     }
     if (tile == ntiles - 1 && threadIdx.x == SPH_THREADS - 1) {
         const int total = s_prefix + block_total;
