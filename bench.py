@@ -331,8 +331,7 @@ class SingleGpu:
         return self.ctx.launches
 
     def init_lattice(self):
-        a, uid = self.sph.lattice(self.prob)
-        self.ctx.upload(a, uid)
+        self.ctx.init_lattice(self.prob)            # filled on the device: no host AoS
 
     def run(self, n):
         if n > 0:

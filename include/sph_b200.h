@@ -136,6 +136,12 @@ int sph_set_edges(sph_ctx *ctx, float node_start_x, float node_end_x);
  * neighbour structure (the reference starts with empty lists, fluid.c:202; velocities are
  * zero there so both give no impulse).  uid may be NULL (uid = index). */
 int sph_upload(sph_ctx *ctx, const sph_particle *aos, const uint32_t *uid, int n);
+/* constructFluidVolume + initParticles (geometry.c:29-59, fluid.c:747-768) on the device: the lattice of
+ * columns [start_col, start_col+ncols) of the water block, uid = row * total_cols + column, velocities
+ * zero; then binned like an upload.  Large problems never need a host AoS (the reference's own
+ * allocation overflows 32 bits above ~5.3 M particles, fluid.c:203).  Returns the count or <0. */
+int sph_init_lattice(sph_ctx *ctx, float water_min_x, float water_min_y, float water_max_y, float spacing,
+                     int start_col, int ncols, int total_cols);
 #define SPH_ORDER_UID 0      /* ascending uid == the reference's pointer order on one rank */
 #define SPH_ORDER_CELL 1     /* device order: row-major cell, then uid == bucket order */
 /* Device SoA -> host AoS (local particles; halo too if include_halo). Returns count or <0. */

@@ -42,6 +42,11 @@ int sph_host_lattice(float water_min_x, float water_min_y, float water_max_y, fl
  * renderer.c:280,290). */
 void sph_host_balance(sph_tunable *master, int nactive, const int *counts, int total);
 
+/* The render rank's idle "autopilot" for the mover (renderer.c:513-531): per frame gl_x += 0.01 * dir,
+ * direction flips outside [-1, 1], gl_y = sinf(3.14 * 5 * gl_x) / 10 - 0.6, then opengl_to_sim
+ * (renderer.c:396-404).  Updates t->mover_center_{x,y}; *gl_x / *direction carry the state. */
+void sph_host_mover_autopilot(sph_tunable *t, float tank_w, float tank_h, float *gl_x, int *direction);
+
 /* remove_partition / add_partition (controls.c:405-455): park the last active slab outside the
  * tank / split the last active slab in half. Return the new number of active slabs. */
 int sph_host_remove_partition(sph_tunable *master, int nactive);

@@ -60,7 +60,7 @@ C_ABI_SYMBOLS = (
     "sph_set_params", "sph_queue_params", "sph_set_edges", "sph_upload", "sph_download",
     "sph_advect", "sph_sort", "sph_density", "sph_relax", "sph_step", "sph_exchange_buffers",
     "sph_set_neighbors", "sph_get_cells", "sph_get_pairs", "sph_get_forward_counts",
-    "sph_pack_coords", "sph_launch_count", "sph_run_frame", "sph_p2p_local_handle", "sph_p2p_connect", "sph_copy_n_local",
+    "sph_pack_coords", "sph_launch_count", "sph_run_frame", "sph_p2p_local_handle", "sph_p2p_connect", "sph_copy_n_local", "sph_init_lattice",
 )
 
 _lib = None
@@ -99,6 +99,7 @@ def lib():
         L.sph_get_forward_counts.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         L.sph_pack_coords.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         L.sph_run_frame.argtypes = [C.c_void_p, C.POINTER(Tunable), C.c_int, C.c_void_p, C.c_int]
+        L.sph_init_lattice.argtypes = [C.c_void_p] + [C.c_float] * 4 + [C.c_int] * 3
         L.sph_copy_n_local.argtypes = [C.c_void_p, C.c_void_p]
         L.sph_p2p_local_handle.argtypes = [C.c_void_p, C.c_void_p]
         L.sph_p2p_connect.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
@@ -150,6 +151,14 @@ class Context:
         aos = np.ascontiguousarray(aos, PARTICLE)
         u = None if uid is None else np.ascontiguousarray(uid, "u4")
         self._ck(self.L.sph_upload(self.h, _p(aos), None if u is None else _p(u), len(aos)), "sph_upload")
+
+    def init_lattice(self, prob, rank=0):
+        """Device-side lattice fill of one slab of make_problem()'s geometry. Returns the particle count."""
+        sc, nc, _, _ = prob["slabs"][rank]
+        n = self.L.sph_init_lattice(self.h, 0.0, 0.0, prob["tank_h"], prob["spacing"], sc, nc, prob["total_cols"])
+        if n < 0:
+            self._ck(-n, "sph_init_lattice")
+        return n
 
     def download(self, order=ORDER_UID, include_halo=False):
         a = np.zeros(self.capacity, PARTICLE)
@@ -241,7 +250,7 @@ class Context:
 # ------------------------------------------------------------------------------------------------
 # C host layer (include/sph_host.h): start-up geometry, parameter model, slab load balancer
 # ------------------------------------------------------------------------------------------------
-HOST_SYMBOLS = ("sph_host_spacing", "sph_host_default_params", "sph_host_preset", "sph_host_partition",
+HOST_SYMBOLS = ("sph_host_mover_autopilot", "sph_host_spacing", "sph_host_default_params", "sph_host_preset", "sph_host_partition",
                 "sph_host_lattice", "sph_host_balance", "sph_host_remove_partition", "sph_host_add_partition")
 
 
@@ -254,6 +263,7 @@ def _host():
         L.sph_host_preset.argtypes = [C.POINTER(Tunable), C.c_char]
         L.sph_host_partition.argtypes = [C.c_float] * 6 + [C.c_int] + [C.c_void_p] * 4
         L.sph_host_lattice.argtypes = [C.c_float] * 4 + [C.c_int] * 3 + [C.c_void_p] * 2
+        L.sph_host_mover_autopilot.argtypes = [C.POINTER(Tunable), C.c_float, C.c_float, C.POINTER(C.c_float), C.POINTER(C.c_int)]
         L.sph_host_balance.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
         L.sph_host_remove_partition.argtypes = [C.c_void_p, C.c_int]
         L.sph_host_add_partition.argtypes = [C.c_void_p, C.c_int, C.c_int]

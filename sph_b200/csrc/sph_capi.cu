@@ -436,22 +436,9 @@ extern "C" int sph_step(sph_ctx *ctx, int n)
 // ------------------------------------------------------------------------------------------
 // state transfer
 // ------------------------------------------------------------------------------------------
-extern "C" int sph_upload(sph_ctx *ctx, const sph_particle *aos, const uint32_t *uid, int n)
+// n particles sit in the sort-2 source arrays (P3 / Q2 / U1): reset the counters, bin and sort them
+static int ingest(sph_ctx *ctx, int n)
 {
-    if (!ctx || (!aos && n > 0) || n < 0) return SPH_ERR_ARG;
-    if (n > ctx->cfg.capacity) return fail(ctx, SPH_ERR_CAPACITY, "sph_upload: more particles than capacity");
-    std::vector<float2> p(n), v(n);
-    std::vector<uint32_t> u(n);
-    for (int i = 0; i < n; i++) {
-        p[i] = make_float2(aos[i].x, aos[i].y);
-        v[i] = make_float2(aos[i].v_x, aos[i].v_y);
-        u[i] = uid ? (uid[i] & SPH_UID_MASK) : (uint32_t)i;
-    }
-    CK(cudaStreamSynchronize(ctx->stream));
-    // enter the pipeline where sort 2 does: source arrays P3 / Q2 / U1
-    CK(cudaMemcpyAsync(ctx->P[3], p.data(), n * sizeof(float2), cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->Q[2], v.data(), n * sizeof(float2), cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->U[1], u.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
     int zero[CN_COUNT] = {0};
     zero[CN_NTOT] = n;
     int epoch = 0;
@@ -471,6 +458,40 @@ extern "C" int sph_upload(sph_ctx *ctx, const sph_particle *aos, const uint32_t 
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->stage = ST_READY;
     return SPH_OK;
+}
+
+extern "C" int sph_upload(sph_ctx *ctx, const sph_particle *aos, const uint32_t *uid, int n)
+{
+    if (!ctx || (!aos && n > 0) || n < 0) return SPH_ERR_ARG;
+    if (n > ctx->cfg.capacity) return fail(ctx, SPH_ERR_CAPACITY, "sph_upload: more particles than capacity");
+    std::vector<float2> p(n), v(n);
+    std::vector<uint32_t> u(n);
+    for (int i = 0; i < n; i++) {
+        p[i] = make_float2(aos[i].x, aos[i].y);
+        v[i] = make_float2(aos[i].v_x, aos[i].v_y);
+        u[i] = uid ? (uid[i] & SPH_UID_MASK) : (uint32_t)i;
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    // enter the pipeline where sort 2 does: source arrays P3 / Q2 / U1
+    CK(cudaMemcpyAsync(ctx->P[3], p.data(), n * sizeof(float2), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->Q[2], v.data(), n * sizeof(float2), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->U[1], u.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));       // the host vectors go out of scope
+    return ingest(ctx, n);
+}
+
+extern "C" int sph_init_lattice(sph_ctx *ctx, float water_min_x, float water_min_y, float water_max_y, float spacing,
+                                int start_col, int ncols, int total_cols)
+{
+    if (!ctx || spacing <= 0.0f || ncols < 0) return -SPH_ERR_ARG;
+    const int rows = (int)floor((water_max_y - water_min_y) / spacing);           // geometry.c:35
+    const long long n = (long long)rows * ncols;
+    if (n > ctx->cfg.capacity) { fail(ctx, SPH_ERR_CAPACITY, "sph_init_lattice: more particles than capacity"); return -SPH_ERR_CAPACITY; }
+    k_init_lattice<<<ctx->grid, SPH_THREADS, 0, ctx->stream>>>(water_min_x, water_min_y, spacing, start_col, ncols, rows,
+                                                               total_cols, ctx->P[3], ctx->Q[2], ctx->U[1]);
+    ctx->launches++;
+    int rc = ingest(ctx, (int)n);
+    return rc ? -rc : (int)n;
 }
 
 static int read_counters(sph_ctx *ctx, int *c)

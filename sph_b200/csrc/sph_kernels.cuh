@@ -670,6 +670,25 @@ k_bin_upload(const DevParams *__restrict__ Pp, int *__restrict__ counters, const
 }
 
 // -------------------------------------------------------------------------------------------
+// device-side constructFluidVolume + initParticles (geometry.c:29-59, fluid.c:747-768): the lattice of
+// one slab's columns written straight into the sort's source arrays, so large problems never need a
+// host AoS.  x = min_x + (start_col + col) * spacing, y = min_y + row * spacing, unfused as on the host.
+// -------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(SPH_THREADS)
+k_init_lattice(float min_x, float min_y, float spacing, int start_col, int ncols, int rows, int total_cols,
+               float2 *__restrict__ pos, float2 *__restrict__ vel, uint32_t *__restrict__ uid)
+{
+    const long long n = (long long)ncols * rows;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int row = (int)(i / ncols), col = (int)(i % ncols);
+        pos[i] = make_float2(__fadd_rn(min_x, __fmul_rn((float)(start_col + col), spacing)),
+                             __fadd_rn(min_y, __fmul_rn((float)row, spacing)));
+        vel[i] = make_float2(0.0f, 0.0f);
+        uid[i] = (uint32_t)(row * total_cols + start_col + col);
+    }
+}
+
+// -------------------------------------------------------------------------------------------
 // render feed (fluid.c:358-361): (2x/max_x - 1) * SHRT_MAX, truncated to int16
 // -------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(SPH_THREADS)

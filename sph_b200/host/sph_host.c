@@ -130,6 +130,19 @@ void sph_host_balance(sph_tunable *m, int nactive, const int *counts, int total)
     }
 }
 
+void sph_host_mover_autopilot(sph_tunable *t, float tank_w, float tank_h, float *gl_x, int *direction)
+{
+    /* renderer.c:513-531 */
+    float x = *gl_x + 0.01f * (float)(*direction);
+    if (x > 1.0f || x < -1.0f) *direction = -*direction;
+    const float y = sinf(3.14f * 5.0f * x) / 10.0f - 0.6f;
+    *gl_x = x;
+    /* opengl_to_sim, renderer.c:396-404 */
+    const float half_w = tank_w * 0.5f, half_h = tank_h * 0.5f;
+    t->mover_center_x = x * half_w + half_w;
+    t->mover_center_y = y * half_h + half_h;
+}
+
 int sph_host_remove_partition(sph_tunable *m, int nactive)
 {
     /* controls.c:405-426 */

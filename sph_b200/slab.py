@@ -140,11 +140,11 @@ class SlabRunner:
     # -------------------------------------------------------------------------------- simulation
     def init_lattice(self):
         if self.cuda:
-            a, uid = self.sph.lattice(self.prob, self.rank)
+            self.ctx.init_lattice(self.prob, self.rank)        # filled on the device: no host AoS
         else:
             import sph_b200
             a, uid = sph_b200.lattice(self.prob, self.rank)
-        self.ctx.upload(a, uid)
+            self.ctx.upload(a, uid)
         if self.world > 1:
             if self.cuda:
                 self.torch.cuda.synchronize()

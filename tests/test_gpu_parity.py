@@ -179,3 +179,57 @@ def test_full_size_properties(built_lib, n_request):
         x, _ = b2.download(); y, _ = o.download()
         tol = 16 * ulp32(prob["tank_w"])
         assert np.abs(x["x"] - y["x"]).max() <= tol and np.abs(x["y"] - y["y"]).max() <= tol
+
+
+def test_device_side_lattice_equals_host_lattice(built_lib):
+    """sph_init_lattice (geometry.c:29-59 on the device) == upload of the host lattice, bit for bit."""
+    import sph_b200
+    for nranks, rank in ((1, 0), (3, 1)):
+        prob = sph_b200.make_problem(20000, tank_w=15.0 * np.sqrt(20000 / 750.0), water_frac=0.5, nranks=nranks)
+        a, uid = sph_b200.lattice(prob, rank)
+        t = sph_b200.default_params(prob["h"], prob["tank_w"], prob["tank_h"])
+        c1 = sph_b200.Context(prob["tank_w"], prob["tank_h"], prob["h"], len(a) + 64)
+        c2 = sph_b200.Context(prob["tank_w"], prob["tank_h"], prob["h"], len(a) + 64)
+        c1.set_params(t); c2.set_params(t)
+        c1.upload(a, uid)
+        assert c2.init_lattice(prob, rank) == len(a)
+        x1, u1 = c1.download(); x2, u2 = c2.download()
+        assert np.array_equal(u1, u2)
+        for f in ("x", "y", "v_x", "v_y"):
+            assert np.array_equal(x1[f].view("u4"), x2[f].view("u4"))
+        c1.step(5); c2.step(5)
+        x1, _ = c1.download(); x2, _ = c2.download()
+        assert np.array_equal(x1["x"].view("u4"), x2["x"].view("u4"))
+
+
+def test_mover_autopilot_and_preset_cycle(built_lib):
+    """BASELINE.json config 4 in small: mover on the render rank's autopilot path (renderer.c:513-531),
+    fluid presets cycled a -> b -> x -> y (controls.c:344-401), a new parameter block every frame landing
+    in the last sub-step (fluid.c:293-294).  CUDA (sph_run_frame) vs the gather oracle."""
+    import ctypes as C
+    import sph_b200
+    n_req = 12000
+    prob = make_problem(n_req, tank_w=15.0 * np.sqrt(n_req / 750.0), water_frac=0.5)
+    a, uid = lattice(prob)
+    t = default_tunable(prob["h"], prob["tank_w"], prob["tank_h"])
+    ts = as_sph(t)
+    b = sph_b200.Context(prob["tank_w"], prob["tank_h"], prob["h"], len(a) + 64)
+    o = make_oracle(prob["tank_w"], prob["tank_h"], prob["h"], len(a) + 64)
+    b.set_params(ts); o.set_params(t)
+    b.upload(a, uid); o.upload(a, uid)
+    L = sph_b200._host()
+    gl_x, direction = C.c_float(-0.2), C.c_int(1)
+    coords = np.zeros(2 * (len(a) + 64), "i2")
+    for frame in range(8):
+        L.sph_host_mover_autopilot(C.byref(ts), prob["tank_w"], prob["tank_h"], C.byref(gl_x), C.byref(direction))
+        L.sph_host_preset(C.byref(ts), "abxy"[(frame // 2) % 4].encode())
+        C.memmove(C.byref(t), C.byref(ts), 64)
+        n = b.run_frame(ts, 4, coords)
+        o.step(3); o.queue_params(t); o.step(1)
+        assert n == len(a)
+    x, _ = b.download(); y, _ = o.download()
+    d = np.hypot(x["x"] - y["x"], x["y"] - y["y"]) / prob["h"]
+    assert d.max() <= 2e-2 and np.sqrt((d ** 2).mean()) <= 1e-3, (d.max(), np.sqrt((d ** 2).mean()))
+    assert np.array_equal(coords[:2 * n].reshape(n, 2), b.pack_coords())
+    s = b.status()
+    assert s.capacity_overflow == 0 and s.n_local == len(a)
