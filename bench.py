@@ -150,7 +150,8 @@ def main_reference(args):
     if rank != 0:
         return 0
     n = args.n * args.gpus
-    r = run_reference_cpu(n, args.water_frac, args.steps, args.warmup)
+    # same initial condition and the same number of steps before the timed region as our arm
+    r = run_reference_cpu(n, args.water_frac, args.steps, args.preroll + args.warmup)
     line = {
         "impl": "reference", "metric": "particle-steps/sec", "value": r["value"], "unit": "particle-steps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
@@ -299,7 +300,7 @@ def main_ours(args):
         }
         if not args.no_cpu_baseline and world == 1:
             try:
-                r = run_reference_cpu(args.n, args.water_frac, steps=args.cpu_steps, warmup=2, budget_s=40.0)
+                r = run_reference_cpu(args.n, args.water_frac, steps=args.cpu_steps, warmup=args.cpu_warmup, budget_s=40.0)
                 line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
             except Exception as e:  # the baseline is reported, never fatal
                 line["cpu_baseline"] = {"value": None, "unit": "particle-steps/s", "cores": 0, "kind": "reference",
@@ -394,7 +395,9 @@ def main():
     ap.add_argument("--preroll", type=int, default=1000, help="untimed steps before warm-up (state preparation)")
     ap.add_argument("--water-frac", type=float, default=0.5)
     ap.add_argument("--preset", default="x")
-    ap.add_argument("--cpu-steps", type=int, default=10)
+    ap.add_argument("--cpu-steps", type=int, default=20, help="timed steps of the cpu_baseline sample")
+    ap.add_argument("--cpu-warmup", type=int, default=300, help="untimed steps of the cpu_baseline sample (bounded: the "
+                    "reference arm, --impl reference, runs the full pre-roll)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3:
