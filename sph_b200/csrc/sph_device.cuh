@@ -92,7 +92,9 @@ __device__ __forceinline__ int cell_coord(float v, float cell_h) { return (int)f
 __device__ __forceinline__ float dist2(float dx, float dy) { return __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)); }
 
 // checkVelocity (fluid.c:613-625)
-__device__ __forceinline__ float clamp5(float v) { return v > 5.0f ? 5.0f : (v < -5.0f ? -5.0f : v); }
+// (two FMNMX; differs from the reference's compare chain only for NaN, which cannot reach it: the
+//  impulse is gated by u > 0 and the velocity by finite positions)
+__device__ __forceinline__ float clamp5(float v) { return fminf(fmaxf(v, -5.0f), 5.0f); }
 
 // boundaryConditions (fluid.c:656-744)
 __device__ __forceinline__ float2 boundary(float2 p, const DevParams &P)

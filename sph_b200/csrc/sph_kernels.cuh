@@ -27,7 +27,9 @@ struct Rows { int b[3], e[3]; };
 // reference's 1.0f/r.
 __device__ __forceinline__ void r_and_recip(float r2, float &r, float &r_recip)
 {
-    r_recip = rsqrtf(r2);
+    // bare MUFU.RSQ: rsqrtf() wraps it in a denormal rescue (4 more instructions per pair); squared
+    // distances below 1.2e-38 are flushed and behave like coincident particles
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r_recip) : "f"(r2));
     r = r2 > 0.0f ? r2 * r_recip : 0.0f;
 }
 
@@ -530,24 +532,29 @@ k_density(const DevParams *__restrict__ Pp, int *__restrict__ counters,
             // acceptance mask of this row's first 64 candidates: k_relax works on the same positions and
             // the same ranges, so it iterates these bits instead of repeating ~60 distance tests
             unsigned long long m = 0ull;
-            const int b = R.b[dd];
+            const int b = R.b[dd], e = R.e[dd];
+            // the particle itself sits in its own row's range: walk [b, i) and (i, e) instead of paying a
+            // self test on every candidate (coincident OTHER particles do count: ratio 0)
+            const int self = (dd == 1 && i >= b && i < e) ? i : e;
+            for (int seg = 0; seg < 2; seg++) {
+                const int jb = seg == 0 ? b : self + 1, je = seg == 0 ? self : e;
 #pragma unroll 4
-            for (int j = b; j < R.e[dd]; j++) {
-                const float2 q = pos[j];
-                const float dx = q.x - p.x, dy = q.y - p.y;
-                const float r2 = dist2(dx, dy);
-                if (r2 > h2) continue;
-                if (r2 == 0.0f && j == i) continue;                     // self; coincident others do count (ratio 0)
-                if (j - b < 64) m |= 1ull << (j - b);
-                nn++;
-                float r, r_recip;
-                r_and_recip(r2, r, r_recip);
-                const float ratio = r * h_recip;
-                if (ratio < 1.0f) {
-                    const float omr = 1.0f - ratio;
-                    const float omr2 = omr * omr;
-                    d += omr2;
-                    dn += omr2 * omr;
+                for (int j = jb; j < je; j++) {
+                    const float2 q = pos[j];
+                    const float dx = q.x - p.x, dy = q.y - p.y;
+                    const float r2 = dist2(dx, dy);
+                    if (r2 > h2) continue;
+                    if (j - b < 64) m |= 1ull << (j - b);
+                    nn++;
+                    float r, r_recip;
+                    r_and_recip(r2, r, r_recip);
+                    const float ratio = r * h_recip;
+                    if (ratio < 1.0f) {
+                        const float omr = 1.0f - ratio;
+                        const float omr2 = omr * omr;
+                        d += omr2;
+                        dn += omr2 * omr;
+                    }
                 }
             }
             nmask[(size_t)dd * P.cap + i] = m;
