@@ -73,6 +73,14 @@ typedef struct sph_param {
 #define SPH_SPHERE_MOVER 0
 #define SPH_RECTANGLE_MOVER 1
 
+/* Sort-grid refinement.  Particles are binned into the reference's hash cells (side h, hash.c:35-47)
+ * subdivided SPH_CELL_DIV times per axis, and the neighbour search visits (2*DIV+1)^2 sub-cells: 5x5
+ * half-size cells cover 6.25 h^2 instead of the 9 h^2 of 3x3 full cells, i.e. 30% fewer distance tests.
+ * The reference cell id is exactly recoverable: floor(DIV * (x/h)) / DIV == floor(x/h) for DIV a power of
+ * two, because scaling an fp32 quotient by a power of two is exact.  The oracle's gather form uses the
+ * same constant so that both sum in the same order. */
+#define SPH_CELL_DIV 2
+
 /* reference capacities (fluid.c:174-175): detected, see sph_status */
 #define SPH_REF_MAX_BUCKET 100
 #define SPH_REF_MAX_NEIGHBORS 400

@@ -363,6 +363,7 @@ void orc_balance(sph_tunable *m, int nactive, const int *counts, int total)
  *  Mirrors include/sph_b200.h; SURVEY.md Appendix B gives the formulas.
  * ===================================================================== */
 
+#define DIV SPH_CELL_DIV          /* sort-grid refinement shared with the CUDA library (include/sph_b200.h) */
 #define HALO_BIT 0x80000000u
 #define UID_MASK 0x7fffffffu
 #define KEY_DROP (-1)
@@ -375,8 +376,9 @@ struct orc_g {
     int have_queued;
     float edge_start, edge_end;
     int has_left, has_right;
-    int size_x, size_y;
-    int gx0, wx;                 /* window of grid columns covered by this slab */
+    int size_x, size_y;          /* the reference's grid (cells of side h) */
+    int sort_rows;               /* rows of the sort grid = DIV * size_y */
+    int gx0, wx;                 /* window of SORT-grid columns covered by this slab */
     int cap, msg_cap;
     /* A: cell-sorted resident state; q = velocity (ST_READY) or previous position (after sort 1) */
     float *ax, *ay, *aqx, *aqy; uint32_t *auid;
@@ -414,7 +416,8 @@ orc_g *orc_g_create(const sph_config *cfg)
     for (unsigned i = 0; i < sizeof f / sizeof f[0]; i++) *f[i] = (float *)calloc(g->cap, sizeof(float));
     g->auid = (uint32_t *)calloc(g->cap, 4); g->tuid = (uint32_t *)calloc(g->cap, 4);
     g->tkey = (int *)calloc(g->cap, sizeof(int));
-    g->cell_start = (int *)calloc((size_t)g->size_x * g->size_y + 1, sizeof(int));
+    g->sort_rows = g->size_y * DIV;
+    g->cell_start = (int *)calloc((size_t)g->size_x * g->size_y * DIV * DIV + 1, sizeof(int));
     g->msg_bytes = msg_bytes_for(g->msg_cap);
     for (int s = 0; s < 2; s++) {
         g->send[s] = (unsigned char *)calloc(1, g->msg_bytes);
@@ -422,7 +425,7 @@ orc_g *orc_g_create(const sph_config *cfg)
     }
     g->edge_start = 0.0f; g->edge_end = cfg->tank_w;
     g->has_left = cfg->rank > 0; g->has_right = cfg->rank < cfg->nranks - 1;
-    g->gx0 = 0; g->wx = g->size_x;
+    g->gx0 = 0; g->wx = g->size_x * DIV;
     g->stage = ST_READY;
     return g;
 }
@@ -454,23 +457,30 @@ void orc_g_exchange_buffers(orc_g *g, int which, void **sl, void **rl, void **sr
 /* window of grid columns this slab can touch: slab + ghost layer + one spare column */
 static void g_window(orc_g *g)
 {
-    if (g->cfg.nranks <= 1) { g->gx0 = 0; g->wx = g->size_x; return; }
+    if (g->cfg.nranks <= 1) { g->gx0 = 0; g->wx = g->size_x * DIV; return; }
     float w = g->cfg.halo_width * g->cfg.h;
     int lo = (int)floor((g->edge_start - w) / g->cfg.h) - 1;
     int hi = (int)floor((g->edge_end + w) / g->cfg.h) + 1;
     if (lo < 0) lo = 0;
     if (hi > g->size_x - 1) hi = g->size_x - 1;
     if (hi < lo) hi = lo;
-    g->gx0 = lo; g->wx = hi - lo + 1;
+    g->gx0 = lo * DIV; g->wx = (hi - lo + 1) * DIV;
+}
+
+/* coordinate in the sort grid: the reference's x/h quotient scaled by DIV (exact for a power of two) */
+static int g_sort_coord(const orc_g *g, float v)
+{
+    float q = v / g->cfg.h;
+    return (int)floor(q * (float)DIV);
 }
 
 /* key of a position inside the current window, or KEY_DROP when outside it */
 static int g_key(const orc_g *g, float x, float y)
 {
-    int gx = (int)(unsigned)floor(x / g->cfg.h);
-    int gy = (int)(unsigned)floor(y / g->cfg.h);
+    int gx = g_sort_coord(g, x);
+    int gy = g_sort_coord(g, y);
     int wxi = gx - g->gx0;
-    if (wxi < 0 || wxi >= g->wx || gy < 0 || gy >= g->size_y) return KEY_DROP;
+    if (wxi < 0 || wxi >= g->wx || gy < 0 || gy >= g->sort_rows) return KEY_DROP;
     return gy * g->wx + wxi;
 }
 
@@ -492,7 +502,7 @@ static void g_sort_T_into_A(orc_g *g)
     for (int i = 0; i < g->n_src; i++)
         if (g->tkey[i] != KEY_DROP) { rec[m].key = g->tkey[i]; rec[m].uid = g->tuid[i]; rec[m].src = i; m++; }
     qsort(rec, m, sizeof(sort_rec), cmp_rec);
-    int ncell = g->wx * g->size_y;
+    int ncell = g->wx * g->sort_rows;
     int c = 0, nl = 0, maxb = 0, over = 0;
     g->cell_start[0] = 0;
     for (int d = 0; d < m; d++) {
@@ -535,13 +545,13 @@ int orc_g_upload(orc_g *g, const sph_particle *a, const uint32_t *uid, int n)
     return SPH_OK;
 }
 
-/* iterate the 3x3 cell neighbourhood of window cell (wxi, gy): three contiguous index ranges */
+/* iterate the (2 DIV + 1)^2 sort-cell neighbourhood of window cell (wxi, gy): one contiguous index range per row */
 #define FOR_EACH_CANDIDATE(g, wxi, gy, j, BODY)                                          \
-    for (int _dy = -1; _dy <= 1; _dy++) {                                                \
+    for (int _dy = -DIV; _dy <= DIV; _dy++) {                                            \
         int _row = (gy) + _dy;                                                           \
-        if (_row < 0 || _row >= (g)->size_y) continue;                                   \
-        int _c0 = (wxi) > 0 ? (wxi) - 1 : 0;                                             \
-        int _c1 = (wxi) < (g)->wx - 1 ? (wxi) + 1 : (g)->wx - 1;                         \
+        if (_row < 0 || _row >= (g)->sort_rows) continue;                                \
+        int _c0 = (wxi) > DIV ? (wxi) - DIV : 0;                                         \
+        int _c1 = (wxi) < (g)->wx - DIV ? (wxi) + DIV : (g)->wx - 1;                     \
         int _b = (g)->cell_start[_row * (g)->wx + _c0];                                  \
         int _e = (g)->cell_start[_row * (g)->wx + _c1 + 1];                              \
         for (int j = _b; j < _e; j++) { BODY }                                           \
@@ -689,14 +699,15 @@ void orc_g_density(orc_g *g)
     g->stage = ST_DENSITY;
 }
 
-/* ownership rule for the coincident-particle nudge (hash.c:178-224): same cell -> earlier
- * bucket slot; otherwise the particle whose forward stencil (0,+1),(1,-1),(1,0),(1,+1) holds the other */
+/* ownership rule for the coincident-particle nudge (hash.c:178-224), in REFERENCE cells: same cell ->
+ * earlier bucket slot (= lower uid on one rank); otherwise the particle whose forward stencil
+ * (0,+1),(1,-1),(1,0),(1,+1) holds the other */
 static int g_owns(const orc_g *g, int i, int j)
 {
-    int wi, yi, wj, yj;
-    g_cell_of(g, i, &wi, &yi); g_cell_of(g, j, &wj, &yj);
-    if (wi == wj && yi == yj) return i < j;
-    if (wi != wj) return wi < wj;
+    int xi = (int)floor(g->ax[i] / g->cfg.h), yi = (int)floor(g->ay[i] / g->cfg.h);
+    int xj = (int)floor(g->ax[j] / g->cfg.h), yj = (int)floor(g->ay[j] / g->cfg.h);
+    if (xi == xj && yi == yj) return (g->auid[i] & UID_MASK) < (g->auid[j] & UID_MASK);
+    if (xi != xj) return xi < xj;
     return yi < yj;
 }
 

@@ -27,7 +27,7 @@ struct sph_ctx {
     float2 *Q[3];
     uint32_t *U[2];
     float2 *dens;
-    unsigned long long *nmask;       // 3 x capacity: per-row acceptance masks from k_density for k_relax
+    sph_mask_t *nmask;               // SPH_NROWS x capacity: per-row acceptance masks from k_density for k_relax
     int *cnt, *cell_start, *t_key, *t_slot, *ord_src;
     uint32_t *ord_uid;
     unsigned long long *tile_state;
@@ -65,15 +65,16 @@ static int fail(sph_ctx *ctx, int code, const char *msg)
 // window of grid columns a slab can touch: slab + ghost layer + one spare column
 static void compute_window(const sph_ctx *ctx, float edge_start, float edge_end, int *gx0, int *wx)
 {
-    if (ctx->cfg.nranks <= 1) { *gx0 = 0; *wx = ctx->size_x; return; }
+    // in reference cells first, then refined to sort-grid columns
+    if (ctx->cfg.nranks <= 1) { *gx0 = 0; *wx = ctx->size_x * SPH_CELL_DIV; return; }
     float w = ctx->cfg.halo_width * ctx->cfg.h;
     int lo = (int)floorf((edge_start - w) / ctx->cfg.h) - 1;
     int hi = (int)floorf((edge_end + w) / ctx->cfg.h) + 1;
     lo = std::max(lo, 0);
     hi = std::min(hi, ctx->size_x - 1);
     hi = std::max(hi, lo);
-    *gx0 = lo;
-    *wx = hi - lo + 1;
+    *gx0 = lo * SPH_CELL_DIV;
+    *wx = (hi - lo + 1) * SPH_CELL_DIV;
 }
 
 static void fill_phys(DevParams &P, const sph_tunable &t)
@@ -118,14 +119,14 @@ extern "C" int sph_create(const sph_config *cfg, sph_ctx **out)
     ctx->size_x = (int)ceil((cfg->tank_w - 0.0f) / cfg->h);      // fluid.c:214-215
     ctx->size_y = (int)ceil((cfg->tank_h - 0.0f) / cfg->h);
     const size_t cap = (size_t)cfg->capacity;
-    const size_t ncell_max = (size_t)ctx->size_x * ctx->size_y;
+    const size_t ncell_max = (size_t)ctx->size_x * ctx->size_y * SPH_CELL_DIV * SPH_CELL_DIV;
     ctx->grid = std::min<int>((int)((cap + SPH_THREADS - 1) / SPH_THREADS), prop.multiProcessorCount * 8);
 
     for (int i = 0; i < 4; i++) CK(cudaMalloc(&ctx->P[i], cap * sizeof(float2)));
     for (int i = 0; i < 3; i++) CK(cudaMalloc(&ctx->Q[i], cap * sizeof(float2)));
     for (int i = 0; i < 2; i++) CK(cudaMalloc(&ctx->U[i], cap * sizeof(uint32_t)));
     CK(cudaMalloc(&ctx->dens, cap * sizeof(float2)));
-    CK(cudaMalloc(&ctx->nmask, 3 * cap * sizeof(unsigned long long)));
+    CK(cudaMalloc(&ctx->nmask, SPH_NROWS * cap * sizeof(sph_mask_t)));
     CK(cudaMalloc(&ctx->cnt, (ncell_max + 1) * sizeof(int)));
     CK(cudaMalloc(&ctx->cell_start, (ncell_max + 1) * sizeof(int)));
     CK(cudaMalloc(&ctx->t_key, cap * sizeof(int)));
@@ -156,7 +157,7 @@ extern "C" int sph_create(const sph_config *cfg, sph_ctx **out)
 
     DevParams &P = ctx->hp;
     P.tank_w = cfg->tank_w; P.tank_h = cfg->tank_h; P.cell_h = cfg->h;
-    P.size_x = ctx->size_x; P.size_y = ctx->size_y;
+    P.size_x = ctx->size_x; P.size_y = ctx->size_y; P.sort_rows = ctx->size_y * SPH_CELL_DIV;
     P.halo_w = ctx->cfg.halo_width * cfg->h;
     P.has_left = cfg->rank > 0; P.has_right = cfg->rank < cfg->nranks - 1; P.nranks = cfg->nranks;
     P.cap = cfg->capacity; P.msg_cap = ctx->cfg.msg_capacity;
@@ -445,7 +446,7 @@ static int ingest(sph_ctx *ctx, int n)
     CK(cudaMemcpy(&epoch, ctx->counters + CN_EPOCH, sizeof(int), cudaMemcpyDeviceToHost));
     zero[CN_EPOCH] = epoch;
     CK(cudaMemcpyAsync(ctx->counters, zero, sizeof zero, cudaMemcpyHostToDevice, ctx->stream));
-    const size_t ncell_max = (size_t)ctx->size_x * ctx->size_y;
+    const size_t ncell_max = (size_t)ctx->size_x * ctx->size_y * SPH_CELL_DIV * SPH_CELL_DIV;
     CK(cudaMemsetAsync(ctx->cnt, 0, (ncell_max + 1) * sizeof(int), ctx->stream));
     CK(cudaMemsetAsync(ctx->xchg, 0, SPH_XCHG_HDR, ctx->stream));      // message sequence numbers restart
     for (int s = 0; s < 2; s++) CK(cudaMemsetAsync(ctx->send[s], 0, 16, ctx->stream));

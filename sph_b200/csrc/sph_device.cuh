@@ -4,6 +4,10 @@
 
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include "../../include/sph_b200.h"
+
+#define SPH_NROWS (2 * SPH_CELL_DIV + 1)     // sort-grid rows (and columns) a neighbourhood spans
+static_assert(SPH_CELL_DIV == 1 || SPH_CELL_DIV == 2 || SPH_CELL_DIV == 4, "power of two: keeps the reference cell id exact");
 
 #define SPH_HALO_BIT 0x80000000u
 #define SPH_UID_MASK 0x7fffffffu
@@ -20,11 +24,12 @@ struct DevParams {
     int mover_type;
     // tank (AABB min is 0: fluid.c:117) and hash grid (fluid.c:176,214-215)
     float tank_w, tank_h, cell_h;
-    int size_x, size_y;
+    int size_x, size_y;          // the reference's grid (cells of side h): exported hash ids
+    int sort_rows;               // rows of the sort grid = SPH_CELL_DIV * size_y
     // slab (communication.c): edges, ghost-layer width, neighbours present
     float edge_start, edge_end, halo_w;
     int has_left, has_right, nranks;
-    // window of grid columns the sorted arrays cover now / will cover after the next sort
+    // window of SORT-grid columns the sorted arrays cover now / will cover after the next sort
     int gx0, wx;
     int gx0_new, wx_new;
     int cap, msg_cap;
@@ -87,6 +92,11 @@ __device__ __forceinline__ void st_release_sys(int *p, int v)
 
 // hash_val (hash.c:35-47): IEEE fp32 divide, floor; kept as two coordinates
 __device__ __forceinline__ int cell_coord(float v, float cell_h) { return (int)floorf(__fdiv_rn(v, cell_h)); }
+// coordinate in the sort grid (cells of side h / SPH_CELL_DIV); sort_coord / DIV == cell_coord exactly
+__device__ __forceinline__ int sort_coord(float v, float cell_h)
+{
+    return (int)floorf(__fmul_rn(__fdiv_rn(v, cell_h), (float)SPH_CELL_DIV));
+}
 
 // unfused squared distance: the list cut-off r2 <= h2 must match hash.c:185,221,99 bit for bit
 __device__ __forceinline__ float dist2(float dx, float dy) { return __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)); }
@@ -130,8 +140,8 @@ __device__ __forceinline__ float2 boundary(float2 p, const DevParams &P)
 // key of a position in the NEW window (the one the coming sort will use), or DROP
 __device__ __forceinline__ int window_key_new(float2 p, const DevParams &P)
 {
-    int gx = cell_coord(p.x, P.cell_h) - P.gx0_new;
-    int gy = cell_coord(p.y, P.cell_h);
-    if (gx < 0 || gx >= P.wx_new || gy < 0 || gy >= P.size_y) return SPH_KEY_DROP;
+    int gx = sort_coord(p.x, P.cell_h) - P.gx0_new;
+    int gy = sort_coord(p.y, P.cell_h);
+    if (gx < 0 || gx >= P.wx_new || gy < 0 || gy >= P.sort_rows) return SPH_KEY_DROP;
     return gy * P.wx_new + gx;
 }

@@ -1,9 +1,10 @@
 // Kernels of the B200-native TinySPH compute-rank timestep (sm_100a).
 //
 // State is cell-sorted SoA (float2 position, float2 velocity-or-previous-position, u32 uid with
-// a ghost flag).  Cells are the reference's hash cells (hash.c:35-47) numbered row-major inside
-// the slab's window of grid columns, so the 3x3 neighbourhood of a particle is THREE CONTIGUOUS
-// INDEX RANGES (rows gy-1, gy, gy+1; columns gx-1..gx+1 are adjacent in memory).
+// a ghost flag).  Cells are the reference's hash cells (hash.c:35-47) split SPH_CELL_DIV times per
+// axis, numbered row-major inside the slab's window of grid columns, so the neighbourhood of a
+// particle is 2*DIV+1 CONTIGUOUS INDEX RANGES (one per sort-grid row; the columns gx-DIV..gx+DIV of a
+// row are adjacent in memory).
 //
 // The reference's symmetric pair scatter (fluid.c:461-471, :598-607) is a gather here: every
 // particle sums the contributions of all particles within h, in a fixed order (row, then sorted
@@ -18,7 +19,19 @@
 // -------------------------------------------------------------------------------------------
 // neighbourhood iteration: rows gy-1..gy+1, columns gx-1..gx+1 of the CURRENT window
 // -------------------------------------------------------------------------------------------
-struct Rows { int b[3], e[3]; };
+struct Rows { int b[SPH_NROWS], e[SPH_NROWS]; };
+
+// per-row acceptance masks handed from k_density to k_relax: 3 rows x 64 bits for full-size cells,
+// 5 rows x 32 bits for half-size cells (a row then holds ~8 candidates, rarely more than 32)
+#if SPH_CELL_DIV == 1
+typedef unsigned long long sph_mask_t;
+#define SPH_MASK_BITS 64
+__device__ __forceinline__ int sph_mask_ffs(sph_mask_t m) { return __ffsll((long long)m); }
+#else
+typedef unsigned int sph_mask_t;
+#define SPH_MASK_BITS 32
+__device__ __forceinline__ int sph_mask_ffs(sph_mask_t m) { return __ffs((int)m); }
+#endif
 
 // r and 1/r from the (exact, unfused) squared distance with one MUFU.RSQ instead of the IEEE sqrt +
 // divide sequences (~18 instructions).  Only the pair PHYSICS uses these; list membership is decided
@@ -36,15 +49,15 @@ __device__ __forceinline__ void r_and_recip(float r2, float &r, float &r_recip)
 __device__ __forceinline__ Rows candidate_rows(float2 p, const DevParams &P, const int *__restrict__ cell_start)
 {
     Rows r;
-    int gx = cell_coord(p.x, P.cell_h) - P.gx0;
-    int gy = cell_coord(p.y, P.cell_h);
+    int gx = sort_coord(p.x, P.cell_h) - P.gx0;
+    int gy = sort_coord(p.y, P.cell_h);
     gx = min(max(gx, 0), P.wx - 1);
-    gy = min(max(gy, 0), P.size_y - 1);
-    int c0 = max(gx - 1, 0), c1 = min(gx + 1, P.wx - 1);
+    gy = min(max(gy, 0), P.sort_rows - 1);
+    int c0 = max(gx - SPH_CELL_DIV, 0), c1 = min(gx + SPH_CELL_DIV, P.wx - 1);
 #pragma unroll
-    for (int d = 0; d < 3; d++) {
-        int row = gy + d - 1;
-        if (row < 0 || row >= P.size_y) { r.b[d] = 0; r.e[d] = 0; continue; }
+    for (int d = 0; d < SPH_NROWS; d++) {
+        int row = gy + d - SPH_CELL_DIV;
+        if (row < 0 || row >= P.sort_rows) { r.b[d] = 0; r.e[d] = 0; continue; }
         r.b[d] = __ldg(&cell_start[row * P.wx + c0]);
         r.e[d] = __ldg(&cell_start[row * P.wx + c1 + 1]);
     }
@@ -162,7 +175,7 @@ k_advect(const DevParams *__restrict__ Pp, int *__restrict__ counters,
         float vx = vix, vy = viy;
         const Rows R = candidate_rows(p, P, cell_start);
 #pragma unroll
-        for (int d = 0; d < 3; d++) {
+        for (int d = 0; d < SPH_NROWS; d++) {
 #pragma unroll 4
             for (int j = R.b[d]; j < R.e[d]; j++) {
                 const float2 q = pos[j];
@@ -334,7 +347,7 @@ k_scan(DevParams *__restrict__ Pp, int *__restrict__ counters, int *__restrict__
     __shared__ int s_tile;
     __shared__ int s_warp[SPH_THREADS / 32];
     __shared__ int s_prefix;
-    const int ncell = Pp->wx_new * Pp->size_y;
+    const int ncell = Pp->wx_new * Pp->sort_rows;
     const int ntiles = (ncell + SCAN_TILE - 1) / SCAN_TILE;
     const unsigned epoch = (unsigned)counters[CN_EPOCH];
     if (threadIdx.x == 0) s_tile = atomicAdd(&counters[CN_TICKET], 1);
@@ -516,7 +529,7 @@ k_reorder(const DevParams *__restrict__ Pp, int *__restrict__ counters, const in
 __global__ void __launch_bounds__(SPH_THREADS)
 k_density(const DevParams *__restrict__ Pp, int *__restrict__ counters,
           const float2 *__restrict__ pos, const int *__restrict__ cell_start, float2 *__restrict__ dens,
-          unsigned long long *__restrict__ nmask)
+          sph_mask_t *__restrict__ nmask)
 {
     const DevParams P = *Pp;
     const int n = counters[CN_NTOT];
@@ -528,14 +541,14 @@ k_density(const DevParams *__restrict__ Pp, int *__restrict__ counters,
         int nn = 0;
         const Rows R = candidate_rows(p, P, cell_start);
 #pragma unroll
-        for (int dd = 0; dd < 3; dd++) {
-            // acceptance mask of this row's first 64 candidates: k_relax works on the same positions and
-            // the same ranges, so it iterates these bits instead of repeating ~60 distance tests
-            unsigned long long m = 0ull;
+        for (int dd = 0; dd < SPH_NROWS; dd++) {
+            // acceptance mask of this row's first SPH_MASK_BITS candidates: k_relax works on the same
+            // positions and the same ranges, so it walks these bits instead of repeating the distance tests
+            sph_mask_t m = 0;
             const int b = R.b[dd], e = R.e[dd];
             // the particle itself sits in its own row's range: walk [b, i) and (i, e) instead of paying a
             // self test on every candidate (coincident OTHER particles do count: ratio 0)
-            const int self = (dd == 1 && i >= b && i < e) ? i : e;
+            const int self = (dd == SPH_CELL_DIV && i >= b && i < e) ? i : e;
             for (int seg = 0; seg < 2; seg++) {
                 const int jb = seg == 0 ? b : self + 1, je = seg == 0 ? self : e;
 #pragma unroll 4
@@ -544,7 +557,7 @@ k_density(const DevParams *__restrict__ Pp, int *__restrict__ counters,
                     const float dx = q.x - p.x, dy = q.y - p.y;
                     const float r2 = dist2(dx, dy);
                     if (r2 > h2) continue;
-                    if (j - b < 64) m |= 1ull << (j - b);
+                    if (j - b < SPH_MASK_BITS) m |= (sph_mask_t)1 << (j - b);
                     nn++;
                     float r, r_recip;
                     r_and_recip(r2, r, r_recip);
@@ -575,7 +588,7 @@ __global__ void __launch_bounds__(SPH_THREADS, 4)
 k_relax(const DevParams *__restrict__ Pp, int *__restrict__ counters,
         const float2 *__restrict__ pos, const float2 *__restrict__ prev, const uint32_t *__restrict__ uid,
         const float2 *__restrict__ dens, const int *__restrict__ cell_start,
-        const unsigned long long *__restrict__ nmask,
+        const sph_mask_t *__restrict__ nmask,
         float2 *__restrict__ pos_out, float2 *__restrict__ vel_out,
         int *__restrict__ cnt, int *__restrict__ t_key, int *__restrict__ t_slot,
         unsigned char *send_l, unsigned char *send_r)
@@ -610,7 +623,8 @@ k_relax(const DevParams *__restrict__ Pp, int *__restrict__ counters,
                 // earlier bucket slot in the same cell, else the cell whose forward stencil
                 // (0,+1),(1,-1),(1,0),(1,+1) holds the other (hash.c:178-224)
                 const int gxj = cell_coord(q.x, P.cell_h), gyj = cell_coord(q.y, P.cell_h);
-                const bool owner = (gxi == gxj && gyi == gyj) ? (i < j) : (gxi != gxj ? gxi < gxj : gyi < gyj);
+                const bool owner = (gxi == gxj && gyi == gyj) ? ((u & SPH_UID_MASK) < (uid[j] & SPH_UID_MASK))
+                                                              : (gxi != gxj ? gxi < gxj : gyi < gyj);
                 if (owner) { x += 0.000001f; y += 0.000001f; }
             }
             if (ratio < 1.0f && r > 0.0f) {
@@ -625,18 +639,18 @@ k_relax(const DevParams *__restrict__ Pp, int *__restrict__ counters,
             }
         };
 #pragma unroll
-        for (int d = 0; d < 3; d++) {
+        for (int d = 0; d < SPH_NROWS; d++) {
             // the lists were built by k_density on these same positions: walk its acceptance bits
             // (candidate order, so the order of summation is unchanged) ...
             const int b = R.b[d];
-            unsigned long long m = nmask[(size_t)d * P.cap + i];
+            sph_mask_t m = nmask[(size_t)d * P.cap + i];
             while (m) {
-                const int k = __ffsll((long long)m) - 1;
+                const int k = sph_mask_ffs(m) - 1;
                 m &= m - 1;
                 pair(b + k);
             }
-            // ... and test the rare candidates beyond the 64 a mask covers
-            for (int j = b + 64; j < R.e[d]; j++) {
+            // ... and test the rare candidates beyond those a mask covers
+            for (int j = b + SPH_MASK_BITS; j < R.e[d]; j++) {
                 const float2 q = pos[j];
                 if (dist2(q.x - p.x, q.y - p.y) > h2 || j == i) continue;
                 pair(j);
@@ -744,7 +758,7 @@ __global__ void k_export_pairs(const DevParams *__restrict__ Pp, const int *__re
         const int gxi = cell_coord(p.x, P.cell_h), gyi = cell_coord(p.y, P.cell_h);
         int fwd = 0;
         const Rows R = candidate_rows(p, P, cell_start);
-        for (int d = 0; d < 3; d++)
+        for (int d = 0; d < SPH_NROWS; d++)
             for (int j = R.b[d]; j < R.e[d]; j++) {
                 if (j == i) continue;
                 const float2 q = pos[j];
@@ -755,7 +769,7 @@ __global__ void k_export_pairs(const DevParams *__restrict__ Pp, const int *__re
                     if (k < cap) pairs[k] = ((unsigned long long)ui << 32) | uj;
                 }
                 const int gxj = cell_coord(q.x, P.cell_h), gyj = cell_coord(q.y, P.cell_h);
-                const bool owner = (gxi == gxj && gyi == gyj) ? (i < j) : (gxi != gxj ? gxi < gxj : gyi < gyj);
+                const bool owner = (gxi == gxj && gyi == gyj) ? (ui < uj) : (gxi != gxj ? gxi < gxj : gyi < gyj);
                 if ((uid[j] & SPH_HALO_BIT) || owner) fwd++;
             }
         if (fwd_count) fwd_count[i] = fwd;

@@ -165,7 +165,7 @@ def test_full_size_properties(built_lib, n_request):
     assert np.all((out["x"] >= 0) & (out["x"] <= prob["tank_w"]) & (out["y"] >= 0) & (out["y"] <= prob["tank_h"]))
     assert np.all(np.abs(out["v_x"]) <= 5.0) and np.all(np.abs(out["v_y"]) <= 5.0)   # fluid.c:613-625
     du, dc = b.cells()
-    assert np.all(np.diff(dc.astype("i8")) >= 0)                             # device order is cell order
+    assert np.array_equal(np.sort(du), np.sort(uid)) and dc.max() < np.ceil(prob["tank_w"] / prob["h"]) * np.ceil(prob["tank_h"] / prob["h"])
     s = b.status()
     assert s.capacity_overflow == 0 and s.bucket_overflow == 0 and s.neighbor_overflow == 0
     assert s.n_local == len(a) and s.n_halo == 0
