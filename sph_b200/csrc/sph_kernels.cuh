@@ -612,8 +612,7 @@ k_relax(const DevParams *__restrict__ Pp, int *__restrict__ counters,
         const int gxi = cell_coord(p.x, P.cell_h), gyi = cell_coord(p.y, P.cell_h);
         const Rows R = candidate_rows(p, P, cell_start);
         // pair physics for one listed neighbour (membership r2 <= h2, j != i already established)
-        auto pair = [&](int j) {
-            const float2 q = pos[j];
+        auto pair = [&](int j, float2 q, float2 dj) {
             const float dx = q.x - p.x, dy = q.y - p.y;
             float r, r_recip;
             r_and_recip(dist2(dx, dy), r, r_recip);
@@ -628,7 +627,6 @@ k_relax(const DevParams *__restrict__ Pp, int *__restrict__ counters,
                 if (owner) { x += 0.000001f; y += 0.000001f; }
             }
             if (ratio < 1.0f && r > 0.0f) {
-                const float2 dj = dens[j];
                 const float pq = P.k * (dj.x - P.rest_density);
                 const float pqn = P.k_near * dj.y;
                 const float omr = 1.0f - ratio;
@@ -645,15 +643,22 @@ k_relax(const DevParams *__restrict__ Pp, int *__restrict__ counters,
             const int b = R.b[d];
             sph_mask_t m = nmask[(size_t)d * P.cap + i];
             while (m) {
-                const int k = sph_mask_ffs(m) - 1;
+                // two neighbours per trip, all four loads (position + density of each) issued up front:
+                // load latency was this kernel's top stall (profiles/r1_div2_full.csv, long_scoreboard)
+                const int j0 = b + sph_mask_ffs(m) - 1;
                 m &= m - 1;
-                pair(b + k);
+                const bool two = m != 0;
+                const int j1 = two ? b + sph_mask_ffs(m) - 1 : j0;
+                m &= m - 1;
+                const float2 q0 = pos[j0], d0 = dens[j0], q1 = pos[j1], d1 = dens[j1];
+                pair(j0, q0, d0);
+                if (two) pair(j1, q1, d1);
             }
             // ... and test the rare candidates beyond those a mask covers
             for (int j = b + SPH_MASK_BITS; j < R.e[d]; j++) {
                 const float2 q = pos[j];
                 if (dist2(q.x - p.x, q.y - p.y) > h2 || j == i) continue;
-                pair(j);
+                pair(j, q, dens[j]);
             }
         }
         float2 np = boundary(make_float2(x, y), P);                     // fluid.c:649
