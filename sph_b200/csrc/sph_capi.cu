@@ -28,7 +28,7 @@ struct sph_ctx {
     uint32_t *U[2];
     float2 *dens;
     sph_mask_t *nmask;               // SPH_NROWS x capacity: per-row acceptance masks from k_density for k_relax
-    int *cnt, *cell_start, *t_key, *t_slot, *ord_src;
+    int *cnt, *cell_start, *t_key, *t_slot, *ord_src, *ord_key;
     uint32_t *ord_uid;
     unsigned long long *tile_state;
     unsigned char *send[2], *recv[2];
@@ -132,6 +132,7 @@ extern "C" int sph_create(const sph_config *cfg, sph_ctx **out)
     CK(cudaMalloc(&ctx->t_key, cap * sizeof(int)));
     CK(cudaMalloc(&ctx->t_slot, cap * sizeof(int)));
     CK(cudaMalloc(&ctx->ord_src, cap * sizeof(int)));
+    CK(cudaMalloc(&ctx->ord_key, cap * sizeof(int)));
     CK(cudaMalloc(&ctx->ord_uid, cap * sizeof(uint32_t)));
     CK(cudaMalloc(&ctx->coords, cap * sizeof(short2)));
     const size_t ntiles_max = (ncell_max + SCAN_TILE - 1) / SCAN_TILE + 1;
@@ -181,7 +182,7 @@ extern "C" void sph_destroy(sph_ctx *ctx)
     for (int i = 0; i < 3; i++) cudaFree(ctx->Q[i]);
     for (int i = 0; i < 2; i++) cudaFree(ctx->U[i]);
     cudaFree(ctx->dens); cudaFree(ctx->nmask); cudaFree(ctx->cnt); cudaFree(ctx->cell_start); cudaFree(ctx->t_key);
-    cudaFree(ctx->t_slot); cudaFree(ctx->ord_src); cudaFree(ctx->ord_uid); cudaFree(ctx->coords);
+    cudaFree(ctx->t_slot); cudaFree(ctx->ord_src); cudaFree(ctx->ord_key); cudaFree(ctx->ord_uid); cudaFree(ctx->coords);
     cudaFree(ctx->tile_state); cudaFree(ctx->counters); cudaFree(ctx->dp);
     for (int s = 0; s < 2; s++) { cudaFree(ctx->send[s]); cudaFree(ctx->recv[s]); }
     for (int s = 0; s < 2; s++) if (ctx->peer[s]) cudaIpcCloseMemHandle(ctx->peer[s]);
@@ -301,8 +302,8 @@ static int launch_sort(sph_ctx *ctx, int which, bool with_unpack = true)
                                                             ctx->cfg.nranks > 1 ? ctx->send[1] : nullptr,
                                                             (which == 1 && with_unpack) ? 1 : 0);
     k_scatter<<<ctx->grid, SPH_THREADS, 0, ctx->stream>>>(ctx->counters, ctx->cell_start, ctx->t_key, ctx->t_slot, su,
-                                                          ctx->ord_uid, ctx->ord_src);
-    k_reorder<<<ctx->grid, SPH_THREADS, 0, ctx->stream>>>(ctx->dp, ctx->counters, ctx->cell_start, ctx->t_key,
+                                                          ctx->ord_uid, ctx->ord_src, ctx->ord_key);
+    k_reorder<<<ctx->grid, SPH_THREADS, 0, ctx->stream>>>(ctx->dp, ctx->counters, ctx->cell_start, ctx->ord_key,
                                                           ctx->ord_uid, ctx->ord_src, sp, sq, dp, dq, du);
     ctx->launches += 3;
     ctx->hp.gx0 = ctx->hp.gx0_new;     // the scan kernel did the same on the device

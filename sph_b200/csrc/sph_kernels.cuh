@@ -346,6 +346,7 @@ k_scan(DevParams *__restrict__ Pp, int *__restrict__ counters, int *__restrict__
 {
     __shared__ int s_tile;
     __shared__ int s_warp[SPH_THREADS / 32];
+    __shared__ int s_wmax[SPH_THREADS / 32], s_wover[SPH_THREADS / 32];
     __shared__ int s_prefix;
     const int ncell = Pp->wx_new * Pp->sort_rows;
     const int ntiles = (ncell + SCAN_TILE - 1) / SCAN_TILE;
@@ -397,10 +398,7 @@ k_scan(DevParams *__restrict__ Pp, int *__restrict__ counters, int *__restrict__
     mx = __reduce_max_sync(0xffffffffu, mx);
     over = __reduce_add_sync(0xffffffffu, over);
     if (lane == 31) s_warp[warp] = inc;
-    if (lane == 0) {
-        if (mx > 0) atomicMax(&counters[CN_MAX_BUCKET], mx);
-        if (over > 0) atomicAdd(&counters[CN_BUCKET_OVER], over);
-    }
+    if (lane == 0) { s_wmax[warp] = mx; s_wover[warp] = over; }
     __syncthreads();
     int warp_off = 0, block_total = 0;
 #pragma unroll
@@ -408,6 +406,15 @@ k_scan(DevParams *__restrict__ Pp, int *__restrict__ counters, int *__restrict__
         const int sw = s_warp[w];
         if (w < warp) warp_off += sw;
         block_total += sw;
+    }
+    if (threadIdx.x == 0) {
+        // one atomic per block: per-warp atomics on these two addresses serialised in L2 and made up
+        // most of this kernel's time
+        int bmx = 0, bover = 0;
+#pragma unroll
+        for (int w = 0; w < SPH_THREADS / 32; w++) { bmx = max(bmx, s_wmax[w]); bover += s_wover[w]; }
+        if (bmx > 0) atomicMax(&counters[CN_MAX_BUCKET], bmx);
+        if (bover > 0) atomicAdd(&counters[CN_BUCKET_OVER], bover);
     }
     // publish this tile's total, then add up every preceding tile's total (one warp)
     if (warp == 0) {
@@ -476,7 +483,7 @@ k_scan(DevParams *__restrict__ Pp, int *__restrict__ counters, int *__restrict__
 __global__ void __launch_bounds__(SPH_THREADS)
 k_scatter(const int *__restrict__ counters, const int *__restrict__ cell_start,
           const int *__restrict__ t_key, const int *__restrict__ t_slot, const uint32_t *__restrict__ src_uid,
-          uint32_t *__restrict__ ord_uid, int *__restrict__ ord_src)
+          uint32_t *__restrict__ ord_uid, int *__restrict__ ord_src, int *__restrict__ ord_key)
 {
     const int n = counters[CN_NSRC];
     for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) {
@@ -487,6 +494,7 @@ k_scatter(const int *__restrict__ counters, const int *__restrict__ cell_start,
         if (key & SPH_KEY_EMIG) u |= SPH_HALO_BIT;
         ord_uid[d] = u;
         ord_src[d] = s;
+        ord_key[d] = key & SPH_KEY_MASK;
     }
 }
 
@@ -496,23 +504,25 @@ k_scatter(const int *__restrict__ counters, const int *__restrict__ cell_start,
 // -------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(SPH_THREADS)
 k_reorder(const DevParams *__restrict__ Pp, int *__restrict__ counters, const int *__restrict__ cell_start,
-          const int *__restrict__ t_key, const uint32_t *__restrict__ ord_uid, const int *__restrict__ ord_src,
+          const int *__restrict__ ord_key, const uint32_t *__restrict__ ord_uid, const int *__restrict__ ord_src,
           const float2 *__restrict__ src_pos, const float2 *__restrict__ src_q,
           float2 *__restrict__ dst_pos, float2 *__restrict__ dst_q, uint32_t *__restrict__ dst_uid)
 {
     const int n = counters[CN_NTOT];
     int locals = 0;
     for (int d = blockIdx.x * blockDim.x + threadIdx.x; d < n; d += gridDim.x * blockDim.x) {
+        // three levels of dependent loads instead of five: (src, uid, key) | (payload, cell bounds) | cell uids
         const int s = ord_src[d];
         const uint32_t u = ord_uid[d];
-        const int key = t_key[s] & SPH_KEY_MASK;
+        const int key = ord_key[d];
+        const float2 pp = src_pos[s], qq = src_q[s];
         const int b = cell_start[key], e = cell_start[key + 1];
         const uint32_t um = u & SPH_UID_MASK;
         int rank = 0;
         for (int k = b; k < e; k++) rank += (ord_uid[k] & SPH_UID_MASK) < um;
         const int dst = b + rank;
-        dst_pos[dst] = src_pos[s];
-        dst_q[dst] = src_q[s];
+        dst_pos[dst] = pp;
+        dst_q[dst] = qq;
         dst_uid[dst] = u;
         locals += !(u & SPH_HALO_BIT);
     }
