@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- particle-steps/s of the TinySPH compute-rank timestep on B200.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--n PARTICLES]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--particles PER_GPU]
 
 Workload (BASELINE.json configs[1]): 2-D dam-break block, 1 M particles per GPU, default fluid
 preset 'x', lattice spacing and h of the reference (s0 = 0.2905, h = 0.5809), tank scaled so the
@@ -179,6 +179,13 @@ def main_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    import faulthandler
+    import signal
+    faulthandler.register(signal.SIGUSR1, all_threads=True)     # kill -USR1 <pid>: where is it stuck?
+
+    def mark(msg):
+        if os.environ.get("SPH_BENCH_TRACE"):
+            print(f"[bench rank {rank}] {msg} t={time.time():.1f}", file=sys.stderr, flush=True)
     # stdout carries exactly one JSON line: libraries that chat on fd 1 (NCCL prints its version there)
     # are sent to stderr until the result is printed
     sys.stdout.flush()
@@ -214,12 +221,16 @@ def main_ours(args):
         else:
             from sph_b200.slab import SlabRunner
             sim = SlabRunner(prob, t, rank, world, stream, capacity_factor=2.0)
+        mark("created")
         sim.init_lattice()
+        mark("lattice")
         sampler = ClockSampler(local_rank)   # nvidia-smi needs ~0.2 s to start: begin before the pre-roll,
         sampler.start()                      # stop after the last measured phase; everything in between is load
         sim.run(args.preroll)
+        mark("preroll enqueued")
         sim.run(args.warmup)
         barrier()
+        mark("warm")
         launches0 = sim.launches
         if os.environ.get("SPH_PROFILE"):      # ncu --profile-from-start off: instrument the timed region only
             torch.cuda.profiler.start()
@@ -232,6 +243,7 @@ def main_ours(args):
             sim.run(1)
             ev[k][1].record(stream)
         barrier()
+        mark("timed")
         wall = time.perf_counter() - wall0
         launches = sim.launches - launches0
         if os.environ.get("SPH_PROFILE"):
@@ -245,11 +257,15 @@ def main_ours(args):
         barrier()
         b2b_ms = e0.elapsed_time(e1)
         # ---- per-stage device times for the roofline (stage API, flushed between steps)
+        mark("b2b")
         stage_ms = sim.stage_times(min(args.steps, 20), flush_buf)
+        mark("stages")
         # ---- end to end through the frame call with host buffers
         e2e = sim.e2e(max(3, args.steps // 4), flush_buf)
+        mark("e2e")
         clocks = sampler.stop()
         stats = sim.stats()
+        mark("stats")
 
     if world > 1:
         tmax = torch.tensor([total_ms, b2b_ms, e2e["seconds"]], device="cuda", dtype=torch.float64)
@@ -391,7 +407,7 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=1_000_000, help="particles per GPU")
+    ap.add_argument("--particles", dest="n", type=int, default=1_000_000, help="particles per GPU")
     ap.add_argument("--preroll", type=int, default=1000, help="untimed steps before warm-up (state preparation)")
     ap.add_argument("--water-frac", type=float, default=0.5)
     ap.add_argument("--preset", default="x")

@@ -35,6 +35,7 @@ struct sph_ctx {
     unsigned char *xchg;             // exchange block for peer-memory mode (flags + 8 message buffers)
     void *peer[2];                   // neighbours' exchange blocks mapped with cudaIpcOpenMemHandle
     int scan_grid;                   // tiles of the widest possible window
+    int unpack_grid;                 // k_unpack waits on the neighbour inside the kernel: grid must be fully co-resident
     short2 *coords;
     int stage;
     int grid;
@@ -154,6 +155,16 @@ extern "C" int sph_create(const sph_config *cfg, sph_ctx **out)
     CK(cudaMalloc(&ctx->xchg, xchg_bytes(ctx->cfg.msg_capacity)));
     CK(cudaMemset(ctx->xchg, 0, xchg_bytes(ctx->cfg.msg_capacity)));
     ctx->scan_grid = (int)((ncell_max + SCAN_TILE - 1) / SCAN_TILE);
+    {
+        // k_unpack sends, then spins until the neighbour's message has arrived, and a message is only
+        // released once EVERY block of the sender's grid has run.  If the grid did not fit on the device at
+        // once, the resident blocks of both neighbours would wait for each other's unscheduled blocks
+        // forever.  So its grid is bounded by what the occupancy calculator says is co-resident.
+        int per_sm = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_unpack, SPH_THREADS, 0));
+        if (per_sm < 1) return fail(ctx, SPH_ERR_CUDA, "k_unpack cannot be resident");
+        ctx->unpack_grid = std::min(ctx->grid, per_sm * prop.multiProcessorCount);
+    }
     CK(cudaMalloc(&ctx->dp, sizeof(DevParams)));
 
     DevParams &P = ctx->hp;
@@ -163,6 +174,11 @@ extern "C" int sph_create(const sph_config *cfg, sph_ctx **out)
     P.has_left = cfg->rank > 0; P.has_right = cfg->rank < cfg->nranks - 1; P.nranks = cfg->nranks;
     P.cap = cfg->capacity; P.msg_cap = ctx->cfg.msg_capacity;
     P.p2p = 0; P.xchg_base = (unsigned long long)ctx->xchg; P.remote_base[0] = P.remote_base[1] = 0;
+    {   // device-side waits give up after this long (default 10 s) instead of hanging the GPU
+        const char *ms = getenv("SPH_SPIN_TIMEOUT_MS");
+        const double khz = prop.clockRate > 0 ? (double)prop.clockRate : 1.9e6;
+        P.spin_timeout = (long long)((ms ? atof(ms) : 10000.0) * khz);
+    }
     P.h = cfg->h; P.dt = 1.0f / 120.0f; P.mover_type = -1;
     fill_edges(ctx, 0.0f, cfg->tank_w);
     P.gx0 = P.gx0_new; P.wx = P.wx_new;
@@ -291,7 +307,7 @@ static int launch_sort(sph_ctx *ctx, int which, bool with_unpack = true)
     float2 *dq = which == 0 ? ctx->Q[1] : ctx->Q[0];
     uint32_t *du = which == 0 ? ctx->U[1] : ctx->U[0];
     if (ctx->cfg.nranks > 1 && with_unpack) {
-        k_unpack<<<ctx->grid, SPH_THREADS, 0, ctx->stream>>>(ctx->dp, ctx->counters, which, ctx->send[0], ctx->send[1],
+        k_unpack<<<ctx->unpack_grid, SPH_THREADS, 0, ctx->stream>>>(ctx->dp, ctx->counters, which, ctx->send[0], ctx->send[1],
                                                              ctx->recv[0], ctx->recv[1],
                                                              sp, sq, su, ctx->cnt, ctx->t_key, ctx->t_slot);
         ctx->launches++;
@@ -571,6 +587,9 @@ extern "C" int sph_get_status(sph_ctx *ctx, sph_status *out)
     out->neighbor_overflow = c[CN_NEIGH_OVER];
     out->capacity_overflow = c[CN_CAP_OVER];
     out->msg_overflow = c[CN_MSG_OVER];
+    if (c[CN_TIMEOUT_MSG] || c[CN_TIMEOUT_SCAN])
+        snprintf(ctx->err, sizeof ctx->err, "device-side waits timed out: %d neighbour messages, %d scan tiles",
+                 c[CN_TIMEOUT_MSG], c[CN_TIMEOUT_SCAN]);
     if (ctx->cfg.nranks > 1) {
         int hl[2] = {0, 0}, hr[2] = {0, 0};
         CK(cudaMemcpy(hl, ctx->send[0], sizeof hl, cudaMemcpyDeviceToHost));

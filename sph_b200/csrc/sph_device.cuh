@@ -38,6 +38,7 @@ struct DevParams {
     int p2p;
     unsigned long long xchg_base;
     unsigned long long remote_base[2];
+    long long spin_timeout;          // clock64 cycles a device-side wait may last before it gives up and flags an error
 };
 
 // device-side counters (ints); indices below
@@ -52,7 +53,9 @@ enum {
     CN_EPOCH,           // scan epoch (so tile flags never need clearing)
     CN_STEP,            // completed steps (message sequence numbers and buffer parity)
     CN_PUB,             // blocks that finished packing (last one publishes the message)
-    CN_COUNT = 16
+    CN_TIMEOUT_MSG,     // neighbour messages that never arrived (peer-memory waits that timed out)
+    CN_TIMEOUT_SCAN,    // scan tiles whose predecessors never published
+    CN_COUNT = 24
 };
 
 // neighbour message: 16-byte header {n_migrants, n_halo, 0, 0} then SoA sections sized by msg_cap

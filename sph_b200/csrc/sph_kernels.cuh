@@ -266,7 +266,7 @@ k_unpack(const DevParams *__restrict__ Pp, int *__restrict__ counters, int which
                 const int *flag = xchg_flag(P.xchg_base, s, which);
                 const long long t0 = clock64();
                 while (ld_acquire_sys(flag) < 2 * step + which + 1) {
-                    if (clock64() - t0 > 20000000000LL) { ok = 0; break; }     // ~10 s: neighbour lost
+                    if (clock64() - t0 > P.spin_timeout) { ok = 0; break; }    // neighbour lost
                     __nanosleep(200);
                 }
             }
@@ -275,11 +275,14 @@ k_unpack(const DevParams *__restrict__ Pp, int *__restrict__ counters, int which
         __syncthreads();
         for (int s = 0; s < 2; s++) {
             buf[s] = (unsigned char *)(P.xchg_base + xchg_offset(s, which, step & 1, P.msg_cap));
-            if (!s_ok[s]) { buf[s] = recv_l; if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&counters[CN_MSG_OVER], 1 << 20); }
+            if (!s_ok[s]) {      // treat the missing message as empty; the run is invalid and says so
+                buf[s] = nullptr;
+                if (blockIdx.x == 0 && threadIdx.x == 0) { atomicAdd(&counters[CN_TIMEOUT_MSG], 1); atomicAdd(&counters[CN_MSG_OVER], 1); }
+            }
         }
     }
     for (int s = 0; s < 2; s++) {
-        if (!present[s]) continue;
+        if (!present[s] || !buf[s]) continue;
         n_mig[s] = which == 0 ? min(ld_acquire_sys(&msg_hdr(buf[s])[0]), P.msg_cap) : 0;
         n_halo[s] = min(ld_acquire_sys(&msg_hdr(buf[s])[1]), P.msg_cap);
     }
@@ -421,9 +424,14 @@ k_scan(DevParams *__restrict__ Pp, int *__restrict__ counters, int *__restrict__
         const unsigned long long tag = (unsigned long long)epoch << 32;
         if (lane == 0) st_release_u64(&tile_state[tile], tag | (unsigned)block_total);
         int prefix = 0;
+        const long long t0 = clock64();
+        const long long limit = Pp->spin_timeout;
         for (int idx = lane; idx < tile; idx += 32) {
             unsigned long long st;
-            do { st = ld_acquire_u64(&tile_state[idx]); } while ((unsigned)(st >> 32) != epoch);
+            do {
+                st = ld_acquire_u64(&tile_state[idx]);
+                if (clock64() - t0 > limit) { atomicAdd(&counters[CN_TIMEOUT_SCAN], 1); atomicAdd(&counters[CN_CAP_OVER], 1); break; }
+            } while ((unsigned)(st >> 32) != epoch);
             prefix += (int)(unsigned)st;
         }
         prefix = __reduce_add_sync(0xffffffffu, prefix);

@@ -32,6 +32,8 @@ def main():
         sim.run(steps)
         a, uid = sim.ctx.download()
         st = sim.ctx.status()
+        print(f"rank {rank}: n_local={st.n_local} n_halo={st.n_halo} cap_over={st.capacity_overflow} msg_over={st.msg_overflow} "
+              f"err={sim.ctx.L.sph_last_error(sim.ctx.h).decode()!r}", flush=True)
     np.savez(f"{out}.rank{rank}.npz", state=a, uid=uid, overflow=np.array([st.capacity_overflow, st.msg_overflow]),
              edges=np.array(sim.edges, "f8"))
     if rank == 0:
