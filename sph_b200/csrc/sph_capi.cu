@@ -163,7 +163,8 @@ extern "C" int sph_create(const sph_config *cfg, sph_ctx **out)
         int per_sm = 0;
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_unpack, SPH_THREADS, 0));
         if (per_sm < 1) return fail(ctx, SPH_ERR_CUDA, "k_unpack cannot be resident");
-        ctx->unpack_grid = std::min(ctx->grid, per_sm * prop.multiProcessorCount);
+        // (and kept small: the messages are a few hundred KB, and every block pays for a fence and a flag poll)
+        ctx->unpack_grid = std::min(std::min(ctx->grid, per_sm * prop.multiProcessorCount), 2 * prop.multiProcessorCount);
     }
     CK(cudaMalloc(&ctx->dp, sizeof(DevParams)));
 
