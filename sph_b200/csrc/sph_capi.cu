@@ -30,7 +30,7 @@ struct sph_ctx {
     sph_mask_t *nmask;               // SPH_NROWS x capacity: per-row acceptance masks from k_density for k_relax
     int *cnt, *cell_start, *t_key, *t_slot, *ord_src, *ord_key;
     uint32_t *ord_uid;
-    unsigned long long *tile_state;
+    int *tile_total;                 // one population total per scan tile
     unsigned char *send[2], *recv[2];
     unsigned char *xchg;             // exchange block for peer-memory mode (flags + 8 message buffers)
     void *peer[2];                   // neighbours' exchange blocks mapped with cudaIpcOpenMemHandle
@@ -137,14 +137,12 @@ extern "C" int sph_create(const sph_config *cfg, sph_ctx **out)
     CK(cudaMalloc(&ctx->ord_uid, cap * sizeof(uint32_t)));
     CK(cudaMalloc(&ctx->coords, cap * sizeof(short2)));
     const size_t ntiles_max = (ncell_max + SCAN_TILE - 1) / SCAN_TILE + 1;
-    CK(cudaMalloc(&ctx->tile_state, ntiles_max * sizeof(unsigned long long)));
-    CK(cudaMemset(ctx->tile_state, 0, ntiles_max * sizeof(unsigned long long)));
+    CK(cudaMalloc(&ctx->tile_total, ntiles_max * sizeof(int)));
+    CK(cudaMemset(ctx->tile_total, 0, ntiles_max * sizeof(int)));
     CK(cudaMemset(ctx->cnt, 0, (ncell_max + 1) * sizeof(int)));
     CK(cudaMemset(ctx->cell_start, 0, (ncell_max + 1) * sizeof(int)));
     CK(cudaMalloc(&ctx->counters, CN_COUNT * sizeof(int)));
     CK(cudaMemset(ctx->counters, 0, CN_COUNT * sizeof(int)));
-    int one = 1;
-    CK(cudaMemcpy(ctx->counters + CN_EPOCH, &one, sizeof(int), cudaMemcpyHostToDevice));
     const size_t mb = msg_bytes_full(ctx->cfg.msg_capacity);
     for (int s = 0; s < 2; s++) {
         CK(cudaMalloc(&ctx->send[s], mb));
@@ -200,7 +198,7 @@ extern "C" void sph_destroy(sph_ctx *ctx)
     for (int i = 0; i < 2; i++) cudaFree(ctx->U[i]);
     cudaFree(ctx->dens); cudaFree(ctx->nmask); cudaFree(ctx->cnt); cudaFree(ctx->cell_start); cudaFree(ctx->t_key);
     cudaFree(ctx->t_slot); cudaFree(ctx->ord_src); cudaFree(ctx->ord_key); cudaFree(ctx->ord_uid); cudaFree(ctx->coords);
-    cudaFree(ctx->tile_state); cudaFree(ctx->counters); cudaFree(ctx->dp);
+    cudaFree(ctx->tile_total); cudaFree(ctx->counters); cudaFree(ctx->dp);
     for (int s = 0; s < 2; s++) { cudaFree(ctx->send[s]); cudaFree(ctx->recv[s]); }
     for (int s = 0; s < 2; s++) if (ctx->peer[s]) cudaIpcCloseMemHandle(ctx->peer[s]);
     cudaFree(ctx->xchg);
@@ -313,16 +311,18 @@ static int launch_sort(sph_ctx *ctx, int which, bool with_unpack = true)
                                                              sp, sq, su, ctx->cnt, ctx->t_key, ctx->t_slot);
         ctx->launches++;
     }
-    // grid sized for the widest window: a captured graph survives moving slab edges
-    k_scan<<<ctx->scan_grid, SPH_THREADS, 0, ctx->stream>>>(ctx->dp, ctx->counters, ctx->cnt, ctx->cell_start, ctx->tile_state,
-                                                            ctx->cfg.nranks > 1 ? ctx->send[0] : nullptr,
-                                                            ctx->cfg.nranks > 1 ? ctx->send[1] : nullptr,
-                                                            (which == 1 && with_unpack) ? 1 : 0);
+    // grids sized for the widest window (tile loops inside): a captured graph survives moving slab edges
+    const int sgrid = std::max(1, std::min(ctx->scan_grid, 4 * 148));
+    k_scan_totals<<<sgrid, SPH_THREADS, 0, ctx->stream>>>(ctx->dp, ctx->counters, ctx->cnt, ctx->tile_total);
+    k_scan_apply<<<sgrid, SPH_THREADS, 0, ctx->stream>>>(ctx->dp, ctx->counters, ctx->cnt, ctx->cell_start, ctx->tile_total,
+                                                         ctx->cfg.nranks > 1 ? ctx->send[0] : nullptr,
+                                                         ctx->cfg.nranks > 1 ? ctx->send[1] : nullptr,
+                                                         (which == 1 && with_unpack) ? 1 : 0);
     k_scatter<<<ctx->grid, SPH_THREADS, 0, ctx->stream>>>(ctx->counters, ctx->cell_start, ctx->t_key, ctx->t_slot, su,
                                                           ctx->ord_uid, ctx->ord_src, ctx->ord_key);
     k_reorder<<<ctx->grid, SPH_THREADS, 0, ctx->stream>>>(ctx->dp, ctx->counters, ctx->cell_start, ctx->ord_key,
                                                           ctx->ord_uid, ctx->ord_src, sp, sq, dp, dq, du);
-    ctx->launches += 3;
+    ctx->launches += 4;
     ctx->hp.gx0 = ctx->hp.gx0_new;     // the scan kernel did the same on the device
     ctx->hp.wx = ctx->hp.wx_new;
     CK(cudaGetLastError());
@@ -446,7 +446,7 @@ extern "C" int sph_step(sph_ctx *ctx, int n)
             ctx->graph_ready = true;
         }
         CK(cudaGraphLaunch(ctx->graph, ctx->stream));
-        ctx->launches += ctx->cfg.nranks > 1 ? 11 : 9;
+        ctx->launches += ctx->cfg.nranks > 1 ? 13 : 11;
         ctx->steps++;
     }
     return SPH_OK;
@@ -460,9 +460,6 @@ static int ingest(sph_ctx *ctx, int n)
 {
     int zero[CN_COUNT] = {0};
     zero[CN_NTOT] = n;
-    int epoch = 0;
-    CK(cudaMemcpy(&epoch, ctx->counters + CN_EPOCH, sizeof(int), cudaMemcpyDeviceToHost));
-    zero[CN_EPOCH] = epoch;
     CK(cudaMemcpyAsync(ctx->counters, zero, sizeof zero, cudaMemcpyHostToDevice, ctx->stream));
     const size_t ncell_max = (size_t)ctx->size_x * ctx->size_y * SPH_CELL_DIV * SPH_CELL_DIV;
     CK(cudaMemsetAsync(ctx->cnt, 0, (ncell_max + 1) * sizeof(int), ctx->stream));
@@ -588,9 +585,8 @@ extern "C" int sph_get_status(sph_ctx *ctx, sph_status *out)
     out->neighbor_overflow = c[CN_NEIGH_OVER];
     out->capacity_overflow = c[CN_CAP_OVER];
     out->msg_overflow = c[CN_MSG_OVER];
-    if (c[CN_TIMEOUT_MSG] || c[CN_TIMEOUT_SCAN])
-        snprintf(ctx->err, sizeof ctx->err, "device-side waits timed out: %d neighbour messages, %d scan tiles",
-                 c[CN_TIMEOUT_MSG], c[CN_TIMEOUT_SCAN]);
+    if (c[CN_TIMEOUT_MSG])
+        snprintf(ctx->err, sizeof ctx->err, "device-side waits timed out: %d neighbour messages never arrived", c[CN_TIMEOUT_MSG]);
     if (ctx->cfg.nranks > 1) {
         int hl[2] = {0, 0}, hr[2] = {0, 0};
         CK(cudaMemcpy(hl, ctx->send[0], sizeof hl, cudaMemcpyDeviceToHost));

@@ -48,13 +48,12 @@ enum {
     CN_NSRC,            // entries the scatter kernel must visit (written by the scan)
     CN_NLOCAL,          // non-ghost entries after the last sort (accumulated by reorder)
     CN_MAX_BUCKET, CN_BUCKET_OVER, CN_NEIGH_OVER, CN_CAP_OVER, CN_MSG_OVER,
-    CN_TICKET, CN_DONE, // scan bookkeeping
+    CN_SPARE0, CN_SPARE1,
     CN_COORDS,          // pack_coords compaction cursor
-    CN_EPOCH,           // scan epoch (so tile flags never need clearing)
+    CN_SPARE2,
     CN_STEP,            // completed steps (message sequence numbers and buffer parity)
     CN_PUB,             // blocks that finished packing (last one publishes the message)
     CN_TIMEOUT_MSG,     // neighbour messages that never arrived (peer-memory waits that timed out)
-    CN_TIMEOUT_SCAN,    // scan tiles whose predecessors never published
     CN_COUNT = 24
 };
 

@@ -320,167 +320,152 @@ k_unpack(const DevParams *__restrict__ Pp, int *__restrict__ counters, int which
 }
 
 // -------------------------------------------------------------------------------------------
-// K3  exclusive prefix sum of the cell populations -> cell_start, one pass.
-//     Every tile (8192 cells) publishes its total; a tile's offset is the sum of ALL preceding
-//     totals, read directly.  All tiles of a launch are co-resident (a few hundred blocks at most)
-//     and take their tile index from a ticket, so every predecessor is already running: there is one
-//     round of waiting instead of the chained look-back of the first version, whose ~8 sequential
-//     L2 round trips made this kernel 20 us for 2 MB of data (profiles/r1_masks_full.csv).
-//     Also clears the populations for the next sort, records the largest bucket (the reference
-//     silently drops above 100: hash.c:160-165) and publishes the new entry counts.
+// K3  exclusive prefix sum of the cell populations -> cell_start, in two plain streaming kernels:
+//       k_scan_totals  one total per tile of 8192 cells (also the bucket statistics)
+//       k_scan_apply   tile offset = sum of the preceding tile totals (read coalesced, block-reduced),
+//                      then the tile's own scan; clears the populations for the next sort and
+//                      publishes the new entry counts.
+//     The first versions did this in one kernel with inter-block waiting (chained look-back, then
+//     "sum all predecessors"); both were latency-bound at ~18-20 us for 8 MB because every tile sat in
+//     a dependent chain of L2 round trips and barriers (profiles/r1_div2_full.csv).  Two independent
+//     passes have no waiting at all and the second read of the populations hits L2.
+//     The reference silently drops particles above 100 per bucket (hash.c:160-165): the largest
+//     population seen is recorded so that this can be detected.
 // -------------------------------------------------------------------------------------------
 #define SCAN_ITEMS 32
 #define SCAN_TILE (SPH_THREADS * SCAN_ITEMS)
 
-__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long *p)
+__device__ __forceinline__ void scan_load_tile(const int *__restrict__ cnt, int base, int ncell, int (&v)[SCAN_ITEMS])
 {
-    unsigned long long v;
-    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release_u64(unsigned long long *p, unsigned long long v)
-{
-    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-
-__global__ void __launch_bounds__(SPH_THREADS)
-k_scan(DevParams *__restrict__ Pp, int *__restrict__ counters, int *__restrict__ cnt, int *__restrict__ cell_start,
-       unsigned long long *__restrict__ tile_state, unsigned char *send_l, unsigned char *send_r, int end_of_step)
-{
-    __shared__ int s_tile;
-    __shared__ int s_warp[SPH_THREADS / 32];
-    __shared__ int s_wmax[SPH_THREADS / 32], s_wover[SPH_THREADS / 32];
-    __shared__ int s_prefix;
-    const int ncell = Pp->wx_new * Pp->sort_rows;
-    const int ntiles = (ncell + SCAN_TILE - 1) / SCAN_TILE;
-    const unsigned epoch = (unsigned)counters[CN_EPOCH];
-    if (threadIdx.x == 0) s_tile = atomicAdd(&counters[CN_TICKET], 1);
-    __syncthreads();
-    const int tile = s_tile;
-    // the grid is sized for the widest window a slab can have; surplus blocks only check out
-    if (tile >= ntiles) {
-        if (threadIdx.x == 0 && atomicAdd(&counters[CN_DONE], 1) == (int)gridDim.x - 1) {
-            counters[CN_TICKET] = 0;
-            counters[CN_DONE] = 0;
-            counters[CN_EPOCH] = (int)((epoch + 1) & 0x3fffffffu);
-        }
-        return;
-    }
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int base = tile * SCAN_TILE + threadIdx.x * SCAN_ITEMS;     // 32 consecutive cells = 128 bytes per thread
-
-    int v[SCAN_ITEMS];
-    int sum = 0, mx = 0, over = 0;
     if (base + SCAN_ITEMS <= ncell) {
-        const int4 *src = reinterpret_cast<const int4 *>(cnt + base);
-        int4 *dstz = reinterpret_cast<int4 *>(cnt + base);
+        const int4 *src = reinterpret_cast<const int4 *>(cnt + base);     // 32 consecutive cells = 128 bytes per thread
 #pragma unroll
         for (int k = 0; k < SCAN_ITEMS / 4; k++) {
             const int4 q = src[k];
             v[4 * k] = q.x; v[4 * k + 1] = q.y; v[4 * k + 2] = q.z; v[4 * k + 3] = q.w;
         }
-#pragma unroll
-        for (int k = 0; k < SCAN_ITEMS / 4; k++) dstz[k] = make_int4(0, 0, 0, 0);
     } else {
 #pragma unroll
-        for (int k = 0; k < SCAN_ITEMS; k++) {
-            const int idx = base + k;
-            v[k] = idx < ncell ? cnt[idx] : 0;
-            if (idx < ncell) cnt[idx] = 0;
+        for (int k = 0; k < SCAN_ITEMS; k++) v[k] = base + k < ncell ? cnt[base + k] : 0;
+    }
+}
+
+__global__ void __launch_bounds__(SPH_THREADS)
+k_scan_totals(const DevParams *__restrict__ Pp, int *__restrict__ counters, const int *__restrict__ cnt,
+              int *__restrict__ tile_total)
+{
+    __shared__ int s_sum[SPH_THREADS / 32], s_max[SPH_THREADS / 32], s_over[SPH_THREADS / 32];
+    const int ncell = Pp->wx_new * Pp->sort_rows;
+    const int ntiles = (ncell + SCAN_TILE - 1) / SCAN_TILE;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        int v[SCAN_ITEMS];
+        scan_load_tile(cnt, tile * SCAN_TILE + threadIdx.x * SCAN_ITEMS, ncell, v);
+        int sum = 0, mx = 0, over = 0;
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; k++) { sum += v[k]; mx = max(mx, v[k]); over += v[k] > 100; }
+        sum = __reduce_add_sync(0xffffffffu, sum);
+        mx = __reduce_max_sync(0xffffffffu, mx);
+        over = __reduce_add_sync(0xffffffffu, over);
+        if (lane == 0) { s_sum[warp] = sum; s_max[warp] = mx; s_over[warp] = over; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int t = 0, m = 0, o = 0;
+#pragma unroll
+            for (int w = 0; w < SPH_THREADS / 32; w++) { t += s_sum[w]; m = max(m, s_max[w]); o += s_over[w]; }
+            tile_total[tile] = t;
+            if (m > 0) atomicMax(&counters[CN_MAX_BUCKET], m);
+            if (o > 0) atomicAdd(&counters[CN_BUCKET_OVER], o);
         }
+        __syncthreads();
     }
+}
+
+__global__ void __launch_bounds__(SPH_THREADS)
+k_scan_apply(DevParams *__restrict__ Pp, int *__restrict__ counters, int *__restrict__ cnt, int *__restrict__ cell_start,
+             const int *__restrict__ tile_total, unsigned char *send_l, unsigned char *send_r, int end_of_step)
+{
+    __shared__ int s_warp[SPH_THREADS / 32];
+    __shared__ int s_prefix;
+    const int ncell = Pp->wx_new * Pp->sort_rows;
+    const int ntiles = (ncell + SCAN_TILE - 1) / SCAN_TILE;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        // offset of this tile: all preceding totals, coalesced, block-reduced
+        int part = 0;
+        for (int idx = threadIdx.x; idx < tile; idx += SPH_THREADS) part += tile_total[idx];
+        part = __reduce_add_sync(0xffffffffu, part);
+        if (lane == 0) s_warp[warp] = part;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int t = 0;
 #pragma unroll
-    for (int k = 0; k < SCAN_ITEMS; k++) { sum += v[k]; mx = max(mx, v[k]); over += v[k] > 100; }
-    // warp inclusive scan of the thread sums
-    int inc = sum;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= o) inc += t;
-    }
-    mx = __reduce_max_sync(0xffffffffu, mx);
-    over = __reduce_add_sync(0xffffffffu, over);
-    if (lane == 31) s_warp[warp] = inc;
-    if (lane == 0) { s_wmax[warp] = mx; s_wover[warp] = over; }
-    __syncthreads();
-    int warp_off = 0, block_total = 0;
-#pragma unroll
-    for (int w = 0; w < SPH_THREADS / 32; w++) {
-        const int sw = s_warp[w];
-        if (w < warp) warp_off += sw;
-        block_total += sw;
-    }
-    if (threadIdx.x == 0) {
-        // one atomic per block: per-warp atomics on these two addresses serialised in L2 and made up
-        // most of this kernel's time
-        int bmx = 0, bover = 0;
-#pragma unroll
-        for (int w = 0; w < SPH_THREADS / 32; w++) { bmx = max(bmx, s_wmax[w]); bover += s_wover[w]; }
-        if (bmx > 0) atomicMax(&counters[CN_MAX_BUCKET], bmx);
-        if (bover > 0) atomicAdd(&counters[CN_BUCKET_OVER], bover);
-    }
-    // publish this tile's total, then add up every preceding tile's total (one warp)
-    if (warp == 0) {
-        const unsigned long long tag = (unsigned long long)epoch << 32;
-        if (lane == 0) st_release_u64(&tile_state[tile], tag | (unsigned)block_total);
-        int prefix = 0;
-        const long long t0 = clock64();
-        const long long limit = Pp->spin_timeout;
-        for (int idx = lane; idx < tile; idx += 32) {
-            unsigned long long st;
-            do {
-                st = ld_acquire_u64(&tile_state[idx]);
-                if (clock64() - t0 > limit) { atomicAdd(&counters[CN_TIMEOUT_SCAN], 1); atomicAdd(&counters[CN_CAP_OVER], 1); break; }
-            } while ((unsigned)(st >> 32) != epoch);
-            prefix += (int)(unsigned)st;
+            for (int w = 0; w < SPH_THREADS / 32; w++) t += s_warp[w];
+            s_prefix = t;
         }
-        prefix = __reduce_add_sync(0xffffffffu, prefix);
-        if (lane == 0) s_prefix = prefix;
-    }
-    __syncthreads();
-    int run = s_prefix + warp_off + (inc - sum);
-    if (base + SCAN_ITEMS <= ncell) {
-        int4 *dst = reinterpret_cast<int4 *>(cell_start + base);
+        __syncthreads();
+        const int prefix = s_prefix;
+        __syncthreads();                                   // s_warp is reused below
+
+        const int base = tile * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+        int v[SCAN_ITEMS];
+        scan_load_tile(cnt, base, ncell, v);
+        int sum = 0;
 #pragma unroll
-        for (int k = 0; k < SCAN_ITEMS / 4; k++) {
-            int4 o;
-            o.x = run; run += v[4 * k];
-            o.y = run; run += v[4 * k + 1];
-            o.z = run; run += v[4 * k + 2];
-            o.w = run; run += v[4 * k + 3];
-            dst[k] = o;
-        }
-    } else {
+        for (int k = 0; k < SCAN_ITEMS; k++) sum += v[k];
+        int inc = sum;                                     // warp inclusive scan of the thread sums
 #pragma unroll
-        for (int k = 0; k < SCAN_ITEMS; k++) {
-            const int idx = base + k;
-            if (idx < ncell) cell_start[idx] = run;
-            run += v[k];
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
         }
-    }
-    if (tile == ntiles - 1 && threadIdx.x == SPH_THREADS - 1) {
-        const int total = s_prefix + block_total;
-        cell_start[ncell] = total;
-        counters[CN_NSRC] = counters[CN_NTOT] + counters[CN_EXTRA];
-        counters[CN_EXTRA] = 0;
-        counters[CN_NTOT] = total;
-        counters[CN_NLOCAL] = 0;
-        // the sorted arrays are about to be rebuilt for the new window
-        Pp->gx0 = Pp->gx0_new;
-        Pp->wx = Pp->wx_new;
-        // send buffers are free again: the messages they held were consumed before this sort
-        if (send_l) { msg_hdr(send_l)[0] = 0; msg_hdr(send_l)[1] = 0; }
-        if (send_r) { msg_hdr(send_r)[0] = 0; msg_hdr(send_r)[1] = 0; }
-        if (end_of_step) counters[CN_STEP] += 1;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        if (atomicAdd(&counters[CN_DONE], 1) == (int)gridDim.x - 1) {   // last block out resets the bookkeeping
-            counters[CN_TICKET] = 0;
-            counters[CN_DONE] = 0;
-            counters[CN_EPOCH] = (int)((epoch + 1) & 0x3fffffffu);
+        if (lane == 31) s_warp[warp] = inc;
+        __syncthreads();
+        int warp_off = 0, block_total = 0;
+#pragma unroll
+        for (int w = 0; w < SPH_THREADS / 32; w++) {
+            const int sw = s_warp[w];
+            if (w < warp) warp_off += sw;
+            block_total += sw;
         }
+        int run = prefix + warp_off + (inc - sum);
+        if (base + SCAN_ITEMS <= ncell) {
+            int4 *dst = reinterpret_cast<int4 *>(cell_start + base);
+            int4 *zero = reinterpret_cast<int4 *>(cnt + base);
+#pragma unroll
+            for (int k = 0; k < SCAN_ITEMS / 4; k++) {
+                int4 o;
+                o.x = run; run += v[4 * k];
+                o.y = run; run += v[4 * k + 1];
+                o.z = run; run += v[4 * k + 2];
+                o.w = run; run += v[4 * k + 3];
+                dst[k] = o;
+                zero[k] = make_int4(0, 0, 0, 0);
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < SCAN_ITEMS; k++) {
+                const int idx = base + k;
+                if (idx < ncell) { cell_start[idx] = run; cnt[idx] = 0; }
+                run += v[k];
+            }
+        }
+        if (tile == ntiles - 1 && threadIdx.x == SPH_THREADS - 1) {
+            const int total = prefix + block_total;
+            cell_start[ncell] = total;
+            counters[CN_NSRC] = counters[CN_NTOT] + counters[CN_EXTRA];
+            counters[CN_EXTRA] = 0;
+            counters[CN_NTOT] = total;
+            counters[CN_NLOCAL] = 0;
+            // the sorted arrays are about to be rebuilt for the new window
+            Pp->gx0 = Pp->gx0_new;
+            Pp->wx = Pp->wx_new;
+            // send buffers are free again: the messages they held were consumed before this sort
+            if (send_l) { msg_hdr(send_l)[0] = 0; msg_hdr(send_l)[1] = 0; }
+            if (send_r) { msg_hdr(send_r)[0] = 0; msg_hdr(send_r)[1] = 0; }
+            if (end_of_step) counters[CN_STEP] += 1;
+        }
+        __syncthreads();
     }
 }
 
