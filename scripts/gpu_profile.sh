@@ -3,4 +3,4 @@
 mkdir -p gpurun_out
 TAG=${TAG:-r1_final}
 SPH_PROFILE=1 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_${TAG}.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_l.log 2>&1; tail -1 gpurun_out/ncu_l.log | cut -c1-200
-SPH_PROFILE=1 ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:"k_advect|k_density|k_relax|k_scan|k_scatter|k_reorder" -c 6 -f -o gpurun_out/prof_${TAG} python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_f.log 2>&1; tail -1 gpurun_out/ncu_f.log | cut -c1-200
+SPH_PROFILE=1 ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:"k_advect|k_density|k_relax|k_scan_totals|k_scan_apply|k_scatter|k_reorder" -c 7 -f -o gpurun_out/prof_${TAG} python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_f.log 2>&1; tail -1 gpurun_out/ncu_f.log | cut -c1-200

@@ -312,7 +312,7 @@ static int launch_sort(sph_ctx *ctx, int which, bool with_unpack = true)
         ctx->launches++;
     }
     // grids sized for the widest window (tile loops inside): a captured graph survives moving slab edges
-    const int sgrid = std::max(1, std::min(ctx->scan_grid, 4 * 148));
+    const int sgrid = std::max(1, std::min(ctx->scan_grid, 8 * 148));
     k_scan_totals<<<sgrid, SPH_THREADS, 0, ctx->stream>>>(ctx->dp, ctx->counters, ctx->cnt, ctx->tile_total);
     k_scan_apply<<<sgrid, SPH_THREADS, 0, ctx->stream>>>(ctx->dp, ctx->counters, ctx->cnt, ctx->cell_start, ctx->tile_total,
                                                          ctx->cfg.nranks > 1 ? ctx->send[0] : nullptr,

@@ -332,7 +332,7 @@ k_unpack(const DevParams *__restrict__ Pp, int *__restrict__ counters, int which
 //     The reference silently drops particles above 100 per bucket (hash.c:160-165): the largest
 //     population seen is recorded so that this can be detected.
 // -------------------------------------------------------------------------------------------
-#define SCAN_ITEMS 32
+#define SCAN_ITEMS 8
 #define SCAN_TILE (SPH_THREADS * SCAN_ITEMS)
 
 __device__ __forceinline__ void scan_load_tile(const int *__restrict__ cnt, int base, int ncell, int (&v)[SCAN_ITEMS])
