@@ -110,8 +110,9 @@ typedef struct sph_config {
 /* what the reference silently drops (hash.c:160-165, :188-197, :223-232) is counted here */
 typedef struct sph_status {
     int n_local, n_halo;
-    int max_bucket;              /* largest cell population seen by the last sort */
-    int bucket_overflow;         /* cells above SPH_REF_MAX_BUCKET (reference would drop particles) */
+    int max_bucket;              /* largest population of a reference bucket (cell of side h) in the current state */
+    int bucket_overflow;         /* buckets above SPH_REF_MAX_BUCKET now, or sub-cells above it in any earlier sort
+                                  * (the reference would have dropped particles, hash.c:160-165) */
     int neighbor_overflow;       /* particles with > SPH_REF_MAX_NEIGHBORS forward neighbours */
     int capacity_overflow;       /* particles dropped because `capacity` was exceeded (fatal) */
     int msg_overflow;            /* particles that did not fit a neighbour message (fatal) */

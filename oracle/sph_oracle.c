@@ -513,11 +513,17 @@ static void g_sort_T_into_A(orc_g *g)
         if (!(g->tuid[s] & HALO_BIT)) nl++;
     }
     while (c < ncell) g->cell_start[++c] = m;
-    for (int k = 0; k < ncell; k++) {
-        int cnt = g->cell_start[k + 1] - g->cell_start[k];
-        if (cnt > maxb) maxb = cnt;
-        if (cnt > SPH_REF_MAX_BUCKET) over++;
-    }
+    /* statistics of the REFERENCE's buckets (cells of side h = DIV x DIV sort cells), hash.c:160-165 */
+    for (int R = 0; R < g->sort_rows / DIV; R++)
+        for (int C = 0; C < g->wx / DIV; C++) {
+            int cnt = 0;
+            for (int r = 0; r < DIV; r++) {
+                int row = R * DIV + r;
+                cnt += g->cell_start[row * g->wx + (C + 1) * DIV] - g->cell_start[row * g->wx + C * DIV];
+            }
+            if (cnt > maxb) maxb = cnt;
+            if (cnt > SPH_REF_MAX_BUCKET) over++;
+        }
     g->n_tot = m; g->n_local = nl;
     g->st.max_bucket = maxb; g->st.bucket_overflow += over;
     free(rec);
@@ -529,7 +535,8 @@ static int g_append_T(orc_g *g, float x, float y, float qx, float qy, uint32_t u
     int i = g->n_src++;
     g->tx[i] = x; g->ty[i] = y; g->tqx[i] = qx; g->tqy[i] = qy; g->tuid[i] = uid;
     g->tkey[i] = g_key(g, x, y);
-    if (g->tkey[i] == KEY_DROP) g->st.capacity_overflow++;
+    /* a ghost outside this slab's window is simply not needed (parked slab, controls.c:405-426) */
+    if (g->tkey[i] == KEY_DROP && !(uid & HALO_BIT)) g->st.capacity_overflow++;
     return i;
 }
 

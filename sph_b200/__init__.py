@@ -306,13 +306,34 @@ def lattice(prob, rank=0):
     return a, uid
 
 
-def balance(edges, counts, h):
-    """check_partition_left (renderer.c:427-477) on a list of (start_x, end_x); returns the new list."""
-    L = _host()
-    n = len(edges)
-    m = (Tunable * n)()
+def _edge_blocks(edges, h):
+    m = (Tunable * len(edges))()
     for r, (s, e) in enumerate(edges):
         m[r].smoothing_radius = h; m[r].node_start_x = s; m[r].node_end_x = e
+    return m
+
+
+def balance(edges, counts, h, nactive=None):
+    """check_partition_left (renderer.c:427-477) on a list of (start_x, end_x); returns the new list.
+    Only the first `nactive` slabs take part (render_state->num_compute_procs_active)."""
+    L = _host()
+    n = len(edges)
+    nactive = n if nactive is None else nactive
+    m = _edge_blocks(edges, h)
     c = np.asarray(counts, "i4")
-    L.sph_host_balance(m, n, _p(c), int(c.sum()))
+    L.sph_host_balance(m, nactive, _p(c), int(c.sum()))
     return [(float(m[r].node_start_x), float(m[r].node_end_x)) for r in range(n)]
+
+
+def remove_partition(edges, h, nactive):
+    """remove_partition (controls.c:405-426): returns (new edges, new nactive)."""
+    m = _edge_blocks(edges, h)
+    na = _host().sph_host_remove_partition(m, nactive)
+    return [(float(m[r].node_start_x), float(m[r].node_end_x)) for r in range(len(edges))], na
+
+
+def add_partition(edges, h, nactive):
+    """add_partition (controls.c:429-455): returns (new edges, new nactive)."""
+    m = _edge_blocks(edges, h)
+    na = _host().sph_host_add_partition(m, nactive, len(edges))
+    return [(float(m[r].node_start_x), float(m[r].node_end_x)) for r in range(len(edges))], na

@@ -580,8 +580,19 @@ extern "C" int sph_get_status(sph_ctx *ctx, sph_status *out)
     memset(out, 0, sizeof *out);
     out->n_local = c[CN_NLOCAL];
     out->n_halo = c[CN_NTOT] - c[CN_NLOCAL];
-    out->max_bucket = c[CN_MAX_BUCKET];
-    out->bucket_overflow = c[CN_BUCKET_OVER];
+    {
+        // exact statistics of the reference's buckets for the current sorted state (the hot path only keeps a
+        // conservative per-sub-cell count in CN_BUCKET_OVER)
+        int *dstat = ctx->counters + CN_SPARE0;          // two spare counters as scratch
+        int hz[2] = {0, 0};
+        CK(cudaMemcpyAsync(dstat, hz, sizeof hz, cudaMemcpyHostToDevice, ctx->stream));
+        k_bucket_stats<<<ctx->grid, SPH_THREADS, 0, ctx->stream>>>(ctx->dp, ctx->cell_start, dstat);
+        ctx->launches++;
+        CK(cudaMemcpyAsync(hz, dstat, sizeof hz, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        out->max_bucket = hz[0];
+        out->bucket_overflow = std::max(hz[1], c[CN_BUCKET_OVER]);
+    }
     out->neighbor_overflow = c[CN_NEIGH_OVER];
     out->capacity_overflow = c[CN_CAP_OVER];
     out->msg_overflow = c[CN_MSG_OVER];

@@ -315,7 +315,9 @@ k_unpack(const DevParams *__restrict__ Pp, int *__restrict__ counters, int which
         src_pos[idx] = p;
         src_q[idx] = q;
         src_uid[idx] = u;
-        bin_position(idx, p, 0, P, cnt, t_key, t_slot, counters);
+        // a ghost outside this slab's window is simply not needed (a slab parked outside the tank,
+        // controls.c:405-426, still receives its neighbour's edge particles): same flag as an emigrant
+        bin_position(idx, p, (u & SPH_HALO_BIT) ? SPH_KEY_EMIG : 0, P, cnt, t_key, t_slot, counters);
     }
 }
 
@@ -363,6 +365,8 @@ k_scan_totals(const DevParams *__restrict__ Pp, int *__restrict__ counters, cons
         scan_load_tile(cnt, tile * SCAN_TILE + threadIdx.x * SCAN_ITEMS, ncell, v);
         int sum = 0, mx = 0, over = 0;
 #pragma unroll
+        // (per sort-grid sub-cell: a sub-cell above 100 implies its reference bucket is; the exact bucket
+        //  statistics are computed on demand by k_bucket_stats)
         for (int k = 0; k < SCAN_ITEMS; k++) { sum += v[k]; mx = max(mx, v[k]); over += v[k] > 100; }
         sum = __reduce_add_sync(0xffffffffu, sum);
         mx = __reduce_max_sync(0xffffffffu, mx);
@@ -740,6 +744,28 @@ k_pack_coords(const DevParams *__restrict__ Pp, int *__restrict__ counters, cons
 // -------------------------------------------------------------------------------------------
 // parity / inspection kernels (not on the hot path)
 // -------------------------------------------------------------------------------------------
+// Populations of the REFERENCE's buckets (cells of side h) from the sort grid's cell_start: the largest one
+// and how many exceed the reference's capacity of 100 (hash.c:160-165 drops the excess silently).
+__global__ void k_bucket_stats(const DevParams *__restrict__ Pp, const int *__restrict__ cell_start, int *__restrict__ out)
+{
+    const DevParams P = *Pp;
+    const int cols = P.wx / SPH_CELL_DIV, rows = P.sort_rows / SPH_CELL_DIV;
+    int mx = 0, over = 0;
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < cols * rows; c += gridDim.x * blockDim.x) {
+        const int C = c % cols, R = c / cols;
+        int n = 0;
+        for (int r = 0; r < SPH_CELL_DIV; r++) {
+            const int row = R * SPH_CELL_DIV + r;
+            n += cell_start[row * P.wx + (C + 1) * SPH_CELL_DIV] - cell_start[row * P.wx + C * SPH_CELL_DIV];
+        }
+        mx = max(mx, n);
+        over += n > SPH_REF_MAX_BUCKET;
+    }
+    mx = __reduce_max_sync(0xffffffffu, mx);
+    over = __reduce_add_sync(0xffffffffu, over);
+    if ((threadIdx.x & 31) == 0) { if (mx) atomicMax(&out[0], mx); if (over) atomicAdd(&out[1], over); }
+}
+
 __global__ void k_export_cells(const DevParams *__restrict__ Pp, const int *__restrict__ counters,
                                const float2 *__restrict__ pos, uint32_t *__restrict__ cell)
 {

@@ -35,6 +35,7 @@ class SlabRunner:
         self.prob, self.rank, self.world, self.group = prob, rank, world, group
         self.steps_per_frame, self.do_balance = steps_per_frame, balance
         self.sub_step = 0
+        self.n_active = world            # slabs taking part (render_state->num_compute_procs_active)
         self.async_counts = async_counts
         self.stream = stream
         self.t = tunable.copy()
@@ -133,9 +134,28 @@ class SlabRunner:
             counts = self.gather_counts()
         self.counts = counts
         # the reference feeds coordinate counts (2 per particle) on both sides of the ratio (renderer.c:280,290)
-        self.edges = sph_b200.balance(self.edges, [2 * c for c in counts], self.prob["h"])
+        self.edges = sph_b200.balance(self.edges, [2 * c for c in counts], self.prob["h"], self.n_active)
+        self._queue_edges()
+
+    def _queue_edges(self):
         self.t.node_start_x, self.t.node_end_x = self.edges[self.rank]
+        self.t.active = bytes([1 if self.rank < self.n_active else 0])
         self.ctx.queue_params(self.t)
+
+    def remove_partition(self):
+        """Park the last active slab outside the tank (controls.c:405-426); its particles drain into the left
+        neighbour through the ordinary migration path, at most one message capacity per step.  Call on every
+        rank at the same step."""
+        import sph_b200
+        self.edges, self.n_active = sph_b200.remove_partition(self.edges, self.prob["h"], self.n_active)
+        self._queue_edges()
+
+    def add_partition(self):
+        """Split the last active slab in half and hand the right half to the next parked rank
+        (controls.c:429-455).  Call on every rank at the same step."""
+        import sph_b200
+        self.edges, self.n_active = sph_b200.add_partition(self.edges, self.prob["h"], self.n_active)
+        self._queue_edges()
 
     # -------------------------------------------------------------------------------- simulation
     def init_lattice(self):

@@ -33,7 +33,13 @@ def main():
     sim = SlabRunner(prob, t, rank, world, backend=backend, balance=bool(balance))
     sim.init_lattice()
     history = []
+    elastic = len(sys.argv) > 5 and sys.argv[5] == "elastic"
     for s in range(steps):
+        if elastic and s == 43:
+            sim.remove_partition()          # last slab parked: it drains into its left neighbour
+        if elastic and s == 123:
+            history.append((-1, sim.ctx.status().n_local, 0, 0))
+            sim.add_partition()             # and comes back with the right half of that neighbour's slab
         sim.step_once()
         if s % 20 == 19:
             st = sim.ctx.status()

@@ -87,6 +87,25 @@ def test_four_slabs_block_with_mover_across_an_edge(tmp_path, built_lib):
         assert np.array_equal(state[f][order].view("u4"), ref[f].view("u4")), f
 
 
+def test_partition_removed_and_added_back(tmp_path, built_lib):
+    """Runtime partition control (controls.c:405-455): at step 43 the last of three slabs is parked outside the
+    tank and must drain completely into its neighbour; at step 123 it is added back and refills.  No particle
+    is lost and, because the gather does not depend on the decomposition, the result is still bit-identical
+    to the single-slab run."""
+    steps = 200
+    parts = run_world(tmp_path, 3, 1500, steps, True, "elastic")
+    state = np.concatenate([p["state"] for p in parts]); uid = np.concatenate([p["uid"] for p in parts])
+    assert np.array_equal(np.sort(uid), np.arange(1508))
+    assert all(int(p["overflow"][0]) == 0 for p in parts), [p["overflow"] for p in parts]
+    drained = [h for h in parts[2]["history"] if h[0] == -1]
+    assert drained and drained[0][1] == 0, "the parked slab still held particles when it was added back"
+    assert len(parts[2]["uid"]) > 100, "the re-added slab did not refill"
+    ref, _ = single_slab(1500, steps)
+    order = np.argsort(uid)
+    for f in ("x", "y", "v_x", "v_y"):
+        assert np.array_equal(state[f][order].view("u4"), ref[f].view("u4")), f
+
+
 def test_three_slabs_agree_with_reference_three_ranks_statistically(tmp_path, built_lib):
     """The reference's own 3-rank run (tests/golden/multirank_r3.npz, 200 steps): trajectories are
     chaotic and its cross-slab pairs are swept in a different order, so compare distributions."""
