@@ -375,7 +375,8 @@ class SingleGpu:
 
     def kernel_name(self, stage):
         return {"advect": "k_advect", "density": "k_density", "relax": "k_relax",
-                "sort1": "k_scan+k_scatter+k_reorder", "sort2": "k_scan+k_scatter+k_reorder"}[stage]
+                "sort1": "k_scan_totals+k_scan_apply+k_scatter+k_reorder",
+                "sort2": "k_scan_totals+k_scan_apply+k_scatter+k_reorder"}[stage]
 
     def e2e(self, frames, flush_buf):
         import torch

@@ -17,7 +17,7 @@
 #define SPH_THREADS 256
 
 // -------------------------------------------------------------------------------------------
-// neighbourhood iteration: rows gy-1..gy+1, columns gx-1..gx+1 of the CURRENT window
+// neighbourhood iteration: sort-grid rows gy-DIV..gy+DIV, columns gx-DIV..gx+DIV of the CURRENT window
 // -------------------------------------------------------------------------------------------
 struct Rows { int b[SPH_NROWS], e[SPH_NROWS]; };
 
@@ -71,7 +71,10 @@ __device__ __forceinline__ Rows candidate_rows(float2 p, const DevParams &P, con
 // the neighbour GPU's exchange block over NVLink with coalesced stores spread over the whole grid,
 // (2) the last block to finish releases the neighbour's arrival flag with system scope, and (3) every
 // block waits for this rank's own arrival flags before unpacking.  Both neighbours send before they
-// wait, so there is no deadlock; nothing goes through the host or a collective library.
+// wait; the host launches this kernel with a grid that is fully co-resident (occupancy API), because a
+// message is released only after EVERY block of the sender has run -- with unscheduled blocks on both
+// sides the resident ones would wait for each other forever.  Nothing goes through the host or a
+// collective library.
 // (Storing each record remotely from inside the compute kernels was tried first: the scattered 8-byte
 // NVLink stores lengthened k_advect/k_relax by 30-45 us.)
 // -------------------------------------------------------------------------------------------

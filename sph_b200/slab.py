@@ -1,8 +1,11 @@
 """Multi-rank driver: one process per GPU, one x-slab per process (communication.c's design).
 
-torch.distributed is the plumbing (NCCL on the GPU box, gloo in the CPU tests): it moves the
-fixed-size neighbour messages whose packing is fused into the advect/relax kernels and whose
-unpacking is fused into the sort (include/sph_b200.h, "slab exchange").  Per step:
+torch.distributed is plumbing: it bootstraps the ranks, exchanges the cudaIpc handles of the exchange blocks
+and all-gathers one int per rank per frame.  The neighbour messages themselves -- packed inside the
+advect/relax kernels, unpacked inside the sort (include/sph_b200.h, "slab exchange") -- move over NVLink by
+peer-memory stores with device-side arrival flags (transport="p2p", one CUDA graph per step), or, as an
+alternative and in the CPU tests (gloo), through torch.distributed send/recv (transport="collective").
+Per step:
 
     advect -> exchange 0 (migrants + predicted-position ghosts) -> sort -> density -> relax
            -> exchange 1 (relaxed position + velocity ghosts)   -> sort
@@ -228,7 +231,8 @@ class SlabRunner:
     def kernel_name(self, stage):
         return {"advect": "k_advect", "density": "k_density", "relax": "k_relax",
                 "exchange": "peer stores inside k_advect/k_relax" if self.transport == "p2p" else "nccl send/recv",
-                "sort1": "k_unpack+k_scan+k_scatter+k_reorder", "sort2": "k_unpack+k_scan+k_scatter+k_reorder"}[stage]
+                "sort1": "k_unpack+k_scan_totals+k_scan_apply+k_scatter+k_reorder",
+                "sort2": "k_unpack+k_scan_totals+k_scan_apply+k_scatter+k_reorder"}[stage]
 
     def e2e(self, frames, flush_buf):
         """Frames with host buffers: parameter block H2D (queued, lands at the last sub-step), 4 steps, the
