@@ -109,7 +109,9 @@ def run_reference_cpu(n, water_frac, steps, warmup, ranks=None, budget_s=150.0):
     if exe:
         ranks = ranks or max(1, min(cores, 64))
         est_rate = 0.5e6 * ranks                       # particle-steps/s, conservative
-        n_s = int(min(n, max(20000, est_rate * budget_s / max(steps + warmup, 1))))
+        # bounded sample: by time, and to 2 M particles (the reference allocates ~6.6 KB of capacity per global
+        # particle PER RANK, fluid.c:156,202-203; larger samples risk the box's memory, not just its time)
+        n_s = int(min(n, 2_000_000, max(20000, est_rate * budget_s / max(steps + warmup, 1))))
         tank_w = problem_dims(n_s, water_frac)
         cmd = [exe, "--ranks", str(ranks), "--n", str(n_s), "--tank-w", f"{tank_w:.6f}",
                "--tank-h", f"{tank_w * 9.0 / 16.0:.6f}", "--water-frac", str(water_frac),
