@@ -269,7 +269,15 @@ def main_ours(args):
         stats = sim.stats()
         mark("stats")
 
+    per_rank = None
     if world > 1:
+        # per-slab picture: population, neighbours, pure compute time (the three gather kernels) per step
+        mine = torch.tensor([stats["n_local"], stats["n_halo"], stats["mean_neighbours"],
+                             1e3 * (stage_ms["advect"] + stage_ms["density"] + stage_ms["relax"]),
+                             1e3 * (stage_ms["sort1"] + stage_ms["sort2"])], device="cuda", dtype=torch.float64)
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank = [[round(float(v), 1) for v in r.tolist()] for r in allr]
         tmax = torch.tensor([total_ms, b2b_ms, e2e["seconds"]], device="cuda", dtype=torch.float64)
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         total_ms, b2b_ms, e2e_s = [float(x) for x in tmax.tolist()]
@@ -304,6 +312,7 @@ def main_ours(args):
                 "stage_ms": stage_ms,
                 "step_hbm_frac": step_gbs / peak,
                 "parallelism": f"slab{world}",
+                "per_slab_[n_local,n_ghost,neighbours,gather_us,sort_us]": per_rank,
             },
             "roofline": {"bound": "hbm", "kernel": sim.kernel_name(dom), "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak,

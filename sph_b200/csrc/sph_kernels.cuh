@@ -112,21 +112,25 @@ __device__ __forceinline__ void send_messages(const DevParams &P, int *counters,
             copy_words(remote, local[s], 16 + (size_t)m * 16, n_halo, gtid, gstride, wrote);        // ghost uid
         }
     }
-    // only blocks that stored remotely pay for a system-scope fence
+    // only blocks that stored remotely pay for a system-scope fence (they run in parallel)
     const int any = __syncthreads_or(wrote ? 1 : 0);
     if (threadIdx.x == 0) {
         if (any) __threadfence_system(); else __threadfence();
         if (atomicAdd(&counters[CN_PUB], 1) == (int)gridDim.x - 1) {
             counters[CN_PUB] = 0;
-            __threadfence_system();
+            // last block: counts into the remote headers, ONE system-scope fence, then the two arrival
+            // flags as plain stores (fence + store = release; every other block fenced before its
+            // atomicAdd, which this thread has observed).  The first version issued four system fences
+            // back to back here; at several microseconds each they were most of the exchange cost.
             for (int s = 0; s < 2; s++) {
                 if (!present[s]) continue;
                 int *rh = msg_hdr((unsigned char *)(P.remote_base[s] + xchg_offset(1 - s, which, step & 1, m)));
                 rh[0] = which == 0 ? min(msg_hdr(local[s])[0], m) : 0;
                 rh[1] = min(msg_hdr(local[s])[1], m);
-                __threadfence_system();
-                st_release_sys(xchg_flag(P.remote_base[s], 1 - s, which), 2 * step + which + 1);
             }
+            __threadfence_system();
+            for (int s = 0; s < 2; s++)
+                if (present[s]) *(volatile int *)xchg_flag(P.remote_base[s], 1 - s, which) = 2 * step + which + 1;
         }
     }
 }
@@ -286,8 +290,10 @@ k_unpack(const DevParams *__restrict__ Pp, int *__restrict__ counters, int which
     }
     for (int s = 0; s < 2; s++) {
         if (!present[s] || !buf[s]) continue;
-        n_mig[s] = which == 0 ? min(ld_acquire_sys(&msg_hdr(buf[s])[0]), P.msg_cap) : 0;
-        n_halo[s] = min(ld_acquire_sys(&msg_hdr(buf[s])[1]), P.msg_cap);
+        // (plain L2 loads: the thread that saw the flag did the system-scope acquire, the barrier after it
+        //  orders the rest of the block; a sys-scope acquire per thread here cost microseconds)
+        n_mig[s] = which == 0 ? min(__ldcg(&msg_hdr(buf[s])[0]), P.msg_cap) : 0;
+        n_halo[s] = min(__ldcg(&msg_hdr(buf[s])[1]), P.msg_cap);
     }
     const int total = n_mig[0] + n_halo[0] + n_mig[1] + n_halo[1];
     if (blockIdx.x == 0 && threadIdx.x == 0) {
