@@ -137,6 +137,9 @@ def test_edge_cases(built_lib):
     assert np.abs(x["x"][ok] - y["x"][ok]).max() <= 1e-4 and np.abs(x["y"][ok] - y["y"][ok]).max() <= 1e-4
     s = b.status()
     assert s.capacity_overflow == 0 and s.n_local == 1500
+    # populations of the reference's buckets (what its 100-entry cap applies to, hash.c:160-165)
+    so = o.status()
+    assert s.max_bucket == so.max_bucket and s.max_bucket >= 2
 
 
 def test_pack_coords_matches_reference_formula(built_lib):
