@@ -94,7 +94,7 @@ static void fill_edges(sph_ctx *ctx, float s, float e)
 
 static int push_params(sph_ctx *ctx)
 {
-    // pageable source: the runtime stages the 128 bytes before returning, so hp may change right away
+    // pageable source: the runtime stages the small block before returning, so hp may change right away
     CK(cudaMemcpyAsync(ctx->dp, &ctx->hp, sizeof(DevParams), cudaMemcpyHostToDevice, ctx->stream));
     return SPH_OK;
 }
@@ -183,7 +183,7 @@ extern "C" int sph_create(const sph_config *cfg, sph_ctx **out)
     P.gx0 = P.gx0_new; P.wx = P.wx_new;
     int rc = push_params(ctx);
     if (rc) return rc;
-    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaDeviceSynchronize());       // the memsets above ran on the legacy stream, ctx->stream does not wait for it
     ctx->stage = ST_READY;
     return SPH_OK;
 }
