@@ -27,10 +27,12 @@ struct Rows { int b[SPH_NROWS], e[SPH_NROWS]; };
 typedef unsigned long long sph_mask_t;
 #define SPH_MASK_BITS 64
 __device__ __forceinline__ int sph_mask_ffs(sph_mask_t m) { return __ffsll((long long)m); }
+__device__ __forceinline__ int sph_mask_popc(sph_mask_t m) { return __popcll(m); }
 #else
 typedef unsigned int sph_mask_t;
 #define SPH_MASK_BITS 32
 __device__ __forceinline__ int sph_mask_ffs(sph_mask_t m) { return __ffs((int)m); }
+__device__ __forceinline__ int sph_mask_popc(sph_mask_t m) { return __popc(m); }
 #endif
 
 // r and 1/r from the (exact, unfused) squared distance with one MUFU.RSQ instead of the IEEE sqrt +
@@ -44,6 +46,14 @@ __device__ __forceinline__ void r_and_recip(float r2, float &r, float &r_recip)
     // distances below 1.2e-38 are flushed and behave like coincident particles
     asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r_recip) : "f"(r2));
     r = r2 > 0.0f ? r2 * r_recip : 0.0f;
+}
+
+// r alone from one MUFU.SQRT (relative error ~2^-22, sqrt(0) = 0)
+__device__ __forceinline__ float sqrt_approx(float r2)
+{
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(r2));
+    return r;
 }
 
 __device__ __forceinline__ Rows candidate_rows(float2 p, const DevParams &P, const int *__restrict__ cell_start)
@@ -169,6 +179,7 @@ k_advect(const DevParams *__restrict__ Pp, int *__restrict__ counters,
     const int n = counters[CN_NTOT];
     const float dt = P.dt;
     const float gdt = (-P.g) * dt;
+    const float hdt = 0.5f * dt;
     const float h_recip = __fdiv_rn(1.0f, P.h);
     const float h2 = __fmul_rn(P.h, P.h);
     if (blockIdx.x == 0 && threadIdx.x == 0) counters[CN_MAX_BUCKET] = 0;
@@ -178,31 +189,35 @@ k_advect(const DevParams *__restrict__ Pp, int *__restrict__ counters,
         if (u & SPH_HALO_BIT) { t_key[i] = SPH_KEY_DROP; continue; }   // ghosts are replaced every exchange
         const float2 p = pos[i];
         const float2 v0 = vel[i];
-        const float vix = v0.x, viy = v0.y + gdt;                      // apply_gravity
-        float vx = vix, vy = viy;
+        float vx = v0.x, vy = v0.y + gdt;                               // apply_gravity
         const Rows R = candidate_rows(p, P, cell_start);
 #pragma unroll
         for (int d = 0; d < SPH_NROWS; d++) {
+            // Branch-free body (see k_density): a candidate that is not a neighbour, or a neighbour that
+            // is not approaching, subtracts nothing, so values and order of the sums are those of the gated
+            // loop.  With the branches the warp ran the impulse path on nearly every trip with half its
+            // lanes idle.
 #pragma unroll 4
             for (int j = R.b[d]; j < R.e[d]; j++) {
                 const float2 q = pos[j];
                 const float dx = q.x - p.x, dy = q.y - p.y;
                 const float r2 = dist2(dx, dy);
-                if (r2 > h2) continue;                                  // list membership
-                // (the particle itself, r2 == 0, falls out below: 0 * inf = NaN fails u > 0, as does
-                //  any coincident neighbour in the reference, fluid.c:446-451)
-                const float2 vq = vel[j];
-                float r, r_recip;
-                r_and_recip(r2, r, r_recip);
-                const float ratio = r * h_recip;
-                const float u_in = ((vix - vq.x) * dx + (viy - (vq.y + gdt)) * dy) * r_recip;
-                if (u_in > 0.0f) {                                      // fluid.c:451-462 (r == 0 gives NaN: skipped)
-                    const float imp = dt * (1.0f - ratio) * (P.sigma * u_in + P.beta * u_in * u_in);
-                    const float ix = clamp5(imp * dx * r_recip);
-                    const float iy = clamp5(imp * dy * r_recip);
-                    vx -= ix * 0.5f;
-                    vy -= iy * 0.5f;
-                }
+                const bool in = r2 <= h2;                               // list membership
+                const float2 vq = vel[j];                               // unconditional: cheaper than a predicated address
+                float rs;
+                asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rs) : "f"(r2));
+                // gravity is the same on both sides of the difference (fluid.c:398-412, :446-449)
+                const float u_in = ((v0.x - vq.x) * dx + (v0.y - vq.y) * dy) * rs;
+                // fluid.c:451-462; the particle itself and any coincident neighbour have r2 == 0, rs = inf,
+                // u = NaN, which fails u > 0 here exactly as the reference's 0/0 does
+                const bool hit = in && u_in > 0.0f;
+                // half the impulse, so that the +-5 clamp of checkVelocity becomes +-2.5 (exact scaling)
+                const float whdt = fmaf(-r2 * rs, h_recip, 1.0f) * hdt;
+                const float t = u_in * fmaf(P.beta, u_in, P.sigma) * whdt * rs;
+                const float ix = fminf(fmaxf(t * dx, -2.5f), 2.5f);
+                const float iy = fminf(fmaxf(t * dy, -2.5f), 2.5f);
+                vx -= hit ? ix : 0.0f;
+                vy -= hit ? iy : 0.0f;
             }
         }
         float2 np = make_float2(p.x + vx * dt, p.y + vy * dt);          // fluid.c:517-518
@@ -567,26 +582,30 @@ k_density(const DevParams *__restrict__ Pp, int *__restrict__ counters,
             const int self = (dd == SPH_CELL_DIV && i >= b && i < e) ? i : e;
             for (int seg = 0; seg < 2; seg++) {
                 const int jb = seg == 0 ? b : self + 1, je = seg == 0 ? self : e;
+                sph_mask_t bit = jb - b < SPH_MASK_BITS ? (sph_mask_t)1 << (jb - b) : 0;   // shifts out after the last mask bit
+                // Branch-free body: a candidate outside h adds an exact +0 (the weight is selected to 0),
+                // so the value and the order of the sums are those of the gated loop, but no lane ever
+                // waits for another lane's accept path.  With the branch the warp ran the accept path
+                // on nearly every trip with half its lanes idle (profiles/r1_final_full.csv: 23 of 32).
 #pragma unroll 4
                 for (int j = jb; j < je; j++) {
                     const float2 q = pos[j];
                     const float dx = q.x - p.x, dy = q.y - p.y;
                     const float r2 = dist2(dx, dy);
-                    if (r2 > h2) continue;
-                    if (j - b < SPH_MASK_BITS) m |= (sph_mask_t)1 << (j - b);
-                    nn++;
-                    float r, r_recip;
-                    r_and_recip(r2, r, r_recip);
-                    const float ratio = r * h_recip;
-                    if (ratio < 1.0f) {
-                        const float omr = 1.0f - ratio;
-                        const float omr2 = omr * omr;
-                        d += omr2;
-                        dn += omr2 * omr;
-                    }
+                    const bool in = r2 <= h2;                           // list membership (hash.c:185,221)
+                    m |= in ? bit : (sph_mask_t)0;
+                    bit += bit;
+                    // fluid.c:527-539 with r from one MUFU.SQRT (only r is needed here; sqrt(0) = 0, so a
+                    // coincident neighbour counts with ratio 0 like in the reference)
+                    float w = fmaxf(fmaf(-sqrt_approx(r2), h_recip, 1.0f), 0.0f);   // ratio < 1 gate: (1 - ratio)+
+                    w = in ? w : 0.0f;
+                    const float w2 = w * w;
+                    d += w2;
+                    dn = fmaf(w2, w, dn);
                 }
             }
             nmask[(size_t)dd * P.cap + i] = m;
+            nn += sph_mask_popc(m) + max(e - b - SPH_MASK_BITS, 0);     // candidates past the mask count as accepted
         }
         dens[i] = make_float2(d, dn);
         // a forward list cannot exceed the full neighbour count: cheap, conservative detection
@@ -615,6 +634,7 @@ k_relax(const DevParams *__restrict__ Pp, int *__restrict__ counters,
     const float h = P.h;
     const float h_recip = __fdiv_rn(1.0f, h);
     const float h2 = __fmul_rn(h, h);
+    const float K1 = dt2 * P.k, K2 = dt2 * P.k_near, Cs = dt2 * P.k_spring * h * 0.5f;
     if (blockIdx.x == 0 && threadIdx.x == 0) counters[CN_MAX_BUCKET] = 0;
 
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -622,35 +642,52 @@ k_relax(const DevParams *__restrict__ Pp, int *__restrict__ counters,
         if (u & SPH_HALO_BIT) { t_key[i] = SPH_KEY_DROP; continue; }
         const float2 p = pos[i];
         const float2 di = dens[i];
-        const float pp = P.k * (di.x - P.rest_density);        // fluid.c:563-564
-        const float ppn = P.k_near * di.y;
+        // fluid.c:563-564 + :591 with the constants folded.  With w = 1 - r/h the spring term is
+        // k_spring*(h - r)/2 = k_spring*h*w/2, so
+        //   D = dt^2 ((P_i+P_j) w + (Pn_i+Pn_j) w^2 + k_spring (h-r)/2) = w (A + B w),
+        //   A = K1 (rho_i + rho_j - 2 rho0) + C,  B = K2 (rhon_i + rhon_j),
+        //   K1 = dt^2 k,  K2 = dt^2 k_near,  C = dt^2 k_spring h / 2
+        // and a pair costs two FFMAs for A and B instead of forming four pressures.
+        const float Ai = fmaf(K1, di.x - 2.0f * P.rest_density, Cs);
+        const float Bi = K2 * di.y;
         float x = p.x, y = p.y;
         const int gxi = cell_coord(p.x, P.cell_h), gyi = cell_coord(p.y, P.cell_h);
         const Rows R = candidate_rows(p, P, cell_start);
         // pair physics for one listed neighbour (membership r2 <= h2, j != i already established)
         auto pair = [&](int j, float2 q, float2 dj) {
             const float dx = q.x - p.x, dy = q.y - p.y;
-            float r, r_recip;
-            r_and_recip(dist2(dx, dy), r, r_recip);
-            const float ratio = r * h_recip;
-            if (r <= 0.000001f) {
-                // coincident particles: only the list owner is nudged (fluid.c:583-586); owner =
-                // earlier bucket slot in the same cell, else the cell whose forward stencil
-                // (0,+1),(1,-1),(1,0),(1,+1) holds the other (hash.c:178-224)
-                const int gxj = cell_coord(q.x, P.cell_h), gyj = cell_coord(q.y, P.cell_h);
-                const bool owner = (gxi == gxj && gyi == gyj) ? ((u & SPH_UID_MASK) < (uid[j] & SPH_UID_MASK))
-                                                              : (gxi != gxj ? gxi < gxj : gyi < gyj);
-                if (owner) { x += 0.000001f; y += 0.000001f; }
+            const float r2 = dist2(dx, dy);
+            const float A = fmaf(dj.x, K1, Ai), B = fmaf(dj.y, K2, Bi);
+            if (r2 <= 1.0001e-12f) {
+                // (nearly) coincident particles, rare: the reference's tests as written, with an IEEE r
+                const float r = __fsqrt_rn(r2);
+                if (r <= 0.000001f) {
+                    // only the list owner is nudged (fluid.c:583-586); owner = earlier bucket slot in
+                    // the same cell, else the cell whose forward stencil (0,+1),(1,-1),(1,0),(1,+1)
+                    // holds the other (hash.c:178-224)
+                    const int gxj = cell_coord(q.x, P.cell_h), gyj = cell_coord(q.y, P.cell_h);
+                    const bool owner = (gxi == gxj && gyi == gyj) ? ((u & SPH_UID_MASK) < (uid[j] & SPH_UID_MASK))
+                                                                  : (gxi != gxj ? gxi < gxj : gyi < gyj);
+                    if (owner) { x += 0.000001f; y += 0.000001f; }
+                }
+                const float ratio = r * h_recip;
+                if (ratio < 1.0f && r > 0.0f) {                        // fluid.c:588
+                    const float w = 1.0f - ratio;
+                    const float s = __fdiv_rn(fmaf(B, w, A) * w, r);
+                    x = fmaf(-s, dx, x);
+                    y = fmaf(-s, dy, y);
+                }
+                return;
             }
-            if (ratio < 1.0f && r > 0.0f) {
-                const float pq = P.k * (dj.x - P.rest_density);
-                const float pqn = P.k_near * dj.y;
-                const float omr = 1.0f - ratio;
-                // fluid.c:591; the reference's fp64 tail is evaluated in fp32 here (<= 1 ulp of D)
-                const float D = dt2 * ((pp + pq) * omr + (ppn + pqn) * omr * omr + P.k_spring * (h - r) * 0.5f);
-                x -= D * dx * r_recip;
-                y -= D * dy * r_recip;
-            }
+            // r and 1/r from one MUFU.RSQ (r2 > 1e-12: finite); the ratio < 1 gate as (1 - ratio)+,
+            // branch-free: a listed neighbour has r2 <= h2, so the gate can only fail within rounding
+            // of r == h, where the displacement vanishes anyway
+            float rs;
+            asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rs) : "f"(r2));
+            const float w = fmaxf(fmaf(-r2 * rs, h_recip, 1.0f), 0.0f);
+            const float s = fmaf(B, w, A) * w * rs;
+            x = fmaf(-s, dx, x);
+            y = fmaf(-s, dy, y);
         };
 #pragma unroll
         for (int d = 0; d < SPH_NROWS; d++) {

@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 
 import parity_checks as pc
-from common import load_golden, random_state, ulp32
+from common import ULPS_POS, load_golden, random_state, ulp32
 from oracle.oracle import GatherOracle, default_tunable, lattice, make_problem
 
 pytestmark = pytest.mark.gpu
@@ -208,7 +208,13 @@ def test_device_side_lattice_equals_host_lattice(built_lib):
 def test_mover_autopilot_and_preset_cycle(built_lib):
     """BASELINE.json config 4 in small: mover on the render rank's autopilot path (renderer.c:513-531),
     fluid presets cycled a -> b -> x -> y (controls.c:344-401), a new parameter block every frame landing
-    in the last sub-step (fluid.c:293-294).  CUDA (sph_run_frame) vs the gather oracle."""
+    in the last sub-step (fluid.c:293-294).  CUDA (sph_run_frame) vs the gather oracle, frame by frame.
+
+    The two are compared after every frame at rounding level (the bar of check_tight_vs_gather_oracle:
+    ULPS_POS ulps of the tank width, x4 per step) and then put back on ONE trajectory, because this
+    lattice collapse amplifies a 1-ulp change of the initial x to 2e-2 h within two frames and to 0.9 h
+    within eight (measured on the oracle against itself): a comparison of free-running trajectories
+    over 32 steps would test luck, not the kernels."""
     import ctypes as C
     import sph_b200
     n_req = 12000
@@ -223,16 +229,22 @@ def test_mover_autopilot_and_preset_cycle(built_lib):
     L = sph_b200._host()
     gl_x, direction = C.c_float(-0.2), C.c_int(1)
     coords = np.zeros(2 * (len(a) + 64), "i2")
-    for frame in range(8):
+    tol = ULPS_POS * ulp32(prob["tank_w"]) * 4 ** 3          # four steps per frame
+    frames = 8
+    for frame in range(frames):
         L.sph_host_mover_autopilot(C.byref(ts), prob["tank_w"], prob["tank_h"], C.byref(gl_x), C.byref(direction))
         L.sph_host_preset(C.byref(ts), "abxy"[(frame // 2) % 4].encode())
         C.memmove(C.byref(t), C.byref(ts), 64)
         n = b.run_frame(ts, 4, coords)
         o.step(3); o.queue_params(t); o.step(1)
         assert n == len(a)
-    x, _ = b.download(); y, _ = o.download()
-    d = np.hypot(x["x"] - y["x"], x["y"] - y["y"]) / prob["h"]
-    assert d.max() <= 2e-2 and np.sqrt((d ** 2).mean()) <= 1e-3, (d.max(), np.sqrt((d ** 2).mean()))
+        x, ux = b.download(); y, uy = o.download()
+        assert np.array_equal(ux, uy)
+        err = max(np.abs(x["x"] - y["x"]).max(), np.abs(x["y"] - y["y"]).max())
+        assert err <= tol, (frame, err, tol)
+        assert np.abs(x["v_x"] - y["v_x"]).max() <= tol / t.time_step * 1.5, frame
+        if frame < frames - 1:
+            b.upload(y, uy)                                  # same trajectory again
     assert np.array_equal(coords[:2 * n].reshape(n, 2), b.pack_coords())
     s = b.status()
     assert s.capacity_overflow == 0 and s.n_local == len(a)
