@@ -14,8 +14,9 @@ def _stale(out, deps):
     return not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps)
 
 
-def build(force=False, verbose=False):
-    out = os.path.join(HERE, "libsph_b200.so")
+def build(force=False, verbose=False, defines=(), out_name="libsph_b200.so"):
+    """defines / out_name: tuning variants for A/B runs on the GPU box (scripts/gpu_variants.sh)."""
+    out = os.path.join(HERE, out_name)
     csrc = os.path.join(HERE, "csrc")
     host = os.path.join(HERE, "host")
     inc = os.path.join(HERE, "..", "include")
@@ -32,10 +33,18 @@ def build(force=False, verbose=False):
         o = os.path.join(bdir, os.path.basename(src) + ".o")
         subprocess.check_call(["gcc", "-std=gnu99", "-O2", "-ffp-contract=off", "-fPIC", "-Wall", "-I", inc, "-c", src, "-o", o])
         objs.append(o)
-    cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-I", inc, "-shared", "-o", out] + cu + objs
+    cmd = ["nvcc"] + NVCC_FLAGS + [f"-D{d}" for d in defines] + (["-Xptxas", "-v"] if verbose else []) + \
+        ["-I", inc, "-shared", "-o", out] + cu + objs
     subprocess.check_call(cmd)
     return out
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    # python -m sph_b200.build [--force] [-v] [--variant NAME -DSPH_X=1 ...]  ->  sph_b200/variants/NAME.so
+    if "--variant" in sys.argv:
+        name = sys.argv[sys.argv.index("--variant") + 1]
+        os.makedirs(os.path.join(HERE, "variants"), exist_ok=True)
+        print(build(force=True, verbose="-v" in sys.argv, defines=[a[2:] for a in sys.argv if a.startswith("-D")],
+                    out_name=os.path.join("variants", name + ".so")))
+    else:
+        print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -15,6 +15,20 @@
 #include "sph_device.cuh"
 
 #define SPH_THREADS 256
+// resident blocks per SM the register allocation of each gather is held to (measured)
+#ifndef SPH_UNROLL
+#define SPH_UNROLL 4          // candidates per trip of the gather loops (loads issued together)
+#endif
+constexpr int kGatherUnroll = SPH_UNROLL;     // (#pragma unroll takes a constant expression, not a macro)
+#ifndef SPH_BLOCKS_ADVECT
+#define SPH_BLOCKS_ADVECT 4
+#endif
+#ifndef SPH_BLOCKS_DENSITY
+#define SPH_BLOCKS_DENSITY 6
+#endif
+#ifndef SPH_BLOCKS_RELAX
+#define SPH_BLOCKS_RELAX 4
+#endif
 
 // -------------------------------------------------------------------------------------------
 // neighbourhood iteration: sort-grid rows gy-DIV..gy+DIV, columns gx-DIV..gx+DIV of the CURRENT window
@@ -56,6 +70,11 @@ __device__ __forceinline__ float sqrt_approx(float r2)
     return r;
 }
 
+// Candidate ranges of a particle: the columns gx-DIV..gx+DIV of the rows gy-DIV..gy+DIV.
+// (Cutting each row's columns to what its distance in y leaves reachable -- about 14 % fewer candidates
+//  per particle for DIV = 2 -- was measured and gained nothing: a warp runs the LONGEST range of its 32
+//  lanes, and those sit at different places inside their cells; the per-lane ranges also stop coinciding,
+//  which costs L1 wavefronts.)
 __device__ __forceinline__ Rows candidate_rows(float2 p, const DevParams &P, const int *__restrict__ cell_start)
 {
     Rows r;
@@ -168,7 +187,7 @@ __device__ __forceinline__ void bin_position(int i, float2 p, int extra_bits, co
 //     + boundaryConditions (:656) + identify_oob_particles (:481) + ghost selection
 //     (communication.c:134-141) + first half of hash_fluid pass 1 (hash.c:153-166)
 // -------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(SPH_THREADS, 4)
+__global__ void __launch_bounds__(SPH_THREADS, SPH_BLOCKS_ADVECT)
 k_advect(const DevParams *__restrict__ Pp, int *__restrict__ counters,
          const float2 *__restrict__ pos, const float2 *__restrict__ vel, const uint32_t *__restrict__ uid,
          const int *__restrict__ cell_start,
@@ -197,7 +216,7 @@ k_advect(const DevParams *__restrict__ Pp, int *__restrict__ counters,
             // is not approaching, subtracts nothing, so values and order of the sums are those of the gated
             // loop.  With the branches the warp ran the impulse path on nearly every trip with half its
             // lanes idle.
-#pragma unroll 4
+#pragma unroll kGatherUnroll
             for (int j = R.b[d]; j < R.e[d]; j++) {
                 const float2 q = pos[j];
                 const float dx = q.x - p.x, dy = q.y - p.y;
@@ -557,7 +576,7 @@ k_reorder(const DevParams *__restrict__ Pp, int *__restrict__ counters, const in
 //     Output: (density, density_near) per resident entry, ghosts included (their pressure is
 //     needed by the relaxation of the locals next to them, fluid.c:560-565).
 // -------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(SPH_THREADS)
+__global__ void __launch_bounds__(SPH_THREADS, SPH_BLOCKS_DENSITY)
 k_density(const DevParams *__restrict__ Pp, int *__restrict__ counters,
           const float2 *__restrict__ pos, const int *__restrict__ cell_start, float2 *__restrict__ dens,
           sph_mask_t *__restrict__ nmask)
@@ -587,7 +606,7 @@ k_density(const DevParams *__restrict__ Pp, int *__restrict__ counters,
                 // so the value and the order of the sums are those of the gated loop, but no lane ever
                 // waits for another lane's accept path.  With the branch the warp ran the accept path
                 // on nearly every trip with half its lanes idle (profiles/r1_final_full.csv: 23 of 32).
-#pragma unroll 4
+#pragma unroll kGatherUnroll
                 for (int j = jb; j < je; j++) {
                     const float2 q = pos[j];
                     const float dx = q.x - p.x, dy = q.y - p.y;
@@ -619,7 +638,7 @@ k_density(const DevParams *__restrict__ Pp, int *__restrict__ counters,
 //     incl. boundaryConditions + second ghost selection (fluid.c:337) + binning for the re-hash
 //     (fluid.c:341).
 // -------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(SPH_THREADS, 4)
+__global__ void __launch_bounds__(SPH_THREADS, SPH_BLOCKS_RELAX)
 k_relax(const DevParams *__restrict__ Pp, int *__restrict__ counters,
         const float2 *__restrict__ pos, const float2 *__restrict__ prev, const uint32_t *__restrict__ uid,
         const float2 *__restrict__ dens, const int *__restrict__ cell_start,
@@ -693,11 +712,15 @@ k_relax(const DevParams *__restrict__ Pp, int *__restrict__ counters,
         for (int d = 0; d < SPH_NROWS; d++) {
             // the lists were built by k_density on these same positions: walk its acceptance bits
             // (candidate order, so the order of summation is unchanged) ...
+            // (A branch-free loop over ALL candidates like k_density's was measured here too: 121 us
+            //  against 68 -- it loads position AND density of ~50 candidates instead of ~22 neighbours,
+            //  and L1 wavefronts, not instruction issue, then bound the kernel.)
             const int b = R.b[d];
             sph_mask_t m = nmask[(size_t)d * P.cap + i];
             while (m) {
                 // two neighbours per trip, all four loads (position + density of each) issued up front:
-                // load latency was this kernel's top stall (profiles/r1_div2_full.csv, long_scoreboard)
+                // load latency was this kernel's top stall (profiles/r1_div2_full.csv, long_scoreboard);
+                // four per trip (eight loads) was measured slower, 83 us against 68
                 const int j0 = b + sph_mask_ffs(m) - 1;
                 m &= m - 1;
                 const bool two = m != 0;
