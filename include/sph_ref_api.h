@@ -60,6 +60,16 @@ void sph_ref_detach(void);
 int sph_ref_pack_coords(short *fluid_particle_coords, int max_pairs);
 const char *sph_ref_last_error(void);
 sph_ctx *sph_ref_context(void);
+/* An UNMODIFIED start_simulation (no attach call at all) also works: the first predict_positions attaches
+ * by itself from what the calls carry (device from SPH_B200_DEVICE, default 0) and switches the host
+ * mirror on, because such a driver packs its frame from the host AoS (fluid.c:358-362).  If the GPU
+ * cannot be used that path aborts -- there is no CPU fallback.
+ * sph_ref_set_mirror(n): write positions/velocities back into the host AoS after every n-th step
+ * (0 = never, the default after an explicit attach; SPH_REF_MIRROR_EVERY overrides the lazy default 1). */
+void sph_ref_set_mirror(int every_n_steps);
+/* what MPI_Comm_rank / MPI_Comm_size(MPI_COMM_COMPUTE) say on this rank (partitionProblem asks them,
+ * geometry.c:105-108; the library itself does not link MPI).  Default 0 of 1. */
+void sph_ref_set_rank(int rank, int nranks);
 
 /* ---- fluid.h:112-126 ---- */
 void apply_gravity(fluid_particle **fluid_particle_pointers, param *params);
@@ -74,6 +84,15 @@ void boundaryConditions(fluid_particle *p, AABB_t *boundary, param *params);
 void calculate_density(fluid_particle *p, fluid_particle *q, float ratio);
 void updateVelocity(fluid_particle *p, param *params);
 void checkVelocity(float *v_x, float *v_y);
+
+/* ---- start-up: geometry.h:45-49, fluid.h:121 (host arithmetic identical to the reference's; silent) ---- */
+void constructFluidVolume(fluid_particle **fluid_particle_pointers, fluid_particle *fluid_particles, AABB_t *fluid,
+                          int start_x, int number_particles_x, edge_t *edges, float spacing, param *params);
+void setParticleNumbers(AABB_t *boundary_global, AABB_t *fluid_global, edge_t *edges, oob_t *out_of_bounds,
+                        int number_particles_x, float spacing, param *params);
+void partitionProblem(AABB_t *boundary_global, AABB_t *fluid_global, int *x_start, int *length_x, float spacing, param *params);
+void initParticles(fluid_particle **fluid_particle_pointers, fluid_particle *fluid_particles, AABB_t *water, int start_x,
+                   int number_particles_x, edge_t *edges, int max_fluid_particles_local, float spacing, param *params);
 
 /* ---- hash.h:50-52 ---- */
 unsigned int hash_val(float x, float y, neighbor_grid_t *grid, param *params);

@@ -282,8 +282,15 @@ static void do_recv(void *buf, int count, MPI_Datatype type, int src, int tag, M
     }
 }
 
+static int to_render(MPI_Comm comm, int rank);
+static int send_to_render(const void *buf, int count, MPI_Datatype type, int tag);
+
 int MPI_Send(const void *buf, int count, MPI_Datatype type, int dest, int tag, MPI_Comm comm)
-{ (void)comm; do_send(buf, count, type, dest, tag); return MPI_SUCCESS; }
+{
+    if (to_render(comm, dest)) return send_to_render(buf, count, type, tag);
+    do_send(buf, count, type, dest, tag);
+    return MPI_SUCCESS;
+}
 
 int MPI_Recv(void *buf, int count, MPI_Datatype type, int src, int tag, MPI_Comm comm, MPI_Status *status)
 { (void)comm; do_recv(buf, count, type, src, tag, status); return MPI_SUCCESS; }
@@ -313,8 +320,8 @@ static int new_req(void)
 
 int MPI_Isend(const void *buf, int count, MPI_Datatype type, int dest, int tag, MPI_Comm comm, MPI_Request *req)
 {
-    (void)comm;
-    do_send(buf, count, type, dest, tag);
+    if (to_render(comm, dest)) send_to_render(buf, count, type, tag);
+    else do_send(buf, count, type, dest, tag);
     int r = new_req();
     g_reqs[r].is_recv = 0;
     *req = r;
@@ -362,23 +369,56 @@ double MPI_Wtime(void)
     return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
 }
 
-/* Every communicator the harness uses is "all compute ranks". */
-int MPI_Comm_rank(MPI_Comm comm, int *rank) { (void)comm; *rank = g_rank; return MPI_SUCCESS; }
-int MPI_Comm_size(MPI_Comm comm, int *size) { (void)comm; *size = g_nranks; return MPI_SUCCESS; }
+/* Communicators.  Without a render stub every communicator is "all compute ranks" (the harness sets
+ * MPI_COMM_COMPUTE = MPI_COMM_WORLD).  With one (mini_mpi_set_render, used by ref_drive.c to run the
+ * reference's own start_simulation) the world has one more rank in front, the render rank, which lives
+ * in the hooks: MPI_COMM_WORLD ranks are shifted by one and MPI_Comm_create hands out the compute
+ * communicator (communication.c:36-47). */
+#define COMM_COMPUTE 2
+static const mini_mpi_render_t *g_render = NULL;
+void mini_mpi_set_render(const mini_mpi_render_t *r) { g_render = r; }
+static int to_render(MPI_Comm comm, int rank) { return g_render && comm == MPI_COMM_WORLD && rank == 0; }
+
+int MPI_Comm_rank(MPI_Comm comm, int *rank) { *rank = g_rank + (g_render && comm == MPI_COMM_WORLD); return MPI_SUCCESS; }
+int MPI_Comm_size(MPI_Comm comm, int *size) { *size = g_nranks + (g_render && comm == MPI_COMM_WORLD); return MPI_SUCCESS; }
 int MPI_Comm_group(MPI_Comm comm, MPI_Group *group) { (void)comm; *group = 1; return MPI_SUCCESS; }
 int MPI_Group_excl(MPI_Group g, int n, const int r[], MPI_Group *ng) { (void)g; (void)n; (void)r; *ng = 2; return MPI_SUCCESS; }
 int MPI_Group_incl(MPI_Group g, int n, const int r[], MPI_Group *ng) { (void)g; (void)n; (void)r; *ng = 3; return MPI_SUCCESS; }
-int MPI_Comm_create(MPI_Comm c, MPI_Group g, MPI_Comm *nc) { (void)c; (void)g; *nc = MPI_COMM_WORLD; return MPI_SUCCESS; }
+int MPI_Comm_create(MPI_Comm c, MPI_Group g, MPI_Comm *nc)
+{ (void)c; *nc = (g_render && g == 2) ? COMM_COMPUTE : MPI_COMM_WORLD; return MPI_SUCCESS; }
 int MPI_Group_free(MPI_Group *g) { *g = 0; return MPI_SUCCESS; }
 
-/* Render-rank protocol: deliberately unimplemented (see file header). */
+/* Render-rank protocol (fluid.c:122-124, :167-171, :238, :293-294, :365): served by the hooks when a
+ * render stub is installed, otherwise deliberately unimplemented (see file header). */
 #define UNIMPL(name) do { die(name " is part of the render-rank protocol, not provided by this shim"); return -1; } while (0)
 int MPI_Probe(int s, int t, MPI_Comm c, MPI_Status *st) { (void)s; (void)t; (void)c; (void)st; UNIMPL("MPI_Probe"); }
-int MPI_Bcast(void *b, int n, MPI_Datatype t, int r, MPI_Comm c) { (void)b; (void)n; (void)t; (void)r; (void)c; UNIMPL("MPI_Bcast"); }
+int MPI_Bcast(void *b, int n, MPI_Datatype t, int r, MPI_Comm c)
+{
+    if (!to_render(c, r)) UNIMPL("MPI_Bcast");
+    g_render->bcast(b, type_bytes(t, n));
+    return MPI_SUCCESS;
+}
 int MPI_Gatherv(const void *sb, int sc, MPI_Datatype st, void *rb, const int rc[], const int d[], MPI_Datatype rt, int r, MPI_Comm c)
-{ (void)sb; (void)sc; (void)st; (void)rb; (void)rc; (void)d; (void)rt; (void)r; (void)c; UNIMPL("MPI_Gatherv"); }
+{
+    (void)rb; (void)rc; (void)d; (void)rt;
+    if (!to_render(c, r)) UNIMPL("MPI_Gatherv");
+    g_render->from_compute(sb, type_bytes(st, sc), MINI_MPI_TAG_GATHER);
+    return MPI_SUCCESS;
+}
 int MPI_Scatterv(const void *sb, const int sc[], const int d[], MPI_Datatype st, void *rb, int rc, MPI_Datatype rt, int r, MPI_Comm c)
-{ (void)sb; (void)sc; (void)d; (void)st; (void)rb; (void)rc; (void)rt; (void)r; (void)c; UNIMPL("MPI_Scatterv"); }
+{
+    (void)sb; (void)sc; (void)d; (void)st;
+    if (!to_render(c, r)) UNIMPL("MPI_Scatterv");
+    g_render->scatter(rb, type_bytes(rt, rc));
+    return MPI_SUCCESS;
+}
+
+static int send_to_render(const void *buf, int count, MPI_Datatype type, int tag)
+{
+    if (T(type)->disp) die("indexed type sent to the render rank");
+    g_render->from_compute(buf, type_bytes(type, count), tag);
+    return MPI_SUCCESS;
+}
 
 /* fluid.c's main() (renamed by -Dmain=ref_main) references the render rank. */
 int start_renderer(void) { die("start_renderer: no render rank in the oracle build"); return -1; }

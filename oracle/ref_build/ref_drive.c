@@ -1,0 +1,146 @@
+/*
+ * ref_drive -- runs the reference's OWN start_simulation() (fluid.c:71-395, unmodified, compiled where
+ * it lies) against a headless render rank that lives in this process.  TEST INFRASTRUCTURE ONLY.
+ *
+ * Two binaries are linked from this file by oracle/ref_build/Makefile:
+ *
+ *   oracle/_ref/sph_ref_cpu_drive   ref_drive.o + libref_driver.so
+ *       the pure reference.  Pins the oracle's start-up path (tests/test_ref_drive.py).
+ *   oracle/_ref/sph_ref_gpu_drive   ref_drive.o + libsph_b200.so + libref_driver.so, in that order
+ *       the same unmodified driver, but every function of include/sph_ref_api.h that it calls
+ *       (apply_gravity ... hash_fluid ... updateVelocities, partitionProblem, initParticles, ...) is
+ *       resolved by the dynamic linker to libsph_b200.so, which comes first in the lookup order; the
+ *       reference's bodies in libref_driver.so are never reached.  This is the drop-in of INTEGRATION.md
+ *       with ZERO source changes: the library attaches itself at the first predict_positions and keeps
+ *       the host AoS current, because this driver packs its frames from it (fluid.c:358-362).
+ *
+ * The render stub answers the compute rank's protocol (shim/mpi.h, mini_mpi_render_t) and records what
+ * a renderer would have been given:
+ *
+ *   header   "SPHD", int32 n_global, float world_w, float world_h, int32 frames
+ *   64 bytes the first parameter block (Gatherv, fluid.c:238)
+ *   per frame: 64 bytes the block scattered for that frame (fluid.c:293-294), int32 pairs, pairs x 2 int16
+ *
+ * Per frame the stub moves the mover (cx = W (0.25 + 0.03 f), cy = 0.3 H) and after --frames frames it
+ * sets kill_sim (renderer.c:340-345).
+ */
+#define _GNU_SOURCE
+#include <dlfcn.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "mpi.h"
+#include "fluid.h"
+#include "communication.h"
+
+static struct {
+    int frames_wanted, frames_seen, scatters;
+    float world[2];
+    int n_global;
+    tunable_parameters first, current;
+    int have_first;
+    FILE *out;
+} R;
+
+static void r_bcast(void *buf, size_t bytes)
+{
+    /* init_ogl's screen size (renderer.c:94-102 sends pixel dims): 1920 x 1080 -> a 16:9 tank */
+    short dims[2] = { 1920, 1080 };
+    if (bytes != sizeof dims) { fprintf(stderr, "ref_drive: unexpected Bcast of %zu bytes\n", bytes); exit(3); }
+    memcpy(buf, dims, sizeof dims);
+}
+
+static void write_header(void)
+{
+    int32_t n = R.n_global, f = R.frames_wanted;
+    fwrite("SPHD", 1, 4, R.out);
+    fwrite(&n, 4, 1, R.out);
+    fwrite(R.world, 4, 2, R.out);
+    fwrite(&f, 4, 1, R.out);
+    fwrite(&R.first, sizeof R.first, 1, R.out);
+}
+
+static void r_from_compute(const void *buf, size_t bytes, int tag)
+{
+    if (tag == 8 && bytes == 8) memcpy(R.world, buf, 8);                 /* fluid.c:169 */
+    else if (tag == 9 && bytes == 4) memcpy(&R.n_global, buf, 4);        /* fluid.c:170 */
+    else if (tag == MINI_MPI_TAG_GATHER && bytes == sizeof R.first) {    /* fluid.c:238 */
+        memcpy(&R.first, buf, sizeof R.first);
+        R.current = R.first;
+        R.have_first = 1;
+        write_header();
+    } else if (tag == 17) {                                              /* fluid.c:365 */
+        int32_t pairs = (int32_t)(bytes / 4);
+        fwrite(&R.current, sizeof R.current, 1, R.out);
+        fwrite(&pairs, 4, 1, R.out);
+        fwrite(buf, 4, (size_t)pairs, R.out);
+        R.frames_seen++;
+    } else {
+        fprintf(stderr, "ref_drive: unexpected message to the render rank: tag %d, %zu bytes\n", tag, bytes);
+        exit(3);
+    }
+}
+
+static void r_scatter(void *buf, size_t bytes)
+{
+    if (bytes != sizeof R.current || !R.have_first) { fprintf(stderr, "ref_drive: bad Scatterv\n"); exit(3); }
+    const int f = R.scatters++;
+    R.current = R.first;
+    R.current.mover_center_x = R.world[0] * (0.25f + 0.03f * (float)f);
+    R.current.mover_center_y = R.world[1] * 0.3f;
+    R.current.kill_sim = f >= R.frames_wanted;
+    memcpy(buf, &R.current, sizeof R.current);
+}
+
+/* start_simulation leaves params.tunable_params.mover_center_{x,y} uninitialised until the first Scatterv
+ * (fluid.c:80, :279): give that stack memory a defined content so that two runs see the same block */
+static __attribute__((noinline)) void paint_stack(void)
+{
+    volatile char pad[1 << 16];
+    for (size_t i = 0; i < sizeof pad; i++) pad[i] = 0;
+}
+
+static void report_binding(const char *name)
+{
+    void *sym = dlsym(RTLD_DEFAULT, name);
+    Dl_info info;
+    if (sym && dladdr(sym, &info) && info.dli_fname) printf("binding: %s -> %s\n", name, info.dli_fname);
+    else printf("binding: %s -> ?\n", name);
+}
+
+int main(int argc, char **argv)
+{
+    const char *out = "ref_drive.bin";
+    R.frames_wanted = 4;
+    for (int i = 1; i + 1 < argc; i++) {
+        if (!strcmp(argv[i], "--frames")) R.frames_wanted = atoi(argv[i + 1]);
+        if (!strcmp(argv[i], "--out")) out = argv[i + 1];
+    }
+    R.out = fopen(out, "wb");
+    if (!R.out) { perror(out); return 2; }
+
+    static const mini_mpi_render_t hooks = { r_bcast, r_from_compute, r_scatter };
+    mini_mpi_set_render(&hooks);
+
+    const char *probe[] = { "start_simulation", "apply_gravity", "viscosity_impluses", "predict_positions",
+                            "identify_oob_particles", "hash_fluid", "hash_halo", "startHaloExchange",
+                            "finishHaloExchange", "double_density_relaxation", "updateVelocities",
+                            "partitionProblem", "setParticleNumbers", "initParticles" };
+    for (size_t i = 0; i < sizeof probe / sizeof *probe; i++) report_binding(probe[i]);
+    fflush(stdout);
+
+    /* the compute rank's side of fluid.c:46-68, with the reference's own functions */
+    MPI_Init(&argc, &argv);
+    create_communicators();
+    createMpiTypes();
+    paint_stack();
+    start_simulation();
+    MPI_Finalize();
+
+    fclose(R.out);
+    printf("ref_drive: %d frames of %d particles, world %.4f x %.4f -> %s\n", R.frames_seen, R.n_global,
+           R.world[0], R.world[1], out);
+    return R.frames_seen == R.frames_wanted ? 0 : 4;
+}

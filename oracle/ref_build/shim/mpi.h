@@ -93,4 +93,18 @@ void mini_mpi_barrier(void);
 /* Small shared scratch array of doubles (nranks*8 slots) for harness reductions. */
 double *mini_mpi_shared_doubles(void);
 
+
+/* ---- headless render rank living in the same process (oracle/ref_build/ref_drive.c) ----
+ * The reference's start_simulation talks to rank 0 of MPI_COMM_WORLD: Bcast of the pixel size
+ * (fluid.c:122-124), Sends of the world size and particle count (:167-171), Gatherv of the first
+ * parameter block (:238), one Scatterv of parameters (:293-294) and one Isend of int16 coordinates
+ * (:365) per frame.  With these hooks installed the shim serves exactly that and nothing else. */
+#define MINI_MPI_TAG_GATHER (-100)
+typedef struct {
+    void (*bcast)(void *buf, size_t bytes);
+    void (*from_compute)(const void *buf, size_t bytes, int tag);   /* Send, Isend, Gatherv (MINI_MPI_TAG_GATHER) */
+    void (*scatter)(void *buf, size_t bytes);
+} mini_mpi_render_t;
+void mini_mpi_set_render(const mini_mpi_render_t *r);
+
 #endif

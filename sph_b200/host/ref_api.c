@@ -30,8 +30,12 @@ static struct {
     int pending_gravity, pending_viscosity, pending_relax;
     int n;
     float tank_w, tank_h;
+    int mirror;                 /* keep the host AoS current (an unmodified driver reads it, fluid.c:358-362) */
+    int mirror_every;           /* ... every N completed steps (1 = every step) */
+    long steps_done;
+    int rank, nranks;           /* what MPI_Comm_rank/size(MPI_COMM_COMPUTE) would say (geometry.c:105-108) */
     char err[256];
-} G;
+} G = { .nranks = 1 };
 
 static void note(const char *where, int rc)
 {
@@ -52,10 +56,17 @@ static void sync_params(const char *where, const param *params)
     note(where, sph_set_params(G.ctx, &G.pushed));
 }
 
+void sph_ref_set_rank(int rank, int nranks) { G.rank = rank; G.nranks = nranks > 0 ? nranks : 1; }
+void sph_ref_set_mirror(int every_n_steps) { G.mirror = every_n_steps > 0; G.mirror_every = every_n_steps > 0 ? every_n_steps : 1; }
+
 int sph_ref_attach(fluid_particle **pointers, param *params, AABB_t *boundary, neighbor_grid_t *grid, int device)
 {
     sph_ref_detach();
+    const int rank = G.rank, nranks = G.nranks, mirror = G.mirror, mirror_every = G.mirror_every;
+    const int armed_g = G.pending_gravity, armed_v = G.pending_viscosity;    /* a lazy attach happens between arming and firing */
     memset(&G, 0, sizeof G);
+    G.rank = rank; G.nranks = nranks; G.mirror = mirror; G.mirror_every = mirror_every ? mirror_every : 1;
+    G.pending_gravity = armed_g; G.pending_viscosity = armed_v;
     const int n = params->number_fluid_particles_local;
     sph_config cfg;
     memset(&cfg, 0, sizeof cfg);
@@ -109,20 +120,41 @@ int sph_ref_pack_coords(short *coords, int max_pairs)
 void apply_gravity(fluid_particle **pointers, param *params)
 {
     (void)pointers;
-    sync_params("apply_gravity", params);
+    if (G.ctx) sync_params("apply_gravity", params);     /* (an unmodified driver attaches at predict_positions) */
     G.pending_gravity = 1;
 }
 
 void viscosity_impluses(fluid_particle **pointers, neighbor *neighbors, param *params)
 {
     (void)pointers; (void)neighbors;
-    sync_params("viscosity_impluses", params);
+    if (G.ctx) sync_params("viscosity_impluses", params);
     G.pending_viscosity = 1;
+}
+
+/* An UNMODIFIED start_simulation never calls sph_ref_attach.  Its first call that has to run on the
+ * device is predict_positions, and by then everything attach needs has been passed in: the pointer
+ * array and counts (apply_gravity), the tank (this call), and the hash spacing, which the driver sets
+ * to the smoothing radius (fluid.c:176).  Such a driver also reads the host AoS when it packs the
+ * frame (fluid.c:358-362), so the mirror is switched on (SPH_REF_MIRROR_EVERY=N relaxes it to every
+ * N-th step; the driver packs every 4th, fluid.c:105).  Without a usable GPU this ABORTS: the
+ * reference's functions are void, and carrying on would hand the renderer a frozen fluid. */
+static void lazy_attach(fluid_particle **pointers, AABB_t *boundary, param *params)
+{
+    neighbor_grid_t grid;
+    memset(&grid, 0, sizeof grid);
+    grid.spacing = params->tunable_params.smoothing_radius;
+    const char *dev = getenv("SPH_B200_DEVICE"), *every = getenv("SPH_REF_MIRROR_EVERY");
+    if (!G.mirror) sph_ref_set_mirror(every && atoi(every) > 0 ? atoi(every) : 1);
+    const int rc = sph_ref_attach(pointers, params, boundary, &grid, dev ? atoi(dev) : 0);
+    if (rc != SPH_OK) {
+        fprintf(stderr, "sph_ref_api: cannot put the simulation on the GPU (%s); there is no CPU path\n", G.err);
+        abort();
+    }
 }
 
 void predict_positions(fluid_particle **pointers, AABB_t *boundary_global, param *params)
 {
-    (void)pointers; (void)boundary_global;
+    if (!G.ctx) lazy_attach(pointers, boundary_global, params);
     sync_params("predict_positions", params);
     if (!G.pending_gravity || !G.pending_viscosity) {
         snprintf(G.err, sizeof G.err, "predict_positions: the fused stage needs apply_gravity and "
@@ -164,11 +196,16 @@ void updateVelocities(fluid_particle **pointers, edge_t *edges, AABB_t *boundary
 
 void hash_fluid(fluid_particle **pointers, neighbor_grid_t *grid, param *params, bool compute_density)
 {
-    (void)pointers; (void)grid;
+    (void)grid;
     sync_params("hash_fluid", params);
     int rc = sph_sort(G.ctx);
     note("hash_fluid", rc);
     if (rc == SPH_OK && compute_density) note("hash_fluid", sph_density(G.ctx));
+    if (rc == SPH_OK && !compute_density) {
+        /* the re-hash of fluid.c:341 ends the step: positions and velocities are final */
+        G.steps_done++;
+        if (G.mirror && G.steps_done % G.mirror_every == 0) note("hash_fluid", sph_ref_sync_to_host(pointers, params));
+    }
 }
 
 void hash_halo(fluid_particle **pointers, neighbor_grid_t *grid, param *params, bool compute_density)
@@ -193,6 +230,78 @@ void finishHaloExchange(fluid_particle **pointers, fluid_particle *particles, ed
 { (void)pointers; (void)particles; (void)edges; params->number_halo_particles = 0; }
 void transferOOBParticles(fluid_particle **pointers, fluid_particle *particles, oob_t *oob, param *params)
 { (void)pointers; (void)particles; (void)oob; (void)params; }
+
+/* ------------------------------------------------------------------ geometry.h / fluid.h start-up (host) */
+
+/* The leading members of edge_t / oob_t (communication.h:45-63).  edge_t ends in MPI_Request reqs[4],
+ * whose size depends on the MPI ABI; nothing here goes that far. */
+struct edge_head { int max_edge_particles; fluid_particle **left, **right; int n_left, n_right; };
+struct oob_head { int max_oob_particles; int *left, *right; int n_left, n_right; int *vacant; int number_vacancies; };
+
+void constructFluidVolume(fluid_particle **pointers, fluid_particle *particles, AABB_t *fluid, int start_x,
+                          int number_particles_x, edge_t *edges, float spacing, param *params)
+{
+    const int num_y = (int)floor((fluid->max_y - fluid->min_y) / spacing);          /* geometry.c:35 */
+    struct edge_head *e = (struct edge_head *)edges;
+    e->n_left = 0; e->n_right = 0;                                                  /* :38-39 */
+    int i = 0;
+    for (int ny = 0; ny < num_y; ny++) {
+        const float y = fluid->min_y + ny * spacing;                                /* :47 */
+        for (int nx = 0; nx < number_particles_x; nx++) {
+            fluid_particle *p = particles + i;
+            p->x = fluid->min_x + (start_x + nx) * spacing;                         /* :49 */
+            p->y = y;
+            pointers[i] = p;
+            p->id = i;
+            i++;
+        }
+    }
+    params->number_fluid_particles_local = i;                                       /* :65-66 */
+    params->max_fluid_particle_index = i - 1;
+}
+
+void setParticleNumbers(AABB_t *boundary_global, AABB_t *fluid_global, edge_t *edges, oob_t *out_of_bounds,
+                        int number_particles_x, float spacing, param *params)
+{
+    (void)boundary_global; (void)fluid_global; (void)number_particles_x; (void)spacing;
+    ((struct edge_head *)edges)->max_edge_particles = params->number_fluid_particles_global;       /* geometry.c:82 */
+    ((struct oob_head *)out_of_bounds)->max_oob_particles = params->number_fluid_particles_global; /* :87 */
+    ((struct oob_head *)out_of_bounds)->number_vacancies = 0;                                      /* :96 */
+}
+
+void partitionProblem(AABB_t *boundary_global, AABB_t *fluid_global, int *x_start, int *length_x, float spacing, param *params)
+{
+    const int nprocs = G.nranks, rank = G.rank;                                     /* geometry.c:105-108 */
+    const int fluid_particles_x = (int)floor((fluid_global->max_x - fluid_global->min_x) / spacing) + 1;   /* :112 */
+    const int equal = fluid_particles_x / nprocs, remaining = fluid_particles_x - equal * nprocs;          /* :118-125 */
+    int number_to_left = 0, mine = 0, total_x = 0;
+    for (int i = 0; i < nprocs; i++) {
+        const int len = equal + (i < remaining ? 1 : 0);                            /* :128-129 */
+        if (i < rank) number_to_left += len;
+        if (i == rank) mine = len;
+        total_x += len;
+    }
+    *x_start = number_to_left;                                                      /* :137-139 */
+    *length_x = mine;
+    sph_tunable *t = &params->tunable_params;
+    t->node_start_x = fluid_global->min_x + ((number_to_left - 1) * spacing);       /* :142-143 */
+    t->node_end_x = t->node_start_x + (mine * spacing);
+    if (rank == 0) t->node_start_x = boundary_global->min_x;                        /* :145-148 */
+    if (rank == nprocs - 1) t->node_end_x = boundary_global->max_x;
+    const int num_y = (int)floor((fluid_global->max_y - fluid_global->min_y) / spacing);   /* :153-157 */
+    params->number_fluid_particles_global = total_x * num_y;
+}
+
+void initParticles(fluid_particle **pointers, fluid_particle *particles, AABB_t *water, int start_x,
+                   int number_particles_x, edge_t *edges, int max_fluid_particles_local, float spacing, param *params)
+{
+    constructFluidVolume(pointers, particles, water, start_x, number_particles_x, edges, spacing, params);
+    for (int i = params->number_fluid_particles_local; i < max_fluid_particles_local; i++) pointers[i] = NULL;   /* fluid.c:758-759 */
+    for (int i = 0; i < params->number_fluid_particles_local; i++) {                /* :762-767 */
+        pointers[i]->a_x = 0.0f; pointers[i]->a_y = 0.0f;
+        pointers[i]->v_x = 0.0f; pointers[i]->v_y = 0.0f;
+    }
+}
 
 /* ------------------------------------------------------------------ per-particle helpers (host) */
 
