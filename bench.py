@@ -222,7 +222,7 @@ def main_ours(args):
             sim = SingleGpu(sph_b200, prob, t, stream, args)
         else:
             from sph_b200.slab import SlabRunner
-            sim = SlabRunner(prob, t, rank, world, stream, capacity_factor=2.0)
+            sim = SlabRunner(prob, t, rank, world, stream, capacity_factor=2.0, balance_policy=args.balance)
         mark("created")
         sim.init_lattice()
         mark("lattice")
@@ -312,6 +312,8 @@ def main_ours(args):
                 "stage_ms": stage_ms,
                 "step_hbm_frac": step_gbs / peak,
                 "parallelism": f"slab{world}",
+                "edge_policy": ("particle count, dead band 1/15 (renderer.c:427-477)" if args.balance == "count" else
+                                "work estimate per slab (sph_copy_load), dead band 1/40 -- NOT the reference's policy") if world > 1 else None,
                 "per_slab_[n_local,n_ghost,neighbours,gather_us,sort_us]": per_rank,
             },
             "roofline": {"bound": "hbm", "kernel": sim.kernel_name(dom), "achieved": achieved, "peak": peak,
@@ -427,6 +429,8 @@ def main():
     ap.add_argument("--cpu-warmup", type=int, default=300, help="untimed steps of the cpu_baseline sample (bounded: the "
                     "reference arm, --impl reference, runs the full pre-roll)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--balance", default="count", choices=["count", "cost"],
+                    help="slab edge policy at N > 1: the reference's particle counts (default) or the optional work estimate")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -130,6 +130,12 @@ int sph_get_status(sph_ctx *ctx, sph_status *out);
 /* Stream-ordered copy of the local particle count (one int) to DEVICE memory, without synchronising:
  * what a multi-rank driver all-gathers once per frame for the edge balancer (renderer.c:280,290). */
 int sph_copy_n_local(sph_ctx *ctx, void *device_dst);
+/* Same, two ints: {local particle count, work estimate of the last completed step}.  The estimate is the
+ * sum over resident entries (ghosts included: their density is computed too) of 14 + neighbours, formed
+ * by the density kernel; it is the input of the OPTIONAL cost-based edge policy (sph_host_balance_ex fed
+ * with costs instead of counts).  Results do not depend on where the edges are, so the
+ * policy changes the schedule only. */
+int sph_copy_load(sph_ctx *ctx, void *device_dst);
 
 /* ---- parameters ---- */
 /* Full tunable block, as the render rank scatters it (fluid.c:293-294). Stream-ordered. */

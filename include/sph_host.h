@@ -41,6 +41,9 @@ int sph_host_lattice(float water_min_x, float water_min_y, float water_max_y, fl
  * uses consistently on both sides of the ratio (the reference passes coordinate counts,
  * renderer.c:280,290). */
 void sph_host_balance(sph_tunable *master, int nactive, const int *counts, int total);
+/* The same edge arithmetic with the dead band as a parameter (even / band_divisor; the reference's is 15):
+ * for callers that balance on a work estimate (sph_copy_load) and want it tighter than +-6.7 %. */
+void sph_host_balance_ex(sph_tunable *master, int nactive, const int *counts, int total, float band_divisor);
 
 /* The render rank's idle "autopilot" for the mover (renderer.c:513-531): per frame gl_x += 0.01 * dir,
  * direction flips outside [-1, 1], gl_y = sinf(3.14 * 5 * gl_x) / 10 - 0.6, then opengl_to_sim

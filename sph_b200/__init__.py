@@ -60,7 +60,7 @@ C_ABI_SYMBOLS = (
     "sph_set_params", "sph_queue_params", "sph_set_edges", "sph_upload", "sph_download",
     "sph_advect", "sph_sort", "sph_density", "sph_relax", "sph_step", "sph_exchange_buffers",
     "sph_set_neighbors", "sph_get_cells", "sph_get_pairs", "sph_get_forward_counts",
-    "sph_pack_coords", "sph_launch_count", "sph_run_frame", "sph_p2p_local_handle", "sph_p2p_connect", "sph_copy_n_local", "sph_init_lattice",
+    "sph_pack_coords", "sph_launch_count", "sph_run_frame", "sph_p2p_local_handle", "sph_p2p_connect", "sph_copy_n_local", "sph_copy_load", "sph_init_lattice",
 )
 
 _lib = None
@@ -101,6 +101,7 @@ def lib():
         L.sph_run_frame.argtypes = [C.c_void_p, C.POINTER(Tunable), C.c_int, C.c_void_p, C.c_int]
         L.sph_init_lattice.argtypes = [C.c_void_p] + [C.c_float] * 4 + [C.c_int] * 3
         L.sph_copy_n_local.argtypes = [C.c_void_p, C.c_void_p]
+        L.sph_copy_load.argtypes = [C.c_void_p, C.c_void_p]
         L.sph_p2p_local_handle.argtypes = [C.c_void_p, C.c_void_p]
         L.sph_p2p_connect.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.sph_exchange_buffers.argtypes = [C.c_void_p, C.c_int] + [C.POINTER(C.c_void_p)] * 4 + [C.POINTER(C.c_size_t)]
@@ -200,6 +201,10 @@ class Context:
     def copy_n_local(self, device_ptr):
         self._ck(self.L.sph_copy_n_local(self.h, device_ptr), "sph_copy_n_local")
 
+    def copy_load(self, device_ptr):
+        """{n_local, work estimate} as two ints into device memory, stream-ordered (sph_copy_load)."""
+        self._ck(self.L.sph_copy_load(self.h, device_ptr), "sph_copy_load")
+
     def p2p_handle(self):
         """64-byte cudaIpc handle of this rank's exchange block."""
         buf = C.create_string_buffer(64)
@@ -251,7 +256,7 @@ class Context:
 # C host layer (include/sph_host.h): start-up geometry, parameter model, slab load balancer
 # ------------------------------------------------------------------------------------------------
 HOST_SYMBOLS = ("sph_host_mover_autopilot", "sph_host_spacing", "sph_host_default_params", "sph_host_preset", "sph_host_partition",
-                "sph_host_lattice", "sph_host_balance", "sph_host_remove_partition", "sph_host_add_partition")
+                "sph_host_lattice", "sph_host_balance", "sph_host_balance_ex", "sph_host_remove_partition", "sph_host_add_partition")
 
 
 def _host():
@@ -313,15 +318,17 @@ def _edge_blocks(edges, h):
     return m
 
 
-def balance(edges, counts, h, nactive=None):
+def balance(edges, counts, h, nactive=None, band_divisor=15.0):
     """check_partition_left (renderer.c:427-477) on a list of (start_x, end_x); returns the new list.
-    Only the first `nactive` slabs take part (render_state->num_compute_procs_active)."""
+    Only the first `nactive` slabs take part (render_state->num_compute_procs_active).  `band_divisor`:
+    dead band = even / band_divisor (the reference's 15 unless the caller balances on a work estimate)."""
     L = _host()
     n = len(edges)
     nactive = n if nactive is None else nactive
     m = _edge_blocks(edges, h)
     c = np.asarray(counts, "i4")
-    L.sph_host_balance(m, nactive, _p(c), int(c.sum()))
+    L.sph_host_balance_ex.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_float]
+    L.sph_host_balance_ex(m, nactive, _p(c), int(c.sum()), float(band_divisor))
     return [(float(m[r].node_start_x), float(m[r].node_end_x)) for r in range(n)]
 
 

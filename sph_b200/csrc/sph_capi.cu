@@ -571,6 +571,14 @@ extern "C" int sph_copy_n_local(sph_ctx *ctx, void *device_dst)
     return SPH_OK;
 }
 
+extern "C" int sph_copy_load(sph_ctx *ctx, void *device_dst)
+{
+    if (!ctx || !device_dst) return SPH_ERR_ARG;
+    CK(cudaMemcpyAsync(device_dst, ctx->counters + CN_NLOCAL, sizeof(int), cudaMemcpyDeviceToDevice, ctx->stream));
+    CK(cudaMemcpyAsync((int *)device_dst + 1, ctx->counters + CN_COST, sizeof(int), cudaMemcpyDeviceToDevice, ctx->stream));
+    return SPH_OK;
+}
+
 extern "C" int sph_get_status(sph_ctx *ctx, sph_status *out)
 {
     if (!ctx || !out) return SPH_ERR_ARG;

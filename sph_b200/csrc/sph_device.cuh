@@ -54,8 +54,14 @@ enum {
     CN_STEP,            // completed steps (message sequence numbers and buffer parity)
     CN_PUB,             // blocks that finished packing (last one publishes the message)
     CN_TIMEOUT_MSG,     // neighbour messages that never arrived (peer-memory waits that timed out)
+    CN_COST,            // work estimate of the last step: sum over resident entries of (SPH_COST_BASE + neighbours)
     CN_COUNT = 24
 };
+
+// Work estimate of a slab for the optional cost-based edge policy (sph_copy_load): the three gathers cost
+// a fixed part per entry plus a part per neighbour; 1 M particles took 113 us + 8.2 us per mean neighbour
+// over the dam-break's states, i.e. about 14 neighbour-equivalents per entry.
+#define SPH_COST_BASE 14
 
 // neighbour message: 16-byte header {n_migrants, n_halo, 0, 0} then SoA sections sized by msg_cap
 __host__ __device__ inline size_t msg_bytes_full(int m) { return 16 + (size_t)m * 32; }

@@ -201,7 +201,7 @@ k_advect(const DevParams *__restrict__ Pp, int *__restrict__ counters,
     const float hdt = 0.5f * dt;
     const float h_recip = __fdiv_rn(1.0f, P.h);
     const float h2 = __fmul_rn(P.h, P.h);
-    if (blockIdx.x == 0 && threadIdx.x == 0) counters[CN_MAX_BUCKET] = 0;
+    if (blockIdx.x == 0 && threadIdx.x == 0) { counters[CN_MAX_BUCKET] = 0; counters[CN_COST] = 0; }
 
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const uint32_t u = uid[i];
@@ -585,6 +585,7 @@ k_density(const DevParams *__restrict__ Pp, int *__restrict__ counters,
     const int n = counters[CN_NTOT];
     const float h_recip = __fdiv_rn(1.0f, P.h);
     const float h2 = __fmul_rn(P.h, P.h);
+    int cost = 0;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const float2 p = pos[i];
         float d = 0.0f, dn = 0.0f;
@@ -630,7 +631,11 @@ k_density(const DevParams *__restrict__ Pp, int *__restrict__ counters,
         // a forward list cannot exceed the full neighbour count: cheap, conservative detection
         // of the reference's 400-entry cap (hash.c:188,223)
         if (nn > 400) atomicAdd(&counters[CN_NEIGH_OVER], 1);
+        cost += SPH_COST_BASE + nn;
     }
+    // work estimate of this slab (one atomic per warp per launch): input of the cost-based edge policy
+    cost = __reduce_add_sync(0xffffffffu, cost);
+    if ((threadIdx.x & 31) == 0 && cost) atomicAdd(&counters[CN_COST], cost);
 }
 
 // -------------------------------------------------------------------------------------------

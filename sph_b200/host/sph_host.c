@@ -106,9 +106,14 @@ static void shift_edge(sph_tunable *m, int left, float delta)
 
 void sph_host_balance(sph_tunable *m, int nactive, const int *counts, int total)
 {
+    sph_host_balance_ex(m, nactive, counts, total, 15.0f);
+}
+
+void sph_host_balance_ex(sph_tunable *m, int nactive, const int *counts, int total, float band_divisor)
+{
     /* renderer.c:433-440 */
     const int even = total / nactive;
-    const int band = (int)(even / 15.0f);
+    const int band = (int)(even / band_divisor);
     const float h = m[0].smoothing_radius;
     const float dx = (float)(h * 0.125);
     /* renderer.c:444-458: right to left, each slab looks at its own left edge */

@@ -15,6 +15,12 @@ which replaces transferOOBParticles + 2 x start/finishHaloExchange + 2 x hash_ha
 reference's MPI_Scatterv lands, fluid.c:293-294) all ranks share their particle counts and run the
 reference's edge balancer (renderer.c:427-477) on identical inputs, so every rank derives the same
 new edges without a coordinator.
+
+balance_policy="cost" (optional, not the reference's): the same edge arithmetic fed with a work estimate per
+slab (sum over resident entries of 14 + neighbours, formed by the density kernel, sph_copy_load) and a
+tighter dead band.  In a dam-break the cost per particle follows the local density, which differs from slab
+to slab while the reference equalises particle COUNTS; since the gather gives bit-identical results for any
+decomposition, only the schedule changes (tests/test_slab_gloo.py).
 """
 import time
 
@@ -31,12 +37,15 @@ class _CudaBytes:
 class SlabRunner:
     def __init__(self, prob, tunable, rank, world, stream=None, capacity_factor=2.0, backend=None,
                  msg_capacity=None, steps_per_frame=4, balance=True, group=None, transport="p2p",
-                 async_counts=True):
+                 async_counts=True, balance_policy="count", cost_band_divisor=40.0):
         import torch
         import torch.distributed as dist
         self.torch, self.dist = torch, dist
         self.prob, self.rank, self.world, self.group = prob, rank, world, group
         self.steps_per_frame, self.do_balance = steps_per_frame, balance
+        assert balance_policy in ("count", "cost")
+        self.balance_policy, self.cost_band_divisor = balance_policy, cost_band_divisor
+        self.costs = None
         self.sub_step = 0
         self.n_active = world            # slabs taking part (render_state->num_compute_procs_active)
         self.async_counts = async_counts
@@ -99,14 +108,25 @@ class SlabRunner:
             for r in dist.batch_isend_irecv(ops):
                 r.wait()
 
+    def _load_now(self):
+        """(local count, work estimate) of this slab, read synchronously (tests, non-CUDA backends)."""
+        st = self.ctx.status()
+        if self.cuda:
+            buf = self.torch.zeros(2, dtype=self.torch.int32, device="cuda")
+            self.ctx.copy_load(buf.data_ptr())
+            return [int(v) for v in buf.tolist()]
+        from .csrc_constants import COST_BASE
+        return [st.n_local, COST_BASE * (st.n_local + st.n_halo) + 2 * len(self.ctx.pairs())]
+
     def gather_counts(self):
+        """-> (counts, costs) of all slabs"""
         torch, dist = self.torch, self.dist
-        n = self.ctx.status().n_local
         dev = "cuda" if self.cuda else "cpu"
-        mine = torch.tensor([n], dtype=torch.int32, device=dev)
-        out = [torch.zeros(1, dtype=torch.int32, device=dev) for _ in range(self.world)]
+        mine = torch.tensor(self._load_now(), dtype=torch.int32, device=dev)
+        out = [torch.zeros(2, dtype=torch.int32, device=dev) for _ in range(self.world)]
         dist.all_gather(out, mine, group=self.group)
-        return [int(x.item()) for x in out]
+        vals = [[int(v) for v in x.tolist()] for x in out]
+        return [v[0] for v in vals], [v[1] for v in vals]
 
     def sample_counts_async(self):
         """End of a frame: all-gather the slab populations WITHOUT stalling the host.  The result is used
@@ -114,11 +134,11 @@ class SlabRunner:
         the coordinate messages of the previous frame (renderer.c:268-290)."""
         torch, dist = self.torch, self.dist
         if not hasattr(self, "_cnt_mine"):
-            self._cnt_mine = torch.zeros(1, dtype=torch.int32, device="cuda")
-            self._cnt_all = torch.zeros(self.world, dtype=torch.int32, device="cuda")
-            self._cnt_host = torch.zeros(self.world, dtype=torch.int32).pin_memory()
+            self._cnt_mine = torch.zeros(2, dtype=torch.int32, device="cuda")
+            self._cnt_all = torch.zeros(2 * self.world, dtype=torch.int32, device="cuda")
+            self._cnt_host = torch.zeros(2 * self.world, dtype=torch.int32).pin_memory()
             self._cnt_event = torch.cuda.Event()
-        self.ctx.copy_n_local(self._cnt_mine.data_ptr())
+        self.ctx.copy_load(self._cnt_mine.data_ptr())
         dist.all_gather_into_tensor(self._cnt_all, self._cnt_mine, group=self.group)
         self._cnt_host.copy_(self._cnt_all, non_blocking=True)
         self._cnt_event.record(self.stream)
@@ -132,12 +152,18 @@ class SlabRunner:
             if not getattr(self, "_cnt_pending", False):
                 return                                  # first frame: nothing sampled yet
             self._cnt_event.synchronize()               # recorded a frame ago: already complete
-            counts = [int(c) for c in self._cnt_host.tolist()]
+            both = [int(c) for c in self._cnt_host.tolist()]
+            counts, costs = both[0::2], both[1::2]
         else:
-            counts = self.gather_counts()
-        self.counts = counts
-        # the reference feeds coordinate counts (2 per particle) on both sides of the ratio (renderer.c:280,290)
-        self.edges = sph_b200.balance(self.edges, [2 * c for c in counts], self.prob["h"], self.n_active)
+            counts, costs = self.gather_counts()
+        self.counts, self.costs = counts, costs
+        if self.balance_policy == "cost":
+            # same edge arithmetic, fed with the work estimate (scaled to stay far from int overflow)
+            self.edges = sph_b200.balance(self.edges, [c >> 4 for c in costs], self.prob["h"], self.n_active,
+                                          band_divisor=self.cost_band_divisor)
+        else:
+            # the reference feeds coordinate counts (2 per particle) on both sides of the ratio (renderer.c:280,290)
+            self.edges = sph_b200.balance(self.edges, [2 * c for c in counts], self.prob["h"], self.n_active)
         self._queue_edges()
 
     def _queue_edges(self):

@@ -16,7 +16,8 @@ def main():
     from sph_b200.slab import SlabRunner
 
     out, n_req, steps, balance = sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4])
-    block = len(sys.argv) > 5 and sys.argv[5] == "block"
+    block = len(sys.argv) > 5 and sys.argv[5] in ("block", "block_cost")
+    policy = "cost" if len(sys.argv) > 5 and sys.argv[5] == "block_cost" else "count"
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     dist.init_process_group("gloo", rank=rank, world_size=world)
     if block:   # dam-break block in the left half, mover sphere straddling a slab edge inside the water
@@ -30,7 +31,7 @@ def main():
     def backend(tw, th, h, cap, msg, r, w):
         return GatherOracle(tw, th, h, cap, msg, r, w)
 
-    sim = SlabRunner(prob, t, rank, world, backend=backend, balance=bool(balance))
+    sim = SlabRunner(prob, t, rank, world, backend=backend, balance=bool(balance), balance_policy=policy)
     sim.init_lattice()
     history = []
     elastic = len(sys.argv) > 5 and sys.argv[5] == "elastic"
@@ -47,7 +48,8 @@ def main():
     a, uid = sim.ctx.download()
     st = sim.ctx.status()
     np.savez(f"{out}.rank{rank}.npz", state=a, uid=uid, history=np.array(history, "f8"),
-             overflow=np.array([st.capacity_overflow, st.msg_overflow]), edges=np.array(sim.edges, "f8"))
+             overflow=np.array([st.capacity_overflow, st.msg_overflow]), edges=np.array(sim.edges, "f8"),
+             costs=np.array(sim.costs if sim.costs is not None else [], "f8"))
     dist.barrier()
     dist.destroy_process_group()
 

@@ -40,3 +40,10 @@ def test_sass_is_sm100a(built_lib):
     import subprocess
     out = subprocess.run(["cuobjdump", "-lelf", built_lib], capture_output=True, text=True).stdout
     assert "sm_100a" in out
+
+
+def test_python_constants_match_the_device_header():
+    import re
+    from sph_b200.csrc_constants import COST_BASE
+    hdr = open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "sph_b200", "csrc", "sph_device.cuh")).read()
+    assert int(re.search(r"#define SPH_COST_BASE (\d+)", hdr).group(1)) == COST_BASE
