@@ -255,6 +255,11 @@ class GatherOracle:
     def set_params(self, t): self.L.orc_g_set_params(self.h, C.byref(t))
     def queue_params(self, t): self.L.orc_g_queue_params(self.h, C.byref(t))
     def set_edges(self, s, e): self.L.orc_g_set_edges(self.h, s, e)
+
+    def set_viscosity_stabilisation(self, gamma):
+        """Proposal (off by default): symmetric damping of the viscosity gather for stiff presets."""
+        self.L.orc_g_set_viscosity_stabilisation.argtypes = [C.c_void_p, C.c_float]
+        self.L.orc_g_set_viscosity_stabilisation(self.h, float(gamma))
     def set_neighbors(self, l, r): self.L.orc_g_set_neighbors(self.h, int(l), int(r))
 
     def upload(self, aos, uid=None):

@@ -387,6 +387,8 @@ struct orc_g {
     float *tx, *ty, *tqx, *tqy; uint32_t *tuid; int *tkey;
     int n_src;
     float *dens, *densn;
+    float *coupling;             /* per entry: sum of its pairs' viscosity coefficients (stabilised mode only) */
+    float visc_gamma;            /* 0 = the plain Jacobi gather; > 0 = stabilised, see orc_g_set_viscosity_stabilisation */
     int *cell_start;
     int stage;
     unsigned char *send[2], *recv[2];   /* [0]=left, [1]=right */
@@ -416,6 +418,7 @@ orc_g *orc_g_create(const sph_config *cfg)
     for (unsigned i = 0; i < sizeof f / sizeof f[0]; i++) *f[i] = (float *)calloc(g->cap, sizeof(float));
     g->auid = (uint32_t *)calloc(g->cap, 4); g->tuid = (uint32_t *)calloc(g->cap, 4);
     g->tkey = (int *)calloc(g->cap, sizeof(int));
+    g->coupling = (float *)calloc(g->cap, sizeof(float));
     g->sort_rows = g->size_y * DIV;
     g->cell_start = (int *)calloc((size_t)g->size_x * g->size_y * DIV * DIV + 1, sizeof(int));
     g->msg_bytes = msg_bytes_for(g->msg_cap);
@@ -435,7 +438,7 @@ void orc_g_destroy(orc_g *g)
     if (!g) return;
     free(g->ax); free(g->ay); free(g->aqx); free(g->aqy); free(g->auid);
     free(g->tx); free(g->ty); free(g->tqx); free(g->tqy); free(g->tuid); free(g->tkey);
-    free(g->dens); free(g->densn); free(g->cell_start);
+    free(g->dens); free(g->densn); free(g->cell_start); free(g->coupling);
     for (int s = 0; s < 2; s++) { free(g->send[s]); free(g->recv[s]); }
     free(g);
 }
@@ -580,6 +583,46 @@ static void g_pack_halo0(orc_g *g, int side, float x, float y, uint32_t uid)
     msg_halo_uid(g->send[side], g->msg_cap)[k] = uid;
 }
 
+/* Stabilised viscosity gather (PROPOSAL, off by default; the CUDA path does not implement it yet).
+ *
+ * The reference applies the viscosity impulses pair by pair IN PLACE (fluid.c:442-472): every pair sees the
+ * velocities the pairs before it left behind, which damps a pair's approach speed by the factor
+ * 1 - dt (1-q)(sigma + beta u) and never overshoots.  The plain gather sums all of a particle's impulses from
+ * FROZEN velocities; with C_i = sum_j dt (1-q_ij)(sigma + beta u_ij) over its approaching pairs, the particle's
+ * velocity changes by about C_i / 2 times its approach speed, and for C_i >> 1 that overshoots and feeds
+ * itself: with the "goo" preset (sigma 100, beta 10, controls.c:359-371: dt sigma = 0.83 per pair) the fluid
+ * never settles.  Here every pair's impulse is scaled by
+ *     s_ij = 1 / max(1, gamma * max(C_i, C_j)),
+ * which is symmetric in (i, j) -- momentum is still exchanged pairwise -- and equal to 1 wherever the gather
+ * was stable anyway (the default fluid: C_i ~ 0.3), so those results do not change by a bit.
+ * gamma = 0.5 reproduced the reference's long-run statistics for all four presets within the reference's
+ * own sensitivity to the particle order. */
+void orc_g_set_viscosity_stabilisation(orc_g *g, float gamma) { g->visc_gamma = gamma; }
+
+static void g_viscosity_coupling(orc_g *g)
+{
+    const sph_tunable *t = &g->t;
+    float dt = t->time_step, gdt = (-t->g) * dt;
+    float h = t->smoothing_radius, h_recip = 1.0f / h, h2 = h * h;
+    float sigma = t->sigma, beta = t->beta;
+    for (int i = 0; i < g->n_tot; i++) {
+        float px = g->ax[i], py = g->ay[i];
+        float vix = g->aqx[i], viy = g->aqy[i] + gdt;
+        float c = 0.0f;
+        int wxi, gy; g_cell_of(g, i, &wxi, &gy);
+        FOR_EACH_CANDIDATE(g, wxi, gy, j,
+            if (j == i) continue;
+            float dx = g->ax[j] - px; float dy = g->ay[j] - py;
+            float r2 = dx * dx + dy * dy;
+            if (r2 > h2) continue;
+            float r = sqrtf(r2);
+            float u = ((vix - g->aqx[j]) * dx + (viy - (g->aqy[j] + gdt)) * dy) * (1.0f / r);
+            if (u > 0.0f) c += dt * (1 - r * h_recip) * (sigma + beta * u);
+        )
+        g->coupling[i] = c;
+    }
+}
+
 /* gravity + viscosity gather + predict + boundary + migration/halo classification */
 void orc_g_advect(orc_g *g)
 {
@@ -590,6 +633,8 @@ void orc_g_advect(orc_g *g)
     g->n_src = g->n_tot;
     for (int s = 0; s < 2; s++) { int *hd = msg_hdr(g->send[s]); hd[0] = hd[1] = hd[2] = hd[3] = 0; }
     g->st.migrated_left = g->st.migrated_right = 0;
+    const float gamma = g->visc_gamma;
+    if (gamma > 0.0f) g_viscosity_coupling(g);
 
     for (int i = 0; i < g->n_tot; i++) {
         g->tuid[i] = g->auid[i];
@@ -611,6 +656,10 @@ void orc_g_advect(orc_g *g)
             float u = ((vix - vjx) * dx + (viy - vjy) * dy) * r_recip;
             if (u > 0.0f) {                                  /* fluid.c:451-462 */
                 float imp = dt * (1 - ratio) * (sigma * u + beta * u * u);
+                if (gamma > 0.0f) {
+                    float cmax = g->coupling[i] > g->coupling[j] ? g->coupling[i] : g->coupling[j];
+                    if (gamma * cmax > 1.0f) imp = imp / (gamma * cmax);
+                }
                 float ix = imp * dx * r_recip; float iy = imp * dy * r_recip;
                 orc_check_velocity(&ix, &iy);
                 vx -= ix * 0.5f; vy -= iy * 0.5f;

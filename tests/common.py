@@ -22,6 +22,22 @@ DENSITY_REL = 1e-5
 STAT_REL = 0.02         # mean density, max density, mean height
 STAT_REL_MAXDENS = 0.05
 KE_REL = 0.25           # kinetic energy per particle
+# ... but never tighter than the REFERENCE's own sensitivity to the (arbitrary) order of its particle array:
+# the same lattice run through the sequential oracle as is / reversed / shuffled moves these statistics by the
+# amounts recorded in golden/order_sensitivity.json (make_order_sensitivity.py), e.g. the mean height of the
+# "goo" heap by 14 % and the kinetic energy of the default fluid by 32 %.  An implementation that sums the
+# pairs in yet another order gets 1.5 x that spread where it exceeds the figures above.
+ORDER_SPREAD_FACTOR = 1.5
+
+
+def longrun_tolerances(name):
+    """-> dict(mean_density, max_density, mean_height, ke_rel, ke_abs) for check_long_run_statistics"""
+    import json
+    z = json.load(open(os.path.join(GOLDEN, "order_sensitivity.json")))[name]
+    d = [ORDER_SPREAD_FACTOR * v for v in z["max_rel_deviation"]]
+    return {"mean_density": max(STAT_REL, d[0]), "max_density": max(STAT_REL_MAXDENS, d[1]),
+            "mean_height": max(STAT_REL, d[2]), "ke_rel": max(KE_REL, min(d[3], 1.0)),
+            "ke_abs": max(1e-3, ORDER_SPREAD_FACTOR * z["max_abs_ke"] if d[3] > 1.0 else 1e-3)}
 
 
 def load_golden(name):
