@@ -52,6 +52,24 @@ def measured_traffic(kernel, n_particles):
     return e["dram_bytes_per_launch"]
 
 
+def profiled_limiter(kernel, source="r1_branchfree_full.csv"):
+    """What actually bounds `kernel` according to the last `ncu --set full` capture summarised under profiles/
+    (NOT measured in this run): issue-slot utilisation, active lanes per instruction and DRAM throughput.  The
+    HBM roofline fraction is small because these gathers are instruction-issue bound."""
+    import csv
+    p = os.path.join(ROOT, "profiles", source)
+    try:
+        rows = list(csv.reader(open(p)))
+        col = rows[0].index(kernel.split("+")[0])
+        get = lambda m: float(next(r[col] for r in rows if r[0] == m))
+        return {"issue_active_pct": get("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+                "active_lanes_per_instruction": get("smsp__thread_inst_executed_per_inst_executed.ratio"),
+                "dram_pct_of_peak": get("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"),
+                "source": f"profiles/{source} (ncu capture of this build's kernels, not this run)"}
+    except (OSError, ValueError, StopIteration):
+        return None
+
+
 def problem_dims(n, water_frac):
     import numpy as np
     tank_w = 15.0 * float(np.sqrt(n / (1500.0 * water_frac)))
@@ -319,7 +337,8 @@ def main_ours(args):
             "roofline": {"bound": "hbm", "kernel": sim.kernel_name(dom), "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak,
                          "traffic": measured_traffic(sim.kernel_name(dom), n_per_launch), "peak_source": peak_kind,
-                         "algorithmic_bytes_per_particle": ALG_BYTES[dom_key]},
+                         "algorithmic_bytes_per_particle": ALG_BYTES[dom_key],
+                         "profiled_limiter": profiled_limiter(sim.kernel_name(dom))},
             "clocks": clocks,
             "e2e": {"value": n_global * e2e["steps"] / e2e["seconds"], "unit": "particle-steps/s",
                     "h2d_bytes_per_step": e2e["h2d_per_step"], "d2h_bytes_per_step": e2e["d2h_per_step"],
