@@ -18,6 +18,7 @@ def main():
     out, n_req, steps, balance = sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4])
     block = len(sys.argv) > 5 and sys.argv[5] in ("block", "block_cost")
     policy = "cost" if len(sys.argv) > 5 and sys.argv[5] == "block_cost" else "count"
+    goo = len(sys.argv) > 5 and sys.argv[5] == "goo_stabilised"
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     dist.init_process_group("gloo", rank=rank, world_size=world)
     if block:   # dam-break block in the left half, mover sphere straddling a slab edge inside the water
@@ -26,10 +27,13 @@ def main():
         t.mover_center_x = 0.4 * prob["tank_w"]
     else:
         prob = make_problem(n_req, nranks=world)
-        t = default_tunable(prob["h"], prob["tank_w"], prob["tank_h"])
+        t = default_tunable(prob["h"], prob["tank_w"], prob["tank_h"], preset="y" if goo else "x")
 
     def backend(tw, th, h, cap, msg, r, w):
-        return GatherOracle(tw, th, h, cap, msg, r, w)
+        g = GatherOracle(tw, th, h, cap, msg, r, w)
+        if goo:
+            g.set_viscosity_stabilisation(0.5)      # the proposal of DESIGN.md 5b (oracle only)
+        return g
 
     sim = SlabRunner(prob, t, rank, world, backend=backend, balance=bool(balance), balance_policy=policy)
     sim.init_lattice()

@@ -107,6 +107,27 @@ def test_cost_based_edge_policy_changes_the_schedule_not_the_result(tmp_path, bu
     assert spread(by_cost) < spread(by_count), (spread(by_cost), spread(by_count))     # measured: 1.02 against 1.17
 
 
+def test_stabilised_viscosity_is_decomposition_independent(tmp_path, built_lib):
+    """The proposal of DESIGN.md 5b (gather oracle only): pair impulses scaled by 1 / max(1, gamma max(C_i, C_j)).
+    C_j of a ghost within h of the edge needs that ghost's whole neighbourhood WITH velocities, i.e. the 2h-wide
+    ghost layer of exchange 1 -- which is what travels.  Goo preset, 3 slabs with rebalancing: bit-identical
+    to the single slab."""
+    steps = 160
+    parts = run_world(tmp_path, 3, 1500, steps, True, "goo_stabilised")
+    state = np.concatenate([p["state"] for p in parts]); uid = np.concatenate([p["uid"] for p in parts])
+    assert np.array_equal(np.sort(uid), np.arange(1508))
+    assert all(int(p["overflow"].sum()) == 0 for p in parts)
+    prob = make_problem(1500)
+    a, u0 = lattice(prob)
+    t = default_tunable(prob["h"], prob["tank_w"], prob["tank_h"], preset="y")
+    g = GatherOracle(prob["tank_w"], prob["tank_h"], prob["h"], len(a) + 64)
+    g.set_params(t); g.set_viscosity_stabilisation(0.5); g.upload(a, u0); g.step(steps)
+    ref, _ = g.download()
+    order = np.argsort(uid)
+    for f in ("x", "y", "v_x", "v_y"):
+        assert np.array_equal(state[f][order].view("u4"), ref[f].view("u4")), f
+
+
 def test_partition_removed_and_added_back(tmp_path, built_lib):
     """Runtime partition control (controls.c:405-455): at step 43 the last of three slabs is parked outside the
     tank and must drain completely into its neighbour; at step 123 it is added back and refills.  No particle
