@@ -77,36 +77,40 @@ def lib():
         if not os.path.exists(LIB_PATH):
             raise SphError(f"{LIB_PATH} is missing: build it with `python -m sph_b200.build` "
                            "(nvcc, sm_100a). sph_b200 has no CPU path.")
-        L = C.CDLL(LIB_PATH)
-        L.sph_last_error.restype = C.c_char_p
-        L.sph_last_error.argtypes = [C.c_void_p]
-        L.sph_launch_count.restype = C.c_longlong
-        L.sph_launch_count.argtypes = [C.c_void_p]
-        L.sph_get_pairs.restype = C.c_longlong
-        L.sph_get_pairs.argtypes = [C.c_void_p, C.c_void_p, C.c_longlong]
-        L.sph_set_edges.argtypes = [C.c_void_p, C.c_float, C.c_float]
-        L.sph_create.argtypes = [C.POINTER(Config), C.POINTER(C.c_void_p)]
-        for name in ("sph_destroy", "sph_synchronize", "sph_advect", "sph_sort", "sph_density", "sph_relax"):
-            getattr(L, name).argtypes = [C.c_void_p]
-        L.sph_step.argtypes = [C.c_void_p, C.c_int]
-        L.sph_set_params.argtypes = [C.c_void_p, C.POINTER(Tunable)]
-        L.sph_queue_params.argtypes = [C.c_void_p, C.POINTER(Tunable)]
-        L.sph_get_status.argtypes = [C.c_void_p, C.POINTER(Status)]
-        L.sph_upload.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
-        L.sph_download.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
-        L.sph_set_neighbors.argtypes = [C.c_void_p, C.c_int, C.c_int]
-        L.sph_get_cells.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
-        L.sph_get_forward_counts.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
-        L.sph_pack_coords.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
-        L.sph_run_frame.argtypes = [C.c_void_p, C.POINTER(Tunable), C.c_int, C.c_void_p, C.c_int]
-        L.sph_init_lattice.argtypes = [C.c_void_p] + [C.c_float] * 4 + [C.c_int] * 3
-        L.sph_copy_n_local.argtypes = [C.c_void_p, C.c_void_p]
-        L.sph_copy_load.argtypes = [C.c_void_p, C.c_void_p]
-        L.sph_p2p_local_handle.argtypes = [C.c_void_p, C.c_void_p]
-        L.sph_p2p_connect.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
-        L.sph_exchange_buffers.argtypes = [C.c_void_p, C.c_int] + [C.POINTER(C.c_void_p)] * 4 + [C.POINTER(C.c_size_t)]
-        _lib = L
+        _lib = _bind(C.CDLL(LIB_PATH))
     return _lib
+
+
+def _bind(L):
+    """Declare the C-ABI signatures on a loaded library."""
+    L.sph_last_error.restype = C.c_char_p
+    L.sph_last_error.argtypes = [C.c_void_p]
+    L.sph_launch_count.restype = C.c_longlong
+    L.sph_launch_count.argtypes = [C.c_void_p]
+    L.sph_get_pairs.restype = C.c_longlong
+    L.sph_get_pairs.argtypes = [C.c_void_p, C.c_void_p, C.c_longlong]
+    L.sph_set_edges.argtypes = [C.c_void_p, C.c_float, C.c_float]
+    L.sph_create.argtypes = [C.POINTER(Config), C.POINTER(C.c_void_p)]
+    for name in ("sph_destroy", "sph_synchronize", "sph_advect", "sph_sort", "sph_density", "sph_relax"):
+        getattr(L, name).argtypes = [C.c_void_p]
+    L.sph_step.argtypes = [C.c_void_p, C.c_int]
+    L.sph_set_params.argtypes = [C.c_void_p, C.POINTER(Tunable)]
+    L.sph_queue_params.argtypes = [C.c_void_p, C.POINTER(Tunable)]
+    L.sph_get_status.argtypes = [C.c_void_p, C.POINTER(Status)]
+    L.sph_upload.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+    L.sph_download.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+    L.sph_set_neighbors.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    L.sph_get_cells.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+    L.sph_get_forward_counts.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+    L.sph_pack_coords.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    L.sph_run_frame.argtypes = [C.c_void_p, C.POINTER(Tunable), C.c_int, C.c_void_p, C.c_int]
+    L.sph_init_lattice.argtypes = [C.c_void_p] + [C.c_float] * 4 + [C.c_int] * 3
+    L.sph_copy_n_local.argtypes = [C.c_void_p, C.c_void_p]
+    L.sph_copy_load.argtypes = [C.c_void_p, C.c_void_p]
+    L.sph_p2p_local_handle.argtypes = [C.c_void_p, C.c_void_p]
+    L.sph_p2p_connect.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.sph_exchange_buffers.argtypes = [C.c_void_p, C.c_int] + [C.POINTER(C.c_void_p)] * 4 + [C.POINTER(C.c_size_t)]
+    return L
 
 
 def _p(a):

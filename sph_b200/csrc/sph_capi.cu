@@ -11,6 +11,13 @@
 #include <cstring>
 #include <vector>
 
+// every kernel launch of the library: SPH_THREADS threads per block, no dynamic shared memory
+#ifndef SPH_EMU
+#define SPH_LAUNCH(kernel, grid, stream) kernel<<<(grid), SPH_THREADS, 0, (stream)>>>
+#else       // tests/emu: this file compiled by g++ against a fake runtime (test infrastructure, see sph_device.cuh)
+#define SPH_LAUNCH(kernel, grid, stream) emu::make_launcher(kernel, (grid), SPH_THREADS, (stream))
+#endif
+
 enum { ST_READY = 0, ST_ADVECTED, ST_SORTED1, ST_DENSITY, ST_RELAXED };
 
 struct sph_ctx {
@@ -306,21 +313,21 @@ static int launch_sort(sph_ctx *ctx, int which, bool with_unpack = true)
     float2 *dq = which == 0 ? ctx->Q[1] : ctx->Q[0];
     uint32_t *du = which == 0 ? ctx->U[1] : ctx->U[0];
     if (ctx->cfg.nranks > 1 && with_unpack) {
-        k_unpack<<<ctx->unpack_grid, SPH_THREADS, 0, ctx->stream>>>(ctx->dp, ctx->counters, which, ctx->send[0], ctx->send[1],
+        SPH_LAUNCH(k_unpack, ctx->unpack_grid, ctx->stream)(ctx->dp, ctx->counters, which, ctx->send[0], ctx->send[1],
                                                              ctx->recv[0], ctx->recv[1],
                                                              sp, sq, su, ctx->cnt, ctx->t_key, ctx->t_slot);
         ctx->launches++;
     }
     // grids sized for the widest window (tile loops inside): a captured graph survives moving slab edges
     const int sgrid = std::max(1, std::min(ctx->scan_grid, 8 * 148));
-    k_scan_totals<<<sgrid, SPH_THREADS, 0, ctx->stream>>>(ctx->dp, ctx->counters, ctx->cnt, ctx->tile_total);
-    k_scan_apply<<<sgrid, SPH_THREADS, 0, ctx->stream>>>(ctx->dp, ctx->counters, ctx->cnt, ctx->cell_start, ctx->tile_total,
+    SPH_LAUNCH(k_scan_totals, sgrid, ctx->stream)(ctx->dp, ctx->counters, ctx->cnt, ctx->tile_total);
+    SPH_LAUNCH(k_scan_apply, sgrid, ctx->stream)(ctx->dp, ctx->counters, ctx->cnt, ctx->cell_start, ctx->tile_total,
                                                          ctx->cfg.nranks > 1 ? ctx->send[0] : nullptr,
                                                          ctx->cfg.nranks > 1 ? ctx->send[1] : nullptr,
                                                          (which == 1 && with_unpack) ? 1 : 0);
-    k_scatter<<<ctx->grid, SPH_THREADS, 0, ctx->stream>>>(ctx->counters, ctx->cell_start, ctx->t_key, ctx->t_slot, su,
+    SPH_LAUNCH(k_scatter, ctx->grid, ctx->stream)(ctx->counters, ctx->cell_start, ctx->t_key, ctx->t_slot, su,
                                                           ctx->ord_uid, ctx->ord_src, ctx->ord_key);
-    k_reorder<<<ctx->grid, SPH_THREADS, 0, ctx->stream>>>(ctx->dp, ctx->counters, ctx->cell_start, ctx->ord_key,
+    SPH_LAUNCH(k_reorder, ctx->grid, ctx->stream)(ctx->dp, ctx->counters, ctx->cell_start, ctx->ord_key,
                                                           ctx->ord_uid, ctx->ord_src, sp, sq, dp, dq, du);
     ctx->launches += 4;
     ctx->hp.gx0 = ctx->hp.gx0_new;     // the scan kernel did the same on the device
@@ -331,7 +338,7 @@ static int launch_sort(sph_ctx *ctx, int which, bool with_unpack = true)
 
 static int launch_advect(sph_ctx *ctx)
 {
-    k_advect<<<ctx->grid, SPH_THREADS, 0, ctx->stream>>>(ctx->dp, ctx->counters, ctx->P[0], ctx->Q[0], ctx->U[0],
+    SPH_LAUNCH(k_advect, ctx->grid, ctx->stream)(ctx->dp, ctx->counters, ctx->P[0], ctx->Q[0], ctx->U[0],
                                                          ctx->cell_start, ctx->P[1], ctx->cnt, ctx->t_key, ctx->t_slot,
                                                          ctx->send[0], ctx->send[1]);
     ctx->launches++;
@@ -341,7 +348,7 @@ static int launch_advect(sph_ctx *ctx)
 
 static int launch_density(sph_ctx *ctx)
 {
-    k_density<<<ctx->grid, SPH_THREADS, 0, ctx->stream>>>(ctx->dp, ctx->counters, ctx->P[2], ctx->cell_start, ctx->dens, ctx->nmask);
+    SPH_LAUNCH(k_density, ctx->grid, ctx->stream)(ctx->dp, ctx->counters, ctx->P[2], ctx->cell_start, ctx->dens, ctx->nmask);
     ctx->launches++;
     CK(cudaGetLastError());
     return SPH_OK;
@@ -349,7 +356,7 @@ static int launch_density(sph_ctx *ctx)
 
 static int launch_relax(sph_ctx *ctx)
 {
-    k_relax<<<ctx->grid, SPH_THREADS, 0, ctx->stream>>>(ctx->dp, ctx->counters, ctx->P[2], ctx->Q[1], ctx->U[1], ctx->dens,
+    SPH_LAUNCH(k_relax, ctx->grid, ctx->stream)(ctx->dp, ctx->counters, ctx->P[2], ctx->Q[1], ctx->U[1], ctx->dens,
                                                         ctx->cell_start, ctx->nmask, ctx->P[3], ctx->Q[2], ctx->cnt, ctx->t_key,
                                                         ctx->t_slot, ctx->send[0], ctx->send[1]);
     ctx->launches++;
@@ -467,7 +474,7 @@ static int ingest(sph_ctx *ctx, int n)
     for (int s = 0; s < 2; s++) CK(cudaMemsetAsync(ctx->send[s], 0, 16, ctx->stream));
     int rc = push_params(ctx);
     if (rc) return rc;
-    k_bin_upload<<<ctx->grid, SPH_THREADS, 0, ctx->stream>>>(ctx->dp, ctx->counters, ctx->P[3], ctx->cnt, ctx->t_key, ctx->t_slot);
+    SPH_LAUNCH(k_bin_upload, ctx->grid, ctx->stream)(ctx->dp, ctx->counters, ctx->P[3], ctx->cnt, ctx->t_key, ctx->t_slot);
     ctx->launches++;
     // no neighbour messages belong to an upload: skip the unpack kernel
     if ((rc = launch_sort(ctx, 1, false))) return rc;
@@ -503,7 +510,7 @@ extern "C" int sph_init_lattice(sph_ctx *ctx, float water_min_x, float water_min
     const int rows = (int)floor((water_max_y - water_min_y) / spacing);           // geometry.c:35
     const long long n = (long long)rows * ncols;
     if (n > ctx->cfg.capacity) { fail(ctx, SPH_ERR_CAPACITY, "sph_init_lattice: more particles than capacity"); return -SPH_ERR_CAPACITY; }
-    k_init_lattice<<<ctx->grid, SPH_THREADS, 0, ctx->stream>>>(water_min_x, water_min_y, spacing, start_col, ncols, rows,
+    SPH_LAUNCH(k_init_lattice, ctx->grid, ctx->stream)(water_min_x, water_min_y, spacing, start_col, ncols, rows,
                                                                total_cols, ctx->P[3], ctx->Q[2], ctx->U[1]);
     ctx->launches++;
     int rc = ingest(ctx, (int)n);
@@ -594,7 +601,7 @@ extern "C" int sph_get_status(sph_ctx *ctx, sph_status *out)
         int *dstat = ctx->counters + CN_SPARE0;          // two spare counters as scratch
         int hz[2] = {0, 0};
         CK(cudaMemcpyAsync(dstat, hz, sizeof hz, cudaMemcpyHostToDevice, ctx->stream));
-        k_bucket_stats<<<ctx->grid, SPH_THREADS, 0, ctx->stream>>>(ctx->dp, ctx->cell_start, dstat);
+        SPH_LAUNCH(k_bucket_stats, ctx->grid, ctx->stream)(ctx->dp, ctx->cell_start, dstat);
         ctx->launches++;
         CK(cudaMemcpyAsync(hz, dstat, sizeof hz, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
@@ -624,7 +631,7 @@ extern "C" int sph_pack_coords(sph_ctx *ctx, int16_t *xy, int cap)
     auto bail = [&](cudaError_t e) { snprintf(ctx->err, sizeof ctx->err, "pack_coords: %s", cudaGetErrorString(e)); return -SPH_ERR_CUDA; };
     cudaError_t e;
     if ((e = cudaMemsetAsync(ctx->counters + CN_COORDS, 0, sizeof(int), ctx->stream))) return bail(e);
-    k_pack_coords<<<ctx->grid, SPH_THREADS, 0, ctx->stream>>>(ctx->dp, ctx->counters, dpos, duid, ctx->coords, ctx->cfg.capacity);
+    SPH_LAUNCH(k_pack_coords, ctx->grid, ctx->stream)(ctx->dp, ctx->counters, dpos, duid, ctx->coords, ctx->cfg.capacity);
     ctx->launches++;
     int c[CN_COUNT];
     if ((e = cudaMemcpyAsync(c, ctx->counters, sizeof c, cudaMemcpyDeviceToHost, ctx->stream))) return bail(e);
@@ -660,7 +667,7 @@ extern "C" int sph_get_cells(sph_ctx *ctx, uint32_t *uid, uint32_t *cell, int ca
     if (read_counters(ctx, c)) return -SPH_ERR_CUDA;
     const int n = c[CN_NTOT];
     uint32_t *dcell = (uint32_t *)ctx->ord_uid;      // scratch: free between sorts
-    k_export_cells<<<ctx->grid, SPH_THREADS, 0, ctx->stream>>>(ctx->dp, ctx->counters, dpos, dcell);
+    SPH_LAUNCH(k_export_cells, ctx->grid, ctx->stream)(ctx->dp, ctx->counters, dpos, dcell);
     ctx->launches++;
     std::vector<uint32_t> hu(n), hc(n);
     if (n > 0) {
@@ -694,7 +701,7 @@ static long long export_pairs(sph_ctx *ctx, uint64_t *pairs, long long cap, uint
         if (count && cudaMalloc(&dfwd, (size_t)std::max(n, 1) * sizeof(int))) break;
         // count-only calls still need a non-null marker so the kernel counts pairs
         unsigned long long *pairs_arg = (pairs || !count) ? (dpairs ? dpairs : (unsigned long long *)dn) : nullptr;
-        k_export_pairs<<<ctx->grid, SPH_THREADS, 0, ctx->stream>>>(ctx->dp, ctx->counters, dpos, duid, ctx->cell_start,
+        SPH_LAUNCH(k_export_pairs, ctx->grid, ctx->stream)(ctx->dp, ctx->counters, dpos, duid, ctx->cell_start,
                                                                    pairs_arg, dpairs ? (unsigned long long)cap : 0ull, dn, dfwd);
         ctx->launches++;
         if (cudaStreamSynchronize(ctx->stream)) break;

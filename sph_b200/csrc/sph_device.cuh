@@ -87,6 +87,9 @@ __device__ __forceinline__ int *xchg_flag(unsigned long long base, int side, int
 {
     return (int *)(base + (size_t)(side * 2 + which) * 16);
 }
+// The only PTX in the library.  (SPH_EMU: tests/emu compiles this source for the host to exercise the kernel
+// and C-ABI logic without a GPU -- test infrastructure; the product is built by nvcc without it.)
+#ifndef SPH_EMU
 __device__ __forceinline__ int ld_acquire_sys(const int *p)
 {
     int v;
@@ -97,6 +100,27 @@ __device__ __forceinline__ void st_release_sys(int *p, int v)
 {
     asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+// bare MUFU.RSQ / MUFU.SQRT (relative error ~2^-22; rsqrt(0) = +inf, sqrt(0) = 0): rsqrtf() wraps the
+// instruction in a denormal rescue (4 more instructions per pair); squared distances below 1.2e-38 are
+// flushed and behave like coincident particles
+__device__ __forceinline__ float rsqrt_approx(float x)
+{
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float sqrt_approx(float x)
+{
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+#else
+static inline int ld_acquire_sys(const int *p) { return *(const volatile int *)p; }
+static inline void st_release_sys(int *p, int v) { *(volatile int *)p = v; }
+static inline float rsqrt_approx(float x) { return 1.0f / sqrtf(x); }
+static inline float sqrt_approx(float x) { return sqrtf(x); }
+#endif
 
 // hash_val (hash.c:35-47): IEEE fp32 divide, floor; kept as two coordinates
 __device__ __forceinline__ int cell_coord(float v, float cell_h) { return (int)floorf(__fdiv_rn(v, cell_h)); }

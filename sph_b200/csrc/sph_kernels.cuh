@@ -56,18 +56,8 @@ __device__ __forceinline__ int sph_mask_popc(sph_mask_t m) { return __popc(m); }
 // reference's 1.0f/r.
 __device__ __forceinline__ void r_and_recip(float r2, float &r, float &r_recip)
 {
-    // bare MUFU.RSQ: rsqrtf() wraps it in a denormal rescue (4 more instructions per pair); squared
-    // distances below 1.2e-38 are flushed and behave like coincident particles
-    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r_recip) : "f"(r2));
+    r_recip = rsqrt_approx(r2);
     r = r2 > 0.0f ? r2 * r_recip : 0.0f;
-}
-
-// r alone from one MUFU.SQRT (relative error ~2^-22, sqrt(0) = 0)
-__device__ __forceinline__ float sqrt_approx(float r2)
-{
-    float r;
-    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(r2));
-    return r;
 }
 
 // Candidate ranges of a particle: the columns gx-DIV..gx+DIV of the rows gy-DIV..gy+DIV.
@@ -223,8 +213,7 @@ k_advect(const DevParams *__restrict__ Pp, int *__restrict__ counters,
                 const float r2 = dist2(dx, dy);
                 const bool in = r2 <= h2;                               // list membership
                 const float2 vq = vel[j];                               // unconditional: cheaper than a predicated address
-                float rs;
-                asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rs) : "f"(r2));
+                const float rs = rsqrt_approx(r2);
                 // gravity is the same on both sides of the difference (fluid.c:398-412, :446-449)
                 const float u_in = ((v0.x - vq.x) * dx + (v0.y - vq.y) * dy) * rs;
                 // fluid.c:451-462; the particle itself and any coincident neighbour have r2 == 0, rs = inf,
@@ -706,8 +695,7 @@ k_relax(const DevParams *__restrict__ Pp, int *__restrict__ counters,
             // r and 1/r from one MUFU.RSQ (r2 > 1e-12: finite); the ratio < 1 gate as (1 - ratio)+,
             // branch-free: a listed neighbour has r2 <= h2, so the gate can only fail within rounding
             // of r == h, where the displacement vanishes anyway
-            float rs;
-            asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rs) : "f"(r2));
+            const float rs = rsqrt_approx(r2);
             const float w = fmaxf(fmaf(-r2 * rs, h_recip, 1.0f), 0.0f);
             const float s = fmaf(B, w, A) * w * rs;
             x = fmaf(-s, dx, x);

@@ -1,0 +1,172 @@
+// TEST INFRASTRUCTURE -- NOT PART OF THE PRODUCT.  See fake/cuda_runtime.h.
+// The fiber scheduler and the fake runtime API behind the kernel-source emulator.
+#include <cuda_runtime.h>
+
+#include <stdio.h>
+
+namespace emu {
+
+Fiber *cur = nullptr;
+Block blk;
+uint3 block_idx, block_dim, grid_dim;
+
+static const size_t kStack = 256 * 1024;
+static std::vector<Fiber> fibers;
+static std::vector<char *> stacks;
+static ucontext_t main_ctx;
+static const std::function<void()> *body_now = nullptr;
+static int last_error = cudaSuccess;
+
+void yield()
+{
+    Fiber *f = cur;
+    swapcontext(&f->ctx, &main_ctx);
+}
+
+static void trampoline()
+{
+    (*body_now)();
+    cur->done = true;
+    swapcontext(&cur->ctx, &main_ctx);
+}
+
+static void run_grid(int grid, int threads, const std::function<void()> &body)
+{
+    if (grid <= 0 || threads <= 0 || threads > 1024 || (threads & 31)) { last_error = cudaErrorInvalidValue; return; }
+    if ((int)fibers.size() < threads) {
+        fibers.resize(threads);
+        while ((int)stacks.size() < threads) stacks.push_back((char *)malloc(kStack));
+    }
+    body_now = &body;
+    grid_dim = uint3{(unsigned)grid, 1, 1};
+    block_dim = uint3{(unsigned)threads, 1, 1};
+    for (int b = 0; b < grid; b++) {
+        block_idx = uint3{(unsigned)b, 0, 0};
+        memset(&blk, 0, sizeof blk);
+        blk.nthreads = threads;
+        for (int t = 0; t < threads; t++) {
+            Fiber &f = fibers[t];
+            f.tid = uint3{(unsigned)t, 0, 0};
+            f.done = false;
+            getcontext(&f.ctx);
+            f.ctx.uc_stack.ss_sp = stacks[t];
+            f.ctx.uc_stack.ss_size = kStack;
+            f.ctx.uc_link = nullptr;
+            makecontext(&f.ctx, trampoline, 0);
+        }
+        int alive = threads;
+        long long rounds = 0;
+        while (alive > 0) {
+            alive = 0;
+            for (int t = 0; t < threads; t++) {
+                if (fibers[t].done) continue;
+                cur = &fibers[t];
+                swapcontext(&main_ctx, &cur->ctx);
+                alive += !fibers[t].done;
+            }
+            if (++rounds > 100000000ll) { fprintf(stderr, "emu: block %d never finished (barrier not reached by all threads?)\n", b); abort(); }
+        }
+    }
+    cur = nullptr;
+    body_now = nullptr;
+}
+
+}  // namespace emu
+
+struct emu_graph { std::vector<std::tuple<int, int, std::function<void()>>> nodes; };
+struct emu_stream { emu_graph *capturing; };
+
+static int g_devices = -1;
+
+static int device_count()
+{
+    if (g_devices < 0) {
+        const char *e = getenv("SPH_EMU_DEVICES");
+        g_devices = e ? atoi(e) : 1;
+    }
+    return g_devices;
+}
+
+void emu::launch_on_stream(cudaStream_t s, int grid, int threads, std::function<void()> body)
+{
+    if (s && s->capturing) { s->capturing->nodes.emplace_back(grid, threads, std::move(body)); return; }
+    run_grid(grid, threads, body);
+}
+
+const char *cudaGetErrorString(cudaError_t e)
+{
+    switch (e) {
+    case cudaSuccess: return "no error";
+    case cudaErrorInvalidValue: return "invalid value";
+    case cudaErrorNoDevice: return "no device";
+    case cudaErrorNotSupported: return "not supported by the emulator";
+    case cudaErrorStreamCaptureUnsupported: return "operation not permitted while capturing";
+    default: return "error";
+    }
+}
+cudaError_t cudaGetLastError() { int e = emu::last_error; emu::last_error = cudaSuccess; return e; }
+cudaError_t cudaGetDeviceCount(int *n) { *n = device_count(); return cudaSuccess; }
+cudaError_t cudaSetDevice(int d) { return d >= 0 && d < device_count() ? cudaSuccess : cudaErrorInvalidValue; }
+cudaError_t cudaGetDeviceProperties(cudaDeviceProp *p, int)
+{
+    memset(p, 0, sizeof *p);
+    const char *e = getenv("SPH_EMU_SMS");
+    p->multiProcessorCount = e ? atoi(e) : 1;       // grid = SMs x 8 blocks at most: small grids keep the fiber count down
+    p->clockRate = 1000000;                         // kHz; clock64() counts nanoseconds here
+    strcpy(p->name, "kernel-source emulator (host)");
+    return cudaSuccess;
+}
+cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
+cudaError_t cudaStreamCreateWithFlags(cudaStream_t *s, unsigned) { *s = new emu_stream{nullptr}; return cudaSuccess; }
+cudaError_t cudaStreamDestroy(cudaStream_t s) { delete s; return cudaSuccess; }
+cudaError_t cudaStreamSynchronize(cudaStream_t s) { return s && s->capturing ? cudaErrorStreamCaptureUnsupported : cudaSuccess; }
+cudaError_t cudaStreamBeginCapture(cudaStream_t s, int)
+{
+    if (!s || s->capturing) return cudaErrorInvalidValue;
+    s->capturing = new emu_graph();
+    return cudaSuccess;
+}
+cudaError_t cudaStreamEndCapture(cudaStream_t s, cudaGraph_t *g)
+{
+    if (!s || !s->capturing) return cudaErrorInvalidValue;
+    *g = s->capturing;
+    s->capturing = nullptr;
+    return cudaSuccess;
+}
+cudaError_t cudaGraphInstantiate(cudaGraphExec_t *e, cudaGraph_t g, unsigned long long) { *e = new emu_graph(*g); return cudaSuccess; }
+cudaError_t cudaGraphDestroy(cudaGraph_t g) { delete g; return cudaSuccess; }
+cudaError_t cudaGraphExecDestroy(cudaGraphExec_t e) { delete e; return cudaSuccess; }
+cudaError_t cudaGraphLaunch(cudaGraphExec_t e, cudaStream_t s)
+{
+    if (s && s->capturing) return cudaErrorStreamCaptureUnsupported;
+    for (auto &n : e->nodes) emu::run_grid(std::get<0>(n), std::get<1>(n), std::get<2>(n));
+    return cudaSuccess;
+}
+
+// device memory: filled with a poison pattern, because cudaMalloc does not zero either
+cudaError_t emu_malloc(void **p, size_t bytes)
+{
+    *p = malloc(bytes ? bytes : 1);
+    if (!*p) return cudaErrorInvalidValue;
+    memset(*p, 0xCD, bytes);
+    return cudaSuccess;
+}
+cudaError_t cudaFree(void *p) { free(p); return cudaSuccess; }
+cudaError_t cudaMemset(void *p, int v, size_t bytes) { memset(p, v, bytes); return cudaSuccess; }
+static bool capturing(cudaStream_t s) { return s && s->capturing; }
+cudaError_t cudaMemsetAsync(void *p, int v, size_t bytes, cudaStream_t s)
+{
+    if (capturing(s)) return cudaErrorStreamCaptureUnsupported;
+    memset(p, v, bytes);
+    return cudaSuccess;
+}
+cudaError_t cudaMemcpy(void *d, const void *s, size_t bytes, cudaMemcpyKind) { memmove(d, s, bytes); return cudaSuccess; }
+cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t bytes, cudaMemcpyKind, cudaStream_t st)
+{
+    if (capturing(st)) return cudaErrorStreamCaptureUnsupported;
+    memmove(d, s, bytes);
+    return cudaSuccess;
+}
+cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t *, void *) { return cudaErrorNotSupported; }
+cudaError_t cudaIpcOpenMemHandle(void **, cudaIpcMemHandle_t, unsigned) { return cudaErrorNotSupported; }
+cudaError_t cudaIpcCloseMemHandle(void *) { return cudaSuccess; }

@@ -19,6 +19,8 @@ def main():
     block = len(sys.argv) > 5 and sys.argv[5] in ("block", "block_cost")
     policy = "cost" if len(sys.argv) > 5 and sys.argv[5] == "block_cost" else "count"
     goo = len(sys.argv) > 5 and sys.argv[5] == "goo_stabilised"
+    emu = len(sys.argv) > 5 and sys.argv[5].startswith("emu")       # the CUDA source compiled for the host (tests/emu)
+    block = block or (emu and "block" in sys.argv[5])
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     dist.init_process_group("gloo", rank=rank, world_size=world)
     if block:   # dam-break block in the left half, mover sphere straddling a slab edge inside the water
@@ -30,6 +32,10 @@ def main():
         t = default_tunable(prob["h"], prob["tank_w"], prob["tank_h"], preset="y" if goo else "x")
 
     def backend(tw, th, h, cap, msg, r, w):
+        if emu:
+            sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+            from emu.backend import EmuSlab
+            return EmuSlab(tw, th, h, cap, msg, r, w)
         g = GatherOracle(tw, th, h, cap, msg, r, w)
         if goo:
             g.set_viscosity_stabilisation(0.5)      # the proposal of DESIGN.md 5b (oracle only)

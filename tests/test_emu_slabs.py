@@ -1,0 +1,47 @@
+"""The slab kernels' logic without a GPU: message packing in k_advect / k_relax, k_unpack, windows of grid
+columns, migration, the per-frame rebalancing -- the CUDA source compiled for the host (tests/emu) as the engine
+of the real multi-rank driver over gloo, with the buffers moved by torch.distributed (the "collective"
+transport; the peer-memory transport needs NVLink and is covered by tests/test_gpu_slabs.py).
+N slabs must equal one slab BIT FOR BIT, and both must sit at rounding level from the gather oracle."""
+import numpy as np
+import pytest
+
+from common import ULPS_POS, ulp32
+from emu.backend import EmuSlab
+from oracle.oracle import default_tunable, lattice, make_problem
+from test_slab_gloo import run_world, single_slab
+
+
+def emu_single(prob, t, steps):
+    a, uid = lattice(prob)
+    e = EmuSlab(prob["tank_w"], prob["tank_h"], prob["h"], len(a) + 64, 1, 0, 1)
+    e.set_params(t); e.upload(a, uid); e.step(steps)
+    return e.download()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_emulated_slabs_equal_single_slab_bit_for_bit(tmp_path, built_lib, world):
+    steps = 120
+    parts = run_world(tmp_path, world, 1500, steps, True, "emu")
+    state = np.concatenate([p["state"] for p in parts]); uid = np.concatenate([p["uid"] for p in parts])
+    assert all(int(p["overflow"].sum()) == 0 for p in parts)
+    assert np.array_equal(np.sort(uid), np.arange(1508)), "particles lost or duplicated in migration"
+    order = np.argsort(uid)
+    prob = make_problem(1500)
+    ref, _ = emu_single(prob, default_tunable(prob["h"], prob["tank_w"], prob["tank_h"]), steps)
+    for f in ("x", "y", "v_x", "v_y"):
+        assert np.array_equal(state[f][order].view("u4"), ref[f].view("u4")), f
+
+
+def test_emulated_four_slabs_block_with_mover_across_an_edge(tmp_path, built_lib):
+    n_req, steps = 12000, 60
+    parts = run_world(tmp_path, 4, n_req, steps, True, "emu_block")
+    state = np.concatenate([p["state"] for p in parts]); uid = np.concatenate([p["uid"] for p in parts])
+    assert all(int(p["overflow"].sum()) == 0 for p in parts), [p["overflow"] for p in parts]
+    prob = make_problem(n_req, tank_w=15.0 * float(np.sqrt(n_req / 750.0)), water_frac=0.5)
+    t = default_tunable(prob["h"], prob["tank_w"], prob["tank_h"]); t.mover_center_x = 0.4 * prob["tank_w"]
+    ref, ru = emu_single(prob, t, steps)
+    assert np.array_equal(np.sort(uid), ru)
+    order = np.argsort(uid)
+    for f in ("x", "y", "v_x", "v_y"):
+        assert np.array_equal(state[f][order].view("u4"), ref[f].view("u4")), f
