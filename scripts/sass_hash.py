@@ -23,7 +23,7 @@ def kernel_hashes(lib):
         if m:
             if name:
                 out[name] = [n, h.hexdigest()[:16]]
-            name, h, n = m.group(1), hashlib.sha256(), 0
+            name, h, n = short(m.group(1)), hashlib.sha256(), 0
             continue
         m = re.match(r"\s*/\*[0-9a-f]{4,}\*/\s+(.*?);", line)
         if m and name:
@@ -35,8 +35,10 @@ def kernel_hashes(lib):
 
 
 def short(name):
-    m = re.match(r"_Z(\d+)", name)
-    return name[m.end():m.end() + int(m.group(1))] + ("<>" if "ILb" in name or "ILi" in name else "") if m else name
+    """k_advect<false> is the plain kernel (the default path): it keeps the name it had before it became a template"""
+    d = subprocess.run(["c++filt", name], capture_output=True, text=True).stdout.strip()
+    d = re.sub(r"^void ", "", d)
+    return d.split("(")[0].replace("<false>", "")
 
 
 if __name__ == "__main__":
@@ -52,8 +54,8 @@ if __name__ == "__main__":
             a, b = hs.get(k), ref.get(k)
             state = "same" if a == b else ("NEW" if b is None else ("GONE" if a is None else "CHANGED"))
             bad += state in ("CHANGED", "GONE")
-            print(f"{state:8s} {short(k):18s} {a} {'' if a == b else b}")
+            print(f"{state:8s} {k:18s} {a} {'' if a == b else b}")
         sys.exit(1 if bad else 0)
     else:
         for k, v in sorted(hs.items()):
-            print(f"{short(k):18s} {v[0]:6d} {v[1]}")
+            print(f"{k:18s} {v[0]:6d} {v[1]}")

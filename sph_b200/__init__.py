@@ -61,6 +61,7 @@ C_ABI_SYMBOLS = (
     "sph_advect", "sph_sort", "sph_density", "sph_relax", "sph_step", "sph_exchange_buffers",
     "sph_set_neighbors", "sph_get_cells", "sph_get_pairs", "sph_get_forward_counts",
     "sph_pack_coords", "sph_launch_count", "sph_run_frame", "sph_p2p_local_handle", "sph_p2p_connect", "sph_copy_n_local", "sph_copy_load", "sph_init_lattice",
+    "sph_set_viscosity_stabilisation",
 )
 
 _lib = None
@@ -90,6 +91,7 @@ def _bind(L):
     L.sph_get_pairs.restype = C.c_longlong
     L.sph_get_pairs.argtypes = [C.c_void_p, C.c_void_p, C.c_longlong]
     L.sph_set_edges.argtypes = [C.c_void_p, C.c_float, C.c_float]
+    L.sph_set_viscosity_stabilisation.argtypes = [C.c_void_p, C.c_float, C.c_float]
     L.sph_create.argtypes = [C.POINTER(Config), C.POINTER(C.c_void_p)]
     for name in ("sph_destroy", "sph_synchronize", "sph_advect", "sph_sort", "sph_density", "sph_relax"):
         getattr(L, name).argtypes = [C.c_void_p]
@@ -148,6 +150,10 @@ class Context:
 
     def set_params(self, t): self._ck(self.L.sph_set_params(self.h, C.byref(t)), "sph_set_params")
     def queue_params(self, t): self._ck(self.L.sph_queue_params(self.h, C.byref(t)), "sph_queue_params")
+    def set_viscosity_stabilisation(self, gamma, min_dt_sigma=0.0):
+        """Optional stabilised viscosity gather (sph_set_viscosity_stabilisation): needed for the goo preset."""
+        self._ck(self.L.sph_set_viscosity_stabilisation(self.h, gamma, min_dt_sigma), "sph_set_viscosity_stabilisation")
+
     def set_edges(self, s, e): self._ck(self.L.sph_set_edges(self.h, s, e), "sph_set_edges")
     def set_neighbors(self, l, r): self._ck(self.L.sph_set_neighbors(self.h, int(l), int(r)), "sph_set_neighbors")
     def synchronize(self): self._ck(self.L.sph_synchronize(self.h), "sph_synchronize")

@@ -35,6 +35,9 @@ struct sph_ctx {
     uint32_t *U[2];
     float2 *dens;
     sph_mask_t *nmask;               // SPH_NROWS x capacity: per-row acceptance masks from k_density for k_relax
+    float *coupling;                 // per entry: sum of its pairs' viscosity coefficients (stabilised viscosity gather only)
+    DevOptions *dopt;                // device copy of the optional-path parameters
+    float visc_gamma, visc_min_dt_sigma;
     int *cnt, *cell_start, *t_key, *t_slot, *ord_src, *ord_key;
     uint32_t *ord_uid;
     int *tile_total;                 // one population total per scan tile
@@ -47,8 +50,8 @@ struct sph_ctx {
     int stage;
     int grid;
     int size_x, size_y;
-    cudaGraphExec_t graph;
-    bool graph_ready;
+    cudaGraphExec_t graph[2];        // whole step, [1] = with the stabilised viscosity gather
+    bool graph_ready[2];
     long long launches;
     long long steps;
     char err[256];
@@ -135,6 +138,9 @@ extern "C" int sph_create(const sph_config *cfg, sph_ctx **out)
     for (int i = 0; i < 2; i++) CK(cudaMalloc(&ctx->U[i], cap * sizeof(uint32_t)));
     CK(cudaMalloc(&ctx->dens, cap * sizeof(float2)));
     CK(cudaMalloc(&ctx->nmask, SPH_NROWS * cap * sizeof(sph_mask_t)));
+    CK(cudaMalloc(&ctx->coupling, cap * sizeof(float)));
+    CK(cudaMalloc(&ctx->dopt, sizeof(DevOptions)));
+    CK(cudaMemset(ctx->dopt, 0, sizeof(DevOptions)));
     CK(cudaMalloc(&ctx->cnt, (ncell_max + 1) * sizeof(int)));
     CK(cudaMalloc(&ctx->cell_start, (ncell_max + 1) * sizeof(int)));
     CK(cudaMalloc(&ctx->t_key, cap * sizeof(int)));
@@ -199,7 +205,8 @@ extern "C" void sph_destroy(sph_ctx *ctx)
 {
     if (!ctx) return;
     cudaStreamSynchronize(ctx->stream);
-    if (ctx->graph_ready) cudaGraphExecDestroy(ctx->graph);
+    for (int m = 0; m < 2; m++) if (ctx->graph_ready[m]) cudaGraphExecDestroy(ctx->graph[m]);
+    cudaFree(ctx->coupling); cudaFree(ctx->dopt);
     for (int i = 0; i < 4; i++) cudaFree(ctx->P[i]);
     for (int i = 0; i < 3; i++) cudaFree(ctx->Q[i]);
     for (int i = 0; i < 2; i++) cudaFree(ctx->U[i]);
@@ -236,6 +243,17 @@ extern "C" int sph_queue_params(sph_ctx *ctx, const sph_tunable *t)
     if (!ctx || !t) return SPH_ERR_ARG;
     ctx->queued = *t;
     ctx->have_queued = true;
+    return SPH_OK;
+}
+
+extern "C" int sph_set_viscosity_stabilisation(sph_ctx *ctx, float gamma, float min_dt_sigma)
+{
+    if (!ctx || !(gamma >= 0.0f) || !(min_dt_sigma >= 0.0f)) return SPH_ERR_ARG;
+    ctx->visc_gamma = gamma;
+    ctx->visc_min_dt_sigma = min_dt_sigma;
+    DevOptions o;
+    o.visc_gamma = gamma;
+    CK(cudaMemcpyAsync(ctx->dopt, &o, sizeof o, cudaMemcpyHostToDevice, ctx->stream));   // pageable: staged before returning
     return SPH_OK;
 }
 
@@ -291,7 +309,7 @@ extern "C" int sph_p2p_connect(sph_ctx *ctx, const void *left_handle64, const vo
         ctx->hp.remote_base[s] = (unsigned long long)ctx->peer[s];
     }
     ctx->hp.p2p = 1;
-    if (ctx->graph_ready) { cudaGraphExecDestroy(ctx->graph); ctx->graph_ready = false; }
+    for (int m = 0; m < 2; m++) if (ctx->graph_ready[m]) { cudaGraphExecDestroy(ctx->graph[m]); ctx->graph_ready[m] = false; }
     return push_params(ctx);
 }
 
@@ -336,11 +354,27 @@ static int launch_sort(sph_ctx *ctx, int which, bool with_unpack = true)
     return SPH_OK;
 }
 
+// The stabilised viscosity gather runs for the parameter blocks that need it: gamma > 0 and a per-pair
+// coefficient dt*sigma at or above the caller's threshold (the goo preset: 0.83; the default fluid: 0.17).
+static bool stabilised(const sph_ctx *ctx)
+{
+    return ctx->visc_gamma > 0.0f && ctx->hp.dt * ctx->hp.sigma >= ctx->visc_min_dt_sigma;
+}
+
 static int launch_advect(sph_ctx *ctx)
 {
-    SPH_LAUNCH(k_advect, ctx->grid, ctx->stream)(ctx->dp, ctx->counters, ctx->P[0], ctx->Q[0], ctx->U[0],
+    if (stabilised(ctx)) {
+        SPH_LAUNCH(k_coupling, ctx->grid, ctx->stream)(ctx->dp, ctx->counters, ctx->P[0], ctx->Q[0], ctx->cell_start, ctx->coupling);
+        SPH_LAUNCH(k_advect<true>, ctx->grid, ctx->stream)(ctx->dp, ctx->counters, ctx->P[0], ctx->Q[0], ctx->U[0],
+                                                            ctx->cell_start, ctx->P[1], ctx->cnt, ctx->t_key, ctx->t_slot,
+                                                            ctx->send[0], ctx->send[1], ctx->coupling, ctx->dopt);
+        ctx->launches += 2;
+        CK(cudaGetLastError());
+        return SPH_OK;
+    }
+    SPH_LAUNCH(k_advect<false>, ctx->grid, ctx->stream)(ctx->dp, ctx->counters, ctx->P[0], ctx->Q[0], ctx->U[0],
                                                          ctx->cell_start, ctx->P[1], ctx->cnt, ctx->t_key, ctx->t_slot,
-                                                         ctx->send[0], ctx->send[1]);
+                                                         ctx->send[0], ctx->send[1], nullptr, nullptr);
     ctx->launches++;
     CK(cudaGetLastError());
     return SPH_OK;
@@ -439,7 +473,8 @@ extern "C" int sph_step(sph_ctx *ctx, int n)
                 (rc = sph_relax(ctx)) || (rc = sph_sort(ctx))) return rc;
             continue;
         }
-        if (!ctx->graph_ready) {
+        const int m = stabilised(ctx) ? 1 : 0;           // one captured step per variant of the viscosity gather
+        if (!ctx->graph_ready[m]) {
             cudaGraph_t g;
             long long before = ctx->launches;
             CK(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
@@ -448,12 +483,12 @@ extern "C" int sph_step(sph_ctx *ctx, int n)
             ctx->launches = before;
             if (rc) return rc;
             CK(e);
-            CK(cudaGraphInstantiate(&ctx->graph, g, 0));
+            CK(cudaGraphInstantiate(&ctx->graph[m], g, 0));
             CK(cudaGraphDestroy(g));
-            ctx->graph_ready = true;
+            ctx->graph_ready[m] = true;
         }
-        CK(cudaGraphLaunch(ctx->graph, ctx->stream));
-        ctx->launches += ctx->cfg.nranks > 1 ? 13 : 11;
+        CK(cudaGraphLaunch(ctx->graph[m], ctx->stream));
+        ctx->launches += (ctx->cfg.nranks > 1 ? 13 : 11) + m;
         ctx->steps++;
     }
     return SPH_OK;

@@ -41,6 +41,12 @@ struct DevParams {
     long long spin_timeout;          // clock64 cycles a device-side wait may last before it gives up and flags an error
 };
 
+// Parameters of the optional paths, resident like DevParams (a captured graph keeps working when they change)
+// but kept out of it, so that the kernels measured in round 1 keep their machine code.
+struct DevOptions {
+    float visc_gamma;                // stabilised viscosity gather: s_ij = 1 / max(1, gamma max(C_i, C_j))
+};
+
 // device-side counters (ints); indices below
 enum {
     CN_NTOT = 0,        // resident entries in the sorted arrays
@@ -115,7 +121,14 @@ __device__ __forceinline__ float sqrt_approx(float x)
     asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 }
+__device__ __forceinline__ float rcp_approx(float x)
+{
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
 #else
+static inline float rcp_approx(float x) { return 1.0f / x; }
 static inline int ld_acquire_sys(const int *p) { return *(const volatile int *)p; }
 static inline void st_release_sys(int *p, int v) { *(volatile int *)p = v; }
 static inline float rsqrt_approx(float x) { return 1.0f / sqrtf(x); }

@@ -177,14 +177,29 @@ __device__ __forceinline__ void bin_position(int i, float2 p, int extra_bits, co
 //     + boundaryConditions (:656) + identify_oob_particles (:481) + ghost selection
 //     (communication.c:134-141) + first half of hash_fluid pass 1 (hash.c:153-166)
 // -------------------------------------------------------------------------------------------
+// s_ij = 1 / max(1, gamma max(C_i, C_j)): symmetric, and exactly 1 wherever the plain gather is stable
+template <bool STAB>
+__device__ __forceinline__ float stab_scale(float t, float gci, float gamma, const float *__restrict__ coupling, int j)
+{
+    if constexpr (STAB) {
+        const float gc = fmaxf(gci, gamma * coupling[j]);
+        return t * (gc > 1.0f ? rcp_approx(gc) : 1.0f);
+    } else {
+        return t;
+    }
+}
+
+// STAB: the stabilised viscosity gather (k_coupling below); false = the plain gather, the default
+template <bool STAB>
 __global__ void __launch_bounds__(SPH_THREADS, SPH_BLOCKS_ADVECT)
 k_advect(const DevParams *__restrict__ Pp, int *__restrict__ counters,
          const float2 *__restrict__ pos, const float2 *__restrict__ vel, const uint32_t *__restrict__ uid,
          const int *__restrict__ cell_start,
          float2 *__restrict__ pos_pred, int *__restrict__ cnt, int *__restrict__ t_key, int *__restrict__ t_slot,
-         unsigned char *send_l, unsigned char *send_r)
+         unsigned char *send_l, unsigned char *send_r, const float *__restrict__ coupling, const DevOptions *__restrict__ Op)
 {
     const DevParams P = *Pp;
+    const float gamma = STAB ? Op->visc_gamma : 0.0f;
     const int n = counters[CN_NTOT];
     const float dt = P.dt;
     const float gdt = (-P.g) * dt;
@@ -200,6 +215,7 @@ k_advect(const DevParams *__restrict__ Pp, int *__restrict__ counters,
         const float2 v0 = vel[i];
         float vx = v0.x, vy = v0.y + gdt;                               // apply_gravity
         const Rows R = candidate_rows(p, P, cell_start);
+        const float gci = STAB ? gamma * coupling[i] : 0.0f;
 #pragma unroll
         for (int d = 0; d < SPH_NROWS; d++) {
             // Branch-free body (see k_density): a candidate that is not a neighbour, or a neighbour that
@@ -221,7 +237,7 @@ k_advect(const DevParams *__restrict__ Pp, int *__restrict__ counters,
                 const bool hit = in && u_in > 0.0f;
                 // half the impulse, so that the +-5 clamp of checkVelocity becomes +-2.5 (exact scaling)
                 const float whdt = fmaf(-r2 * rs, h_recip, 1.0f) * hdt;
-                const float t = u_in * fmaf(P.beta, u_in, P.sigma) * whdt * rs;
+                const float t = stab_scale<STAB>(u_in * fmaf(P.beta, u_in, P.sigma) * whdt * rs, gci, gamma, coupling, j);
                 const float ix = fminf(fmaxf(t * dx, -2.5f), 2.5f);
                 const float iy = fminf(fmaxf(t * dy, -2.5f), 2.5f);
                 vx -= hit ? ix : 0.0f;
@@ -263,6 +279,54 @@ k_advect(const DevParams *__restrict__ Pp, int *__restrict__ counters,
             }
         }
         bin_position(i, np, extra, P, cnt, t_key, t_slot, counters);
+    }
+}
+
+// -------------------------------------------------------------------------------------------
+// K1s Stabilised viscosity gather (optional, sph_set_viscosity_stabilisation).
+//     The reference applies its impulses pair by pair IN PLACE (fluid.c:442-472), so every pair sees the
+//     velocities the pairs before it left behind and a pair's approach speed is damped by the factor
+//     1 - dt (1-q)(sigma + beta u) without overshoot.  A gather sums a particle's impulses from FROZEN
+//     velocities; with C_i = sum_j dt (1-q_ij)(sigma + beta u_ij) over its approaching pairs the velocity
+//     changes by about C_i / 2 times the approach speed, which overshoots and feeds itself once C_i >> 1:
+//     the "goo" preset (sigma 100, beta 10, controls.c:359-371; dt sigma = 0.83 per pair) never settles.
+//     k_coupling forms C for every resident entry (ghosts included: the 2h ghost layer holds all their
+//     neighbours), and k_advect_stab scales each pair's impulse by s_ij = 1 / max(1, gamma max(C_i, C_j)):
+//     symmetric, so momentum is still exchanged pairwise; independent of the decomposition; exactly 1
+//     wherever the plain gather is stable, so those results do not change.
+// -------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(SPH_THREADS, SPH_BLOCKS_DENSITY)
+k_coupling(const DevParams *__restrict__ Pp, const int *__restrict__ counters,
+           const float2 *__restrict__ pos, const float2 *__restrict__ vel, const int *__restrict__ cell_start,
+           float *__restrict__ coupling)
+{
+    const DevParams P = *Pp;
+    const int n = counters[CN_NTOT];
+    const float h_recip = __fdiv_rn(1.0f, P.h);
+    const float h2 = __fmul_rn(P.h, P.h);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float2 p = pos[i];
+        const float2 v0 = vel[i];
+        float c = 0.0f;
+        const Rows R = candidate_rows(p, P, cell_start);
+#pragma unroll
+        for (int d = 0; d < SPH_NROWS; d++) {
+#pragma unroll kGatherUnroll
+            for (int j = R.b[d]; j < R.e[d]; j++) {
+                const float2 q = pos[j];
+                const float dx = q.x - p.x, dy = q.y - p.y;
+                const float r2 = dist2(dx, dy);
+                const float2 vq = vel[j];
+                const float rs = rsqrt_approx(r2);
+                // as in k_advect: the particle itself (r2 == 0) gives u = NaN and fails u > 0
+                const float u_in = ((v0.x - vq.x) * dx + (v0.y - vq.y) * dy) * rs;
+                const bool hit = r2 <= h2 && u_in > 0.0f;
+                const float wdt = fmaf(-r2 * rs, h_recip, 1.0f) * P.dt;
+                const float cj = wdt * fmaf(P.beta, u_in, P.sigma);
+                c += hit ? cj : 0.0f;
+            }
+        }
+        coupling[i] = c;
     }
 }
 

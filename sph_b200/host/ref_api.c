@@ -80,6 +80,14 @@ int sph_ref_attach(fluid_particle **pointers, param *params, AABB_t *boundary, n
     int rc = sph_create(&cfg, &G.ctx);
     if (rc) { note("sph_ref_attach", rc); if (G.ctx) { sph_destroy(G.ctx); G.ctx = NULL; } return rc; }
     G.tank_w = cfg.tank_w; G.tank_h = cfg.tank_h;
+    {   /* optional stabilised viscosity gather for hosts driven through the reference's own entry points, which
+         * have no call for it: SPH_VISC_STAB=gamma[,min_dt_sigma] (e.g. "0.5,0.5": engages for the goo preset only) */
+        const char *vs = getenv("SPH_VISC_STAB");
+        if (vs) {
+            float gamma = 0.0f, thr = 0.0f;
+            if (sscanf(vs, "%f,%f", &gamma, &thr) >= 1) note("sph_set_viscosity_stabilisation", sph_set_viscosity_stabilisation(G.ctx, gamma, thr));
+        }
+    }
     sync_params("sph_ref_attach", params);
     sph_particle *flat = (sph_particle *)malloc((size_t)(n > 0 ? n : 1) * sizeof(sph_particle));
     for (int i = 0; i < n; i++) flat[i] = *pointers[i];

@@ -30,6 +30,13 @@ KE_REL = 0.25           # kinetic energy per particle
 ORDER_SPREAD_FACTOR = 1.5
 
 
+# The goo heap under the stabilised gather settles into one of two packings -- mean density 10.03 or 10.18
+# (+0.7 % / +2.2 % of the reference's 9.97), mean height 0.640 or 0.557 (reference 0.667, own order spread 14 %) --
+# and a 1-ulp change of ONE initial coordinate decides which (gather oracle against itself; the CUDA source lands
+# on the other one than the oracle from the unperturbed lattice).  So for this case the mean-density bar is 3 %.
+GOO_STABILISED_WIDEN = {"mean_density": 0.03}
+
+
 def longrun_tolerances(name):
     """-> dict(mean_density, max_density, mean_height, ke_rel, ke_abs) for check_long_run_statistics"""
     import json

@@ -94,12 +94,13 @@ def density_of(make, tank_w, tank_h, h, t, aos):
     return b.download()[0]["density"]
 
 
-def check_long_run_statistics(make, name, lattice_state, dens_make=None, prepare=None):
+def check_long_run_statistics(make, name, lattice_state, dens_make=None, prepare=None, widen=None):
     """1200 steps from the lattice; statistics averaged over the last 200 agree with the reference's within
     common.longrun_tolerances(name) (the stated tolerances, widened to 1.5 x the reference's own sensitivity to
     its particle order where that is larger)."""
     z, t, tank_w, tank_h, h, _ = load_golden(name)
     tol = longrun_tolerances(name)
+    tol.update(widen or {})
     b = make(tank_w, tank_h, h, len(lattice_state) + 64)
     if prepare:
         prepare(b)

@@ -18,16 +18,19 @@ def main():
 
     out, n_req, steps = sys.argv[1], int(sys.argv[2]), int(sys.argv[3])
     transport = sys.argv[4] if len(sys.argv) > 4 else "p2p"
+    goo = len(sys.argv) > 5 and sys.argv[5] == "goo_stabilised"     # preset y with the stabilised viscosity gather
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
     dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ["LOCAL_RANK"])))
     tank_w = 15.0 * float(np.sqrt(n_req / (1500.0 * 0.5)))
     prob = sph_b200.make_problem(n_req, tank_w=tank_w, water_frac=0.5, nranks=world)
-    t = sph_b200.default_params(prob["h"], prob["tank_w"], prob["tank_h"])
+    t = sph_b200.default_params(prob["h"], prob["tank_w"], prob["tank_h"], preset="y" if goo else "x")
     t.mover_center_x = 0.4 * prob["tank_w"]          # in the path of the collapsing block
     stream = torch.cuda.Stream()
     with torch.cuda.stream(stream):
         sim = SlabRunner(prob, t, rank, world, stream, transport=transport)
+        if goo:
+            sim.ctx.set_viscosity_stabilisation(0.5)
         sim.init_lattice()
         sim.run(steps)
         a, uid = sim.ctx.download()
@@ -39,8 +42,10 @@ def main():
     if rank == 0:
         p1 = sph_b200.make_problem(n_req, tank_w=tank_w, water_frac=0.5, nranks=1)
         ctx = sph_b200.Context(p1["tank_w"], p1["tank_h"], p1["h"], p1["n_global"] + 64)
-        t1 = sph_b200.default_params(p1["h"], p1["tank_w"], p1["tank_h"]); t1.mover_center_x = 0.4 * p1["tank_w"]
+        t1 = sph_b200.default_params(p1["h"], p1["tank_w"], p1["tank_h"], preset="y" if goo else "x"); t1.mover_center_x = 0.4 * p1["tank_w"]
         ctx.set_params(t1)
+        if goo:
+            ctx.set_viscosity_stabilisation(0.5)
         a1, u1 = sph_b200.lattice(p1)
         ctx.upload(a1, u1)
         ctx.step(steps)

@@ -18,7 +18,7 @@ def main():
     out, n_req, steps, balance = sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4])
     block = len(sys.argv) > 5 and sys.argv[5] in ("block", "block_cost")
     policy = "cost" if len(sys.argv) > 5 and sys.argv[5] == "block_cost" else "count"
-    goo = len(sys.argv) > 5 and sys.argv[5] == "goo_stabilised"
+    goo = len(sys.argv) > 5 and sys.argv[5] in ("goo_stabilised", "emu_goo_stabilised")
     emu = len(sys.argv) > 5 and sys.argv[5].startswith("emu")       # the CUDA source compiled for the host (tests/emu)
     block = block or (emu and "block" in sys.argv[5])
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
@@ -35,7 +35,10 @@ def main():
         if emu:
             sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
             from emu.backend import EmuSlab
-            return EmuSlab(tw, th, h, cap, msg, r, w)
+            e = EmuSlab(tw, th, h, cap, msg, r, w)
+            if goo:
+                e.set_viscosity_stabilisation(0.5)
+            return e
         g = GatherOracle(tw, th, h, cap, msg, r, w)
         if goo:
             g.set_viscosity_stabilisation(0.5)      # the proposal of DESIGN.md 5b (oracle only)

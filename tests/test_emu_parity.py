@@ -39,6 +39,10 @@ from test_gpu_parity import (  # noqa: E402,F401
     test_pack_coords_matches_reference_formula,
     test_device_side_lattice_equals_host_lattice,
     test_mover_autopilot_and_preset_cycle,
+    test_stabilised_viscosity_rounding_level_agreement_with_gather_oracle,
+    test_stabilised_viscosity_engages_on_goo_and_leaves_stable_presets_bit_identical,
+    test_stabilisation_threshold_selects_the_pass_per_parameter_block,
+    test_long_run_statistics_goo_with_stabilised_viscosity,
 )
 
 

@@ -78,6 +78,74 @@ def test_long_run_statistics_default(built_lib):
     pc.check_long_run_statistics(mk, "default1508", a, dens_make=make_oracle)
 
 
+# ---- the optional stabilised viscosity gather (sph_set_viscosity_stabilisation) ----
+GAMMA = 0.5
+
+
+def mk_stab(*a):
+    b = Cuda(*a)
+    b.c.set_viscosity_stabilisation(GAMMA)
+    return b
+
+
+def make_oracle_stab(*a):
+    o = make_oracle(*a)
+    o.set_viscosity_stabilisation(GAMMA)
+    return o
+
+
+@pytest.mark.parametrize("name,warm", [("goo_rect1508", 300), ("default1508", 400)])
+def test_stabilised_viscosity_rounding_level_agreement_with_gather_oracle(built_lib, name, warm):
+    """k_coupling + k_advect<true> against orc_g_set_viscosity_stabilisation: same algorithm, same order."""
+    pc.check_tight_vs_gather_oracle(mk_stab, make_oracle_stab, name, warm, steps=3)
+
+
+def test_stabilised_viscosity_engages_on_goo_and_leaves_stable_presets_bit_identical(built_lib):
+    """s_ij = 1 exactly wherever gamma * C <= 1: the default fluid, the block and the gas do not change by a bit
+    (graph and staged paths); goo does change."""
+    for name, warm, same in (("default1508", 400, True), ("block3000", 150, True), ("gas1508", 200, True),
+                             ("goo_rect1508", 300, False)):
+        z, t, tank_w, tank_h, h, _ = load_golden(name)
+        st = z[f"w{warm}_state"]
+        outs = []
+        for maker in (mk, mk_stab):
+            b = maker(tank_w, tank_h, h, len(st) + 64)
+            b.set_params(t); b.upload(st); b.step(20)
+            b.advect(); b.sort(); b.density(); b.relax(); b.sort()
+            outs.append(b.download()[0])
+        eq = all(np.array_equal(outs[0][f].view("u4"), outs[1][f].view("u4")) for f in ("x", "y", "v_x", "v_y"))
+        assert eq == same, name
+
+
+def test_stabilisation_threshold_selects_the_pass_per_parameter_block(built_lib):
+    """min_dt_sigma: the extra pass (one more launch per step) only runs for blocks with dt*sigma at or above
+    it -- goo 0.83, default fluid 0.17 -- and a preset change in mid-run switches it."""
+    import sph_b200
+    z, t, tank_w, tank_h, h, _ = load_golden("default1508")
+    st = z["w400_state"]
+    b = mk(tank_w, tank_h, h, len(st) + 64)
+    b.c.set_viscosity_stabilisation(GAMMA, 0.5)
+    b.set_params(t); b.upload(st)
+    n0 = b.launches; b.step(4); per_step_plain = (b.launches - n0) // 4
+    ts = as_sph(t)
+    sph_b200._host().sph_host_preset(sph_b200.C.byref(ts), b"y")
+    b.c.set_params(ts)
+    n0 = b.launches; b.step(4); per_step_goo = (b.launches - n0) // 4
+    assert per_step_goo == per_step_plain + 1
+    sph_b200._host().sph_host_preset(sph_b200.C.byref(ts), b"x")
+    b.c.set_params(ts)
+    n0 = b.launches; b.step(4)
+    assert (b.launches - n0) // 4 == per_step_plain
+
+
+def test_long_run_statistics_goo_with_stabilised_viscosity(built_lib):
+    """The goo preset (sigma 100, beta 10) settles to the reference's statistics with the stabilised gather;
+    with the plain gather it never settles (tests/test_oracle_gather.py pins that on the oracle)."""
+    a, _ = lattice(make_problem(1500))
+    from common import GOO_STABILISED_WIDEN
+    pc.check_long_run_statistics(mk_stab, "goo_rect1508", a, dens_make=make_oracle, widen=GOO_STABILISED_WIDEN)
+
+
 def test_graph_step_equals_staged_and_is_deterministic(built_lib):
     z, t, tank_w, tank_h, h, _ = load_golden("default1508")
     st = z["w400_state"]

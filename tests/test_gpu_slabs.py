@@ -22,15 +22,19 @@ def ngpus():
 @pytest.mark.skipif(ngpus() < 2, reason="needs 2 GPUs")
 @pytest.mark.parametrize("world,transport,n_req,steps", [
     (2, "p2p", 40000, 240), (2, "collective", 40000, 240), (4, "p2p", 40000, 240), (8, "p2p", 40000, 240),
+    # the goo preset with the stabilised viscosity gather (k_coupling runs on ghosts too): steps < 0 selects it
+    (2, "p2p", 40000, -120),
     # big enough that every kernel runs its full grid: the exchange kernel waits for the neighbour inside the
     # kernel, which deadlocks unless its grid is fully co-resident (regression test)
     (2, "p2p", 600000, 40)])
 def test_two_gpu_slabs_match_single_gpu_bit_for_bit(tmp_path, built_lib, world, transport, n_req, steps):
     if ngpus() < world:
         pytest.skip(f"needs {world} GPUs")
+    goo = steps < 0
+    steps = abs(steps)
     base = str(tmp_path / "slab")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
-           "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.join(HERE, "slab_gpu_worker.py"), base, str(n_req), str(steps), transport]
+           "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.join(HERE, "slab_gpu_worker.py"), base, str(n_req), str(steps), transport] + (["goo_stabilised"] if goo else [])
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-4000:]
     parts = [np.load(f"{base}.rank{r}.npz") for r in range(world)]

@@ -56,7 +56,13 @@ def test_goo_preset_needs_the_stabilised_viscosity_gather():
     a, _ = lattice(make_problem(**LONGRUN["goo_rect1508"]))
     with pytest.raises(AssertionError):
         pc.check_long_run_statistics(make, "goo_rect1508", a)
-    pc.check_long_run_statistics(make, "goo_rect1508", a, prepare=lambda g: g.set_viscosity_stabilisation(0.5))
+    from common import GOO_STABILISED_WIDEN
+    pc.check_long_run_statistics(make, "goo_rect1508", a, prepare=lambda g: g.set_viscosity_stabilisation(0.5),
+                                 widen=GOO_STABILISED_WIDEN)
+    # ... and from a lattice with ONE coordinate moved by one ulp, which lands in the other packing of the heap
+    b = a.copy(); b["x"][700] = np.nextafter(b["x"][700], np.float32(100))
+    pc.check_long_run_statistics(make, "goo_rect1508", b, prepare=lambda g: g.set_viscosity_stabilisation(0.5),
+                                 widen=GOO_STABILISED_WIDEN)
 
 
 def test_stabilised_viscosity_leaves_stable_presets_bit_identical():
