@@ -241,6 +241,8 @@ def main_ours(args):
         else:
             from sph_b200.slab import SlabRunner
             sim = SlabRunner(prob, t, rank, world, stream, capacity_factor=2.0, balance_policy=args.balance)
+        if args.visc_stab > 0.0:
+            sim.ctx.set_viscosity_stabilisation(args.visc_stab)
         mark("created")
         sim.init_lattice()
         mark("lattice")
@@ -321,6 +323,7 @@ def main_ours(args):
             "config": {
                 "workload": f"2D dam-break block, {n_global} particles ({args.n} requested per GPU), preset {args.preset}, "
                             f"h={prob['h']:.6f}, tank {prob['tank_w']:.1f}x{prob['tank_h']:.1f}, {world} x-slab(s)",
+                "viscosity_gather": f"stabilised, gamma {args.visc_stab} (k_coupling + k_advect<true>)" if args.visc_stab > 0.0 else "plain",
                 "state": f"{args.preroll} pre-roll steps + {args.warmup} warm-up steps from the lattice",
                 "mean_neighbours_per_particle": stats["mean_neighbours"], "max_bucket": stats["max_bucket"],
                 "l2": "flushed between timed steps (256 MiB write, outside the per-step CUDA-event brackets)",
@@ -444,6 +447,8 @@ def main():
     ap.add_argument("--preroll", type=int, default=1000, help="untimed steps before warm-up (state preparation)")
     ap.add_argument("--water-frac", type=float, default=0.5)
     ap.add_argument("--preset", default="x")
+    ap.add_argument("--visc-stab", type=float, default=0.0, metavar="GAMMA",
+                    help="optional stabilised viscosity gather (needed for --preset y, DESIGN.md 5b); 0 = plain gather (default)")
     ap.add_argument("--cpu-steps", type=int, default=20, help="timed steps of the cpu_baseline sample")
     ap.add_argument("--cpu-warmup", type=int, default=300, help="untimed steps of the cpu_baseline sample (bounded: the "
                     "reference arm, --impl reference, runs the full pre-roll)")

@@ -127,8 +127,38 @@ __device__ __forceinline__ float rcp_approx(float x)
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 }
+// Packed FP32 (sm_100: FADD2 / FMUL2 / FFMA2, two IEEE round-to-nearest fp32 operations per issued instruction;
+// the gathers are bound by instruction issue, not by the FMA pipe).  A pair lives in a 64-bit register; a float2
+// loaded from memory is already one.  Every operation is the same rn operation as its scalar counterpart, so
+// packing changes no result bit.  Used by the SPH_PACKED build of the gather kernels.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi)
+{
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ float2 unpk2(f32x2 v)
+{
+    float2 r;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+    return r;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) { f32x2 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ f32x2 ld2(const float2 *p) { return *reinterpret_cast<const f32x2 *>(p); }
 #else
 static inline float rcp_approx(float x) { return 1.0f / x; }
+struct f32x2 { float lo, hi; };
+static inline f32x2 pk2(float lo, float hi) { return f32x2{lo, hi}; }
+static inline float2 unpk2(f32x2 v) { return float2{v.lo, v.hi}; }
+static inline f32x2 add2(f32x2 a, f32x2 b) { return f32x2{a.lo + b.lo, a.hi + b.hi}; }
+static inline f32x2 sub2(f32x2 a, f32x2 b) { return f32x2{a.lo - b.lo, a.hi - b.hi}; }
+static inline f32x2 mul2(f32x2 a, f32x2 b) { return f32x2{a.lo * b.lo, a.hi * b.hi}; }
+static inline f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { return f32x2{fmaf(a.lo, b.lo, c.lo), fmaf(a.hi, b.hi, c.hi)}; }
+static inline f32x2 ld2(const float2 *p) { return f32x2{p->x, p->y}; }
 static inline int ld_acquire_sys(const int *p) { return *(const volatile int *)p; }
 static inline void st_release_sys(int *p, int v) { *(volatile int *)p = v; }
 static inline float rsqrt_approx(float x) { return 1.0f / sqrtf(x); }

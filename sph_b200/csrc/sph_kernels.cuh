@@ -20,6 +20,15 @@
 #define SPH_UNROLL 4          // candidates per trip of the gather loops (loads issued together)
 #endif
 constexpr int kGatherUnroll = SPH_UNROLL;     // (#pragma unroll takes a constant expression, not a macro)
+// SPH_PACKED=1: the candidate loops of k_advect, k_coupling and k_density process two candidates per trip with
+// packed FP32 instructions (FADD2 / FMUL2 / FFMA2, sph_device.cuh): the same rn operations in the same order, so
+// the results do not change by a bit (tests/test_emu_variants.py), but 20-30 % fewer issued instructions per
+// candidate in kernels that are bound by instruction issue.  Built and checked in the emulator, NOT yet timed
+// on the B200: the default (0) is the scalar code measured in round 1.
+#ifndef SPH_PACKED
+#define SPH_PACKED 0
+#endif
+constexpr int kPackedUnroll = SPH_UNROLL / 2 > 0 ? SPH_UNROLL / 2 : 1;
 #ifndef SPH_BLOCKS_ADVECT
 #define SPH_BLOCKS_ADVECT 4
 #endif
@@ -216,14 +225,52 @@ k_advect(const DevParams *__restrict__ Pp, int *__restrict__ counters,
         float vx = v0.x, vy = v0.y + gdt;                               // apply_gravity
         const Rows R = candidate_rows(p, P, cell_start);
         const float gci = STAB ? gamma * coupling[i] : 0.0f;
+#if SPH_PACKED
+        const f32x2 pp = pk2(p.x, p.y), v0p = pk2(v0.x, v0.y);
+        const f32x2 nh2 = pk2(-h_recip, -h_recip), one2 = pk2(1.0f, 1.0f), hdt2 = pk2(hdt, hdt);
+        const f32x2 beta2 = pk2(P.beta, P.beta), sigma2 = pk2(P.sigma, P.sigma);
+#endif
 #pragma unroll
         for (int d = 0; d < SPH_NROWS; d++) {
             // Branch-free body (see k_density): a candidate that is not a neighbour, or a neighbour that
             // is not approaching, subtracts nothing, so values and order of the sums are those of the gated
             // loop.  With the branches the warp ran the impulse path on nearly every trip with half its
             // lanes idle.
+#if SPH_PACKED
+            int j = R.b[d];
+            const int je = R.e[d];
+#pragma unroll kPackedUnroll
+            for (; j + 1 < je; j += 2) {
+                // two candidates per trip; per candidate the operations and their order are those of the scalar
+                // loop below (the dot product is formed unfused, like the oracle's)
+                const f32x2 d0 = sub2(ld2(pos + j), pp), d1 = sub2(ld2(pos + j + 1), pp);
+                const float2 s0 = unpk2(mul2(d0, d0)), s1 = unpk2(mul2(d1, d1));
+                const float r20 = __fadd_rn(s0.x, s0.y), r21 = __fadd_rn(s1.x, s1.y);
+                const float2 m0 = unpk2(mul2(sub2(v0p, ld2(vel + j)), d0)), m1 = unpk2(mul2(sub2(v0p, ld2(vel + j + 1)), d1));
+                const f32x2 rs = pk2(rsqrt_approx(r20), rsqrt_approx(r21));
+                const f32x2 u = mul2(pk2(__fadd_rn(m0.x, m0.y), __fadd_rn(m1.x, m1.y)), rs);
+                const float2 uu = unpk2(u);
+                const bool hit0 = (r20 <= h2) & (uu.x > 0.0f), hit1 = (r21 <= h2) & (uu.y > 0.0f);
+                const f32x2 whdt = mul2(fma2(mul2(pk2(r20, r21), rs), nh2, one2), hdt2);
+                f32x2 t = mul2(mul2(mul2(u, fma2(beta2, u, sigma2)), whdt), rs);
+                if (STAB) {
+                    const float g0 = fmaxf(gci, gamma * coupling[j]), g1 = fmaxf(gci, gamma * coupling[j + 1]);
+                    t = mul2(t, pk2(g0 > 1.0f ? rcp_approx(g0) : 1.0f, g1 > 1.0f ? rcp_approx(g1) : 1.0f));
+                }
+                // a candidate that does not contribute gets t = 0: its clamped components are +-0, and subtracting
+                // those changes nothing (one select per candidate instead of one per component)
+                const float2 tt = unpk2(t), e0 = unpk2(d0), e1 = unpk2(d1);
+                const float t0 = hit0 ? tt.x : 0.0f, t1 = hit1 ? tt.y : 0.0f;
+                vx -= fminf(fmaxf(t0 * e0.x, -2.5f), 2.5f);
+                vy -= fminf(fmaxf(t0 * e0.y, -2.5f), 2.5f);
+                vx -= fminf(fmaxf(t1 * e1.x, -2.5f), 2.5f);
+                vy -= fminf(fmaxf(t1 * e1.y, -2.5f), 2.5f);
+            }
+            for (; j < je; j++) {
+#else
 #pragma unroll kGatherUnroll
             for (int j = R.b[d]; j < R.e[d]; j++) {
+#endif
                 const float2 q = pos[j];
                 const float dx = q.x - p.x, dy = q.y - p.y;
                 const float r2 = dist2(dx, dy);
@@ -309,10 +356,34 @@ k_coupling(const DevParams *__restrict__ Pp, const int *__restrict__ counters,
         const float2 v0 = vel[i];
         float c = 0.0f;
         const Rows R = candidate_rows(p, P, cell_start);
+#if SPH_PACKED
+        const f32x2 pp = pk2(p.x, p.y), v0p = pk2(v0.x, v0.y);
+        const f32x2 nh2 = pk2(-h_recip, -h_recip), one2 = pk2(1.0f, 1.0f), dt2 = pk2(P.dt, P.dt);
+        const f32x2 beta2 = pk2(P.beta, P.beta), sigma2 = pk2(P.sigma, P.sigma);
+#endif
 #pragma unroll
         for (int d = 0; d < SPH_NROWS; d++) {
+#if SPH_PACKED
+            int j = R.b[d];
+            const int je = R.e[d];
+#pragma unroll kPackedUnroll
+            for (; j + 1 < je; j += 2) {
+                const f32x2 d0 = sub2(ld2(pos + j), pp), d1 = sub2(ld2(pos + j + 1), pp);
+                const float2 s0 = unpk2(mul2(d0, d0)), s1 = unpk2(mul2(d1, d1));
+                const float r20 = __fadd_rn(s0.x, s0.y), r21 = __fadd_rn(s1.x, s1.y);
+                const float2 m0 = unpk2(mul2(sub2(v0p, ld2(vel + j)), d0)), m1 = unpk2(mul2(sub2(v0p, ld2(vel + j + 1)), d1));
+                const f32x2 rs = pk2(rsqrt_approx(r20), rsqrt_approx(r21));
+                const f32x2 u = mul2(pk2(__fadd_rn(m0.x, m0.y), __fadd_rn(m1.x, m1.y)), rs);
+                const float2 uu = unpk2(u);
+                const float2 cj = unpk2(mul2(mul2(fma2(mul2(pk2(r20, r21), rs), nh2, one2), dt2), fma2(beta2, u, sigma2)));
+                c += (r20 <= h2 && uu.x > 0.0f) ? cj.x : 0.0f;
+                c += (r21 <= h2 && uu.y > 0.0f) ? cj.y : 0.0f;
+            }
+            for (; j < je; j++) {
+#else
 #pragma unroll kGatherUnroll
             for (int j = R.b[d]; j < R.e[d]; j++) {
+#endif
                 const float2 q = pos[j];
                 const float dx = q.x - p.x, dy = q.y - p.y;
                 const float r2 = dist2(dx, dy);
@@ -644,6 +715,9 @@ k_density(const DevParams *__restrict__ Pp, int *__restrict__ counters,
         float d = 0.0f, dn = 0.0f;
         int nn = 0;
         const Rows R = candidate_rows(p, P, cell_start);
+#if SPH_PACKED
+        const f32x2 pp = pk2(p.x, p.y), nh2 = pk2(-h_recip, -h_recip), one2 = pk2(1.0f, 1.0f);
+#endif
 #pragma unroll
         for (int dd = 0; dd < SPH_NROWS; dd++) {
             // acceptance mask of this row's first SPH_MASK_BITS candidates: k_relax works on the same
@@ -660,8 +734,31 @@ k_density(const DevParams *__restrict__ Pp, int *__restrict__ counters,
                 // so the value and the order of the sums are those of the gated loop, but no lane ever
                 // waits for another lane's accept path.  With the branch the warp ran the accept path
                 // on nearly every trip with half its lanes idle (profiles/r1_final_full.csv: 23 of 32).
+#if SPH_PACKED
+                int j = jb;
+#pragma unroll kPackedUnroll
+                for (; j + 1 < je; j += 2) {
+                    const f32x2 d0 = sub2(ld2(pos + j), pp), d1 = sub2(ld2(pos + j + 1), pp);
+                    const float2 s0 = unpk2(mul2(d0, d0)), s1 = unpk2(mul2(d1, d1));
+                    const float r20 = __fadd_rn(s0.x, s0.y), r21 = __fadd_rn(s1.x, s1.y);
+                    const bool in0 = r20 <= h2, in1 = r21 <= h2;
+                    m |= in0 ? bit : (sph_mask_t)0;
+                    bit += bit;
+                    m |= in1 ? bit : (sph_mask_t)0;
+                    bit += bit;
+                    const float2 w = unpk2(fma2(pk2(sqrt_approx(r20), sqrt_approx(r21)), nh2, one2));
+                    const float w0 = in0 ? fmaxf(w.x, 0.0f) : 0.0f, w1 = in1 ? fmaxf(w.y, 0.0f) : 0.0f;
+                    const float2 ww = unpk2(mul2(pk2(w0, w1), pk2(w0, w1)));
+                    d += ww.x;
+                    dn = fmaf(ww.x, w0, dn);
+                    d += ww.y;
+                    dn = fmaf(ww.y, w1, dn);
+                }
+                for (; j < je; j++) {
+#else
 #pragma unroll kGatherUnroll
                 for (int j = jb; j < je; j++) {
+#endif
                     const float2 q = pos[j];
                     const float dx = q.x - p.x, dy = q.y - p.y;
                     const float r2 = dist2(dx, dy);

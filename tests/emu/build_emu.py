@@ -13,7 +13,10 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 OUT = os.path.join(HERE, "_build", "libsph_emu.so")
 
 
-def build(force=False, defines=()):
+def build(force=False, defines=(), name="libsph_emu.so"):
+    """defines / name: build-flag variants of the kernels (tests/test_emu_variants.py)"""
+    OUT = os.path.join(HERE, "_build", name)
+    tag = os.path.splitext(name)[0]
     pkg = os.path.join(ROOT, "sph_b200")
     inc = os.path.join(ROOT, "include")
     cu = os.path.join(pkg, "csrc", "sph_capi.cu")
@@ -30,7 +33,7 @@ def build(force=False, defines=()):
         objs.append(o)
     cxx = ["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-DSPH_EMU", "-w",
            "-I", os.path.join(HERE, "fake"), "-I", inc] + [f"-D{d}" for d in defines]
-    o1 = os.path.join(HERE, "_build", "sph_capi.o")
+    o1 = os.path.join(HERE, "_build", tag + ".sph_capi.o")
     subprocess.check_call(cxx + ["-x", "c++", "-c", cu, "-o", o1])
     o2 = os.path.join(HERE, "_build", "emu_runtime.o")
     subprocess.check_call(cxx + ["-c", os.path.join(HERE, "emu_runtime.cpp"), "-o", o2])
