@@ -28,6 +28,12 @@ constexpr int kGatherUnroll = SPH_UNROLL;     // (#pragma unroll takes a constan
 #ifndef SPH_PACKED
 #define SPH_PACKED 0
 #endif
+// SPH_PACKED_RELAX=1: the same for k_relax's pair physics ((x, y) accumulate in one register).  Separate flag:
+// in SASS the packed pair saves ~4 FP instructions but ptxas adds register moves around the rare-path branches,
+// and the kernel is latency- rather than issue-bound; to be decided by measurement.
+#ifndef SPH_PACKED_RELAX
+#define SPH_PACKED_RELAX 0
+#endif
 constexpr int kPackedUnroll = SPH_UNROLL / 2 > 0 ? SPH_UNROLL / 2 : 1;
 #ifndef SPH_BLOCKS_ADVECT
 #define SPH_BLOCKS_ADVECT 4
@@ -239,6 +245,7 @@ k_advect(const DevParams *__restrict__ Pp, int *__restrict__ counters,
 #if SPH_PACKED
             int j = R.b[d];
             const int je = R.e[d];
+            f32x2 vv = pk2(vx, vy);
 #pragma unroll kPackedUnroll
             for (; j + 1 < je; j += 2) {
                 // two candidates per trip; per candidate the operations and their order are those of the scalar
@@ -259,13 +266,13 @@ k_advect(const DevParams *__restrict__ Pp, int *__restrict__ counters,
                 }
                 // a candidate that does not contribute gets t = 0: its clamped components are +-0, and subtracting
                 // those changes nothing (one select per candidate instead of one per component)
-                const float2 tt = unpk2(t), e0 = unpk2(d0), e1 = unpk2(d1);
+                const float2 tt = unpk2(t);
                 const float t0 = hit0 ? tt.x : 0.0f, t1 = hit1 ? tt.y : 0.0f;
-                vx -= fminf(fmaxf(t0 * e0.x, -2.5f), 2.5f);
-                vy -= fminf(fmaxf(t0 * e0.y, -2.5f), 2.5f);
-                vx -= fminf(fmaxf(t1 * e1.x, -2.5f), 2.5f);
-                vy -= fminf(fmaxf(t1 * e1.y, -2.5f), 2.5f);
+                const float2 i0 = unpk2(mul2(d0, pk2(t0, t0))), i1 = unpk2(mul2(d1, pk2(t1, t1)));
+                vv = sub2(vv, pk2(fminf(fmaxf(i0.x, -2.5f), 2.5f), fminf(fmaxf(i0.y, -2.5f), 2.5f)));
+                vv = sub2(vv, pk2(fminf(fmaxf(i1.x, -2.5f), 2.5f), fminf(fmaxf(i1.y, -2.5f), 2.5f)));
             }
+            { const float2 v2 = unpk2(vv); vx = v2.x; vy = v2.y; }
             for (; j < je; j++) {
 #else
 #pragma unroll kGatherUnroll
@@ -828,6 +835,43 @@ k_relax(const DevParams *__restrict__ Pp, int *__restrict__ counters,
         const int gxi = cell_coord(p.x, P.cell_h), gyi = cell_coord(p.y, P.cell_h);
         const Rows R = candidate_rows(p, P, cell_start);
         // pair physics for one listed neighbour (membership r2 <= h2, j != i already established)
+#if SPH_PACKED_RELAX
+        // packed build: (x, y) accumulate in one 64-bit register; the same rn operations in the same order
+        const f32x2 pp = pk2(p.x, p.y), K12 = pk2(K1, K2), AB0 = pk2(Ai, Bi);
+        f32x2 xy = pp;
+        auto pair = [&](int j, float2 q, float2 dj) {
+            const f32x2 dd = sub2(pk2(q.x, q.y), pp);
+            const float2 sq = unpk2(mul2(dd, dd));
+            const float r2 = __fadd_rn(sq.x, sq.y);
+            const float2 ab = unpk2(fma2(pk2(dj.x, dj.y), K12, AB0));
+            const float A = ab.x, B = ab.y;
+            if (r2 <= 1.0001e-12f) {
+                // (nearly) coincident particles, rare: as in the scalar build below
+                const float2 d1 = unpk2(dd);
+                float2 a = unpk2(xy);
+                const float r = __fsqrt_rn(r2);
+                if (r <= 0.000001f) {
+                    const int gxj = cell_coord(q.x, P.cell_h), gyj = cell_coord(q.y, P.cell_h);
+                    const bool owner = (gxi == gxj && gyi == gyj) ? ((u & SPH_UID_MASK) < (uid[j] & SPH_UID_MASK))
+                                                                  : (gxi != gxj ? gxi < gxj : gyi < gyj);
+                    if (owner) { a.x += 0.000001f; a.y += 0.000001f; }
+                }
+                const float ratio = r * h_recip;
+                if (ratio < 1.0f && r > 0.0f) {
+                    const float w = 1.0f - ratio;
+                    const float s = __fdiv_rn(fmaf(B, w, A) * w, r);
+                    a.x = fmaf(-s, d1.x, a.x);
+                    a.y = fmaf(-s, d1.y, a.y);
+                }
+                xy = pk2(a.x, a.y);
+                return;
+            }
+            const float rs = rsqrt_approx(r2);
+            const float w = fmaxf(fmaf(-r2 * rs, h_recip, 1.0f), 0.0f);
+            const float s = fmaf(B, w, A) * w * rs;
+            xy = fma2(pk2(-s, -s), dd, xy);
+        };
+#else
         auto pair = [&](int j, float2 q, float2 dj) {
             const float dx = q.x - p.x, dy = q.y - p.y;
             const float r2 = dist2(dx, dy);
@@ -862,6 +906,7 @@ k_relax(const DevParams *__restrict__ Pp, int *__restrict__ counters,
             x = fmaf(-s, dx, x);
             y = fmaf(-s, dy, y);
         };
+#endif
 #pragma unroll
         for (int d = 0; d < SPH_NROWS; d++) {
             // the lists were built by k_density on these same positions: walk its acceptance bits
@@ -891,6 +936,9 @@ k_relax(const DevParams *__restrict__ Pp, int *__restrict__ counters,
                 pair(j, q, dens[j]);
             }
         }
+#if SPH_PACKED_RELAX
+        { const float2 a = unpk2(xy); x = a.x; y = a.y; }
+#endif
         float2 np = boundary(make_float2(x, y), P);                     // fluid.c:649
         const float2 pv = prev[i];
         const float2 v = make_float2(clamp5(__fdiv_rn(np.x - pv.x, dt)), clamp5(__fdiv_rn(np.y - pv.y, dt)));
