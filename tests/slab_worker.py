@@ -18,14 +18,14 @@ def main():
     out, n_req, steps, balance = sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4])
     block = len(sys.argv) > 5 and sys.argv[5] in ("block", "block_cost")
     policy = "cost" if len(sys.argv) > 5 and sys.argv[5] == "block_cost" else "count"
-    goo = len(sys.argv) > 5 and sys.argv[5] in ("goo_stabilised", "emu_goo_stabilised")
+    goo = len(sys.argv) > 5 and "goo_stabilised" in sys.argv[5]
     emu = len(sys.argv) > 5 and sys.argv[5].startswith("emu")       # the CUDA source compiled for the host (tests/emu)
     block = block or (emu and "block" in sys.argv[5])
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     dist.init_process_group("gloo", rank=rank, world_size=world)
     if block:   # dam-break block in the left half, mover sphere straddling a slab edge inside the water
         prob = make_problem(n_req, tank_w=15.0 * float(np.sqrt(n_req / 750.0)), water_frac=0.5, nranks=world)
-        t = default_tunable(prob["h"], prob["tank_w"], prob["tank_h"])
+        t = default_tunable(prob["h"], prob["tank_w"], prob["tank_h"], preset="y" if goo else "x")
         t.mover_center_x = 0.4 * prob["tank_w"]
     else:
         prob = make_problem(n_req, nranks=world)
