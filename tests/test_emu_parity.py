@@ -50,6 +50,11 @@ def test_full_size_properties_in_small(built_lib):
     gpu.test_full_size_properties(built_lib, 20_000)
 
 
+def test_config4_properties_in_small(built_lib):
+    prob, b, n0, coords, per_frame = gpu.run_config4(6000, 32, 4)
+    gpu.check_config4(prob, b, n0, coords, per_frame, 4)
+
+
 def test_product_library_has_no_emulator_in_it(built_lib):
     """libsph_b200.so is nvcc output with device code and real CUDA runtime calls; the emulator's symbols
     exist only in tests/emu/_build/libsph_emu.so."""

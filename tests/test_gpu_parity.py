@@ -316,3 +316,58 @@ def test_mover_autopilot_and_preset_cycle(built_lib):
     assert np.array_equal(coords[:2 * n].reshape(n, 2), b.pack_coords())
     s = b.status()
     assert s.capacity_overflow == 0 and s.n_local == len(a)
+
+
+def run_config4(n_req, frames, frames_per_preset):
+    """BASELINE.json config 4: dam-break block, mover sphere on the render rank's autopilot path
+    (renderer.c:513-531) ploughing through the water, fluid presets cycled a -> b -> x -> y
+    (controls.c:344-401), one parameter block per frame landing in the last sub-step (fluid.c:293-294), the
+    stabilised viscosity gather engaging for the y phases only (dt*sigma >= 0.5)."""
+    import ctypes as C
+    import sph_b200
+    prob = sph_b200.make_problem(n_req, tank_w=15.0 * float(np.sqrt(n_req / 750.0)), water_frac=0.5)
+    ts = sph_b200.default_params(prob["h"], prob["tank_w"], prob["tank_h"])
+    b = sph_b200.Context(prob["tank_w"], prob["tank_h"], prob["h"], prob["n_global"] + 4096)
+    b.set_viscosity_stabilisation(GAMMA, 0.5)
+    b.set_params(ts)
+    n0 = b.init_lattice(prob)
+    L = sph_b200._host()
+    gl_x, direction = C.c_float(-0.9), C.c_int(1)
+    coords = np.zeros(2 * (n0 + 4096), "i2")
+    per_frame = []
+    for frame in range(frames):
+        L.sph_host_mover_autopilot(C.byref(ts), prob["tank_w"], prob["tank_h"], C.byref(gl_x), C.byref(direction))
+        L.sph_host_preset(C.byref(ts), "abxy"[(frame // frames_per_preset) % 4].encode())
+        before = b.launches
+        n = b.run_frame(ts, 4, coords)
+        per_frame.append(b.launches - before)
+        assert n == n0, (frame, n, n0)
+    return prob, b, n0, coords, per_frame
+
+
+def check_config4(prob, b, n0, coords, per_frame, frames_per_preset):
+    out, u = b.download()
+    assert np.array_equal(u, np.arange(n0, dtype=u.dtype))                           # nobody lost, nobody duplicated
+    assert np.all((out["x"] >= 0) & (out["x"] <= prob["tank_w"]) & (out["y"] >= 0) & (out["y"] <= prob["tank_h"]))
+    assert np.all(np.abs(out["v_x"]) <= 5.0) and np.all(np.abs(out["v_y"]) <= 5.0)   # fluid.c:613-625
+    assert np.all(np.isfinite(out["x"])) and np.all(np.isfinite(out["y"]))
+    s = b.status()
+    assert s.capacity_overflow == 0 and s.neighbor_overflow == 0 and s.n_local == n0 and s.n_halo == 0
+    # the coordinate feed is the reference's formula on the final state (fluid.c:358-361)
+    assert np.array_equal(coords[:2 * n0].reshape(n0, 2), b.pack_coords())
+    # The extra pass ran in the y phases only: one more launch per step there.  A frame whose block CHANGES the
+    # preset runs its last step with the old block's viscosity (the scatter lands after the prediction,
+    # fluid.c:279-310), so only frames inside a phase are counted.
+    plain = per_frame[1]
+    for f in range(1, len(per_frame)):
+        prev_y = "abxy"[((f - 1) // frames_per_preset) % 4] == "y"
+        this_y = "abxy"[(f // frames_per_preset) % 4] == "y"
+        if prev_y == this_y:
+            assert per_frame[f] == plain + (4 if this_y else 0), (f, per_frame)
+    assert any("abxy"[(f // frames_per_preset) % 4] == "y" for f in range(len(per_frame)))
+
+
+def test_config4_full_size_properties(built_lib):
+    """4 M particles (BASELINE.json config 4), 32 frames: size-independent properties only."""
+    prob, b, n0, coords, per_frame = run_config4(4_000_000, 32, 4)
+    check_config4(prob, b, n0, coords, per_frame, 4)
