@@ -159,8 +159,8 @@ static inline f32x2 sub2(f32x2 a, f32x2 b) { return f32x2{a.lo - b.lo, a.hi - b.
 static inline f32x2 mul2(f32x2 a, f32x2 b) { return f32x2{a.lo * b.lo, a.hi * b.hi}; }
 static inline f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { return f32x2{fmaf(a.lo, b.lo, c.lo), fmaf(a.hi, b.hi, c.hi)}; }
 static inline f32x2 ld2(const float2 *p) { return f32x2{p->x, p->y}; }
-static inline int ld_acquire_sys(const int *p) { return *(const volatile int *)p; }
-static inline void st_release_sys(int *p, int v) { *(volatile int *)p = v; }
+static inline int ld_acquire_sys(const int *p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
+static inline void st_release_sys(int *p, int v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
 static inline float rsqrt_approx(float x) { return 1.0f / sqrtf(x); }
 static inline float sqrt_approx(float x) { return sqrtf(x); }
 #endif

@@ -6,16 +6,16 @@
 
 namespace emu {
 
-Fiber *cur = nullptr;
-Block blk;
-uint3 block_idx, block_dim, grid_dim;
+thread_local Fiber *cur = nullptr;
+thread_local Block blk;
+thread_local uint3 block_idx, block_dim, grid_dim;
 
 static const size_t kStack = 256 * 1024;
-static std::vector<Fiber> fibers;
-static std::vector<char *> stacks;
-static ucontext_t main_ctx;
-static const std::function<void()> *body_now = nullptr;
-static int last_error = cudaSuccess;
+static thread_local std::vector<Fiber> fibers;
+static thread_local std::vector<char *> stacks;
+static thread_local ucontext_t main_ctx;
+static thread_local const std::function<void()> *body_now = nullptr;
+static thread_local int last_error = cudaSuccess;
 
 void yield()
 {
@@ -76,15 +76,11 @@ static void run_grid(int grid, int threads, const std::function<void()> &body)
 struct emu_graph { std::vector<std::tuple<int, int, std::function<void()>>> nodes; };
 struct emu_stream { emu_graph *capturing; };
 
-static int g_devices = -1;
-
+// emulated devices are just host threads; SPH_EMU_DEVICES=0 plays a box without a GPU
 static int device_count()
 {
-    if (g_devices < 0) {
-        const char *e = getenv("SPH_EMU_DEVICES");
-        g_devices = e ? atoi(e) : 1;
-    }
-    return g_devices;
+    const char *e = getenv("SPH_EMU_DEVICES");
+    return e ? atoi(e) : 8;
 }
 
 void emu::launch_on_stream(cudaStream_t s, int grid, int threads, std::function<void()> body)
@@ -110,8 +106,7 @@ cudaError_t cudaSetDevice(int d) { return d >= 0 && d < device_count() ? cudaSuc
 cudaError_t cudaGetDeviceProperties(cudaDeviceProp *p, int)
 {
     memset(p, 0, sizeof *p);
-    const char *e = getenv("SPH_EMU_SMS");
-    p->multiProcessorCount = e ? atoi(e) : 1;       // grid = SMs x 8 blocks at most: small grids keep the fiber count down
+    p->multiProcessorCount = 1;                     // one block at a time; grids of at most 8 blocks keep the fiber count down
     p->clockRate = 1000000;                         // kHz; clock64() counts nanoseconds here
     strcpy(p->name, "kernel-source emulator (host)");
     return cudaSuccess;
@@ -167,6 +162,7 @@ cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t bytes, cudaMemcpyKind
     memmove(d, s, bytes);
     return cudaSuccess;
 }
-cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t *, void *) { return cudaErrorNotSupported; }
-cudaError_t cudaIpcOpenMemHandle(void **, cudaIpcMemHandle_t, unsigned) { return cudaErrorNotSupported; }
+// "peer memory": every emulated device lives in this process, so a handle is just the pointer
+cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t *h, void *p) { memset(h, 0, sizeof *h); memcpy(h->reserved, &p, sizeof p); return cudaSuccess; }
+cudaError_t cudaIpcOpenMemHandle(void **p, cudaIpcMemHandle_t h, unsigned) { memcpy(p, h.reserved, sizeof *p); return cudaSuccess; }
 cudaError_t cudaIpcCloseMemHandle(void *) { return cudaSuccess; }

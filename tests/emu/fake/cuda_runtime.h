@@ -7,8 +7,8 @@
 // resulting tests/emu/_build/libsph_emu.so.  libsph_b200.so (nvcc, sm_100a) never sees any of this and has
 // no CPU path; the GPU parity tests (-m gpu) remain the parity tests proper.
 //
-// Execution model: one OS thread.  A kernel launch runs its blocks one after another; the SPH_THREADS threads
-// of a block are fibers (ucontext) run round-robin, switching only at __syncthreads and warp collectives.
+// Execution model: the host thread that calls the library is the device.  A kernel launch runs its blocks one
+// after another; the SPH_THREADS threads of a block are fibers (ucontext) run round-robin, switching only at __syncthreads and warp collectives.
 // Data races between threads of a launch are therefore NOT detected (atomics are plain read-modify-writes),
 // and floating point differs from the GPU where nvcc contracts a*b+c into FFMA and where MUFU approximations
 // are used (the IEEE results here are closer to the oracle, not further).  The _rn intrinsics are exact.
@@ -38,7 +38,7 @@
 #define __host__
 #define __forceinline__ inline
 #define __launch_bounds__(...)
-#define __shared__ static          // blocks run one after another, so one static instance IS the block's copy
+#define __shared__ static thread_local   // a device's blocks run one after another on its OS thread: one instance IS the block's copy
 
 struct float2 { float x, y; };
 struct int4 { int x, y, z, w; };
@@ -56,9 +56,10 @@ struct Block {
     Warp warp[32];
 };
 struct Fiber { ucontext_t ctx; uint3 tid; bool done; };
-extern Fiber *cur;
-extern Block blk;
-extern uint3 block_idx, block_dim, grid_dim;
+// one emulated device per OS thread: two slabs of a peer-memory test run as two threads of one process
+extern thread_local Fiber *cur;
+extern thread_local Block blk;
+extern thread_local uint3 block_idx, block_dim, grid_dim;
 void yield();
 void launch(int grid, int threads, std::function<void()> body);     // runs now, or records into a capturing stream
 }
@@ -116,11 +117,12 @@ static inline unsigned __ballot_sync(unsigned, int p)
     return (unsigned)emu_warp_collective(p != 0, [](long long *s, long long *r) { unsigned m = 0; for (int i = 0; i < 32; i++) m |= (unsigned)(s[i] != 0) << i; for (int i = 0; i < 32; i++) r[i] = m; });
 }
 
-// atomics: one OS thread, fibers switch only at barriers
+// atomics: within a launch one OS thread runs all fibers and switches only at barriers, so plain read-modify-writes
+// suffice; memory shared with ANOTHER emulated device (peer-memory exchange blocks) is ordered by the fences
 template <class T> static inline T atomicAdd(T *p, T v) { T o = *p; *p = o + v; return o; }
 static inline int atomicMax(int *p, int v) { int o = *p; if (v > o) *p = v; return o; }
-static inline void __threadfence() {}
-static inline void __threadfence_system() {}
+static inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+static inline void __threadfence_system() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 static inline void __nanosleep(unsigned) { emu::yield(); }
 static inline long long clock64() { struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return (long long)t.tv_sec * 1000000000ll + t.tv_nsec; }
 
@@ -183,7 +185,9 @@ cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t bytes, cudaMemcpyKind
 cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t *h, void *p);
 cudaError_t cudaIpcOpenMemHandle(void **p, cudaIpcMemHandle_t h, unsigned flags);
 cudaError_t cudaIpcCloseMemHandle(void *p);
-template <class K> static inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int *n, K, int, size_t) { *n = 4; return cudaSuccess; }
+// an emulated device runs ONE block at a time: that is its co-resident capacity (k_unpack's grid is bounded by it,
+// because its blocks wait for the neighbour device inside the kernel)
+template <class K> static inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int *n, K, int, size_t) { *n = 1; return cudaSuccess; }
 
 // kernel launch: SPH_LAUNCH(kernel, grid, stream)(args...)  (sph_capi.cu; k<<<grid, SPH_THREADS, 0, stream>>> under nvcc)
 namespace emu {

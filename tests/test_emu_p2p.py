@@ -1,0 +1,89 @@
+"""The peer-memory exchange protocol without NVLink: two emulated devices (two host threads of this process, each
+running the CUDA source compiled for the host, tests/emu) map each other's exchange block and run whole slab
+steps from captured graphs -- send_messages, the last-block publication, the arrival flags and the device-side
+waits of k_unpack, double buffering by step parity.  The result must equal the single-slab run bit for bit.
+Timing, co-residency and the memory model of real GPUs are out of reach here (tests/test_gpu_slabs.py)."""
+import ctypes as C
+import os
+import threading
+
+import numpy as np
+import pytest
+
+import sph_b200
+from emu.build_emu import build as build_emu
+from oracle.oracle import default_tunable, lattice, make_problem
+from test_gpu_parity import as_sph
+
+
+@pytest.fixture(autouse=True)
+def emulated_library(monkeypatch):
+    monkeypatch.setenv("SPH_SPIN_TIMEOUT_MS", "60000")
+    monkeypatch.setattr(sph_b200, "_lib", sph_b200._bind(C.CDLL(build_emu())))
+    yield
+
+
+@pytest.mark.parametrize("world,goo", [(2, False), (3, True)])
+def test_peer_memory_slab_steps_equal_single_slab_bit_for_bit(built_lib, world, goo):
+    n_req, steps = 3000, 80
+    tank_w = 15.0 * float(np.sqrt(n_req / 750.0))
+    prob = make_problem(n_req, tank_w=tank_w, water_frac=0.5, nranks=world)
+    p1 = make_problem(n_req, tank_w=tank_w, water_frac=0.5)
+
+    def params(p, rank=None):
+        t = default_tunable(p["h"], p["tank_w"], p["tank_h"], preset="y" if goo else "x")
+        t.mover_center_x = 0.3 * p["tank_w"]
+        if rank is not None:
+            t.node_start_x, t.node_end_x = p["slabs"][rank][2], p["slabs"][rank][3]
+        return as_sph(t)
+
+    ctxs = []
+    for r in range(world):
+        a, uid = lattice(prob, r)
+        c = sph_b200.Context(prob["tank_w"], prob["tank_h"], prob["h"], 2 * len(a) + 4096, msg_capacity=2048,
+                             device=r, rank=r, nranks=world)
+        if goo:
+            c.set_viscosity_stabilisation(0.5)
+        c.set_params(params(prob, r))
+        c.upload(a, uid)
+        ctxs.append(c)
+    handles = [c.p2p_handle() for c in ctxs]
+    for r, c in enumerate(ctxs):
+        c.p2p_connect(handles[r - 1] if r > 0 else None, handles[r + 1] if r < world - 1 else None)
+
+    errors = []
+
+    def run(c):
+        try:
+            for _ in range(steps // 8):
+                c.step(8)            # graph replays; neighbours drift apart by at most one exchange
+            c.synchronize()
+        except Exception as e:       # noqa: BLE001
+            errors.append(e)
+
+    threads = [threading.Thread(target=run, args=(c,)) for c in ctxs]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=300)
+    assert not errors, errors
+    assert not any(t.is_alive() for t in threads), "a slab is still waiting for its neighbour"
+
+    parts = [c.download() for c in ctxs]
+    state = np.concatenate([p[0] for p in parts]); uid = np.concatenate([p[1] for p in parts])
+    for c in ctxs:
+        s = c.status()
+        assert s.capacity_overflow == 0 and s.msg_overflow == 0, (s.capacity_overflow, s.msg_overflow)
+        assert b"timed out" not in sph_b200.lib().sph_last_error(c.h)
+
+    a1, u1 = lattice(p1)
+    one = sph_b200.Context(p1["tank_w"], p1["tank_h"], p1["h"], len(a1) + 64)
+    if goo:
+        one.set_viscosity_stabilisation(0.5)
+    one.set_params(params(p1)); one.upload(a1, u1); one.step(steps)
+    ref, ru = one.download()
+    assert np.array_equal(np.sort(uid), ru), "particles lost or duplicated in migration"
+    order = np.argsort(uid)
+    for f in ("x", "y", "v_x", "v_y"):
+        assert np.array_equal(state[f][order].view("u4"), ref[f].view("u4")), f
+    assert sum(c.status().migrated_left + c.status().migrated_right for c in ctxs) >= 0

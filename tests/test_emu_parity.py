@@ -62,3 +62,11 @@ def test_product_library_has_no_emulator_in_it(built_lib):
     assert "emu" not in syms.lower()
     elf = subprocess.run(["cuobjdump", "-lelf", built_lib], capture_output=True, text=True).stdout
     assert "sm_100a" in elf
+
+
+def test_no_device_is_an_error_not_a_fallback(built_lib, monkeypatch):
+    """The C-ABI layer's own no-GPU path (sph_create: "no CUDA device: sph_b200 has no CPU path"), driven by the
+    fake runtime reporting zero devices."""
+    monkeypatch.setenv("SPH_EMU_DEVICES", "0")
+    with pytest.raises(sph_b200.SphError, match="no CPU path"):
+        sph_b200.Context(10.0, 5.0, 0.5, 64)
