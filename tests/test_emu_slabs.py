@@ -22,7 +22,7 @@ def emu_single(prob, t, steps, gamma=0.0):
 
 @pytest.mark.parametrize("world", [2, 3])
 def test_emulated_slabs_equal_single_slab_bit_for_bit(tmp_path, built_lib, world):
-    steps = 120
+    steps = 80
     parts = run_world(tmp_path, world, 1500, steps, True, "emu")
     state = np.concatenate([p["state"] for p in parts]); uid = np.concatenate([p["uid"] for p in parts])
     assert all(int(p["overflow"].sum()) == 0 for p in parts)
@@ -35,7 +35,7 @@ def test_emulated_slabs_equal_single_slab_bit_for_bit(tmp_path, built_lib, world
 
 
 def test_emulated_four_slabs_block_with_mover_across_an_edge(tmp_path, built_lib):
-    n_req, steps = 12000, 60
+    n_req, steps = 12000, 40
     parts = run_world(tmp_path, 4, n_req, steps, True, "emu_block")
     state = np.concatenate([p["state"] for p in parts]); uid = np.concatenate([p["uid"] for p in parts])
     assert all(int(p["overflow"].sum()) == 0 for p in parts), [p["overflow"] for p in parts]
@@ -51,7 +51,7 @@ def test_emulated_four_slabs_block_with_mover_across_an_edge(tmp_path, built_lib
 def test_emulated_stabilised_viscosity_is_decomposition_independent(tmp_path, built_lib):
     """k_coupling forms C for ghosts too (their neighbours sit in the 2h ghost layer), so the scaled impulses of
     the goo preset are the same bits on 3 slabs as on one."""
-    steps = 120
+    steps = 80
     parts = run_world(tmp_path, 3, 1500, steps, True, "emu_goo_stabilised")
     state = np.concatenate([p["state"] for p in parts]); uid = np.concatenate([p["uid"] for p in parts])
     assert all(int(p["overflow"].sum()) == 0 for p in parts)
