@@ -224,6 +224,18 @@ int sph_pack_coords(sph_ctx *ctx, int16_t *xy_pairs, int cap);
  * Returns the local particle count or a negative error. */
 int sph_run_frame(sph_ctx *ctx, const sph_tunable *t, int steps, int16_t *xy_pairs, int cap);
 
+/* ---- the same feed without stalling the compute rank ----
+ * The reference MPI_Isends its frame and starts the next one; it waits for that send only before it overwrites
+ * the buffer (fluid.c:283-287, :354-365).  sph_pack_coords_async packs on the compute stream, lets a second
+ * stream copy the frame into xy_pairs (pinned host memory; untouched until collected) and returns a ticket
+ * (0 or 1, alternating; at most two frames in flight) or a negative error.  sph_coords_wait(ticket) blocks until
+ * that frame has arrived and returns its particle count, like sph_pack_coords.  A single slab copies exactly its
+ * particles; a slab among others copies min(cap, capacity) entries, because its count is not known on the host
+ * without a synchronisation.  sph_run_frame_async = sph_run_frame ending in sph_pack_coords_async. */
+int sph_pack_coords_async(sph_ctx *ctx, int16_t *xy_pairs, int cap);
+int sph_coords_wait(sph_ctx *ctx, int ticket);
+int sph_run_frame_async(sph_ctx *ctx, const sph_tunable *t, int steps, int16_t *xy_pairs, int cap);
+
 /* kernels launched since the context was created (bench bookkeeping) */
 long long sph_launch_count(const sph_ctx *ctx);
 

@@ -61,7 +61,7 @@ C_ABI_SYMBOLS = (
     "sph_advect", "sph_sort", "sph_density", "sph_relax", "sph_step", "sph_exchange_buffers",
     "sph_set_neighbors", "sph_get_cells", "sph_get_pairs", "sph_get_forward_counts",
     "sph_pack_coords", "sph_launch_count", "sph_run_frame", "sph_p2p_local_handle", "sph_p2p_connect", "sph_copy_n_local", "sph_copy_load", "sph_init_lattice",
-    "sph_set_viscosity_stabilisation",
+    "sph_set_viscosity_stabilisation", "sph_pack_coords_async", "sph_coords_wait", "sph_run_frame_async",
 )
 
 _lib = None
@@ -106,6 +106,9 @@ def _bind(L):
     L.sph_get_forward_counts.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
     L.sph_pack_coords.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
     L.sph_run_frame.argtypes = [C.c_void_p, C.POINTER(Tunable), C.c_int, C.c_void_p, C.c_int]
+    L.sph_run_frame_async.argtypes = [C.c_void_p, C.POINTER(Tunable), C.c_int, C.c_void_p, C.c_int]
+    L.sph_pack_coords_async.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    L.sph_coords_wait.argtypes = [C.c_void_p, C.c_int]
     L.sph_init_lattice.argtypes = [C.c_void_p] + [C.c_float] * 4 + [C.c_int] * 3
     L.sph_copy_n_local.argtypes = [C.c_void_p, C.c_void_p]
     L.sph_copy_load.argtypes = [C.c_void_p, C.c_void_p]
@@ -193,6 +196,27 @@ class Context:
                                  0 if coords_out is None else coords_out.size // 2)
         if n < 0:
             self._ck(-n, "sph_run_frame")
+        return n
+
+    def run_frame_async(self, tunable, steps, coords_out):
+        """run_frame without the wait at its end: returns a ticket for coords_wait (sph_run_frame_async)."""
+        k = self.L.sph_run_frame_async(self.h, C.byref(tunable) if tunable is not None else None, int(steps),
+                                       _p(coords_out), coords_out.size // 2)
+        if k < 0:
+            self._ck(-k, "sph_run_frame_async")
+        return k
+
+    def pack_coords_async(self, coords_out):
+        k = self.L.sph_pack_coords_async(self.h, _p(coords_out), coords_out.size // 2)
+        if k < 0:
+            self._ck(-k, "sph_pack_coords_async")
+        return k
+
+    def coords_wait(self, ticket):
+        """Blocks until the frame of `ticket` is in its host buffer; returns its particle count."""
+        n = self.L.sph_coords_wait(self.h, int(ticket))
+        if n < 0:
+            self._ck(-n, "sph_coords_wait")
         return n
 
     def status(self):

@@ -47,6 +47,14 @@ struct sph_ctx {
     int scan_grid;                   // tiles of the widest possible window
     int unpack_grid;                 // k_unpack waits on the neighbour inside the kernel: grid must be fully co-resident
     short2 *coords;
+    // asynchronous coordinate feed (sph_pack_coords_async): the copy of frame f drains on its own stream while the
+    // steps of frame f+1 run, like the reference's MPI_Isend of its frame (fluid.c:283-287, :354-365)
+    cudaStream_t copy_stream;
+    struct { cudaEvent_t packed, copied; int cap; bool pending; } feed[2];
+    int *feed_cnt_dev;               // 2 x CN_COUNT: counters as they stood when the frame was packed
+    int *feed_cnt_host;              // the same, in pinned host memory
+    unsigned feed_seq;
+    int n_uploaded;                  // single slab: the particle count never changes after an upload
     int stage;
     int grid;
     int size_x, size_y;
@@ -178,6 +186,13 @@ extern "C" int sph_create(const sph_config *cfg, sph_ctx **out)
         ctx->unpack_grid = std::min(std::min(ctx->grid, per_sm * prop.multiProcessorCount), 2 * prop.multiProcessorCount);
     }
     CK(cudaMalloc(&ctx->dp, sizeof(DevParams)));
+    CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    for (int k = 0; k < 2; k++) {
+        CK(cudaEventCreateWithFlags(&ctx->feed[k].packed, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&ctx->feed[k].copied, cudaEventDisableTiming));
+    }
+    CK(cudaMalloc(&ctx->feed_cnt_dev, 2 * CN_COUNT * sizeof(int)));
+    CK(cudaMallocHost(&ctx->feed_cnt_host, 2 * CN_COUNT * sizeof(int)));
 
     DevParams &P = ctx->hp;
     P.tank_w = cfg->tank_w; P.tank_h = cfg->tank_h; P.cell_h = cfg->h;
@@ -207,6 +222,13 @@ extern "C" void sph_destroy(sph_ctx *ctx)
     cudaStreamSynchronize(ctx->stream);
     for (int m = 0; m < 2; m++) if (ctx->graph_ready[m]) cudaGraphExecDestroy(ctx->graph[m]);
     cudaFree(ctx->coupling); cudaFree(ctx->dopt);
+    if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
+    for (int k = 0; k < 2; k++) {
+        if (ctx->feed[k].packed) cudaEventDestroy(ctx->feed[k].packed);
+        if (ctx->feed[k].copied) cudaEventDestroy(ctx->feed[k].copied);
+    }
+    cudaFree(ctx->feed_cnt_dev);
+    if (ctx->feed_cnt_host) cudaFreeHost(ctx->feed_cnt_host);
     for (int i = 0; i < 4; i++) cudaFree(ctx->P[i]);
     for (int i = 0; i < 3; i++) cudaFree(ctx->Q[i]);
     for (int i = 0; i < 2; i++) cudaFree(ctx->U[i]);
@@ -515,6 +537,7 @@ static int ingest(sph_ctx *ctx, int n)
     if ((rc = launch_sort(ctx, 1, false))) return rc;
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->stage = ST_READY;
+    ctx->n_uploaded = n;
     return SPH_OK;
 }
 
@@ -658,6 +681,54 @@ extern "C" int sph_get_status(sph_ctx *ctx, sph_status *out)
     return SPH_OK;
 }
 
+// ---- asynchronous coordinate feed --------------------------------------------------------------------------
+// The reference's compute rank MPI_Isends its frame and goes on with the next one; it only waits for that send
+// before it overwrites the buffer (fluid.c:283-287, :354-365).  Same here: sph_pack_coords_async packs on the
+// compute stream, hands the copy to a second stream and returns a ticket; the caller launches the next frame's
+// steps and then collects the ticket.  At most two frames are in flight (tickets 0 and 1 alternate); `xy` should
+// be pinned memory and must stay untouched until the ticket is collected.
+extern "C" int sph_pack_coords_async(sph_ctx *ctx, int16_t *xy, int cap)
+{
+    if (!ctx || !xy || cap < 0) return -SPH_ERR_ARG;
+    float2 *dpos, *dq; uint32_t *duid; bool q_is_prev;
+    if (current_arrays(ctx, &dpos, &dq, &duid, &q_is_prev)) return -SPH_ERR_STATE;
+    const int k = (int)(ctx->feed_seq & 1);
+    if (ctx->feed[k].pending) { fail(ctx, SPH_ERR_STATE, "sph_pack_coords_async: two frames in flight, collect one with sph_coords_wait"); return -SPH_ERR_STATE; }
+    auto bail = [&](cudaError_t e) { snprintf(ctx->err, sizeof ctx->err, "pack_coords_async: %s", cudaGetErrorString(e)); return -SPH_ERR_CUDA; };
+    cudaError_t e;
+    // one device-side buffer: the copy of the frame before must have drained before it is packed again
+    if (ctx->feed[k ^ 1].pending && (e = cudaStreamWaitEvent(ctx->stream, ctx->feed[k ^ 1].copied, 0))) return bail(e);
+    if ((e = cudaMemsetAsync(ctx->counters + CN_COORDS, 0, sizeof(int), ctx->stream))) return bail(e);
+    SPH_LAUNCH(k_pack_coords, ctx->grid, ctx->stream)(ctx->dp, ctx->counters, dpos, duid, ctx->coords, ctx->cfg.capacity);
+    ctx->launches++;
+    // the counters as they stand now (the next frame's sorts will rewrite them while the copy is still running)
+    if ((e = cudaMemcpyAsync(ctx->feed_cnt_dev + k * CN_COUNT, ctx->counters, CN_COUNT * sizeof(int), cudaMemcpyDeviceToDevice, ctx->stream))) return bail(e);
+    if ((e = cudaEventRecord(ctx->feed[k].packed, ctx->stream))) return bail(e);
+    if ((e = cudaStreamWaitEvent(ctx->copy_stream, ctx->feed[k].packed, 0))) return bail(e);
+    // how many entries to bring over is not known on the host without a synchronisation: a single slab keeps
+    // the count of its upload; a slab among others may have gained particles, so its whole buffer travels
+    const int entries = std::min(cap, ctx->cfg.nranks == 1 ? ctx->n_uploaded : ctx->cfg.capacity);
+    if ((e = cudaMemcpyAsync(ctx->feed_cnt_host + k * CN_COUNT, ctx->feed_cnt_dev + k * CN_COUNT, CN_COUNT * sizeof(int), cudaMemcpyDeviceToHost, ctx->copy_stream))) return bail(e);
+    if (entries > 0 && (e = cudaMemcpyAsync(xy, ctx->coords, (size_t)entries * sizeof(short2), cudaMemcpyDeviceToHost, ctx->copy_stream))) return bail(e);
+    if ((e = cudaEventRecord(ctx->feed[k].copied, ctx->copy_stream))) return bail(e);
+    ctx->feed[k].cap = cap;
+    ctx->feed[k].pending = true;
+    ctx->feed_seq++;
+    return k;
+}
+
+// Collect a ticket: blocks until that frame's coordinates are in `xy`; returns the number of particles (like
+// sph_pack_coords: the count, of which min(count, cap) were written) or <0.
+extern "C" int sph_coords_wait(sph_ctx *ctx, int ticket)
+{
+    if (!ctx || ticket < 0 || ticket > 1) return -SPH_ERR_ARG;
+    if (!ctx->feed[ticket].pending) { fail(ctx, SPH_ERR_STATE, "sph_coords_wait: no such frame in flight"); return -SPH_ERR_STATE; }
+    cudaError_t e = cudaEventSynchronize(ctx->feed[ticket].copied);
+    ctx->feed[ticket].pending = false;
+    if (e) { snprintf(ctx->err, sizeof ctx->err, "coords_wait: %s", cudaGetErrorString(e)); return -SPH_ERR_CUDA; }
+    return ctx->feed_cnt_host[ticket * CN_COUNT + CN_NLOCAL];
+}
+
 extern "C" int sph_pack_coords(sph_ctx *ctx, int16_t *xy, int cap)
 {
     if (!ctx || !xy) return -SPH_ERR_ARG;
@@ -665,6 +736,9 @@ extern "C" int sph_pack_coords(sph_ctx *ctx, int16_t *xy, int cap)
     if (current_arrays(ctx, &dpos, &dq, &duid, &q_is_prev)) return -SPH_ERR_STATE;
     auto bail = [&](cudaError_t e) { snprintf(ctx->err, sizeof ctx->err, "pack_coords: %s", cudaGetErrorString(e)); return -SPH_ERR_CUDA; };
     cudaError_t e;
+    // frames of the asynchronous feed still draining read the same device buffer
+    for (int k = 0; k < 2; k++)
+        if (ctx->feed[k].pending && (e = cudaEventSynchronize(ctx->feed[k].copied))) return bail(e);
     if ((e = cudaMemsetAsync(ctx->counters + CN_COORDS, 0, sizeof(int), ctx->stream))) return bail(e);
     SPH_LAUNCH(k_pack_coords, ctx->grid, ctx->stream)(ctx->dp, ctx->counters, dpos, duid, ctx->coords, ctx->cfg.capacity);
     ctx->launches++;
@@ -691,6 +765,17 @@ extern "C" int sph_run_frame(sph_ctx *ctx, const sph_tunable *t, int steps, int1
     int c[CN_COUNT];
     if ((rc = read_counters(ctx, c))) return -rc;
     return c[CN_NLOCAL];
+}
+
+// sph_run_frame without the wait at its end: returns a ticket for sph_coords_wait
+extern "C" int sph_run_frame_async(sph_ctx *ctx, const sph_tunable *t, int steps, int16_t *xy, int cap)
+{
+    if (!ctx || steps < 1 || !xy) return -SPH_ERR_ARG;
+    int rc;
+    if ((rc = sph_step(ctx, steps - 1))) return -rc;
+    if (t && (rc = sph_queue_params(ctx, t))) return -rc;
+    if ((rc = sph_step(ctx, 1))) return -rc;
+    return sph_pack_coords_async(ctx, xy, cap);
 }
 
 extern "C" int sph_get_cells(sph_ctx *ctx, uint32_t *uid, uint32_t *cell, int cap)

@@ -138,6 +138,14 @@ cudaError_t cudaGraphLaunch(cudaGraphExec_t e, cudaStream_t s)
     return cudaSuccess;
 }
 
+struct emu_event { int unused; };
+cudaError_t cudaEventCreateWithFlags(cudaEvent_t *e, unsigned) { *e = new emu_event{0}; return cudaSuccess; }
+cudaError_t cudaEventDestroy(cudaEvent_t e) { delete e; return cudaSuccess; }
+cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t s) { return !e || (s && s->capturing) ? cudaErrorInvalidValue : cudaSuccess; }
+cudaError_t cudaEventSynchronize(cudaEvent_t e) { return e ? cudaSuccess : cudaErrorInvalidValue; }
+cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t e, unsigned) { return e ? cudaSuccess : cudaErrorInvalidValue; }
+cudaError_t cudaFreeHost(void *p) { free(p); return cudaSuccess; }
+
 // device memory: filled with a poison pattern, because cudaMalloc does not zero either
 cudaError_t emu_malloc(void **p, size_t bytes)
 {

@@ -175,7 +175,18 @@ cudaError_t cudaGraphInstantiate(cudaGraphExec_t *e, cudaGraph_t g, unsigned lon
 cudaError_t cudaGraphDestroy(cudaGraph_t g);
 cudaError_t cudaGraphExecDestroy(cudaGraphExec_t e);
 cudaError_t cudaGraphLaunch(cudaGraphExec_t e, cudaStream_t s);
+// events: every stream of the emulator is synchronous, so an event has nothing to remember
+struct emu_event;
+typedef emu_event *cudaEvent_t;
+enum { cudaEventDisableTiming = 2 };
+cudaError_t cudaEventCreateWithFlags(cudaEvent_t *e, unsigned flags);
+cudaError_t cudaEventDestroy(cudaEvent_t e);
+cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t s);
+cudaError_t cudaEventSynchronize(cudaEvent_t e);
+cudaError_t cudaStreamWaitEvent(cudaStream_t s, cudaEvent_t e, unsigned flags);
 cudaError_t emu_malloc(void **p, size_t bytes);
+template <class T> static inline cudaError_t cudaMallocHost(T **p, size_t bytes) { return emu_malloc((void **)p, bytes); }
+cudaError_t cudaFreeHost(void *p);
 template <class T> static inline cudaError_t cudaMalloc(T **p, size_t bytes) { return emu_malloc((void **)p, bytes); }
 cudaError_t cudaFree(void *p);
 cudaError_t cudaMemset(void *p, int v, size_t bytes);
