@@ -17,17 +17,52 @@ static thread_local ucontext_t main_ctx;
 static thread_local const std::function<void()> *body_now = nullptr;
 static thread_local int last_error = cudaSuccess;
 
-void yield()
+// Fiber switch.  x86-64: callee-saved registers + stack pointer, no system call (swapcontext saves and restores
+// the signal mask with two of them per switch, which was a quarter of the suite's run time); elsewhere ucontext.
+#if defined(__x86_64__)
+extern "C" void emu_switch(void **save_sp, void *load_sp);
+asm(".text\n.globl emu_switch\n.type emu_switch,@function\nemu_switch:\n"
+    "  pushq %rbp\n  pushq %rbx\n  pushq %r12\n  pushq %r13\n  pushq %r14\n  pushq %r15\n"
+    "  movq %rsp, (%rdi)\n  movq %rsi, %rsp\n"
+    "  popq %r15\n  popq %r14\n  popq %r13\n  popq %r12\n  popq %rbx\n  popq %rbp\n  ret\n"
+    ".size emu_switch, .-emu_switch\n");
+static thread_local void *main_sp = nullptr;
+static thread_local std::vector<void *> fiber_sp;
+static void to_main() { emu_switch(&fiber_sp[cur->tid.x], main_sp); }
+static void to_fiber(int t) { emu_switch(&main_sp, fiber_sp[t]); }
+static void trampoline();
+static void prepare(int t)
 {
-    Fiber *f = cur;
-    swapcontext(&f->ctx, &main_ctx);
+    // a frame that emu_switch "returns" into: six zeroed registers, then the entry point; the stack pointer is
+    // 8 modulo 16 when trampoline starts, as after a call
+    void **top = (void **)(((uintptr_t)stacks[t] + kStack) & ~(uintptr_t)15);
+    top[-2] = (void *)trampoline;
+    for (int k = 3; k <= 8; k++) top[-k] = nullptr;
+    fiber_sp[t] = (void *)(top - 8);
 }
+#else
+static void to_main() { swapcontext(&cur->ctx, &main_ctx); }
+static void to_fiber(int t) { swapcontext(&main_ctx, &fibers[t].ctx); }
+static void trampoline();
+static void prepare(int t)
+{
+    Fiber &f = fibers[t];
+    getcontext(&f.ctx);
+    f.ctx.uc_stack.ss_sp = stacks[t];
+    f.ctx.uc_stack.ss_size = kStack;
+    f.ctx.uc_link = nullptr;
+    makecontext(&f.ctx, trampoline, 0);
+}
+#endif
+
+void yield() { to_main(); }
 
 static void trampoline()
 {
     (*body_now)();
     cur->done = true;
-    swapcontext(&cur->ctx, &main_ctx);
+    to_main();
+    abort();        // a finished fiber is never resumed
 }
 
 static void run_grid(int grid, int threads, const std::function<void()> &body)
@@ -36,6 +71,9 @@ static void run_grid(int grid, int threads, const std::function<void()> &body)
     if ((int)fibers.size() < threads) {
         fibers.resize(threads);
         while ((int)stacks.size() < threads) stacks.push_back((char *)malloc(kStack));
+#if defined(__x86_64__)
+        fiber_sp.resize(threads);
+#endif
     }
     body_now = &body;
     grid_dim = uint3{(unsigned)grid, 1, 1};
@@ -45,14 +83,9 @@ static void run_grid(int grid, int threads, const std::function<void()> &body)
         memset(&blk, 0, sizeof blk);
         blk.nthreads = threads;
         for (int t = 0; t < threads; t++) {
-            Fiber &f = fibers[t];
-            f.tid = uint3{(unsigned)t, 0, 0};
-            f.done = false;
-            getcontext(&f.ctx);
-            f.ctx.uc_stack.ss_sp = stacks[t];
-            f.ctx.uc_stack.ss_size = kStack;
-            f.ctx.uc_link = nullptr;
-            makecontext(&f.ctx, trampoline, 0);
+            fibers[t].tid = uint3{(unsigned)t, 0, 0};
+            fibers[t].done = false;
+            prepare(t);
         }
         int alive = threads;
         long long rounds = 0;
@@ -61,7 +94,7 @@ static void run_grid(int grid, int threads, const std::function<void()> &body)
             for (int t = 0; t < threads; t++) {
                 if (fibers[t].done) continue;
                 cur = &fibers[t];
-                swapcontext(&main_ctx, &cur->ctx);
+                to_fiber(t);
                 alive += !fibers[t].done;
             }
             if (++rounds > 100000000ll) { fprintf(stderr, "emu: block %d never finished (barrier not reached by all threads?)\n", b); abort(); }
