@@ -47,7 +47,6 @@ from test_gpu_parity import (  # noqa: E402,F401
 )
 
 
-@pytest.mark.skipif(not os.environ.get("SPH_EMU_LONG"), reason="50 s: set SPH_EMU_LONG=1 (the oracle and GPU suites run it)")
 def test_long_run_statistics_goo_with_stabilised_viscosity(built_lib):
     gpu.test_long_run_statistics_goo_with_stabilised_viscosity(built_lib)
 
