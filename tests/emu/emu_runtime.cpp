@@ -4,6 +4,8 @@
 
 #include <stdio.h>
 
+#include <algorithm>
+
 namespace emu {
 
 thread_local Fiber *cur = nullptr;
@@ -78,7 +80,24 @@ static void run_grid(int grid, int threads, const std::function<void()> &body)
     body_now = &body;
     grid_dim = uint3{(unsigned)grid, 1, 1};
     block_dim = uint3{(unsigned)threads, 1, 1};
-    for (int b = 0; b < grid; b++) {
+    // SPH_EMU_ORDER=reverse | shuffle: blocks (and the threads inside them) run in another order, so atomics hand out
+    // their slots differently -- what a result must not depend on (tests/test_emu_parity.py)
+    const char *order = getenv("SPH_EMU_ORDER");
+    const int mode = !order ? 0 : (order[0] == 'r' ? 1 : 2);
+    static thread_local unsigned long long lcg = 88172645463325252ull;
+    std::vector<int> border(grid), torder(threads);
+    for (int b = 0; b < grid; b++) border[b] = mode == 1 ? grid - 1 - b : b;
+    for (int t = 0; t < threads; t++) torder[t] = mode == 1 ? threads - 1 - t : t;
+    auto shuffle = [&](std::vector<int> &v) {
+        for (int k = (int)v.size() - 1; k > 0; k--) {
+            lcg = lcg * 6364136223846793005ull + 1442695040888963407ull;
+            std::swap(v[k], v[(int)((lcg >> 33) % (unsigned)(k + 1))]);
+        }
+    };
+    if (mode == 2) shuffle(border);
+    for (int bi = 0; bi < grid; bi++) {
+        const int b = border[bi];
+        if (mode == 2) shuffle(torder);
         block_idx = uint3{(unsigned)b, 0, 0};
         memset(&blk, 0, sizeof blk);
         blk.nthreads = threads;
@@ -91,7 +110,8 @@ static void run_grid(int grid, int threads, const std::function<void()> &body)
         long long rounds = 0;
         while (alive > 0) {
             alive = 0;
-            for (int t = 0; t < threads; t++) {
+            for (int ti = 0; ti < threads; ti++) {
+                const int t = torder[ti];
                 if (fibers[t].done) continue;
                 cur = &fibers[t];
                 to_fiber(t);
