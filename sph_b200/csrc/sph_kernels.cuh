@@ -273,7 +273,8 @@ k_advect(const DevParams *__restrict__ Pp, int *__restrict__ counters,
                 vv = sub2(vv, pk2(fminf(fmaxf(i1.x, -2.5f), 2.5f), fminf(fmaxf(i1.y, -2.5f), 2.5f)));
             }
             { const float2 v2 = unpk2(vv); vx = v2.x; vy = v2.y; }
-            for (; j < je; j++) {
+#pragma unroll 1
+            for (; j < je; j++) {      // at most one left over
 #else
 #pragma unroll kGatherUnroll
             for (int j = R.b[d]; j < R.e[d]; j++) {
@@ -386,7 +387,8 @@ k_coupling(const DevParams *__restrict__ Pp, const int *__restrict__ counters,
                 c += (r20 <= h2 && uu.x > 0.0f) ? cj.x : 0.0f;
                 c += (r21 <= h2 && uu.y > 0.0f) ? cj.y : 0.0f;
             }
-            for (; j < je; j++) {
+#pragma unroll 1
+            for (; j < je; j++) {      // at most one left over
 #else
 #pragma unroll kGatherUnroll
             for (int j = R.b[d]; j < R.e[d]; j++) {
@@ -761,7 +763,8 @@ k_density(const DevParams *__restrict__ Pp, int *__restrict__ counters,
                     d += ww.y;
                     dn = fmaf(ww.y, w1, dn);
                 }
-                for (; j < je; j++) {
+#pragma unroll 1
+                for (; j < je; j++) {      // at most one left over
 #else
 #pragma unroll kGatherUnroll
                 for (int j = jb; j < je; j++) {
