@@ -240,7 +240,8 @@ def main_ours(args):
             sim = SingleGpu(sph_b200, prob, t, stream, args)
         else:
             from sph_b200.slab import SlabRunner
-            sim = SlabRunner(prob, t, rank, world, stream, capacity_factor=2.0, balance_policy=args.balance)
+            sim = SlabRunner(prob, t, rank, world, stream, capacity_factor=2.0, balance_policy=args.balance,
+                             halo_width=args.halo_width)
         if args.visc_stab > 0.0:
             sim.ctx.set_viscosity_stabilisation(args.visc_stab)
         mark("created")
@@ -333,6 +334,7 @@ def main_ours(args):
                 "stage_ms": stage_ms,
                 "step_hbm_frac": step_gbs / peak,
                 "parallelism": f"slab{world}",
+                "exchanges_per_step": getattr(sim, "exchanges", None),
                 "edge_policy": ("particle count, dead band 1/15 (renderer.c:427-477)" if args.balance == "count" else
                                 "work estimate per slab (sph_copy_load), dead band 1/40 -- NOT the reference's policy") if world > 1 else None,
                 "per_slab_[n_local,n_ghost,neighbours,gather_us,sort_us]": per_rank,
@@ -499,6 +501,8 @@ def main():
     ap.add_argument("--preroll", type=int, default=1000, help="untimed steps before warm-up (state preparation)")
     ap.add_argument("--water-frac", type=float, default=0.5)
     ap.add_argument("--preset", default="x")
+    ap.add_argument("--halo-width", type=float, default=None,
+                    help="ghost-layer width in h at N > 1 (default: the build's, 2; the one-exchange build: 3.5, 4.5 with --visc-stab)")
     ap.add_argument("--visc-stab", type=float, default=0.0, metavar="GAMMA",
                     help="optional stabilised viscosity gather (needed for --preset y, DESIGN.md 5b); 0 = plain gather (default)")
     ap.add_argument("--cpu-steps", type=int, default=20, help="timed steps of the cpu_baseline sample")

@@ -194,6 +194,10 @@ int sph_step(sph_ctx *ctx, int n);
  * which = 0: after advect (migrants + predicted-position halo), 1: after relax (pos+vel halo). */
 int sph_exchange_buffers(sph_ctx *ctx, int which, void **send_left, void **recv_left,
                          void **send_right, void **recv_right, size_t *bytes);
+/* Exchanges per step of this build: 2 (which = 0 after sph_advect, which = 1 after sph_relax), or 1 for the
+ * one-exchange build variant (-DSPH_ONE_EXCHANGE=1), whose ghosts are relaxed redundantly and which needs
+ * halo_width >= 3 (4 with the stabilised viscosity gather); the driver then skips the which = 1 transfer. */
+int sph_exchanges_per_step(void);
 /* Mark a neighbour as absent for the coming sort (edge slabs): its recv buffer is ignored. */
 int sph_set_neighbors(sph_ctx *ctx, int has_left, int has_right);
 

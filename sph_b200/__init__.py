@@ -62,6 +62,7 @@ C_ABI_SYMBOLS = (
     "sph_set_neighbors", "sph_get_cells", "sph_get_pairs", "sph_get_forward_counts",
     "sph_pack_coords", "sph_launch_count", "sph_run_frame", "sph_p2p_local_handle", "sph_p2p_connect", "sph_copy_n_local", "sph_copy_load", "sph_init_lattice",
     "sph_set_viscosity_stabilisation", "sph_pack_coords_async", "sph_coords_wait", "sph_run_frame_async",
+    "sph_exchanges_per_step",
 )
 
 _lib = None
@@ -223,6 +224,10 @@ class Context:
         s = Status()
         self._ck(self.L.sph_get_status(self.h, C.byref(s)), "sph_get_status")
         return s
+
+    @property
+    def exchanges_per_step(self):
+        return int(self.L.sph_exchanges_per_step())
 
     def exchange_pointers(self, which):
         """Device pointers (send_left, recv_left, send_right, recv_right) and message bytes."""

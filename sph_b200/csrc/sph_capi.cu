@@ -124,7 +124,9 @@ extern "C" int sph_create(const sph_config *cfg, sph_ctx **out)
     memset(ctx, 0, sizeof *ctx);
     *out = ctx;
     ctx->cfg = *cfg;
-    if (ctx->cfg.halo_width <= 0.0f) ctx->cfg.halo_width = 2.0f;
+    if (ctx->cfg.halo_width <= 0.0f) ctx->cfg.halo_width = SPH_ONE_EXCHANGE ? 3.5f : 2.0f;
+    if (SPH_ONE_EXCHANGE && cfg->nranks > 1 && ctx->cfg.halo_width < 3.0f)
+        return fail(ctx, SPH_ERR_ARG, "one-exchange build: the ghost layer must be at least 3 h wide (4 h with the stabilised viscosity gather)");
     if (ctx->cfg.msg_capacity <= 0) ctx->cfg.msg_capacity = 1;
     int ndev = 0;
     CK(cudaGetDeviceCount(&ndev));
@@ -305,6 +307,10 @@ extern "C" int sph_exchange_buffers(sph_ctx *ctx, int which, void **sl, void **r
     return SPH_OK;
 }
 
+// how often neighbours meet per step in this build: 2 (after the prediction and after the relaxation), or 1 in the
+// one-exchange build, where a multi-rank driver skips the second transfer
+extern "C" int sph_exchanges_per_step(void) { return SPH_ONE_EXCHANGE ? 1 : 2; }
+
 // ------------------------------------------------------------------------------------------
 // peer-memory exchange: neighbours map each other's exchange block (cudaIpc) and the pack code in
 // k_advect / k_relax stores outgoing records straight into it over NVLink
@@ -352,7 +358,8 @@ static int launch_sort(sph_ctx *ctx, int which, bool with_unpack = true)
     float2 *dp = which == 0 ? ctx->P[2] : ctx->P[0];
     float2 *dq = which == 0 ? ctx->Q[1] : ctx->Q[0];
     uint32_t *du = which == 0 ? ctx->U[1] : ctx->U[0];
-    if (ctx->cfg.nranks > 1 && with_unpack) {
+    // (one-exchange build: nothing arrives after the relaxation, the ghosts were relaxed here)
+    if (ctx->cfg.nranks > 1 && with_unpack && !(SPH_ONE_EXCHANGE && which == 1)) {
         SPH_LAUNCH(k_unpack, ctx->unpack_grid, ctx->stream)(ctx->dp, ctx->counters, which, ctx->send[0], ctx->send[1],
                                                              ctx->recv[0], ctx->recv[1],
                                                              sp, sq, su, ctx->cnt, ctx->t_key, ctx->t_slot);
@@ -510,7 +517,7 @@ extern "C" int sph_step(sph_ctx *ctx, int n)
             ctx->graph_ready[m] = true;
         }
         CK(cudaGraphLaunch(ctx->graph[m], ctx->stream));
-        ctx->launches += (ctx->cfg.nranks > 1 ? 13 : 11) + m;
+        ctx->launches += (ctx->cfg.nranks > 1 ? (SPH_ONE_EXCHANGE ? 12 : 13) : 11) + m;
         ctx->steps++;
     }
     return SPH_OK;

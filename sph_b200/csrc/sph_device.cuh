@@ -69,8 +69,16 @@ enum {
 // over the dam-break's states, i.e. about 14 neighbour-equivalents per entry.
 #define SPH_COST_BASE 14
 
+// SPH_ONE_EXCHANGE=1 (build variant, emulator-checked, not yet timed): neighbours meet ONCE per step.  The ghosts
+// of exchange 0 carry x_prev as well, the ghost layer is >= 3h wide, and k_relax relaxes the ghosts redundantly
+// (those within layer - 2h of the edge come out exactly as on their owner: same neighbours, same order), so the
+// next k_advect has its neighbours' velocities without the second message.
+#ifndef SPH_ONE_EXCHANGE
+#define SPH_ONE_EXCHANGE 0
+#endif
+
 // neighbour message: 16-byte header {n_migrants, n_halo, 0, 0} then SoA sections sized by msg_cap
-__host__ __device__ inline size_t msg_bytes_full(int m) { return 16 + (size_t)m * 32; }
+__host__ __device__ inline size_t msg_bytes_full(int m) { return 16 + (size_t)m * (SPH_ONE_EXCHANGE ? 40 : 32); }
 __host__ __device__ inline size_t msg_bytes_halo1(int m) { return 16 + (size_t)m * 20; }
 __device__ __forceinline__ int *msg_hdr(unsigned char *b) { return (int *)b; }
 __device__ __forceinline__ float2 *msg_a(unsigned char *b) { return (float2 *)(b + 16); }                       // migrant pos / halo-1 pos
@@ -78,6 +86,7 @@ __device__ __forceinline__ float2 *msg_b(unsigned char *b, int m) { return (floa
 __device__ __forceinline__ uint32_t *msg_u(unsigned char *b, int m) { return (uint32_t *)(b + 16 + (size_t)m * 16); }
 __device__ __forceinline__ float2 *msg_hp(unsigned char *b, int m) { return (float2 *)(b + 16 + (size_t)m * 20); } // halo-0 pos
 __device__ __forceinline__ uint32_t *msg_hu(unsigned char *b, int m) { return (uint32_t *)(b + 16 + (size_t)m * 28); }
+__device__ __forceinline__ float2 *msg_hq(unsigned char *b, int m) { return (float2 *)(b + 16 + (size_t)m * 32); } // halo-0 x_prev (one-exchange build)
 
 // Exchange block of one rank (peer-memory mode): 4 arrival flags, then one message buffer per
 // (side it arrives from, which exchange, step parity).  Double buffering by step parity is enough:

@@ -140,6 +140,9 @@ __device__ __forceinline__ void send_messages(const DevParams &P, int *counters,
             copy_words(remote, local[s], 16 + (size_t)m * 16, n_mig, gtid, gstride, wrote);         // migrant uid
             copy_words(remote, local[s], 16 + (size_t)m * 20, n_halo * 2, gtid, gstride, wrote);    // ghost pos
             copy_words(remote, local[s], 16 + (size_t)m * 28, n_halo, gtid, gstride, wrote);        // ghost uid
+#if SPH_ONE_EXCHANGE
+            copy_words(remote, local[s], 16 + (size_t)m * 32, n_halo * 2, gtid, gstride, wrote);    // ghost x_prev
+#endif
         } else {
             copy_words(remote, local[s], 16, n_halo * 2, gtid, gstride, wrote);                     // ghost pos
             copy_words(remote, local[s], 16 + (size_t)m * 8, n_halo * 2, gtid, gstride, wrote);     // ghost vel
@@ -323,12 +326,22 @@ k_advect(const DevParams *__restrict__ Pp, int *__restrict__ counters,
                 // ghost layer: widened to halo_w and tested per side (communication.c:137-140 uses h, else-if)
                 if (P.has_left && np.x - P.edge_start <= P.halo_w) {
                     int k = atomicAdd(&msg_hdr(send_l)[1], 1);
-                    if (k < P.msg_cap) { msg_hp(send_l, P.msg_cap)[k] = np; msg_hu(send_l, P.msg_cap)[k] = u; }
+                    if (k < P.msg_cap) {
+                        msg_hp(send_l, P.msg_cap)[k] = np; msg_hu(send_l, P.msg_cap)[k] = u;
+#if SPH_ONE_EXCHANGE
+                        msg_hq(send_l, P.msg_cap)[k] = p;
+#endif
+                    }
                     else atomicAdd(&counters[CN_MSG_OVER], 1);
                 }
                 if (P.has_right && P.edge_end - np.x <= P.halo_w) {
                     int k = atomicAdd(&msg_hdr(send_r)[1], 1);
-                    if (k < P.msg_cap) { msg_hp(send_r, P.msg_cap)[k] = np; msg_hu(send_r, P.msg_cap)[k] = u; }
+                    if (k < P.msg_cap) {
+                        msg_hp(send_r, P.msg_cap)[k] = np; msg_hu(send_r, P.msg_cap)[k] = u;
+#if SPH_ONE_EXCHANGE
+                        msg_hq(send_r, P.msg_cap)[k] = p;
+#endif
+                    }
                     else atomicAdd(&counters[CN_MSG_OVER], 1);
                 }
             }
@@ -480,7 +493,11 @@ k_unpack(const DevParams *__restrict__ Pp, int *__restrict__ counters, int which
         uint32_t u;
         if (which == 0 && !is_mig) {
             p = msg_hp(buf[s], P.msg_cap)[k];
+#if SPH_ONE_EXCHANGE
+            q = msg_hq(buf[s], P.msg_cap)[k];                           // the ghost will be relaxed here too
+#else
             q = make_float2(0.0f, 0.0f);
+#endif
             u = msg_hu(buf[s], P.msg_cap)[k] | SPH_HALO_BIT;
         } else {
             p = msg_a(buf[s])[k];
@@ -823,7 +840,11 @@ k_relax(const DevParams *__restrict__ Pp, int *__restrict__ counters,
 
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const uint32_t u = uid[i];
+#if SPH_ONE_EXCHANGE
+        const bool ghost = (u & SPH_HALO_BIT) != 0;     // relaxed redundantly and kept as a ghost for the coming k_advect
+#else
         if (u & SPH_HALO_BIT) { t_key[i] = SPH_KEY_DROP; continue; }
+#endif
         const float2 p = pos[i];
         const float2 di = dens[i];
         // fluid.c:563-564 + :591 with the constants folded.  With w = 1 - r/h the spring term is
@@ -947,6 +968,10 @@ k_relax(const DevParams *__restrict__ Pp, int *__restrict__ counters,
         const float2 v = make_float2(clamp5(__fdiv_rn(np.x - pv.x, dt)), clamp5(__fdiv_rn(np.y - pv.y, dt)));
         pos_out[i] = np;
         vel_out[i] = v;
+#if SPH_ONE_EXCHANGE
+        bin_position(i, np, ghost ? SPH_KEY_EMIG : 0, P, cnt, t_key, t_slot, counters);
+        continue;
+#endif
         if (P.nranks > 1) {
             if (P.has_left && np.x - P.edge_start <= P.halo_w) {
                 int k = atomicAdd(&msg_hdr(send_l)[1], 1);

@@ -37,7 +37,7 @@ class _CudaBytes:
 class SlabRunner:
     def __init__(self, prob, tunable, rank, world, stream=None, capacity_factor=2.0, backend=None,
                  msg_capacity=None, steps_per_frame=4, balance=True, group=None, transport="p2p",
-                 async_counts=True, balance_policy="count", cost_band_divisor=40.0):
+                 async_counts=True, balance_policy="count", cost_band_divisor=40.0, halo_width=None):
         import torch
         import torch.distributed as dist
         self.torch, self.dist = torch, dist
@@ -61,15 +61,18 @@ class SlabRunner:
         if backend is None:
             import sph_b200
             self.sph = sph_b200
+            # halo_width None: the build's default (2 h; 3.5 h for the one-exchange build, which needs 4.5 h with
+            # the stabilised viscosity gather)
             self.ctx = sph_b200.Context(prob["tank_w"], prob["tank_h"], prob["h"], self.capacity,
                                         msg_capacity=self.msg_capacity, device=torch.cuda.current_device(),
-                                        rank=rank, nranks=world,
+                                        rank=rank, nranks=world, halo_width=halo_width or 0.0,
                                         stream=stream.cuda_stream if stream is not None else None)
             self.cuda = True
         else:
             self.ctx = backend(prob["tank_w"], prob["tank_h"], prob["h"], self.capacity, self.msg_capacity, rank, world)
             self.cuda = False
         self.ctx.set_params(self.t)
+        self.exchanges = int(getattr(self.ctx, "exchanges_per_step", 2))     # 1: one-exchange build of the library
         self.has_left, self.has_right = rank > 0, rank < world - 1
         # "p2p": neighbours map each other's exchange block (cudaIpc) and the kernels store messages
         # straight into it over NVLink; "collective": torch.distributed send/recv moves the buffers
@@ -214,7 +217,8 @@ class SlabRunner:
         c.sort()
         c.density()
         c.relax()
-        self.exchange(1)
+        if self.exchanges == 2:
+            self.exchange(1)
         c.sort()
         if self.do_balance and self.cuda and self.async_counts and self.world > 1 and self.sub_step == self.steps_per_frame - 1:
             self.sample_counts_async()
@@ -234,7 +238,7 @@ class SlabRunner:
         names = ("advect", "exchange0", "sort1", "density", "relax", "exchange1", "sort2")
         acc = {k: 0.0 for k in names}
         c = self.ctx
-        x = (lambda w: None) if self.transport == "p2p" else self.exchange
+        x = (lambda w: None) if self.transport == "p2p" else (lambda w: self.exchange(w) if w < self.exchanges else None)
         for _ in range(nsteps):
             flush_buf.zero_()
             ev = [torch.cuda.Event(enable_timing=True) for _ in range(8)]

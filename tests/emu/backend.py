@@ -9,17 +9,24 @@ import numpy as np
 
 
 def use_emulator():
-    """Point sph_b200's binding at the emulator library for THIS process (tests only)."""
+    """Point sph_b200's binding at the emulator library for THIS process (tests only).  SPH_EMU_DEFINES selects a
+    build-flag variant of the kernels, e.g. "SPH_ONE_EXCHANGE=1" or "SPH_PACKED=1 SPH_ONE_EXCHANGE=1"."""
+    import os
     import sph_b200
     from .build_emu import build
-    sph_b200._lib = sph_b200._bind(C.CDLL(build()))
+    defines = tuple(os.environ.get("SPH_EMU_DEFINES", "").split())
+    name = "libsph_emu" + "".join("_" + d.replace("=", "") for d in defines).lower() + ".so"
+    sph_b200._lib = sph_b200._bind(C.CDLL(build(defines=defines, name=name)))
     return sph_b200
 
 
 class EmuSlab:
     def __init__(self, tank_w, tank_h, h, capacity, msg_capacity, rank, nranks):
         sph = self.sph = use_emulator()
-        self.c = sph.Context(tank_w, tank_h, h, capacity, msg_capacity=msg_capacity, rank=rank, nranks=nranks)
+        import os
+        # ghost-layer width: the build's default (2 h, or 3.5 h for the one-exchange build) unless the test says otherwise
+        self.c = sph.Context(tank_w, tank_h, h, capacity, msg_capacity=msg_capacity, rank=rank, nranks=nranks,
+                             halo_width=float(os.environ.get("SPH_EMU_HALO_WIDTH", "0")))
         self._views = {}
 
     def _t(self, t):

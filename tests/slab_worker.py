@@ -62,7 +62,7 @@ def main():
     st = sim.ctx.status()
     np.savez(f"{out}.rank{rank}.npz", state=a, uid=uid, history=np.array(history, "f8"),
              overflow=np.array([st.capacity_overflow, st.msg_overflow]), edges=np.array(sim.edges, "f8"),
-             costs=np.array(sim.costs if sim.costs is not None else [], "f8"))
+             costs=np.array(sim.costs if sim.costs is not None else [], "f8"), exchanges=np.array([sim.exchanges]))
     dist.barrier()
     dist.destroy_process_group()
 

@@ -17,14 +17,16 @@ from test_gpu_parity import as_sph
 
 
 @pytest.fixture(autouse=True)
-def emulated_library(monkeypatch):
+def spin_timeout(monkeypatch):
     monkeypatch.setenv("SPH_SPIN_TIMEOUT_MS", "60000")
-    monkeypatch.setattr(sph_b200, "_lib", sph_b200._bind(C.CDLL(build_emu())))
     yield
 
 
-@pytest.mark.parametrize("world,goo", [(2, False), (3, True)])
-def test_peer_memory_slab_steps_equal_single_slab_bit_for_bit(built_lib, world, goo):
+@pytest.mark.parametrize("world,goo,one_exchange", [(2, False, False), (3, True, False), (3, False, True), (2, True, True)])
+def test_peer_memory_slab_steps_equal_single_slab_bit_for_bit(built_lib, monkeypatch, world, goo, one_exchange):
+    lib = build_emu(defines=("SPH_ONE_EXCHANGE=1",), name="libsph_emu_sph_one_exchange1.so") if one_exchange else build_emu()
+    monkeypatch.setattr(sph_b200, "_lib", sph_b200._bind(C.CDLL(lib)))
+    halo = (4.5 if goo else 3.5) if one_exchange else 2.0
     n_req, steps = 3000, 80
     tank_w = 15.0 * float(np.sqrt(n_req / 750.0))
     prob = make_problem(n_req, tank_w=tank_w, water_frac=0.5, nranks=world)
@@ -41,7 +43,8 @@ def test_peer_memory_slab_steps_equal_single_slab_bit_for_bit(built_lib, world, 
     for r in range(world):
         a, uid = lattice(prob, r)
         c = sph_b200.Context(prob["tank_w"], prob["tank_h"], prob["h"], 2 * len(a) + 4096, msg_capacity=2048,
-                             device=r, rank=r, nranks=world)
+                             device=r, rank=r, nranks=world, halo_width=halo)
+        assert c.exchanges_per_step == (1 if one_exchange else 2)
         if goo:
             c.set_viscosity_stabilisation(0.5)
         c.set_params(params(prob, r))

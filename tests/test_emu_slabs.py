@@ -64,3 +64,27 @@ def test_emulated_stabilised_viscosity_is_decomposition_independent(tmp_path, bu
     for f in ("x", "y", "v_x", "v_y"):
         assert np.array_equal(state[f][order].view("u4"), ref[f].view("u4")), f
     assert not np.array_equal(ref["x"].view("u4"), plain["x"].view("u4"))     # the pass did engage
+
+
+@pytest.mark.parametrize("config,world,n_req,steps,halo", [("emu", 3, 1500, 80, "0"), ("emu_block", 4, 12000, 40, "0"),
+                                                         ("emu_goo_stabilised", 3, 1500, 80, "4.5")])
+def test_one_exchange_build_equals_single_slab_bit_for_bit(tmp_path, built_lib, monkeypatch, config, world, n_req, steps, halo):
+    """-DSPH_ONE_EXCHANGE=1: neighbours meet once per step; the ghosts travel with x_prev in a >= 3 h layer and are
+    relaxed redundantly, so the next viscosity pass has their velocities without a second message.  Same bits as
+    one slab (and therefore as the two-exchange build), with the rebalancer moving the edges underneath."""
+    monkeypatch.setenv("SPH_EMU_DEFINES", "SPH_ONE_EXCHANGE=1")
+    monkeypatch.setenv("SPH_EMU_HALO_WIDTH", halo)
+    parts = run_world(tmp_path, world, n_req, steps, True, config)
+    assert all(int(p["exchanges"][0]) == 1 for p in parts), "the workers did not run the one-exchange build"
+    state = np.concatenate([p["state"] for p in parts]); uid = np.concatenate([p["uid"] for p in parts])
+    assert all(int(p["overflow"].sum()) == 0 for p in parts), [p["overflow"] for p in parts]
+    block, goo = "block" in config, "goo" in config
+    prob = make_problem(n_req, tank_w=15.0 * float(np.sqrt(n_req / 750.0)), water_frac=0.5) if block else make_problem(n_req)
+    t = default_tunable(prob["h"], prob["tank_w"], prob["tank_h"], preset="y" if goo else "x")
+    if block:
+        t.mover_center_x = 0.4 * prob["tank_w"]
+    ref, ru = emu_single(prob, t, steps, gamma=0.5 if goo else 0.0)
+    assert np.array_equal(np.sort(uid), ru), "particles lost or duplicated in migration"
+    order = np.argsort(uid)
+    for f in ("x", "y", "v_x", "v_y"):
+        assert np.array_equal(state[f][order].view("u4"), ref[f].view("u4")), f
