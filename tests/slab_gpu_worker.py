@@ -28,7 +28,9 @@ def main():
     t.mover_center_x = 0.4 * prob["tank_w"]          # in the path of the collapsing block
     stream = torch.cuda.Stream()
     with torch.cuda.stream(stream):
-        sim = SlabRunner(prob, t, rank, world, stream, transport=transport)
+        # (a one-exchange build of the library needs one more h of ghost layer with the stabilised gather)
+        halo = 4.5 if goo and sph_b200.lib().sph_exchanges_per_step() == 1 else None
+        sim = SlabRunner(prob, t, rank, world, stream, transport=transport, halo_width=halo)
         if goo:
             sim.ctx.set_viscosity_stabilisation(0.5)
         sim.init_lattice()
