@@ -44,6 +44,7 @@ from test_gpu_parity import (  # noqa: E402,F401
     test_stabilised_viscosity_engages_on_goo_and_leaves_stable_presets_bit_identical,
     test_stabilisation_threshold_selects_the_pass_per_parameter_block,
     test_asynchronous_coordinate_feed_equals_the_synchronous_one,
+    test_long_run_statistics_default,
 )
 
 
