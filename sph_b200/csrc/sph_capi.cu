@@ -35,6 +35,9 @@ struct sph_ctx {
     uint32_t *U[2];
     float2 *dens;
     sph_mask_t *nmask;               // SPH_NROWS x capacity: per-row acceptance masks from k_density for k_relax
+#if SPH_RELAX_PD4
+    float4 *pd;                      // (x, y, density, density_near) per entry: k_density -> k_relax
+#endif
     float *coupling;                 // per entry: sum of its pairs' viscosity coefficients (stabilised viscosity gather only)
     DevOptions *dopt;                // device copy of the optional-path parameters
     float visc_gamma, visc_min_dt_sigma;
@@ -148,6 +151,9 @@ extern "C" int sph_create(const sph_config *cfg, sph_ctx **out)
     for (int i = 0; i < 2; i++) CK(cudaMalloc(&ctx->U[i], cap * sizeof(uint32_t)));
     CK(cudaMalloc(&ctx->dens, cap * sizeof(float2)));
     CK(cudaMalloc(&ctx->nmask, SPH_NROWS * cap * sizeof(sph_mask_t)));
+#if SPH_RELAX_PD4
+    CK(cudaMalloc(&ctx->pd, cap * sizeof(float4)));
+#endif
     CK(cudaMalloc(&ctx->coupling, cap * sizeof(float)));
     CK(cudaMalloc(&ctx->dopt, sizeof(DevOptions)));
     CK(cudaMemset(ctx->dopt, 0, sizeof(DevOptions)));
@@ -224,6 +230,9 @@ extern "C" void sph_destroy(sph_ctx *ctx)
     cudaStreamSynchronize(ctx->stream);
     for (int m = 0; m < 2; m++) if (ctx->graph_ready[m]) cudaGraphExecDestroy(ctx->graph[m]);
     cudaFree(ctx->coupling); cudaFree(ctx->dopt);
+#if SPH_RELAX_PD4
+    cudaFree(ctx->pd);
+#endif
     if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
     for (int k = 0; k < 2; k++) {
         if (ctx->feed[k].packed) cudaEventDestroy(ctx->feed[k].packed);
@@ -411,7 +420,11 @@ static int launch_advect(sph_ctx *ctx)
 
 static int launch_density(sph_ctx *ctx)
 {
-    SPH_LAUNCH(k_density, ctx->grid, ctx->stream)(ctx->dp, ctx->counters, ctx->P[2], ctx->cell_start, ctx->dens, ctx->nmask);
+    SPH_LAUNCH(k_density, ctx->grid, ctx->stream)(ctx->dp, ctx->counters, ctx->P[2], ctx->cell_start, ctx->dens, ctx->nmask
+#if SPH_RELAX_PD4
+                                                   , ctx->pd
+#endif
+                                                   );
     ctx->launches++;
     CK(cudaGetLastError());
     return SPH_OK;
@@ -421,7 +434,11 @@ static int launch_relax(sph_ctx *ctx)
 {
     SPH_LAUNCH(k_relax, ctx->grid, ctx->stream)(ctx->dp, ctx->counters, ctx->P[2], ctx->Q[1], ctx->U[1], ctx->dens,
                                                         ctx->cell_start, ctx->nmask, ctx->P[3], ctx->Q[2], ctx->cnt, ctx->t_key,
-                                                        ctx->t_slot, ctx->send[0], ctx->send[1]);
+                                                        ctx->t_slot, ctx->send[0], ctx->send[1]
+#if SPH_RELAX_PD4
+                                                        , ctx->pd
+#endif
+                                                        );
     ctx->launches++;
     CK(cudaGetLastError());
     return SPH_OK;

@@ -34,6 +34,20 @@ constexpr int kGatherUnroll = SPH_UNROLL;     // (#pragma unroll takes a constan
 #ifndef SPH_PACKED_RELAX
 #define SPH_PACKED_RELAX 0
 #endif
+// SPH_RELAX_PD4=1: k_density also writes (x, y, density, density_near) as one 16-byte record per entry and
+// k_relax's neighbour walk reads that record: one load and one address per neighbour instead of two.  k_relax is
+// bound by load latency (profiles/r1_branchfree_full.csv), and its trip of two neighbours spends 23 of ~59
+// instructions on index arithmetic and loads.  Emulator-checked, not yet timed.
+#ifndef SPH_RELAX_PD4
+#define SPH_RELAX_PD4 0
+#endif
+#if SPH_RELAX_PD4
+#define SPH_PD4_PARAM , float4 *__restrict__ pd
+#define SPH_PD4_CPARAM , const float4 *__restrict__ pd
+#else
+#define SPH_PD4_PARAM
+#define SPH_PD4_CPARAM
+#endif
 constexpr int kPackedUnroll = SPH_UNROLL / 2 > 0 ? SPH_UNROLL / 2 : 1;
 #ifndef SPH_BLOCKS_ADVECT
 #define SPH_BLOCKS_ADVECT 4
@@ -729,7 +743,7 @@ k_reorder(const DevParams *__restrict__ Pp, int *__restrict__ counters, const in
 __global__ void __launch_bounds__(SPH_THREADS, SPH_BLOCKS_DENSITY)
 k_density(const DevParams *__restrict__ Pp, int *__restrict__ counters,
           const float2 *__restrict__ pos, const int *__restrict__ cell_start, float2 *__restrict__ dens,
-          sph_mask_t *__restrict__ nmask)
+          sph_mask_t *__restrict__ nmask SPH_PD4_PARAM)
 {
     const DevParams P = *Pp;
     const int n = counters[CN_NTOT];
@@ -805,6 +819,9 @@ k_density(const DevParams *__restrict__ Pp, int *__restrict__ counters,
             nn += sph_mask_popc(m) + max(e - b - SPH_MASK_BITS, 0);     // candidates past the mask count as accepted
         }
         dens[i] = make_float2(d, dn);
+#if SPH_RELAX_PD4
+        pd[i] = make_float4(p.x, p.y, d, dn);
+#endif
         // a forward list cannot exceed the full neighbour count: cheap, conservative detection
         // of the reference's 400-entry cap (hash.c:188,223)
         if (nn > 400) atomicAdd(&counters[CN_NEIGH_OVER], 1);
@@ -827,7 +844,7 @@ k_relax(const DevParams *__restrict__ Pp, int *__restrict__ counters,
         const sph_mask_t *__restrict__ nmask,
         float2 *__restrict__ pos_out, float2 *__restrict__ vel_out,
         int *__restrict__ cnt, int *__restrict__ t_key, int *__restrict__ t_slot,
-        unsigned char *send_l, unsigned char *send_r)
+        unsigned char *send_l, unsigned char *send_r SPH_PD4_CPARAM)
 {
     const DevParams P = *Pp;
     const int n = counters[CN_NTOT];
@@ -949,7 +966,13 @@ k_relax(const DevParams *__restrict__ Pp, int *__restrict__ counters,
                 const bool two = m != 0;
                 const int j1 = two ? b + sph_mask_ffs(m) - 1 : j0;
                 m &= m - 1;
+#if SPH_RELAX_PD4
+                const float4 r0 = pd[j0], r1 = pd[j1];
+                const float2 q0 = make_float2(r0.x, r0.y), d0 = make_float2(r0.z, r0.w);
+                const float2 q1 = make_float2(r1.x, r1.y), d1 = make_float2(r1.z, r1.w);
+#else
                 const float2 q0 = pos[j0], d0 = dens[j0], q1 = pos[j1], d1 = dens[j1];
+#endif
                 pair(j0, q0, d0);
                 if (two) pair(j1, q1, d1);
             }

@@ -42,6 +42,8 @@
 
 struct float2 { float x, y; };
 struct int4 { int x, y, z, w; };
+struct alignas(16) float4 { float x, y, z, w; };
+static inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
 struct short2 { short x, y; };
 struct uint3 { unsigned x, y, z; };
 static inline float2 make_float2(float x, float y) { return float2{x, y}; }

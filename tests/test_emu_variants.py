@@ -1,6 +1,7 @@
 """Build-flag variants of the kernels, checked in the kernel-source emulator (tests/emu) before they are ever
 timed on the B200.
 
+SPH_RELAX_PD4=1: k_relax's neighbour walk reads one 16-byte (x, y, density, density_near) record instead of two.
 SPH_PACKED=1 (+ SPH_PACKED_RELAX=1 for k_relax's pair physics): the candidate loops of k_advect / k_coupling /
 k_density take two candidates per trip with packed FP32 instructions (FADD2 / FMUL2 / FFMA2).  Every packed operation is the same round-to-nearest operation as its
 scalar counterpart and the order of every sum is kept, so in the emulator (where neither build contracts
@@ -37,7 +38,7 @@ def run(libpath, name, warm, steps, gamma, monkeypatch):
                                              ("goo_rect1508", 300, 0.5), ("gas1508", 200, 0.5)])
 def test_packed_fp32_variant_is_bit_identical_in_the_emulator(built_lib, monkeypatch, name, warm, gamma):
     base = build_emu()
-    packed = build_emu(defines=("SPH_PACKED=1", "SPH_PACKED_RELAX=1"), name="libsph_emu_packed.so")
+    packed = build_emu(defines=("SPH_PACKED=1", "SPH_PACKED_RELAX=1", "SPH_RELAX_PD4=1"), name="libsph_emu_packed.so")
     d0, a0 = run(base, name, warm, 12, gamma, monkeypatch)
     d1, a1 = run(packed, name, warm, 12, gamma, monkeypatch)
     for f in ("density", "density_near", "x", "y"):
