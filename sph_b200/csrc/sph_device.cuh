@@ -159,19 +159,7 @@ __device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 r; asm("mul.rn.f
 __device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
 __device__ __forceinline__ f32x2 ld2(const float2 *p) { return *reinterpret_cast<const f32x2 *>(p); }
 #else
-static inline float rcp_approx(float x) { return 1.0f / x; }
-struct f32x2 { float lo, hi; };
-static inline f32x2 pk2(float lo, float hi) { return f32x2{lo, hi}; }
-static inline float2 unpk2(f32x2 v) { return float2{v.lo, v.hi}; }
-static inline f32x2 add2(f32x2 a, f32x2 b) { return f32x2{a.lo + b.lo, a.hi + b.hi}; }
-static inline f32x2 sub2(f32x2 a, f32x2 b) { return f32x2{a.lo - b.lo, a.hi - b.hi}; }
-static inline f32x2 mul2(f32x2 a, f32x2 b) { return f32x2{a.lo * b.lo, a.hi * b.hi}; }
-static inline f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { return f32x2{fmaf(a.lo, b.lo, c.lo), fmaf(a.hi, b.hi, c.hi)}; }
-static inline f32x2 ld2(const float2 *p) { return f32x2{p->x, p->y}; }
-static inline int ld_acquire_sys(const int *p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
-static inline void st_release_sys(int *p, int v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
-static inline float rsqrt_approx(float x) { return 1.0f / sqrtf(x); }
-static inline float sqrt_approx(float x) { return sqrtf(x); }
+#include "sph_emu_ptx.h"      // tests/emu/fake/: host stand-ins for the helpers above (test infrastructure, not product code)
 #endif
 
 // hash_val (hash.c:35-47): IEEE fp32 divide, floor; kept as two coordinates

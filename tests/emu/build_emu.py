@@ -21,7 +21,7 @@ def build(force=False, defines=(), name="libsph_emu.so"):
     inc = os.path.join(ROOT, "include")
     cu = os.path.join(pkg, "csrc", "sph_capi.cu")
     hc = sorted(glob.glob(os.path.join(pkg, "host", "*.c")))
-    deps = [cu, os.path.join(HERE, "emu_runtime.cpp"), os.path.join(HERE, "fake", "cuda_runtime.h"), __file__] + hc + \
+    deps = [cu, os.path.join(HERE, "emu_runtime.cpp"), os.path.join(HERE, "fake", "cuda_runtime.h"), os.path.join(HERE, "fake", "sph_emu_ptx.h"), __file__] + hc + \
         glob.glob(os.path.join(pkg, "csrc", "*.cuh")) + glob.glob(os.path.join(inc, "*.h"))
     if not force and os.path.exists(OUT) and all(os.path.getmtime(d) <= os.path.getmtime(OUT) for d in deps):
         return OUT

@@ -1,0 +1,18 @@
+// TEST INFRASTRUCTURE -- NOT PART OF THE PRODUCT.  See cuda_runtime.h in this directory.
+// Host stand-ins for the PTX helpers of sph_b200/csrc/sph_device.cuh (included from there under SPH_EMU only):
+// IEEE operations in place of the MUFU approximations, a struct of two floats in place of a packed register pair,
+// GCC atomics in place of the system-scope acquire / release.
+#pragma once
+static inline float rcp_approx(float x) { return 1.0f / x; }
+struct f32x2 { float lo, hi; };
+static inline f32x2 pk2(float lo, float hi) { return f32x2{lo, hi}; }
+static inline float2 unpk2(f32x2 v) { return float2{v.lo, v.hi}; }
+static inline f32x2 add2(f32x2 a, f32x2 b) { return f32x2{a.lo + b.lo, a.hi + b.hi}; }
+static inline f32x2 sub2(f32x2 a, f32x2 b) { return f32x2{a.lo - b.lo, a.hi - b.hi}; }
+static inline f32x2 mul2(f32x2 a, f32x2 b) { return f32x2{a.lo * b.lo, a.hi * b.hi}; }
+static inline f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { return f32x2{fmaf(a.lo, b.lo, c.lo), fmaf(a.hi, b.hi, c.hi)}; }
+static inline f32x2 ld2(const float2 *p) { return f32x2{p->x, p->y}; }
+static inline int ld_acquire_sys(const int *p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
+static inline void st_release_sys(int *p, int v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
+static inline float rsqrt_approx(float x) { return 1.0f / sqrtf(x); }
+static inline float sqrt_approx(float x) { return sqrtf(x); }
