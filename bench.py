@@ -52,20 +52,35 @@ def measured_traffic(kernel, n_particles):
     return e["dram_bytes_per_launch"]
 
 
-def profiled_limiter(kernel, source="r1_branchfree_full.csv"):
+def profiled_limiter(kernel, source="r1_branchfree_full.csv", launch_seconds=None, sm_mhz=None, n_particles=None, sms=148):
     """What actually bounds `kernel` according to the last `ncu --set full` capture summarised under profiles/
     (NOT measured in this run): issue-slot utilisation, active lanes per instruction and DRAM throughput.  The
-    HBM roofline fraction is small because these gathers are instruction-issue bound."""
+    HBM roofline fraction is small because these gathers are instruction-issue bound.
+    `issue_roofline`: the second roof SURVEY.md 8(d) asks for -- the capture's warp-instruction count per launch
+    (valid for the particle count and state it was taken at) over THIS run's launch time, against
+    SMs x 4 schedulers x the SM clock sampled during this run."""
     import csv
     p = os.path.join(ROOT, "profiles", source)
     try:
         rows = list(csv.reader(open(p)))
-        col = rows[0].index(kernel.split("+")[0])
+        k = kernel.split("+")[0]
+        col = rows[0].index(k)
         get = lambda m: float(next(r[col] for r in rows if r[0] == m))
-        return {"issue_active_pct": get("smsp__issue_active.avg.pct_of_peak_sustained_active"),
-                "active_lanes_per_instruction": get("smsp__thread_inst_executed_per_inst_executed.ratio"),
-                "dram_pct_of_peak": get("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"),
-                "source": f"profiles/{source} (ncu capture of this build's kernels, not this run)"}
+        out = {"issue_active_pct": get("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+               "active_lanes_per_instruction": get("smsp__thread_inst_executed_per_inst_executed.ratio"),
+               "dram_pct_of_peak": get("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"),
+               "source": f"profiles/{source} (ncu capture of this build's kernels, not this run)"}
+        try:
+            t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(k)
+            if launch_seconds and sm_mhz and t and n_particles and abs(t["n_particles"] - n_particles) <= 0.02 * n_particles:
+                inst = get("smsp__inst_executed.sum")
+                peak = sms * 4 * sm_mhz * 1e6
+                out["issue_roofline"] = {"warp_instructions_per_launch": inst, "achieved": inst / launch_seconds, "peak": peak,
+                                         "unit": "warp-instructions/s", "frac": inst / launch_seconds / peak,
+                                         "note": "instruction count from the committed capture, launch time and SM clock from this run"}
+        except Exception:
+            pass
+        return out
     except Exception:       # a missing or reshaped summary must never cost the bench line
         return None
 
@@ -343,7 +358,8 @@ def main_ours(args):
                          "unit": "GB/s", "frac": achieved / peak,
                          "traffic": measured_traffic(sim.kernel_name(dom), n_per_launch), "peak_source": peak_kind,
                          "algorithmic_bytes_per_particle": ALG_BYTES[dom_key],
-                         "profiled_limiter": profiled_limiter(sim.kernel_name(dom))},
+                         "profiled_limiter": profiled_limiter(sim.kernel_name(dom), launch_seconds=stage_ms[dom] * 1e-3,
+                                                              sm_mhz=(clocks or {}).get("sm_mhz"), n_particles=n_per_launch)},
             "clocks": clocks,
             "e2e": {"value": n_global * e2e["steps"] / e2e["seconds"], "unit": "particle-steps/s",
                     "h2d_bytes_per_step": e2e["h2d_per_step"], "d2h_bytes_per_step": e2e["d2h_per_step"],
