@@ -47,7 +47,7 @@ def main():
     sim = SlabRunner(prob, t, rank, world, backend=backend, balance=bool(balance), balance_policy=policy)
     sim.init_lattice()
     history = []
-    elastic = len(sys.argv) > 5 and sys.argv[5] == "elastic"
+    elastic = len(sys.argv) > 5 and "elastic" in sys.argv[5]
     for s in range(steps):
         if elastic and s == 43:
             sim.remove_partition()          # last slab parked: it drains into its left neighbour

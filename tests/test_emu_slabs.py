@@ -88,3 +88,24 @@ def test_one_exchange_build_equals_single_slab_bit_for_bit(tmp_path, built_lib, 
     order = np.argsort(uid)
     for f in ("x", "y", "v_x", "v_y"):
         assert np.array_equal(state[f][order].view("u4"), ref[f].view("u4")), f
+
+
+@pytest.mark.parametrize("defines", ["", "SPH_ONE_EXCHANGE=1"])
+def test_emulated_partition_removed_and_added_back(tmp_path, built_lib, monkeypatch, defines):
+    """Runtime partition control on the CUDA source (controls.c:405-455): the last of three slabs is parked outside the
+    tank at step 43, drains through the migration path, and is added back at step 123 -- in the shipped build and in
+    the one-exchange build.  Nothing is lost and the result is the single-slab result bit for bit."""
+    monkeypatch.setenv("SPH_EMU_DEFINES", defines)
+    steps = 200
+    parts = run_world(tmp_path, 3, 1500, steps, True, "emu_elastic")
+    state = np.concatenate([p["state"] for p in parts]); uid = np.concatenate([p["uid"] for p in parts])
+    assert np.array_equal(np.sort(uid), np.arange(1508))
+    assert all(int(p["overflow"][0]) == 0 for p in parts), [p["overflow"] for p in parts]
+    drained = [h for h in parts[2]["history"] if h[0] == -1]
+    assert drained and drained[0][1] == 0, "the parked slab still held particles when it was added back"
+    assert len(parts[2]["uid"]) > 100, "the re-added slab did not refill"
+    prob = make_problem(1500)
+    ref, _ = emu_single(prob, default_tunable(prob["h"], prob["tank_w"], prob["tank_h"]), steps)
+    order = np.argsort(uid)
+    for f in ("x", "y", "v_x", "v_y"):
+        assert np.array_equal(state[f][order].view("u4"), ref[f].view("u4")), f
