@@ -444,6 +444,20 @@ static int launch_relax(sph_ctx *ctx)
     return SPH_OK;
 }
 
+// One-exchange build: an interior slab narrower than the ghost layer would leave its neighbours' layers incomplete
+// (a rank only sends its own particles).  The reference's balancer keeps slabs >= 2 h wide, which covers the 2 h
+// layer of the two-exchange build but not this one's.
+static int check_layer(sph_ctx *ctx)
+{
+#if SPH_ONE_EXCHANGE
+    if (ctx->hp.has_left && ctx->hp.has_right && ctx->hp.edge_end > ctx->hp.edge_start &&
+        ctx->hp.edge_end - ctx->hp.edge_start < ctx->hp.halo_w)
+        return fail(ctx, SPH_ERR_STATE, "one-exchange build: interior slab narrower than the ghost layer");
+#endif
+    (void)ctx;
+    return SPH_OK;
+}
+
 extern "C" int sph_advect(sph_ctx *ctx)
 {
     if (!ctx) return SPH_ERR_ARG;
@@ -455,6 +469,7 @@ extern "C" int sph_advect(sph_ctx *ctx)
         fill_edges(ctx, ctx->queued.node_start_x, ctx->queued.node_end_x);
         if ((rc = push_params(ctx))) return rc;
     }
+    if ((rc = check_layer(ctx))) return rc;
     if ((rc = launch_advect(ctx))) return rc;
     if (ctx->have_queued) {
         // ... then everything else, for the stages after the prediction
@@ -519,6 +534,7 @@ extern "C" int sph_step(sph_ctx *ctx, int n)
                 (rc = sph_relax(ctx)) || (rc = sph_sort(ctx))) return rc;
             continue;
         }
+        if ((rc = check_layer(ctx))) return rc;
         const int m = stabilised(ctx) ? 1 : 0;           // one captured step per variant of the viscosity gather
         if (!ctx->graph_ready[m]) {
             cudaGraph_t g;
