@@ -18,6 +18,7 @@ import pytest
 
 import sph_b200
 import test_gpu_parity as gpu
+import test_gpu_stabilised_and_feed as late
 from emu.build_emu import build as build_emu
 
 
@@ -40,16 +41,15 @@ from test_gpu_parity import (  # noqa: E402,F401
     test_pack_coords_matches_reference_formula,
     test_device_side_lattice_equals_host_lattice,
     test_mover_autopilot_and_preset_cycle,
+    test_long_run_statistics_default,
+)
+from test_gpu_stabilised_and_feed import (  # noqa: E402,F401
     test_stabilised_viscosity_rounding_level_agreement_with_gather_oracle,
     test_stabilised_viscosity_engages_on_goo_and_leaves_stable_presets_bit_identical,
     test_stabilisation_threshold_selects_the_pass_per_parameter_block,
+    test_long_run_statistics_goo_with_stabilised_viscosity,
     test_asynchronous_coordinate_feed_equals_the_synchronous_one,
-    test_long_run_statistics_default,
 )
-
-
-def test_long_run_statistics_goo_with_stabilised_viscosity(built_lib):
-    gpu.test_long_run_statistics_goo_with_stabilised_viscosity(built_lib)
 
 
 def test_full_size_properties_in_small(built_lib):
@@ -57,8 +57,8 @@ def test_full_size_properties_in_small(built_lib):
 
 
 def test_config4_properties_in_small(built_lib):
-    prob, b, n0, coords, per_frame = gpu.run_config4(6000, 32, 4)
-    gpu.check_config4(prob, b, n0, coords, per_frame, 4)
+    prob, b, n0, coords, per_frame = late.run_config4(6000, 32, 4)
+    late.check_config4(prob, b, n0, coords, per_frame, 4)
 
 
 def test_product_library_has_no_emulator_in_it(built_lib):

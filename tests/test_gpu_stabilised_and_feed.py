@@ -1,0 +1,176 @@
+"""GPU tests of what was written after round 1's GPU budget was spent: the stabilised viscosity gather
+(k_coupling + k_advect<true>), the asynchronous coordinate feed, and BASELINE config 4 at full size.  The same
+bodies have run on the kernel-source emulator (tests/test_emu_parity.py); this file sorts after the other GPU
+files so that a surprise on first hardware contact cannot mask the tests that were already green on the B200.
+Run on the B200 box: pytest -m gpu."""
+import numpy as np
+import pytest
+
+import parity_checks as pc
+from common import load_golden
+from oracle.oracle import lattice, make_problem
+from test_gpu_parity import Cuda, as_sph, make_oracle, mk
+
+pytestmark = pytest.mark.gpu
+
+# ---- the optional stabilised viscosity gather (sph_set_viscosity_stabilisation) ----
+GAMMA = 0.5
+
+
+def mk_stab(*a):
+    b = Cuda(*a)
+    b.c.set_viscosity_stabilisation(GAMMA)
+    return b
+
+
+def make_oracle_stab(*a):
+    o = make_oracle(*a)
+    o.set_viscosity_stabilisation(GAMMA)
+    return o
+
+
+@pytest.mark.parametrize("name,warm", [("goo_rect1508", 300), ("default1508", 400)])
+def test_stabilised_viscosity_rounding_level_agreement_with_gather_oracle(built_lib, name, warm):
+    """k_coupling + k_advect<true> against orc_g_set_viscosity_stabilisation: same algorithm, same order."""
+    pc.check_tight_vs_gather_oracle(mk_stab, make_oracle_stab, name, warm, steps=3)
+
+
+def test_stabilised_viscosity_engages_on_goo_and_leaves_stable_presets_bit_identical(built_lib):
+    """s_ij = 1 exactly wherever gamma * C <= 1: the default fluid, the block and the gas do not change by a bit
+    (graph and staged paths); goo does change."""
+    for name, warm, same in (("default1508", 400, True), ("block3000", 150, True), ("gas1508", 200, True),
+                             ("goo_rect1508", 300, False)):
+        z, t, tank_w, tank_h, h, _ = load_golden(name)
+        st = z[f"w{warm}_state"]
+        outs = []
+        for maker in (mk, mk_stab):
+            b = maker(tank_w, tank_h, h, len(st) + 64)
+            b.set_params(t); b.upload(st); b.step(20)
+            b.advect(); b.sort(); b.density(); b.relax(); b.sort()
+            outs.append(b.download()[0])
+        eq = all(np.array_equal(outs[0][f].view("u4"), outs[1][f].view("u4")) for f in ("x", "y", "v_x", "v_y"))
+        assert eq == same, name
+
+
+def test_stabilisation_threshold_selects_the_pass_per_parameter_block(built_lib):
+    """min_dt_sigma: the extra pass (one more launch per step) only runs for blocks with dt*sigma at or above
+    it -- goo 0.83, default fluid 0.17 -- and a preset change in mid-run switches it."""
+    import sph_b200
+    z, t, tank_w, tank_h, h, _ = load_golden("default1508")
+    st = z["w400_state"]
+    b = mk(tank_w, tank_h, h, len(st) + 64)
+    b.c.set_viscosity_stabilisation(GAMMA, 0.5)
+    b.set_params(t); b.upload(st)
+    n0 = b.launches; b.step(4); per_step_plain = (b.launches - n0) // 4
+    ts = as_sph(t)
+    sph_b200._host().sph_host_preset(sph_b200.C.byref(ts), b"y")
+    b.c.set_params(ts)
+    n0 = b.launches; b.step(4); per_step_goo = (b.launches - n0) // 4
+    assert per_step_goo == per_step_plain + 1
+    sph_b200._host().sph_host_preset(sph_b200.C.byref(ts), b"x")
+    b.c.set_params(ts)
+    n0 = b.launches; b.step(4)
+    assert (b.launches - n0) // 4 == per_step_plain
+
+
+def test_long_run_statistics_goo_with_stabilised_viscosity(built_lib):
+    """The goo preset (sigma 100, beta 10) settles to the reference's statistics with the stabilised gather;
+    with the plain gather it never settles (tests/test_oracle_gather.py pins that on the oracle)."""
+    a, _ = lattice(make_problem(1500))
+    from common import GOO_STABILISED_WIDEN
+    pc.check_long_run_statistics(mk_stab, "goo_rect1508", a, dens_make=make_oracle, widen=GOO_STABILISED_WIDEN)
+
+
+def run_config4(n_req, frames, frames_per_preset):
+    """BASELINE.json config 4: dam-break block, mover sphere on the render rank's autopilot path
+    (renderer.c:513-531) ploughing through the water, fluid presets cycled a -> b -> x -> y
+    (controls.c:344-401), one parameter block per frame landing in the last sub-step (fluid.c:293-294), the
+    stabilised viscosity gather engaging for the y phases only (dt*sigma >= 0.5)."""
+    import ctypes as C
+    import sph_b200
+    prob = sph_b200.make_problem(n_req, tank_w=15.0 * float(np.sqrt(n_req / 750.0)), water_frac=0.5)
+    ts = sph_b200.default_params(prob["h"], prob["tank_w"], prob["tank_h"])
+    b = sph_b200.Context(prob["tank_w"], prob["tank_h"], prob["h"], prob["n_global"] + 4096)
+    b.set_viscosity_stabilisation(GAMMA, 0.5)
+    b.set_params(ts)
+    n0 = b.init_lattice(prob)
+    L = sph_b200._host()
+    gl_x, direction = C.c_float(-0.9), C.c_int(1)
+    coords = np.zeros(2 * (n0 + 4096), "i2")
+    per_frame = []
+    for frame in range(frames):
+        L.sph_host_mover_autopilot(C.byref(ts), prob["tank_w"], prob["tank_h"], C.byref(gl_x), C.byref(direction))
+        L.sph_host_preset(C.byref(ts), "abxy"[(frame // frames_per_preset) % 4].encode())
+        before = b.launches
+        n = b.run_frame(ts, 4, coords)
+        per_frame.append(b.launches - before)
+        assert n == n0, (frame, n, n0)
+    return prob, b, n0, coords, per_frame
+
+
+def check_config4(prob, b, n0, coords, per_frame, frames_per_preset):
+    out, u = b.download()
+    assert np.array_equal(u, np.arange(n0, dtype=u.dtype))                           # nobody lost, nobody duplicated
+    assert np.all((out["x"] >= 0) & (out["x"] <= prob["tank_w"]) & (out["y"] >= 0) & (out["y"] <= prob["tank_h"]))
+    assert np.all(np.abs(out["v_x"]) <= 5.0) and np.all(np.abs(out["v_y"]) <= 5.0)   # fluid.c:613-625
+    assert np.all(np.isfinite(out["x"])) and np.all(np.isfinite(out["y"]))
+    s = b.status()
+    assert s.capacity_overflow == 0 and s.neighbor_overflow == 0 and s.n_local == n0 and s.n_halo == 0
+    # the coordinate feed is the reference's formula on the final state (fluid.c:358-361)
+    assert np.array_equal(coords[:2 * n0].reshape(n0, 2), b.pack_coords())
+    # The extra pass ran in the y phases only: one more launch per step there.  A frame whose block CHANGES the
+    # preset runs its last step with the old block's viscosity (the scatter lands after the prediction,
+    # fluid.c:279-310), so only frames inside a phase are counted.
+    plain = per_frame[1]
+    for f in range(1, len(per_frame)):
+        prev_y = "abxy"[((f - 1) // frames_per_preset) % 4] == "y"
+        this_y = "abxy"[(f // frames_per_preset) % 4] == "y"
+        if prev_y == this_y:
+            assert per_frame[f] == plain + (4 if this_y else 0), (f, per_frame)
+    assert any("abxy"[(f // frames_per_preset) % 4] == "y" for f in range(len(per_frame)))
+
+
+def test_config4_full_size_properties(built_lib):
+    """4 M particles (BASELINE.json config 4), 32 frames: size-independent properties only."""
+    prob, b, n0, coords, per_frame = run_config4(4_000_000, 32, 4)
+    check_config4(prob, b, n0, coords, per_frame, 4)
+
+
+def test_asynchronous_coordinate_feed_equals_the_synchronous_one(built_lib):
+    """sph_run_frame_async / sph_coords_wait (the reference's MPI_Isend of its frame, fluid.c:283-287, :354-365):
+    frames collected one frame late, two host buffers in rotation, must be the frames sph_run_frame delivers;
+    the protocol errors are reported, not ignored."""
+    import sph_b200
+    z, t, tank_w, tank_h, h, _ = load_golden("default1508")
+    st = z["w400_state"]
+    ts = as_sph(t)
+    a = sph_b200.Context(tank_w, tank_h, h, len(st) + 64); b = sph_b200.Context(tank_w, tank_h, h, len(st) + 64)
+    for c in (a, b):
+        c.set_params(ts); c.upload(st)
+    n = len(st)
+    sync_xy = np.zeros(2 * n, "i2")
+    bufs = [np.zeros(2 * n, "i2"), np.zeros(2 * n, "i2")]
+    want, got, tickets = [], [], []
+    for f in range(7):
+        t2 = ts.copy(); t2.mover_center_x = (0.2 + 0.08 * f) * tank_w
+        assert a.run_frame(t2, 4, sync_xy) == n
+        want.append(sync_xy.copy())
+        tickets.append(b.run_frame_async(t2, 4, bufs[f % 2]))
+        if f > 0:
+            assert b.coords_wait(tickets[f - 1]) == n
+            got.append(bufs[(f - 1) % 2].copy())
+    with pytest.raises(sph_b200.SphError):
+        b.coords_wait(tickets[-2])                       # already collected
+    assert b.coords_wait(tickets[-1]) == n
+    got.append(bufs[(7 - 1) % 2].copy())
+    assert tickets == [0, 1, 0, 1, 0, 1, 0]
+    for f in range(7):
+        assert np.array_equal(want[f], got[f]), f
+    # a third frame in flight is refused
+    k0 = b.pack_coords_async(bufs[0]); k1 = b.pack_coords_async(bufs[1])
+    with pytest.raises(sph_b200.SphError):
+        b.pack_coords_async(bufs[0])
+    # the synchronous call still works while frames are in flight, and sees the same state
+    assert np.array_equal(b.pack_coords().ravel(), want[-1])
+    assert b.coords_wait(k0) == n and b.coords_wait(k1) == n
+    assert np.array_equal(bufs[0], want[-1]) and np.array_equal(bufs[1], want[-1])
