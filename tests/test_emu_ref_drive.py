@@ -48,3 +48,12 @@ def test_unmodified_reference_driver_on_the_emulated_library(built_lib, tmp_path
         assert ctx.run_frame(sph(blk), 4, coords) == n
         s, _ = ctx.download()
         assert np.array_equal(pack(s["x"], s["y"], w, h), got), k
+
+
+def test_reference_call_order_on_the_emulated_library(built_lib, monkeypatch):
+    """tests/test_ref_api.py's GPU test (the reference's call sequence through the reference-named entry points
+    equals sph_step bit for bit) with the emulator library in place of libsph_b200.so."""
+    import test_ref_api
+    emu = build_emu()
+    monkeypatch.setattr(sph_b200, "_lib", sph_b200._bind(C.CDLL(emu)))
+    test_ref_api.test_reference_call_order_reproduces_sph_step(emu)
