@@ -34,6 +34,23 @@ class _CudaBytes:
         self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
 
 
+def keep_slabs_wider_than(old, new, min_width, nactive):
+    """One-exchange build: an interior slab narrower than the ghost layer would leave its neighbours' layers
+    incomplete, and the reference's balancer (renderer.c:427-477) only guarantees 2 h.  Undo every edge move that
+    would shrink an interior slab below `min_width`.  Pure arithmetic on identical inputs: every rank gets the same
+    answer."""
+    out = [list(e) for e in new]
+    for r in range(nactive - 1):                       # the edge between slab r and slab r+1
+        if out[r][1] == old[r][1]:
+            continue
+        shrunk = r if out[r][1] < old[r][1] else r + 1
+        interior = 0 < shrunk < nactive - 1
+        if interior and out[shrunk][1] - out[shrunk][0] < min_width:
+            out[r][1] = old[r][1]
+            out[r + 1][0] = old[r + 1][0]
+    return [tuple(e) for e in out]
+
+
 class SlabRunner:
     def __init__(self, prob, tunable, rank, world, stream=None, capacity_factor=2.0, backend=None,
                  msg_capacity=None, steps_per_frame=4, balance=True, group=None, transport="p2p",
@@ -160,6 +177,7 @@ class SlabRunner:
         else:
             counts, costs = self.gather_counts()
         self.counts, self.costs = counts, costs
+        old_edges = list(self.edges)
         if self.balance_policy == "cost":
             # same edge arithmetic, fed with the work estimate (scaled to stay far from int overflow)
             self.edges = sph_b200.balance(self.edges, [c >> 4 for c in costs], self.prob["h"], self.n_active,
@@ -167,6 +185,8 @@ class SlabRunner:
         else:
             # the reference feeds coordinate counts (2 per particle) on both sides of the ratio (renderer.c:280,290)
             self.edges = sph_b200.balance(self.edges, [2 * c for c in counts], self.prob["h"], self.n_active)
+        if self.exchanges == 1:
+            self.edges = keep_slabs_wider_than(old_edges, self.edges, (self.ctx.cfg.halo_width or 3.5) * self.prob["h"], self.n_active)
         self._queue_edges()
 
     def _queue_edges(self):

@@ -105,3 +105,17 @@ def test_remove_and_add_partition(built_lib):
     n = L.sph_host_add_partition(m, n, 4)
     assert n == 4 and m[2].node_end_x == 15.0 and m[3].node_start_x == 15.0 and m[3].node_end_x == 20.0 and m[3].active == bytes([1])
     assert L.sph_host_remove_partition(m, 1) == 1 and L.sph_host_add_partition(m, 4, 4) == 4
+
+
+def test_one_exchange_edge_filter_keeps_interior_slabs_wider_than_the_layer():
+    from sph_b200.slab import keep_slabs_wider_than
+    old = [(0.0, 4.0), (4.0, 6.1), (6.1, 10.0), (10.0, 15.0)]
+    # edge 0|1 moves right (slab 1 shrinks to 2.0 < 2.05: undone), edge 2|3 moves left (slab 2 shrinks to 3.8: fine)
+    new = [(0.0, 4.1), (4.1, 6.1), (6.1, 9.9), (9.9, 15.0)]
+    out = keep_slabs_wider_than(old, new, 2.05, 4)
+    assert out == [(0.0, 4.0), (4.0, 6.1), (6.1, 9.9), (9.9, 15.0)]
+    # boundary slabs may be as narrow as the reference allows: nothing lies beyond them
+    new = [(0.0, 3.9), (3.9, 6.1), (6.1, 10.0), (10.0, 15.0)]
+    assert keep_slabs_wider_than(old, new, 5.0, 4) == new
+    # unchanged edges stay unchanged, parked slabs (beyond nactive) are not looked at
+    assert keep_slabs_wider_than(old, old, 100.0, 3) == old
