@@ -62,6 +62,14 @@ void sph_ref_set_mirror(int every_n_steps) { G.mirror = every_n_steps > 0; G.mir
 int sph_ref_attach(fluid_particle **pointers, param *params, AABB_t *boundary, neighbor_grid_t *grid, int device)
 {
     sph_ref_detach();
+    if (G.nranks > 1) {
+        /* start/finishHaloExchange and transferOOBParticles are no-ops here: carrying on would simulate every slab as
+         * if it were alone.  Slabs are driven through the handle API. */
+        snprintf(G.err, sizeof G.err, "sph_ref_attach: the reference-named entry points serve ONE compute rank (got %d); "
+                 "a multi-rank host drives its slabs through the handle API (sph_create with rank/nranks, sph_exchange_buffers)", G.nranks);
+        fprintf(stderr, "sph_ref_api: %s\n", G.err);
+        return SPH_ERR_STATE;
+    }
     const int rank = G.rank, nranks = G.nranks, mirror = G.mirror, mirror_every = G.mirror_every;
     const int armed_g = G.pending_gravity, armed_v = G.pending_viscosity;    /* a lazy attach happens between arming and firing */
     memset(&G, 0, sizeof G);

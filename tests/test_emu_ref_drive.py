@@ -57,3 +57,16 @@ def test_reference_call_order_on_the_emulated_library(built_lib, monkeypatch):
     emu = build_emu()
     monkeypatch.setattr(sph_b200, "_lib", sph_b200._bind(C.CDLL(emu)))
     test_ref_api.test_reference_call_order_reproduces_sph_step(emu)
+
+
+def test_reference_named_attach_refuses_more_than_one_rank(built_lib):
+    """start/finishHaloExchange and transferOOBParticles are single-rank no-ops; a host that announces more than one
+    compute rank must be told so, not handed isolated slabs."""
+    L = C.CDLL(build_emu())
+    L.sph_ref_last_error.restype = C.c_char_p
+    L.sph_ref_set_rank(1, 3)
+    try:
+        assert L.sph_ref_attach(None, None, None, None, 0) != 0
+        assert b"ONE compute rank" in L.sph_ref_last_error()
+    finally:
+        L.sph_ref_set_rank(0, 1)
