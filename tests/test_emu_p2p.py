@@ -90,3 +90,58 @@ def test_peer_memory_slab_steps_equal_single_slab_bit_for_bit(built_lib, monkeyp
     for f in ("x", "y", "v_x", "v_y"):
         assert np.array_equal(state[f][order].view("u4"), ref[f].view("u4")), f
     assert sum(c.status().migrated_left + c.status().migrated_right for c in ctxs) >= 0
+
+
+@pytest.mark.parametrize("one_exchange", [False, True])
+def test_hostile_soup_across_three_devices(built_lib, monkeypatch, one_exchange):
+    """Clustered random particles at rest, coincident pairs -- one inside a slab, two straddling the slab edges exactly
+    (on the edge, and one ulp to its left) -- through the peer-memory protocol on three emulated devices: the owner
+    rule of the coincident-particle nudge (fluid.c:583-586, hash.c:178-224) and the strict </> of the migration
+    test (fluid.c:494-497) must give the single-slab bits.  (At rest: a slab has no ghosts for the viscosity pass
+    of its very first step after an upload; the reference starts at rest with empty lists, fluid.c:202.)"""
+    from common import random_state
+    lib = build_emu(defines=("SPH_ONE_EXCHANGE=1",), name="libsph_emu_sph_one_exchange1.so") if one_exchange else build_emu()
+    monkeypatch.setattr(sph_b200, "_lib", sph_b200._bind(C.CDLL(lib)))
+    world, n, steps = 3, 3000, 20
+    prob = make_problem(n, nranks=world)
+    tw, th, h = prob["tank_w"], prob["tank_h"], prob["h"]
+
+    def params(rank=None):
+        t = default_tunable(h, tw, th)
+        if rank is not None:
+            t.node_start_x, t.node_end_x = prob["slabs"][rank][2], prob["slabs"][rank][3]
+        return as_sph(t)
+
+    for seed in (1, 2):
+        a = random_state(n, tw, th, seed=seed, clustered=True)
+        e1, e2 = prob["slabs"][1][2], prob["slabs"][2][2]
+        a[10] = a[11]
+        a[20]["x"] = a[21]["x"] = e1; a[21]["y"] = a[20]["y"]
+        a[22]["x"] = np.nextafter(np.float32(e2), np.float32(0)); a[23]["x"] = e2; a[23]["y"] = a[22]["y"]
+        a["x_prev"] = a["x"]; a["y_prev"] = a["y"]; a["v_x"] = 0; a["v_y"] = 0; a["id"] = np.arange(n)
+        uid = np.arange(n, dtype="u4")
+        ctxs = []
+        for r in range(world):
+            s, e = prob["slabs"][r][2], prob["slabs"][r][3]
+            own = ((a["x"] >= s) if r == 0 else (a["x"] > s)) & (a["x"] <= e)
+            c = sph_b200.Context(tw, th, h, 2 * n, msg_capacity=4096, device=r, rank=r, nranks=world,
+                                 halo_width=3.5 if one_exchange else 2.0)
+            c.set_params(params(r)); c.upload(a[own], uid[own]); ctxs.append(c)
+        hs = [c.p2p_handle() for c in ctxs]
+        for r, c in enumerate(ctxs):
+            c.p2p_connect(hs[r - 1] if r > 0 else None, hs[r + 1] if r < world - 1 else None)
+        threads = [threading.Thread(target=lambda c=c: c.step(steps)) for c in ctxs]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join(timeout=300)
+        parts = [c.download() for c in ctxs]
+        st = np.concatenate([p[0] for p in parts]); u = np.concatenate([p[1] for p in parts])
+        assert all(c.status().capacity_overflow == 0 and c.status().msg_overflow == 0 for c in ctxs)
+        one = sph_b200.Context(tw, th, h, n + 64)
+        one.set_params(params()); one.upload(a, uid); one.step(steps)
+        ref, ru = one.download()
+        assert np.array_equal(np.sort(u), ru), seed
+        order = np.argsort(u)
+        for f in ("x", "y", "v_x", "v_y"):
+            assert np.array_equal(st[f][order].view("u4"), ref[f].view("u4")), (seed, f)
