@@ -56,15 +56,21 @@ def test_peer_memory_slab_steps_equal_single_slab_bit_for_bit(built_lib, monkeyp
 
     errors = []
 
-    def run(c):
+    def changed(ts):                 # the render rank's scatter in mid-run: mover moved, stiffer fluid (fluid.c:293-294)
+        t2 = ts.copy(); t2.mover_center_x = 0.45 * prob["tank_w"]; t2.mover_center_y = 0.2 * prob["tank_h"]; t2.k = 0.35
+        return t2
+
+    def run(c, r):
         try:
-            for _ in range(steps // 8):
+            for k in range(steps // 8):
+                if k == 4:
+                    c.queue_params(changed(params(prob, r)))     # lands inside the next step, on every slab alike
                 c.step(8)            # graph replays; neighbours drift apart by at most one exchange
             c.synchronize()
         except Exception as e:       # noqa: BLE001
             errors.append(e)
 
-    threads = [threading.Thread(target=run, args=(c,)) for c in ctxs]
+    threads = [threading.Thread(target=run, args=(c, r)) for r, c in enumerate(ctxs)]
     for t in threads:
         t.start()
     for t in threads:
@@ -83,7 +89,8 @@ def test_peer_memory_slab_steps_equal_single_slab_bit_for_bit(built_lib, monkeyp
     one = sph_b200.Context(p1["tank_w"], p1["tank_h"], p1["h"], len(a1) + 64)
     if goo:
         one.set_viscosity_stabilisation(0.5)
-    one.set_params(params(p1)); one.upload(a1, u1); one.step(steps)
+    one.set_params(params(p1)); one.upload(a1, u1)
+    one.step(32); one.queue_params(changed(params(p1))); one.step(steps - 32)
     ref, ru = one.download()
     assert np.array_equal(np.sort(uid), ru), "particles lost or duplicated in migration"
     order = np.argsort(uid)
