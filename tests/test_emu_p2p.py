@@ -4,7 +4,6 @@ steps from captured graphs -- send_messages, the last-block publication, the arr
 waits of k_unpack, double buffering by step parity.  The result must equal the single-slab run bit for bit.
 Timing, co-residency and the memory model of real GPUs are out of reach here (tests/test_gpu_slabs.py)."""
 import ctypes as C
-import os
 import threading
 
 import numpy as np

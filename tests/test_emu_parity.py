@@ -10,7 +10,6 @@ reproduced, and nothing here counts as parity of the product -- that is tests/te
 The product library never loads the emulator (test_product_library_has_no_emulator_in_it).
 """
 import ctypes as C
-import os
 import subprocess
 
 import numpy as np

@@ -6,10 +6,9 @@ N slabs must equal one slab BIT FOR BIT, and both must sit at rounding level fro
 import numpy as np
 import pytest
 
-from common import ULPS_POS, ulp32
 from emu.backend import EmuSlab
 from oracle.oracle import default_tunable, lattice, make_problem
-from test_slab_gloo import run_world, single_slab
+from test_slab_gloo import run_world
 
 
 def emu_single(prob, t, steps, gamma=0.0):

@@ -16,7 +16,6 @@ import pytest
 import sph_b200
 from common import load_golden
 from emu.build_emu import build as build_emu
-from oracle.oracle import lattice, make_problem
 from test_gpu_parity import as_sph
 
 
