@@ -81,6 +81,16 @@ def test_long_run_statistics_goo_with_stabilised_viscosity(built_lib):
     pc.check_long_run_statistics(mk_stab, "goo_rect1508", a, dens_make=make_oracle, widen=GOO_STABILISED_WIDEN)
 
 
+@pytest.mark.parametrize("name,kw", [("block3000", dict(n_request=3000, tank_w=21.2, water_frac=0.5)),
+                                     ("zerog1508", dict(n_request=1500)), ("gas1508", dict(n_request=1500))])
+def test_long_run_statistics_other_presets(built_lib, name, kw):
+    """Dam-break block, zero-g (preset a) and the spring gas (preset b): 1200 steps from the lattice, statistics of
+    the last 200 within the stated bars of the reference's (tests/common.py; the default fluid's run is in
+    tests/test_gpu_parity.py, goo's above)."""
+    a, _ = lattice(make_problem(**kw))
+    pc.check_long_run_statistics(mk, name, a, dens_make=make_oracle)
+
+
 def run_config4(n_req, frames, frames_per_preset):
     """BASELINE.json config 4: dam-break block, mover sphere on the render rank's autopilot path
     (renderer.c:513-531) ploughing through the water, fluid presets cycled a -> b -> x -> y
