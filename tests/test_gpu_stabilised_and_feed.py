@@ -73,22 +73,44 @@ def test_stabilisation_threshold_selects_the_pass_per_parameter_block(built_lib)
     assert (b.launches - n0) // 4 == per_step_plain
 
 
-def test_long_run_statistics_goo_with_stabilised_viscosity(built_lib):
-    """The goo preset (sigma 100, beta 10) settles to the reference's statistics with the stabilised gather;
-    with the plain gather it never settles (tests/test_oracle_gather.py pins that on the oracle)."""
-    a, _ = lattice(make_problem(1500))
-    from common import GOO_STABILISED_WIDEN
-    pc.check_long_run_statistics(mk_stab, "goo_rect1508", a, dens_make=make_oracle, widen=GOO_STABILISED_WIDEN)
-
-
-@pytest.mark.parametrize("name,kw", [("block3000", dict(n_request=3000, tank_w=21.2, water_frac=0.5)),
-                                     ("zerog1508", dict(n_request=1500)), ("gas1508", dict(n_request=1500))])
-def test_long_run_statistics_other_presets(built_lib, name, kw):
-    """Dam-break block, zero-g (preset a) and the spring gas (preset b): 1200 steps from the lattice, statistics of
-    the last 200 within the stated bars of the reference's (tests/common.py; the default fluid's run is in
-    tests/test_gpu_parity.py, goo's above)."""
-    a, _ = lattice(make_problem(**kw))
-    pc.check_long_run_statistics(mk, name, a, dens_make=make_oracle)
+def test_asynchronous_coordinate_feed_equals_the_synchronous_one(built_lib):
+    """sph_run_frame_async / sph_coords_wait (the reference's MPI_Isend of its frame, fluid.c:283-287, :354-365):
+    frames collected one frame late, two host buffers in rotation, must be the frames sph_run_frame delivers;
+    the protocol errors are reported, not ignored."""
+    import sph_b200
+    z, t, tank_w, tank_h, h, _ = load_golden("default1508")
+    st = z["w400_state"]
+    ts = as_sph(t)
+    a = sph_b200.Context(tank_w, tank_h, h, len(st) + 64); b = sph_b200.Context(tank_w, tank_h, h, len(st) + 64)
+    for c in (a, b):
+        c.set_params(ts); c.upload(st)
+    n = len(st)
+    sync_xy = np.zeros(2 * n, "i2")
+    bufs = [np.zeros(2 * n, "i2"), np.zeros(2 * n, "i2")]
+    want, got, tickets = [], [], []
+    for f in range(7):
+        t2 = ts.copy(); t2.mover_center_x = (0.2 + 0.08 * f) * tank_w
+        assert a.run_frame(t2, 4, sync_xy) == n
+        want.append(sync_xy.copy())
+        tickets.append(b.run_frame_async(t2, 4, bufs[f % 2]))
+        if f > 0:
+            assert b.coords_wait(tickets[f - 1]) == n
+            got.append(bufs[(f - 1) % 2].copy())
+    with pytest.raises(sph_b200.SphError):
+        b.coords_wait(tickets[-2])                       # already collected
+    assert b.coords_wait(tickets[-1]) == n
+    got.append(bufs[(7 - 1) % 2].copy())
+    assert tickets == [0, 1, 0, 1, 0, 1, 0]
+    for f in range(7):
+        assert np.array_equal(want[f], got[f]), f
+    # a third frame in flight is refused
+    k0 = b.pack_coords_async(bufs[0]); k1 = b.pack_coords_async(bufs[1])
+    with pytest.raises(sph_b200.SphError):
+        b.pack_coords_async(bufs[0])
+    # the synchronous call still works while frames are in flight, and sees the same state
+    assert np.array_equal(b.pack_coords().ravel(), want[-1])
+    assert b.coords_wait(k0) == n and b.coords_wait(k1) == n
+    assert np.array_equal(bufs[0], want[-1]) and np.array_equal(bufs[1], want[-1])
 
 
 def run_config4(n_req, frames, frames_per_preset):
@@ -146,41 +168,19 @@ def test_config4_full_size_properties(built_lib):
     check_config4(prob, b, n0, coords, per_frame, 4)
 
 
-def test_asynchronous_coordinate_feed_equals_the_synchronous_one(built_lib):
-    """sph_run_frame_async / sph_coords_wait (the reference's MPI_Isend of its frame, fluid.c:283-287, :354-365):
-    frames collected one frame late, two host buffers in rotation, must be the frames sph_run_frame delivers;
-    the protocol errors are reported, not ignored."""
-    import sph_b200
-    z, t, tank_w, tank_h, h, _ = load_golden("default1508")
-    st = z["w400_state"]
-    ts = as_sph(t)
-    a = sph_b200.Context(tank_w, tank_h, h, len(st) + 64); b = sph_b200.Context(tank_w, tank_h, h, len(st) + 64)
-    for c in (a, b):
-        c.set_params(ts); c.upload(st)
-    n = len(st)
-    sync_xy = np.zeros(2 * n, "i2")
-    bufs = [np.zeros(2 * n, "i2"), np.zeros(2 * n, "i2")]
-    want, got, tickets = [], [], []
-    for f in range(7):
-        t2 = ts.copy(); t2.mover_center_x = (0.2 + 0.08 * f) * tank_w
-        assert a.run_frame(t2, 4, sync_xy) == n
-        want.append(sync_xy.copy())
-        tickets.append(b.run_frame_async(t2, 4, bufs[f % 2]))
-        if f > 0:
-            assert b.coords_wait(tickets[f - 1]) == n
-            got.append(bufs[(f - 1) % 2].copy())
-    with pytest.raises(sph_b200.SphError):
-        b.coords_wait(tickets[-2])                       # already collected
-    assert b.coords_wait(tickets[-1]) == n
-    got.append(bufs[(7 - 1) % 2].copy())
-    assert tickets == [0, 1, 0, 1, 0, 1, 0]
-    for f in range(7):
-        assert np.array_equal(want[f], got[f]), f
-    # a third frame in flight is refused
-    k0 = b.pack_coords_async(bufs[0]); k1 = b.pack_coords_async(bufs[1])
-    with pytest.raises(sph_b200.SphError):
-        b.pack_coords_async(bufs[0])
-    # the synchronous call still works while frames are in flight, and sees the same state
-    assert np.array_equal(b.pack_coords().ravel(), want[-1])
-    assert b.coords_wait(k0) == n and b.coords_wait(k1) == n
-    assert np.array_equal(bufs[0], want[-1]) and np.array_equal(bufs[1], want[-1])
+@pytest.mark.parametrize("name,kw", [("block3000", dict(n_request=3000, tank_w=21.2, water_frac=0.5)),
+                                     ("zerog1508", dict(n_request=1500)), ("gas1508", dict(n_request=1500))])
+def test_long_run_statistics_other_presets(built_lib, name, kw):
+    """Dam-break block, zero-g (preset a) and the spring gas (preset b): 1200 steps from the lattice, statistics of
+    the last 200 within the stated bars of the reference's (tests/common.py; the default fluid's run is in
+    tests/test_gpu_parity.py, goo's above)."""
+    a, _ = lattice(make_problem(**kw))
+    pc.check_long_run_statistics(mk, name, a, dens_make=make_oracle)
+
+
+def test_long_run_statistics_goo_with_stabilised_viscosity(built_lib):
+    """The goo preset (sigma 100, beta 10) settles to the reference's statistics with the stabilised gather;
+    with the plain gather it never settles (tests/test_oracle_gather.py pins that on the oracle)."""
+    a, _ = lattice(make_problem(1500))
+    from common import GOO_STABILISED_WIDEN
+    pc.check_long_run_statistics(mk_stab, "goo_rect1508", a, dens_make=make_oracle, widen=GOO_STABILISED_WIDEN)
