@@ -194,6 +194,13 @@ int sph_step(sph_ctx *ctx, int n);
  * which = 0: after advect (migrants + predicted-position halo), 1: after relax (pos+vel halo). */
 int sph_exchange_buffers(sph_ctx *ctx, int which, void **send_left, void **recv_left,
                          void **send_right, void **recv_right, size_t *bytes);
+/* Restart from a moving snapshot on several slabs.  sph_upload places a slab's own particles only, so the viscosity
+ * pass of the very first step would miss the neighbours across the edges (the reference, and sph_init_lattice,
+ * start at rest, where that pass does nothing).  After every rank has uploaded: sph_refresh_ghosts (packs the
+ * ghost layer, position + velocity, like the end of a step) -> move the which = 1 buffers of
+ * sph_exchange_buffers (nothing to do with sph_p2p_connect) -> sph_sort.  All ranks must do this together: it
+ * consumes one message sequence number.  No-op for nranks == 1. */
+int sph_refresh_ghosts(sph_ctx *ctx);
 /* Exchanges per step of this build: 2 (which = 0 after sph_advect, which = 1 after sph_relax), or 1 for the
  * one-exchange build variant (-DSPH_ONE_EXCHANGE=1), whose ghosts are relaxed redundantly and which needs
  * halo_width >= 3 (4 with the stabilised viscosity gather); the driver then skips the which = 1 transfer. */

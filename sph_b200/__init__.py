@@ -62,7 +62,7 @@ C_ABI_SYMBOLS = (
     "sph_set_neighbors", "sph_get_cells", "sph_get_pairs", "sph_get_forward_counts",
     "sph_pack_coords", "sph_launch_count", "sph_run_frame", "sph_p2p_local_handle", "sph_p2p_connect", "sph_copy_n_local", "sph_copy_load", "sph_init_lattice",
     "sph_set_viscosity_stabilisation", "sph_pack_coords_async", "sph_coords_wait", "sph_run_frame_async",
-    "sph_exchanges_per_step",
+    "sph_exchanges_per_step", "sph_refresh_ghosts",
 )
 
 _lib = None
@@ -94,7 +94,7 @@ def _bind(L):
     L.sph_set_edges.argtypes = [C.c_void_p, C.c_float, C.c_float]
     L.sph_set_viscosity_stabilisation.argtypes = [C.c_void_p, C.c_float, C.c_float]
     L.sph_create.argtypes = [C.POINTER(Config), C.POINTER(C.c_void_p)]
-    for name in ("sph_destroy", "sph_synchronize", "sph_advect", "sph_sort", "sph_density", "sph_relax"):
+    for name in ("sph_destroy", "sph_synchronize", "sph_advect", "sph_sort", "sph_density", "sph_relax", "sph_refresh_ghosts"):
         getattr(L, name).argtypes = [C.c_void_p]
     L.sph_step.argtypes = [C.c_void_p, C.c_int]
     L.sph_set_params.argtypes = [C.c_void_p, C.POINTER(Tunable)]
@@ -188,6 +188,7 @@ class Context:
     def density(self): self._ck(self.L.sph_density(self.h), "sph_density")
     def relax(self): self._ck(self.L.sph_relax(self.h), "sph_relax")
     def step(self, n=1): self._ck(self.L.sph_step(self.h, int(n)), "sph_step")
+    def refresh_ghosts(self): self._ck(self.L.sph_refresh_ghosts(self.h), "sph_refresh_ghosts")
 
     def run_frame(self, tunable, steps, coords_out):
         """One render frame (fluid.c:270-372): `steps` sub-steps, the parameter scatter landing in

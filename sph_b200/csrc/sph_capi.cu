@@ -18,7 +18,7 @@
 #define SPH_LAUNCH(kernel, grid, stream) emu::make_launcher(kernel, (grid), SPH_THREADS, (stream))
 #endif
 
-enum { ST_READY = 0, ST_ADVECTED, ST_SORTED1, ST_DENSITY, ST_RELAXED };
+enum { ST_READY = 0, ST_ADVECTED, ST_SORTED1, ST_DENSITY, ST_RELAXED, ST_REQUEUED };
 
 struct sph_ctx {
     sph_config cfg;
@@ -359,7 +359,7 @@ extern "C" int sph_p2p_connect(sph_ctx *ctx, const void *left_handle64, const vo
 //   relax    : reads P2,Q1,U1,dens       writes relaxed pos P3, vel Q2 (source order)
 //   sort 2   : src (P3, Q2, U1)          dst (P0, Q0, U0)
 // ------------------------------------------------------------------------------------------
-static int launch_sort(sph_ctx *ctx, int which, bool with_unpack = true)
+static int launch_sort(sph_ctx *ctx, int which, bool with_unpack = true, bool refresh = false)
 {
     float2 *sp = which == 0 ? ctx->P[1] : ctx->P[3];
     float2 *sq = which == 0 ? ctx->P[0] : ctx->Q[2];
@@ -368,7 +368,8 @@ static int launch_sort(sph_ctx *ctx, int which, bool with_unpack = true)
     float2 *dq = which == 0 ? ctx->Q[1] : ctx->Q[0];
     uint32_t *du = which == 0 ? ctx->U[1] : ctx->U[0];
     // (one-exchange build: nothing arrives after the relaxation, the ghosts were relaxed here)
-    if (ctx->cfg.nranks > 1 && with_unpack && !(SPH_ONE_EXCHANGE && which == 1)) {
+    // (refresh: sph_refresh_ghosts always brings its ghosts in the which = 1 format)
+    if (ctx->cfg.nranks > 1 && with_unpack && (refresh || !(SPH_ONE_EXCHANGE && which == 1))) {
         SPH_LAUNCH(k_unpack, ctx->unpack_grid, ctx->stream)(ctx->dp, ctx->counters, which, ctx->send[0], ctx->send[1],
                                                              ctx->recv[0], ctx->recv[1],
                                                              sp, sq, su, ctx->cnt, ctx->t_key, ctx->t_slot);
@@ -486,7 +487,22 @@ extern "C" int sph_sort(sph_ctx *ctx)
     int rc;
     if (ctx->stage == ST_ADVECTED) { if ((rc = launch_sort(ctx, 0))) return rc; ctx->stage = ST_SORTED1; }
     else if (ctx->stage == ST_RELAXED) { if ((rc = launch_sort(ctx, 1))) return rc; ctx->stage = ST_READY; ctx->steps++; }
+    else if (ctx->stage == ST_REQUEUED) { if ((rc = launch_sort(ctx, 1, true, true))) return rc; ctx->stage = ST_READY; }
     else return fail(ctx, SPH_ERR_STATE, "sph_sort: nothing to sort");
+    return SPH_OK;
+}
+
+// Ghosts for a slab that has just been uploaded (a restart from a moving snapshot): see include/sph_b200.h
+extern "C" int sph_refresh_ghosts(sph_ctx *ctx)
+{
+    if (!ctx) return SPH_ERR_ARG;
+    if (ctx->stage != ST_READY) return fail(ctx, SPH_ERR_STATE, "sph_refresh_ghosts: state is not at a step boundary");
+    if (ctx->cfg.nranks <= 1) return SPH_OK;
+    SPH_LAUNCH(k_requeue, ctx->grid, ctx->stream)(ctx->dp, ctx->counters, ctx->P[0], ctx->Q[0], ctx->U[0], ctx->P[3], ctx->Q[2],
+                                                  ctx->U[1], ctx->cnt, ctx->t_key, ctx->t_slot, ctx->send[0], ctx->send[1]);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    ctx->stage = ST_REQUEUED;
     return SPH_OK;
 }
 

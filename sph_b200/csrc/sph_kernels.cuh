@@ -1025,6 +1025,43 @@ k_bin_upload(const DevParams *__restrict__ Pp, int *__restrict__ counters, const
 }
 
 // -------------------------------------------------------------------------------------------
+// restart helper (sph_refresh_ghosts): a slab that was uploaded has no ghosts yet.  Put the resident LOCALS
+// back into the sort's source arrays, bin them, and pack the ghost message a k_relax would have packed
+// (position + velocity, which = 1); the following sort exchanges and unpacks it like any other.
+// -------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(SPH_THREADS)
+k_requeue(const DevParams *__restrict__ Pp, int *__restrict__ counters,
+          const float2 *__restrict__ pos, const float2 *__restrict__ vel, const uint32_t *__restrict__ uid,
+          float2 *__restrict__ pos_out, float2 *__restrict__ vel_out, uint32_t *__restrict__ uid_out,
+          int *__restrict__ cnt, int *__restrict__ t_key, int *__restrict__ t_slot,
+          unsigned char *send_l, unsigned char *send_r)
+{
+    const DevParams P = *Pp;
+    const int n = counters[CN_NTOT];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t u = uid[i];
+        uid_out[i] = u;
+        if (u & SPH_HALO_BIT) { t_key[i] = SPH_KEY_DROP; continue; }
+        const float2 p = pos[i], v = vel[i];
+        pos_out[i] = p;
+        vel_out[i] = v;
+        if (P.nranks > 1) {
+            if (P.has_left && p.x - P.edge_start <= P.halo_w) {
+                int k = atomicAdd(&msg_hdr(send_l)[1], 1);
+                if (k < P.msg_cap) { msg_a(send_l)[k] = p; msg_b(send_l, P.msg_cap)[k] = v; msg_u(send_l, P.msg_cap)[k] = u; }
+                else atomicAdd(&counters[CN_MSG_OVER], 1);
+            }
+            if (P.has_right && P.edge_end - p.x <= P.halo_w) {
+                int k = atomicAdd(&msg_hdr(send_r)[1], 1);
+                if (k < P.msg_cap) { msg_a(send_r)[k] = p; msg_b(send_r, P.msg_cap)[k] = v; msg_u(send_r, P.msg_cap)[k] = u; }
+                else atomicAdd(&counters[CN_MSG_OVER], 1);
+            }
+        }
+        bin_position(i, p, 0, P, cnt, t_key, t_slot, counters);
+    }
+}
+
+// -------------------------------------------------------------------------------------------
 // device-side constructFluidVolume + initParticles (geometry.c:29-59, fluid.c:747-768): the lattice of
 // one slab's columns written straight into the sort's source arrays, so large problems never need a
 // host AoS.  x = min_x + (start_col + col) * spacing, y = min_y + row * spacing, unfused as on the host.

@@ -222,6 +222,15 @@ class SlabRunner:
                 self.torch.cuda.synchronize()
             self.dist.barrier(group=self.group)       # message sequence numbers restart together
 
+    def refresh_ghosts(self):
+        """After an upload of MOVING particles on several slabs (a restart): give every slab its ghost layer, so that
+        the viscosity pass of the first step sees the neighbours across the edges (sph_refresh_ghosts).  Call on every
+        rank together."""
+        self.ctx.refresh_ghosts()
+        if self.transport != "p2p":
+            self.exchange(1)
+        self.ctx.sort()
+
     def step_once(self):
         if self.do_balance and self.world > 1 and self.sub_step == self.steps_per_frame - 1:
             self.rebalance()

@@ -98,13 +98,14 @@ def test_peer_memory_slab_steps_equal_single_slab_bit_for_bit(built_lib, monkeyp
     assert sum(c.status().migrated_left + c.status().migrated_right for c in ctxs) >= 0
 
 
-@pytest.mark.parametrize("one_exchange", [False, True])
-def test_hostile_soup_across_three_devices(built_lib, monkeypatch, one_exchange):
+@pytest.mark.parametrize("one_exchange,moving", [(False, False), (True, False), (False, True), (True, True)])
+def test_hostile_soup_across_three_devices(built_lib, monkeypatch, one_exchange, moving):
     """Clustered random particles at rest, coincident pairs -- one inside a slab, two straddling the slab edges exactly
     (on the edge, and one ulp to its left) -- through the peer-memory protocol on three emulated devices: the owner
     rule of the coincident-particle nudge (fluid.c:583-586, hash.c:178-224) and the strict </> of the migration
-    test (fluid.c:494-497) must give the single-slab bits.  (At rest: a slab has no ghosts for the viscosity pass
-    of its very first step after an upload; the reference starts at rest with empty lists, fluid.c:202.)"""
+    test (fluid.c:494-497) must give the single-slab bits.  `moving`: the soup keeps its random velocities -- a
+    restart from a moving snapshot -- and every slab calls sph_refresh_ghosts + sph_sort after its upload, so that
+    the viscosity pass of the first step sees the neighbours across the edges."""
     from common import random_state
     lib = build_emu(defines=("SPH_ONE_EXCHANGE=1",), name="libsph_emu_sph_one_exchange1.so") if one_exchange else build_emu()
     monkeypatch.setattr(sph_b200, "_lib", sph_b200._bind(C.CDLL(lib)))
@@ -124,7 +125,9 @@ def test_hostile_soup_across_three_devices(built_lib, monkeypatch, one_exchange)
         a[10] = a[11]
         a[20]["x"] = a[21]["x"] = e1; a[21]["y"] = a[20]["y"]
         a[22]["x"] = np.nextafter(np.float32(e2), np.float32(0)); a[23]["x"] = e2; a[23]["y"] = a[22]["y"]
-        a["x_prev"] = a["x"]; a["y_prev"] = a["y"]; a["v_x"] = 0; a["v_y"] = 0; a["id"] = np.arange(n)
+        a["x_prev"] = a["x"]; a["y_prev"] = a["y"]; a["id"] = np.arange(n)
+        if not moving:
+            a["v_x"] = 0; a["v_y"] = 0
         uid = np.arange(n, dtype="u4")
         ctxs = []
         # owner = the first slab whose right edge is not exceeded (adjacent edges come out of partitionProblem by two
@@ -139,7 +142,11 @@ def test_hostile_soup_across_three_devices(built_lib, monkeypatch, one_exchange)
         hs = [c.p2p_handle() for c in ctxs]
         for r, c in enumerate(ctxs):
             c.p2p_connect(hs[r - 1] if r > 0 else None, hs[r + 1] if r < world - 1 else None)
-        threads = [threading.Thread(target=lambda c=c: c.step(steps)) for c in ctxs]
+        def run(c):
+            if moving:
+                c.refresh_ghosts(); c.sort()
+            c.step(steps)
+        threads = [threading.Thread(target=run, args=(c,)) for c in ctxs]
         for t in threads:
             t.start()
         for t in threads:
