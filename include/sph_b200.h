@@ -194,6 +194,16 @@ int sph_step(sph_ctx *ctx, int n);
  * which = 0: after advect (migrants + predicted-position halo), 1: after relax (pos+vel halo). */
 int sph_exchange_buffers(sph_ctx *ctx, int which, void **send_left, void **recv_left,
                          void **send_right, void **recv_right, size_t *bytes);
+/* The same exchange for a host whose transport moves HOST memory (plain MPI_Sendrecv, sockets): the library stages
+ * the message buffers through pinned memory around two calls of `fn`, ordered like the reference's own pair of
+ * MPI_Sendrecv (communication.c:173-199): first (send to the right, receive from the left), then (send to the left,
+ * receive from the right); side 0 = left neighbour (rank - 1), 1 = right (rank + 1).  An absent neighbour appears
+ * as (NULL, 0), the reference's MPI_PROC_NULL.  Call it where the buffers of sph_exchange_buffers(which) would be
+ * moved.  Blocks until the outgoing messages are in host memory; the incoming ones are copied stream-ordered. */
+typedef void (*sph_sendrecv_fn)(const void *send, size_t send_bytes, int to_side,
+                                void *recv, size_t recv_bytes, int from_side, void *user);
+int sph_exchange_via_host(sph_ctx *ctx, int which, sph_sendrecv_fn fn, void *user);
+
 /* Restart from a moving snapshot on several slabs.  sph_upload places a slab's own particles only, so the viscosity
  * pass of the very first step would miss the neighbours across the edges (the reference, and sph_init_lattice,
  * start at rest, where that pass does nothing).  After every rank has uploaded: sph_refresh_ghosts (packs the

@@ -62,7 +62,7 @@ C_ABI_SYMBOLS = (
     "sph_set_neighbors", "sph_get_cells", "sph_get_pairs", "sph_get_forward_counts",
     "sph_pack_coords", "sph_launch_count", "sph_run_frame", "sph_p2p_local_handle", "sph_p2p_connect", "sph_copy_n_local", "sph_copy_load", "sph_init_lattice",
     "sph_set_viscosity_stabilisation", "sph_pack_coords_async", "sph_coords_wait", "sph_run_frame_async",
-    "sph_exchanges_per_step", "sph_refresh_ghosts",
+    "sph_exchanges_per_step", "sph_refresh_ghosts", "sph_exchange_via_host",
 )
 
 _lib = None
@@ -229,6 +229,19 @@ class Context:
     @property
     def exchanges_per_step(self):
         return int(self.L.sph_exchanges_per_step())
+
+    def exchange_via_host(self, which, sendrecv):
+        """sph_exchange_via_host with a Python callable sendrecv(send_bytes_or_None, to_side, recv_nbytes, from_side)
+        -> bytes received (or None): what a host with a plain (not CUDA-aware) MPI_Sendrecv would plug in."""
+        FN = C.CFUNCTYPE(None, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p)
+
+        def cb(send, nsend, to_side, recv, nrecv, from_side, user):
+            got = sendrecv(C.string_at(send, nsend) if send else None, to_side, nrecv, from_side)
+            if recv and got is not None:
+                C.memmove(recv, got, min(len(got), nrecv))
+        fn = FN(cb)
+        self.L.sph_exchange_via_host.argtypes = [C.c_void_p, C.c_int, FN, C.c_void_p]
+        self._ck(self.L.sph_exchange_via_host(self.h, int(which), fn, None), "sph_exchange_via_host")
 
     def exchange_pointers(self, which):
         """Device pointers (send_left, recv_left, send_right, recv_right) and message bytes."""

@@ -58,6 +58,7 @@ struct sph_ctx {
     int *feed_cnt_host;              // the same, in pinned host memory
     unsigned feed_seq;
     int n_uploaded;                  // single slab: the particle count never changes after an upload
+    unsigned char *stage_host;       // sph_exchange_via_host: 4 pinned message buffers (send l/r, recv l/r), allocated on first use
     int stage;
     int grid;
     int size_x, size_y;
@@ -238,6 +239,7 @@ extern "C" void sph_destroy(sph_ctx *ctx)
         if (ctx->feed[k].packed) cudaEventDestroy(ctx->feed[k].packed);
         if (ctx->feed[k].copied) cudaEventDestroy(ctx->feed[k].copied);
     }
+    if (ctx->stage_host) cudaFreeHost(ctx->stage_host);
     cudaFree(ctx->feed_cnt_dev);
     if (ctx->feed_cnt_host) cudaFreeHost(ctx->feed_cnt_host);
     for (int i = 0; i < 4; i++) cudaFree(ctx->P[i]);
@@ -313,6 +315,30 @@ extern "C" int sph_exchange_buffers(sph_ctx *ctx, int which, void **sl, void **r
     if (sr) *sr = ctx->send[1];
     if (rr) *rr = ctx->recv[1];
     if (bytes) *bytes = which == 0 ? msg_bytes_full(ctx->cfg.msg_capacity) : msg_bytes_halo1(ctx->cfg.msg_capacity);
+    return SPH_OK;
+}
+
+// The exchange for a host whose transport moves HOST memory (plain MPI_Sendrecv, sockets): the message buffers are
+// staged through pinned memory around two calls of the host's sendrecv, ordered like the reference's own pair of
+// MPI_Sendrecv (communication.c:173-199: to the right / from the left, then to the left / from the right), so a
+// blocking transport cannot deadlock.  An absent neighbour is (NULL, 0), the reference's MPI_PROC_NULL.
+extern "C" int sph_exchange_via_host(sph_ctx *ctx, int which, sph_sendrecv_fn fn, void *user)
+{
+    if (!ctx || !fn || (which != 0 && which != 1)) return SPH_ERR_ARG;
+    if (ctx->cfg.nranks <= 1) return SPH_OK;
+    const size_t full = msg_bytes_full(ctx->cfg.msg_capacity);
+    const size_t nb = which == 0 ? full : msg_bytes_halo1(ctx->cfg.msg_capacity);
+    if (!ctx->stage_host) CK(cudaMallocHost(&ctx->stage_host, 4 * full));
+    unsigned char *hs[2] = {ctx->stage_host, ctx->stage_host + full}, *hr[2] = {ctx->stage_host + 2 * full, ctx->stage_host + 3 * full};
+    const int present[2] = {ctx->hp.has_left, ctx->hp.has_right};
+    for (int s = 0; s < 2; s++)
+        if (present[s]) CK(cudaMemcpyAsync(hs[s], ctx->send[s], nb, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    // to the right / from the left, then to the left / from the right
+    fn(present[1] ? hs[1] : nullptr, present[1] ? nb : 0, 1, present[0] ? hr[0] : nullptr, present[0] ? nb : 0, 0, user);
+    fn(present[0] ? hs[0] : nullptr, present[0] ? nb : 0, 0, present[1] ? hr[1] : nullptr, present[1] ? nb : 0, 1, user);
+    for (int s = 0; s < 2; s++)
+        if (present[s]) CK(cudaMemcpyAsync(ctx->recv[s], hr[s], nb, cudaMemcpyHostToDevice, ctx->stream));
     return SPH_OK;
 }
 

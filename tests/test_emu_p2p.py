@@ -161,3 +161,58 @@ def test_hostile_soup_across_three_devices(built_lib, monkeypatch, one_exchange,
         order = np.argsort(u)
         for f in ("x", "y", "v_x", "v_y"):
             assert np.array_equal(st[f][order].view("u4"), ref[f].view("u4")), (seed, f)
+
+
+def test_exchange_via_host_callback_equals_single_slab(built_lib, monkeypatch):
+    """sph_exchange_via_host: the exchange for a host with a plain (host-memory) sendrecv, here Python queues between
+    three threads standing in for MPI_Sendrecv.  Stage by stage through the handle API, as INTEGRATION.md 4 describes."""
+    import queue
+    monkeypatch.setattr(sph_b200, "_lib", sph_b200._bind(C.CDLL(build_emu())))
+    world, n_req, steps = 3, 3000, 40
+    tank_w = 15.0 * float(np.sqrt(n_req / 750.0))
+    prob = make_problem(n_req, tank_w=tank_w, water_frac=0.5, nranks=world)
+    p1 = make_problem(n_req, tank_w=tank_w, water_frac=0.5)
+    wires = {(a, b): queue.Queue() for a in range(world) for b in range(world) if abs(a - b) == 1}
+
+    def params(p, rank=None):
+        t = default_tunable(p["h"], p["tank_w"], p["tank_h"]); t.mover_center_x = 0.3 * p["tank_w"]
+        if rank is not None:
+            t.node_start_x, t.node_end_x = p["slabs"][rank][2], p["slabs"][rank][3]
+        return as_sph(t)
+
+    ctxs = []
+    for r in range(world):
+        a, uid = lattice(prob, r)
+        c = sph_b200.Context(prob["tank_w"], prob["tank_h"], prob["h"], 2 * len(a) + 4096, msg_capacity=2048, device=r, rank=r, nranks=world)
+        c.set_params(params(prob, r)); c.upload(a, uid); ctxs.append(c)
+    errors = []
+
+    def run(c, r):
+        def sendrecv(send, to_side, nrecv, from_side):
+            if send is not None:
+                wires[(r, r - 1 if to_side == 0 else r + 1)].put(send)
+            return wires[(r - 1 if from_side == 0 else r + 1, r)].get(timeout=120) if nrecv else None
+        try:
+            for _ in range(steps):
+                c.advect(); c.exchange_via_host(0, sendrecv); c.sort(); c.density(); c.relax()
+                c.exchange_via_host(1, sendrecv); c.sort()
+        except Exception as e:       # noqa: BLE001
+            errors.append(e)
+
+    threads = [threading.Thread(target=run, args=(c, r)) for r, c in enumerate(ctxs)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=300)
+    assert not errors, errors
+    parts = [c.download() for c in ctxs]
+    state = np.concatenate([p[0] for p in parts]); uid = np.concatenate([p[1] for p in parts])
+    assert all(c.status().capacity_overflow == 0 and c.status().msg_overflow == 0 for c in ctxs)
+    a1, u1 = lattice(p1)
+    one = sph_b200.Context(p1["tank_w"], p1["tank_h"], p1["h"], len(a1) + 64)
+    one.set_params(params(p1)); one.upload(a1, u1); one.step(steps)
+    ref, ru = one.download()
+    assert np.array_equal(np.sort(uid), ru)
+    order = np.argsort(uid)
+    for f in ("x", "y", "v_x", "v_y"):
+        assert np.array_equal(state[f][order].view("u4"), ref[f].view("u4")), f
