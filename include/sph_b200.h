@@ -196,7 +196,7 @@ int sph_exchange_buffers(sph_ctx *ctx, int which, void **send_left, void **recv_
                          void **send_right, void **recv_right, size_t *bytes);
 /* The same exchange for a host whose transport moves HOST memory (plain MPI_Sendrecv, sockets): the library stages
  * the message buffers through pinned memory around two calls of `fn`, ordered like the reference's own pair of
- * MPI_Sendrecv (communication.c:173-199): first (send to the right, receive from the left), then (send to the left,
+ * MPI_Sendrecv (communication.c:158-161, :340-344): first (send to the right, receive from the left), then (send to the left,
  * receive from the right); side 0 = left neighbour (rank - 1), 1 = right (rank + 1).  An absent neighbour appears
  * as (NULL, 0), the reference's MPI_PROC_NULL.  Call it where the buffers of sph_exchange_buffers(which) would be
  * moved.  Blocks until the outgoing messages are in host memory; the incoming ones are copied stream-ordered. */

@@ -320,7 +320,7 @@ extern "C" int sph_exchange_buffers(sph_ctx *ctx, int which, void **sl, void **r
 
 // The exchange for a host whose transport moves HOST memory (plain MPI_Sendrecv, sockets): the message buffers are
 // staged through pinned memory around two calls of the host's sendrecv, ordered like the reference's own pair of
-// MPI_Sendrecv (communication.c:173-199: to the right / from the left, then to the left / from the right), so a
+// MPI_Sendrecv (communication.c:158-161, :340-344: to the right / from the left, then to the left / from the right), so a
 // blocking transport cannot deadlock.  An absent neighbour is (NULL, 0), the reference's MPI_PROC_NULL.
 extern "C" int sph_exchange_via_host(sph_ctx *ctx, int which, sph_sendrecv_fn fn, void *user)
 {
