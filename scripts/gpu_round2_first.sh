@@ -9,9 +9,10 @@
 #   python -m sph_b200.build --variant packed_b3 -DSPH_PACKED=1 -DSPH_BLOCKS_ADVECT=3     # no spills, fewer warps
 #   python -m sph_b200.build --variant pd4 -DSPH_RELAX_PD4=1                               # k_relax: one 16-byte record per neighbour
 #   python -m sph_b200.build --variant relax_b3 -DSPH_BLOCKS_RELAX=3                       # k_relax at 85 registers (param reloads gone)
+#   python -m sph_b200.build --variant pdl -DSPH_PDL=1                                     # programmatic dependent launch of all 11 kernels of a step
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -15 | tee gpurun_out/r2_gpu_tests.txt
-VARIANTS="${VARIANTS:-packed packed_relax packed_b3 pd4 relax_b3}" bash scripts/gpu_variants.sh 2>&1 | tee gpurun_out/r2_variants.txt
+VARIANTS="${VARIANTS:-packed packed_relax packed_b3 pd4 relax_b3 pdl}" bash scripts/gpu_variants.sh 2>&1 | tee gpurun_out/r2_variants.txt
 python bench.py --steps 60 --warmup 5 --no-cpu-baseline --preset y --visc-stab 0.5 --preroll 300 > gpurun_out/bench_goo_stab.json 2> gpurun_out/bench_goo_stab.err
 python - <<'PY'
 import json

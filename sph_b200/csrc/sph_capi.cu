@@ -12,8 +12,32 @@
 #include <vector>
 
 // every kernel launch of the library: SPH_THREADS threads per block, no dynamic shared memory
-#ifndef SPH_EMU
+#if !defined(SPH_EMU) && !SPH_PDL
 #define SPH_LAUNCH(kernel, grid, stream) kernel<<<(grid), SPH_THREADS, 0, (stream)>>>
+#elif !defined(SPH_EMU)
+// -DSPH_PDL=1: every launch may be scheduled while the kernel before it in the stream drains (pdl_enter() in
+// sph_device.cuh is the other half); stream capture records these as programmatic edges of the step graph
+template <class... A> struct PdlLauncher {
+    void (*kernel)(A...);
+    int grid;
+    cudaStream_t stream;
+    template <class... B> void operator()(B... args) const
+    {
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)grid);
+        cfg.blockDim = dim3(SPH_THREADS);
+        cfg.dynamicSmemBytes = 0;
+        cfg.stream = stream;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        cudaLaunchKernelEx(&cfg, kernel, static_cast<A>(args)...);     // errors: cudaGetLastError() after the launch
+    }
+};
+template <class... A> static PdlLauncher<A...> pdl_launcher(void (*k)(A...), int grid, cudaStream_t s) { return PdlLauncher<A...>{k, grid, s}; }
+#define SPH_LAUNCH(kernel, grid, stream) pdl_launcher(kernel, (grid), (stream))
 #else       // tests/emu: this file compiled by g++ against a fake runtime (test infrastructure, see sph_device.cuh)
 #define SPH_LAUNCH(kernel, grid, stream) emu::make_launcher(kernel, (grid), SPH_THREADS, (stream))
 #endif

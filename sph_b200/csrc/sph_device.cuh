@@ -158,6 +158,22 @@ __device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) { f32x2 r; asm("sub.rn.f
 __device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 __device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
 __device__ __forceinline__ f32x2 ld2(const float2 *p) { return *reinterpret_cast<const f32x2 *>(p); }
+// Programmatic dependent launch (build variant -DSPH_PDL=1; default off, then this is empty and the machine code
+// of every kernel is unchanged).  Every kernel of the library starts with pdl_enter(): it waits until the grid
+// before it in the stream has completed and its memory is visible -- nothing a predecessor wrote, *Pp and the
+// counters included, is read earlier, so the stream order is the one of plain launches -- and then lets the grid
+// after it be scheduled.  What overlaps is only the launch of grid n+1 (block scheduling, parameter loads)
+// with the tail of grid n: a step is 11 launches of 4-100 us each (13 on a slab), all dependent.
+#ifndef SPH_PDL
+#define SPH_PDL 0
+#endif
+__device__ __forceinline__ void pdl_enter()
+{
+#if SPH_PDL
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
 #else
 #include "sph_emu_ptx.h"      // tests/emu/fake/: host stand-ins for the helpers above (test infrastructure, not product code)
 #endif

@@ -230,6 +230,7 @@ k_advect(const DevParams *__restrict__ Pp, int *__restrict__ counters,
          float2 *__restrict__ pos_pred, int *__restrict__ cnt, int *__restrict__ t_key, int *__restrict__ t_slot,
          unsigned char *send_l, unsigned char *send_r, const float *__restrict__ coupling, const DevOptions *__restrict__ Op)
 {
+    pdl_enter();
     const DevParams P = *Pp;
     const float gamma = STAB ? Op->visc_gamma : 0.0f;
     const int n = counters[CN_NTOT];
@@ -382,6 +383,7 @@ k_coupling(const DevParams *__restrict__ Pp, const int *__restrict__ counters,
            const float2 *__restrict__ pos, const float2 *__restrict__ vel, const int *__restrict__ cell_start,
            float *__restrict__ coupling)
 {
+    pdl_enter();
     const DevParams P = *Pp;
     const int n = counters[CN_NTOT];
     const float h_recip = __fdiv_rn(1.0f, P.h);
@@ -449,6 +451,7 @@ k_unpack(const DevParams *__restrict__ Pp, int *__restrict__ counters, int which
          float2 *__restrict__ src_pos, float2 *__restrict__ src_q, uint32_t *__restrict__ src_uid,
          int *__restrict__ cnt, int *__restrict__ t_key, int *__restrict__ t_slot)
 {
+    pdl_enter();
     const DevParams P = *Pp;
     const int base = counters[CN_NTOT];
     int n_mig[2] = {0, 0}, n_halo[2] = {0, 0};
@@ -563,6 +566,7 @@ __global__ void __launch_bounds__(SPH_THREADS)
 k_scan_totals(const DevParams *__restrict__ Pp, int *__restrict__ counters, const int *__restrict__ cnt,
               int *__restrict__ tile_total)
 {
+    pdl_enter();
     __shared__ int s_sum[SPH_THREADS / 32], s_max[SPH_THREADS / 32], s_over[SPH_THREADS / 32];
     const int ncell = Pp->wx_new * Pp->sort_rows;
     const int ntiles = (ncell + SCAN_TILE - 1) / SCAN_TILE;
@@ -596,6 +600,7 @@ __global__ void __launch_bounds__(SPH_THREADS)
 k_scan_apply(DevParams *__restrict__ Pp, int *__restrict__ counters, int *__restrict__ cnt, int *__restrict__ cell_start,
              const int *__restrict__ tile_total, unsigned char *send_l, unsigned char *send_r, int end_of_step)
 {
+    pdl_enter();
     __shared__ int s_warp[SPH_THREADS / 32];
     __shared__ int s_prefix;
     const int ncell = Pp->wx_new * Pp->sort_rows;
@@ -689,6 +694,7 @@ k_scatter(const int *__restrict__ counters, const int *__restrict__ cell_start,
           const int *__restrict__ t_key, const int *__restrict__ t_slot, const uint32_t *__restrict__ src_uid,
           uint32_t *__restrict__ ord_uid, int *__restrict__ ord_src, int *__restrict__ ord_key)
 {
+    pdl_enter();
     const int n = counters[CN_NSRC];
     for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) {
         const int key = t_key[s];
@@ -712,6 +718,7 @@ k_reorder(const DevParams *__restrict__ Pp, int *__restrict__ counters, const in
           const float2 *__restrict__ src_pos, const float2 *__restrict__ src_q,
           float2 *__restrict__ dst_pos, float2 *__restrict__ dst_q, uint32_t *__restrict__ dst_uid)
 {
+    pdl_enter();
     const int n = counters[CN_NTOT];
     int locals = 0;
     for (int d = blockIdx.x * blockDim.x + threadIdx.x; d < n; d += gridDim.x * blockDim.x) {
@@ -745,6 +752,7 @@ k_density(const DevParams *__restrict__ Pp, int *__restrict__ counters,
           const float2 *__restrict__ pos, const int *__restrict__ cell_start, float2 *__restrict__ dens,
           sph_mask_t *__restrict__ nmask SPH_PD4_PARAM)
 {
+    pdl_enter();
     const DevParams P = *Pp;
     const int n = counters[CN_NTOT];
     const float h_recip = __fdiv_rn(1.0f, P.h);
@@ -846,6 +854,7 @@ k_relax(const DevParams *__restrict__ Pp, int *__restrict__ counters,
         int *__restrict__ cnt, int *__restrict__ t_key, int *__restrict__ t_slot,
         unsigned char *send_l, unsigned char *send_r SPH_PD4_CPARAM)
 {
+    pdl_enter();
     const DevParams P = *Pp;
     const int n = counters[CN_NTOT];
     const float dt = P.dt, dt2 = dt * dt;
@@ -1018,6 +1027,7 @@ __global__ void __launch_bounds__(SPH_THREADS)
 k_bin_upload(const DevParams *__restrict__ Pp, int *__restrict__ counters, const float2 *__restrict__ pos,
              int *__restrict__ cnt, int *__restrict__ t_key, int *__restrict__ t_slot)
 {
+    pdl_enter();
     const DevParams P = *Pp;
     const int n = counters[CN_NTOT];
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
@@ -1036,6 +1046,7 @@ k_requeue(const DevParams *__restrict__ Pp, int *__restrict__ counters,
           int *__restrict__ cnt, int *__restrict__ t_key, int *__restrict__ t_slot,
           unsigned char *send_l, unsigned char *send_r)
 {
+    pdl_enter();
     const DevParams P = *Pp;
     const int n = counters[CN_NTOT];
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -1070,6 +1081,7 @@ __global__ void __launch_bounds__(SPH_THREADS)
 k_init_lattice(float min_x, float min_y, float spacing, int start_col, int ncols, int rows, int total_cols,
                float2 *__restrict__ pos, float2 *__restrict__ vel, uint32_t *__restrict__ uid)
 {
+    pdl_enter();
     const long long n = (long long)ncols * rows;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         const int row = (int)(i / ncols), col = (int)(i % ncols);
@@ -1087,6 +1099,7 @@ __global__ void __launch_bounds__(SPH_THREADS)
 k_pack_coords(const DevParams *__restrict__ Pp, int *__restrict__ counters, const float2 *__restrict__ pos,
               const uint32_t *__restrict__ uid, short2 *__restrict__ out, int cap)
 {
+    pdl_enter();
     const DevParams P = *Pp;
     const int n = counters[CN_NTOT];
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -1107,6 +1120,7 @@ k_pack_coords(const DevParams *__restrict__ Pp, int *__restrict__ counters, cons
 // and how many exceed the reference's capacity of 100 (hash.c:160-165 drops the excess silently).
 __global__ void k_bucket_stats(const DevParams *__restrict__ Pp, const int *__restrict__ cell_start, int *__restrict__ out)
 {
+    pdl_enter();
     const DevParams P = *Pp;
     const int cols = P.wx / SPH_CELL_DIV, rows = P.sort_rows / SPH_CELL_DIV;
     int mx = 0, over = 0;
@@ -1128,6 +1142,7 @@ __global__ void k_bucket_stats(const DevParams *__restrict__ Pp, const int *__re
 __global__ void k_export_cells(const DevParams *__restrict__ Pp, const int *__restrict__ counters,
                                const float2 *__restrict__ pos, uint32_t *__restrict__ cell)
 {
+    pdl_enter();
     const DevParams P = *Pp;
     const int n = counters[CN_NTOT];
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -1142,6 +1157,7 @@ __global__ void k_export_pairs(const DevParams *__restrict__ Pp, const int *__re
                                unsigned long long cap, unsigned long long *__restrict__ n_pairs,
                                int *__restrict__ fwd_count)
 {
+    pdl_enter();
     const DevParams P = *Pp;
     const int n = counters[CN_NTOT];
     const float h2 = __fmul_rn(P.h, P.h);

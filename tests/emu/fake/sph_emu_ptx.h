@@ -16,3 +16,4 @@ static inline int ld_acquire_sys(const int *p) { return __atomic_load_n(p, __ATO
 static inline void st_release_sys(int *p, int v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
 static inline float rsqrt_approx(float x) { return 1.0f / sqrtf(x); }
 static inline float sqrt_approx(float x) { return sqrtf(x); }
+static inline void pdl_enter() {}   // launches of the emulator are already serialised
