@@ -61,3 +61,30 @@ def test_shipped_kernels_are_the_profiled_kernels(built_lib):
                         os.path.join(root, "profiles", "r1_sass_hashes.json")], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout
     assert r.stdout.count("same") == 14, r.stdout
+
+
+def test_pdl_variant_builds_and_every_kernel_waits_before_it_reads(built_lib):
+    """-DSPH_PDL=1: every kernel entry point must carry the grid-dependency wait (SASS ACQBULK) and
+    the early trigger (PREEXIT), the wait before the first global load -- a kernel without it would read what its
+    predecessor in the stream is still writing.  The default build has neither instruction."""
+    import subprocess
+    from sph_b200.build import build
+    os.makedirs(os.path.join(os.path.dirname(built_lib), "variants"), exist_ok=True)
+    lib = build(force=True, defines=("SPH_PDL=1",), out_name=os.path.join("variants", "pdl_test.so"))
+    per_kernel, name = {}, None
+    for line in subprocess.run(["cuobjdump", "-sass", lib], check=True, capture_output=True, text=True).stdout.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            name = m.group(1); per_kernel[name] = []
+            continue
+        m = re.match(r"\s*/\*[0-9a-f]{4,}\*/\s+(?:@!?U?P\d\s+)?([A-Z0-9_.]+)", line)
+        if m and name:
+            per_kernel[name].append(m.group(1))
+    assert len(per_kernel) >= 17
+    for k, ops in per_kernel.items():
+        assert "ACQBULK" in ops and "PREEXIT" in ops, k
+        first_global = min(i for i, o in enumerate(ops) if o.startswith(("LDG", "STG", "ATOMG", "RED", "LD.", "ST.")))
+        assert ops.index("ACQBULK") < first_global, k
+    base = subprocess.run(["cuobjdump", "-sass", built_lib], check=True, capture_output=True, text=True).stdout
+    assert "ACQBULK" not in base and "PREEXIT" not in base
+    os.remove(lib)
