@@ -70,6 +70,11 @@ void sph_ref_set_mirror(int every_n_steps);
 /* what MPI_Comm_rank / MPI_Comm_size(MPI_COMM_COMPUTE) say on this rank (partitionProblem asks them,
  * geometry.c:105-108; the library itself does not link MPI).  Default 0 of 1. */
 void sph_ref_set_rank(int rank, int nranks);
+/* Several compute ranks, one slab each: how this rank's neighbour messages travel (sph_exchange_via_host's callback;
+ * side 0 = rank - 1, 1 = rank + 1).  Without a transport an attach with nranks > 1 is refused.  An unmodified driver
+ * cannot make these two calls: it links sph_b200/host/glue/sph_ref_mpi_glue.c instead, whose sph_ref_host_mpi() the
+ * library finds by itself and which answers both questions from MPI_COMM_COMPUTE. */
+void sph_ref_set_transport(sph_sendrecv_fn fn, void *user);
 
 /* ---- fluid.h:112-126 ---- */
 void apply_gravity(fluid_particle **fluid_particle_pointers, param *params);
@@ -99,7 +104,8 @@ unsigned int hash_val(float x, float y, neighbor_grid_t *grid, param *params);
 void hash_fluid(fluid_particle **fluid_particle_pointers, neighbor_grid_t *grid, param *params, bool compute_density);
 void hash_halo(fluid_particle **fluid_particle_pointers, neighbor_grid_t *grid, param *params, bool compute_density);
 
-/* ---- communication.h:65-70 (one rank: nothing to exchange; slabs use sph_b200.h's message API) ---- */
+/* ---- communication.h:65-70 (one rank: nothing to exchange; several ranks: identify_oob_particles moves migrants +
+ *      ghost layer, the startHaloExchange after updateVelocities moves the relaxed ghost layer, through the transport) ---- */
 void startHaloExchange(fluid_particle **fluid_particle_pointers, fluid_particle *fluid_particles, edge_t *edges, param *params);
 void finishHaloExchange(fluid_particle **fluid_particle_pointers, fluid_particle *fluid_particles, edge_t *edges, param *params);
 void transferOOBParticles(fluid_particle **fluid_particle_pointers, fluid_particle *fluid_particles, oob_t *out_of_bounds, param *params);

@@ -23,6 +23,12 @@
  *
  * Per frame the stub moves the mover (cx = W (0.25 + 0.03 f), cy = 0.3 H) and after --frames frames it
  * sets kill_sim (renderer.c:340-345).
+ *
+ * --ranks K (K > 1): K compute ranks as forked processes over the mini-MPI's neighbour rings, each with its own
+ * render stub (same mover path, the rank's own slab edges from its first block: no rebalancing) and its own
+ * record <out>.r<rank>, whose frames hold that rank's particles.  With libsph_b200.so in front this is the
+ * unmodified driver running one slab per rank (sph_b200/host/glue/sph_ref_mpi_glue.c is linked into both binaries;
+ * only the library ever calls it).
  */
 #define _GNU_SOURCE
 #include <dlfcn.h>
@@ -30,6 +36,8 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <sys/wait.h>
+#include <unistd.h>
 
 #include "mpi.h"
 #include "fluid.h"
@@ -42,6 +50,7 @@ static struct {
     tunable_parameters first, current;
     int have_first;
     FILE *out;
+    volatile double *shared;     /* --ranks K: world size, written by rank 0's stub */
 } R;
 
 static void r_bcast(void *buf, size_t bytes)
@@ -64,7 +73,10 @@ static void write_header(void)
 
 static void r_from_compute(const void *buf, size_t bytes, int tag)
 {
-    if (tag == 8 && bytes == 8) memcpy(R.world, buf, 8);                 /* fluid.c:169 */
+    if (tag == 8 && bytes == 8) {                                        /* fluid.c:169: compute rank 0 only */
+        memcpy(R.world, buf, 8);
+        if (R.shared) { R.shared[0] = R.world[0]; R.shared[1] = R.world[1]; }
+    }
     else if (tag == 9 && bytes == 4) memcpy(&R.n_global, buf, 4);        /* fluid.c:170 */
     else if (tag == MINI_MPI_TAG_GATHER && bytes == sizeof R.first) {    /* fluid.c:238 */
         memcpy(&R.first, buf, sizeof R.first);
@@ -87,6 +99,9 @@ static void r_scatter(void *buf, size_t bytes)
 {
     if (bytes != sizeof R.current || !R.have_first) { fprintf(stderr, "ref_drive: bad Scatterv\n"); exit(3); }
     const int f = R.scatters++;
+    /* several ranks: the stubs of ranks > 0 never hear the world size; rank 0's stub has left it in shared memory
+     * long before the first scatter (the ranks have met in every exchange of three steps by then) */
+    if (R.shared) { R.world[0] = (float)R.shared[0]; R.world[1] = (float)R.shared[1]; }
     R.current = R.first;
     R.current.mover_center_x = R.world[0] * (0.25f + 0.03f * (float)f);
     R.current.mover_center_y = R.world[1] * 0.3f;
@@ -113,10 +128,33 @@ static void report_binding(const char *name)
 int main(int argc, char **argv)
 {
     const char *out = "ref_drive.bin";
+    static char rank_out[4096];
+    int ranks = 1;
     R.frames_wanted = 4;
     for (int i = 1; i + 1 < argc; i++) {
         if (!strcmp(argv[i], "--frames")) R.frames_wanted = atoi(argv[i + 1]);
         if (!strcmp(argv[i], "--out")) out = argv[i + 1];
+        if (!strcmp(argv[i], "--ranks")) ranks = atoi(argv[i + 1]);
+    }
+    if (ranks > 1) {
+        /* before anything touches a device: every rank is a process of its own */
+        if (mini_mpi_world_create(ranks, (size_t)16 << 20)) { fprintf(stderr, "ref_drive: cannot create %d ranks\n", ranks); return 2; }
+        fflush(stdout);
+        int rank = -1;
+        for (int r = 0; r < ranks; r++) {
+            pid_t pid = fork();
+            if (pid < 0) { perror("fork"); return 2; }
+            if (pid == 0) { rank = r; break; }
+        }
+        if (rank < 0) {
+            int worst = 0, st;
+            while (wait(&st) > 0) if (!WIFEXITED(st) || WEXITSTATUS(st)) worst = WIFEXITED(st) ? WEXITSTATUS(st) : 5;
+            return worst;
+        }
+        mini_mpi_bind(rank);
+        R.shared = mini_mpi_shared_doubles();
+        snprintf(rank_out, sizeof rank_out, "%s.r%d", out, rank);
+        out = rank_out;
     }
     R.out = fopen(out, "wb");
     if (!R.out) { perror(out); return 2; }

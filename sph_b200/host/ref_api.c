@@ -15,6 +15,25 @@
  * from the last one pushed is sent to the device before the stage is enqueued, which reproduces
  * where the render rank's scatter lands (between predict_positions and the later calls,
  * fluid.c:279-310).
+ *
+ * More than one compute rank (one slab per rank, geometry.c:101-160).  The library does not link MPI; the
+ * host's transport reaches it through sph_ref_set_transport() or, for a driver that is not touched at all,
+ * through the weak hook sph_ref_host_mpi() that the glue object sph_b200/host/glue/sph_ref_mpi_glue.c
+ * defines (compiled with the host's own mpi.h, added to the link line).  Then:
+ *
+ *   identify_oob_particles              -> exchange 0: migrants + ghost layer with predicted positions, one message
+ *                                          per neighbour (transferOOBParticles, communication.c:249-450, and the
+ *                                          first start/finishHaloExchange, :120-246, in one meeting)
+ *   first start/finishHaloExchange      nothing left to do (hash_halo likewise: the sort bins the ghosts)
+ *   startHaloExchange after updateVelocities -> exchange 1: relaxed position + velocity of the ghost layer
+ *   hash_fluid(false)                   -> sph_sort, unpacks them
+ *
+ * Both go through sph_exchange_via_host, i.e. two send/receive pairs in the reference's own order
+ * (communication.c:158-161).  New slab edges in a scattered block take effect at the next predict_positions:
+ * the device has binned the predicted positions into the old window by the time the scatter lands.  Results
+ * do not depend on where the edges are, so this shifts the balancer by one sub-step and nothing else.
+ * The host mirror then also maintains the pointer array: slot i of the particle array holds the i-th local
+ * particle in ascending uid, pointers past the local count are NULL (fluid.c:758-759).
  */
 #include "sph_ref_api.h"
 
@@ -34,8 +53,39 @@ static struct {
     int mirror_every;           /* ... every N completed steps (1 = every step) */
     long steps_done;
     int rank, nranks;           /* what MPI_Comm_rank/size(MPI_COMM_COMPUTE) would say (geometry.c:105-108) */
+    float edge_start, edge_end; /* several ranks: the slab edges in force on the device (they change at step boundaries only) */
+    int relaxed;                /* several ranks: updateVelocities has run, the next startHaloExchange is exchange 1 */
+    int capacity;
     char err[256];
 } G = { .nranks = 1 };
+
+/* what the host told us; survives attach / detach */
+static struct {
+    sph_sendrecv_fn fn;
+    void *user;
+    int asked;
+    int x_start, len_x, total_x;    /* this rank's share of the lattice columns (partitionProblem) */
+    fluid_particle *base;           /* the particle array behind the pointer array (identify_oob_particles carries it) */
+} H;
+
+/* Defined by the host's glue object, if there is one (sph_b200/host/glue/sph_ref_mpi_glue.c). */
+extern int sph_ref_host_mpi(int *rank, int *nranks, sph_sendrecv_fn *fn, void **user) __attribute__((weak));
+
+static void ask_host(void)
+{
+    if (H.asked) return;
+    H.asked = 1;
+    if (!sph_ref_host_mpi) return;
+    int rank = 0, nranks = 1;
+    sph_sendrecv_fn fn = NULL;
+    void *user = NULL;
+    if (sph_ref_host_mpi(&rank, &nranks, &fn, &user) == 0 && nranks >= 1 && rank >= 0 && rank < nranks) {
+        G.rank = rank; G.nranks = nranks;
+        H.fn = fn; H.user = user;
+    }
+}
+
+void sph_ref_set_transport(sph_sendrecv_fn fn, void *user) { H.fn = fn; H.user = user; H.asked = 1; }
 
 static void note(const char *where, int rc)
 {
@@ -50,8 +100,10 @@ sph_ctx *sph_ref_context(void) { return G.ctx; }
 static void sync_params(const char *where, const param *params)
 {
     if (!G.ctx) { note(where, SPH_ERR_STATE); return; }
-    if (G.have_pushed && memcmp(&G.pushed, &params->tunable_params, sizeof(sph_tunable)) == 0) return;
-    G.pushed = params->tunable_params;
+    sph_tunable t = params->tunable_params;
+    if (G.nranks > 1) { t.node_start_x = G.edge_start; t.node_end_x = G.edge_end; }    /* new edges wait for predict_positions */
+    if (G.have_pushed && memcmp(&G.pushed, &t, sizeof(sph_tunable)) == 0) return;
+    G.pushed = t;
     G.have_pushed = 1;
     note(where, sph_set_params(G.ctx, &G.pushed));
 }
@@ -62,11 +114,12 @@ void sph_ref_set_mirror(int every_n_steps) { G.mirror = every_n_steps > 0; G.mir
 int sph_ref_attach(fluid_particle **pointers, param *params, AABB_t *boundary, neighbor_grid_t *grid, int device)
 {
     sph_ref_detach();
-    if (G.nranks > 1) {
-        /* start/finishHaloExchange and transferOOBParticles are no-ops here: carrying on would simulate every slab as
-         * if it were alone.  Slabs are driven through the handle API. */
-        snprintf(G.err, sizeof G.err, "sph_ref_attach: the reference-named entry points serve ONE compute rank (got %d); "
-                 "a multi-rank host drives its slabs through the handle API (sph_create with rank/nranks, sph_exchange_buffers)", G.nranks);
+    ask_host();
+    if (G.nranks > 1 && !H.fn) {
+        /* without a transport start/finishHaloExchange and transferOOBParticles could do nothing: carrying on would
+         * simulate every slab as if it were alone */
+        snprintf(G.err, sizeof G.err, "sph_ref_attach: without a transport the reference-named entry points serve ONE compute rank "
+                 "(got %d): link host/glue/sph_ref_mpi_glue.c, call sph_ref_set_transport, or use the handle API", G.nranks);
         fprintf(stderr, "sph_ref_api: %s\n", G.err);
         return SPH_ERR_STATE;
     }
@@ -85,6 +138,16 @@ int sph_ref_attach(fluid_particle **pointers, param *params, AABB_t *boundary, n
     if (cfg.capacity < 1) cfg.capacity = 1;
     cfg.msg_capacity = 1;
     cfg.device = device; cfg.rank = 0; cfg.nranks = 1;
+    if (nranks > 1) {
+        /* a message carries the ghost layer (2 h of a column of fluid) plus the migrants of one step */
+        const int rows = (int)ceilf(cfg.tank_h / cfg.h);
+        cfg.msg_capacity = 30 * rows > 4096 ? 30 * rows : 4096;
+        cfg.capacity += 2 * cfg.msg_capacity;
+        cfg.rank = rank; cfg.nranks = nranks;
+        G.edge_start = params->tunable_params.node_start_x;
+        G.edge_end = params->tunable_params.node_end_x;
+    }
+    G.capacity = cfg.capacity;
     int rc = sph_create(&cfg, &G.ctx);
     if (rc) { note("sph_ref_attach", rc); if (G.ctx) { sph_destroy(G.ctx); G.ctx = NULL; } return rc; }
     G.tank_w = cfg.tank_w; G.tank_h = cfg.tank_h;
@@ -99,7 +162,19 @@ int sph_ref_attach(fluid_particle **pointers, param *params, AABB_t *boundary, n
     sync_params("sph_ref_attach", params);
     sph_particle *flat = (sph_particle *)malloc((size_t)(n > 0 ? n : 1) * sizeof(sph_particle));
     for (int i = 0; i < n; i++) flat[i] = *pointers[i];
-    rc = sph_upload(G.ctx, flat, NULL, n);           /* uid = pointer index */
+    uint32_t *uid = NULL;
+    if (nranks > 1) {
+        /* one numbering for all ranks: the pointer index the particle has in a one-rank run, row-major over the whole
+         * lattice (geometry.c:44-62) -- the order inside a cell, hence every bit of the result, is then the one-rank
+         * run's.  A host that did not come through partitionProblem gets disjoint blocks per rank. */
+        uid = (uint32_t *)malloc((size_t)(n > 0 ? n : 1) * sizeof(uint32_t));
+        const int lattice = H.len_x > 0 && H.total_x >= H.len_x && n % H.len_x == 0;
+        for (int i = 0; i < n; i++)
+            uid[i] = lattice ? (uint32_t)((i / H.len_x) * H.total_x + H.x_start + i % H.len_x)
+                             : (uint32_t)rank * (uint32_t)params->number_fluid_particles_global + (uint32_t)i;
+    }
+    rc = sph_upload(G.ctx, flat, uid, n);            /* one rank: uid = pointer index */
+    free(uid);
     free(flat);
     G.n = n;
     note("sph_ref_attach", rc);
@@ -115,9 +190,18 @@ void sph_ref_detach(void)
 int sph_ref_sync_to_host(fluid_particle **pointers, param *params)
 {
     if (!G.ctx) return SPH_ERR_STATE;
-    sph_particle *flat = (sph_particle *)malloc((size_t)(G.n > 0 ? G.n : 1) * sizeof(sph_particle));
+    const int room = G.nranks > 1 ? G.capacity : G.n;
+    sph_particle *flat = (sph_particle *)malloc((size_t)(room > 0 ? room : 1) * sizeof(sph_particle));
     int n = sph_download(G.ctx, flat, NULL, SPH_ORDER_UID, 0);
     if (n < 0) { free(flat); note("sph_ref_sync_to_host", -n); return -n; }
+    if (G.nranks > 1) {
+        /* the population changes with every migration (communication.c:370-431 rewires the pointer array there) */
+        if (!H.base && n > G.n) { free(flat); note("sph_ref_sync_to_host", SPH_ERR_STATE); return SPH_ERR_STATE; }
+        for (int i = 0; i < n && H.base; i++) pointers[i] = H.base + i;
+        for (int i = n; i < G.n; i++) pointers[i] = NULL;
+        G.n = n;
+        params->max_fluid_particle_index = n - 1;
+    }
     for (int i = 0; i < n; i++) { *pointers[i] = flat[i]; pointers[i]->id = i; }
     free(flat);
     params->number_fluid_particles_local = n;
@@ -159,9 +243,12 @@ static void lazy_attach(fluid_particle **pointers, AABB_t *boundary, param *para
     neighbor_grid_t grid;
     memset(&grid, 0, sizeof grid);
     grid.spacing = params->tunable_params.smoothing_radius;
-    const char *dev = getenv("SPH_B200_DEVICE"), *every = getenv("SPH_REF_MIRROR_EVERY");
+    const char *dev = getenv("SPH_B200_DEVICE"), *ndev = getenv("SPH_B200_DEVICES"), *every = getenv("SPH_REF_MIRROR_EVERY");
     if (!G.mirror) sph_ref_set_mirror(every && atoi(every) > 0 ? atoi(every) : 1);
-    const int rc = sph_ref_attach(pointers, params, boundary, &grid, dev ? atoi(dev) : 0);
+    ask_host();
+    /* several ranks on one box: SPH_B200_DEVICES=8 spreads them, rank r on device r mod 8 */
+    const int device = dev ? atoi(dev) : (ndev && atoi(ndev) > 0 ? G.rank % atoi(ndev) : 0);
+    const int rc = sph_ref_attach(pointers, params, boundary, &grid, device);
     if (rc != SPH_OK) {
         fprintf(stderr, "sph_ref_api: cannot put the simulation on the GPU (%s); there is no CPU path\n", G.err);
         abort();
@@ -179,13 +266,22 @@ void predict_positions(fluid_particle **pointers, AABB_t *boundary_global, param
         return;
     }
     G.pending_gravity = G.pending_viscosity = 0;
+    if (G.nranks > 1 && (params->tunable_params.node_start_x != G.edge_start || params->tunable_params.node_end_x != G.edge_end)) {
+        /* the balancer moved this slab (renderer.c:427-477): the step boundary is where the device can follow */
+        G.edge_start = params->tunable_params.node_start_x;
+        G.edge_end = params->tunable_params.node_end_x;
+        G.pushed = params->tunable_params;
+        note("predict_positions", sph_queue_params(G.ctx, &G.pushed));
+    }
     note("predict_positions", sph_advect(G.ctx));
 }
 
 void identify_oob_particles(fluid_particle **pointers, fluid_particle *particles, oob_t *oob, AABB_t *b, param *params)
 {
-    (void)pointers; (void)particles; (void)oob; (void)b;
+    (void)pointers; (void)oob; (void)b;
+    H.base = particles;
     sync_params("identify_oob_particles", params);     /* the scatter has landed by now (fluid.c:293-310) */
+    if (G.nranks > 1) note("identify_oob_particles", sph_exchange_via_host(G.ctx, 0, H.fn, H.user));
 }
 
 void double_density_relaxation(fluid_particle **pointers, neighbor *neighbors, param *params)
@@ -206,6 +302,7 @@ void updateVelocities(fluid_particle **pointers, edge_t *edges, AABB_t *boundary
     }
     G.pending_relax = 0;
     note("updateVelocities", sph_relax(G.ctx));
+    G.relaxed = 1;
 }
 
 /* ------------------------------------------------------------------ hash.h */
@@ -217,6 +314,7 @@ void hash_fluid(fluid_particle **pointers, neighbor_grid_t *grid, param *params,
     int rc = sph_sort(G.ctx);
     note("hash_fluid", rc);
     if (rc == SPH_OK && compute_density) note("hash_fluid", sph_density(G.ctx));
+    if (!compute_density) G.relaxed = 0;
     if (rc == SPH_OK && !compute_density) {
         /* the re-hash of fluid.c:341 ends the step: positions and velocities are final */
         G.steps_done++;
@@ -238,10 +336,20 @@ unsigned int hash_val(float x, float y, neighbor_grid_t *grid, param *params)
     return row * grid->size_x + col;
 }
 
-/* ------------------------------------------------------------------ communication.h (one rank) */
+/* ------------------------------------------------------------------ communication.h */
 
 void startHaloExchange(fluid_particle **pointers, fluid_particle *particles, edge_t *edges, param *params)
-{ (void)pointers; (void)particles; (void)edges; (void)params; }
+{
+    (void)pointers; (void)edges; (void)params;
+    H.base = particles;
+    /* the call after updateVelocities (fluid.c:337) carries the relaxed ghost layer; the one before the relaxation
+     * (fluid.c:318) has nothing left to move, its ghosts came with the migrants.  (A one-exchange build of the library
+     * relaxes its ghosts itself and skips this meeting.) */
+    if (G.ctx && G.nranks > 1 && G.relaxed && sph_exchanges_per_step() == 2) {
+        G.relaxed = 0;
+        note("startHaloExchange", sph_exchange_via_host(G.ctx, 1, H.fn, H.user));
+    }
+}
 void finishHaloExchange(fluid_particle **pointers, fluid_particle *particles, edge_t *edges, param *params)
 { (void)pointers; (void)particles; (void)edges; params->number_halo_particles = 0; }
 void transferOOBParticles(fluid_particle **pointers, fluid_particle *particles, oob_t *oob, param *params)
@@ -287,6 +395,7 @@ void setParticleNumbers(AABB_t *boundary_global, AABB_t *fluid_global, edge_t *e
 
 void partitionProblem(AABB_t *boundary_global, AABB_t *fluid_global, int *x_start, int *length_x, float spacing, param *params)
 {
+    ask_host();
     const int nprocs = G.nranks, rank = G.rank;                                     /* geometry.c:105-108 */
     const int fluid_particles_x = (int)floor((fluid_global->max_x - fluid_global->min_x) / spacing) + 1;   /* :112 */
     const int equal = fluid_particles_x / nprocs, remaining = fluid_particles_x - equal * nprocs;          /* :118-125 */
@@ -299,6 +408,7 @@ void partitionProblem(AABB_t *boundary_global, AABB_t *fluid_global, int *x_star
     }
     *x_start = number_to_left;                                                      /* :137-139 */
     *length_x = mine;
+    H.x_start = number_to_left; H.len_x = mine; H.total_x = total_x;
     sph_tunable *t = &params->tunable_params;
     t->node_start_x = fluid_global->min_x + ((number_to_left - 1) * spacing);       /* :142-143 */
     t->node_end_x = t->node_start_x + (mine * spacing);

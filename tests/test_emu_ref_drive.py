@@ -50,6 +50,54 @@ def test_unmodified_reference_driver_on_the_emulated_library(built_lib, tmp_path
         assert np.array_equal(pack(s["x"], s["y"], w, h), got), k
 
 
+def frames_of_all_ranks(out, ranks):
+    """-> world, per frame: [coords of rank 0, rank 1, ...] from <out>.r<rank> (oracle/ref_build/ref_drive.c --ranks)"""
+    parts = [read_drive(f"{out}.r{r}") for r in range(ranks)]
+    n, w, h = parts[0][:3]                       # only compute rank 0 tells its render rank (fluid.c:167-171)
+    return n, w, h, [[p[4][k][1] for p in parts] for k in range(len(parts[0][4]))], [p[3] for p in parts]
+
+
+def check_ranks_against_one_rank(drive, env, tmp_path, ranks, frames, libname):
+    """The unmodified driver as `ranks` compute ranks (one slab each, over the mini-MPI, glue object linked in)
+    against the same driver as ONE rank: every frame must hold the same pixels, bit for bit, whoever owns them."""
+    one, many = str(tmp_path / "one.bin"), str(tmp_path / "many.bin")
+    r1 = subprocess.run([drive, "--frames", str(frames), "--out", one], capture_output=True, text=True, timeout=300, env=env)
+    assert r1.returncode == 0, (r1.stdout[-300:], r1.stderr[-800:])
+    rk = subprocess.run([drive, "--ranks", str(ranks), "--frames", str(frames), "--out", many], capture_output=True,
+                        text=True, timeout=600, env=env)
+    assert rk.returncode == 0, (rk.stdout[-300:], rk.stderr[-800:])
+    b = bindings(rk.stdout)
+    assert b["start_simulation"].endswith("libref_driver.so")
+    assert all(b[k].endswith(libname) for k in HOT), b
+    assert "sph_ref_api:" not in rk.stderr, rk.stderr[-800:]          # no stage reported an error
+    n, w, h, first, f1 = read_drive(one)
+    nk, wk, hk, fk, firsts = frames_of_all_ranks(many, ranks)
+    assert (nk, wk, hk) == (n, w, h) and len(fk) == len(f1) == frames
+    # the slabs are partitionProblem's (geometry.c:101-160): contiguous, covering the tank
+    assert firsts[0].node_start_x == 0.0 and firsts[-1].node_end_x == np.float32(w)
+    moved = False
+    for k in range(frames):
+        counts = [len(c) for c in fk[k]]
+        assert sum(counts) == n, (k, counts)                          # nobody lost, nobody duplicated
+        moved |= counts != [len(c) for c in fk[0]]
+        got = np.sort(np.concatenate(fk[k]).copy().view("i4").ravel())
+        want = np.sort(f1[k][1].copy().view("i4").ravel())
+        assert np.array_equal(got, want), k
+    assert moved                                                      # particles did change owner on the way
+
+
+@pytest.mark.skipif(not os.path.exists(GPU_DRIVE), reason="oracle/_ref not built")
+@pytest.mark.parametrize("ranks,mirror_every", [(3, None), (2, "4"), (4, None)])
+def test_unmodified_reference_driver_with_several_compute_ranks_on_the_emulated_library(built_lib, tmp_path, ranks, mirror_every):
+    """BASELINE config 1's shape (mpirun -n 4: 1 render + 3 compute ranks) through the reference-named entry points:
+    identify_oob_particles / startHaloExchange move the slab messages through the host's MPI_Sendrecv
+    (sph_b200/host/glue/sph_ref_mpi_glue.c -> sph_exchange_via_host)."""
+    env = dict(os.environ, LD_PRELOAD=build_emu())
+    if mirror_every:
+        env["SPH_REF_MIRROR_EVERY"] = mirror_every
+    check_ranks_against_one_rank(GPU_DRIVE, env, tmp_path, ranks, 8, "libsph_emu.so")
+
+
 def test_reference_call_order_on_the_emulated_library(built_lib, monkeypatch):
     """tests/test_ref_api.py's GPU test (the reference's call sequence through the reference-named entry points
     equals sph_step bit for bit) with the emulator library in place of libsph_b200.so."""

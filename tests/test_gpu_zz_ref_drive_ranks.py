@@ -1,0 +1,22 @@
+"""The reference's UNMODIFIED start_simulation() as SEVERAL compute ranks on the B200 path (written after round 1's GPU
+budget was spent; the same check passes on the kernel-source emulator, tests/test_emu_ref_drive.py; this file sorts
+last among the GPU files on purpose).  Every rank is a process of its own with one slab; all of them share device 0
+unless SPH_B200_DEVICES says how many devices to spread over.  Run on the B200 box: pytest -m gpu."""
+import os
+
+import pytest
+
+from test_emu_ref_drive import check_ranks_against_one_rank
+from test_ref_drive import GPU_DRIVE
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.skipif(not os.path.exists(GPU_DRIVE), reason="oracle/_ref not built")
+@pytest.mark.parametrize("ranks", [3])
+def test_unmodified_reference_driver_with_several_compute_ranks_on_the_gpu_path(built_lib, tmp_path, ranks):
+    import torch
+    env = dict(os.environ)
+    if torch.cuda.device_count() > 1:
+        env["SPH_B200_DEVICES"] = str(torch.cuda.device_count())
+    check_ranks_against_one_rank(GPU_DRIVE, env, tmp_path, ranks, 8, "libsph_b200.so")
