@@ -28,7 +28,9 @@
  * render stub (same mover path, the rank's own slab edges from its first block: no rebalancing) and its own
  * record <out>.r<rank>, whose frames hold that rank's particles.  With libsph_b200.so in front this is the
  * unmodified driver running one slab per rank (sph_b200/host/glue/sph_ref_mpi_glue.c is linked into both binaries;
- * only the library ever calls it).
+ * only the library ever calls it).  --wobble 1: the stubs also move every interior slab edge, the way the render rank's
+ * balancer does (renderer.c:427-477: h/8 per frame), three frames to the right from frame 2 and back again, so
+ * that particles change owner because the EDGE crossed them.
  */
 #define _GNU_SOURCE
 #include <dlfcn.h>
@@ -50,7 +52,8 @@ static struct {
     tunable_parameters first, current;
     int have_first;
     FILE *out;
-    volatile double *shared;     /* --ranks K: world size, written by rank 0's stub */
+    volatile double *shared;     /* --ranks K: world size, written by rank 0's stub; [8 + 2r], [9 + 2r]: first edges of rank r */
+    int rank, ranks, wobble;
 } R;
 
 static void r_bcast(void *buf, size_t bytes)
@@ -82,6 +85,7 @@ static void r_from_compute(const void *buf, size_t bytes, int tag)
         memcpy(&R.first, buf, sizeof R.first);
         R.current = R.first;
         R.have_first = 1;
+        if (R.shared) { R.shared[8 + 2 * R.rank] = R.first.node_start_x; R.shared[9 + 2 * R.rank] = R.first.node_end_x; }
         write_header();
     } else if (tag == 17) {                                              /* fluid.c:365 */
         int32_t pairs = (int32_t)(bytes / 4);
@@ -105,6 +109,13 @@ static void r_scatter(void *buf, size_t bytes)
     R.current = R.first;
     R.current.mover_center_x = R.world[0] * (0.25f + 0.03f * (float)f);
     R.current.mover_center_y = R.world[1] * 0.3f;
+    if (R.wobble && R.shared && R.ranks > 1) {
+        /* one expression for both sides of an edge: neighbours must agree on it to the bit */
+        const int k = f < 2 ? 0 : f < 5 ? f - 1 : f < 8 ? 7 - f : 0;
+        const float dx = R.first.smoothing_radius * 0.125f * (float)k;
+        if (R.rank > 0) R.current.node_start_x = (float)R.shared[8 + 2 * R.rank] + dx;
+        if (R.rank < R.ranks - 1) R.current.node_end_x = (float)R.shared[8 + 2 * (R.rank + 1)] + dx;
+    }
     R.current.kill_sim = f >= R.frames_wanted;
     memcpy(buf, &R.current, sizeof R.current);
 }
@@ -135,6 +146,7 @@ int main(int argc, char **argv)
         if (!strcmp(argv[i], "--frames")) R.frames_wanted = atoi(argv[i + 1]);
         if (!strcmp(argv[i], "--out")) out = argv[i + 1];
         if (!strcmp(argv[i], "--ranks")) ranks = atoi(argv[i + 1]);
+        if (!strcmp(argv[i], "--wobble")) R.wobble = atoi(argv[i + 1]);
     }
     if (ranks > 1) {
         /* before anything touches a device: every rank is a process of its own */
@@ -153,6 +165,7 @@ int main(int argc, char **argv)
         }
         mini_mpi_bind(rank);
         R.shared = mini_mpi_shared_doubles();
+        R.rank = rank; R.ranks = ranks;
         snprintf(rank_out, sizeof rank_out, "%s.r%d", out, rank);
         out = rank_out;
     }

@@ -57,14 +57,14 @@ def frames_of_all_ranks(out, ranks):
     return n, w, h, [[p[4][k][1] for p in parts] for k in range(len(parts[0][4]))], [p[3] for p in parts]
 
 
-def check_ranks_against_one_rank(drive, env, tmp_path, ranks, frames, libname):
+def check_ranks_against_one_rank(drive, env, tmp_path, ranks, frames, libname, wobble=0):
     """The unmodified driver as `ranks` compute ranks (one slab each, over the mini-MPI, glue object linked in)
     against the same driver as ONE rank: every frame must hold the same pixels, bit for bit, whoever owns them."""
     one, many = str(tmp_path / "one.bin"), str(tmp_path / "many.bin")
     r1 = subprocess.run([drive, "--frames", str(frames), "--out", one], capture_output=True, text=True, timeout=300, env=env)
     assert r1.returncode == 0, (r1.stdout[-300:], r1.stderr[-800:])
-    rk = subprocess.run([drive, "--ranks", str(ranks), "--frames", str(frames), "--out", many], capture_output=True,
-                        text=True, timeout=600, env=env)
+    rk = subprocess.run([drive, "--ranks", str(ranks), "--wobble", str(wobble), "--frames", str(frames), "--out", many],
+                        capture_output=True, text=True, timeout=600, env=env)
     assert rk.returncode == 0, (rk.stdout[-300:], rk.stderr[-800:])
     b = bindings(rk.stdout)
     assert b["start_simulation"].endswith("libref_driver.so")
@@ -75,6 +75,9 @@ def check_ranks_against_one_rank(drive, env, tmp_path, ranks, frames, libname):
     assert (nk, wk, hk) == (n, w, h) and len(fk) == len(f1) == frames
     # the slabs are partitionProblem's (geometry.c:101-160): contiguous, covering the tank
     assert firsts[0].node_start_x == 0.0 and firsts[-1].node_end_x == np.float32(w)
+    if wobble:      # the stubs moved the interior edges the way the balancer does (h/8 per frame) and back again
+        blocks = [read_drive(f"{many}.r1")[4][k][0] for k in range(frames)]
+        assert blocks[4].node_start_x > blocks[1].node_start_x and blocks[frames - 1].node_start_x == blocks[0].node_start_x
     moved = False
     for k in range(frames):
         counts = [len(c) for c in fk[k]]
@@ -87,15 +90,25 @@ def check_ranks_against_one_rank(drive, env, tmp_path, ranks, frames, libname):
 
 
 @pytest.mark.skipif(not os.path.exists(GPU_DRIVE), reason="oracle/_ref not built")
-@pytest.mark.parametrize("ranks,mirror_every", [(3, None), (2, "4"), (4, None)])
-def test_unmodified_reference_driver_with_several_compute_ranks_on_the_emulated_library(built_lib, tmp_path, ranks, mirror_every):
+@pytest.mark.parametrize("ranks,mirror_every,wobble", [(3, None, 0), (2, "4", 0), (4, None, 1), (3, "4", 1)])
+def test_unmodified_reference_driver_with_several_compute_ranks_on_the_emulated_library(built_lib, tmp_path, ranks, mirror_every,
+                                                                                        wobble):
     """BASELINE config 1's shape (mpirun -n 4: 1 render + 3 compute ranks) through the reference-named entry points:
     identify_oob_particles / startHaloExchange move the slab messages through the host's MPI_Sendrecv
-    (sph_b200/host/glue/sph_ref_mpi_glue.c -> sph_exchange_via_host)."""
+    (sph_b200/host/glue/sph_ref_mpi_glue.c -> sph_exchange_via_host); slab edges that move in mid-run follow at the
+    next predict_positions."""
     env = dict(os.environ, LD_PRELOAD=build_emu())
     if mirror_every:
         env["SPH_REF_MIRROR_EVERY"] = mirror_every
-    check_ranks_against_one_rank(GPU_DRIVE, env, tmp_path, ranks, 8, "libsph_emu.so")
+    check_ranks_against_one_rank(GPU_DRIVE, env, tmp_path, ranks, 10, "libsph_emu.so", wobble)
+
+
+@pytest.mark.skipif(not os.path.exists(GPU_DRIVE), reason="oracle/_ref not built")
+def test_several_compute_ranks_through_the_reference_names_on_the_one_exchange_build(built_lib, tmp_path):
+    """-DSPH_ONE_EXCHANGE=1 relaxes its ghosts itself: the startHaloExchange after updateVelocities has nothing to move
+    (sph_exchanges_per_step() == 1) and the frames are still the one-rank frames."""
+    lib = build_emu(defines=("SPH_ONE_EXCHANGE=1",), name="libsph_emu_sph_one_exchange1.so")
+    check_ranks_against_one_rank(GPU_DRIVE, dict(os.environ, LD_PRELOAD=lib), tmp_path, 3, 10, os.path.basename(lib), 1)
 
 
 def test_reference_call_order_on_the_emulated_library(built_lib, monkeypatch):

@@ -13,10 +13,10 @@ pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.skipif(not os.path.exists(GPU_DRIVE), reason="oracle/_ref not built")
-@pytest.mark.parametrize("ranks", [3])
-def test_unmodified_reference_driver_with_several_compute_ranks_on_the_gpu_path(built_lib, tmp_path, ranks):
+@pytest.mark.parametrize("ranks,wobble", [(3, 0), (3, 1)])
+def test_unmodified_reference_driver_with_several_compute_ranks_on_the_gpu_path(built_lib, tmp_path, ranks, wobble):
     import torch
     env = dict(os.environ)
     if torch.cuda.device_count() > 1:
         env["SPH_B200_DEVICES"] = str(torch.cuda.device_count())
-    check_ranks_against_one_rank(GPU_DRIVE, env, tmp_path, ranks, 8, "libsph_b200.so")
+    check_ranks_against_one_rank(GPU_DRIVE, env, tmp_path, ranks, 10, "libsph_b200.so", wobble)
