@@ -15,9 +15,12 @@
  * and MPI_Type_indexed over a struct type (block length 1 everywhere in the
  * reference: communication.c:174-185, :287-299, :317-325).
  *
- * The render-rank protocol (Bcast/Gatherv/Scatterv/Probe) is NOT implemented:
- * the harness drives the reference's physics/exchange functions directly and
- * never calls start_simulation()/start_renderer(); those entry points abort.
+ * The render-rank protocol (Bcast/Gatherv/Scatterv/Probe/Irecv between world
+ * rank 0 and the compute ranks) exists in two forms: hooks for a render stub
+ * living inside the compute process (mini_mpi_set_render, ref_drive.c), and a
+ * render rank that is a process of its own with one ring to and one from every
+ * compute rank (mini_mpi_world_create_render, ref_world.c: the reference's own
+ * renderer.c).  Without either, those calls abort.
  */
 #define _GNU_SOURCE
 #include "mpi.h"
@@ -41,6 +44,7 @@ typedef struct {
 
 typedef struct {
     int nranks;
+    int render_proc;          /* world rank 0 is a process of its own (mini_mpi_world_create_render) */
     size_t ring_bytes;
     volatile int barrier_count;
     volatile int barrier_sense;
@@ -59,16 +63,27 @@ static void die(const char *msg)
     abort();
 }
 
-int mini_mpi_world_create(int nranks, size_t ring_bytes)
+static int g_render_proc = 0;      /* the world has a render process ... */
+static int g_is_render = 0;        /* ... and this is it */
+
+static int world_create(int nranks, size_t ring_bytes, int render_proc);
+int mini_mpi_world_create(int nranks, size_t ring_bytes) { return world_create(nranks, ring_bytes, 0); }
+/* K compute ranks plus the render rank as a process of its own: two more rings per compute rank (to / from it) */
+int mini_mpi_world_create_render(int nranks, size_t ring_bytes) { return world_create(nranks, ring_bytes, 1); }
+void mini_mpi_bind_render(void) { g_is_render = 1; g_rank = -1; }
+
+static int world_create(int nranks, size_t ring_bytes, int render_proc)
 {
     if (nranks < 1 || nranks > 256) return -1;
-    size_t nrings = 2 * (size_t)nranks;
+    size_t nrings = (render_proc ? 4 : 2) * (size_t)nranks;
+    g_render_proc = render_proc;
     size_t bytes = sizeof(world_hdr_t) + nrings * sizeof(ring_ctl_t) + nrings * ring_bytes;
     void *m = mmap(NULL, bytes, PROT_READ | PROT_WRITE, MAP_SHARED | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
     if (m == MAP_FAILED) return -1;
     g_world = (world_hdr_t *)m;
     g_world->nranks = nranks;
     g_world->ring_bytes = ring_bytes;
+    g_world->render_proc = render_proc;
     g_world->barrier_count = 0;
     g_world->barrier_sense = 0;
     g_ctl = (ring_ctl_t *)((char *)m + sizeof(world_hdr_t));
@@ -285,15 +300,45 @@ static void do_recv(void *buf, int count, MPI_Datatype type, int src, int tag, M
 static int to_render(MPI_Comm comm, int rank);
 static int send_to_render(const void *buf, int count, MPI_Datatype type, int tag);
 
+/* ---- the render rank as a process of its own: rings 2K + 2r (compute r -> render) and 2K + 2r + 1 (render -> r) ---- */
+static int ring_up(int r) { return 2 * g_nranks + 2 * r; }
+static int ring_down(int r) { return 2 * g_nranks + 2 * r + 1; }
+static int compute_to_render_proc(MPI_Comm comm, int rank) { return g_render_proc && !g_is_render && comm == MPI_COMM_WORLD && rank == 0; }
+
+static void raw_send(int id, const void *buf, size_t bytes, int tag)
+{
+    msg_hdr_t h = { tag, (int)bytes };
+    ring_write(id, &h, sizeof h);
+    if (bytes) ring_write(id, buf, bytes);
+}
+
+static size_t raw_recv(int id, void *buf, size_t room, int tag)
+{
+    msg_hdr_t h;
+    ring_read(id, &h, sizeof h);
+    if (h.tag != tag) { fprintf(stderr, "mini-mpi: render protocol: got tag %d, want %d\n", h.tag, tag); abort(); }
+    if ((size_t)h.nbytes > room) die("render protocol: message truncated");
+    if (h.nbytes) ring_read(id, buf, (size_t)h.nbytes);
+    return (size_t)h.nbytes;
+}
+
 int MPI_Send(const void *buf, int count, MPI_Datatype type, int dest, int tag, MPI_Comm comm)
 {
+    if (compute_to_render_proc(comm, dest)) { raw_send(ring_up(g_rank), buf, type_bytes(type, count), tag); return MPI_SUCCESS; }
     if (to_render(comm, dest)) return send_to_render(buf, count, type, tag);
     do_send(buf, count, type, dest, tag);
     return MPI_SUCCESS;
 }
 
 int MPI_Recv(void *buf, int count, MPI_Datatype type, int src, int tag, MPI_Comm comm, MPI_Status *status)
-{ (void)comm; do_recv(buf, count, type, src, tag, status); return MPI_SUCCESS; }
+{
+    if (g_is_render) {      /* renderer.c:133,138: from world rank src = compute rank src - 1 */
+        size_t n = raw_recv(ring_up(src - 1), buf, type_bytes(type, count), tag);
+        if (status) { status->MPI_SOURCE = src; status->MPI_TAG = tag; status->MPI_ERROR = MPI_SUCCESS; status->_nbytes = (int)n; }
+        return MPI_SUCCESS;
+    }
+    (void)comm; do_recv(buf, count, type, src, tag, status); return MPI_SUCCESS;
+}
 
 int MPI_Sendrecv(const void *sendbuf, int sendcount, MPI_Datatype sendtype, int dest, int sendtag,
                  void *recvbuf, int recvcount, MPI_Datatype recvtype, int src, int recvtag,
@@ -320,7 +365,8 @@ static int new_req(void)
 
 int MPI_Isend(const void *buf, int count, MPI_Datatype type, int dest, int tag, MPI_Comm comm, MPI_Request *req)
 {
-    if (to_render(comm, dest)) send_to_render(buf, count, type, tag);
+    if (compute_to_render_proc(comm, dest)) raw_send(ring_up(g_rank), buf, type_bytes(type, count), tag);
+    else if (to_render(comm, dest)) send_to_render(buf, count, type, tag);
     else do_send(buf, count, type, dest, tag);
     int r = new_req();
     g_reqs[r].is_recv = 0;
@@ -331,6 +377,13 @@ int MPI_Isend(const void *buf, int count, MPI_Datatype type, int dest, int tag, 
 int MPI_Irecv(void *buf, int count, MPI_Datatype type, int src, int tag, MPI_Comm comm, MPI_Request *req)
 {
     (void)comm;
+    if (g_is_render) {
+        /* renderer.c:276-282 posts this right after MPI_Probe(MPI_ANY_SOURCE): the message must be CONSUMED here, or
+         * the next Probe would report the same rank again */
+        raw_recv(ring_up(src - 1), buf, type_bytes(type, count), tag);
+        *req = MPI_REQUEST_NULL;
+        return MPI_SUCCESS;
+    }
     int r = new_req();
     g_reqs[r].is_recv = 1;
     g_reqs[r].buf = buf; g_reqs[r].count = count; g_reqs[r].type = type;
@@ -379,27 +432,62 @@ static const mini_mpi_render_t *g_render = NULL;
 void mini_mpi_set_render(const mini_mpi_render_t *r) { g_render = r; }
 static int to_render(MPI_Comm comm, int rank) { return g_render && comm == MPI_COMM_WORLD && rank == 0; }
 
-int MPI_Comm_rank(MPI_Comm comm, int *rank) { *rank = g_rank + (g_render && comm == MPI_COMM_WORLD); return MPI_SUCCESS; }
-int MPI_Comm_size(MPI_Comm comm, int *size) { *size = g_nranks + (g_render && comm == MPI_COMM_WORLD); return MPI_SUCCESS; }
+int MPI_Comm_rank(MPI_Comm comm, int *rank) { *rank = g_rank + ((g_render || g_render_proc) && comm == MPI_COMM_WORLD); return MPI_SUCCESS; }
+int MPI_Comm_size(MPI_Comm comm, int *size) { *size = g_nranks + ((g_render || g_render_proc) && comm == MPI_COMM_WORLD); return MPI_SUCCESS; }
 int MPI_Comm_group(MPI_Comm comm, MPI_Group *group) { (void)comm; *group = 1; return MPI_SUCCESS; }
 int MPI_Group_excl(MPI_Group g, int n, const int r[], MPI_Group *ng) { (void)g; (void)n; (void)r; *ng = 2; return MPI_SUCCESS; }
 int MPI_Group_incl(MPI_Group g, int n, const int r[], MPI_Group *ng) { (void)g; (void)n; (void)r; *ng = 3; return MPI_SUCCESS; }
 int MPI_Comm_create(MPI_Comm c, MPI_Group g, MPI_Comm *nc)
-{ (void)c; *nc = (g_render && g == 2) ? COMM_COMPUTE : MPI_COMM_WORLD; return MPI_SUCCESS; }
+{ (void)c; *nc = ((g_render || g_render_proc) && g == 2) ? COMM_COMPUTE : MPI_COMM_WORLD; return MPI_SUCCESS; }
 int MPI_Group_free(MPI_Group *g) { *g = 0; return MPI_SUCCESS; }
 
 /* Render-rank protocol (fluid.c:122-124, :167-171, :238, :293-294, :365): served by the hooks when a
  * render stub is installed, otherwise deliberately unimplemented (see file header). */
 #define UNIMPL(name) do { die(name " is part of the render-rank protocol, not provided by this shim"); return -1; } while (0)
-int MPI_Probe(int s, int t, MPI_Comm c, MPI_Status *st) { (void)s; (void)t; (void)c; (void)st; UNIMPL("MPI_Probe"); }
+int MPI_Probe(int s, int t, MPI_Comm c, MPI_Status *st)
+{
+    (void)s; (void)c;
+    if (!g_is_render) UNIMPL("MPI_Probe");
+    for (;;) {      /* renderer.c:276: any compute rank whose next message has at least its header in the ring */
+        for (int r = 0; r < g_nranks; r++) {
+            ring_ctl_t *ctl = &g_ctl[ring_up(r)];
+            if (ctl->tail - ctl->head < sizeof(msg_hdr_t)) continue;
+            __sync_synchronize();
+            msg_hdr_t h;
+            size_t cap = g_world->ring_bytes, off = (size_t)(ctl->head % cap);
+            char *base = g_data + (size_t)ring_up(r) * cap;
+            size_t first = sizeof h < cap - off ? sizeof h : cap - off;
+            memcpy(&h, base + off, first);
+            if (first < sizeof h) memcpy((char *)&h + first, base, sizeof h - first);
+            if (h.tag != t) die("MPI_Probe: unexpected tag at the head of a ring");
+            st->MPI_SOURCE = r + 1; st->MPI_TAG = h.tag; st->MPI_ERROR = MPI_SUCCESS; st->_nbytes = h.nbytes;
+            return MPI_SUCCESS;
+        }
+        sched_yield();
+    }
+}
+#define TAG_BCAST (-101)
+#define TAG_SCATTER (-102)
 int MPI_Bcast(void *b, int n, MPI_Datatype t, int r, MPI_Comm c)
 {
+    if (g_render_proc && c == MPI_COMM_WORLD && r == 0) {
+        if (g_is_render) for (int k = 0; k < g_nranks; k++) raw_send(ring_down(k), b, type_bytes(t, n), TAG_BCAST);
+        else raw_recv(ring_down(g_rank), b, type_bytes(t, n), TAG_BCAST);
+        return MPI_SUCCESS;
+    }
     if (!to_render(c, r)) UNIMPL("MPI_Bcast");
     g_render->bcast(b, type_bytes(t, n));
     return MPI_SUCCESS;
 }
 int MPI_Gatherv(const void *sb, int sc, MPI_Datatype st, void *rb, const int rc[], const int d[], MPI_Datatype rt, int r, MPI_Comm c)
 {
+    if (g_render_proc && c == MPI_COMM_WORLD && r == 0) {
+        if (g_is_render) {      /* renderer.c:151: one block from every compute rank, world rank k lands at displacement d[k] */
+            for (int k = 1; k <= g_nranks; k++)
+                raw_recv(ring_up(k - 1), (char *)rb + (size_t)d[k] * type_bytes(rt, 1), type_bytes(rt, rc[k]), MINI_MPI_TAG_GATHER);
+        } else raw_send(ring_up(g_rank), sb, type_bytes(st, sc), MINI_MPI_TAG_GATHER);
+        return MPI_SUCCESS;
+    }
     (void)rb; (void)rc; (void)d; (void)rt;
     if (!to_render(c, r)) UNIMPL("MPI_Gatherv");
     g_render->from_compute(sb, type_bytes(st, sc), MINI_MPI_TAG_GATHER);
@@ -407,6 +495,13 @@ int MPI_Gatherv(const void *sb, int sc, MPI_Datatype st, void *rb, const int rc[
 }
 int MPI_Scatterv(const void *sb, const int sc[], const int d[], MPI_Datatype st, void *rb, int rc, MPI_Datatype rt, int r, MPI_Comm c)
 {
+    if (g_render_proc && c == MPI_COMM_WORLD && r == 0) {
+        if (g_is_render) {      /* renderer.c:248,268 */
+            for (int k = 1; k <= g_nranks; k++)
+                raw_send(ring_down(k - 1), (const char *)sb + (size_t)d[k] * type_bytes(st, 1), type_bytes(st, sc[k]), TAG_SCATTER);
+        } else raw_recv(ring_down(g_rank), rb, type_bytes(rt, rc), TAG_SCATTER);
+        return MPI_SUCCESS;
+    }
     (void)sb; (void)sc; (void)d; (void)st;
     if (!to_render(c, r)) UNIMPL("MPI_Scatterv");
     g_render->scatter(rb, type_bytes(rt, rc));
@@ -421,4 +516,6 @@ static int send_to_render(const void *buf, int count, MPI_Datatype type, int tag
 }
 
 /* fluid.c's main() (renamed by -Dmain=ref_main) references the render rank. */
+#ifndef MINI_MPI_WITH_RENDERER   /* (the full-program build links the reference's own renderer.c) */
 int start_renderer(void) { die("start_renderer: no render rank in the oracle build"); return -1; }
+#endif

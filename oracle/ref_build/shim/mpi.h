@@ -86,6 +86,10 @@ int MPI_Scatterv(const void *sendbuf, const int sendcounts[], const int displs[]
 /* ---- shim control (not MPI): used by oracle/ref_build/ref_harness.c ---- */
 /* Create the shared mailboxes for `nranks` ranks; call BEFORE fork(). */
 int mini_mpi_world_create(int nranks, size_t ring_bytes);
+/* The same plus world rank 0 as a process of its own (the reference's render rank, oracle/ref_build/ref_world.c):
+ * Bcast / Recv / Gatherv / Scatterv / Probe / Irecv between it and the compute ranks, as renderer.c uses them. */
+int mini_mpi_world_create_render(int nranks, size_t ring_bytes);
+void mini_mpi_bind_render(void);
 /* Bind the calling process to `rank` (call in each child after fork). */
 void mini_mpi_bind(int rank);
 /* Spin barrier across all ranks of the world. */

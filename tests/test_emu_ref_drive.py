@@ -12,7 +12,7 @@ import pytest
 import sph_b200
 from emu.build_emu import build as build_emu
 from oracle.oracle import lattice, make_problem
-from test_ref_drive import GPU_DRIVE, HOT, bindings, pack, read_drive
+from test_ref_drive import GPU_DRIVE, HOT, WORLD_GPU, bindings, pack, read_drive, read_world
 
 
 @pytest.mark.skipif(not os.path.exists(GPU_DRIVE), reason="oracle/_ref not built")
@@ -109,6 +109,35 @@ def test_several_compute_ranks_through_the_reference_names_on_the_one_exchange_b
     (sph_exchanges_per_step() == 1) and the frames are still the one-rank frames."""
     lib = build_emu(defines=("SPH_ONE_EXCHANGE=1",), name="libsph_emu_sph_one_exchange1.so")
     check_ranks_against_one_rank(GPU_DRIVE, dict(os.environ, LD_PRELOAD=lib), tmp_path, 3, 10, os.path.basename(lib), 1)
+
+
+def check_whole_program(world, env, tmp_path, ranks, frames, libname):
+    """The reference's whole program (its main(), renderer.c with its load balancer, controls.c; oracle/ref_build/
+    ref_world.c) with the compute ranks' hot path in the library: K ranks must draw the pixels ONE rank draws."""
+    outs = {}
+    for k in (1, ranks):
+        outs[k] = str(tmp_path / f"world{k}.bin")
+        r = subprocess.run([world, "--ranks", str(k), "--frames", str(frames), "--out", outs[k]], capture_output=True,
+                           text=True, timeout=600, env=env)
+        assert r.returncode == 0, (r.stdout[-300:], r.stderr[-800:])
+        assert "sph_ref_api:" not in r.stderr, r.stderr[-800:]
+        b = bindings(r.stdout)
+        assert all(b[k_].endswith("libref_full.so") for k_ in ("start_renderer", "check_partition_left", "start_simulation")), b
+        assert all(b[k_].endswith(libname) for k_ in HOT), b
+    K1, w, h, one = read_world(outs[1])
+    K, wk, hk, many = read_world(outs[ranks])
+    assert (K1, K, wk, hk) == (1, ranks, w, h) and len(one) == len(many) == frames
+    for f in range(frames):
+        assert np.array_equal(many[f][1], one[f][1])                                  # same mover path
+        assert np.array_equal(np.sort(many[f][2].copy().view("i8").ravel()), np.sort(one[f][2].copy().view("i8").ravel())), f
+    # the reference's balancer did move a slab edge on the way (renderer.c:427-477), and the pixels did not notice
+    assert any(not np.array_equal(many[f][0], many[0][0]) for f in range(frames))
+
+
+@pytest.mark.skipif(not os.path.exists(WORLD_GPU), reason="oracle/_ref not built")
+@pytest.mark.parametrize("ranks", [3, 4])
+def test_whole_reference_program_with_its_renderer_on_the_emulated_library(built_lib, tmp_path, ranks):
+    check_whole_program(WORLD_GPU, dict(os.environ, LD_PRELOAD=build_emu()), tmp_path, ranks, 14, "libsph_emu.so")
 
 
 def test_reference_call_order_on_the_emulated_library(built_lib, monkeypatch):

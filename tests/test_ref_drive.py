@@ -52,6 +52,25 @@ def pack(x, y, w, h):
                      ((f(2.0) * y / f(h) - f(1.0)) * f(32767.0)).astype("i2")], axis=1)
 
 
+WORLD_CPU = os.path.join(ROOT, "oracle", "_ref", "sph_ref_world_cpu")
+WORLD_GPU = os.path.join(ROOT, "oracle", "_ref", "sph_ref_world_gpu")
+
+
+def read_world(path):
+    """oracle/ref_build/render_stubs.c's record -> (K, world_w, world_h, [(edges[K, 2], mover[2], points[n, 2] f32)])"""
+    raw = open(path, "rb").read()
+    assert raw[:4] == b"SPHR"
+    K = int(np.frombuffer(raw, "i4", 1, 4)[0])
+    w, h = [float(v) for v in np.frombuffer(raw, "f4", 2, 8)]
+    off, frames = 16, []
+    while off < len(raw):
+        n = int(np.frombuffer(raw, "i4", 1, off)[0]); off += 4
+        edges = np.frombuffer(raw, "f4", 2 * K, off).reshape(K, 2).copy(); off += 8 * K
+        mover = np.frombuffer(raw, "f4", 2, off).copy(); off += 8
+        frames.append((edges, mover, np.frombuffer(raw, "f4", 2 * n, off).reshape(n, 2).copy())); off += 8 * n
+    return K, w, h, frames
+
+
 def bindings(stdout):
     return dict(line.split(": ", 1)[1].split(" -> ") for line in stdout.splitlines() if line.startswith("binding: "))
 
@@ -74,6 +93,26 @@ def test_unmodified_reference_driver_equals_sequential_oracle(tmp_path):
         o.step(); o.step(); o.step(); o.step(queued=blk)                   # the scatter lands in the 4th sub-step
         s = o.store()
         assert np.array_equal(pack(s["x"], s["y"], w, h), coords), k
+
+
+@pytest.mark.skipif(not os.path.exists(WORLD_CPU), reason="oracle/_ref not built")
+def test_whole_reference_program_runs_headless(tmp_path):
+    """The reference's own main(), renderer.c and controls.c (unmodified, fake GL headers, no-op GL modules) with three
+    compute ranks over the mini-MPI -- BASELINE config 1, `mpirun -n 4` -- to its clean end through the kill_sim
+    scatter: the harness the GPU path is put under in tests/test_emu_ref_drive.py / test_gpu_zz_ref_drive_ranks.py."""
+    out = str(tmp_path / "world.bin")
+    r = subprocess.run([WORLD_CPU, "--ranks", "3", "--frames", "12", "--out", out], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr[-500:]
+    b = bindings(r.stdout)
+    assert all(v.endswith("libref_full.so") for v in b.values()), b          # the pure reference, renderer included
+    K, w, h, frames = read_world(out)
+    prob = make_problem(1500)
+    assert (K, w, h, len(frames)) == (3, prob["tank_w"], prob["tank_h"], 12)
+    for edges, mover, pts in frames:
+        assert len(pts) == prob["n_global"] and np.all(np.abs(pts) <= 1.0)    # everybody drawn, inside the screen
+        assert edges[0, 0] == 0.0 and edges[-1, 1] == np.float32(w) 
+        assert np.all(np.abs(edges[1:, 0] - edges[:-1, 1]) < 1e-5)            # (partitionProblem's adjacent edges may differ in the last bit)
+    assert frames[5][1][0] > frames[0][1][0]                                 # the stub's "user" dragged the mover
 
 
 @pytest.mark.skipif(not os.path.exists(GPU_DRIVE), reason="oracle/_ref not built")
