@@ -9,6 +9,9 @@
  *   init_ogl             1920 x 1080 "screen" (renderer.c:127-129 broadcasts it: a 16:9 tank)
  *   check_user_input     the "user": drags the mover along a fixed path through the reference's own
  *                        set_mover_gl_center (controls.c:227-237), one position per frame
+ *                        and presses the keys listed in $SPH_RENDER_SCRIPT ("4:remove 9:add 6:b 12:x": at frame 4
+ *                        the reference's own remove_partition, controls.c:405-426; add_partition, :429-455; the
+ *                        fluid presets set_fluid_x/y/a/b, :344-401)
  *   render_liquid /      records the frame the renderer would have drawn
  *   render_particles
  *   swap_ogl             end of frame: appends it to $SPH_RENDER_OUT
@@ -56,6 +59,21 @@ void check_user_input(gl_t *state)
 {
     (void)state;
     set_mover_gl_center(S.rs, -0.5f + 0.06f * (float)S.frames, -0.4f);
+    const char *script = getenv("SPH_RENDER_SCRIPT");
+    for (const char *p = script; p && *p; ) {
+        int frame = 0, used = 0;
+        char key[16];
+        if (sscanf(p, " %d:%15s%n", &frame, key, &used) < 2) break;
+        p += used;
+        if (frame != S.frames) continue;
+        if (!strcmp(key, "remove")) remove_partition(S.rs);
+        else if (!strcmp(key, "add")) add_partition(S.rs);
+        else if (!strcmp(key, "x")) set_fluid_x(S.rs);
+        else if (!strcmp(key, "y")) set_fluid_y(S.rs);
+        else if (!strcmp(key, "a")) set_fluid_a(S.rs);
+        else if (!strcmp(key, "b")) set_fluid_b(S.rs);
+        else { fprintf(stderr, "render_stubs: unknown key '%s' in SPH_RENDER_SCRIPT\n", key); exit(2); }
+    }
 }
 
 void render_liquid(float *points, float diameter_pixels, int num_points, liquid_t *state)

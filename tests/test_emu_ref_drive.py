@@ -111,10 +111,15 @@ def test_several_compute_ranks_through_the_reference_names_on_the_one_exchange_b
     check_ranks_against_one_rank(GPU_DRIVE, dict(os.environ, LD_PRELOAD=lib), tmp_path, 3, 10, os.path.basename(lib), 1)
 
 
-def check_whole_program(world, env, tmp_path, ranks, frames, libname):
+KEYS = "3:remove 6:b 9:add 12:x 15:remove 17:add"        # what the headless "user" presses, frame:key (render_stubs.c)
+
+
+def check_whole_program(world, env, tmp_path, ranks, frames, libname, script=None):
     """The reference's whole program (its main(), renderer.c with its load balancer, controls.c; oracle/ref_build/
     ref_world.c) with the compute ranks' hot path in the library: K ranks must draw the pixels ONE rank draws."""
     outs = {}
+    if script:
+        env = dict(env, SPH_RENDER_SCRIPT=script)
     for k in (1, ranks):
         outs[k] = str(tmp_path / f"world{k}.bin")
         r = subprocess.run([world, "--ranks", str(k), "--frames", str(frames), "--out", outs[k]], capture_output=True,
@@ -132,12 +137,25 @@ def check_whole_program(world, env, tmp_path, ranks, frames, libname):
         assert np.array_equal(np.sort(many[f][2].copy().view("i8").ravel()), np.sort(one[f][2].copy().view("i8").ravel())), f
     # the reference's balancer did move a slab edge on the way (renderer.c:427-477), and the pixels did not notice
     assert any(not np.array_equal(many[f][0], many[0][0]) for f in range(frames))
+    if script:
+        # remove_partition (controls.c:405-426) parked the last slab outside the tank: it drained into its neighbour
+        # through the migration path; add_partition (:429-455) split the last active slab and it filled up again
+        parked = [f for f in range(frames) if many[f][0][-1, 0] > w]
+        assert parked and parked[0] == 3 and (frames - 1) not in parked
+        assert many[4][0][-2, 1] == np.float32(w)
 
 
 @pytest.mark.skipif(not os.path.exists(WORLD_GPU), reason="oracle/_ref not built")
 @pytest.mark.parametrize("ranks", [3, 4])
 def test_whole_reference_program_with_its_renderer_on_the_emulated_library(built_lib, tmp_path, ranks):
     check_whole_program(WORLD_GPU, dict(os.environ, LD_PRELOAD=build_emu()), tmp_path, ranks, 14, "libsph_emu.so")
+
+
+@pytest.mark.skipif(not os.path.exists(WORLD_GPU), reason="oracle/_ref not built")
+def test_reference_controls_park_and_re_add_a_slab_and_switch_presets_on_the_emulated_library(built_lib, tmp_path):
+    """The reference's own remove_partition / add_partition / set_fluid_b / set_fluid_x (controls.c, unmodified) pressed
+    in mid-run while its balancer keeps moving the edges: three ranks still draw the one-rank pixels in every frame."""
+    check_whole_program(WORLD_GPU, dict(os.environ, LD_PRELOAD=build_emu()), tmp_path, 3, 20, "libsph_emu.so", KEYS)
 
 
 def test_reference_call_order_on_the_emulated_library(built_lib, monkeypatch):

@@ -6,7 +6,7 @@ import os
 
 import pytest
 
-from test_emu_ref_drive import check_ranks_against_one_rank, check_whole_program
+from test_emu_ref_drive import KEYS, check_ranks_against_one_rank, check_whole_program
 from test_ref_drive import GPU_DRIVE, WORLD_GPU
 
 pytestmark = pytest.mark.gpu
@@ -23,10 +23,11 @@ def test_unmodified_reference_driver_with_several_compute_ranks_on_the_gpu_path(
 
 
 @pytest.mark.skipif(not os.path.exists(WORLD_GPU), reason="oracle/_ref not built")
-def test_whole_reference_program_with_its_renderer_on_the_gpu_path(built_lib, tmp_path):
+@pytest.mark.parametrize("frames,script", [(14, None), (20, KEYS)])
+def test_whole_reference_program_with_its_renderer_on_the_gpu_path(built_lib, tmp_path, frames, script):
     """BASELINE config 1 (mpirun -n 4: the reference's render rank + 3 compute ranks), hot path on the B200."""
     import torch
     env = dict(os.environ)
     if torch.cuda.device_count() > 1:
         env["SPH_B200_DEVICES"] = str(torch.cuda.device_count())
-    check_whole_program(WORLD_GPU, env, tmp_path, 3, 14, "libsph_b200.so")
+    check_whole_program(WORLD_GPU, env, tmp_path, 3, frames, "libsph_b200.so", script)
