@@ -318,7 +318,19 @@ void hash_fluid(fluid_particle **pointers, neighbor_grid_t *grid, param *params,
     if (rc == SPH_OK && !compute_density) {
         /* the re-hash of fluid.c:341 ends the step: positions and velocities are final */
         G.steps_done++;
-        if (G.mirror && G.steps_done % G.mirror_every == 0) note("hash_fluid", sph_ref_sync_to_host(pointers, params));
+        if (G.mirror && G.steps_done % G.mirror_every == 0) {
+            note("hash_fluid", sph_ref_sync_to_host(pointers, params));
+            if (G.nranks > 1) {
+                /* the reference's functions are void: what a slab could not hold or send is reported here (stderr and
+                 * sph_ref_last_error), where the host is synchronised anyway */
+                sph_status st;
+                if (sph_get_status(G.ctx, &st) == SPH_OK && (st.msg_overflow || st.capacity_overflow)) {
+                    snprintf(G.err, sizeof G.err, "rank %d: %d particles did not fit a neighbour message, %d exceeded the slab's capacity",
+                             G.rank, st.msg_overflow, st.capacity_overflow);
+                    fprintf(stderr, "sph_ref_api: %s\n", G.err);
+                }
+            }
+        }
     }
 }
 
