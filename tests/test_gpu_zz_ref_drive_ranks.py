@@ -6,7 +6,7 @@ import os
 
 import pytest
 
-from test_emu_ref_drive import KEYS, check_ranks_against_one_rank, check_whole_program
+from test_emu_ref_drive import KEYS, check_config1_against_the_pure_reference, check_ranks_against_one_rank, check_whole_program
 from test_ref_drive import GPU_DRIVE, WORLD_GPU
 
 pytestmark = pytest.mark.gpu
@@ -31,3 +31,9 @@ def test_whole_reference_program_with_its_renderer_on_the_gpu_path(built_lib, tm
     if torch.cuda.device_count() > 1:
         env["SPH_B200_DEVICES"] = str(torch.cuda.device_count())
     check_whole_program(WORLD_GPU, env, tmp_path, 3, frames, "libsph_b200.so", script)
+
+
+@pytest.mark.skipif(not os.path.exists(WORLD_GPU), reason="oracle/_ref not built")
+def test_config1_whole_program_statistics_against_the_pure_reference_on_the_gpu_path(built_lib, tmp_path):
+    """BASELINE config 1 end to end: the reference's whole program, pure vs with its hot path on the B200."""
+    print("worst deviation (mean y, std y, mean x, std x):", check_config1_against_the_pure_reference(dict(os.environ), tmp_path))
