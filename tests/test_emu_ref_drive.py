@@ -151,11 +151,19 @@ def test_whole_reference_program_with_its_renderer_on_the_emulated_library(built
     check_whole_program(WORLD_GPU, dict(os.environ, LD_PRELOAD=build_emu()), tmp_path, ranks, 14, "libsph_emu.so")
 
 
+GOO_KEYS = "2:y 3:remove 9:add 12:x"      # the goo preset needs SPH_VISC_STAB
+
+
 @pytest.mark.skipif(not os.path.exists(WORLD_GPU), reason="oracle/_ref not built")
-def test_reference_controls_park_and_re_add_a_slab_and_switch_presets_on_the_emulated_library(built_lib, tmp_path):
-    """The reference's own remove_partition / add_partition / set_fluid_b / set_fluid_x (controls.c, unmodified) pressed
-    in mid-run while its balancer keeps moving the edges: three ranks still draw the one-rank pixels in every frame."""
-    check_whole_program(WORLD_GPU, dict(os.environ, LD_PRELOAD=build_emu()), tmp_path, 3, 20, "libsph_emu.so", KEYS)
+@pytest.mark.parametrize("keys,stab", [(KEYS, None), (GOO_KEYS, "0.5,0.5")])
+def test_reference_controls_park_and_re_add_a_slab_and_switch_presets_on_the_emulated_library(built_lib, tmp_path, keys, stab):
+    """The reference's own remove_partition / add_partition / set_fluid_b / set_fluid_x / set_fluid_y (controls.c,
+    unmodified) pressed in mid-run while its balancer keeps moving the edges: three ranks still draw the one-rank
+    pixels in every frame -- also through the goo phase with the stabilised viscosity gather switched on by environment."""
+    env = dict(os.environ, LD_PRELOAD=build_emu())
+    if stab:
+        env["SPH_VISC_STAB"] = stab
+    check_whole_program(WORLD_GPU, env, tmp_path, 3, 20, "libsph_emu.so", keys)
 
 
 def check_config1_against_the_pure_reference(env, tmp_path, frames=120):
