@@ -37,7 +37,9 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <signal.h>
 #include <string.h>
+#include <sys/prctl.h>
 #include <sys/wait.h>
 #include <unistd.h>
 
@@ -153,16 +155,25 @@ int main(int argc, char **argv)
         if (mini_mpi_world_create(ranks, (size_t)16 << 20)) { fprintf(stderr, "ref_drive: cannot create %d ranks\n", ranks); return 2; }
         fflush(stdout);
         int rank = -1;
+        pid_t pids[256];
         for (int r = 0; r < ranks; r++) {
             pid_t pid = fork();
             if (pid < 0) { perror("fork"); return 2; }
             if (pid == 0) { rank = r; break; }
+            pids[r] = pid;
         }
         if (rank < 0) {
             int worst = 0, st;
-            while (wait(&st) > 0) if (!WIFEXITED(st) || WEXITSTATUS(st)) worst = WIFEXITED(st) ? WEXITSTATUS(st) : 5;
+            while (wait(&st) > 0)
+                if ((!WIFEXITED(st) || WEXITSTATUS(st)) && !worst) {
+                    /* one rank failed: the others would wait for its messages for ever */
+                    worst = WIFEXITED(st) ? WEXITSTATUS(st) : 5;
+                    for (int i = 0; i < ranks; i++) kill(pids[i], SIGKILL);
+                }
             return worst;
         }
+        prctl(PR_SET_PDEATHSIG, SIGKILL);        /* nobody outlives the launcher (a test's time-out kills only that) */
+        alarm(getenv("SPH_WORLD_TIMEOUT") ? (unsigned)atoi(getenv("SPH_WORLD_TIMEOUT")) : 240);
         mini_mpi_bind(rank);
         R.shared = mini_mpi_shared_doubles();
         R.rank = rank; R.ranks = ranks;

@@ -15,7 +15,9 @@
 #include <dlfcn.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <signal.h>
 #include <string.h>
+#include <sys/prctl.h>
 #include <sys/wait.h>
 #include <unistd.h>
 
@@ -51,16 +53,23 @@ int main(int argc, char **argv)
     if (mini_mpi_world_create_render(ranks, (size_t)16 << 20)) { fprintf(stderr, "ref_world: cannot create %d ranks\n", ranks); return 2; }
     fflush(stdout);
     int me = -2;
+    pid_t pids[257];
     for (int r = -1; r < ranks; r++) {           /* -1: the render rank */
         pid_t pid = fork();
         if (pid < 0) { perror("fork"); return 2; }
         if (pid == 0) { me = r; break; }
+        pids[r + 1] = pid;
     }
     if (me == -2) {
         int worst = 0, st;
-        while (wait(&st) > 0) if (!WIFEXITED(st)) worst = 5;    /* compute ranks return an uninitialised code (fluid.c:48,68) */
+        /* compute ranks return an uninitialised code (fluid.c:48,68): only a rank that was KILLED counts, and then
+         * the others, which would wait for its messages for ever, go too */
+        while (wait(&st) > 0)
+            if (!WIFEXITED(st) && !worst) { worst = 5; for (int i = 0; i <= ranks; i++) kill(pids[i], SIGKILL); }
         return worst;
     }
+    prctl(PR_SET_PDEATHSIG, SIGKILL);            /* nobody outlives the launcher (a test's time-out kills only that) */
+    alarm(getenv("SPH_WORLD_TIMEOUT") ? (unsigned)atoi(getenv("SPH_WORLD_TIMEOUT")) : 240);
     if (me < 0) mini_mpi_bind_render(); else mini_mpi_bind(me);
     ref_main(argc, argv);
     fflush(stdout);

@@ -128,6 +128,22 @@ def test_driver_binds_to_product_library_and_has_no_cpu_path(tmp_path):
     assert r.returncode != 0 and "there is no CPU path" in r.stderr       # aborts instead of limping on
 
 
+@pytest.mark.skipif(not os.path.exists(WORLD_GPU), reason="oracle/_ref not built")
+def test_whole_program_on_the_library_without_a_gpu_stops_at_once(tmp_path):
+    """Three compute ranks under the reference's renderer, product library in front, no device: every rank aborts with
+    "there is no CPU path", and the launcher takes the render rank down with them instead of leaving it waiting."""
+    import time
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: covered by test_gpu_zz_ref_drive_ranks.py")
+    t0 = time.time()
+    r = subprocess.run([WORLD_GPU, "--ranks", "3", "--frames", "2", "--out", str(tmp_path / "w.bin")], capture_output=True,
+                       text=True, timeout=120)
+    b = bindings(r.stdout)
+    assert b["start_renderer"].endswith("libref_full.so") and all(b[k].endswith("libsph_b200.so") for k in HOT), b
+    assert r.returncode != 0 and "there is no CPU path" in r.stderr and time.time() - t0 < 30
+
+
 def test_startup_entry_points_match_reference_golden(built_lib):
     """partitionProblem / setParticleNumbers / initParticles of sph_ref_api.h (geometry.c:29-160,
     fluid.c:747-768) against rows produced by the reference's own partitionProblem."""
