@@ -176,6 +176,13 @@ int sph_ref_attach(fluid_particle **pointers, param *params, AABB_t *boundary, n
     rc = sph_upload(G.ctx, flat, uid, n);            /* one rank: uid = pointer index */
     free(uid);
     free(flat);
+    if (rc == SPH_OK && nranks > 1) {
+        /* a slab uploads its own particles only; if they are already moving (a restart) the first viscosity pass needs
+         * the neighbours across the edges: one ghost exchange, all ranks together (harmless from rest, where the
+         * reference starts: fluid.c:762-767) */
+        if ((rc = sph_refresh_ghosts(G.ctx)) == SPH_OK && (rc = sph_exchange_via_host(G.ctx, 1, H.fn, H.user)) == SPH_OK)
+            rc = sph_sort(G.ctx);
+    }
     G.n = n;
     note("sph_ref_attach", rc);
     return rc;
