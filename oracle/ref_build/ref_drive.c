@@ -130,6 +130,30 @@ static __attribute__((noinline)) void paint_stack(void)
     for (size_t i = 0; i < sizeof pad; i++) pad[i] = 0;
 }
 
+/* --explicit 1: a host that is being edited anyway announces itself with sph_ref_set_rank + sph_ref_set_transport
+ * (include/sph_ref_api.h) instead of linking the glue object; looked up at run time because the pure-reference link
+ * of this file has no such symbols */
+static long explicit_calls;
+static void explicit_sendrecv(const void *send, size_t send_bytes, int to_side, void *recv, size_t recv_bytes, int from_side,
+                              void *user)
+{
+    (void)user;
+    const int to = !send ? MPI_PROC_NULL : to_side == 0 ? R.rank - 1 : R.rank + 1;
+    const int from = !recv ? MPI_PROC_NULL : from_side == 0 ? R.rank - 1 : R.rank + 1;
+    MPI_Sendrecv((void *)send, (int)send_bytes, MPI_CHAR, to, 31, recv, (int)recv_bytes, MPI_CHAR, from, 31, MPI_COMM_COMPUTE,
+                 MPI_STATUS_IGNORE);
+    explicit_calls++;
+}
+
+static void announce_explicitly(void)
+{
+    void (*set_rank)(int, int) = (void (*)(int, int))dlsym(RTLD_DEFAULT, "sph_ref_set_rank");
+    void (*set_transport)(void *, void *) = (void (*)(void *, void *))dlsym(RTLD_DEFAULT, "sph_ref_set_transport");
+    if (!set_rank || !set_transport) { fprintf(stderr, "ref_drive: --explicit needs the product library in the link\n"); exit(2); }
+    set_transport((void *)explicit_sendrecv, NULL);       /* first: it also tells the library not to look for the glue */
+    set_rank(R.rank, R.ranks);
+}
+
 static void report_binding(const char *name)
 {
     void *sym = dlsym(RTLD_DEFAULT, name);
@@ -142,13 +166,14 @@ int main(int argc, char **argv)
 {
     const char *out = "ref_drive.bin";
     static char rank_out[4096];
-    int ranks = 1;
+    int ranks = 1, explicit = 0;
     R.frames_wanted = 4;
     for (int i = 1; i + 1 < argc; i++) {
         if (!strcmp(argv[i], "--frames")) R.frames_wanted = atoi(argv[i + 1]);
         if (!strcmp(argv[i], "--out")) out = argv[i + 1];
         if (!strcmp(argv[i], "--ranks")) ranks = atoi(argv[i + 1]);
         if (!strcmp(argv[i], "--wobble")) R.wobble = atoi(argv[i + 1]);
+        if (!strcmp(argv[i], "--explicit")) explicit = atoi(argv[i + 1]);
     }
     if (ranks > 1) {
         /* before anything touches a device: every rank is a process of its own */
@@ -197,9 +222,11 @@ int main(int argc, char **argv)
     MPI_Init(&argc, &argv);
     create_communicators();
     createMpiTypes();
+    if (explicit && ranks > 1) announce_explicitly();
     paint_stack();
     start_simulation();
     MPI_Finalize();
+    if (explicit) printf("explicit transport calls: %ld\n", explicit_calls);
 
     fclose(R.out);
     printf("ref_drive: %d frames of %d particles, world %.4f x %.4f -> %s\n", R.frames_seen, R.n_global,

@@ -57,19 +57,25 @@ def frames_of_all_ranks(out, ranks):
     return n, w, h, [[p[4][k][1] for p in parts] for k in range(len(parts[0][4]))], [p[3] for p in parts]
 
 
-def check_ranks_against_one_rank(drive, env, tmp_path, ranks, frames, libname, wobble=0):
+def check_ranks_against_one_rank(drive, env, tmp_path, ranks, frames, libname, wobble=0, explicit=0):
     """The unmodified driver as `ranks` compute ranks (one slab each, over the mini-MPI, glue object linked in)
     against the same driver as ONE rank: every frame must hold the same pixels, bit for bit, whoever owns them."""
     one, many = str(tmp_path / "one.bin"), str(tmp_path / "many.bin")
     r1 = subprocess.run([drive, "--frames", str(frames), "--out", one], capture_output=True, text=True, timeout=300, env=env)
     assert r1.returncode == 0, (r1.stdout[-300:], r1.stderr[-800:])
-    rk = subprocess.run([drive, "--ranks", str(ranks), "--wobble", str(wobble), "--frames", str(frames), "--out", many],
-                        capture_output=True, text=True, timeout=600, env=env)
+    rk = subprocess.run([drive, "--ranks", str(ranks), "--wobble", str(wobble), "--explicit", str(explicit), "--frames", str(frames),
+                         "--out", many], capture_output=True, text=True, timeout=600, env=env)
     assert rk.returncode == 0, (rk.stdout[-300:], rk.stderr[-800:])
     b = bindings(rk.stdout)
     assert b["start_simulation"].endswith("libref_driver.so")
     assert all(b[k].endswith(libname) for k in HOT), b
     assert "sph_ref_api:" not in rk.stderr, rk.stderr[-800:]          # no stage reported an error
+    if explicit:
+        # sph_ref_set_rank + sph_ref_set_transport instead of the glue: two send/receive pairs per exchange, two
+        # exchanges per step, one at the attach; the kill_sim scatter arrives in the 4th sub-step of frame `frames`,
+        # after three more whole steps (fluid.c:293-304)
+        calls = [int(line.split(": ")[1]) for line in rk.stdout.splitlines() if line.startswith("explicit transport calls")]
+        assert calls == [2 * (2 * (4 * frames + 3) + 1)] * ranks, calls
     n, w, h, first, f1 = read_drive(one)
     nk, wk, hk, fk, firsts = frames_of_all_ranks(many, ranks)
     assert (nk, wk, hk) == (n, w, h) and len(fk) == len(f1) == frames
@@ -101,6 +107,13 @@ def test_unmodified_reference_driver_with_several_compute_ranks_on_the_emulated_
     if mirror_every:
         env["SPH_REF_MIRROR_EVERY"] = mirror_every
     check_ranks_against_one_rank(GPU_DRIVE, env, tmp_path, ranks, 10, "libsph_emu.so", wobble)
+
+
+@pytest.mark.skipif(not os.path.exists(GPU_DRIVE), reason="oracle/_ref not built")
+@pytest.mark.skipif(not os.path.exists(GPU_DRIVE), reason="oracle/_ref not built")
+def test_host_that_announces_rank_and_transport_itself_on_the_emulated_library(built_lib, tmp_path):
+    """sph_ref_set_rank + sph_ref_set_transport (a host that is edited anyway) instead of the glue object's weak hook."""
+    check_ranks_against_one_rank(GPU_DRIVE, dict(os.environ, LD_PRELOAD=build_emu()), tmp_path, 3, 6, "libsph_emu.so", 1, explicit=1)
 
 
 @pytest.mark.skipif(not os.path.exists(GPU_DRIVE), reason="oracle/_ref not built")
