@@ -113,7 +113,7 @@ def test_unmodified_reference_driver_with_several_compute_ranks_on_the_emulated_
 @pytest.mark.skipif(not os.path.exists(GPU_DRIVE), reason="oracle/_ref not built")
 def test_host_that_announces_rank_and_transport_itself_on_the_emulated_library(built_lib, tmp_path):
     """sph_ref_set_rank + sph_ref_set_transport (a host that is edited anyway) instead of the glue object's weak hook."""
-    check_ranks_against_one_rank(GPU_DRIVE, dict(os.environ, LD_PRELOAD=build_emu()), tmp_path, 3, 6, "libsph_emu.so", 1, explicit=1)
+    check_ranks_against_one_rank(GPU_DRIVE, dict(os.environ, LD_PRELOAD=build_emu()), tmp_path, 3, 10, "libsph_emu.so", 1, explicit=1)
 
 
 @pytest.mark.skipif(not os.path.exists(GPU_DRIVE), reason="oracle/_ref not built")
