@@ -17,7 +17,7 @@ import pytest
 
 import sph_b200
 import test_gpu_parity as gpu
-import test_gpu_stabilised_and_feed as late
+import test_zy_gpu_stabilised_and_feed as late
 from emu.build_emu import build as build_emu
 
 
@@ -42,7 +42,7 @@ from test_gpu_parity import (  # noqa: E402,F401
     test_mover_autopilot_and_preset_cycle,
     test_long_run_statistics_default,
 )
-from test_gpu_stabilised_and_feed import (  # noqa: E402,F401
+from test_zy_gpu_stabilised_and_feed import (  # noqa: E402,F401
     test_stabilised_viscosity_rounding_level_agreement_with_gather_oracle,
     test_stabilised_viscosity_engages_on_goo_and_leaves_stable_presets_bit_identical,
     test_stabilisation_threshold_selects_the_pass_per_parameter_block,

@@ -25,10 +25,9 @@ def ngpus():
 
     # big enough that every kernel runs its full grid: the exchange kernel waits for the neighbour inside the
     # kernel, which deadlocks unless its grid is fully co-resident (regression test)
-    (2, "p2p", 600000, 40),
-    # the goo preset with the stabilised viscosity gather (k_coupling runs on ghosts too): steps < 0 selects it.
-    # Last: first hardware run (written after the round's GPU budget was spent; emulator-checked)
-    (2, "p2p", 40000, -120)])
+    (2, "p2p", 600000, 40)])
+    # (steps < 0 selects the goo preset with the stabilised viscosity gather, k_coupling on ghosts too: that case lives in
+    #  tests/test_zy_gpu_stabilised_and_feed.py with the other first-hardware-run tests)
 def test_two_gpu_slabs_match_single_gpu_bit_for_bit(tmp_path, built_lib, world, transport, n_req, steps):
     if ngpus() < world:
         pytest.skip(f"needs {world} GPUs")

@@ -99,7 +99,7 @@ def test_unmodified_reference_driver_equals_sequential_oracle(tmp_path):
 def test_whole_reference_program_runs_headless(tmp_path):
     """The reference's own main(), renderer.c and controls.c (unmodified, fake GL headers, no-op GL modules) with three
     compute ranks over the mini-MPI -- BASELINE config 1, `mpirun -n 4` -- to its clean end through the kill_sim
-    scatter: the harness the GPU path is put under in tests/test_emu_ref_drive.py / test_gpu_zz_ref_drive_ranks.py."""
+    scatter: the harness the GPU path is put under in tests/test_emu_ref_drive.py / test_zz_gpu_ref_drive_ranks.py."""
     out = str(tmp_path / "world.bin")
     r = subprocess.run([WORLD_CPU, "--ranks", "3", "--frames", "12", "--out", out], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0, r.stderr[-500:]
@@ -135,7 +135,7 @@ def test_whole_program_on_the_library_without_a_gpu_stops_at_once(tmp_path):
     import time
     import torch
     if torch.cuda.is_available():
-        pytest.skip("GPU present: covered by test_gpu_zz_ref_drive_ranks.py")
+        pytest.skip("GPU present: covered by test_zz_gpu_ref_drive_ranks.py")
     t0 = time.time()
     r = subprocess.run([WORLD_GPU, "--ranks", "3", "--frames", "2", "--out", str(tmp_path / "w.bin")], capture_output=True,
                        text=True, timeout=120)

@@ -184,3 +184,12 @@ def test_long_run_statistics_goo_with_stabilised_viscosity(built_lib):
     a, _ = lattice(make_problem(1500))
     from common import GOO_STABILISED_WIDEN
     pc.check_long_run_statistics(mk_stab, "goo_rect1508", a, dens_make=make_oracle, widen=GOO_STABILISED_WIDEN)
+
+
+def test_two_gpu_slabs_goo_with_stabilised_viscosity_match_single_gpu(tmp_path, built_lib):
+    """The goo preset with the stabilised viscosity gather on two slabs (k_coupling runs on ghosts too), peer-memory
+    exchange: bit-identical to one GPU (tests/test_gpu_slabs.py's check with steps < 0)."""
+    import test_gpu_slabs
+    if test_gpu_slabs.ngpus() < 2:
+        pytest.skip("needs 2 GPUs")
+    test_gpu_slabs.test_two_gpu_slabs_match_single_gpu_bit_for_bit(tmp_path, built_lib, 2, "p2p", 40000, -120)
