@@ -12,7 +12,7 @@ import pytest
 import sph_b200
 from emu.build_emu import build as build_emu
 from oracle.oracle import lattice, make_problem
-from test_ref_drive import GPU_DRIVE, HOT, WORLD_CPU, WORLD_GPU, bindings, pack, read_drive, read_world
+from test_ref_drive import GPU_DRIVE, HOT, RESTART, WORLD_CPU, WORLD_GPU, bindings, pack, read_drive, read_world
 
 
 @pytest.mark.skipif(not os.path.exists(GPU_DRIVE), reason="oracle/_ref not built")
@@ -214,6 +214,37 @@ def check_config1_against_the_pure_reference(env, tmp_path, frames=120):
 @pytest.mark.skipif(not os.path.exists(WORLD_GPU), reason="oracle/_ref not built")
 def test_config1_whole_program_statistics_against_the_pure_reference_on_the_emulated_library(built_lib, tmp_path):
     check_config1_against_the_pure_reference(dict(os.environ, LD_PRELOAD=build_emu()), tmp_path)
+
+
+def check_restart_from_a_moving_fluid(env, tmp_path, ranks=3, steps=8):
+    """oracle/ref_build/ref_restart.c: a host on the reference-named entry points with EXPLICIT sph_ref_set_rank /
+    sph_ref_set_transport / sph_ref_attach, no host mirror, sph_ref_sync_to_host at the end -- starting from a fluid
+    that already moves.  The attach must hand every slab its ghost layer (one exchange), or the first viscosity pass
+    misses the neighbours across the edges; with it, `ranks` slabs equal one slab bit for bit (without it they do
+    not: checked by hand when this was written)."""
+    def rd(path):
+        raw = open(path, "rb").read()
+        n = int(np.frombuffer(raw, "i4", 1)[0])
+        return np.frombuffer(raw, "f4", 4 * n, 4).reshape(n, 4)
+
+    def canon(a):
+        return a[np.lexsort(a.view("u4").T[::-1])].view("u4")
+
+    for k in (1, ranks):
+        r = subprocess.run([RESTART, "--ranks", str(k), "--steps", str(steps), "--out", str(tmp_path / f"restart{k}.bin")],
+                           capture_output=True, text=True, timeout=300, env=env)
+        assert r.returncode == 0 and "sph_ref_api:" not in r.stderr, (r.stdout[-300:], r.stderr[-800:])
+    one = rd(tmp_path / "restart1.bin.r0")
+    parts = [rd(tmp_path / f"restart{ranks}.bin.r{r}") for r in range(ranks)]
+    assert len(one) == 1508 and sum(len(p) for p in parts) == 1508
+    assert [len(p) for p in parts] != [522, 493, 493]                    # particles crossed the edges on the way
+    assert np.abs(one[:, 2:]).max() > 3.0                                # and it is not a fluid at rest
+    assert np.array_equal(canon(one), canon(np.concatenate(parts)))
+
+
+@pytest.mark.skipif(not os.path.exists(RESTART), reason="oracle/_ref not built")
+def test_restart_from_a_moving_fluid_through_the_reference_names_on_the_emulated_library(built_lib, tmp_path):
+    check_restart_from_a_moving_fluid(dict(os.environ, LD_PRELOAD=build_emu()), tmp_path)
 
 
 def test_reference_call_order_on_the_emulated_library(built_lib, monkeypatch):

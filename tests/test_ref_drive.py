@@ -54,6 +54,7 @@ def pack(x, y, w, h):
 
 WORLD_CPU = os.path.join(ROOT, "oracle", "_ref", "sph_ref_world_cpu")
 WORLD_GPU = os.path.join(ROOT, "oracle", "_ref", "sph_ref_world_gpu")
+RESTART = os.path.join(ROOT, "oracle", "_ref", "sph_ref_restart")
 
 
 def read_world(path):

@@ -6,8 +6,9 @@ import os
 
 import pytest
 
-from test_emu_ref_drive import KEYS, check_config1_against_the_pure_reference, check_ranks_against_one_rank, check_whole_program
-from test_ref_drive import GPU_DRIVE, WORLD_GPU
+from test_emu_ref_drive import (KEYS, check_config1_against_the_pure_reference, check_ranks_against_one_rank,
+                                check_restart_from_a_moving_fluid, check_whole_program)
+from test_ref_drive import GPU_DRIVE, RESTART, WORLD_GPU
 
 pytestmark = pytest.mark.gpu
 
@@ -37,3 +38,8 @@ def test_whole_reference_program_with_its_renderer_on_the_gpu_path(built_lib, tm
 def test_config1_whole_program_statistics_against_the_pure_reference_on_the_gpu_path(built_lib, tmp_path):
     """BASELINE config 1 end to end: the reference's whole program, pure vs with its hot path on the B200."""
     print("worst deviation (mean y, std y, mean x, std x):", check_config1_against_the_pure_reference(dict(os.environ), tmp_path))
+
+
+@pytest.mark.skipif(not os.path.exists(RESTART), reason="oracle/_ref not built")
+def test_restart_from_a_moving_fluid_through_the_reference_names_on_the_gpu_path(built_lib, tmp_path):
+    check_restart_from_a_moving_fluid(dict(os.environ), tmp_path)
