@@ -124,7 +124,7 @@ def test_several_compute_ranks_through_the_reference_names_on_the_one_exchange_b
     check_ranks_against_one_rank(GPU_DRIVE, dict(os.environ, LD_PRELOAD=lib), tmp_path, 3, 10, os.path.basename(lib), 1)
 
 
-KEYS = "3:remove 6:b 9:add 12:x 15:remove 17:add"        # what the headless "user" presses, frame:key (render_stubs.c)
+KEYS = "3:remove 6:b 9:add 12:a 15:remove 17:add 18:x"       # what the headless "user" presses, frame:key (render_stubs.c)
 
 
 def check_whole_program(world, env, tmp_path, ranks, frames, libname, script=None):
