@@ -159,7 +159,7 @@ def check_whole_program(world, env, tmp_path, ranks, frames, libname, script=Non
 
 
 @pytest.mark.skipif(not os.path.exists(WORLD_GPU), reason="oracle/_ref not built")
-@pytest.mark.parametrize("ranks", [3, 4])
+@pytest.mark.parametrize("ranks", [3, 4, 8])
 def test_whole_reference_program_with_its_renderer_on_the_emulated_library(built_lib, tmp_path, ranks):
     # (4 ranks: both runs under a shuffled block / thread order of the emulator -- the arrival order of the atomics must not matter)
     check_whole_program(WORLD_GPU, dict(os.environ, LD_PRELOAD=build_emu(), **({"SPH_EMU_ORDER": "shuffle"} if ranks == 4 else {})),
