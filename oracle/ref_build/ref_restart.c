@@ -5,7 +5,9 @@
  * does (fluid.c:762-767).  K forked ranks over the mini-MPI, one slab each.  TEST INFRASTRUCTURE ONLY; links the product
  * library, no reference code.
  *
- *   ref_restart --ranks K --steps N --out FILE     ->  FILE.r<rank>: int32 n, n x (x, y, v_x, v_y) float32, ascending uid
+ *   ref_restart --ranks K --steps N --out FILE     ->  FILE.r<rank>: int32 n, n x (x, y, v_x, v_y) float32, ascending uid,
+ *                                                      then n x 2 int16: the slab's frame from sph_ref_pack_coords (the
+ *                                                      device-side feed of INTEGRATION.md 2, device order)
  */
 #include <math.h>
 #include <signal.h>
@@ -114,6 +116,9 @@ int main(int argc, char **argv)
     const int n = params.number_fluid_particles_local;
     fwrite(&n, 4, 1, f);
     for (int i = 0; i < n; i++) { float v[4] = { pointers[i]->x, pointers[i]->y, pointers[i]->v_x, pointers[i]->v_y }; fwrite(v, 4, 4, f); }
+    short *coords = calloc((size_t)2 * cap, sizeof *coords);
+    if (sph_ref_pack_coords(coords, cap) != n) { fprintf(stderr, "ref_restart: sph_ref_pack_coords disagrees about the population\n"); return 5; }
+    fwrite(coords, 4, (size_t)n, f);
     fclose(f);
     sph_ref_detach();
     return 0;

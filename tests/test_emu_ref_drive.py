@@ -222,10 +222,15 @@ def check_restart_from_a_moving_fluid(env, tmp_path, ranks=3, steps=8):
     that already moves.  The attach must hand every slab its ghost layer (one exchange), or the first viscosity pass
     misses the neighbours across the edges; with it, `ranks` slabs equal one slab bit for bit (without it they do
     not: checked by hand when this was written)."""
-    def rd(path):
+    def rd(path, w=15.0, h=8.4375):
         raw = open(path, "rb").read()
         n = int(np.frombuffer(raw, "i4", 1)[0])
-        return np.frombuffer(raw, "f4", 4 * n, 4).reshape(n, 4)
+        state = np.frombuffer(raw, "f4", 4 * n, 4).reshape(n, 4)
+        # the slab's device-side frame (sph_ref_pack_coords) is the reference's formula on these positions (fluid.c:358-361)
+        feed = np.frombuffer(raw, "i2", 2 * n, 4 + 16 * n).reshape(n, 2)
+        want = pack(state[:, 0].copy(), state[:, 1].copy(), w, h)
+        assert np.array_equal(np.sort(feed.copy().view("i4").ravel()), np.sort(want.copy().view("i4").ravel()))
+        return state
 
     def canon(a):
         return a[np.lexsort(a.view("u4").T[::-1])].view("u4")
