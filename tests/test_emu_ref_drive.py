@@ -162,8 +162,9 @@ def check_whole_program(world, env, tmp_path, ranks, frames, libname, script=Non
 @pytest.mark.parametrize("ranks", [3, 4, 8])
 def test_whole_reference_program_with_its_renderer_on_the_emulated_library(built_lib, tmp_path, ranks):
     # (4 ranks: both runs under a shuffled block / thread order of the emulator -- the arrival order of the atomics must not matter)
-    check_whole_program(WORLD_GPU, dict(os.environ, LD_PRELOAD=build_emu(), **({"SPH_EMU_ORDER": "shuffle"} if ranks == 4 else {})),
-                        tmp_path, ranks, 14, "libsph_emu.so")
+    # (3 ranks: the host mirror only at the driver's frame rate, every 4th step, fluid.c:105)
+    extra = {4: {"SPH_EMU_ORDER": "shuffle"}, 3: {"SPH_REF_MIRROR_EVERY": "4"}}.get(ranks, {})
+    check_whole_program(WORLD_GPU, dict(os.environ, LD_PRELOAD=build_emu(), **extra), tmp_path, ranks, 14, "libsph_emu.so")
 
 
 GOO_KEYS = "2:y 3:remove 9:add 12:x"      # the goo preset needs SPH_VISC_STAB
