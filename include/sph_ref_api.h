@@ -75,6 +75,9 @@ void sph_ref_set_rank(int rank, int nranks);
  * cannot make these two calls: it links sph_b200/host/glue/sph_ref_mpi_glue.c instead, whose sph_ref_host_mpi() the
  * library finds by itself and which answers both questions from MPI_COMM_COMPUTE. */
 void sph_ref_set_transport(sph_sendrecv_fn fn, void *user);
+/* NOT defined by the library: the host's glue object defines it (sph_b200/host/glue/sph_ref_mpi_glue.c); the library
+ * refers to it weakly and calls it once, before it needs to know its slab.  Returns 0 and fills all four. */
+int sph_ref_host_mpi(int *rank, int *nranks, sph_sendrecv_fn *fn, void **user);
 
 /* ---- fluid.h:112-126 ---- */
 void apply_gravity(fluid_particle **fluid_particle_pointers, param *params);

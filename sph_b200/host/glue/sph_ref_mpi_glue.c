@@ -11,8 +11,8 @@
 #include <stddef.h>
 #include <mpi.h>
 
-#include "communication.h"      /* the reference's: MPI_COMM_COMPUTE */
-#include "sph_b200.h"
+#include "communication.h"      /* the reference's: MPI_COMM_COMPUTE (brings fluid.h, whose types sph_ref_api.h then reuses) */
+#include "sph_ref_api.h"
 
 #define SPH_GLUE_TAG 23         /* the reference uses 7, 8, 9 and 17 */
 

@@ -68,8 +68,8 @@ static struct {
     fluid_particle *base;           /* the particle array behind the pointer array (identify_oob_particles carries it) */
 } H;
 
-/* Defined by the host's glue object, if there is one (sph_b200/host/glue/sph_ref_mpi_glue.c). */
-extern int sph_ref_host_mpi(int *rank, int *nranks, sph_sendrecv_fn *fn, void **user) __attribute__((weak));
+/* Defined by the host's glue object, if there is one (sph_b200/host/glue/sph_ref_mpi_glue.c; declared in sph_ref_api.h). */
+#pragma weak sph_ref_host_mpi
 
 static void ask_host(void)
 {

@@ -32,9 +32,12 @@ def test_reference_named_symbols_exported(built_lib):
     L = C.CDLL(built_lib)
     hdr = open(os.path.join(os.path.dirname(built_lib), "..", "include", "sph_ref_api.h")).read()
     for name in REF_NAMES + ("sph_ref_attach", "sph_ref_sync_to_host", "sph_ref_detach", "sph_ref_pack_coords",
-                             "sph_ref_last_error", "sph_ref_context"):
+                             "sph_ref_last_error", "sph_ref_context", "sph_ref_set_rank", "sph_ref_set_transport",
+                             "sph_ref_set_mirror"):
         assert re.search(r"\b%s\s*\(" % name, hdr), name
         assert hasattr(L, name), name
+    # the weak hook is the HOST's to define (sph_b200/host/glue/sph_ref_mpi_glue.c): declared, referenced, not exported
+    assert re.search(r"\bsph_ref_host_mpi\s*\(", hdr) and not hasattr(L, "sph_ref_host_mpi")
 
 
 def test_host_helpers_match_oracle(built_lib):
