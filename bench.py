@@ -257,7 +257,7 @@ def main_ours(args):
             from sph_b200.slab import SlabRunner
             sim = SlabRunner(prob, t, rank, world, stream, capacity_factor=2.0, balance_policy=args.balance,
                              halo_width=args.halo_width)
-        if args.visc_stab > 0.0:
+        if args.visc_stab is not None:                  # default: the library's (gamma 0.5 for blocks with dt*sigma >= 0.5)
             sim.ctx.set_viscosity_stabilisation(args.visc_stab)
         mark("created")
         sim.init_lattice()
@@ -339,7 +339,8 @@ def main_ours(args):
             "config": {
                 "workload": f"2D dam-break block, {n_global} particles ({args.n} requested per GPU), preset {args.preset}, "
                             f"h={prob['h']:.6f}, tank {prob['tank_w']:.1f}x{prob['tank_h']:.1f}, {world} x-slab(s)",
-                "viscosity_gather": f"stabilised, gamma {args.visc_stab} (k_coupling + k_advect<true>)" if args.visc_stab > 0.0 else "plain",
+                "viscosity_gather": ("library default: stabilised gather (gamma 0.5) for blocks with dt*sigma >= 0.5 (goo), plain otherwise"
+                                     if args.visc_stab is None else f"forced: gamma {args.visc_stab} for every block (0 = plain)"),
                 "state": f"{args.preroll} pre-roll steps + {args.warmup} warm-up steps from the lattice",
                 "mean_neighbours_per_particle": stats["mean_neighbours"], "max_bucket": stats["max_bucket"],
                 "l2": "flushed between timed steps (256 MiB write, outside the per-step CUDA-event brackets)",
@@ -519,8 +520,9 @@ def main():
     ap.add_argument("--preset", default="x")
     ap.add_argument("--halo-width", type=float, default=None,
                     help="ghost-layer width in h at N > 1 (default: the build's, 2; the one-exchange build: 3.5, 4.5 with --visc-stab)")
-    ap.add_argument("--visc-stab", type=float, default=0.0, metavar="GAMMA",
-                    help="optional stabilised viscosity gather (needed for --preset y, DESIGN.md 5b); 0 = plain gather (default)")
+    ap.add_argument("--visc-stab", type=float, default=None, metavar="GAMMA",
+                    help="force the stabilised viscosity gather with this gamma for every block (0 = plain gather everywhere); "
+                         "default: the library's own rule (gamma 0.5 where dt*sigma >= 0.5, i.e. the goo preset, DESIGN.md 5b)")
     ap.add_argument("--cpu-steps", type=int, default=20, help="timed steps of the cpu_baseline sample")
     ap.add_argument("--cpu-warmup", type=int, default=300, help="untimed steps of the cpu_baseline sample (bounded: the "
                     "reference arm, --impl reference, runs the full pre-roll)")

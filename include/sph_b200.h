@@ -146,7 +146,9 @@ int sph_queue_params(sph_ctx *ctx, const sph_tunable *t);
 /* Slab edges only (node_start_x / node_end_x); used by migration and halo selection. */
 int sph_set_edges(sph_ctx *ctx, float node_start_x, float node_end_x);
 
-/* OPTIONAL stabilised viscosity gather (off by default; not in the reference).
+/* Stabilised viscosity gather (not in the reference).  DEFAULT: gamma = 0.5, min_dt_sigma = 0.5, i.e. it
+ * engages by itself for the reference's goo preset (dt*sigma = 0.83) and for none of the others (<= 0.17), whose
+ * results it would not change by a bit anyway; gamma = 0 switches it off (the plain gather for every block).
  * The reference applies viscosity_impluses pair by pair in place (fluid.c:442-472), which never overshoots.
  * A gather sums a particle's impulses from frozen velocities, and once C_i = sum_j dt (1-q)(sigma + beta u)
  * over its approaching pairs exceeds ~2 (the "goo" preset, controls.c:359-371) it overshoots and never
@@ -154,7 +156,8 @@ int sph_set_edges(sph_ctx *ctx, float node_start_x, float node_end_x);
  * symmetric (momentum still exchanged pairwise), independent of the slab decomposition, and exactly 1
  * wherever the plain gather is stable.  It costs one more gather pass (C), so it only runs for parameter
  * blocks with dt * sigma >= min_dt_sigma (0 = whenever gamma > 0).  gamma = 0.5 reproduced the
- * reference's long-run statistics for the goo preset within the reference's own order sensitivity. */
+ * reference's long-run statistics for the goo preset within the reference's own order sensitivity.
+ * This is the library's one algorithmic deviation from the reference beyond gather-vs-sweep order. */
 int sph_set_viscosity_stabilisation(sph_ctx *ctx, float gamma, float min_dt_sigma);
 
 /* ---- state ---- */

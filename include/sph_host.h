@@ -49,6 +49,12 @@ void sph_host_balance_ex(sph_tunable *master, int nactive, const int *counts, in
  * direction flips outside [-1, 1], gl_y = sinf(3.14 * 5 * gl_x) / 10 - 0.6, then opengl_to_sim
  * (renderer.c:396-404).  Updates t->mover_center_{x,y}; *gl_x / *direction carry the state. */
 void sph_host_mover_autopilot(sph_tunable *t, float tank_w, float tank_h, float *gl_x, int *direction);
+/* The same path with the per-frame step as a parameter.  The reference's 0.01 GL units are 0.075 simulation units
+ * per frame in ITS tank (width 15, fluid.c:119), 2.25 units/s against the +-5 velocity clamp (fluid.c:613-625).  In a
+ * tank scaled with the particle count the same GL step is a teleport (4 M particles: 164 units/s), and whatever the
+ * mover meets is piled onto its surface beyond the reference's bucket capacity (hash.c:160-165).  Scaled problems
+ * (BASELINE config 4) therefore pass dx_gl = 0.01 * 15 / tank_w: the reference's step in simulation units. */
+void sph_host_mover_autopilot_ex(sph_tunable *t, float tank_w, float tank_h, float *gl_x, int *direction, float dx_gl);
 
 /* remove_partition / add_partition (controls.c:405-455): park the last active slab outside the
  * tank / split the last active slab in half. Return the new number of active slabs. */

@@ -256,10 +256,10 @@ class GatherOracle:
     def queue_params(self, t): self.L.orc_g_queue_params(self.h, C.byref(t))
     def set_edges(self, s, e): self.L.orc_g_set_edges(self.h, s, e)
 
-    def set_viscosity_stabilisation(self, gamma):
-        """Proposal (off by default): symmetric damping of the viscosity gather for stiff presets."""
-        self.L.orc_g_set_viscosity_stabilisation.argtypes = [C.c_void_p, C.c_float]
-        self.L.orc_g_set_viscosity_stabilisation(self.h, float(gamma))
+    def set_viscosity_stabilisation(self, gamma, min_dt_sigma=0.0):
+        """Symmetric damping of the viscosity gather for stiff presets; default (0.5, 0.5) like sph_create."""
+        self.L.orc_g_set_viscosity_stabilisation_ex.argtypes = [C.c_void_p, C.c_float, C.c_float]
+        self.L.orc_g_set_viscosity_stabilisation_ex(self.h, float(gamma), float(min_dt_sigma))
     def set_neighbors(self, l, r): self.L.orc_g_set_neighbors(self.h, int(l), int(r))
 
     def upload(self, aos, uid=None):

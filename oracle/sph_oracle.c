@@ -389,6 +389,7 @@ struct orc_g {
     float *dens, *densn;
     float *coupling;             /* per entry: sum of its pairs' viscosity coefficients (stabilised mode only) */
     float visc_gamma;            /* 0 = the plain Jacobi gather; > 0 = stabilised, see orc_g_set_viscosity_stabilisation */
+    float visc_min_dt_sigma;     /* the stabilised pass engages for parameter blocks with dt*sigma at or above this */
     int *cell_start;
     int stage;
     unsigned char *send[2], *recv[2];   /* [0]=left, [1]=right */
@@ -419,6 +420,7 @@ orc_g *orc_g_create(const sph_config *cfg)
     g->auid = (uint32_t *)calloc(g->cap, 4); g->tuid = (uint32_t *)calloc(g->cap, 4);
     g->tkey = (int *)calloc(g->cap, sizeof(int));
     g->coupling = (float *)calloc(g->cap, sizeof(float));
+    g->visc_gamma = 0.5f; g->visc_min_dt_sigma = 0.5f;       /* the product library's defaults (sph_create) */
     g->sort_rows = g->size_y * DIV;
     g->cell_start = (int *)calloc((size_t)g->size_x * g->size_y * DIV * DIV + 1, sizeof(int));
     g->msg_bytes = msg_bytes_for(g->msg_cap);
@@ -597,7 +599,13 @@ static void g_pack_halo0(orc_g *g, int side, float x, float y, uint32_t uid)
  * was stable anyway (the default fluid: C_i ~ 0.3), so those results do not change by a bit.
  * gamma = 0.5 reproduced the reference's long-run statistics for all four presets within the reference's
  * own sensitivity to the particle order. */
-void orc_g_set_viscosity_stabilisation(orc_g *g, float gamma) { g->visc_gamma = gamma; }
+void orc_g_set_viscosity_stabilisation(orc_g *g, float gamma) { g->visc_gamma = gamma; g->visc_min_dt_sigma = 0.0f; }
+/* with the threshold of sph_set_viscosity_stabilisation; the default of both libraries is (0.5, 0.5): the pass
+ * engages by itself for the goo preset (dt*sigma = 0.83, controls.c:359-371) and for no other preset */
+void orc_g_set_viscosity_stabilisation_ex(orc_g *g, float gamma, float min_dt_sigma)
+{
+    g->visc_gamma = gamma; g->visc_min_dt_sigma = min_dt_sigma;
+}
 
 static void g_viscosity_coupling(orc_g *g)
 {
@@ -633,7 +641,7 @@ void orc_g_advect(orc_g *g)
     g->n_src = g->n_tot;
     for (int s = 0; s < 2; s++) { int *hd = msg_hdr(g->send[s]); hd[0] = hd[1] = hd[2] = hd[3] = 0; }
     g->st.migrated_left = g->st.migrated_right = 0;
-    const float gamma = g->visc_gamma;
+    const float gamma = (g->visc_gamma > 0.0f && dt * t->sigma >= g->visc_min_dt_sigma) ? g->visc_gamma : 0.0f;
     if (gamma > 0.0f) g_viscosity_coupling(g);
 
     for (int i = 0; i < g->n_tot; i++) {

@@ -85,6 +85,7 @@ void orc_g_set_edges(orc_g *g, float start_x, float end_x);
 /* PROPOSAL, off by default (gamma = 0): symmetric damping of the viscosity gather where the plain Jacobi
  * sum overshoots (stiff presets); see the comment at the definition. */
 void orc_g_set_viscosity_stabilisation(orc_g *g, float gamma);
+void orc_g_set_viscosity_stabilisation_ex(orc_g *g, float gamma, float min_dt_sigma);
 int orc_g_upload(orc_g *g, const sph_particle *aos, const uint32_t *uid, int n);
 int orc_g_download(orc_g *g, sph_particle *aos, uint32_t *uid, int order, int include_halo);
 void orc_g_advect(orc_g *g);

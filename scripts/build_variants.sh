@@ -8,3 +8,8 @@ python -m sph_b200.build --variant pd4 -DSPH_RELAX_PD4=1
 python -m sph_b200.build --variant relax_b3 -DSPH_BLOCKS_RELAX=3
 python -m sph_b200.build --variant pdl -DSPH_PDL=1
 python -m sph_b200.build --variant packed_pdl -DSPH_PACKED=1 -DSPH_PDL=1
+python -m sph_b200.build --variant flat -DSPH_GRID_MULT=0
+python -m sph_b200.build --variant m4 -DSPH_GRID_MULT=4
+python -m sph_b200.build --variant m16 -DSPH_GRID_MULT=16
+python -m sph_b200.build --variant packed_flat -DSPH_PACKED=1 -DSPH_GRID_MULT=0
+python -m sph_b200.build --variant packed_pd4_pdl_flat -DSPH_PACKED=1 -DSPH_RELAX_PD4=1 -DSPH_PDL=1 -DSPH_GRID_MULT=0

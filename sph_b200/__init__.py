@@ -308,7 +308,7 @@ class Context:
 # ------------------------------------------------------------------------------------------------
 # C host layer (include/sph_host.h): start-up geometry, parameter model, slab load balancer
 # ------------------------------------------------------------------------------------------------
-HOST_SYMBOLS = ("sph_host_mover_autopilot", "sph_host_spacing", "sph_host_default_params", "sph_host_preset", "sph_host_partition",
+HOST_SYMBOLS = ("sph_host_mover_autopilot", "sph_host_mover_autopilot_ex", "sph_host_spacing", "sph_host_default_params", "sph_host_preset", "sph_host_partition",
                 "sph_host_lattice", "sph_host_balance", "sph_host_balance_ex", "sph_host_remove_partition", "sph_host_add_partition")
 
 
@@ -322,6 +322,7 @@ def _host():
         L.sph_host_partition.argtypes = [C.c_float] * 6 + [C.c_int] + [C.c_void_p] * 4
         L.sph_host_lattice.argtypes = [C.c_float] * 4 + [C.c_int] * 3 + [C.c_void_p] * 2
         L.sph_host_mover_autopilot.argtypes = [C.POINTER(Tunable), C.c_float, C.c_float, C.POINTER(C.c_float), C.POINTER(C.c_int)]
+        L.sph_host_mover_autopilot_ex.argtypes = [C.POINTER(Tunable), C.c_float, C.c_float, C.POINTER(C.c_float), C.POINTER(C.c_int), C.c_float]
         L.sph_host_balance.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
         L.sph_host_remove_partition.argtypes = [C.c_void_p, C.c_int]
         L.sph_host_add_partition.argtypes = [C.c_void_p, C.c_int, C.c_int]

@@ -42,6 +42,10 @@ template <class... A> static PdlLauncher<A...> pdl_launcher(void (*k)(A...), int
 #define SPH_LAUNCH(kernel, grid, stream) emu::make_launcher(kernel, (grid), SPH_THREADS, (stream))
 #endif
 
+#ifndef SPH_GRID_MULT
+#define SPH_GRID_MULT 8
+#endif
+
 enum { ST_READY = 0, ST_ADVECTED, ST_SORTED1, ST_DENSITY, ST_RELAXED, ST_REQUEUED };
 
 struct sph_ctx {
@@ -169,7 +173,14 @@ extern "C" int sph_create(const sph_config *cfg, sph_ctx **out)
     ctx->size_y = (int)ceil((cfg->tank_h - 0.0f) / cfg->h);
     const size_t cap = (size_t)cfg->capacity;
     const size_t ncell_max = (size_t)ctx->size_x * ctx->size_y * SPH_CELL_DIV * SPH_CELL_DIV;
-    ctx->grid = std::min<int>((int)((cap + SPH_THREADS - 1) / SPH_THREADS), prop.multiProcessorCount * 8);
+    // Blocks of the per-particle kernels.  SPH_GRID_MULT > 0: persistent grid-stride blocks, that many per SM;
+    // 0: one block per 256 entries of CAPACITY (the population lives on the device and a captured graph must
+    // survive its changes; blocks beyond it return at once), so the block scheduler balances the chunks dynamically.
+#if SPH_GRID_MULT > 0
+    ctx->grid = std::min<int>((int)((cap + SPH_THREADS - 1) / SPH_THREADS), prop.multiProcessorCount * SPH_GRID_MULT);
+#else
+    ctx->grid = (int)((cap + SPH_THREADS - 1) / SPH_THREADS);
+#endif
 
     for (int i = 0; i < 4; i++) CK(cudaMalloc(&ctx->P[i], cap * sizeof(float2)));
     for (int i = 0; i < 3; i++) CK(cudaMalloc(&ctx->Q[i], cap * sizeof(float2)));
@@ -181,7 +192,15 @@ extern "C" int sph_create(const sph_config *cfg, sph_ctx **out)
 #endif
     CK(cudaMalloc(&ctx->coupling, cap * sizeof(float)));
     CK(cudaMalloc(&ctx->dopt, sizeof(DevOptions)));
-    CK(cudaMemset(ctx->dopt, 0, sizeof(DevOptions)));
+    {
+        // Default: the stabilised viscosity gather engages by itself for parameter blocks with dt*sigma >= 0.5, i.e.
+        // for the reference's goo preset (controls.c:359-371: 0.83) and for none of its other presets (<= 0.17),
+        // whose results it would not change by a bit anyway.  The plain gather does not settle that preset
+        // (DESIGN.md 5b); this is the library's one algorithmic deviation and needs no call and no environment.
+        ctx->visc_gamma = 0.5f; ctx->visc_min_dt_sigma = 0.5f;
+        DevOptions o; o.visc_gamma = ctx->visc_gamma;
+        CK(cudaMemcpy(ctx->dopt, &o, sizeof o, cudaMemcpyHostToDevice));
+    }
     CK(cudaMalloc(&ctx->cnt, (ncell_max + 1) * sizeof(int)));
     CK(cudaMalloc(&ctx->cell_start, (ncell_max + 1) * sizeof(int)));
     CK(cudaMalloc(&ctx->t_key, cap * sizeof(int)));

@@ -151,8 +151,9 @@ int sph_ref_attach(fluid_particle **pointers, param *params, AABB_t *boundary, n
     int rc = sph_create(&cfg, &G.ctx);
     if (rc) { note("sph_ref_attach", rc); if (G.ctx) { sph_destroy(G.ctx); G.ctx = NULL; } return rc; }
     G.tank_w = cfg.tank_w; G.tank_h = cfg.tank_h;
-    {   /* optional stabilised viscosity gather for hosts driven through the reference's own entry points, which
-         * have no call for it: SPH_VISC_STAB=gamma[,min_dt_sigma] (e.g. "0.5,0.5": engages for the goo preset only) */
+    {   /* the stabilised viscosity gather is on by default (0.5, 0.5: engages for the goo preset only, sph_create);
+         * hosts driven through the reference's own entry points, which have no call for it, can override it:
+         * SPH_VISC_STAB=gamma[,min_dt_sigma] ("0" = the plain gather for every preset) */
         const char *vs = getenv("SPH_VISC_STAB");
         if (vs) {
             float gamma = 0.0f, thr = 0.0f;

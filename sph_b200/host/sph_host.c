@@ -137,8 +137,13 @@ void sph_host_balance_ex(sph_tunable *m, int nactive, const int *counts, int tot
 
 void sph_host_mover_autopilot(sph_tunable *t, float tank_w, float tank_h, float *gl_x, int *direction)
 {
+    sph_host_mover_autopilot_ex(t, tank_w, tank_h, gl_x, direction, 0.01f);
+}
+
+void sph_host_mover_autopilot_ex(sph_tunable *t, float tank_w, float tank_h, float *gl_x, int *direction, float dx_gl)
+{
     /* renderer.c:513-531 */
-    float x = *gl_x + 0.01f * (float)(*direction);
+    float x = *gl_x + dx_gl * (float)(*direction);
     if (x > 1.0f || x < -1.0f) *direction = -*direction;
     const float y = sinf(3.14f * 5.0f * x) / 10.0f - 0.6f;
     *gl_x = x;

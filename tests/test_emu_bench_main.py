@@ -13,7 +13,8 @@ CONTRACT = ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step
             "vs_baseline", "dtype", "data", "config", "roofline", "clocks", "e2e", "gpu_launches")
 
 
-@pytest.mark.parametrize("extra,gather", [([], "plain"), (["--preset", "y", "--visc-stab", "0.5"], "stabilised")])
+@pytest.mark.parametrize("extra,gather", [([], "library default"), (["--preset", "y"], "library default: stabilised"),
+                                          (["--preset", "y", "--visc-stab", "0"], "forced")])
 def test_bench_main_runs_end_to_end_on_the_emulator(built_lib, extra, gather):
     cmd = [sys.executable, os.path.join(HERE, "emu", "run_bench_emulated.py"), "--particles", "3000", "--steps", "4",
            "--warmup", "3", "--preroll", "8", "--no-cpu-baseline"] + extra
@@ -29,4 +30,4 @@ def test_bench_main_runs_end_to_end_on_the_emulator(built_lib, extra, gather):
     assert d["e2e"]["value"] > 0 and d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0
     assert "pipelined" in d["e2e"]["protocol"] and d["e2e"]["synchronous_value"] > 0 and "pipelined_error" not in d["e2e"]
     # 11 launches per step (12 with the stabilised gather's extra pass) in the timed region
-    assert d["gpu_launches"] == 4 * (12 if gather == "stabilised" else 11)
+    assert d["gpu_launches"] == 4 * (12 if gather.endswith("stabilised") else 11)

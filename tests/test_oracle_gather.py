@@ -46,17 +46,19 @@ def test_long_run_statistics(name):
 
 
 def test_goo_preset_needs_the_stabilised_viscosity_gather():
-    """KNOWN GAP of the shipped gather.  With the "goo" preset (sigma 100, beta 10:
+    """Why the stabilised viscosity gather is ON BY DEFAULT for blocks with dt*sigma >= 0.5.  With the "goo" preset (sigma 100, beta 10:
     dt sigma = 0.83 per pair) the viscosity impulses summed from frozen velocities overshoot and the fluid
     never settles (kinetic energy 3.5 against the reference's 2e-4, heap three times too high), while the
     reference's in-place sweep damps every pair without overshoot.  The symmetric damping proposed in
     oracle/sph_oracle.c (orc_g_set_viscosity_stabilisation, gamma 0.5) settles it within the reference's own
-    order sensitivity and leaves the stable presets bit-identical.  The CUDA path implements the plain
-    gather only; this test pins both facts so that neither can change unnoticed."""
+    order sensitivity and leaves the stable presets bit-identical.  Both libraries engage it by default for such
+    blocks (sph_create / orc_g_create: gamma 0.5, threshold 0.5); this test pins the gap of the plain gather
+    (gamma = 0), the fix, and that the DEFAULT is the fix."""
     a, _ = lattice(make_problem(**LONGRUN["goo_rect1508"]))
     with pytest.raises(AssertionError):
-        pc.check_long_run_statistics(make, "goo_rect1508", a)
+        pc.check_long_run_statistics(make, "goo_rect1508", a, prepare=lambda g: g.set_viscosity_stabilisation(0.0))
     from common import GOO_STABILISED_WIDEN
+    pc.check_long_run_statistics(make, "goo_rect1508", a, widen=GOO_STABILISED_WIDEN)       # the default
     pc.check_long_run_statistics(make, "goo_rect1508", a, prepare=lambda g: g.set_viscosity_stabilisation(0.5),
                                  widen=GOO_STABILISED_WIDEN)
     # ... and from a lattice with ONE coordinate moved by one ulp, which lands in the other packing of the heap
