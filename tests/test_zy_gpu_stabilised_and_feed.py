@@ -49,7 +49,7 @@ def test_stabilised_viscosity_engages_on_goo_and_leaves_stable_presets_bit_ident
         z, t, tank_w, tank_h, h, _ = load_golden(name)
         st = z[f"w{warm}_state"]
         outs = []
-        for maker in (mk, mk_stab):
+        for maker in (mk_plain, mk_stab):
             b = maker(tank_w, tank_h, h, len(st) + 64)
             b.set_params(t); b.upload(st); b.step(20)
             b.advect(); b.sort(); b.density(); b.relax(); b.sort()
