@@ -43,7 +43,10 @@ template <class... A> static PdlLauncher<A...> pdl_launcher(void (*k)(A...), int
 #endif
 
 #ifndef SPH_GRID_MULT
-#define SPH_GRID_MULT 8
+#define SPH_GRID_MULT 8          // blocks per SM of the gather kernels (0: one block per 256 entries of capacity)
+#endif
+#ifndef SPH_GRID_MULT_SORT
+#define SPH_GRID_MULT_SORT 8     // blocks per SM of the sort's streaming kernels (scan, scatter, reorder)
 #endif
 
 enum { ST_READY = 0, ST_ADVECTED, ST_SORTED1, ST_DENSITY, ST_RELAXED, ST_REQUEUED };
@@ -88,7 +91,8 @@ struct sph_ctx {
     int n_uploaded;                  // single slab: the particle count never changes after an upload
     unsigned char *stage_host;       // sph_exchange_via_host: 4 pinned message buffers (send l/r, recv l/r), allocated on first use
     int stage;
-    int grid;
+    int grid;                        // per-particle gather kernels
+    int sort_grid;                   // the sort's streaming kernels
     int size_x, size_y;
     cudaGraphExec_t graph[2];        // whole step, [1] = with the stabilised viscosity gather
     bool graph_ready[2];
@@ -181,6 +185,7 @@ extern "C" int sph_create(const sph_config *cfg, sph_ctx **out)
 #else
     ctx->grid = (int)((cap + SPH_THREADS - 1) / SPH_THREADS);
 #endif
+    ctx->sort_grid = std::min<int>((int)((cap + SPH_THREADS - 1) / SPH_THREADS), prop.multiProcessorCount * SPH_GRID_MULT_SORT);
 
     for (int i = 0; i < 4; i++) CK(cudaMalloc(&ctx->P[i], cap * sizeof(float2)));
     for (int i = 0; i < 3; i++) CK(cudaMalloc(&ctx->Q[i], cap * sizeof(float2)));
@@ -445,15 +450,15 @@ static int launch_sort(sph_ctx *ctx, int which, bool with_unpack = true, bool re
         ctx->launches++;
     }
     // grids sized for the widest window (tile loops inside): a captured graph survives moving slab edges
-    const int sgrid = std::max(1, std::min(ctx->scan_grid, 8 * 148));
+    const int sgrid = std::max(1, std::min(ctx->scan_grid, SPH_GRID_MULT_SORT * 148));
     SPH_LAUNCH(k_scan_totals, sgrid, ctx->stream)(ctx->dp, ctx->counters, ctx->cnt, ctx->tile_total);
     SPH_LAUNCH(k_scan_apply, sgrid, ctx->stream)(ctx->dp, ctx->counters, ctx->cnt, ctx->cell_start, ctx->tile_total,
                                                          ctx->cfg.nranks > 1 ? ctx->send[0] : nullptr,
                                                          ctx->cfg.nranks > 1 ? ctx->send[1] : nullptr,
                                                          (which == 1 && with_unpack) ? 1 : 0);
-    SPH_LAUNCH(k_scatter, ctx->grid, ctx->stream)(ctx->counters, ctx->cell_start, ctx->t_key, ctx->t_slot, su,
+    SPH_LAUNCH(k_scatter, ctx->sort_grid, ctx->stream)(ctx->counters, ctx->cell_start, ctx->t_key, ctx->t_slot, su,
                                                           ctx->ord_uid, ctx->ord_src, ctx->ord_key);
-    SPH_LAUNCH(k_reorder, ctx->grid, ctx->stream)(ctx->dp, ctx->counters, ctx->cell_start, ctx->ord_key,
+    SPH_LAUNCH(k_reorder, ctx->sort_grid, ctx->stream)(ctx->dp, ctx->counters, ctx->cell_start, ctx->ord_key,
                                                           ctx->ord_uid, ctx->ord_src, sp, sq, dp, dq, du);
     ctx->launches += 4;
     ctx->hp.gx0 = ctx->hp.gx0_new;     // the scan kernel did the same on the device

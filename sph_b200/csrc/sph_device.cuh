@@ -136,6 +136,13 @@ __device__ __forceinline__ float rcp_approx(float x)
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 }
+// FMNMX.NAN: a NaN operand wins, so that a running maximum also reports "not finite"
+__device__ __forceinline__ float max_nan(float a, float b)
+{
+    float r;
+    asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+    return r;
+}
 // Packed FP32 (sm_100: FADD2 / FMUL2 / FFMA2, two IEEE round-to-nearest fp32 operations per issued instruction;
 // the gathers are bound by instruction issue, not by the FMA pipe).  A pair lives in a 64-bit register; a float2
 // loaded from memory is already one.  Every operation is the same rn operation as its scalar counterpart, so
@@ -171,6 +178,17 @@ __device__ __forceinline__ void pdl_enter()
 {
 #if SPH_PDL
     asm volatile("griddepcontrol.wait;" ::: "memory");
+#if SPH_PDL == 1
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+#endif
+}
+// SPH_PDL=2: the trigger at the END of a block's work instead (round 2: with the trigger at the top the blocks of grid
+// n+1 took the block slots that grid n's second wave of blocks was waiting for, and the step got slower, 263 us
+// against 253; profiles/r2_variants.md).  The dependents then start while the last blocks of grid n drain.
+__device__ __forceinline__ void pdl_done()
+{
+#if SPH_PDL == 2
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 #endif
 }

@@ -31,6 +31,10 @@ constexpr int kGatherUnroll = SPH_UNROLL;     // (#pragma unroll takes a constan
 // SPH_PACKED_RELAX=1: the same for k_relax's pair physics ((x, y) accumulate in one register).  Separate flag:
 // in SASS the packed pair saves ~4 FP instructions but ptxas adds register moves around the rare-path branches,
 // and the kernel is latency- rather than issue-bound; to be decided by measurement.
+// SPH_TRIM=1: k_advect's candidate loop with the impulse clamp moved to a per-row exact redo (see the kernel)
+#ifndef SPH_TRIM
+#define SPH_TRIM 0
+#endif
 #ifndef SPH_PACKED_RELAX
 #define SPH_PACKED_RELAX 0
 #endif
@@ -249,6 +253,96 @@ k_advect(const DevParams *__restrict__ Pp, int *__restrict__ counters,
         float vx = v0.x, vy = v0.y + gdt;                               // apply_gravity
         const Rows R = candidate_rows(p, P, cell_start);
         const float gci = STAB ? gamma * coupling[i] : 0.0f;
+#if SPH_TRIM
+        // SPH_TRIM=1 (round 2): the candidate loop without the per-component clamp.  The +-2.5 clamp of a pair's
+        // half impulse (fluid.c:459 on the whole impulse) can only bind when |t| h > 2.5, because a neighbour has
+        // |dx|, |dy| <= h; the loop applies v -= t d as two FFMAs, tracks max |t| over the row (one FMNMX.NAN), and
+        // only a row in which the clamp COULD bind (never, in a settled fluid) is redone from its saved entry
+        // velocity with the exact body below.  26 instead of 33 issued instructions per candidate; -w hdt is formed
+        // as fma(r, hdt/h, -hdt).  Rounding differs from the default build's (fused accumulate), order does not.
+        const float hdt_over_h = hdt * h_recip, tlim = 2.5f * h_recip;
+        // one candidate, exactly as in the default build: used for the rows that need the clamp
+        auto cand_exact = [&](int j) {
+            const float2 q = pos[j];
+            const float dx = q.x - p.x, dy = q.y - p.y;
+            const float r2 = dist2(dx, dy);
+            const bool in = r2 <= h2;
+            const float2 vq = vel[j];
+            const float rs = rsqrt_approx(r2);
+            const float u_in = ((v0.x - vq.x) * dx + (v0.y - vq.y) * dy) * rs;
+            const bool hit = in && u_in > 0.0f;
+            const float whdt = fmaf(-r2 * rs, h_recip, 1.0f) * hdt;
+            const float t = stab_scale<STAB>(u_in * fmaf(P.beta, u_in, P.sigma) * whdt * rs, gci, gamma, coupling, j);
+            const float ix = fminf(fmaxf(t * dx, -2.5f), 2.5f);
+            const float iy = fminf(fmaxf(t * dy, -2.5f), 2.5f);
+            vx -= hit ? ix : 0.0f;
+            vy -= hit ? iy : 0.0f;
+        };
+#if SPH_PACKED
+        const f32x2 pp = pk2(p.x, p.y), v0p = pk2(v0.x, v0.y);
+        const f32x2 hh2 = pk2(hdt_over_h, hdt_over_h), nhdt2 = pk2(-hdt, -hdt);
+        const f32x2 beta2 = pk2(P.beta, P.beta), sigma2 = pk2(P.sigma, P.sigma);
+#endif
+#pragma unroll
+        for (int d = 0; d < SPH_NROWS; d++) {
+            const float vx_row = vx, vy_row = vy;
+            float tmax = 0.0f;
+            int j = R.b[d];
+            const int je = R.e[d];
+#if SPH_PACKED
+            f32x2 vv = pk2(vx, vy);
+#pragma unroll kPackedUnroll
+            for (; j + 1 < je; j += 2) {
+                const f32x2 d0 = sub2(ld2(pos + j), pp), d1 = sub2(ld2(pos + j + 1), pp);
+                const float2 s0 = unpk2(mul2(d0, d0)), s1 = unpk2(mul2(d1, d1));
+                const float r20 = __fadd_rn(s0.x, s0.y), r21 = __fadd_rn(s1.x, s1.y);
+                const float2 m0 = unpk2(mul2(sub2(v0p, ld2(vel + j)), d0)), m1 = unpk2(mul2(sub2(v0p, ld2(vel + j + 1)), d1));
+                const f32x2 rs = pk2(rsqrt_approx(r20), rsqrt_approx(r21));
+                const f32x2 u = mul2(pk2(__fadd_rn(m0.x, m0.y), __fadd_rn(m1.x, m1.y)), rs);
+                const float2 uu = unpk2(u);
+                const bool hit0 = (r20 <= h2) & (uu.x > 0.0f), hit1 = (r21 <= h2) & (uu.y > 0.0f);
+                const f32x2 nw = fma2(mul2(pk2(r20, r21), rs), hh2, nhdt2);          // -(1 - r/h) dt/2
+                f32x2 t = mul2(mul2(mul2(u, fma2(beta2, u, sigma2)), nw), rs);
+                if (STAB) {
+                    const float g0 = fmaxf(gci, gamma * coupling[j]), g1 = fmaxf(gci, gamma * coupling[j + 1]);
+                    t = mul2(t, pk2(g0 > 1.0f ? rcp_approx(g0) : 1.0f, g1 > 1.0f ? rcp_approx(g1) : 1.0f));
+                }
+                const float2 tt = unpk2(t);
+                const float t0 = hit0 ? tt.x : 0.0f, t1 = hit1 ? tt.y : 0.0f;
+                tmax = max_nan(tmax, fabsf(t0));
+                tmax = max_nan(tmax, fabsf(t1));
+                vv = fma2(pk2(t0, t0), d0, vv);
+                vv = fma2(pk2(t1, t1), d1, vv);
+            }
+            { const float2 v2 = unpk2(vv); vx = v2.x; vy = v2.y; }
+#pragma unroll 1
+            for (; j < je; j++) {      // at most one left over
+#else
+#pragma unroll kGatherUnroll
+            for (; j < je; j++) {
+#endif
+                const float2 q = pos[j];
+                const float dx = q.x - p.x, dy = q.y - p.y;
+                const float r2 = dist2(dx, dy);
+                const bool in = r2 <= h2;
+                const float2 vq = vel[j];
+                const float rs = rsqrt_approx(r2);
+                const float u_in = ((v0.x - vq.x) * dx + (v0.y - vq.y) * dy) * rs;
+                const bool hit = in && u_in > 0.0f;
+                const float nw = fmaf(r2 * rs, hdt_over_h, -hdt);
+                float t = stab_scale<STAB>(u_in * fmaf(P.beta, u_in, P.sigma) * nw * rs, gci, gamma, coupling, j);
+                t = hit ? t : 0.0f;
+                tmax = max_nan(tmax, fabsf(t));
+                vx = fmaf(t, dx, vx);
+                vy = fmaf(t, dy, vy);
+            }
+            if (!(tmax <= tlim)) {      // the clamp may bind in this row (or something was not finite): exact body
+                vx = vx_row; vy = vy_row;
+#pragma unroll 1
+                for (int k = R.b[d]; k < je; k++) cand_exact(k);
+            }
+        }
+#else
 #if SPH_PACKED
         const f32x2 pp = pk2(p.x, p.y), v0p = pk2(v0.x, v0.y);
         const f32x2 nh2 = pk2(-h_recip, -h_recip), one2 = pk2(1.0f, 1.0f), hdt2 = pk2(hdt, hdt);
@@ -317,6 +411,7 @@ k_advect(const DevParams *__restrict__ Pp, int *__restrict__ counters,
                 vy -= hit ? iy : 0.0f;
             }
         }
+#endif
         float2 np = make_float2(p.x + vx * dt, p.y + vy * dt);          // fluid.c:517-518
         np = boundary(np, P);
         pos_pred[i] = np;
@@ -363,6 +458,7 @@ k_advect(const DevParams *__restrict__ Pp, int *__restrict__ counters,
         }
         bin_position(i, np, extra, P, cnt, t_key, t_slot, counters);
     }
+    pdl_done();
 }
 
 // -------------------------------------------------------------------------------------------
@@ -437,6 +533,7 @@ k_coupling(const DevParams *__restrict__ Pp, const int *__restrict__ counters,
         }
         coupling[i] = c;
     }
+    pdl_done();
 }
 
 // -------------------------------------------------------------------------------------------
@@ -529,6 +626,7 @@ k_unpack(const DevParams *__restrict__ Pp, int *__restrict__ counters, int which
         // controls.c:405-426, still receives its neighbour's edge particles): same flag as an emigrant
         bin_position(idx, p, (u & SPH_HALO_BIT) ? SPH_KEY_EMIG : 0, P, cnt, t_key, t_slot, counters);
     }
+    pdl_done();
 }
 
 // -------------------------------------------------------------------------------------------
@@ -594,6 +692,7 @@ k_scan_totals(const DevParams *__restrict__ Pp, int *__restrict__ counters, cons
         }
         __syncthreads();
     }
+    pdl_done();
 }
 
 __global__ void __launch_bounds__(SPH_THREADS)
@@ -683,6 +782,7 @@ k_scan_apply(DevParams *__restrict__ Pp, int *__restrict__ counters, int *__rest
         }
         __syncthreads();
     }
+    pdl_done();
 }
 
 // -------------------------------------------------------------------------------------------
@@ -706,6 +806,7 @@ k_scatter(const int *__restrict__ counters, const int *__restrict__ cell_start,
         ord_src[d] = s;
         ord_key[d] = key & SPH_KEY_MASK;
     }
+    pdl_done();
 }
 
 // -------------------------------------------------------------------------------------------
@@ -737,6 +838,7 @@ k_reorder(const DevParams *__restrict__ Pp, int *__restrict__ counters, const in
         dst_uid[dst] = u;
         locals += !(u & SPH_HALO_BIT);
     }
+    pdl_done();
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) locals += __shfl_xor_sync(0xffffffffu, locals, o);
     if ((threadIdx.x & 31) == 0 && locals) atomicAdd(&counters[CN_NLOCAL], locals);
@@ -835,6 +937,7 @@ k_density(const DevParams *__restrict__ Pp, int *__restrict__ counters,
         if (nn > 400) atomicAdd(&counters[CN_NEIGH_OVER], 1);
         cost += SPH_COST_BASE + nn;
     }
+    pdl_done();
     // work estimate of this slab (one atomic per warp per launch): input of the cost-based edge policy
     cost = __reduce_add_sync(0xffffffffu, cost);
     if ((threadIdx.x & 31) == 0 && cost) atomicAdd(&counters[CN_COST], cost);
@@ -1018,6 +1121,7 @@ k_relax(const DevParams *__restrict__ Pp, int *__restrict__ counters,
         }
         bin_position(i, np, 0, P, cnt, t_key, t_slot, counters);
     }
+    pdl_done();
 }
 
 // -------------------------------------------------------------------------------------------

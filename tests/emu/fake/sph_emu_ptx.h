@@ -4,6 +4,7 @@
 // GCC atomics in place of the system-scope acquire / release.
 #pragma once
 static inline float rcp_approx(float x) { return 1.0f / x; }
+static inline float max_nan(float a, float b) { return (a != a || b != b) ? NAN : (a > b ? a : b); }
 struct f32x2 { float lo, hi; };
 static inline f32x2 pk2(float lo, float hi) { return f32x2{lo, hi}; }
 static inline float2 unpk2(f32x2 v) { return float2{v.lo, v.hi}; }
@@ -17,3 +18,4 @@ static inline void st_release_sys(int *p, int v) { __atomic_store_n(p, v, __ATOM
 static inline float rsqrt_approx(float x) { return 1.0f / sqrtf(x); }
 static inline float sqrt_approx(float x) { return sqrtf(x); }
 static inline void pdl_enter() {}   // launches of the emulator are already serialised
+static inline void pdl_done() {}

@@ -44,3 +44,45 @@ def test_packed_fp32_variant_is_bit_identical_in_the_emulator(built_lib, monkeyp
         assert np.array_equal(d0[f].view("u4"), d1[f].view("u4")), ("density stage", f)
     for f in ("x", "y", "v_x", "v_y"):
         assert np.array_equal(a0[f].view("u4"), a1[f].view("u4")), ("after the step", f)
+
+
+@pytest.mark.parametrize("packed", [False, True])
+def test_trimmed_advect_loop_agrees_with_the_gather_oracle_and_redoes_rows_where_the_clamp_binds(built_lib, monkeypatch, packed):
+    """SPH_TRIM=1: k_advect applies a pair's half impulse without the per-component clamp and redoes, with the exact
+    body, only the rows in which the clamp COULD bind (max |t| h > 2.5).  (1) Rounding-level agreement with the gather
+    oracle on settled fluids (no row is redone).  (2) A violent goo state -- every second particle thrown at 5 units/s
+    against its neighbours, so that the clamp binds in many rows -- must still agree with the oracle's clamped
+    impulses: without the redo the velocities would be off by whole units."""
+    import parity_checks as pc
+    from test_gpu_parity import Cuda, make_oracle
+    defs = ("SPH_TRIM=1",) + (("SPH_PACKED=1", "SPH_PACKED_RELAX=1") if packed else ())
+    lib = build_emu(defines=defs, name="libsph_emu_trim%d.so" % packed)
+    monkeypatch.setattr(sph_b200, "_lib", sph_b200._bind(C.CDLL(lib)))
+    mk = lambda *a: Cuda(*a)
+    pc.check_tight_vs_gather_oracle(mk, make_oracle, "default1508", 400, steps=3)
+    pc.check_tight_vs_gather_oracle(mk, make_oracle, "goo_rect1508", 300, steps=2)
+    # (2)
+    z, t, tank_w, tank_h, h, _ = load_golden("goo_rect1508")
+    st = z["w300_state"].copy()
+    rng = np.random.default_rng(5)
+    st["v_x"] = np.where(np.arange(len(st)) % 2 == 0, 5.0, -5.0).astype("f4") * rng.uniform(0.5, 1.0, len(st)).astype("f4")
+    st["v_y"] = rng.uniform(-5, 5, len(st)).astype("f4")
+    b = mk(tank_w, tank_h, h, len(st) + 64); o = make_oracle(tank_w, tank_h, h, len(st) + 64)
+    for s in (b, o):
+        s.set_params(t); s.upload(st)
+    for s in (b, o):
+        s.advect(); s.sort()
+    a, ua = b.download(); r, ur = o.download()
+    assert np.array_equal(ua, ur)
+    # predicted positions = x + v dt: a unit of velocity error is dt = 8.3e-3 of position
+    assert np.abs(a["x"] - r["x"]).max() <= 1e-5 and np.abs(a["y"] - r["y"]).max() <= 1e-5
+    # the clamp did bind for some pair of this state (brute force over the pairs; fluid.c:451-459 halved)
+    x, y, vx, vy = (st[f].astype("f8") for f in ("x", "y", "v_x", "v_y"))
+    dx = x[None, :] - x[:, None]; dy = y[None, :] - y[:, None]
+    r = np.hypot(dx, dy); np.fill_diagonal(r, np.inf)
+    near = r <= h
+    with np.errstate(divide="ignore", invalid="ignore"):
+        u = ((vx[:, None] - vx[None, :]) * dx + (vy[:, None] - vy[None, :]) * dy) / r
+        imp = 0.5 * t.time_step * (1 - r / h) * (t.sigma * u + t.beta * u * u)
+    binds = near & (u > 0) & ((np.abs(imp * dx / r) > 2.5) | (np.abs(imp * dy / r) > 2.5))
+    assert binds.sum() > 20, binds.sum()
