@@ -218,6 +218,18 @@ int sph_refresh_ghosts(sph_ctx *ctx);
  * one-exchange build variant (-DSPH_ONE_EXCHANGE=1), whose ghosts are relaxed redundantly and which needs
  * halo_width >= 3 (4 with the stabilised viscosity gather); the driver then skips the which = 1 transfer. */
 int sph_exchanges_per_step(void);
+/* Exchange period (one-exchange build): neighbours meet every `period` steps instead of every step; in between a
+ * slab advances its ghosts itself, redundantly and bit for bit as their owner does.  Every pair pass invalidates
+ * one h of the layer from the outside, so a period of E steps needs halo_width >= 3.5 * E (4.5 * E while the
+ * stabilised viscosity gather is engaged); with a narrower layer the library meets as often as the layer allows.
+ * A queued parameter block (sph_queue_params) always makes its own step an exchange step -- it lands exactly where
+ * the exchange is, fluid.c:293-310 -- and so does anything set outside the queue.  Migration happens at exchange
+ * steps only; between them a particle that crossed an edge stays with its owner.  The result is still the
+ * single-slab result bit for bit.  Replaces 2 meetings per step of the reference (fluid.c:310-348) by 1 / E. */
+int sph_set_exchange_period(sph_ctx *ctx, int period);
+/* 1 if the step in progress (between sph_advect and the end of the step) is an exchange step, or, at a step
+ * boundary, if the coming step will be one: a host-side transport moves the which = 0 buffers only then. */
+int sph_exchange_due(sph_ctx *ctx);
 /* Mark a neighbour as absent for the coming sort (edge slabs): its recv buffer is ignored. */
 int sph_set_neighbors(sph_ctx *ctx, int has_left, int has_right);
 

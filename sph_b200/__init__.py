@@ -62,7 +62,7 @@ C_ABI_SYMBOLS = (
     "sph_set_neighbors", "sph_get_cells", "sph_get_pairs", "sph_get_forward_counts",
     "sph_pack_coords", "sph_launch_count", "sph_run_frame", "sph_p2p_local_handle", "sph_p2p_connect", "sph_copy_n_local", "sph_copy_load", "sph_init_lattice",
     "sph_set_viscosity_stabilisation", "sph_pack_coords_async", "sph_coords_wait", "sph_run_frame_async",
-    "sph_exchanges_per_step", "sph_refresh_ghosts", "sph_exchange_via_host",
+    "sph_exchanges_per_step", "sph_refresh_ghosts", "sph_exchange_via_host", "sph_set_exchange_period", "sph_exchange_due",
 )
 
 _lib = None
@@ -116,6 +116,8 @@ def _bind(L):
     L.sph_p2p_local_handle.argtypes = [C.c_void_p, C.c_void_p]
     L.sph_p2p_connect.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.sph_exchange_buffers.argtypes = [C.c_void_p, C.c_int] + [C.POINTER(C.c_void_p)] * 4 + [C.POINTER(C.c_size_t)]
+    L.sph_set_exchange_period.argtypes = [C.c_void_p, C.c_int]
+    L.sph_exchange_due.argtypes = [C.c_void_p]
     return L
 
 
@@ -229,6 +231,14 @@ class Context:
     @property
     def exchanges_per_step(self):
         return int(self.L.sph_exchanges_per_step())
+
+    def set_exchange_period(self, period):
+        """One-exchange build: neighbours meet every `period` steps (sph_set_exchange_period)."""
+        self._ck(self.L.sph_set_exchange_period(self.h, int(period)), "sph_set_exchange_period")
+
+    @property
+    def exchange_due(self):
+        return bool(self.L.sph_exchange_due(self.h))
 
     def exchange_via_host(self, which, sendrecv):
         """sph_exchange_via_host with a Python callable sendrecv(send_bytes_or_None, to_side, recv_nbytes, from_side)

@@ -94,8 +94,14 @@ struct sph_ctx {
     int grid;                        // per-particle gather kernels
     int sort_grid;                   // the sort's streaming kernels
     int size_x, size_y;
-    cudaGraphExec_t graph[2];        // whole step, [1] = with the stabilised viscosity gather
-    bool graph_ready[2];
+    cudaGraphExec_t graph[4];        // whole step: index = stabilised viscosity gather + 2 * exchange step
+    bool graph_ready[4];
+    // exchange period (one-exchange build, sph_set_exchange_period): neighbours meet every `xperiod` steps
+    int launch_per_graph[4];         // kernel launches inside each captured step
+    int xperiod;                     // requested
+    int since_x;                     // steps since the last exchange step
+    bool force_x;                    // the coming step must exchange (fresh upload, parameters set outside the queue, ...)
+    bool cur_x;                      // the step in progress is an exchange step
     long long launches;
     long long steps;
     char err[256];
@@ -270,6 +276,7 @@ extern "C" int sph_create(const sph_config *cfg, sph_ctx **out)
     if (rc) return rc;
     CK(cudaDeviceSynchronize());       // the memsets above ran on the legacy stream, ctx->stream does not wait for it
     ctx->stage = ST_READY;
+    ctx->xperiod = 1; ctx->since_x = 0; ctx->force_x = true; ctx->cur_x = true;
     return SPH_OK;
 }
 
@@ -277,7 +284,7 @@ extern "C" void sph_destroy(sph_ctx *ctx)
 {
     if (!ctx) return;
     cudaStreamSynchronize(ctx->stream);
-    for (int m = 0; m < 2; m++) if (ctx->graph_ready[m]) cudaGraphExecDestroy(ctx->graph[m]);
+    for (int m = 0; m < 4; m++) if (ctx->graph_ready[m]) cudaGraphExecDestroy(ctx->graph[m]);
     cudaFree(ctx->coupling); cudaFree(ctx->dopt);
 #if SPH_RELAX_PD4
     cudaFree(ctx->pd);
@@ -312,13 +319,19 @@ extern "C" int sph_synchronize(sph_ctx *ctx)
     return SPH_OK;
 }
 
-extern "C" int sph_set_params(sph_ctx *ctx, const sph_tunable *t)
+static int apply_params(sph_ctx *ctx, const sph_tunable *t)
 {
-    if (!ctx || !t) return SPH_ERR_ARG;
     ctx->tun = *t;
     fill_phys(ctx->hp, *t);
     fill_edges(ctx, t->node_start_x, t->node_end_x);
     return push_params(ctx);
+}
+
+extern "C" int sph_set_params(sph_ctx *ctx, const sph_tunable *t)
+{
+    if (!ctx || !t) return SPH_ERR_ARG;
+    ctx->force_x = true;      // physics or edges changed outside the queue: the ghosts' validity budget starts over
+    return apply_params(ctx, t);
 }
 
 extern "C" int sph_queue_params(sph_ctx *ctx, const sph_tunable *t)
@@ -334,6 +347,7 @@ extern "C" int sph_set_viscosity_stabilisation(sph_ctx *ctx, float gamma, float 
     if (!ctx || !(gamma >= 0.0f) || !(min_dt_sigma >= 0.0f)) return SPH_ERR_ARG;
     ctx->visc_gamma = gamma;
     ctx->visc_min_dt_sigma = min_dt_sigma;
+    ctx->force_x = true;
     DevOptions o;
     o.visc_gamma = gamma;
     CK(cudaMemcpyAsync(ctx->dopt, &o, sizeof o, cudaMemcpyHostToDevice, ctx->stream));   // pageable: staged before returning
@@ -344,6 +358,7 @@ extern "C" int sph_set_edges(sph_ctx *ctx, float s, float e)
 {
     if (!ctx) return SPH_ERR_ARG;
     ctx->tun.node_start_x = s; ctx->tun.node_end_x = e;
+    ctx->force_x = true;
     fill_edges(ctx, s, e);
     return push_params(ctx);
 }
@@ -352,6 +367,7 @@ extern "C" int sph_set_neighbors(sph_ctx *ctx, int has_left, int has_right)
 {
     if (!ctx) return SPH_ERR_ARG;
     ctx->hp.has_left = has_left; ctx->hp.has_right = has_right;
+    ctx->force_x = true;
     return push_params(ctx);
 }
 
@@ -374,6 +390,7 @@ extern "C" int sph_exchange_via_host(sph_ctx *ctx, int which, sph_sendrecv_fn fn
 {
     if (!ctx || !fn || (which != 0 && which != 1)) return SPH_ERR_ARG;
     if (ctx->cfg.nranks <= 1) return SPH_OK;
+    if (which == 0 && ctx->stage == ST_ADVECTED && !ctx->cur_x) return SPH_OK;      // not an exchange step (sph_set_exchange_period)
     const size_t full = msg_bytes_full(ctx->cfg.msg_capacity);
     const size_t nb = which == 0 ? full : msg_bytes_halo1(ctx->cfg.msg_capacity);
     if (!ctx->stage_host) CK(cudaMallocHost(&ctx->stage_host, 4 * full));
@@ -393,6 +410,7 @@ extern "C" int sph_exchange_via_host(sph_ctx *ctx, int which, sph_sendrecv_fn fn
 // how often neighbours meet per step in this build: 2 (after the prediction and after the relaxation), or 1 in the
 // one-exchange build, where a multi-rank driver skips the second transfer
 extern "C" int sph_exchanges_per_step(void) { return SPH_ONE_EXCHANGE ? 1 : 2; }
+
 
 // ------------------------------------------------------------------------------------------
 // peer-memory exchange: neighbours map each other's exchange block (cudaIpc) and the pack code in
@@ -420,7 +438,8 @@ extern "C" int sph_p2p_connect(sph_ctx *ctx, const void *left_handle64, const vo
         ctx->hp.remote_base[s] = (unsigned long long)ctx->peer[s];
     }
     ctx->hp.p2p = 1;
-    for (int m = 0; m < 2; m++) if (ctx->graph_ready[m]) { cudaGraphExecDestroy(ctx->graph[m]); ctx->graph_ready[m] = false; }
+    for (int m = 0; m < 4; m++) if (ctx->graph_ready[m]) { cudaGraphExecDestroy(ctx->graph[m]); ctx->graph_ready[m] = false; }
+    ctx->force_x = true;
     return push_params(ctx);
 }
 
@@ -443,7 +462,7 @@ static int launch_sort(sph_ctx *ctx, int which, bool with_unpack = true, bool re
     uint32_t *du = which == 0 ? ctx->U[1] : ctx->U[0];
     // (one-exchange build: nothing arrives after the relaxation, the ghosts were relaxed here)
     // (refresh: sph_refresh_ghosts always brings its ghosts in the which = 1 format)
-    if (ctx->cfg.nranks > 1 && with_unpack && (refresh || !(SPH_ONE_EXCHANGE && which == 1))) {
+    if (ctx->cfg.nranks > 1 && with_unpack && (refresh || (!(SPH_ONE_EXCHANGE && which == 1) && ctx->cur_x))) {
         SPH_LAUNCH(k_unpack, ctx->unpack_grid, ctx->stream)(ctx->dp, ctx->counters, which, ctx->send[0], ctx->send[1],
                                                              ctx->recv[0], ctx->recv[1],
                                                              sp, sq, su, ctx->cnt, ctx->t_key, ctx->t_slot);
@@ -455,7 +474,7 @@ static int launch_sort(sph_ctx *ctx, int which, bool with_unpack = true, bool re
     SPH_LAUNCH(k_scan_apply, sgrid, ctx->stream)(ctx->dp, ctx->counters, ctx->cnt, ctx->cell_start, ctx->tile_total,
                                                          ctx->cfg.nranks > 1 ? ctx->send[0] : nullptr,
                                                          ctx->cfg.nranks > 1 ? ctx->send[1] : nullptr,
-                                                         (which == 1 && with_unpack) ? 1 : 0);
+                                                         (which == 1 && with_unpack && (refresh || ctx->cur_x)) ? 1 : 0);
     SPH_LAUNCH(k_scatter, ctx->sort_grid, ctx->stream)(ctx->counters, ctx->cell_start, ctx->t_key, ctx->t_slot, su,
                                                           ctx->ord_uid, ctx->ord_src, ctx->ord_key);
     SPH_LAUNCH(k_reorder, ctx->sort_grid, ctx->stream)(ctx->dp, ctx->counters, ctx->cell_start, ctx->ord_key,
@@ -474,20 +493,87 @@ static bool stabilised(const sph_ctx *ctx)
     return ctx->visc_gamma > 0.0f && ctx->hp.dt * ctx->hp.sigma >= ctx->visc_min_dt_sigma;
 }
 
+// ---- exchange period (one-exchange build) ------------------------------------------------------------------
+// Between two exchanges a slab advances its ghosts itself, redundantly: a ghost comes out exactly as on its owner
+// as long as everything within reach of it was itself exact, and every pair pass eats one h of the layer from the
+// outside (k_advect, k_density, k_relax: 3 h per step; 4 h with the stabilised viscosity gather, whose coupling
+// sums are one more pair pass), plus half an h per step for the motion of the particles themselves.  So a layer
+// of `unit * E` h carries E steps, unit = 3.5 (4.5 stabilised): E = 1 is the one-exchange build of round 1.
+static float layer_unit(const sph_ctx *ctx, float dt, float sigma)
+{
+    return (ctx->visc_gamma > 0.0f && dt * sigma >= ctx->visc_min_dt_sigma) ? 4.5f : 3.5f;
+}
+
+// the period the ghost layer of this context can carry with the parameter block that will be in force
+static int effective_period(const sph_ctx *ctx, const sph_tunable *coming)
+{
+    const float unit = layer_unit(ctx, coming ? coming->time_step : ctx->hp.dt, coming ? coming->sigma : ctx->hp.sigma);
+    const int fits = (int)floorf(ctx->cfg.halo_width / unit + 1e-3f);
+    return std::max(1, std::min(ctx->xperiod, fits));
+}
+
+// Decide whether the step that starts now is an exchange step, and set the width of the layer it sends.
+// Every rank takes the same decision from the same call sequence (the reference's parameter scatter is collective).
+static int begin_step(sph_ctx *ctx)
+{
+    if (ctx->cfg.nranks <= 1) { ctx->cur_x = false; return SPH_OK; }
+    if (!SPH_ONE_EXCHANGE) { ctx->cur_x = true; return SPH_OK; }
+    const sph_tunable *coming = ctx->have_queued ? &ctx->queued : nullptr;
+    const int period = effective_period(ctx, coming);
+    // a queued block lands between this step's prediction and its exchange (fluid.c:279-310): meeting in that same
+    // step means the whole coming period runs under one block, whose viscosity decides the layer it needs
+    ctx->cur_x = ctx->force_x || ctx->have_queued || ctx->since_x + 1 >= period;
+    if (ctx->cur_x) {
+        const float unit = layer_unit(ctx, coming ? coming->time_step : ctx->hp.dt, coming ? coming->sigma : ctx->hp.sigma);
+        // period 1 keeps the layer the caller configured (round 1's one-exchange build); longer periods send what they need
+        const float w = (ctx->xperiod <= 1 ? ctx->cfg.halo_width : unit * (float)period) * ctx->cfg.h;
+        if (w != ctx->hp.halo_w) { ctx->hp.halo_w = w; int rc = push_params(ctx); if (rc) return rc; }
+    }
+    return SPH_OK;
+}
+
+static void end_step(sph_ctx *ctx)
+{
+    if (ctx->cur_x) { ctx->since_x = 0; ctx->force_x = false; }
+    else ctx->since_x++;
+}
+
+// One-exchange build only: neighbours meet every `period` steps instead of every step (see begin_step above).
+extern "C" int sph_set_exchange_period(sph_ctx *ctx, int period)
+{
+    if (!ctx || period < 1) return SPH_ERR_ARG;
+    if (period > 1 && !SPH_ONE_EXCHANGE)
+        return fail(ctx, SPH_ERR_STATE, "sph_set_exchange_period: this build exchanges twice per step (build with -DSPH_ONE_EXCHANGE=1)");
+    ctx->xperiod = period;
+    ctx->force_x = true;
+    return SPH_OK;
+}
+
+// 1 if the step in progress (after sph_advect) exchanges -- or, at a step boundary, if the coming step would
+extern "C" int sph_exchange_due(sph_ctx *ctx)
+{
+    if (!ctx || ctx->cfg.nranks <= 1) return 0;
+    if (ctx->stage != ST_READY) return ctx->cur_x ? 1 : 0;
+    if (!SPH_ONE_EXCHANGE) return 1;
+    return (ctx->force_x || ctx->have_queued ||
+            ctx->since_x + 1 >= effective_period(ctx, ctx->have_queued ? &ctx->queued : nullptr)) ? 1 : 0;
+}
+
+
 static int launch_advect(sph_ctx *ctx)
 {
     if (stabilised(ctx)) {
         SPH_LAUNCH(k_coupling, ctx->grid, ctx->stream)(ctx->dp, ctx->counters, ctx->P[0], ctx->Q[0], ctx->cell_start, ctx->coupling);
         SPH_LAUNCH(k_advect<true>, ctx->grid, ctx->stream)(ctx->dp, ctx->counters, ctx->P[0], ctx->Q[0], ctx->U[0],
                                                             ctx->cell_start, ctx->P[1], ctx->cnt, ctx->t_key, ctx->t_slot,
-                                                            ctx->send[0], ctx->send[1], ctx->coupling, ctx->dopt);
+                                                            ctx->send[0], ctx->send[1], ctx->coupling, ctx->dopt, ctx->cur_x ? 1 : 0);
         ctx->launches += 2;
         CK(cudaGetLastError());
         return SPH_OK;
     }
     SPH_LAUNCH(k_advect<false>, ctx->grid, ctx->stream)(ctx->dp, ctx->counters, ctx->P[0], ctx->Q[0], ctx->U[0],
                                                          ctx->cell_start, ctx->P[1], ctx->cnt, ctx->t_key, ctx->t_slot,
-                                                         ctx->send[0], ctx->send[1], nullptr, nullptr);
+                                                         ctx->send[0], ctx->send[1], nullptr, nullptr, ctx->cur_x ? 1 : 0);
     ctx->launches++;
     CK(cudaGetLastError());
     return SPH_OK;
@@ -538,6 +624,7 @@ extern "C" int sph_advect(sph_ctx *ctx)
     if (!ctx) return SPH_ERR_ARG;
     if (ctx->stage != ST_READY) return fail(ctx, SPH_ERR_STATE, "sph_advect: state is not at a step boundary");
     int rc;
+    if ((rc = begin_step(ctx))) return rc;
     if (ctx->have_queued) {
         // the scatter from the render rank lands between prediction and migration (fluid.c:279-310):
         // new slab edges first (only the classification at the end of the kernel reads them) ...
@@ -549,7 +636,7 @@ extern "C" int sph_advect(sph_ctx *ctx)
     if (ctx->have_queued) {
         // ... then everything else, for the stages after the prediction
         ctx->have_queued = false;
-        if ((rc = sph_set_params(ctx, &ctx->queued))) return rc;
+        if ((rc = apply_params(ctx, &ctx->queued))) return rc;
     }
     ctx->stage = ST_ADVECTED;
     return SPH_OK;
@@ -560,7 +647,7 @@ extern "C" int sph_sort(sph_ctx *ctx)
     if (!ctx) return SPH_ERR_ARG;
     int rc;
     if (ctx->stage == ST_ADVECTED) { if ((rc = launch_sort(ctx, 0))) return rc; ctx->stage = ST_SORTED1; }
-    else if (ctx->stage == ST_RELAXED) { if ((rc = launch_sort(ctx, 1))) return rc; ctx->stage = ST_READY; ctx->steps++; }
+    else if (ctx->stage == ST_RELAXED) { if ((rc = launch_sort(ctx, 1))) return rc; ctx->stage = ST_READY; ctx->steps++; end_step(ctx); }
     else if (ctx->stage == ST_REQUEUED) { if ((rc = launch_sort(ctx, 1, true, true))) return rc; ctx->stage = ST_READY; }
     else return fail(ctx, SPH_ERR_STATE, "sph_sort: nothing to sort");
     return SPH_OK;
@@ -624,14 +711,17 @@ extern "C" int sph_step(sph_ctx *ctx, int n)
                 (rc = sph_relax(ctx)) || (rc = sph_sort(ctx))) return rc;
             continue;
         }
+        if ((rc = begin_step(ctx))) return rc;
         if ((rc = check_layer(ctx))) return rc;
-        const int m = stabilised(ctx) ? 1 : 0;           // one captured step per variant of the viscosity gather
+        // one captured step per variant: viscosity gather (plain / stabilised) x (exchange step or not)
+        const int m = (stabilised(ctx) ? 1 : 0) + (ctx->cur_x ? 2 : 0);
         if (!ctx->graph_ready[m]) {
             cudaGraph_t g;
             long long before = ctx->launches;
             CK(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
             rc = launch_step(ctx);
             cudaError_t e = cudaStreamEndCapture(ctx->stream, &g);
+            ctx->launch_per_graph[m] = (int)(ctx->launches - before);
             ctx->launches = before;
             if (rc) return rc;
             CK(e);
@@ -640,8 +730,9 @@ extern "C" int sph_step(sph_ctx *ctx, int n)
             ctx->graph_ready[m] = true;
         }
         CK(cudaGraphLaunch(ctx->graph[m], ctx->stream));
-        ctx->launches += (ctx->cfg.nranks > 1 ? (SPH_ONE_EXCHANGE ? 12 : 13) : 11) + m;
+        ctx->launches += ctx->launch_per_graph[m];
         ctx->steps++;
+        end_step(ctx);
     }
     return SPH_OK;
 }
@@ -668,6 +759,7 @@ static int ingest(sph_ctx *ctx, int n)
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->stage = ST_READY;
     ctx->n_uploaded = n;
+    ctx->force_x = true;          // a fresh upload has no ghosts
     return SPH_OK;
 }
 

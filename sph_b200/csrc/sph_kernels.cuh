@@ -232,8 +232,11 @@ k_advect(const DevParams *__restrict__ Pp, int *__restrict__ counters,
          const float2 *__restrict__ pos, const float2 *__restrict__ vel, const uint32_t *__restrict__ uid,
          const int *__restrict__ cell_start,
          float2 *__restrict__ pos_pred, int *__restrict__ cnt, int *__restrict__ t_key, int *__restrict__ t_slot,
-         unsigned char *send_l, unsigned char *send_r, const float *__restrict__ coupling, const DevOptions *__restrict__ Op)
+         unsigned char *send_l, unsigned char *send_r, const float *__restrict__ coupling, const DevOptions *__restrict__ Op,
+         int xstep)
 {
+    // xstep: neighbours exchange after this prediction (always, except in the one-exchange build with an exchange
+    // period > 1, where between exchanges the ghosts are advanced here like everything else; see sph_set_exchange_period)
     pdl_enter();
     const DevParams P = *Pp;
     const float gamma = STAB ? Op->visc_gamma : 0.0f;
@@ -247,7 +250,13 @@ k_advect(const DevParams *__restrict__ Pp, int *__restrict__ counters,
 
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const uint32_t u = uid[i];
+#if SPH_ONE_EXCHANGE
+        const bool ghost = (u & SPH_HALO_BIT) != 0;
+        if (ghost && xstep) { t_key[i] = SPH_KEY_DROP; continue; }      // ghosts are replaced at every exchange
+#else
+        const bool ghost = false;
         if (u & SPH_HALO_BIT) { t_key[i] = SPH_KEY_DROP; continue; }   // ghosts are replaced every exchange
+#endif
         const float2 p = pos[i];
         const float2 v0 = vel[i];
         float vx = v0.x, vy = v0.y + gdt;                               // apply_gravity
@@ -416,8 +425,8 @@ k_advect(const DevParams *__restrict__ Pp, int *__restrict__ counters,
         np = boundary(np, P);
         pos_pred[i] = np;
 
-        int extra = 0;
-        if (P.nranks > 1) {
+        int extra = ghost ? SPH_KEY_EMIG : 0;                           // a ghost advanced between exchanges stays a ghost
+        if (P.nranks > 1 && xstep && !ghost) {
             // identify_oob_particles: strict < start / > end (fluid.c:494-497)
             unsigned char *dst = nullptr;
             if (np.x < P.edge_start && P.has_left) dst = send_l;

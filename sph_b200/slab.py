@@ -54,7 +54,7 @@ def keep_slabs_wider_than(old, new, min_width, nactive):
 class SlabRunner:
     def __init__(self, prob, tunable, rank, world, stream=None, capacity_factor=2.0, backend=None,
                  msg_capacity=None, steps_per_frame=4, balance=True, group=None, transport="p2p",
-                 async_counts=True, balance_policy="count", cost_band_divisor=40.0, halo_width=None):
+                 async_counts=True, balance_policy="count", cost_band_divisor=40.0, halo_width=None, exchange_period=1):
         import torch
         import torch.distributed as dist
         self.torch, self.dist = torch, dist
@@ -72,8 +72,12 @@ class SlabRunner:
         self.t.node_start_x, self.t.node_end_x = self.edges[rank]
         n_slab = max(nc for (_, nc, _, _) in prob["slabs"]) * int(np.floor(np.float32(prob["tank_h"]) / np.float32(prob["spacing"])))
         rows = int(np.floor(np.float32(prob["tank_h"]) / np.float32(prob["spacing"])))
-        # ghost layer 2h wide = ~4 lattice columns at rest; settle-time compression and migrants: x6
-        self.msg_capacity = int(msg_capacity or max(4096, 6 * 5 * rows))
+        self.exchange_period = int(exchange_period)
+        if self.exchange_period > 1 and not halo_width:
+            # 3.5 h of ghost layer per step between exchanges, 4.5 h while the stabilised viscosity gather is engaged
+            halo_width = (4.5 if tunable.time_step * tunable.sigma >= 0.5 else 3.5) * self.exchange_period
+        # ghost layer 2h wide = ~4 lattice columns at rest (2 per h); settle-time compression and migrants: x6
+        self.msg_capacity = int(msg_capacity or max(4096, 6 * (int(2 * (halo_width or 2.0)) + 1) * rows))
         self.capacity = int(capacity_factor * n_slab) + 4 * self.msg_capacity
         if backend is None:
             import sph_b200
@@ -90,6 +94,9 @@ class SlabRunner:
             self.cuda = False
         self.ctx.set_params(self.t)
         self.exchanges = int(getattr(self.ctx, "exchanges_per_step", 2))     # 1: one-exchange build of the library
+        if self.exchange_period > 1:
+            # neighbours meet every `exchange_period` steps; needs the one-exchange build and a layer of 3.5 h per step
+            self.ctx.set_exchange_period(self.exchange_period)
         self.has_left, self.has_right = rank > 0, rank < world - 1
         # "p2p": neighbours map each other's exchange block (cudaIpc) and the kernels store messages
         # straight into it over NVLink; "collective": torch.distributed send/recv moves the buffers
@@ -116,6 +123,7 @@ class SlabRunner:
 
     def exchange(self, which):
         dist = self.dist
+        self.n_exchanges = getattr(self, "n_exchanges", 0) + 1
         send_l, recv_l, send_r, recv_r = self._buffers(which)
         ops = []
         if self.has_right:
@@ -242,7 +250,8 @@ class SlabRunner:
             self.sub_step = (self.sub_step + 1) % self.steps_per_frame
             return
         c.advect()
-        self.exchange(0)
+        if getattr(c, "exchange_due", True):           # exchange period > 1: nothing moves between exchange steps
+            self.exchange(0)
         c.sort()
         c.density()
         c.relax()

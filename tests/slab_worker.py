@@ -44,7 +44,9 @@ def main():
             g.set_viscosity_stabilisation(0.5)      # the proposal of DESIGN.md 5b (oracle only)
         return g
 
-    sim = SlabRunner(prob, t, rank, world, backend=backend, balance=bool(balance), balance_policy=policy)
+    sim = SlabRunner(prob, t, rank, world, backend=backend, balance=bool(balance), balance_policy=policy,
+                     exchange_period=int(os.environ.get("SPH_EMU_XPERIOD", "1")),
+                     halo_width=float(os.environ.get("SPH_EMU_HALO_WIDTH", "0")) or None)
     sim.init_lattice()
     history = []
     elastic = len(sys.argv) > 5 and "elastic" in sys.argv[5]
@@ -62,7 +64,8 @@ def main():
     st = sim.ctx.status()
     np.savez(f"{out}.rank{rank}.npz", state=a, uid=uid, history=np.array(history, "f8"),
              overflow=np.array([st.capacity_overflow, st.msg_overflow]), edges=np.array(sim.edges, "f8"),
-             costs=np.array(sim.costs if sim.costs is not None else [], "f8"), exchanges=np.array([sim.exchanges]))
+             costs=np.array(sim.costs if sim.costs is not None else [], "f8"), exchanges=np.array([sim.exchanges]),
+             n_exchanges=np.array([getattr(sim, "n_exchanges", 0)]))
     dist.barrier()
     dist.destroy_process_group()
 

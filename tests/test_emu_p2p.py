@@ -21,11 +21,14 @@ def spin_timeout(monkeypatch):
     yield
 
 
-@pytest.mark.parametrize("world,goo,one_exchange", [(2, False, False), (3, True, False), (3, False, True), (2, True, True)])
-def test_peer_memory_slab_steps_equal_single_slab_bit_for_bit(built_lib, monkeypatch, world, goo, one_exchange):
+@pytest.mark.parametrize("world,goo,one_exchange,period", [(2, False, False, 1), (3, True, False, 1), (3, False, True, 1), (2, True, True, 1),
+                                                           (3, False, True, 2), (2, False, True, 4), (2, True, True, 2)])
+def test_peer_memory_slab_steps_equal_single_slab_bit_for_bit(built_lib, monkeypatch, world, goo, one_exchange, period):
+    """period > 1 (sph_set_exchange_period): the graph of a step exists with and without the exchange kernel, and the
+    message sequence numbers / buffer parity advance with the EXCHANGES, not with the steps."""
     lib = build_emu(defines=("SPH_ONE_EXCHANGE=1",), name="libsph_emu_sph_one_exchange1.so") if one_exchange else build_emu()
     monkeypatch.setattr(sph_b200, "_lib", sph_b200._bind(C.CDLL(lib)))
-    halo = (4.5 if goo else 3.5) if one_exchange else 2.0
+    halo = (4.5 if goo else 3.5) * period if one_exchange else 2.0
     n_req, steps = 3000, 80
     tank_w = 15.0 * float(np.sqrt(n_req / 750.0))
     prob = make_problem(n_req, tank_w=tank_w, water_frac=0.5, nranks=world)
@@ -44,6 +47,8 @@ def test_peer_memory_slab_steps_equal_single_slab_bit_for_bit(built_lib, monkeyp
         c = sph_b200.Context(prob["tank_w"], prob["tank_h"], prob["h"], 2 * len(a) + 4096, msg_capacity=2048,
                              device=r, rank=r, nranks=world, halo_width=halo)
         assert c.exchanges_per_step == (1 if one_exchange else 2)
+        if period > 1:
+            c.set_exchange_period(period)
         if goo:
             c.set_viscosity_stabilisation(0.5)
         c.set_params(params(prob, r))
@@ -79,6 +84,12 @@ def test_peer_memory_slab_steps_equal_single_slab_bit_for_bit(built_lib, monkeyp
 
     parts = [c.download() for c in ctxs]
     state = np.concatenate([p[0] for p in parts]); uid = np.concatenate([p[1] for p in parts])
+    if world > 1:
+        # launches of a slab: 5 for the upload (k_bin_upload + one sort), 11 per step (12 with the goo pass), and one
+        # k_unpack per meeting: the slabs met every `period` steps (+ once for the queued block's own step)
+        if one_exchange:
+            met = ctxs[0].launches - 5 - (11 + (1 if goo else 0)) * steps
+            assert steps // period <= met <= steps // period + 2, (met, steps, period)
     for c in ctxs:
         s = c.status()
         assert s.capacity_overflow == 0 and s.msg_overflow == 0, (s.capacity_overflow, s.msg_overflow)

@@ -108,3 +108,35 @@ def test_emulated_partition_removed_and_added_back(tmp_path, built_lib, monkeypa
     order = np.argsort(uid)
     for f in ("x", "y", "v_x", "v_y"):
         assert np.array_equal(state[f][order].view("u4"), ref[f].view("u4")), f
+
+
+@pytest.mark.parametrize("config,world,n_req,steps,period", [("emu", 3, 1500, 80, 2), ("emu_block", 4, 12000, 40, 2),
+                                                           ("emu_block", 2, 12000, 44, 4), ("emu_goo_stabilised", 2, 1500, 80, 2),
+                                                           ("emu_elastic", 3, 1500, 200, 2)])
+def test_exchange_period_equals_single_slab_bit_for_bit(tmp_path, built_lib, monkeypatch, config, world, n_req, steps, period):
+    """sph_set_exchange_period (one-exchange build): neighbours meet every `period` steps; in between every slab
+    advances its ghosts itself (k_advect no longer drops them, k_relax relaxes them), in a layer of 3.5 h per step
+    (4.5 h with the stabilised viscosity gather).  Every frame's parameter block (the rebalancer's new edges) forces
+    an exchange in its own step.  Still the single-slab bits: plain fluid on 3 slabs, the block with the mover on an
+    edge on 4 slabs and (4 steps between meetings) on 2, goo with the stabilised gather, and a slab parked and re-added."""
+    monkeypatch.setenv("SPH_EMU_DEFINES", "SPH_ONE_EXCHANGE=1")
+    monkeypatch.setenv("SPH_EMU_XPERIOD", str(period))
+    monkeypatch.setenv("SPH_EMU_HALO_WIDTH", str((4.5 if "goo" in config else 3.5) * period))
+    parts = run_world(tmp_path, world, n_req, steps, True, config)
+    assert all(int(p["exchanges"][0]) == 1 for p in parts), "the workers did not run the one-exchange build"
+    # the ranks really met less often: every `period`-th step, plus the steps in which the rebalancer's block landed
+    # (one per frame of 4 steps; they coincide when the period divides 4) -- never in every step
+    met = [int(p["n_exchanges"][0]) for p in parts]
+    assert all(m == met[0] for m in met) and steps // period <= met[0] <= steps // period + steps // 4 + 2 < steps, (met, steps)
+    state = np.concatenate([p["state"] for p in parts]); uid = np.concatenate([p["uid"] for p in parts])
+    assert all(int(p["overflow"].sum()) == 0 for p in parts), [p["overflow"] for p in parts]
+    block, goo = "block" in config, "goo" in config
+    prob = make_problem(n_req, tank_w=15.0 * float(np.sqrt(n_req / 750.0)), water_frac=0.5) if block else make_problem(n_req)
+    t = default_tunable(prob["h"], prob["tank_w"], prob["tank_h"], preset="y" if goo else "x")
+    if block:
+        t.mover_center_x = 0.4 * prob["tank_w"]
+    ref, ru = emu_single(prob, t, steps, gamma=0.5 if goo else 0.0)
+    assert np.array_equal(np.sort(uid), ru), "particles lost or duplicated in migration"
+    order = np.argsort(uid)
+    for f in ("x", "y", "v_x", "v_y"):
+        assert np.array_equal(state[f][order].view("u4"), ref[f].view("u4")), f
