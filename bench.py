@@ -256,7 +256,7 @@ def main_ours(args):
         else:
             from sph_b200.slab import SlabRunner
             sim = SlabRunner(prob, t, rank, world, stream, capacity_factor=2.0, balance_policy=args.balance,
-                             halo_width=args.halo_width)
+                             halo_width=args.halo_width, exchange_period=args.exchange_period)
         if args.visc_stab is not None:                  # default: the library's (gamma 0.5 for blocks with dt*sigma >= 0.5)
             sim.ctx.set_viscosity_stabilisation(args.visc_stab)
         mark("created")
@@ -351,6 +351,7 @@ def main_ours(args):
                 "step_hbm_frac": step_gbs / peak,
                 "parallelism": f"slab{world}",
                 "exchanges_per_step": getattr(sim, "exchanges", None),
+                "exchange_period_steps": getattr(sim, "exchange_period", None),
                 "edge_policy": ("particle count, dead band 1/15 (renderer.c:427-477)" if args.balance == "count" else
                                 "work estimate per slab (sph_copy_load), dead band 1/40 -- NOT the reference's policy") if world > 1 else None,
                 "per_slab_[n_local,n_ghost,neighbours,gather_us,sort_us]": per_rank,
@@ -523,6 +524,8 @@ def main():
     ap.add_argument("--visc-stab", type=float, default=None, metavar="GAMMA",
                     help="force the stabilised viscosity gather with this gamma for every block (0 = plain gather everywhere); "
                          "default: the library's own rule (gamma 0.5 where dt*sigma >= 0.5, i.e. the goo preset, DESIGN.md 5b)")
+    ap.add_argument("--exchange-period", type=int, default=1,
+                    help="N > 1, one-exchange build: neighbours meet every this many steps (ghost layer 3.5 h per step)")
     ap.add_argument("--cpu-steps", type=int, default=20, help="timed steps of the cpu_baseline sample")
     ap.add_argument("--cpu-warmup", type=int, default=300, help="untimed steps of the cpu_baseline sample (bounded: the "
                     "reference arm, --impl reference, runs the full pre-roll)")

@@ -45,6 +45,15 @@ template <class... A> static PdlLauncher<A...> pdl_launcher(void (*k)(A...), int
 #ifndef SPH_GRID_MULT
 #define SPH_GRID_MULT 8          // blocks per SM of the gather kernels (0: one block per 256 entries of capacity)
 #endif
+#ifndef SPH_GRID_ADVECT
+#define SPH_GRID_ADVECT (SPH_GRID_MULT > 0 ? SPH_GRID_MULT : 1 << 20)
+#endif
+#ifndef SPH_GRID_DENSITY
+#define SPH_GRID_DENSITY (SPH_GRID_MULT > 0 ? 2 * SPH_GRID_MULT : 1 << 20)
+#endif
+#ifndef SPH_GRID_RELAX
+#define SPH_GRID_RELAX (SPH_GRID_MULT > 0 ? SPH_GRID_MULT : 1 << 20)
+#endif
 #ifndef SPH_GRID_MULT_SORT
 #define SPH_GRID_MULT_SORT 8     // blocks per SM of the sort's streaming kernels (scan, scatter, reorder)
 #endif
@@ -93,6 +102,7 @@ struct sph_ctx {
     int stage;
     int grid;                        // per-particle gather kernels
     int sort_grid;                   // the sort's streaming kernels
+    int grid_advect, grid_density, grid_relax;
     int size_x, size_y;
     cudaGraphExec_t graph[4];        // whole step: index = stabilised viscosity gather + 2 * exchange step
     bool graph_ready[4];
@@ -191,6 +201,10 @@ extern "C" int sph_create(const sph_config *cfg, sph_ctx **out)
 #else
     ctx->grid = (int)((cap + SPH_THREADS - 1) / SPH_THREADS);
 #endif
+    // per-kernel block counts (A/B of round 2: k_advect and k_density like 16 blocks per SM, k_relax 8)
+    ctx->grid_advect = std::min<int>((int)((cap + SPH_THREADS - 1) / SPH_THREADS), prop.multiProcessorCount * SPH_GRID_ADVECT);
+    ctx->grid_density = std::min<int>((int)((cap + SPH_THREADS - 1) / SPH_THREADS), prop.multiProcessorCount * SPH_GRID_DENSITY);
+    ctx->grid_relax = std::min<int>((int)((cap + SPH_THREADS - 1) / SPH_THREADS), prop.multiProcessorCount * SPH_GRID_RELAX);
     ctx->sort_grid = std::min<int>((int)((cap + SPH_THREADS - 1) / SPH_THREADS), prop.multiProcessorCount * SPH_GRID_MULT_SORT);
 
     for (int i = 0; i < 4; i++) CK(cudaMalloc(&ctx->P[i], cap * sizeof(float2)));
@@ -563,17 +577,17 @@ extern "C" int sph_exchange_due(sph_ctx *ctx)
 static int launch_advect(sph_ctx *ctx)
 {
     if (stabilised(ctx)) {
-        SPH_LAUNCH(k_coupling, ctx->grid, ctx->stream)(ctx->dp, ctx->counters, ctx->P[0], ctx->Q[0], ctx->cell_start, ctx->coupling);
-        SPH_LAUNCH(k_advect<true>, ctx->grid, ctx->stream)(ctx->dp, ctx->counters, ctx->P[0], ctx->Q[0], ctx->U[0],
+        SPH_LAUNCH(k_coupling, ctx->grid_advect, ctx->stream)(ctx->dp, ctx->counters, ctx->P[0], ctx->Q[0], ctx->cell_start, ctx->coupling, ctx->ord_key);
+        SPH_LAUNCH(k_advect<true>, ctx->grid_advect, ctx->stream)(ctx->dp, ctx->counters, ctx->P[0], ctx->Q[0], ctx->U[0],
                                                             ctx->cell_start, ctx->P[1], ctx->cnt, ctx->t_key, ctx->t_slot,
-                                                            ctx->send[0], ctx->send[1], ctx->coupling, ctx->dopt, ctx->cur_x ? 1 : 0);
+                                                            ctx->send[0], ctx->send[1], ctx->coupling, ctx->dopt, ctx->cur_x ? 1 : 0, ctx->ord_key);
         ctx->launches += 2;
         CK(cudaGetLastError());
         return SPH_OK;
     }
-    SPH_LAUNCH(k_advect<false>, ctx->grid, ctx->stream)(ctx->dp, ctx->counters, ctx->P[0], ctx->Q[0], ctx->U[0],
+    SPH_LAUNCH(k_advect<false>, ctx->grid_advect, ctx->stream)(ctx->dp, ctx->counters, ctx->P[0], ctx->Q[0], ctx->U[0],
                                                          ctx->cell_start, ctx->P[1], ctx->cnt, ctx->t_key, ctx->t_slot,
-                                                         ctx->send[0], ctx->send[1], nullptr, nullptr, ctx->cur_x ? 1 : 0);
+                                                         ctx->send[0], ctx->send[1], nullptr, nullptr, ctx->cur_x ? 1 : 0, ctx->ord_key);
     ctx->launches++;
     CK(cudaGetLastError());
     return SPH_OK;
@@ -581,7 +595,7 @@ static int launch_advect(sph_ctx *ctx)
 
 static int launch_density(sph_ctx *ctx)
 {
-    SPH_LAUNCH(k_density, ctx->grid, ctx->stream)(ctx->dp, ctx->counters, ctx->P[2], ctx->cell_start, ctx->dens, ctx->nmask
+    SPH_LAUNCH(k_density, ctx->grid_density, ctx->stream)(ctx->dp, ctx->counters, ctx->P[2], ctx->cell_start, ctx->dens, ctx->nmask, ctx->ord_key
 #if SPH_RELAX_PD4
                                                    , ctx->pd
 #endif
@@ -593,9 +607,9 @@ static int launch_density(sph_ctx *ctx)
 
 static int launch_relax(sph_ctx *ctx)
 {
-    SPH_LAUNCH(k_relax, ctx->grid, ctx->stream)(ctx->dp, ctx->counters, ctx->P[2], ctx->Q[1], ctx->U[1], ctx->dens,
+    SPH_LAUNCH(k_relax, ctx->grid_relax, ctx->stream)(ctx->dp, ctx->counters, ctx->P[2], ctx->Q[1], ctx->U[1], ctx->dens,
                                                         ctx->cell_start, ctx->nmask, ctx->P[3], ctx->Q[2], ctx->cnt, ctx->t_key,
-                                                        ctx->t_slot, ctx->send[0], ctx->send[1]
+                                                        ctx->t_slot, ctx->send[0], ctx->send[1], ctx->ord_key
 #if SPH_RELAX_PD4
                                                         , ctx->pd
 #endif

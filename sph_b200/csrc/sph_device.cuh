@@ -69,7 +69,7 @@ enum {
 // over the dam-break's states, i.e. about 14 neighbour-equivalents per entry.
 #define SPH_COST_BASE 14
 
-// SPH_ONE_EXCHANGE=1 (build variant, emulator-checked, not yet timed): neighbours meet ONCE per step.  The ghosts
+// SPH_ONE_EXCHANGE=1 (build variant): neighbours meet ONCE per step (or every E steps, sph_set_exchange_period).  The ghosts
 // of exchange 0 carry x_prev as well, the ghost layer is >= 3h wide, and k_relax relaxes the ghosts redundantly
 // (those within layer - 2h of the edge come out exactly as on their owner: same neighbours, same order), so the
 // next k_advect has its neighbours' velocities without the second message.
@@ -135,6 +135,12 @@ __device__ __forceinline__ float rcp_approx(float x)
     float r;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
+}
+// a line towards L1 without occupying a register: the per-particle inputs of a thread's NEXT particle, and inputs
+// of this one that are only read after the candidate loops (SPH_PIPE, sph_kernels.cuh)
+__device__ __forceinline__ void prefetch_l1(const void *p)
+{
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
 }
 // FMNMX.NAN: a NaN operand wins, so that a running maximum also reports "not finite"
 __device__ __forceinline__ float max_nan(float a, float b)

@@ -20,30 +20,31 @@
 #define SPH_UNROLL 4          // candidates per trip of the gather loops (loads issued together)
 #endif
 constexpr int kGatherUnroll = SPH_UNROLL;     // (#pragma unroll takes a constant expression, not a macro)
-// SPH_PACKED=1: the candidate loops of k_advect, k_coupling and k_density process two candidates per trip with
-// packed FP32 instructions (FADD2 / FMUL2 / FFMA2, sph_device.cuh): the same rn operations in the same order, so
-// the results do not change by a bit (tests/test_emu_variants.py), but 20-30 % fewer issued instructions per
-// candidate in kernels that are bound by instruction issue.  Built and checked in the emulator, NOT yet timed
-// on the B200: the default (0) is the scalar code measured in round 1.
+// SPH_PACKED=1 (default since round 2): the candidate loops of k_advect, k_coupling and k_density process two
+// candidates per trip with packed FP32 instructions (FADD2 / FMUL2 / FFMA2, sph_device.cuh): the same rn operations
+// in the same order, so the results do not change by a bit (tests/test_emu_variants.py).  Measured on the B200
+// (profiles/r2_variants.md): 26 % fewer issued instructions in k_advect but only 4-5 % less time (90 -> 86 us) --
+// a packed instruction holds the FMA pipe for two passes, so the pipe cycles stay and only issue slots are freed.
 #ifndef SPH_PACKED
-#define SPH_PACKED 0
+#define SPH_PACKED 1
 #endif
-// SPH_PACKED_RELAX=1: the same for k_relax's pair physics ((x, y) accumulate in one register).  Separate flag:
-// in SASS the packed pair saves ~4 FP instructions but ptxas adds register moves around the rare-path branches,
-// and the kernel is latency- rather than issue-bound; to be decided by measurement.
-// SPH_TRIM=1: k_advect's candidate loop with the impulse clamp moved to a per-row exact redo (see the kernel)
-#ifndef SPH_TRIM
-#define SPH_TRIM 0
-#endif
+// SPH_PACKED_RELAX=1 (default since round 2): the same for k_relax's pair physics ((x, y) accumulate in one
+// register).  Measured: within noise of the scalar pair (66.1 vs 66.9 us).
 #ifndef SPH_PACKED_RELAX
-#define SPH_PACKED_RELAX 0
+#define SPH_PACKED_RELAX 1
 #endif
 // SPH_RELAX_PD4=1: k_density also writes (x, y, density, density_near) as one 16-byte record per entry and
-// k_relax's neighbour walk reads that record: one load and one address per neighbour instead of two.  k_relax is
-// bound by load latency (profiles/r1_branchfree_full.csv), and its trip of two neighbours spends 23 of ~59
-// instructions on index arithmetic and loads.  Emulator-checked, not yet timed.
+// k_relax's neighbour walk reads that record: one load and one address per neighbour instead of two.
+// Measured on the B200 in round 2 and REJECTED: k_relax 74 us against 67 (the extra 16 bytes per particle that
+// k_density writes and the larger L1 footprint cost more than the saved address arithmetic).
 #ifndef SPH_RELAX_PD4
 #define SPH_RELAX_PD4 0
+#endif
+// SPH_RELAX_BF=1: k_relax's neighbour loop branch-free in candidate order with mask-predicated loads (see the kernel).
+// Measured on the B200 in round 2 and REJECTED: 88 us against 66 -- a warp runs to the highest set bit of its 32
+// lanes, 53 M issued warp instructions against the walk's 37 M.
+#ifndef SPH_RELAX_BF
+#define SPH_RELAX_BF 0
 #endif
 #if SPH_RELAX_PD4
 #define SPH_PD4_PARAM , float4 *__restrict__ pd
@@ -116,6 +117,28 @@ __device__ __forceinline__ Rows candidate_rows(float2 p, const DevParams &P, con
     return r;
 }
 
+
+// The same ranges from the cell key the last sort assigned to this entry (key = gy * wx + gx in the current window;
+// an entry in the sorted arrays is inside the window, so no clamping of the cell itself is needed).
+__device__ __forceinline__ Rows candidate_rows_key(int key, const DevParams &P, float inv_wx, const int *__restrict__ cell_start)
+{
+    Rows r;
+    // key / wx by reciprocal and one correction step (quotient < 2^15 rows: the float estimate is off by at most 1)
+    int gy = (int)((float)key * inv_wx);
+    int gx = key - gy * P.wx;
+    if (gx < 0) { gy--; gx += P.wx; } else if (gx >= P.wx) { gy++; gx -= P.wx; }
+    const int c0 = max(gx - SPH_CELL_DIV, 0), c1 = min(gx + SPH_CELL_DIV, P.wx - 1);
+    const int base = key - gx;
+#pragma unroll
+    for (int d = 0; d < SPH_NROWS; d++) {
+        const int row = gy + d - SPH_CELL_DIV;
+        if (row < 0 || row >= P.sort_rows) { r.b[d] = 0; r.e[d] = 0; continue; }
+        const int rb = base + (d - SPH_CELL_DIV) * P.wx;
+        r.b[d] = __ldg(&cell_start[rb + c0]);
+        r.e[d] = __ldg(&cell_start[rb + c1 + 1]);
+    }
+    return r;
+}
 
 // -------------------------------------------------------------------------------------------
 // Peer-memory exchange.  The compute kernels (k_advect, k_relax) append outgoing records to a compact
@@ -208,6 +231,23 @@ __device__ __forceinline__ void bin_position(int i, float2 p, int extra_bits, co
     t_key[i] = key | extra_bits;
 }
 
+// The same with the store of the arrival slot left to the caller (SPH_PIPE): returns the slot, or -1 when the entry
+// was dropped.  The caller stores it an iteration later, so that no instruction waits for the atomic's round trip.
+__device__ __forceinline__ bool bin_position_deferred(int i, float2 p, int extra_bits, const DevParams &P,
+                                                      int *__restrict__ cnt, int *__restrict__ t_key, int *__restrict__ counters,
+                                                      int &slot)
+{
+    int key = window_key_new(p, P);
+    if (key == SPH_KEY_DROP) {
+        if (!(extra_bits & SPH_KEY_EMIG)) atomicAdd(&counters[CN_CAP_OVER], 1);
+        t_key[i] = SPH_KEY_DROP;
+        return false;
+    }
+    t_key[i] = key | extra_bits;
+    slot = atomicAdd(&cnt[key], 1);        // (the caller must not look at it before the next iteration)
+    return true;
+}
+
 // -------------------------------------------------------------------------------------------
 // K1  apply_gravity (fluid.c:398) + viscosity_impluses (:416) + predict_positions (:507)
 //     + boundaryConditions (:656) + identify_oob_particles (:481) + ghost selection
@@ -233,7 +273,7 @@ k_advect(const DevParams *__restrict__ Pp, int *__restrict__ counters,
          const int *__restrict__ cell_start,
          float2 *__restrict__ pos_pred, int *__restrict__ cnt, int *__restrict__ t_key, int *__restrict__ t_slot,
          unsigned char *send_l, unsigned char *send_r, const float *__restrict__ coupling, const DevOptions *__restrict__ Op,
-         int xstep)
+         int xstep, const int *__restrict__ ckey)
 {
     // xstep: neighbours exchange after this prediction (always, except in the one-exchange build with an exchange
     // period > 1, where between exchanges the ghosts are advanced here like everything else; see sph_set_exchange_period)
@@ -247,9 +287,23 @@ k_advect(const DevParams *__restrict__ Pp, int *__restrict__ counters,
     const float h_recip = __fdiv_rn(1.0f, P.h);
     const float h2 = __fmul_rn(P.h, P.h);
     if (blockIdx.x == 0 && threadIdx.x == 0) { counters[CN_MAX_BUCKET] = 0; counters[CN_COST] = 0; }
+#if SPH_PIPE
+    const float inv_wx = 1.0f / (float)P.wx;
+    int slot_i = -1, slot_v = 0;                                        // arrival slot whose store is still owed
+#endif
 
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const uint32_t u = uid[i];
+#if SPH_PIPE
+        // all of this particle's inputs are requested before the first of them is looked at
+        const float2 p = pos[i];
+        const float2 v0 = vel[i];
+        const int key_i = ckey[i];
+        {
+            const int nx = i + gridDim.x * blockDim.x;
+            if (nx < n) { prefetch_l1(uid + nx); prefetch_l1(pos + nx); prefetch_l1(vel + nx); prefetch_l1(ckey + nx); }
+        }
+#endif
 #if SPH_ONE_EXCHANGE
         const bool ghost = (u & SPH_HALO_BIT) != 0;
         if (ghost && xstep) { t_key[i] = SPH_KEY_DROP; continue; }      // ghosts are replaced at every exchange
@@ -257,10 +311,16 @@ k_advect(const DevParams *__restrict__ Pp, int *__restrict__ counters,
         const bool ghost = false;
         if (u & SPH_HALO_BIT) { t_key[i] = SPH_KEY_DROP; continue; }   // ghosts are replaced every exchange
 #endif
+#if !SPH_PIPE
         const float2 p = pos[i];
         const float2 v0 = vel[i];
+#endif
         float vx = v0.x, vy = v0.y + gdt;                               // apply_gravity
+#if SPH_PIPE
+        const Rows R = candidate_rows_key(key_i, P, inv_wx, cell_start);
+#else
         const Rows R = candidate_rows(p, P, cell_start);
+#endif
         const float gci = STAB ? gamma * coupling[i] : 0.0f;
 #if SPH_TRIM
         // SPH_TRIM=1 (round 2): the candidate loop without the per-component clamp.  The +-2.5 clamp of a pair's
@@ -465,8 +525,16 @@ k_advect(const DevParams *__restrict__ Pp, int *__restrict__ counters,
                 }
             }
         }
+#if SPH_PIPE
+        if (slot_i >= 0) t_slot[slot_i] = slot_v;                       // the previous particle's: its atomic is back by now
+        slot_i = bin_position_deferred(i, np, extra, P, cnt, t_key, counters, slot_v) ? i : -1;
+#else
         bin_position(i, np, extra, P, cnt, t_key, t_slot, counters);
+#endif
     }
+#if SPH_PIPE
+    if (slot_i >= 0) t_slot[slot_i] = slot_v;
+#endif
     pdl_done();
 }
 
@@ -486,18 +554,26 @@ k_advect(const DevParams *__restrict__ Pp, int *__restrict__ counters,
 __global__ void __launch_bounds__(SPH_THREADS, SPH_BLOCKS_DENSITY)
 k_coupling(const DevParams *__restrict__ Pp, const int *__restrict__ counters,
            const float2 *__restrict__ pos, const float2 *__restrict__ vel, const int *__restrict__ cell_start,
-           float *__restrict__ coupling)
+           float *__restrict__ coupling, const int *__restrict__ ckey)
 {
     pdl_enter();
     const DevParams P = *Pp;
     const int n = counters[CN_NTOT];
     const float h_recip = __fdiv_rn(1.0f, P.h);
     const float h2 = __fmul_rn(P.h, P.h);
+#if SPH_PIPE
+    const float inv_wx = 1.0f / (float)P.wx;
+#endif
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const float2 p = pos[i];
         const float2 v0 = vel[i];
         float c = 0.0f;
+#if SPH_PIPE
+        const Rows R = candidate_rows_key(ckey[i], P, inv_wx, cell_start);
+        { const int nx = i + gridDim.x * blockDim.x; if (nx < n) { prefetch_l1(pos + nx); prefetch_l1(vel + nx); prefetch_l1(ckey + nx); } }
+#else
         const Rows R = candidate_rows(p, P, cell_start);
+#endif
 #if SPH_PACKED
         const f32x2 pp = pk2(p.x, p.y), v0p = pk2(v0.x, v0.y);
         const f32x2 nh2 = pk2(-h_recip, -h_recip), one2 = pk2(1.0f, 1.0f), dt2 = pk2(P.dt, P.dt);
@@ -861,7 +937,7 @@ k_reorder(const DevParams *__restrict__ Pp, int *__restrict__ counters, const in
 __global__ void __launch_bounds__(SPH_THREADS, SPH_BLOCKS_DENSITY)
 k_density(const DevParams *__restrict__ Pp, int *__restrict__ counters,
           const float2 *__restrict__ pos, const int *__restrict__ cell_start, float2 *__restrict__ dens,
-          sph_mask_t *__restrict__ nmask SPH_PD4_PARAM)
+          sph_mask_t *__restrict__ nmask, const int *__restrict__ ckey SPH_PD4_PARAM)
 {
     pdl_enter();
     const DevParams P = *Pp;
@@ -869,11 +945,19 @@ k_density(const DevParams *__restrict__ Pp, int *__restrict__ counters,
     const float h_recip = __fdiv_rn(1.0f, P.h);
     const float h2 = __fmul_rn(P.h, P.h);
     int cost = 0;
+#if SPH_PIPE
+    const float inv_wx = 1.0f / (float)P.wx;
+#endif
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const float2 p = pos[i];
         float d = 0.0f, dn = 0.0f;
         int nn = 0;
+#if SPH_PIPE
+        const Rows R = candidate_rows_key(ckey[i], P, inv_wx, cell_start);
+        { const int nx = i + gridDim.x * blockDim.x; if (nx < n) { prefetch_l1(pos + nx); prefetch_l1(ckey + nx); } }
+#else
         const Rows R = candidate_rows(p, P, cell_start);
+#endif
 #if SPH_PACKED
         const f32x2 pp = pk2(p.x, p.y), nh2 = pk2(-h_recip, -h_recip), one2 = pk2(1.0f, 1.0f);
 #endif
@@ -964,11 +1048,15 @@ k_relax(const DevParams *__restrict__ Pp, int *__restrict__ counters,
         const sph_mask_t *__restrict__ nmask,
         float2 *__restrict__ pos_out, float2 *__restrict__ vel_out,
         int *__restrict__ cnt, int *__restrict__ t_key, int *__restrict__ t_slot,
-        unsigned char *send_l, unsigned char *send_r SPH_PD4_CPARAM)
+        unsigned char *send_l, unsigned char *send_r, const int *__restrict__ ckey SPH_PD4_CPARAM)
 {
     pdl_enter();
     const DevParams P = *Pp;
     const int n = counters[CN_NTOT];
+#if SPH_PIPE
+    const float inv_wx = 1.0f / (float)P.wx;
+    int slot_i = -1, slot_v = 0;                                        // arrival slot whose store is still owed
+#endif
     const float dt = P.dt, dt2 = dt * dt;
     const float h = P.h;
     const float h_recip = __fdiv_rn(1.0f, h);
@@ -978,13 +1066,34 @@ k_relax(const DevParams *__restrict__ Pp, int *__restrict__ counters,
 
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const uint32_t u = uid[i];
+#if SPH_PIPE
+        const float2 p = pos[i];
+        const float2 di = dens[i];
+        const int key_i = ckey[i];
+#endif
 #if SPH_ONE_EXCHANGE
         const bool ghost = (u & SPH_HALO_BIT) != 0;     // relaxed redundantly and kept as a ghost for the coming k_advect
 #else
         if (u & SPH_HALO_BIT) { t_key[i] = SPH_KEY_DROP; continue; }
 #endif
+#if !SPH_PIPE
         const float2 p = pos[i];
         const float2 di = dens[i];
+#else
+        {
+            // this particle's late inputs (the masks of the rows after the first, its previous position) and the
+            // next particle's early ones, all towards L1 now
+#pragma unroll
+            for (int d = 1; d < SPH_NROWS; d++) prefetch_l1(nmask + (size_t)d * P.cap + i);
+            prefetch_l1(prev + i);
+            const int nx = i + gridDim.x * blockDim.x;
+            if (nx < n) {
+                prefetch_l1(uid + nx); prefetch_l1(pos + nx); prefetch_l1(dens + nx); prefetch_l1(ckey + nx);
+#pragma unroll
+                for (int d = 0; d < SPH_NROWS; d++) prefetch_l1(nmask + (size_t)d * P.cap + nx);
+            }
+        }
+#endif
         // fluid.c:563-564 + :591 with the constants folded.  With w = 1 - r/h the spring term is
         // k_spring*(h - r)/2 = k_spring*h*w/2, so
         //   D = dt^2 ((P_i+P_j) w + (Pn_i+Pn_j) w^2 + k_spring (h-r)/2) = w (A + B w),
@@ -994,8 +1103,17 @@ k_relax(const DevParams *__restrict__ Pp, int *__restrict__ counters,
         const float Ai = fmaf(K1, di.x - 2.0f * P.rest_density, Cs);
         const float Bi = K2 * di.y;
         float x = p.x, y = p.y;
+#if SPH_PIPE
+        // (the reference cell of this particle is only needed by the coincident-pair rule: formed there)
+#define SPH_GXI cell_coord(p.x, P.cell_h)
+#define SPH_GYI cell_coord(p.y, P.cell_h)
+        const Rows R = candidate_rows_key(key_i, P, inv_wx, cell_start);
+#else
         const int gxi = cell_coord(p.x, P.cell_h), gyi = cell_coord(p.y, P.cell_h);
+#define SPH_GXI gxi
+#define SPH_GYI gyi
         const Rows R = candidate_rows(p, P, cell_start);
+#endif
         // pair physics for one listed neighbour (membership r2 <= h2, j != i already established)
 #if SPH_PACKED_RELAX
         // packed build: (x, y) accumulate in one 64-bit register; the same rn operations in the same order
@@ -1014,8 +1132,9 @@ k_relax(const DevParams *__restrict__ Pp, int *__restrict__ counters,
                 const float r = __fsqrt_rn(r2);
                 if (r <= 0.000001f) {
                     const int gxj = cell_coord(q.x, P.cell_h), gyj = cell_coord(q.y, P.cell_h);
-                    const bool owner = (gxi == gxj && gyi == gyj) ? ((u & SPH_UID_MASK) < (uid[j] & SPH_UID_MASK))
-                                                                  : (gxi != gxj ? gxi < gxj : gyi < gyj);
+                    const int cxi = SPH_GXI, cyi = SPH_GYI;
+                    const bool owner = (cxi == gxj && cyi == gyj) ? ((u & SPH_UID_MASK) < (uid[j] & SPH_UID_MASK))
+                                                                  : (cxi != gxj ? cxi < gxj : cyi < gyj);
                     if (owner) { a.x += 0.000001f; a.y += 0.000001f; }
                 }
                 const float ratio = r * h_recip;
@@ -1046,8 +1165,9 @@ k_relax(const DevParams *__restrict__ Pp, int *__restrict__ counters,
                     // the same cell, else the cell whose forward stencil (0,+1),(1,-1),(1,0),(1,+1)
                     // holds the other (hash.c:178-224)
                     const int gxj = cell_coord(q.x, P.cell_h), gyj = cell_coord(q.y, P.cell_h);
-                    const bool owner = (gxi == gxj && gyi == gyj) ? ((u & SPH_UID_MASK) < (uid[j] & SPH_UID_MASK))
-                                                                  : (gxi != gxj ? gxi < gxj : gyi < gyj);
+                    const int cxi = SPH_GXI, cyi = SPH_GYI;
+                    const bool owner = (cxi == gxj && cyi == gyj) ? ((u & SPH_UID_MASK) < (uid[j] & SPH_UID_MASK))
+                                                                  : (cxi != gxj ? cxi < gxj : cyi < gyj);
                     if (owner) { x += 0.000001f; y += 0.000001f; }
                 }
                 const float ratio = r * h_recip;
@@ -1069,6 +1189,8 @@ k_relax(const DevParams *__restrict__ Pp, int *__restrict__ counters,
             y = fmaf(-s, dy, y);
         };
 #endif
+        // the exact walk over k_density's acceptance bits, two neighbours per trip, with the coincident-pair rules
+        auto walk_all = [&]() {
 #pragma unroll
         for (int d = 0; d < SPH_NROWS; d++) {
             // the lists were built by k_density on these same positions: walk its acceptance bits
@@ -1104,6 +1226,81 @@ k_relax(const DevParams *__restrict__ Pp, int *__restrict__ counters,
                 pair(j, q, dens[j]);
             }
         }
+        };
+#if SPH_RELAX_BF
+        // SPH_RELAX_BF=1 (round 2): the row's first SPH_MASK_BITS candidates in CANDIDATE order, branch-free: a
+        // candidate whose acceptance bit is off loads nothing (predicated loads) and contributes an exact zero, so
+        // values and order of the sum are the walk's, but the index of a neighbour is a loop counter instead of
+        // the end of a dependent chain mask -> find-first-set -> address -> load (this kernel sat at 50 % issue
+        // utilisation on exactly that chain, profiles/r2_call2_*).  The loop stops after the row's last set bit.
+        // A (nearly) coincident pair -- rare -- raises a flag and the particle is redone by the exact walk.
+        {
+            bool rare = false;
+#if SPH_PACKED_RELAX
+            const f32x2 di2 = pk2(di.x, di.y);
+#endif
+#pragma unroll
+            for (int d = 0; d < SPH_NROWS; d++) {
+                const int b = R.b[d];
+                sph_mask_t m = nmask[(size_t)d * P.cap + i];
+#pragma unroll 4
+                for (int j = b; m != 0; j++, m >>= 1) {
+                    const bool on = (m & 1) != 0;
+#if SPH_PACKED_RELAX
+                    f32x2 qv = pp, dv = di2;
+#if SPH_RELAX_PD4
+                    if (on) { const float4 r4 = pd[j]; qv = pk2(r4.x, r4.y); dv = pk2(r4.z, r4.w); }
+#else
+                    if (on) { qv = ld2(pos + j); dv = ld2(dens + j); }
+#endif
+                    const f32x2 dd = sub2(qv, pp);
+                    const float2 sq = unpk2(mul2(dd, dd));
+                    const float r2 = __fadd_rn(sq.x, sq.y);
+                    rare |= on & (r2 <= 1.0001e-12f);
+                    const float2 ab = unpk2(fma2(dv, K12, AB0));
+                    const float rs = rsqrt_approx(r2);
+                    const float w = fmaxf(fmaf(-r2 * rs, h_recip, 1.0f), 0.0f);
+                    float s = fmaf(ab.y, w, ab.x) * w * rs;
+                    s = on ? s : 0.0f;
+                    xy = fma2(pk2(-s, -s), dd, xy);
+#else
+                    float2 q = p, dj = di;
+#if SPH_RELAX_PD4
+                    if (on) { const float4 r4 = pd[j]; q = make_float2(r4.x, r4.y); dj = make_float2(r4.z, r4.w); }
+#else
+                    if (on) { q = pos[j]; dj = dens[j]; }
+#endif
+                    const float dx = q.x - p.x, dy = q.y - p.y;
+                    const float r2 = dist2(dx, dy);
+                    rare |= on & (r2 <= 1.0001e-12f);
+                    const float A = fmaf(dj.x, K1, Ai), B = fmaf(dj.y, K2, Bi);
+                    const float rs = rsqrt_approx(r2);
+                    const float w = fmaxf(fmaf(-r2 * rs, h_recip, 1.0f), 0.0f);
+                    float s = fmaf(B, w, A) * w * rs;
+                    s = on ? s : 0.0f;
+                    x = fmaf(-s, dx, x);
+                    y = fmaf(-s, dy, y);
+#endif
+                }
+                // the rare candidates beyond those a mask covers
+                for (int j = b + SPH_MASK_BITS; j < R.e[d]; j++) {
+                    const float2 q = pos[j];
+                    if (dist2(q.x - p.x, q.y - p.y) > h2 || j == i) continue;
+                    pair(j, q, dens[j]);
+                }
+            }
+            if (rare) {
+#if SPH_PACKED_RELAX
+                xy = pp;
+#else
+                x = p.x; y = p.y;
+#endif
+                walk_all();
+            }
+        }
+#else
+        walk_all();
+#endif
 #if SPH_PACKED_RELAX
         { const float2 a = unpk2(xy); x = a.x; y = a.y; }
 #endif
@@ -1113,7 +1310,12 @@ k_relax(const DevParams *__restrict__ Pp, int *__restrict__ counters,
         pos_out[i] = np;
         vel_out[i] = v;
 #if SPH_ONE_EXCHANGE
+#if SPH_PIPE
+        if (slot_i >= 0) t_slot[slot_i] = slot_v;
+        slot_i = bin_position_deferred(i, np, ghost ? SPH_KEY_EMIG : 0, P, cnt, t_key, counters, slot_v) ? i : -1;
+#else
         bin_position(i, np, ghost ? SPH_KEY_EMIG : 0, P, cnt, t_key, t_slot, counters);
+#endif
         continue;
 #endif
         if (P.nranks > 1) {
@@ -1128,8 +1330,18 @@ k_relax(const DevParams *__restrict__ Pp, int *__restrict__ counters,
                 else atomicAdd(&counters[CN_MSG_OVER], 1);
             }
         }
+#if SPH_PIPE
+        if (slot_i >= 0) t_slot[slot_i] = slot_v;                       // the previous particle's: its atomic is back by now
+        slot_i = bin_position_deferred(i, np, 0, P, cnt, t_key, counters, slot_v) ? i : -1;
+#else
         bin_position(i, np, 0, P, cnt, t_key, t_slot, counters);
+#endif
     }
+#if SPH_PIPE
+    if (slot_i >= 0) t_slot[slot_i] = slot_v;
+#endif
+#undef SPH_GXI
+#undef SPH_GYI
     pdl_done();
 }
 

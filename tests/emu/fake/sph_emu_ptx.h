@@ -4,6 +4,7 @@
 // GCC atomics in place of the system-scope acquire / release.
 #pragma once
 static inline float rcp_approx(float x) { return 1.0f / x; }
+static inline void prefetch_l1(const void *) {}
 static inline float max_nan(float a, float b) { return (a != a || b != b) ? NAN : (a > b ? a : b); }
 struct f32x2 { float lo, hi; };
 static inline f32x2 pk2(float lo, float hi) { return f32x2{lo, hi}; }

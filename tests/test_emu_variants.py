@@ -86,3 +86,42 @@ def test_trimmed_advect_loop_agrees_with_the_gather_oracle_and_redoes_rows_where
         imp = 0.5 * t.time_step * (1 - r / h) * (t.sigma * u + t.beta * u * u)
     binds = near & (u > 0) & ((np.abs(imp * dx / r) > 2.5) | (np.abs(imp * dy / r) > 2.5))
     assert binds.sum() > 20, binds.sum()
+
+
+@pytest.mark.parametrize("packed", [False, True])
+@pytest.mark.parametrize("name,warm,gamma", [("default1508", 400, 0.0), ("block3000", 150, 0.0), ("goo_rect1508", 300, 0.5)])
+def test_branch_free_relax_loop_is_bit_identical_in_the_emulator(built_lib, monkeypatch, name, warm, gamma, packed):
+    """SPH_RELAX_BF=1: k_relax walks a row's candidates in order with mask-predicated loads instead of chasing the
+    set bits; a masked-off candidate contributes an exact zero, so the default build's bits must come out."""
+    defs = ("SPH_RELAX_BF=1",) + (("SPH_PACKED=1", "SPH_PACKED_RELAX=1") if packed else ())
+    base = build_emu()
+    bf = build_emu(defines=defs, name="libsph_emu_bf%d.so" % packed)
+    d0, a0 = run(base, name, warm, 12, gamma, monkeypatch)
+    d1, a1 = run(bf, name, warm, 12, gamma, monkeypatch)
+    for f in ("x", "y", "v_x", "v_y"):
+        assert np.array_equal(a0[f].view("u4"), a1[f].view("u4")), ("after the step", f)
+
+
+def test_branch_free_relax_loop_redoes_particles_with_coincident_neighbours(built_lib, monkeypatch):
+    """The hostile soup of the edge-case test (coincident particles, pile-ups in the corners, particles on the walls)
+    through the SPH_RELAX_BF build: the coincident-pair rules (fluid.c:583-588) live in the exact walk the fast loop
+    falls back to, so the result must equal the default build's bit for bit -- including rows longer than a mask."""
+    from test_gpu_parity import Cuda
+    outs = []
+    for lib in (build_emu(), build_emu(defines=("SPH_RELAX_BF=1", "SPH_PACKED=1", "SPH_PACKED_RELAX=1"), name="libsph_emu_bf1.so")):
+        monkeypatch.setattr(sph_b200, "_lib", sph_b200._bind(C.CDLL(lib)))
+        z, t, tank_w, tank_h, h, _ = load_golden("default1508")
+        rng = np.random.default_rng(11)
+        n = 1200
+        st = np.zeros(n, z["w400_state"].dtype)
+        st["x"] = rng.uniform(0, tank_w, n); st["y"] = rng.uniform(0, tank_h * 0.3, n)
+        st["x"][:200] = st["x"][200:400]; st["y"][:200] = st["y"][200:400]          # coincident pairs
+        st["x"][400:560] = rng.uniform(0, 0.4 * h, 160); st["y"][400:560] = rng.uniform(0, 0.4 * h, 160)   # a corner pile: rows > 32
+        st["x"][560:600] = 0.0; st["y"][600:640] = 0.0                              # on the walls
+        st["v_x"] = rng.uniform(-3, 3, n); st["v_y"] = rng.uniform(-3, 3, n)
+        st["x_prev"] = st["x"]; st["y_prev"] = st["y"]
+        b = Cuda(tank_w, tank_h, h, n + 64)
+        b.set_params(t); b.upload(st); b.step(6)
+        outs.append(b.download()[0])
+    for f in ("x", "y", "v_x", "v_y"):
+        assert np.array_equal(outs[0][f].view("u4"), outs[1][f].view("u4")), f
