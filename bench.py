@@ -132,19 +132,38 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # reference arm / CPU baseline: the unmodified reference on the host cores
 # ------------------------------------------------------------------------------------------------
-def run_reference_cpu(n, water_frac, steps, warmup, ranks=None, budget_s=150.0):
-    """Runs oracle/_ref/sph_ref_run (reference TUs compiled unmodified + mini-MPI).  Falls back to the
-    C restatement (oracle port, 1 core) when the reference binary is absent.  Sample is bounded so the
-    run stays within `budget_s`."""
+def host_mem_available_bytes():
+    try:
+        for line in open("/proc/meminfo"):
+            if line.startswith("MemAvailable:"):
+                return int(line.split()[1]) * 1024
+    except OSError:
+        pass
+    return 64 << 30
+
+
+def run_reference_cpu(n, water_frac, steps, warmup, ranks=None, budget_s=150.0, shipped=True):
+    """Runs the unmodified reference (reference TUs + mini-MPI, oracle/_ref/) on the host cores: `shipped` = built with
+    the flags the reference ships (-O3 -ffast-math, makefile:5: sph_ref_run_shipped), else the IEEE -O2 build that
+    defines parity (sph_ref_run).  Falls back to the C restatement (oracle port, 1 core) when no binary is there.
+    The sample is bounded by the time budget, by the reference's own 32-bit limit (2N*400 in an unsigned at
+    fluid.c:203,206 overflows above 5.3 M particles) and by the host's memory (~13 KB of touched capacity per
+    particle, fluid.c:156,202-203)."""
     from oracle.oracle import ref_binary
     cores = os.cpu_count() or 1
     exe = ref_binary()
+    if exe and shipped and os.path.exists(exe + "_shipped"):
+        exe = exe + "_shipped"
+    elif exe and shipped:
+        shipped = False
     if exe:
         ranks = ranks or max(1, min(cores, 64))
         est_rate = 0.5e6 * ranks                       # particle-steps/s, conservative (BASELINE.md section 2)
-        # bounded sample: by time, and to 2 M particles (the reference allocates ~6.6 KB of capacity per global
-        # particle PER RANK, fluid.c:156,202-203; larger samples risk the box's memory, not just its time)
-        n_s = int(min(n, 2_000_000, max(20000, est_rate * budget_s / max(steps + warmup, 1))))
+        by_time = est_rate * budget_s / max(steps + warmup, 1)
+        by_mem = 0.5 * host_mem_available_bytes() / 13e3
+        n_s = int(min(n, 5_200_000, by_mem, max(20000, by_time)))
+        bound = ("the full size" if n_s == n else "the reference's 32-bit capacity limit" if n_s == 5_200_000 else
+                 "host memory" if n_s == int(by_mem) else f"the {budget_s:.0f} s time budget")
         tank_w = problem_dims(n_s, water_frac)
         cmd = [exe, "--ranks", str(ranks), "--n", str(n_s), "--tank-w", f"{tank_w:.6f}",
                "--tank-h", f"{tank_w * 9.0 / 16.0:.6f}", "--water-frac", str(water_frac),
@@ -153,12 +172,15 @@ def run_reference_cpu(n, water_frac, steps, warmup, ranks=None, budget_s=150.0):
         out = subprocess.run(cmd, capture_output=True, text=True, timeout=budget_s * 4)
         line = [l for l in out.stdout.splitlines() if l.startswith("{")]
         if out.returncode != 0 or not line:
-            raise RuntimeError(f"sph_ref_run failed rc={out.returncode}: {out.stderr[-400:]}")
+            raise RuntimeError(f"{os.path.basename(exe)} failed rc={out.returncode}: {out.stderr[-400:]}")
         r = json.loads(line[-1])
         return {"value": r["particle_steps_per_s"], "unit": "particle-steps/s", "cores": ranks, "kind": "reference",
+                "build": "-O3 -ffast-math, the flags the reference ships (makefile:5)" if shipped else
+                         "-O2 IEEE (no fast-math, no FMA contraction): the build that defines parity",
                 "sample": f"{r['n_global']} particles x {steps} steps (+{warmup} warm-up) from the lattice, "
                           f"{ranks} compute ranks over mini-MPI, load balancer on, host has {cores} cores, "
-                          f"wall {time.time() - t0:.1f}s",
+                          f"wall {time.time() - t0:.1f}s; size bounded by {bound}"
+                          + ("" if n_s == n else f" (requested {n}: the RATE is what is compared, extrapolated)"),
                 "ms_per_step": 1e3 * r["seconds"] / max(steps, 1), "n_particles": r["n_global"]}
     # oracle port: single core
     import ctypes as C
@@ -186,14 +208,20 @@ def main_reference(args):
         return 0
     n = args.n * args.gpus
     # same initial condition and the same number of steps before the timed region as our arm
-    r = run_reference_cpu(n, args.water_frac, args.steps, args.preroll + args.warmup)
+    r = run_reference_cpu(n, args.water_frac, args.steps, args.preroll + args.warmup, shipped=True)
+    try:    # the parity build beside it, on a shorter pre-roll (same state class, bounded time)
+        ri = run_reference_cpu(n, args.water_frac, args.steps, min(args.preroll + args.warmup, 300), budget_s=40.0, shipped=False)
+        ieee = {k: ri[k] for k in ("value", "unit", "cores", "kind", "build", "sample")}
+    except Exception as e:
+        ieee = {"value": None, "sample": f"failed: {e}"}
     line = {
         "impl": "reference", "metric": "particle-steps/sec", "value": r["value"], "unit": "particle-steps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"2D dam-break block, {n} particles requested ({r['n_particles']} in the bounded sample), "
                                "preset x, CPU reference", "water_frac": args.water_frac},
-        "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "build", "sample")},
+        "cpu_baseline_ieee_build": ieee,
         "e2e": {"value": r["value"], "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -250,6 +278,11 @@ def main_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    parity = None
+    if world > 1 and not args.no_parity_check:
+        parity = slab_parity_check(sph_b200, rank, world, stream, args)
+        mark("parity check")
+    cfg3 = None
     with torch.cuda.stream(stream):
         if world == 1:
             sim = SingleGpu(sph_b200, prob, t, stream, args)
@@ -270,63 +303,119 @@ def main_ours(args):
         barrier()
         mark("warm")
         launches0 = sim.launches
+        if world > 1:
+            sim.ctx.exchange_times(reset=True)
         if os.environ.get("SPH_PROFILE"):      # ncu --profile-from-start off: instrument the timed region only
             torch.cuda.profiler.start()
-        # ---- timed region: K steps, L2 flushed between steps, device time per step from CUDA events
-        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        # ---- timed region: blocks of K steps, L2 flushed between steps, device time per step from CUDA events on the
+        # stream the steps are launched on; every block bracketed by barrier + synchronize on both sides.  The block is
+        # repeated until at least 0.5 s of device time has been measured (a single block of the driver's 20 steps is
+        # 5 ms), and the MEDIAN block is reported with the spread.
+        # Every block times the SAME steps: the state after the pre-roll is snapshotted in device memory and restored
+        # before each block (the dam-break keeps compressing -- 22 neighbours per particle after 1000 steps, 60 after
+        # 4000 -- so blocks timed one after the other would not be the same work).
+        sim.state_save()
+
+        def timed_block():
+            sim.state_restore()
+            barrier()
+            ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+            for k in range(args.steps):
+                flush_buf.zero_()
+                ev[k][0].record(stream)
+                sim.run(1)
+                ev[k][1].record(stream)
+            barrier()
+            return float(sum(a.elapsed_time(b) for a, b in ev))
+
         wall0 = time.perf_counter()
-        for k in range(args.steps):
-            flush_buf.zero_()
-            ev[k][0].record(stream)
-            sim.run(1)
-            ev[k][1].record(stream)
-        barrier()
+        block_ms = [timed_block()]
+        first_ms = block_ms[0]
+        if world > 1:
+            first = torch.tensor([first_ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(first, op=dist.ReduceOp.MAX)
+            first_ms = float(first.item())
+        repeats = int(min(args.max_repeats, max(3, -(-args.min_timed_ms // max(first_ms, 1e-3)))))
+        for _ in range(repeats - 1):
+            block_ms.append(timed_block())
         mark("timed")
         wall = time.perf_counter() - wall0
         launches = sim.launches - launches0
+        xt, n_meet = sim.ctx.exchange_times(reset=True) if world > 1 else (None, 0)
         if os.environ.get("SPH_PROFILE"):
             torch.cuda.profiler.stop()
-        step_ms = [a.elapsed_time(b) for a, b in ev]
-        total_ms = float(sum(step_ms))
+        if world > 1:
+            blocks = torch.tensor(block_ms, device="cuda", dtype=torch.float64)
+            dist.all_reduce(blocks, op=dist.ReduceOp.MAX)          # every block: the slowest rank
+            block_ms = [float(x) for x in blocks.tolist()]
+        block_ms = sorted(block_ms)
+        total_ms = statistics.median(block_ms)
         # ---- the same K steps back to back, state L2-resident (informational)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sim.state_restore()
         barrier()
         e0.record(stream); sim.run(args.steps); e1.record(stream)
         barrier()
         b2b_ms = e0.elapsed_time(e1)
         # ---- per-stage device times for the roofline (stage API, flushed between steps)
         mark("b2b")
+        sim.state_restore()
         stage_ms = sim.stage_times(min(args.steps, 20), flush_buf)
         mark("stages")
-        # ---- end to end through the frame call with host buffers
-        e2e = sim.e2e(max(3, args.steps // 4), flush_buf)
+        # ---- end to end through the frame call with host buffers: enough frames for ~0.5 s
+        e2e_frames = int(min(64, max(8, 0.5 * args.min_timed_ms / (4.0 * max(total_ms / args.steps, 1e-3)))))
+        sim.state_restore()
+        e2e = sim.e2e(e2e_frames, flush_buf)
         mark("e2e")
         clocks = sampler.stop()
+        sim.state_restore()
         stats = sim.stats()
         mark("stats")
+
+    if world == 8 and not args.no_cfg3:
+        del sim
+        try:
+            cfg3 = run_cfg3(sph_b200, rank, world, stream, args, flush_buf, barrier)
+        except Exception as e:
+            cfg3 = {"failed": repr(e)[:300]}
+        mark("cfg3")
 
     per_rank = None
     if world > 1:
         # per-slab picture: population, neighbours, pure compute time (the three gather kernels) per step
         mine = torch.tensor([stats["n_local"], stats["n_halo"], stats["mean_neighbours"],
                              1e3 * (stage_ms["advect"] + stage_ms["density"] + stage_ms["relax"]),
-                             1e3 * (stage_ms["sort1"] + stage_ms["sort2"])], device="cuda", dtype=torch.float64)
+                             1e3 * (stage_ms["sort1"] + stage_ms["sort2"]),
+                             xt["send_us"], xt["wait_us"], xt["unpack_us"], n_meet], device="cuda", dtype=torch.float64)
         allr = [torch.zeros_like(mine) for _ in range(world)]
         dist.all_gather(allr, mine)
         per_rank = [[round(float(v), 1) for v in r.tolist()] for r in allr]
-        tmax = torch.tensor([total_ms, b2b_ms, e2e["seconds"]], device="cuda", dtype=torch.float64)
+        tmax = torch.tensor([b2b_ms, e2e["seconds"], e2e.get("sync_seconds", 0.0)], device="cuda", dtype=torch.float64)
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        total_ms, b2b_ms, e2e_s = [float(x) for x in tmax.tolist()]
-        e2e["seconds"] = e2e_s
-        cnt = torch.tensor([stats["n_local"], launches], device="cuda", dtype=torch.float64)
+        b2b_ms, e2e["seconds"], sync_s = [float(x) for x in tmax.tolist()]
+        if "sync_seconds" in e2e:
+            e2e["sync_seconds"] = sync_s
+        okall = torch.tensor([1.0 if e2e.get("pipelined") else 0.0], device="cuda", dtype=torch.float64)
+        dist.all_reduce(okall, op=dist.ReduceOp.MIN)
+        e2e["pipelined"] = bool(okall.item() > 0)
+        cnt = torch.tensor([stats["n_local"], launches, stats["capacity_overflow"], stats["msg_overflow"],
+                            stats["exchange_timeouts"]], device="cuda", dtype=torch.float64)
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
         n_global = int(cnt[0].item()); launches = int(cnt[1].item())
+        integrity = {"particles_resident": n_global, "particles_created": prob["n_global"],
+                     "nobody_lost_or_duplicated": n_global == prob["n_global"],
+                     "capacity_overflow": int(cnt[2].item()), "msg_overflow": int(cnt[3].item()),
+                     "exchange_timeouts": int(cnt[4].item())}
     else:
         n_global = stats["n_local"]
+        integrity = {"particles_resident": n_global, "particles_created": prob["n_global"],
+                     "nobody_lost_or_duplicated": n_global == prob["n_global"],
+                     "capacity_overflow": stats["capacity_overflow"], "msg_overflow": stats["msg_overflow"], "exchange_timeouts": 0}
 
     if rank == 0:
         ms_per_step = total_ms / args.steps
         value = n_global * args.steps / (total_ms * 1e-3)
+        q = lambda f: block_ms[min(len(block_ms) - 1, int(f * len(block_ms)))]
         dom = max(stage_ms, key=lambda k: stage_ms[k])
         n_per_launch = stats["n_local"] + stats["n_halo"]
         dom_key = "sort" if dom.startswith("sort") else dom
@@ -341,9 +430,16 @@ def main_ours(args):
                             f"h={prob['h']:.6f}, tank {prob['tank_w']:.1f}x{prob['tank_h']:.1f}, {world} x-slab(s)",
                 "viscosity_gather": ("library default: stabilised gather (gamma 0.5) for blocks with dt*sigma >= 0.5 (goo), plain otherwise"
                                      if args.visc_stab is None else f"forced: gamma {args.visc_stab} for every block (0 = plain)"),
-                "state": f"{args.preroll} pre-roll steps + {args.warmup} warm-up steps from the lattice",
+                "state": f"{args.preroll} pre-roll steps + {args.warmup} warm-up steps from the lattice, snapshotted in device memory "
+                         "and restored before every timed block (and before the stage, e2e and statistics sections)",
                 "mean_neighbours_per_particle": stats["mean_neighbours"], "max_bucket": stats["max_bucket"],
                 "l2": "flushed between timed steps (256 MiB write, outside the per-step CUDA-event brackets)",
+                "timed_region": {"blocks": len(block_ms), "steps_per_block": args.steps, "statistic": "median block",
+                                 "block_ms_min_p10_median_p90_max": [round(x, 4) for x in (block_ms[0], q(0.1), total_ms, q(0.9), block_ms[-1])],
+                                 "spread_rel": round((q(0.9) - q(0.1)) / total_ms, 4),
+                                 "bracket": "barrier + torch.cuda.synchronize() on both sides of every block; max over ranks per block"},
+                "integrity": integrity,
+                "slab_parity": parity,
                 "l2_resident_value": n_global * args.steps / (b2b_ms * 1e-3),
                 "l2_resident_ms_per_step": b2b_ms / args.steps,
                 "wall_s_timed_region": wall,
@@ -353,8 +449,10 @@ def main_ours(args):
                 "exchanges_per_step": getattr(sim, "exchanges", None),
                 "exchange_period_steps": getattr(sim, "exchange_period", None),
                 "edge_policy": ("particle count, dead band 1/15 (renderer.c:427-477)" if args.balance == "count" else
-                                "work estimate per slab (sph_copy_load), dead band 1/40 -- NOT the reference's policy") if world > 1 else None,
-                "per_slab_[n_local,n_ghost,neighbours,gather_us,sort_us]": per_rank,
+                                "work estimate per slab (sph_copy_load), dead band 1/40 -- NOT the reference's policy" if args.balance == "cost" else
+                                "measured device time of each slab between meetings (sph_copy_work), dead band 1/100 -- NOT the reference's "
+                                "policy; the result does not depend on where the edges are") if world > 1 else None,
+                "per_slab_[n_local,n_ghost,neighbours,gather_us,sort_us,meet_send_us,meet_wait_us,meet_unpack_us,meetings_in_timed_region]": per_rank,
             },
             "roofline": {"bound": "hbm", "kernel": sim.kernel_name(dom), "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak,
@@ -376,13 +474,17 @@ def main_ours(args):
                     **({"pipelined_error": e2e["pipelined_error"]} if e2e.get("pipelined_error") else {})},
             "gpu_launches": launches,
         }
+        if cfg3 is not None:
+            line["config"]["cfg3_16m"] = cfg3
         if not args.no_cpu_baseline and world == 1:
-            try:
-                r = run_reference_cpu(args.n, args.water_frac, steps=args.cpu_steps, warmup=args.cpu_warmup, budget_s=40.0)
-                line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
-            except Exception as e:  # the baseline is reported, never fatal
-                line["cpu_baseline"] = {"value": None, "unit": "particle-steps/s", "cores": 0, "kind": "reference",
-                                        "sample": f"failed: {e}"}
+            for key, shipped in (("cpu_baseline", True), ("cpu_baseline_ieee_build", False)):
+                try:
+                    r = run_reference_cpu(args.n, args.water_frac, steps=args.cpu_steps, warmup=args.cpu_warmup, budget_s=20.0,
+                                          shipped=shipped)
+                    line[key] = {k: r[k] for k in ("value", "unit", "cores", "kind", "build", "sample")}
+                except Exception as e:  # the baseline is reported, never fatal
+                    line[key] = {"value": None, "unit": "particle-steps/s", "cores": 0, "kind": "reference",
+                                 "sample": f"failed: {e}"}
         sys.stdout.flush()
         os.dup2(real_stdout, 1)
         print(json.dumps(line), flush=True)
@@ -391,6 +493,102 @@ def main_ours(args):
         dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+def slab_parity_check(sph_b200, rank, world, stream, args, n_req=None, steps=40):
+    """Correctness evidence inside the scaling run itself: a small dam-break block on the SAME N slabs (peer-memory
+    exchange, rebalancer on, the bench's exchange period) against ONE slab on rank 0, compared per uid BIT FOR BIT."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from sph_b200.slab import SlabRunner
+    if n_req is None:
+        # 40 k particles, or enough for every slab of the block to be twice as wide as the ghost layer of the
+        # bench's exchange period (3.5 h per step between exchanges; the block is half of a tank 15 sqrt(n / 750) wide)
+        layer = 3.5 * max(args.exchange_period, 1) * 0.58
+        n_req = int(max(40000, 750 * (world * 2.0 * layer / 7.5) ** 2))
+    prob = sph_b200.make_problem(n_req, tank_w=problem_dims(n_req, args.water_frac), water_frac=args.water_frac, nranks=world)
+    t = sph_b200.default_params(prob["h"], prob["tank_w"], prob["tank_h"], args.preset)
+    t.mover_center_x = 0.4 * prob["tank_w"]                 # the mover inside the water, across slab edges
+    out = {"particles": prob["n_global"], "steps": steps, "slabs": world}
+    ok_local, a, uid, bad = 1, None, None, 0
+    try:
+        with torch.cuda.stream(stream):
+            sim = SlabRunner(prob, t, rank, world, stream, capacity_factor=3.0, balance_policy=args.balance,
+                             halo_width=args.halo_width, exchange_period=args.exchange_period)
+            sim.init_lattice()
+            sim.run(steps)
+            a, uid = sim.ctx.download()
+            st = sim.ctx.status()
+            bad = st.capacity_overflow + st.msg_overflow + st.exchange_timeouts
+        torch.cuda.synchronize()
+        del sim
+    except Exception as e:     # evidence, not a gate -- but every rank must still take part in the collectives below
+        ok_local, out["result"] = 0, f"check failed to run on rank {rank}: {e!r}"[:300]
+    try:
+        parts = [None] * world
+        dist.all_gather_object(parts, (a, uid, bad, ok_local, out.get("result")))
+        if not all(p[3] for p in parts):
+            out["result"] = next(p[4] for p in parts if not p[3])
+        elif rank == 0:
+            state = np.concatenate([p[0] for p in parts]); uids = np.concatenate([p[1] for p in parts])
+            p1 = sph_b200.make_problem(n_req, tank_w=problem_dims(n_req, args.water_frac), water_frac=args.water_frac)
+            with torch.cuda.stream(stream):
+                one = sph_b200.Context(p1["tank_w"], p1["tank_h"], p1["h"], p1["n_global"] + 64, stream=stream.cuda_stream)
+                one.set_params(t); one.init_lattice(p1)
+                # the slab runner queues a parameter block (the rebalancer's edges) in the last sub-step of every
+                # frame; its physics does not change, so the single slab just steps
+                one.step(steps)
+                ref, ru = one.download()
+            order = np.argsort(uids)
+            same_set = len(uids) == len(ru) and np.array_equal(uids[order], ru)
+            same_bits = same_set and all(np.array_equal(state[f][order].view("u4"), ref[f].view("u4")) for f in ("x", "y", "v_x", "v_y"))
+            out["result"] = ("bit-identical" if same_bits else "MISMATCH" if same_set else "PARTICLES LOST OR DUPLICATED")
+            out["overflow_or_timeout_counters"] = int(sum(p[2] for p in parts))
+    except Exception as e:
+        out["result"] = f"check failed to run: {e!r}"[:300]
+    return out
+
+
+def run_cfg3(sph_b200, rank, world, stream, args, flush_buf, barrier):
+    """BASELINE.json config 3 inside the 8-GPU run: 2 M particles per GPU = 16 M, 8 x-slabs, halo exchange and load
+    balancing on; same timing rules as the main section, shorter pre-roll."""
+    import torch
+    import torch.distributed as dist
+    from sph_b200.slab import SlabRunner
+    n_per = 2_000_000
+    prob = sph_b200.make_problem(n_per * world, tank_w=problem_dims(n_per * world, args.water_frac), water_frac=args.water_frac, nranks=world)
+    t = sph_b200.default_params(prob["h"], prob["tank_w"], prob["tank_h"], args.preset)
+    t.mover_center_x = 0.75 * prob["tank_w"]
+    preroll = min(args.preroll, 600)
+    with torch.cuda.stream(stream):
+        sim = SlabRunner(prob, t, rank, world, stream, capacity_factor=2.0, balance_policy=args.balance,
+                         halo_width=args.halo_width, exchange_period=args.exchange_period)
+        sim.init_lattice()
+        sim.run(preroll + args.warmup)
+        barrier()
+        blocks = []
+        for _ in range(5):
+            ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+            for k in range(args.steps):
+                flush_buf.zero_()
+                ev[k][0].record(stream); sim.run(1); ev[k][1].record(stream)
+            barrier()
+            blocks.append(float(sum(a.elapsed_time(b) for a, b in ev)))
+        st = sim.stats()
+    bt = torch.tensor(blocks, device="cuda", dtype=torch.float64)
+    dist.all_reduce(bt, op=dist.ReduceOp.MAX)
+    cnt = torch.tensor([st["n_local"], st["capacity_overflow"], st["msg_overflow"], st["exchange_timeouts"]], device="cuda", dtype=torch.float64)
+    dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    med = statistics.median(bt.tolist())
+    n_global = int(cnt[0].item())
+    del sim
+    return {"workload": f"2D dam-break block, {n_global} particles on {world} x-slabs, preset {args.preset}", "value": n_global * args.steps / (med * 1e-3),
+            "unit": "particle-steps/s", "ms_per_step": med / args.steps, "blocks": len(blocks), "steps_per_block": args.steps,
+            "state": f"{preroll} pre-roll + {args.warmup} warm-up steps from the lattice", "mean_neighbours_per_particle": st["mean_neighbours"],
+            "step_hbm_frac_per_gpu": ALG_BYTES["step"] * n_global / world / (med / args.steps * 1e-3) / 1e9 / measured_peak()[0],
+            "particles_resident": n_global, "particles_created": prob["n_global"], "capacity_overflow": int(cnt[1].item()),
+            "msg_overflow": int(cnt[2].item()), "exchange_timeouts": int(cnt[3].item())}
 
 
 class SingleGpu:
@@ -415,6 +613,9 @@ class SingleGpu:
     def run(self, n):
         if n > 0:
             self.ctx.step(n)
+
+    def state_save(self): self.ctx.state_save()
+    def state_restore(self): self.ctx.state_restore()
 
     def stage_times(self, nsteps, flush_buf):
         import torch
@@ -506,7 +707,8 @@ class SingleGpu:
         s = self.ctx.status()
         npairs = self.ctx.L.sph_get_pairs(self.ctx.h, None, 0)
         return {"n_local": s.n_local, "n_halo": s.n_halo, "max_bucket": s.max_bucket,
-                "mean_neighbours": 2.0 * npairs / max(s.n_local, 1)}
+                "mean_neighbours": 2.0 * npairs / max(s.n_local, 1),
+                "capacity_overflow": s.capacity_overflow, "msg_overflow": s.msg_overflow, "exchange_timeouts": 0}
 
 
 def main():
@@ -530,8 +732,13 @@ def main():
     ap.add_argument("--cpu-warmup", type=int, default=300, help="untimed steps of the cpu_baseline sample (bounded: the "
                     "reference arm, --impl reference, runs the full pre-roll)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--balance", default="count", choices=["count", "cost"],
-                    help="slab edge policy at N > 1: the reference's particle counts (default) or the optional work estimate")
+    ap.add_argument("--min-timed-ms", type=float, default=500.0, help="repeat the block of --steps timed steps until this much device time is measured")
+    ap.add_argument("--max-repeats", type=int, default=400)
+    ap.add_argument("--no-parity-check", action="store_true", help="N > 1: skip the small N-slab-vs-1-slab bit comparison before the timed region")
+    ap.add_argument("--no-cfg3", action="store_true", help="--gpus 8: skip the second timed section on BASELINE config 3 (16 M particles)")
+    ap.add_argument("--balance", default="count", choices=["count", "cost", "time"],
+                    help="slab edge policy at N > 1: the reference's particle counts (default), the optional work estimate, "
+                         "or each slab's measured device time between meetings")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

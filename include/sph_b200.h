@@ -115,8 +115,11 @@ typedef struct sph_status {
                                   * (the reference would have dropped particles, hash.c:160-165) */
     int neighbor_overflow;       /* particles with > SPH_REF_MAX_NEIGHBORS forward neighbours */
     int capacity_overflow;       /* particles dropped because `capacity` was exceeded (fatal) */
-    int msg_overflow;            /* particles that did not fit a neighbour message (fatal) */
+    int msg_overflow;            /* entries that did not fit a neighbour message: a ghost is missing on the other side, or
+                                  * an emigrant had to wait for the next exchange (it stays resident: nobody is lost) --
+                                  * either way particles were stepped without their true neighbours: size msg_capacity up */
     int migrated_left, migrated_right;   /* last step */
+    int exchange_timeouts;       /* neighbour messages that never arrived (device-side waits that gave up): the run is invalid */
     long long steps;
 } sph_status;
 
@@ -136,14 +139,23 @@ int sph_copy_n_local(sph_ctx *ctx, void *device_dst);
  * with costs instead of counts).  Results do not depend on where the edges are, so the
  * policy changes the schedule only. */
 int sph_copy_load(sph_ctx *ctx, void *device_dst);
+/* Same, four ints: {local particle count, work estimate, this slab's OWN device time since the last call [us], the time
+ * it spent waiting for its neighbours over the same span [us]} (peer-memory transport; 0, 0 otherwise).  The own time
+ * runs from the end of one wait to the end of the next send -- everything the slab did between two meetings, however
+ * long it then waited -- and feeds the OPTIONAL time-based edge policy: measured cost instead of a model of it. */
+int sph_copy_work(sph_ctx *ctx, void *device_dst);
 
 /* ---- parameters ---- */
-/* Full tunable block, as the render rank scatters it (fluid.c:293-294). Stream-ordered. */
+/* Full tunable block, as the render rank scatters it (fluid.c:293-294). Stream-ordered.
+ * On a slab (nranks > 1) in the MIDDLE of a step (between sph_advect and the step's last sph_sort) only the physics
+ * takes effect at once; the edges are queued and land with the next sph_advect, like sph_queue_params -- the window
+ * of grid columns the running step sorts into cannot move under it. */
 int sph_set_params(sph_ctx *ctx, const sph_tunable *t);
 /* Parameters that take effect between position prediction and migration of the NEXT
  * advect stage, which is where the reference's MPI_Scatterv lands (fluid.c:279-310). */
 int sph_queue_params(sph_ctx *ctx, const sph_tunable *t);
-/* Slab edges only (node_start_x / node_end_x); used by migration and halo selection. */
+/* Slab edges only (node_start_x / node_end_x); used by migration and halo selection.  On a slab only at a step
+ * boundary (SPH_ERR_STATE otherwise; see sph_set_params). */
 int sph_set_edges(sph_ctx *ctx, float node_start_x, float node_end_x);
 
 /* Stabilised viscosity gather (not in the reference).  DEFAULT: gamma = 0.5, min_dt_sigma = 0.5, i.e. it
@@ -161,6 +173,11 @@ int sph_set_edges(sph_ctx *ctx, float node_start_x, float node_end_x);
 int sph_set_viscosity_stabilisation(sph_ctx *ctx, float gamma, float min_dt_sigma);
 
 /* ---- state ---- */
+/* Snapshot of the whole resident state at a step boundary in DEVICE memory (one slot), and its restoration: the
+ * same steps can be run again (a benchmark timing identical work repeatedly; a host that rewinds).  On slabs all
+ * ranks save and restore together; the first step after a restore is an exchange step. */
+int sph_state_save(sph_ctx *ctx);
+int sph_state_restore(sph_ctx *ctx);
 /* Host AoS -> device SoA, then bins by cell so the first viscosity pass has its
  * neighbour structure (the reference starts with empty lists, fluid.c:202; velocities are
  * zero there so both give no impulse).  uid may be NULL (uid = index). */
@@ -227,6 +244,9 @@ int sph_exchanges_per_step(void);
  * steps only; between them a particle that crossed an edge stays with its owner.  The result is still the
  * single-slab result bit for bit.  Replaces 2 meetings per step of the reference (fluid.c:310-348) by 1 / E. */
 int sph_set_exchange_period(sph_ctx *ctx, int period);
+/* Peer-memory transport: microseconds the exchange kernel spent {sending, waiting for the neighbours, unpacking},
+ * summed over *meetings exchanges since the last reset (one block's view).  Synchronises the stream. */
+int sph_get_exchange_times(sph_ctx *ctx, double us[3], int *meetings, int reset);
 /* 1 if the step in progress (between sph_advect and the end of the step) is an exchange step, or, at a step
  * boundary, if the coming step will be one: a host-side transport moves the which = 0 buffers only then. */
 int sph_exchange_due(sph_ctx *ctx);

@@ -66,7 +66,7 @@ class Status(C.Structure):
     """== sph_status (include/sph_b200.h)."""
     _fields_ = [(n, C.c_int) for n in (
         "n_local", "n_halo", "max_bucket", "bucket_overflow", "neighbor_overflow",
-        "capacity_overflow", "msg_overflow", "migrated_left", "migrated_right")] + [("steps", C.c_longlong)]
+        "capacity_overflow", "msg_overflow", "migrated_left", "migrated_right", "exchange_timeouts")] + [("steps", C.c_longlong)]
 
 
 # fluid presets: fluid.c:90-97 / controls.c:344-401

@@ -51,7 +51,7 @@ class Status(C.Structure):
     """== sph_status."""
     _fields_ = [(n, C.c_int) for n in (
         "n_local", "n_halo", "max_bucket", "bucket_overflow", "neighbor_overflow",
-        "capacity_overflow", "msg_overflow", "migrated_left", "migrated_right")] + [("steps", C.c_longlong)]
+        "capacity_overflow", "msg_overflow", "migrated_left", "migrated_right", "exchange_timeouts")] + [("steps", C.c_longlong)]
 
 
 # every symbol include/sph_b200.h declares
@@ -62,7 +62,7 @@ C_ABI_SYMBOLS = (
     "sph_set_neighbors", "sph_get_cells", "sph_get_pairs", "sph_get_forward_counts",
     "sph_pack_coords", "sph_launch_count", "sph_run_frame", "sph_p2p_local_handle", "sph_p2p_connect", "sph_copy_n_local", "sph_copy_load", "sph_init_lattice",
     "sph_set_viscosity_stabilisation", "sph_pack_coords_async", "sph_coords_wait", "sph_run_frame_async",
-    "sph_exchanges_per_step", "sph_refresh_ghosts", "sph_exchange_via_host", "sph_set_exchange_period", "sph_exchange_due",
+    "sph_exchanges_per_step", "sph_refresh_ghosts", "sph_exchange_via_host", "sph_set_exchange_period", "sph_exchange_due", "sph_get_exchange_times", "sph_state_save", "sph_state_restore", "sph_copy_work",
 )
 
 _lib = None
@@ -94,7 +94,8 @@ def _bind(L):
     L.sph_set_edges.argtypes = [C.c_void_p, C.c_float, C.c_float]
     L.sph_set_viscosity_stabilisation.argtypes = [C.c_void_p, C.c_float, C.c_float]
     L.sph_create.argtypes = [C.POINTER(Config), C.POINTER(C.c_void_p)]
-    for name in ("sph_destroy", "sph_synchronize", "sph_advect", "sph_sort", "sph_density", "sph_relax", "sph_refresh_ghosts"):
+    for name in ("sph_destroy", "sph_synchronize", "sph_advect", "sph_sort", "sph_density", "sph_relax", "sph_refresh_ghosts",
+                 "sph_state_save", "sph_state_restore"):
         getattr(L, name).argtypes = [C.c_void_p]
     L.sph_step.argtypes = [C.c_void_p, C.c_int]
     L.sph_set_params.argtypes = [C.c_void_p, C.POINTER(Tunable)]
@@ -113,11 +114,13 @@ def _bind(L):
     L.sph_init_lattice.argtypes = [C.c_void_p] + [C.c_float] * 4 + [C.c_int] * 3
     L.sph_copy_n_local.argtypes = [C.c_void_p, C.c_void_p]
     L.sph_copy_load.argtypes = [C.c_void_p, C.c_void_p]
+    L.sph_copy_work.argtypes = [C.c_void_p, C.c_void_p]
     L.sph_p2p_local_handle.argtypes = [C.c_void_p, C.c_void_p]
     L.sph_p2p_connect.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.sph_exchange_buffers.argtypes = [C.c_void_p, C.c_int] + [C.POINTER(C.c_void_p)] * 4 + [C.POINTER(C.c_size_t)]
     L.sph_set_exchange_period.argtypes = [C.c_void_p, C.c_int]
     L.sph_exchange_due.argtypes = [C.c_void_p]
+    L.sph_get_exchange_times.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int), C.c_int]
     return L
 
 
@@ -191,6 +194,8 @@ class Context:
     def relax(self): self._ck(self.L.sph_relax(self.h), "sph_relax")
     def step(self, n=1): self._ck(self.L.sph_step(self.h, int(n)), "sph_step")
     def refresh_ghosts(self): self._ck(self.L.sph_refresh_ghosts(self.h), "sph_refresh_ghosts")
+    def state_save(self): self._ck(self.L.sph_state_save(self.h), "sph_state_save")
+    def state_restore(self): self._ck(self.L.sph_state_restore(self.h), "sph_state_restore")
 
     def run_frame(self, tunable, steps, coords_out):
         """One render frame (fluid.c:270-372): `steps` sub-steps, the parameter scatter landing in
@@ -236,6 +241,13 @@ class Context:
         """One-exchange build: neighbours meet every `period` steps (sph_set_exchange_period)."""
         self._ck(self.L.sph_set_exchange_period(self.h, int(period)), "sph_set_exchange_period")
 
+    def exchange_times(self, reset=True):
+        """-> ({send, wait, unpack} microseconds per meeting, meetings) since the last reset (peer-memory transport)."""
+        us = (C.c_double * 3)(); n = C.c_int()
+        self._ck(self.L.sph_get_exchange_times(self.h, us, C.byref(n), int(reset)), "sph_get_exchange_times")
+        k = max(n.value, 1)
+        return {"send_us": us[0] / k, "wait_us": us[1] / k, "unpack_us": us[2] / k}, n.value
+
     @property
     def exchange_due(self):
         return bool(self.L.sph_exchange_due(self.h))
@@ -267,6 +279,10 @@ class Context:
     def copy_load(self, device_ptr):
         """{n_local, work estimate} as two ints into device memory, stream-ordered (sph_copy_load)."""
         self._ck(self.L.sph_copy_load(self.h, device_ptr), "sph_copy_load")
+
+    def copy_work(self, device_ptr):
+        """{n_local, work estimate, own time [us], waits [us]} as four ints into device memory (sph_copy_work)."""
+        self._ck(self.L.sph_copy_work(self.h, device_ptr), "sph_copy_work")
 
     def p2p_handle(self):
         """64-byte cudaIpc handle of this rank's exchange block."""

@@ -88,6 +88,10 @@ struct sph_ctx {
     unsigned char *xchg;             // exchange block for peer-memory mode (flags + 8 message buffers)
     void *peer[2];                   // neighbours' exchange blocks mapped with cudaIpcOpenMemHandle
     int scan_grid;                   // tiles of the widest possible window
+    long long *xt;                   // k_unpack's time sums [ns]: sending, waiting, unpacking, meetings, ... (see the kernel)
+    DevParams *stage_dp;             // pinned: the two parameter blocks a captured queued-parameter step copies in
+    cudaEvent_t stage_free;          // ... and the point in the stream after which they may be rewritten
+    bool stage_busy;
     int unpack_grid;                 // k_unpack waits on the neighbour inside the kernel: grid must be fully co-resident
     short2 *coords;
     // asynchronous coordinate feed (sph_pack_coords_async): the copy of frame f drains on its own stream while the
@@ -104,16 +108,22 @@ struct sph_ctx {
     int sort_grid;                   // the sort's streaming kernels
     int grid_advect, grid_density, grid_relax;
     int size_x, size_y;
-    cudaGraphExec_t graph[4];        // whole step: index = stabilised viscosity gather + 2 * exchange step
-    bool graph_ready[4];
+    cudaGraphExec_t graph[8];        // whole step: index = stabilised viscosity gather + 2 * exchange step + 4 * queued block
+    bool graph_ready[8];
     // exchange period (one-exchange build, sph_set_exchange_period): neighbours meet every `xperiod` steps
-    int launch_per_graph[4];         // kernel launches inside each captured step
+    int launch_per_graph[8];         // kernel launches inside each captured step
     int xperiod;                     // requested
     int since_x;                     // steps since the last exchange step
     bool force_x;                    // the coming step must exchange (fresh upload, parameters set outside the queue, ...)
     bool cur_x;                      // the step in progress is an exchange step
     long long launches;
     long long steps;
+    // device-memory snapshot of the state at a step boundary (sph_state_save / sph_state_restore)
+    struct {
+        bool valid;
+        float2 *P, *Q; uint32_t *U; int *cell_start, *ord_key, *counters;
+        DevParams hp; sph_tunable tun; long long steps;
+    } snap;
     char err[256];
 };
 
@@ -180,6 +190,7 @@ extern "C" int sph_create(const sph_config *cfg, sph_ctx **out)
     if (SPH_ONE_EXCHANGE && cfg->nranks > 1 && ctx->cfg.halo_width < 3.0f)
         return fail(ctx, SPH_ERR_ARG, "one-exchange build: the ghost layer must be at least 3 h wide (4 h with the stabilised viscosity gather)");
     if (ctx->cfg.msg_capacity <= 0) ctx->cfg.msg_capacity = 1;
+    ctx->cfg.msg_capacity = (ctx->cfg.msg_capacity + 3) & ~3;       // message sections on 16-byte boundaries (copy_words)
     int ndev = 0;
     CK(cudaGetDeviceCount(&ndev));
     if (ndev == 0) return fail(ctx, SPH_ERR_CUDA, "no CUDA device: sph_b200 has no CPU path");
@@ -248,6 +259,10 @@ extern "C" int sph_create(const sph_config *cfg, sph_ctx **out)
         CK(cudaMemset(ctx->send[s], 0, mb));
         CK(cudaMemset(ctx->recv[s], 0, mb));
     }
+    CK(cudaMalloc(&ctx->xt, 8 * sizeof(long long)));
+    CK(cudaMemset(ctx->xt, 0, 8 * sizeof(long long)));
+    CK(cudaMallocHost(&ctx->stage_dp, 2 * sizeof(DevParams)));
+    CK(cudaEventCreateWithFlags(&ctx->stage_free, cudaEventDisableTiming));
     CK(cudaMalloc(&ctx->xchg, xchg_bytes(ctx->cfg.msg_capacity)));
     CK(cudaMemset(ctx->xchg, 0, xchg_bytes(ctx->cfg.msg_capacity)));
     ctx->scan_grid = (int)((ncell_max + SCAN_TILE - 1) / SCAN_TILE);
@@ -298,7 +313,7 @@ extern "C" void sph_destroy(sph_ctx *ctx)
 {
     if (!ctx) return;
     cudaStreamSynchronize(ctx->stream);
-    for (int m = 0; m < 4; m++) if (ctx->graph_ready[m]) cudaGraphExecDestroy(ctx->graph[m]);
+    for (int m = 0; m < 8; m++) if (ctx->graph_ready[m]) cudaGraphExecDestroy(ctx->graph[m]);
     cudaFree(ctx->coupling); cudaFree(ctx->dopt);
 #if SPH_RELAX_PD4
     cudaFree(ctx->pd);
@@ -319,7 +334,11 @@ extern "C" void sph_destroy(sph_ctx *ctx)
     cudaFree(ctx->tile_total); cudaFree(ctx->counters); cudaFree(ctx->dp);
     for (int s = 0; s < 2; s++) { cudaFree(ctx->send[s]); cudaFree(ctx->recv[s]); }
     for (int s = 0; s < 2; s++) if (ctx->peer[s]) cudaIpcCloseMemHandle(ctx->peer[s]);
-    cudaFree(ctx->xchg);
+    cudaFree(ctx->xchg); cudaFree(ctx->xt);
+    if (ctx->stage_dp) cudaFreeHost(ctx->stage_dp);
+    if (ctx->stage_free) cudaEventDestroy(ctx->stage_free);
+    cudaFree(ctx->snap.P); cudaFree(ctx->snap.Q); cudaFree(ctx->snap.U); cudaFree(ctx->snap.cell_start);
+    cudaFree(ctx->snap.ord_key); cudaFree(ctx->snap.counters);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -345,6 +364,18 @@ extern "C" int sph_set_params(sph_ctx *ctx, const sph_tunable *t)
 {
     if (!ctx || !t) return SPH_ERR_ARG;
     ctx->force_x = true;      // physics or edges changed outside the queue: the ghosts' validity budget starts over
+    if (ctx->cfg.nranks > 1 && ctx->stage != ST_READY) {
+        // Inside a step of a slab the window of grid columns is in use: the producing kernel has binned its particles
+        // for the edges in force when it ran, and the sort that follows must use the same ones (edges moved here would
+        // silently misplace or lose particles).  The physics takes effect now, as for a single slab; the edges are
+        // queued and land with the next sph_advect, which is where the reference's scatter puts them (fluid.c:293-310).
+        ctx->tun = *t;
+        ctx->tun.node_start_x = ctx->hp.edge_start; ctx->tun.node_end_x = ctx->hp.edge_end;
+        fill_phys(ctx->hp, *t);
+        ctx->queued = *t;
+        ctx->have_queued = true;
+        return push_params(ctx);
+    }
     return apply_params(ctx, t);
 }
 
@@ -371,6 +402,8 @@ extern "C" int sph_set_viscosity_stabilisation(sph_ctx *ctx, float gamma, float 
 extern "C" int sph_set_edges(sph_ctx *ctx, float s, float e)
 {
     if (!ctx) return SPH_ERR_ARG;
+    if (ctx->cfg.nranks > 1 && ctx->stage != ST_READY)
+        return fail(ctx, SPH_ERR_STATE, "sph_set_edges: a slab's edges can only move at a step boundary (or through sph_queue_params)");
     ctx->tun.node_start_x = s; ctx->tun.node_end_x = e;
     ctx->force_x = true;
     fill_edges(ctx, s, e);
@@ -426,6 +459,21 @@ extern "C" int sph_exchange_via_host(sph_ctx *ctx, int which, sph_sendrecv_fn fn
 extern "C" int sph_exchanges_per_step(void) { return SPH_ONE_EXCHANGE ? 1 : 2; }
 
 
+// Where the meetings' time goes (peer-memory transport): microseconds spent by the exchange kernel sending its
+// messages, waiting for the neighbours' and unpacking them, summed over `*meetings` exchanges since the last reset
+// (block 0's view; the wait is the sum of the protocol's flight time and of how much later the neighbour arrived).
+extern "C" int sph_get_exchange_times(sph_ctx *ctx, double us[3], int *meetings, int reset)
+{
+    if (!ctx || !us || !meetings) return SPH_ERR_ARG;
+    long long h[4];
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaMemcpy(h, ctx->xt, sizeof h, cudaMemcpyDeviceToHost));
+    for (int k = 0; k < 3; k++) us[k] = (double)h[k] * 1e-3;
+    *meetings = (int)h[3];
+    if (reset) CK(cudaMemset(ctx->xt, 0, sizeof h));
+    return SPH_OK;
+}
+
 // ------------------------------------------------------------------------------------------
 // peer-memory exchange: neighbours map each other's exchange block (cudaIpc) and the pack code in
 // k_advect / k_relax stores outgoing records straight into it over NVLink
@@ -452,7 +500,7 @@ extern "C" int sph_p2p_connect(sph_ctx *ctx, const void *left_handle64, const vo
         ctx->hp.remote_base[s] = (unsigned long long)ctx->peer[s];
     }
     ctx->hp.p2p = 1;
-    for (int m = 0; m < 4; m++) if (ctx->graph_ready[m]) { cudaGraphExecDestroy(ctx->graph[m]); ctx->graph_ready[m] = false; }
+    for (int m = 0; m < 8; m++) if (ctx->graph_ready[m]) { cudaGraphExecDestroy(ctx->graph[m]); ctx->graph_ready[m] = false; }
     ctx->force_x = true;
     return push_params(ctx);
 }
@@ -479,7 +527,7 @@ static int launch_sort(sph_ctx *ctx, int which, bool with_unpack = true, bool re
     if (ctx->cfg.nranks > 1 && with_unpack && (refresh || (!(SPH_ONE_EXCHANGE && which == 1) && ctx->cur_x))) {
         SPH_LAUNCH(k_unpack, ctx->unpack_grid, ctx->stream)(ctx->dp, ctx->counters, which, ctx->send[0], ctx->send[1],
                                                              ctx->recv[0], ctx->recv[1],
-                                                             sp, sq, su, ctx->cnt, ctx->t_key, ctx->t_slot);
+                                                             sp, sq, su, ctx->cnt, ctx->t_key, ctx->t_slot, ctx->xt);
         ctx->launches++;
     }
     // grids sized for the widest window (tile loops inside): a captured graph survives moving slab edges
@@ -701,10 +749,14 @@ extern "C" int sph_relax(sph_ctx *ctx)
     return SPH_OK;
 }
 
-static int launch_step(sph_ctx *ctx)
+static int launch_step(sph_ctx *ctx, bool queued)
 {
     int rc;
+    // a step in which a queued parameter block lands copies it in from pinned staging, in the two halves of
+    // sph_advect: the new edges before the prediction, everything after it (fluid.c:279-310)
+    if (queued) CK(cudaMemcpyAsync(ctx->dp, &ctx->stage_dp[0], sizeof(DevParams), cudaMemcpyHostToDevice, ctx->stream));
     if ((rc = launch_advect(ctx))) return rc;
+    if (queued) CK(cudaMemcpyAsync(ctx->dp, &ctx->stage_dp[1], sizeof(DevParams), cudaMemcpyHostToDevice, ctx->stream));
     if ((rc = launch_sort(ctx, 0))) return rc;
     if ((rc = launch_density(ctx))) return rc;
     if ((rc = launch_relax(ctx))) return rc;
@@ -720,20 +772,24 @@ extern "C" int sph_step(sph_ctx *ctx, int n)
     if (ctx->stage != ST_READY) return fail(ctx, SPH_ERR_STATE, "sph_step: state is not at a step boundary");
     int rc;
     for (int s = 0; s < n; s++) {
-        if (ctx->have_queued) {           // parameter change inside this step: run it stage by stage
-            if ((rc = sph_advect(ctx)) || (rc = sph_sort(ctx)) || (rc = sph_density(ctx)) ||
-                (rc = sph_relax(ctx)) || (rc = sph_sort(ctx))) return rc;
-            continue;
-        }
+        const bool queued = ctx->have_queued;
         if ((rc = begin_step(ctx))) return rc;
+        if (queued) {
+            // Parameter change inside this step (round 1 ran such a step stage by stage, eleven separate launches once
+            // per frame): the captured step reads the two blocks from pinned staging when it RUNS.  The staging may
+            // only be rewritten once the previous queued step has read it.
+            if (ctx->stage_busy) CK(cudaEventSynchronize(ctx->stage_free));
+            fill_edges(ctx, ctx->queued.node_start_x, ctx->queued.node_end_x);      // the prediction runs on the old physics
+            ctx->stage_dp[0] = ctx->hp;
+        }
         if ((rc = check_layer(ctx))) return rc;
-        // one captured step per variant: viscosity gather (plain / stabilised) x (exchange step or not)
-        const int m = (stabilised(ctx) ? 1 : 0) + (ctx->cur_x ? 2 : 0);
+        // one captured step per variant: viscosity gather (plain / stabilised) x exchange step or not x queued block or not
+        const int m = (stabilised(ctx) ? 1 : 0) + (ctx->cur_x ? 2 : 0) + (queued ? 4 : 0);
         if (!ctx->graph_ready[m]) {
             cudaGraph_t g;
             long long before = ctx->launches;
             CK(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
-            rc = launch_step(ctx);
+            rc = launch_step(ctx, queued);
             cudaError_t e = cudaStreamEndCapture(ctx->stream, &g);
             ctx->launch_per_graph[m] = (int)(ctx->launches - before);
             ctx->launches = before;
@@ -743,7 +799,16 @@ extern "C" int sph_step(sph_ctx *ctx, int n)
             CK(cudaGraphDestroy(g));
             ctx->graph_ready[m] = true;
         }
+        if (queued) {
+            ctx->have_queued = false;
+            ctx->tun = ctx->queued;
+            fill_phys(ctx->hp, ctx->queued);
+            ctx->stage_dp[1] = ctx->hp;
+        }
         CK(cudaGraphLaunch(ctx->graph[m], ctx->stream));
+        if (queued) { CK(cudaEventRecord(ctx->stage_free, ctx->stream)); ctx->stage_busy = true; }
+        ctx->hp.gx0 = ctx->hp.gx0_new;          // the step's first scan did the same on the device
+        ctx->hp.wx = ctx->hp.wx_new;
         ctx->launches += ctx->launch_per_graph[m];
         ctx->steps++;
         end_step(ctx);
@@ -775,6 +840,67 @@ static int ingest(sph_ctx *ctx, int n)
     ctx->n_uploaded = n;
     ctx->force_x = true;          // a fresh upload has no ghosts
     return SPH_OK;
+}
+
+// ---- snapshot in device memory -------------------------------------------------------------------------------
+// The sorted state at a step boundary (positions, velocities, uids, ghosts included; cell table; counters; the
+// parameter block with its window) copied aside, and put back later: a benchmark can time the SAME steps again and
+// again (the dam-break keeps compressing, so blocks timed one after the other are not the same work), a host can
+// rewind.  On a slab every rank restores together; message sequence numbers keep counting, and the first step after
+// a restore is an exchange step.
+extern "C" int sph_state_save(sph_ctx *ctx)
+{
+    if (!ctx) return SPH_ERR_ARG;
+    if (ctx->stage != ST_READY) return fail(ctx, SPH_ERR_STATE, "sph_state_save: state is not at a step boundary");
+    if (ctx->have_queued) return fail(ctx, SPH_ERR_STATE, "sph_state_save: a queued parameter block is pending");
+    const size_t cap = (size_t)ctx->cfg.capacity;
+    const size_t ncell = (size_t)ctx->size_x * ctx->size_y * SPH_CELL_DIV * SPH_CELL_DIV + 1;
+    if (!ctx->snap.P) {
+        CK(cudaMalloc(&ctx->snap.P, cap * sizeof(float2)));
+        CK(cudaMalloc(&ctx->snap.Q, cap * sizeof(float2)));
+        CK(cudaMalloc(&ctx->snap.U, cap * sizeof(uint32_t)));
+        CK(cudaMalloc(&ctx->snap.ord_key, cap * sizeof(int)));
+        CK(cudaMalloc(&ctx->snap.cell_start, ncell * sizeof(int)));
+        CK(cudaMalloc(&ctx->snap.counters, CN_COUNT * sizeof(int)));
+    }
+    const cudaMemcpyKind dd = cudaMemcpyDeviceToDevice;
+    CK(cudaMemcpyAsync(ctx->snap.P, ctx->P[0], cap * sizeof(float2), dd, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->snap.Q, ctx->Q[0], cap * sizeof(float2), dd, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->snap.U, ctx->U[0], cap * sizeof(uint32_t), dd, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->snap.ord_key, ctx->ord_key, cap * sizeof(int), dd, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->snap.cell_start, ctx->cell_start, ncell * sizeof(int), dd, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->snap.counters, ctx->counters, CN_COUNT * sizeof(int), dd, ctx->stream));
+    ctx->snap.hp = ctx->hp; ctx->snap.tun = ctx->tun; ctx->snap.steps = ctx->steps;
+    ctx->snap.valid = true;
+    return SPH_OK;
+}
+
+extern "C" int sph_state_restore(sph_ctx *ctx)
+{
+    if (!ctx) return SPH_ERR_ARG;
+    if (!ctx->snap.valid) return fail(ctx, SPH_ERR_STATE, "sph_state_restore: nothing saved");
+    if (ctx->stage != ST_READY) return fail(ctx, SPH_ERR_STATE, "sph_state_restore: state is not at a step boundary");
+    const size_t cap = (size_t)ctx->cfg.capacity;
+    const size_t ncell = (size_t)ctx->size_x * ctx->size_y * SPH_CELL_DIV * SPH_CELL_DIV + 1;
+    const cudaMemcpyKind dd = cudaMemcpyDeviceToDevice;
+    CK(cudaMemcpyAsync(ctx->P[0], ctx->snap.P, cap * sizeof(float2), dd, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->Q[0], ctx->snap.Q, cap * sizeof(float2), dd, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->U[0], ctx->snap.U, cap * sizeof(uint32_t), dd, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->ord_key, ctx->snap.ord_key, cap * sizeof(int), dd, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->cell_start, ctx->snap.cell_start, ncell * sizeof(int), dd, ctx->stream));
+    // counters: everything but the message sequence number (the neighbours' arrival flags only ever grow) and the
+    // cumulative error counters
+    CK(cudaMemcpyAsync(ctx->counters, ctx->snap.counters, CN_MAX_BUCKET * sizeof(int), dd, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->counters + CN_COST, ctx->snap.counters + CN_COST, sizeof(int), dd, ctx->stream));
+    const DevParams now = ctx->hp;
+    ctx->hp = ctx->snap.hp;
+    ctx->hp.p2p = now.p2p; ctx->hp.xchg_base = now.xchg_base;
+    ctx->hp.remote_base[0] = now.remote_base[0]; ctx->hp.remote_base[1] = now.remote_base[1];
+    ctx->tun = ctx->snap.tun; ctx->steps = ctx->snap.steps;
+    ctx->have_queued = false;
+    ctx->force_x = true;
+    for (int s = 0; s < 2; s++) CK(cudaMemsetAsync(ctx->send[s], 0, 16, ctx->stream));
+    return push_params(ctx);
 }
 
 extern "C" int sph_upload(sph_ctx *ctx, const sph_particle *aos, const uint32_t *uid, int n)
@@ -880,6 +1006,17 @@ extern "C" int sph_copy_load(sph_ctx *ctx, void *device_dst)
     return SPH_OK;
 }
 
+// {local particles, work estimate, this slab's own time since the last call [us], its waits over the same span [us]}
+// as four ints into DEVICE memory, stream-ordered, without synchronising; restarts the two time accumulators
+extern "C" int sph_copy_work(sph_ctx *ctx, void *device_dst)
+{
+    if (!ctx || !device_dst) return SPH_ERR_ARG;
+    SPH_LAUNCH(k_pack_work, 1, ctx->stream)(ctx->counters, ctx->xt, (int *)device_dst);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return SPH_OK;
+}
+
 extern "C" int sph_get_status(sph_ctx *ctx, sph_status *out)
 {
     if (!ctx || !out) return SPH_ERR_ARG;
@@ -905,6 +1042,7 @@ extern "C" int sph_get_status(sph_ctx *ctx, sph_status *out)
     out->neighbor_overflow = c[CN_NEIGH_OVER];
     out->capacity_overflow = c[CN_CAP_OVER];
     out->msg_overflow = c[CN_MSG_OVER];
+    out->exchange_timeouts = c[CN_TIMEOUT_MSG];
     if (c[CN_TIMEOUT_MSG])
         snprintf(ctx->err, sizeof ctx->err, "device-side waits timed out: %d neighbour messages never arrived", c[CN_TIMEOUT_MSG]);
     if (ctx->cfg.nranks > 1) {

@@ -142,6 +142,13 @@ __device__ __forceinline__ void prefetch_l1(const void *p)
 {
     asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
 }
+// nanoseconds on a clock all SMs share (clock64 is per SM)
+__device__ __forceinline__ long long global_timer_ns()
+{
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 // FMNMX.NAN: a NaN operand wins, so that a running maximum also reports "not finite"
 __device__ __forceinline__ float max_nan(float a, float b)
 {
@@ -247,6 +254,16 @@ __device__ __forceinline__ float2 boundary(float2 p, const DevParams &P)
     if (x < 0.0f) x = 0.0f; else if (x > P.tank_w) x = P.tank_w - 0.001f;   // :732-743
     if (y < 0.0f) y = 0.0f; else if (y > P.tank_h) y = P.tank_h - 0.001f;
     return make_float2(x, y);
+}
+
+// the nearest cell of the NEW window (an emigrant that could not be sent stays resident there)
+__device__ __forceinline__ int window_key_clamped(float2 p, const DevParams &P)
+{
+    int gx = sort_coord(p.x, P.cell_h) - P.gx0_new;
+    int gy = sort_coord(p.y, P.cell_h);
+    gx = min(max(gx, 0), P.wx_new - 1);
+    gy = min(max(gy, 0), P.sort_rows - 1);
+    return gy * P.wx_new + gx;
 }
 
 // key of a position in the NEW window (the one the coming sort will use), or DROP

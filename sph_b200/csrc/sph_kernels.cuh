@@ -153,12 +153,15 @@ __device__ __forceinline__ Rows candidate_rows_key(int key, const DevParams &P, 
 // (Storing each record remotely from inside the compute kernels was tried first: the scattered 8-byte
 // NVLink stores lengthened k_advect/k_relax by 30-45 us.)
 // -------------------------------------------------------------------------------------------
+// (16 bytes per store: the message capacity is a multiple of 4, so every section starts on a 16-byte boundary and
+//  is a multiple of 16 bytes long; the last store of a section may carry up to 12 stale bytes of the same section)
 __device__ __forceinline__ void copy_words(unsigned char *dst, const unsigned char *src, size_t off, int nwords,
                                            int gtid, int gstride, bool &wrote)
 {
-    const int *s = (const int *)(src + off);
-    int *d = (int *)(dst + off);
-    for (int w = gtid; w < nwords; w += gstride) { d[w] = s[w]; wrote = true; }
+    const int4 *s = (const int4 *)(src + off);
+    int4 *d = (int4 *)(dst + off);
+    const int nq = (nwords + 3) >> 2;
+    for (int w = gtid; w < nq; w += gstride) { d[w] = s[w]; wrote = true; }
 }
 
 __device__ __forceinline__ void send_messages(const DevParams &P, int *counters, int which, int step,
@@ -216,9 +219,10 @@ __device__ __forceinline__ void send_messages(const DevParams &P, int *counters,
 // bin a freshly produced position for the coming sort: key, arrival slot, cell population
 __device__ __forceinline__ void bin_position(int i, float2 p, int extra_bits, const DevParams &P,
                                              int *__restrict__ cnt, int *__restrict__ t_key,
-                                             int *__restrict__ t_slot, int *__restrict__ counters)
+                                             int *__restrict__ t_slot, int *__restrict__ counters, bool keep = false)
 {
     int key = window_key_new(p, P);
+    if (key == SPH_KEY_DROP && keep) key = window_key_clamped(p, P);
     if (key == SPH_KEY_DROP) {
         // Outside this slab's window.  For an emigrant that is fine: it has been handed to its new owner
         // and is too far away to matter as a ghost (a mover can push a particle several cells at once).
@@ -235,9 +239,10 @@ __device__ __forceinline__ void bin_position(int i, float2 p, int extra_bits, co
 // was dropped.  The caller stores it an iteration later, so that no instruction waits for the atomic's round trip.
 __device__ __forceinline__ bool bin_position_deferred(int i, float2 p, int extra_bits, const DevParams &P,
                                                       int *__restrict__ cnt, int *__restrict__ t_key, int *__restrict__ counters,
-                                                      int &slot)
+                                                      int &slot, bool keep = false)
 {
     int key = window_key_new(p, P);
+    if (key == SPH_KEY_DROP && keep) key = window_key_clamped(p, P);
     if (key == SPH_KEY_DROP) {
         if (!(extra_bits & SPH_KEY_EMIG)) atomicAdd(&counters[CN_CAP_OVER], 1);
         t_key[i] = SPH_KEY_DROP;
@@ -486,6 +491,7 @@ k_advect(const DevParams *__restrict__ Pp, int *__restrict__ counters,
         pos_pred[i] = np;
 
         int extra = ghost ? SPH_KEY_EMIG : 0;                           // a ghost advanced between exchanges stays a ghost
+        bool unsent = false;
         if (P.nranks > 1 && xstep && !ghost) {
             // identify_oob_particles: strict < start / > end (fluid.c:494-497)
             unsigned char *dst = nullptr;
@@ -499,7 +505,13 @@ k_advect(const DevParams *__restrict__ Pp, int *__restrict__ counters,
                     msg_u(dst, P.msg_cap)[k] = u;
                     extra = SPH_KEY_EMIG;
                 } else {
+                    // The message is full: this emigrant stays with this slab for now and tries again in the next
+                    // exchange step.  Its position may lie outside the slab's new window (a slab parked outside the
+                    // tank, controls.c:405-426, drains ALL its particles this way, one message capacity per exchange):
+                    // it is binned into the nearest window cell instead of being dropped.  Counted: a particle that
+                    // waits is stepped without its true neighbours, so the run is flagged, but nobody is lost.
                     atomicAdd(&counters[CN_MSG_OVER], 1);
+                    unsent = true;
                 }
             } else {
                 // ghost layer: widened to halo_w and tested per side (communication.c:137-140 uses h, else-if)
@@ -527,9 +539,9 @@ k_advect(const DevParams *__restrict__ Pp, int *__restrict__ counters,
         }
 #if SPH_PIPE
         if (slot_i >= 0) t_slot[slot_i] = slot_v;                       // the previous particle's: its atomic is back by now
-        slot_i = bin_position_deferred(i, np, extra, P, cnt, t_key, counters, slot_v) ? i : -1;
+        slot_i = bin_position_deferred(i, np, extra, P, cnt, t_key, counters, slot_v, unsent) ? i : -1;
 #else
-        bin_position(i, np, extra, P, cnt, t_key, t_slot, counters);
+        bin_position(i, np, extra, P, cnt, t_key, t_slot, counters, unsent);
 #endif
     }
 #if SPH_PIPE
@@ -631,10 +643,17 @@ __global__ void __launch_bounds__(SPH_THREADS)
 k_unpack(const DevParams *__restrict__ Pp, int *__restrict__ counters, int which,
          unsigned char *send_l, unsigned char *send_r, unsigned char *recv_l, unsigned char *recv_r,
          float2 *__restrict__ src_pos, float2 *__restrict__ src_q, uint32_t *__restrict__ src_uid,
-         int *__restrict__ cnt, int *__restrict__ t_key, int *__restrict__ t_slot)
+         int *__restrict__ cnt, int *__restrict__ t_key, int *__restrict__ t_slot, long long *__restrict__ xt)
 {
     pdl_enter();
     const DevParams P = *Pp;
+    // block 0's view of the meeting, in ns of the global timer: xt[0] sending, [1] waiting for the neighbours,
+    // [2] unpacking, [3] meetings (cumulative, sph_get_exchange_times); [4] when the last wait ended, [5] this slab's OWN
+    // time since sph_copy_work last asked -- from the end of one wait to the end of the next send, i.e. everything it
+    // did between two meetings, independent of how long it then waited -- and [6] its waits over the same span
+    const bool timer = blockIdx.x == 0 && threadIdx.x == 0;
+    long long tc0 = 0, tc1 = 0, tc2 = 0;
+    if (timer) tc0 = global_timer_ns();
     const int base = counters[CN_NTOT];
     int n_mig[2] = {0, 0}, n_halo[2] = {0, 0};
     unsigned char *buf[2] = {recv_l, recv_r};
@@ -642,6 +661,7 @@ k_unpack(const DevParams *__restrict__ Pp, int *__restrict__ counters, int which
     if (P.p2p) {
         const int step = counters[CN_STEP];
         send_messages(P, counters, which, step, send_l, send_r);
+        if (timer) tc1 = global_timer_ns();
         // wait for the neighbours' messages of this exchange: they were stored into this rank's
         // exchange block by the neighbours' k_unpack; the flag is released after the payload
         __shared__ int s_ok[2];
@@ -659,6 +679,7 @@ k_unpack(const DevParams *__restrict__ Pp, int *__restrict__ counters, int which
             s_ok[s] = ok;
         }
         __syncthreads();
+        if (timer) tc2 = global_timer_ns();
         for (int s = 0; s < 2; s++) {
             buf[s] = (unsigned char *)(P.xchg_base + xchg_offset(s, which, step & 1, P.msg_cap));
             if (!s_ok[s]) {      // treat the missing message as empty; the run is invalid and says so
@@ -710,6 +731,12 @@ k_unpack(const DevParams *__restrict__ Pp, int *__restrict__ counters, int which
         // a ghost outside this slab's window is simply not needed (a slab parked outside the tank,
         // controls.c:405-426, still receives its neighbour's edge particles): same flag as an emigrant
         bin_position(idx, p, (u & SPH_HALO_BIT) ? SPH_KEY_EMIG : 0, P, cnt, t_key, t_slot, counters);
+    }
+    if (timer && P.p2p) {
+        const long long tc3 = global_timer_ns();
+        xt[0] += tc1 - tc0; xt[1] += tc2 - tc1; xt[2] += tc3 - tc2; xt[3] += 1;
+        if (xt[4] != 0) { xt[5] += tc1 - xt[4]; xt[6] += tc2 - tc1; }
+        xt[4] = tc2;
     }
     pdl_done();
 }
@@ -1312,9 +1339,9 @@ k_relax(const DevParams *__restrict__ Pp, int *__restrict__ counters,
 #if SPH_ONE_EXCHANGE
 #if SPH_PIPE
         if (slot_i >= 0) t_slot[slot_i] = slot_v;
-        slot_i = bin_position_deferred(i, np, ghost ? SPH_KEY_EMIG : 0, P, cnt, t_key, counters, slot_v) ? i : -1;
+        slot_i = bin_position_deferred(i, np, ghost ? SPH_KEY_EMIG : 0, P, cnt, t_key, counters, slot_v, !ghost) ? i : -1;
 #else
-        bin_position(i, np, ghost ? SPH_KEY_EMIG : 0, P, cnt, t_key, t_slot, counters);
+        bin_position(i, np, ghost ? SPH_KEY_EMIG : 0, P, cnt, t_key, t_slot, counters, !ghost);
 #endif
         continue;
 #endif
@@ -1332,9 +1359,10 @@ k_relax(const DevParams *__restrict__ Pp, int *__restrict__ counters,
         }
 #if SPH_PIPE
         if (slot_i >= 0) t_slot[slot_i] = slot_v;                       // the previous particle's: its atomic is back by now
-        slot_i = bin_position_deferred(i, np, 0, P, cnt, t_key, counters, slot_v) ? i : -1;
+        // (a local outside the window can only be an emigrant that is still waiting for room in a message: kept)
+        slot_i = bin_position_deferred(i, np, 0, P, cnt, t_key, counters, slot_v, true) ? i : -1;
 #else
-        bin_position(i, np, 0, P, cnt, t_key, t_slot, counters);
+        bin_position(i, np, 0, P, cnt, t_key, t_slot, counters, true);
 #endif
     }
 #if SPH_PIPE
@@ -1414,6 +1442,21 @@ k_init_lattice(float min_x, float min_y, float spacing, int start_col, int ncols
                              __fadd_rn(min_y, __fmul_rn((float)row, spacing)));
         vel[i] = make_float2(0.0f, 0.0f);
         uid[i] = (uint32_t)(row * total_cols + start_col + col);
+    }
+}
+
+// {local particles, work estimate, own time since the last call [us], waits over the same span [us]} for the edge
+// policies (sph_copy_work); the two time accumulators start over
+__global__ void k_pack_work(const int *__restrict__ counters, long long *__restrict__ xt, int *__restrict__ out)
+{
+    pdl_enter();
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        out[0] = counters[CN_NLOCAL];
+        out[1] = counters[CN_COST];
+        const long long busy_us = xt[5] / 1000, wait_us = xt[6] / 1000;
+        out[2] = busy_us < 2000000000ll ? (int)busy_us : 2000000000;
+        out[3] = wait_us < 2000000000ll ? (int)wait_us : 2000000000;
+        xt[5] = 0; xt[6] = 0;
     }
 }
 

@@ -139,9 +139,16 @@ int sph_ref_attach(fluid_particle **pointers, param *params, AABB_t *boundary, n
     cfg.msg_capacity = 1;
     cfg.device = device; cfg.rank = 0; cfg.nranks = 1;
     if (nranks > 1) {
-        /* a message carries the ghost layer (2 h of a column of fluid) plus the migrants of one step */
+        /* A message carries the ghost layer (2 h of a column of fluid) plus the migrants of one step.  The reference
+         * sizes its out-of-bounds buffers for the GLOBAL particle count (geometry.c:87), which is what lets
+         * remove_partition drain a whole slab in one step (controls.c:405-426); so does this path while that stays
+         * affordable (40 bytes per entry and buffer), else a slab drains at one capacity per step -- nobody is lost,
+         * sph_status.msg_overflow says so.  SPH_REF_MSG_CAPACITY overrides. */
         const int rows = (int)ceilf(cfg.tank_h / cfg.h);
         cfg.msg_capacity = 30 * rows > 4096 ? 30 * rows : 4096;
+        if (params->number_fluid_particles_global > cfg.msg_capacity)
+            cfg.msg_capacity = params->number_fluid_particles_global < (4 << 20) ? params->number_fluid_particles_global : (4 << 20);
+        if (getenv("SPH_REF_MSG_CAPACITY") && atoi(getenv("SPH_REF_MSG_CAPACITY")) > 0) cfg.msg_capacity = atoi(getenv("SPH_REF_MSG_CAPACITY"));
         cfg.capacity += 2 * cfg.msg_capacity;
         cfg.rank = rank; cfg.nranks = nranks;
         G.edge_start = params->tunable_params.node_start_x;
@@ -328,14 +335,20 @@ void hash_fluid(fluid_particle **pointers, neighbor_grid_t *grid, param *params,
         G.steps_done++;
         if (G.mirror && G.steps_done % G.mirror_every == 0) {
             note("hash_fluid", sph_ref_sync_to_host(pointers, params));
-            if (G.nranks > 1) {
+            {
                 /* the reference's functions are void: what a slab could not hold or send is reported here (stderr and
-                 * sph_ref_last_error), where the host is synchronised anyway */
+                 * sph_ref_last_error), where the host is synchronised anyway.  Particles that exceeded the capacity are
+                 * GONE: like the failed attach, that ends the program unless SPH_REF_STRICT=0 asks to carry on. */
                 sph_status st;
-                if (sph_get_status(G.ctx, &st) == SPH_OK && (st.msg_overflow || st.capacity_overflow)) {
-                    snprintf(G.err, sizeof G.err, "rank %d: %d particles did not fit a neighbour message, %d exceeded the slab's capacity",
-                             G.rank, st.msg_overflow, st.capacity_overflow);
+                if (sph_get_status(G.ctx, &st) == SPH_OK && (st.msg_overflow || st.capacity_overflow || st.exchange_timeouts)) {
+                    snprintf(G.err, sizeof G.err, "rank %d: %d entries did not fit a neighbour message, %d particles exceeded the slab's capacity, "
+                             "%d neighbour messages never arrived", G.rank, st.msg_overflow, st.capacity_overflow, st.exchange_timeouts);
                     fprintf(stderr, "sph_ref_api: %s\n", G.err);
+                    const char *strict = getenv("SPH_REF_STRICT");
+                    if ((st.capacity_overflow || st.exchange_timeouts) && !(strict && strict[0] == '0')) {
+                        fprintf(stderr, "sph_ref_api: particles were lost; stopping (SPH_REF_STRICT=0 to carry on)\n");
+                        abort();
+                    }
                 }
             }
         }

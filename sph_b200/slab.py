@@ -60,8 +60,9 @@ class SlabRunner:
         self.torch, self.dist = torch, dist
         self.prob, self.rank, self.world, self.group = prob, rank, world, group
         self.steps_per_frame, self.do_balance = steps_per_frame, balance
-        assert balance_policy in ("count", "cost")
+        assert balance_policy in ("count", "cost", "time")
         self.balance_policy, self.cost_band_divisor = balance_policy, cost_band_divisor
+        self.time_band_divisor = 100.0      # "time" policy: a slab's measured time within 1 % of the mean is left alone
         self.costs = None
         self.sub_step = 0
         self.n_active = world            # slabs taking part (render_state->num_compute_procs_active)
@@ -157,19 +158,29 @@ class SlabRunner:
         return [v[0] for v in vals], [v[1] for v in vals]
 
     def sample_counts_async(self):
-        """End of a frame: all-gather the slab populations WITHOUT stalling the host.  The result is used
-        one frame later, which is the reference's own timing: its render rank balances on the counts of
-        the coordinate messages of the previous frame (renderer.c:268-290)."""
+        """End of a frame: all-gather the slab populations (and work figures) WITHOUT stalling the host or the compute
+        stream -- the collective runs on a side stream behind an event, so it is no barrier between the slabs' steps
+        (in round 1 it sat in the compute stream: every frame all ranks met there a third time).  The result is used
+        one frame later, which is the reference's own timing: its render rank balances on the counts of the
+        coordinate messages of the previous frame (renderer.c:268-290)."""
         torch, dist = self.torch, self.dist
         if not hasattr(self, "_cnt_mine"):
-            self._cnt_mine = torch.zeros(2, dtype=torch.int32, device="cuda")
-            self._cnt_all = torch.zeros(2 * self.world, dtype=torch.int32, device="cuda")
-            self._cnt_host = torch.zeros(2 * self.world, dtype=torch.int32).pin_memory()
+            self._cnt_mine = [torch.zeros(4, dtype=torch.int32, device="cuda") for _ in range(2)]
+            self._cnt_all = [torch.zeros(4 * self.world, dtype=torch.int32, device="cuda") for _ in range(2)]
+            self._cnt_host = torch.zeros(4 * self.world, dtype=torch.int32).pin_memory()
             self._cnt_event = torch.cuda.Event()
-        self.ctx.copy_load(self._cnt_mine.data_ptr())
-        dist.all_gather_into_tensor(self._cnt_all, self._cnt_mine, group=self.group)
-        self._cnt_host.copy_(self._cnt_all, non_blocking=True)
-        self._cnt_event.record(self.stream)
+            self._cnt_ready = torch.cuda.Event()
+            self._side = torch.cuda.Stream()
+            self._cnt_flip = 0
+        k = self._cnt_flip = 1 - self._cnt_flip
+        cur = self.stream if self.stream is not None else torch.cuda.current_stream()
+        self.ctx.copy_work(self._cnt_mine[k].data_ptr())
+        self._cnt_ready.record(cur)
+        with torch.cuda.stream(self._side):
+            self._side.wait_event(self._cnt_ready)
+            dist.all_gather_into_tensor(self._cnt_all[k], self._cnt_mine[k], group=self.group)
+            self._cnt_host.copy_(self._cnt_all[k], non_blocking=True)
+            self._cnt_event.record(self._side)
         self._cnt_pending = True
 
     def rebalance(self):
@@ -181,12 +192,18 @@ class SlabRunner:
                 return                                  # first frame: nothing sampled yet
             self._cnt_event.synchronize()               # recorded a frame ago: already complete
             both = [int(c) for c in self._cnt_host.tolist()]
-            counts, costs = both[0::2], both[1::2]
+            counts, costs, busy, waits = both[0::4], both[1::4], both[2::4], both[3::4]
         else:
             counts, costs = self.gather_counts()
-        self.counts, self.costs = counts, costs
+            busy = waits = [0] * self.world
+        self.counts, self.costs, self.busy_us, self.wait_us = counts, costs, busy, waits
         old_edges = list(self.edges)
-        if self.balance_policy == "cost":
+        active = busy[:self.n_active]
+        if self.balance_policy == "time" and min(active) > 0:
+            # same edge arithmetic, fed with each slab's MEASURED device time between its meetings (sph_copy_work):
+            # whatever makes a slab slow -- denser fluid, more ghosts, a mover, a slower GPU -- it gives up columns
+            self.edges = sph_b200.balance(self.edges, busy, self.prob["h"], self.n_active, band_divisor=self.time_band_divisor)
+        elif self.balance_policy == "cost":
             # same edge arithmetic, fed with the work estimate (scaled to stay far from int overflow)
             self.edges = sph_b200.balance(self.edges, [c >> 4 for c in costs], self.prob["h"], self.n_active,
                                           band_divisor=self.cost_band_divisor)
@@ -266,6 +283,17 @@ class SlabRunner:
         for _ in range(n):
             self.step_once()
 
+    def state_save(self):
+        """Snapshot in device memory (sph_state_save) + this driver's own bookkeeping; every rank together."""
+        self.ctx.state_save()
+        self._saved = (list(self.edges), self.sub_step, self.n_active, self.t.copy(), getattr(self, "_cnt_pending", False))
+
+    def state_restore(self):
+        self.ctx.state_restore()
+        edges, self.sub_step, self.n_active, t, pending = self._saved
+        self.edges, self.t = list(edges), t.copy()
+        self._cnt_pending = False        # counts sampled after the snapshot belong to a future that is being undone
+
     # -------------------------------------------------------------------------------- bench hooks
     @property
     def launches(self):
@@ -303,26 +331,63 @@ class SlabRunner:
                 "sort2": "k_unpack+k_scan_totals+k_scan_apply+k_scatter+k_reorder"}[stage]
 
     def e2e(self, frames, flush_buf):
-        """Frames with host buffers: parameter block H2D (queued, lands at the last sub-step), 4 steps, the
-        slab's int16 coordinates D2H into pinned memory (fluid.c:354-365)."""
-        torch = self.torch
-        coords = torch.empty(2 * self.capacity, dtype=torch.int16).pin_memory().numpy()
-        secs, n = 0.0, 0
-        for f in range(frames + 1):
+        """Frames with host buffers, pipelined like the reference's MPI_Isend of its frame (fluid.c:283-287, :354-365) and
+        like the single-GPU bench: per frame a parameter block H2D (queued by the rebalancer, lands at the last sub-step),
+        4 steps, the slab's int16 coordinates D2H into pinned memory; frame f is collected after frame f+1 has been
+        submitted.  One host clock per rank around all frames (the bench takes the max over ranks).  The synchronous
+        protocol (sph_pack_coords after every frame, L2 flushed before it) is timed too and reported beside it."""
+        torch, np_ = self.torch, np
+        bufs = [torch.empty(2 * self.capacity, dtype=torch.int16).pin_memory().numpy() for _ in range(2)]
+        c = self.ctx
+        # synchronous protocol (a few frames are enough for the comparison figure)
+        sync_frames = max(3, min(frames, 12))
+        secs_sync, n = 0.0, 0
+        for f in range(sync_frames + 1):
             flush_buf.zero_()
             torch.cuda.synchronize()
             self.dist.barrier()
             t0 = time.perf_counter()
             self.run(self.steps_per_frame)
-            n = self.ctx.L.sph_pack_coords(self.ctx.h, coords.ctypes.data, self.capacity)
+            n = c.L.sph_pack_coords(c.h, bufs[0].ctypes.data, self.capacity)
             if f > 0:
-                secs += time.perf_counter() - t0
-        return {"seconds": secs, "steps": self.steps_per_frame * frames, "h2d_per_step": 64 / self.steps_per_frame,
-                "d2h_per_step": 4 * n / self.steps_per_frame}
+                secs_sync += time.perf_counter() - t0
+        out = {"seconds": secs_sync * frames / sync_frames, "steps": self.steps_per_frame * frames,
+               "h2d_per_step": 64 / self.steps_per_frame, "d2h_per_step": 4 * n / self.steps_per_frame, "pipelined": False}
+        try:
+            for f in range(2):
+                self.run(self.steps_per_frame)
+                c.coords_wait(c.pack_coords_async(bufs[f]))
+            torch.cuda.synchronize()
+            self.dist.barrier()
+            tickets = []
+            t0 = time.perf_counter()
+            for f in range(frames):
+                self.run(self.steps_per_frame)
+                tickets.append(c.pack_coords_async(bufs[f % 2]))
+                if f > 0:
+                    n = c.coords_wait(tickets[f - 1])
+            n = c.coords_wait(tickets[-1])
+            secs = time.perf_counter() - t0
+            # the last frame must be what the synchronous call packs from the same state (a slab packs its particles in
+            # the order an atomic cursor hands out: compare as sets of coordinate pairs)
+            last = bufs[(frames - 1) % 2][:2 * n].reshape(n, 2).copy()
+            ref = c.pack_coords()
+            key = lambda a: np_.sort(a[:, 0].astype("i4") * 65536 + a[:, 1].astype("i4"))
+            if len(ref) == n and np_.array_equal(key(last), key(ref)):
+                # a slab does not know its population on the host without a stall: its whole coordinate buffer travels
+                out = {"seconds": secs, "steps": self.steps_per_frame * frames, "h2d_per_step": 64 / self.steps_per_frame,
+                       "d2h_per_step": 4 * self.capacity / self.steps_per_frame, "pipelined": True,
+                       "sync_seconds": secs_sync * frames / sync_frames}
+            else:
+                out["pipelined_error"] = "last frame differs from the synchronous feed"
+        except Exception as e:      # the synchronous number stands
+            out["pipelined_error"] = repr(e)[:200]
+        return out
 
     def stats(self):
         s = self.ctx.status()
         npairs = self.ctx.L.sph_get_pairs(self.ctx.h, None, 0) if self.cuda else 0
         return {"n_local": s.n_local, "n_halo": s.n_halo, "max_bucket": s.max_bucket,
                 "mean_neighbours": 2.0 * npairs / max(s.n_local + s.n_halo, 1),
-                "capacity_overflow": s.capacity_overflow, "msg_overflow": s.msg_overflow}
+                "capacity_overflow": s.capacity_overflow, "msg_overflow": s.msg_overflow,
+                "exchange_timeouts": getattr(s, "exchange_timeouts", 0)}

@@ -219,7 +219,8 @@ cudaError_t cudaMemsetAsync(void *p, int v, size_t bytes, cudaStream_t s)
 cudaError_t cudaMemcpy(void *d, const void *s, size_t bytes, cudaMemcpyKind) { memmove(d, s, bytes); return cudaSuccess; }
 cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t bytes, cudaMemcpyKind, cudaStream_t st)
 {
-    if (capturing(st)) return cudaErrorStreamCaptureUnsupported;
+    // captured: a memcpy node, which reads its source when the graph RUNS (the library's queued-parameter step)
+    if (capturing(st)) { st->capturing->nodes.emplace_back(1, 32, [=]() { if (threadIdx.x == 0) memmove(d, s, bytes); }); return cudaSuccess; }
     memmove(d, s, bytes);
     return cudaSuccess;
 }

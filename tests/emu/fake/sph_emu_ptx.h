@@ -5,6 +5,7 @@
 #pragma once
 static inline float rcp_approx(float x) { return 1.0f / x; }
 static inline void prefetch_l1(const void *) {}
+static inline long long global_timer_ns() { return clock64(); }
 static inline float max_nan(float a, float b) { return (a != a || b != b) ? NAN : (a > b ? a : b); }
 struct f32x2 { float lo, hi; };
 static inline f32x2 pk2(float lo, float hi) { return f32x2{lo, hi}; }

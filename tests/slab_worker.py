@@ -46,6 +46,7 @@ def main():
 
     sim = SlabRunner(prob, t, rank, world, backend=backend, balance=bool(balance), balance_policy=policy,
                      exchange_period=int(os.environ.get("SPH_EMU_XPERIOD", "1")),
+                     msg_capacity=int(os.environ.get("SPH_EMU_MSG_CAPACITY", "0")) or None,
                      halo_width=float(os.environ.get("SPH_EMU_HALO_WIDTH", "0")) or None)
     sim.init_lattice()
     history = []

@@ -140,3 +140,75 @@ def test_exchange_period_equals_single_slab_bit_for_bit(tmp_path, built_lib, mon
     order = np.argsort(uid)
     for f in ("x", "y", "v_x", "v_y"):
         assert np.array_equal(state[f][order].view("u4"), ref[f].view("u4")), f
+
+
+def test_parked_slab_with_a_small_message_capacity_drains_without_losing_anyone(tmp_path, built_lib, monkeypatch):
+    """A slab parked outside the tank (controls.c:405-426) hands over ALL its particles, and its window of grid columns
+    leaves the tank with it.  With a message capacity below its population the emigrants that do not fit must stay
+    resident (binned into the nearest window cell) and follow in the next steps -- round 1 dropped them for good
+    (314 of 1508 at capacity 400).  Nobody is lost; msg_overflow says that particles had to wait."""
+    monkeypatch.setenv("SPH_EMU_MSG_CAPACITY", "400")
+    steps = 200
+    parts = run_world(tmp_path, 3, 1500, steps, True, "emu_elastic")
+    uid = np.concatenate([p["uid"] for p in parts])
+    assert np.array_equal(np.sort(uid), np.arange(1508)), (len(uid), len(np.unique(uid)))
+    assert all(int(p["overflow"][0]) == 0 for p in parts), [p["overflow"] for p in parts]      # capacity_overflow: none lost
+    assert sum(int(p["overflow"][1]) for p in parts) > 0                                       # emigrants did wait
+    drained = [h for h in parts[2]["history"] if h[0] == -1]
+    assert drained and drained[0][1] == 0, "the parked slab still held particles when it was added back"
+    assert len(parts[2]["uid"]) > 100, "the re-added slab did not refill"
+
+
+def test_parameters_set_in_the_middle_of_a_slab_step_do_not_move_the_window_under_the_sort(built_lib, monkeypatch):
+    """sph_set_params between sph_advect and sph_sort on a slab whose edges move by 3 h: round 1 re-derived the window
+    at once, the sort then ran with keys binned for the OLD window, and 91 of 1508 particles vanished with
+    capacity_overflow still 0.  Now the physics applies at once and the edges land with the next sph_advect;
+    sph_set_edges in mid-step is refused."""
+    import sph_b200
+    from emu.backend import use_emulator
+    from oracle.oracle import lattice
+    monkeypatch.setattr(sph_b200, "_lib", sph_b200._lib)      # use_emulator() rebinds the module's library: undone after the test
+    sph = use_emulator()
+    prob = make_problem(1500, nranks=2)
+    h = prob["h"]
+    ctxs = []
+    for r in range(2):
+        a, uid = lattice(prob, r)
+        c = sph.Context(prob["tank_w"], prob["tank_h"], h, 4096, msg_capacity=2048, rank=r, nranks=2)
+        t = sph.default_params(h, prob["tank_w"], prob["tank_h"])
+        t.node_start_x, t.node_end_x = prob["slabs"][r][2], prob["slabs"][r][3]
+        c.set_params(t); c.upload(a, uid)
+        ctxs.append((c, t))
+
+    def exchange(which):
+        bufs = [[np.ctypeslib.as_array((sph.C.c_ubyte * nb).from_address(p)) for p in ptrs]
+                for ptrs, nb in (c.exchange_pointers(which) for c, _ in ctxs)]
+        bufs[1][1][:] = bufs[0][2]      # rank 1 receives from its left what rank 0 sent to its right
+        bufs[0][3][:] = bufs[1][0]      # and the other way round
+
+    shift = 3 * h
+    for step in range(12):
+        for c, _ in ctxs:
+            c.advect()
+        if step == 5:
+            for r, (c, t) in enumerate(ctxs):
+                t2 = t.copy()
+                if r == 0: t2.node_end_x = t.node_end_x + shift
+                else: t2.node_start_x = t.node_start_x + shift
+                with pytest.raises(sph.SphError):
+                    c.set_edges(t2.node_start_x, t2.node_end_x)
+                c.set_params(t2)
+                ctxs[r] = (c, t2)
+        exchange(0)
+        for c, _ in ctxs:
+            c.sort(); c.density(); c.relax()
+        exchange(1)
+        for c, _ in ctxs:
+            c.sort()
+    uid = np.concatenate([c.download()[1] for c, _ in ctxs])
+    assert np.array_equal(np.sort(uid), np.arange(1508)), len(uid)
+    for c, _ in ctxs:
+        st = c.status()
+        assert st.capacity_overflow == 0 and st.msg_overflow == 0
+    # the edges did move: rank 0 now owns more than its half
+    assert ctxs[0][0].status().n_local > 1508 // 2 + 100
