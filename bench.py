@@ -289,7 +289,8 @@ def main_ours(args):
         else:
             from sph_b200.slab import SlabRunner
             sim = SlabRunner(prob, t, rank, world, stream, capacity_factor=2.0, balance_policy=args.balance,
-                             halo_width=args.halo_width, exchange_period=args.exchange_period)
+                             halo_width=args.halo_width, exchange_period=args.exchange_period,
+                             exchanges_per_step=args.exchanges_per_step)
         if args.visc_stab is not None:                  # default: the library's (gamma 0.5 for blocks with dt*sigma >= 0.5)
             sim.ctx.set_viscosity_stabilisation(args.visc_stab)
         mark("created")
@@ -515,7 +516,8 @@ def slab_parity_check(sph_b200, rank, world, stream, args, n_req=None, steps=40)
     try:
         with torch.cuda.stream(stream):
             sim = SlabRunner(prob, t, rank, world, stream, capacity_factor=3.0, balance_policy=args.balance,
-                             halo_width=args.halo_width, exchange_period=args.exchange_period)
+                             halo_width=args.halo_width, exchange_period=args.exchange_period,
+                             exchanges_per_step=args.exchanges_per_step)
             sim.init_lattice()
             sim.run(steps)
             a, uid = sim.ctx.download()
@@ -563,7 +565,8 @@ def run_cfg3(sph_b200, rank, world, stream, args, flush_buf, barrier):
     preroll = min(args.preroll, 600)
     with torch.cuda.stream(stream):
         sim = SlabRunner(prob, t, rank, world, stream, capacity_factor=2.0, balance_policy=args.balance,
-                         halo_width=args.halo_width, exchange_period=args.exchange_period)
+                         halo_width=args.halo_width, exchange_period=args.exchange_period,
+                             exchanges_per_step=args.exchanges_per_step)
         sim.init_lattice()
         sim.run(preroll + args.warmup)
         barrier()
@@ -726,8 +729,11 @@ def main():
     ap.add_argument("--visc-stab", type=float, default=None, metavar="GAMMA",
                     help="force the stabilised viscosity gather with this gamma for every block (0 = plain gather everywhere); "
                          "default: the library's own rule (gamma 0.5 where dt*sigma >= 0.5, i.e. the goo preset, DESIGN.md 5b)")
-    ap.add_argument("--exchange-period", type=int, default=1,
-                    help="N > 1, one-exchange build: neighbours meet every this many steps (ghost layer 3.5 h per step)")
+    ap.add_argument("--exchanges-per-step", type=int, default=1, choices=[1, 2],
+                    help="N > 1: 2 = neighbours meet after the prediction and after the relaxation, like the reference (fluid.c:310-348); "
+                         "1 = once, ghosts relaxed redundantly (default)")
+    ap.add_argument("--exchange-period", type=int, default=2,
+                    help="N > 1, one exchange per step: neighbours meet every this many steps (ghost layer 3.5 h per step; default 2)")
     ap.add_argument("--cpu-steps", type=int, default=20, help="timed steps of the cpu_baseline sample")
     ap.add_argument("--cpu-warmup", type=int, default=300, help="untimed steps of the cpu_baseline sample (bounded: the "
                     "reference arm, --impl reference, runs the full pre-roll)")
@@ -736,12 +742,14 @@ def main():
     ap.add_argument("--max-repeats", type=int, default=400)
     ap.add_argument("--no-parity-check", action="store_true", help="N > 1: skip the small N-slab-vs-1-slab bit comparison before the timed region")
     ap.add_argument("--no-cfg3", action="store_true", help="--gpus 8: skip the second timed section on BASELINE config 3 (16 M particles)")
-    ap.add_argument("--balance", default="count", choices=["count", "cost", "time"],
-                    help="slab edge policy at N > 1: the reference's particle counts (default), the optional work estimate, "
-                         "or each slab's measured device time between meetings")
+    ap.add_argument("--balance", default="time", choices=["count", "cost", "time"],
+                    help="slab edge policy at N > 1: each slab's measured device time between meetings (default), the reference's "
+                         "particle counts (renderer.c:427-477), or the modelled work estimate; results are identical bit for bit")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
+    if args.exchanges_per_step == 2:
+        args.exchange_period = 1
     if args.impl == "reference":
         return main_reference(args)
     return main_ours(args)

@@ -105,6 +105,9 @@ typedef struct sph_config {
     int rank, nranks;        /* slab index / number of slabs; nranks == 1: no exchange */
     float halo_width;        /* ghost-layer width in units of h; 0 -> default 2.0 */
     void *stream;            /* cudaStream_t to run on, or NULL for a private stream */
+    int exchanges_per_step;  /* slabs: 2 = neighbours meet after the prediction and after the relaxation (ghost layer 2 h);
+                              * 1 = once, the ghosts are relaxed redundantly (layer >= 3.5 h; sph_set_exchange_period makes it
+                              * once every E steps); 0 = the build's default (2) */
 } sph_config;
 
 /* what the reference silently drops (hash.c:160-165, :188-197, :223-232) is counted here */
@@ -234,7 +237,8 @@ int sph_refresh_ghosts(sph_ctx *ctx);
 /* Exchanges per step of this build: 2 (which = 0 after sph_advect, which = 1 after sph_relax), or 1 for the
  * one-exchange build variant (-DSPH_ONE_EXCHANGE=1), whose ghosts are relaxed redundantly and which needs
  * halo_width >= 3 (4 with the stabilised viscosity gather); the driver then skips the which = 1 transfer. */
-int sph_exchanges_per_step(void);
+int sph_exchanges_per_step(void);                       /* the build's default */
+int sph_ctx_exchanges_per_step(const sph_ctx *ctx);    /* this context's (sph_config.exchanges_per_step) */
 /* Exchange period (one-exchange build): neighbours meet every `period` steps instead of every step; in between a
  * slab advances its ghosts itself, redundantly and bit for bit as their owner does.  Every pair pass invalidates
  * one h of the layer from the outside, so a period of E steps needs halo_width >= 3.5 * E (4.5 * E while the

@@ -59,7 +59,7 @@ class Config(C.Structure):
     _fields_ = [("tank_w", C.c_float), ("tank_h", C.c_float), ("h", C.c_float),
                 ("capacity", C.c_int), ("msg_capacity", C.c_int), ("device", C.c_int),
                 ("rank", C.c_int), ("nranks", C.c_int), ("halo_width", C.c_float),
-                ("stream", C.c_void_p)]
+                ("stream", C.c_void_p), ("exchanges_per_step", C.c_int)]
 
 
 class Status(C.Structure):

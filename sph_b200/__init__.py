@@ -44,7 +44,7 @@ class Config(C.Structure):
     _fields_ = [("tank_w", C.c_float), ("tank_h", C.c_float), ("h", C.c_float),
                 ("capacity", C.c_int), ("msg_capacity", C.c_int), ("device", C.c_int),
                 ("rank", C.c_int), ("nranks", C.c_int), ("halo_width", C.c_float),
-                ("stream", C.c_void_p)]
+                ("stream", C.c_void_p), ("exchanges_per_step", C.c_int)]
 
 
 class Status(C.Structure):
@@ -62,7 +62,7 @@ C_ABI_SYMBOLS = (
     "sph_set_neighbors", "sph_get_cells", "sph_get_pairs", "sph_get_forward_counts",
     "sph_pack_coords", "sph_launch_count", "sph_run_frame", "sph_p2p_local_handle", "sph_p2p_connect", "sph_copy_n_local", "sph_copy_load", "sph_init_lattice",
     "sph_set_viscosity_stabilisation", "sph_pack_coords_async", "sph_coords_wait", "sph_run_frame_async",
-    "sph_exchanges_per_step", "sph_refresh_ghosts", "sph_exchange_via_host", "sph_set_exchange_period", "sph_exchange_due", "sph_get_exchange_times", "sph_state_save", "sph_state_restore", "sph_copy_work",
+    "sph_exchanges_per_step", "sph_refresh_ghosts", "sph_exchange_via_host", "sph_set_exchange_period", "sph_exchange_due", "sph_get_exchange_times", "sph_state_save", "sph_state_restore", "sph_copy_work", "sph_ctx_exchanges_per_step",
 )
 
 _lib = None
@@ -115,6 +115,7 @@ def _bind(L):
     L.sph_copy_n_local.argtypes = [C.c_void_p, C.c_void_p]
     L.sph_copy_load.argtypes = [C.c_void_p, C.c_void_p]
     L.sph_copy_work.argtypes = [C.c_void_p, C.c_void_p]
+    L.sph_ctx_exchanges_per_step.argtypes = [C.c_void_p]
     L.sph_p2p_local_handle.argtypes = [C.c_void_p, C.c_void_p]
     L.sph_p2p_connect.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.sph_exchange_buffers.argtypes = [C.c_void_p, C.c_int] + [C.POINTER(C.c_void_p)] * 4 + [C.POINTER(C.c_size_t)]
@@ -132,11 +133,12 @@ class Context:
     """One slab of the simulation resident on one GPU (sph_ctx)."""
 
     def __init__(self, tank_w, tank_h, h, capacity, msg_capacity=1, device=0, rank=0, nranks=1,
-                 halo_width=2.0, stream=None):
+                 halo_width=0.0, stream=None, exchanges_per_step=0):
+        """halo_width 0: the mode's default (2 h; 3.5 h with one exchange per step).  exchanges_per_step 0: the build's default."""
         self.L = lib()
         self.capacity = int(capacity)
         self.cfg = Config(tank_w, tank_h, h, int(capacity), int(msg_capacity), device, rank, nranks,
-                          halo_width, stream)
+                          halo_width, stream, int(exchanges_per_step))
         self.h = C.c_void_p()
         rc = self.L.sph_create(C.byref(self.cfg), C.byref(self.h))
         if rc != 0:
@@ -235,7 +237,7 @@ class Context:
 
     @property
     def exchanges_per_step(self):
-        return int(self.L.sph_exchanges_per_step())
+        return int(self.L.sph_ctx_exchanges_per_step(self.h))
 
     def set_exchange_period(self, period):
         """One-exchange build: neighbours meet every `period` steps (sph_set_exchange_period)."""

@@ -116,6 +116,7 @@ struct sph_ctx {
     int since_x;                     // steps since the last exchange step
     bool force_x;                    // the coming step must exchange (fresh upload, parameters set outside the queue, ...)
     bool cur_x;                      // the step in progress is an exchange step
+    bool one_x;                      // one exchange per step (sph_config.exchanges_per_step)
     long long launches;
     long long steps;
     // device-memory snapshot of the state at a step boundary (sph_state_save / sph_state_restore)
@@ -186,8 +187,10 @@ extern "C" int sph_create(const sph_config *cfg, sph_ctx **out)
     memset(ctx, 0, sizeof *ctx);
     *out = ctx;
     ctx->cfg = *cfg;
-    if (ctx->cfg.halo_width <= 0.0f) ctx->cfg.halo_width = SPH_ONE_EXCHANGE ? 3.5f : 2.0f;
-    if (SPH_ONE_EXCHANGE && cfg->nranks > 1 && ctx->cfg.halo_width < 3.0f)
+    if (cfg->exchanges_per_step < 0 || cfg->exchanges_per_step > 2) return SPH_ERR_ARG;
+    ctx->one_x = cfg->exchanges_per_step == 1 || (cfg->exchanges_per_step == 0 && SPH_ONE_EXCHANGE);
+    if (ctx->cfg.halo_width <= 0.0f) ctx->cfg.halo_width = ctx->one_x ? 3.5f : 2.0f;
+    if (ctx->one_x && cfg->nranks > 1 && ctx->cfg.halo_width < 3.0f)
         return fail(ctx, SPH_ERR_ARG, "one-exchange build: the ghost layer must be at least 3 h wide (4 h with the stabilised viscosity gather)");
     if (ctx->cfg.msg_capacity <= 0) ctx->cfg.msg_capacity = 1;
     ctx->cfg.msg_capacity = (ctx->cfg.msg_capacity + 3) & ~3;       // message sections on 16-byte boundaries (copy_words)
@@ -292,6 +295,7 @@ extern "C" int sph_create(const sph_config *cfg, sph_ctx **out)
     P.halo_w = ctx->cfg.halo_width * cfg->h;
     P.has_left = cfg->rank > 0; P.has_right = cfg->rank < cfg->nranks - 1; P.nranks = cfg->nranks;
     P.cap = cfg->capacity; P.msg_cap = ctx->cfg.msg_capacity;
+    P.one_x = ctx->one_x ? 1 : 0;
     P.p2p = 0; P.xchg_base = (unsigned long long)ctx->xchg; P.remote_base[0] = P.remote_base[1] = 0;
     {   // device-side waits give up after this long (default 10 s) instead of hanging the GPU
         const char *ms = getenv("SPH_SPIN_TIMEOUT_MS");
@@ -456,7 +460,8 @@ extern "C" int sph_exchange_via_host(sph_ctx *ctx, int which, sph_sendrecv_fn fn
 
 // how often neighbours meet per step in this build: 2 (after the prediction and after the relaxation), or 1 in the
 // one-exchange build, where a multi-rank driver skips the second transfer
-extern "C" int sph_exchanges_per_step(void) { return SPH_ONE_EXCHANGE ? 1 : 2; }
+extern "C" int sph_exchanges_per_step(void) { return SPH_ONE_EXCHANGE ? 1 : 2; }        // the build's default
+extern "C" int sph_ctx_exchanges_per_step(const sph_ctx *ctx) { return ctx && ctx->one_x ? 1 : 2; }
 
 
 // Where the meetings' time goes (peer-memory transport): microseconds spent by the exchange kernel sending its
@@ -524,7 +529,7 @@ static int launch_sort(sph_ctx *ctx, int which, bool with_unpack = true, bool re
     uint32_t *du = which == 0 ? ctx->U[1] : ctx->U[0];
     // (one-exchange build: nothing arrives after the relaxation, the ghosts were relaxed here)
     // (refresh: sph_refresh_ghosts always brings its ghosts in the which = 1 format)
-    if (ctx->cfg.nranks > 1 && with_unpack && (refresh || (!(SPH_ONE_EXCHANGE && which == 1) && ctx->cur_x))) {
+    if (ctx->cfg.nranks > 1 && with_unpack && (refresh || (!(ctx->one_x && which == 1) && ctx->cur_x))) {
         SPH_LAUNCH(k_unpack, ctx->unpack_grid, ctx->stream)(ctx->dp, ctx->counters, which, ctx->send[0], ctx->send[1],
                                                              ctx->recv[0], ctx->recv[1],
                                                              sp, sq, su, ctx->cnt, ctx->t_key, ctx->t_slot, ctx->xt);
@@ -579,7 +584,7 @@ static int effective_period(const sph_ctx *ctx, const sph_tunable *coming)
 static int begin_step(sph_ctx *ctx)
 {
     if (ctx->cfg.nranks <= 1) { ctx->cur_x = false; return SPH_OK; }
-    if (!SPH_ONE_EXCHANGE) { ctx->cur_x = true; return SPH_OK; }
+    if (!ctx->one_x) { ctx->cur_x = true; return SPH_OK; }
     const sph_tunable *coming = ctx->have_queued ? &ctx->queued : nullptr;
     const int period = effective_period(ctx, coming);
     // a queued block lands between this step's prediction and its exchange (fluid.c:279-310): meeting in that same
@@ -604,8 +609,8 @@ static void end_step(sph_ctx *ctx)
 extern "C" int sph_set_exchange_period(sph_ctx *ctx, int period)
 {
     if (!ctx || period < 1) return SPH_ERR_ARG;
-    if (period > 1 && !SPH_ONE_EXCHANGE)
-        return fail(ctx, SPH_ERR_STATE, "sph_set_exchange_period: this build exchanges twice per step (build with -DSPH_ONE_EXCHANGE=1)");
+    if (period > 1 && !ctx->one_x)
+        return fail(ctx, SPH_ERR_STATE, "sph_set_exchange_period: this context exchanges twice per step (create it with exchanges_per_step = 1)");
     ctx->xperiod = period;
     ctx->force_x = true;
     return SPH_OK;
@@ -616,7 +621,7 @@ extern "C" int sph_exchange_due(sph_ctx *ctx)
 {
     if (!ctx || ctx->cfg.nranks <= 1) return 0;
     if (ctx->stage != ST_READY) return ctx->cur_x ? 1 : 0;
-    if (!SPH_ONE_EXCHANGE) return 1;
+    if (!ctx->one_x) return 1;
     return (ctx->force_x || ctx->have_queued ||
             ctx->since_x + 1 >= effective_period(ctx, ctx->have_queued ? &ctx->queued : nullptr)) ? 1 : 0;
 }
@@ -672,12 +677,9 @@ static int launch_relax(sph_ctx *ctx)
 // layer of the two-exchange build but not this one's.
 static int check_layer(sph_ctx *ctx)
 {
-#if SPH_ONE_EXCHANGE
-    if (ctx->hp.has_left && ctx->hp.has_right && ctx->hp.edge_end > ctx->hp.edge_start &&
+    if (ctx->one_x && ctx->hp.has_left && ctx->hp.has_right && ctx->hp.edge_end > ctx->hp.edge_start &&
         ctx->hp.edge_end - ctx->hp.edge_start < ctx->hp.halo_w)
-        return fail(ctx, SPH_ERR_STATE, "one-exchange build: interior slab narrower than the ghost layer");
-#endif
-    (void)ctx;
+        return fail(ctx, SPH_ERR_STATE, "one-exchange mode: interior slab narrower than the ghost layer");
     return SPH_OK;
 }
 

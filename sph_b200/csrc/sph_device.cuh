@@ -36,6 +36,7 @@ struct DevParams {
     // peer-memory exchange (NVLink): this rank's exchange block and the neighbours' blocks as mapped
     // into this process (cudaIpc); 0 = use the local send/recv buffers and an external transport
     int p2p;
+    int one_x;                       // one-exchange mode: ghosts travel with x_prev and are relaxed (and advanced) redundantly
     unsigned long long xchg_base;
     unsigned long long remote_base[2];
     long long spin_timeout;          // clock64 cycles a device-side wait may last before it gives up and flags an error
@@ -69,7 +70,8 @@ enum {
 // over the dam-break's states, i.e. about 14 neighbour-equivalents per entry.
 #define SPH_COST_BASE 14
 
-// SPH_ONE_EXCHANGE=1 (build variant): neighbours meet ONCE per step (or every E steps, sph_set_exchange_period).  The ghosts
+// One-exchange mode (sph_config.exchanges_per_step = 1; -DSPH_ONE_EXCHANGE=1 makes it the build's default):
+// neighbours meet ONCE per step (or every E steps, sph_set_exchange_period).  The ghosts
 // of exchange 0 carry x_prev as well, the ghost layer is >= 3h wide, and k_relax relaxes the ghosts redundantly
 // (those within layer - 2h of the edge come out exactly as on their owner: same neighbours, same order), so the
 // next k_advect has its neighbours' velocities without the second message.
@@ -78,7 +80,7 @@ enum {
 #endif
 
 // neighbour message: 16-byte header {n_migrants, n_halo, 0, 0} then SoA sections sized by msg_cap
-__host__ __device__ inline size_t msg_bytes_full(int m) { return 16 + (size_t)m * (SPH_ONE_EXCHANGE ? 40 : 32); }
+__host__ __device__ inline size_t msg_bytes_full(int m) { return 16 + (size_t)m * 40; }     // (the last 8 bytes per slot: one-exchange mode)
 __host__ __device__ inline size_t msg_bytes_halo1(int m) { return 16 + (size_t)m * 20; }
 __device__ __forceinline__ int *msg_hdr(unsigned char *b) { return (int *)b; }
 __device__ __forceinline__ float2 *msg_a(unsigned char *b) { return (float2 *)(b + 16); }                       // migrant pos / halo-1 pos

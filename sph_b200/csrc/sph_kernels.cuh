@@ -184,9 +184,7 @@ __device__ __forceinline__ void send_messages(const DevParams &P, int *counters,
             copy_words(remote, local[s], 16 + (size_t)m * 16, n_mig, gtid, gstride, wrote);         // migrant uid
             copy_words(remote, local[s], 16 + (size_t)m * 20, n_halo * 2, gtid, gstride, wrote);    // ghost pos
             copy_words(remote, local[s], 16 + (size_t)m * 28, n_halo, gtid, gstride, wrote);        // ghost uid
-#if SPH_ONE_EXCHANGE
-            copy_words(remote, local[s], 16 + (size_t)m * 32, n_halo * 2, gtid, gstride, wrote);    // ghost x_prev
-#endif
+            if (P.one_x) copy_words(remote, local[s], 16 + (size_t)m * 32, n_halo * 2, gtid, gstride, wrote);    // ghost x_prev
         } else {
             copy_words(remote, local[s], 16, n_halo * 2, gtid, gstride, wrote);                     // ghost pos
             copy_words(remote, local[s], 16 + (size_t)m * 8, n_halo * 2, gtid, gstride, wrote);     // ghost vel
@@ -309,13 +307,10 @@ k_advect(const DevParams *__restrict__ Pp, int *__restrict__ counters,
             if (nx < n) { prefetch_l1(uid + nx); prefetch_l1(pos + nx); prefetch_l1(vel + nx); prefetch_l1(ckey + nx); }
         }
 #endif
-#if SPH_ONE_EXCHANGE
+        // ghosts are replaced at every exchange; in the one-exchange mode there are steps without one (exchange period > 1),
+        // in which a ghost is advanced here like everything else
         const bool ghost = (u & SPH_HALO_BIT) != 0;
-        if (ghost && xstep) { t_key[i] = SPH_KEY_DROP; continue; }      // ghosts are replaced at every exchange
-#else
-        const bool ghost = false;
-        if (u & SPH_HALO_BIT) { t_key[i] = SPH_KEY_DROP; continue; }   // ghosts are replaced every exchange
-#endif
+        if (ghost && (xstep || !P.one_x)) { t_key[i] = SPH_KEY_DROP; continue; }
 #if !SPH_PIPE
         const float2 p = pos[i];
         const float2 v0 = vel[i];
@@ -519,9 +514,7 @@ k_advect(const DevParams *__restrict__ Pp, int *__restrict__ counters,
                     int k = atomicAdd(&msg_hdr(send_l)[1], 1);
                     if (k < P.msg_cap) {
                         msg_hp(send_l, P.msg_cap)[k] = np; msg_hu(send_l, P.msg_cap)[k] = u;
-#if SPH_ONE_EXCHANGE
-                        msg_hq(send_l, P.msg_cap)[k] = p;
-#endif
+                        if (P.one_x) msg_hq(send_l, P.msg_cap)[k] = p;
                     }
                     else atomicAdd(&counters[CN_MSG_OVER], 1);
                 }
@@ -529,9 +522,7 @@ k_advect(const DevParams *__restrict__ Pp, int *__restrict__ counters,
                     int k = atomicAdd(&msg_hdr(send_r)[1], 1);
                     if (k < P.msg_cap) {
                         msg_hp(send_r, P.msg_cap)[k] = np; msg_hu(send_r, P.msg_cap)[k] = u;
-#if SPH_ONE_EXCHANGE
-                        msg_hq(send_r, P.msg_cap)[k] = p;
-#endif
+                        if (P.one_x) msg_hq(send_r, P.msg_cap)[k] = p;
                     }
                     else atomicAdd(&counters[CN_MSG_OVER], 1);
                 }
@@ -713,11 +704,8 @@ k_unpack(const DevParams *__restrict__ Pp, int *__restrict__ counters, int which
         uint32_t u;
         if (which == 0 && !is_mig) {
             p = msg_hp(buf[s], P.msg_cap)[k];
-#if SPH_ONE_EXCHANGE
-            q = msg_hq(buf[s], P.msg_cap)[k];                           // the ghost will be relaxed here too
-#else
-            q = make_float2(0.0f, 0.0f);
-#endif
+            q = P.one_x ? msg_hq(buf[s], P.msg_cap)[k]                  // the ghost will be relaxed here too
+                        : make_float2(0.0f, 0.0f);
             u = msg_hu(buf[s], P.msg_cap)[k] | SPH_HALO_BIT;
         } else {
             p = msg_a(buf[s])[k];
@@ -1098,11 +1086,9 @@ k_relax(const DevParams *__restrict__ Pp, int *__restrict__ counters,
         const float2 di = dens[i];
         const int key_i = ckey[i];
 #endif
-#if SPH_ONE_EXCHANGE
-        const bool ghost = (u & SPH_HALO_BIT) != 0;     // relaxed redundantly and kept as a ghost for the coming k_advect
-#else
-        if (u & SPH_HALO_BIT) { t_key[i] = SPH_KEY_DROP; continue; }
-#endif
+        // one-exchange mode: a ghost is relaxed redundantly and kept as a ghost for the coming k_advect
+        const bool ghost = (u & SPH_HALO_BIT) != 0;
+        if (ghost && !P.one_x) { t_key[i] = SPH_KEY_DROP; continue; }
 #if !SPH_PIPE
         const float2 p = pos[i];
         const float2 di = dens[i];
@@ -1336,15 +1322,15 @@ k_relax(const DevParams *__restrict__ Pp, int *__restrict__ counters,
         const float2 v = make_float2(clamp5(__fdiv_rn(np.x - pv.x, dt)), clamp5(__fdiv_rn(np.y - pv.y, dt)));
         pos_out[i] = np;
         vel_out[i] = v;
-#if SPH_ONE_EXCHANGE
+        if (P.one_x) {
 #if SPH_PIPE
-        if (slot_i >= 0) t_slot[slot_i] = slot_v;
-        slot_i = bin_position_deferred(i, np, ghost ? SPH_KEY_EMIG : 0, P, cnt, t_key, counters, slot_v, !ghost) ? i : -1;
+            if (slot_i >= 0) t_slot[slot_i] = slot_v;
+            slot_i = bin_position_deferred(i, np, ghost ? SPH_KEY_EMIG : 0, P, cnt, t_key, counters, slot_v, !ghost) ? i : -1;
 #else
-        bin_position(i, np, ghost ? SPH_KEY_EMIG : 0, P, cnt, t_key, t_slot, counters, !ghost);
+            bin_position(i, np, ghost ? SPH_KEY_EMIG : 0, P, cnt, t_key, t_slot, counters, !ghost);
 #endif
-        continue;
-#endif
+            continue;
+        }
         if (P.nranks > 1) {
             if (P.has_left && np.x - P.edge_start <= P.halo_w) {
                 int k = atomicAdd(&msg_hdr(send_l)[1], 1);
@@ -1470,10 +1456,21 @@ k_pack_coords(const DevParams *__restrict__ Pp, int *__restrict__ counters, cons
     pdl_enter();
     const DevParams P = *Pp;
     const int n = counters[CN_NTOT];
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        if (uid[i] & SPH_HALO_BIT) continue;
-        int k = P.nranks > 1 ? atomicAdd(&counters[CN_COORDS], 1) : i;
-        if (k >= cap) continue;
+    const int lane = threadIdx.x & 31;
+    for (int base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
+        const int i = base + threadIdx.x;
+        const bool mine = i < n && !(uid[i] & SPH_HALO_BIT);
+        int k = i;
+        if (P.nranks > 1) {
+            // a slab's locals are compacted: ONE atomic per warp on the cursor (a million atomics on a single address
+            // made the multi-GPU frame 25 % longer than its four steps)
+            const unsigned m = __ballot_sync(0xffffffffu, mine);
+            int first = 0;
+            if (lane == 0 && m) first = atomicAdd(&counters[CN_COORDS], __popc(m));
+            first = __shfl_sync(0xffffffffu, first, 0);
+            k = first + __popc(m & ((1u << lane) - 1u));
+        }
+        if (!mine || k >= cap) continue;
         const float2 p = pos[i];
         float fx = __fmul_rn(__fsub_rn(__fdiv_rn(__fmul_rn(2.0f, p.x), P.tank_w), 1.0f), 32767.0f);
         float fy = __fmul_rn(__fsub_rn(__fdiv_rn(__fmul_rn(2.0f, p.y), P.tank_h), 1.0f), 32767.0f);

@@ -54,7 +54,8 @@ def keep_slabs_wider_than(old, new, min_width, nactive):
 class SlabRunner:
     def __init__(self, prob, tunable, rank, world, stream=None, capacity_factor=2.0, backend=None,
                  msg_capacity=None, steps_per_frame=4, balance=True, group=None, transport="p2p",
-                 async_counts=True, balance_policy="count", cost_band_divisor=40.0, halo_width=None, exchange_period=1):
+                 async_counts=True, balance_policy="count", cost_band_divisor=40.0, halo_width=None, exchange_period=1,
+                 exchanges_per_step=0):
         import torch
         import torch.distributed as dist
         self.torch, self.dist = torch, dist
@@ -88,7 +89,8 @@ class SlabRunner:
             self.ctx = sph_b200.Context(prob["tank_w"], prob["tank_h"], prob["h"], self.capacity,
                                         msg_capacity=self.msg_capacity, device=torch.cuda.current_device(),
                                         rank=rank, nranks=world, halo_width=halo_width or 0.0,
-                                        stream=stream.cuda_stream if stream is not None else None)
+                                        stream=stream.cuda_stream if stream is not None else None,
+                                        exchanges_per_step=1 if self.exchange_period > 1 else exchanges_per_step)
             self.cuda = True
         else:
             self.ctx = backend(prob["tank_w"], prob["tank_h"], prob["h"], self.capacity, self.msg_capacity, rank, world)

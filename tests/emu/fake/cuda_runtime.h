@@ -110,6 +110,10 @@ static inline int __shfl_up_sync(unsigned, int v, int o)
 {
     return (int)emu_warp_collective(v, [o](long long *s, long long *r) { for (int i = 0; i < 32; i++) r[i] = i >= o ? s[i - o] : s[i]; });
 }
+static inline int __shfl_sync(unsigned, int v, int src)
+{
+    return (int)emu_warp_collective(v, [src](long long *s, long long *r) { for (int i = 0; i < 32; i++) r[i] = s[src & 31]; });
+}
 static inline int __shfl_xor_sync(unsigned, int v, int o)
 {
     return (int)emu_warp_collective(v, [o](long long *s, long long *r) { for (int i = 0; i < 32; i++) r[i] = s[i ^ o]; });

@@ -141,3 +141,52 @@ def check_tight_vs_gather_oracle(make, make_oracle, name, warm, steps=1):
         grow = 4 ** s      # rounding differences are amplified by the dynamics from step to step
         assert np.abs(a["x"] - r["x"]).max() <= tol * grow and np.abs(a["y"] - r["y"]).max() <= tol * grow, ("relax", s)
         assert np.abs(a["v_x"] - r["v_x"]).max() <= tol * grow / t.time_step * 1.5, ("vel", s)
+
+
+def check_state_snapshot(make_ctx, as_sph):
+    """sph_state_save / sph_state_restore: the steps after a restore are the steps after the save, bit for bit (graph
+    and staged paths, a parameter change in between undone too)."""
+    import sph_b200
+    z, t, tank_w, tank_h, h, _ = load_golden("block3000")
+    st = z["w150_state"]
+    c = make_ctx(tank_w, tank_h, h, len(st) + 64)
+    ts = as_sph(t)
+    c.set_params(ts); c.upload(st); c.step(7)
+    c.state_save()
+    c.step(9)
+    a, ua = c.download(order=sph_b200.ORDER_CELL)
+    t2 = ts.copy(); t2.k = 0.5; t2.mover_center_x = 0.3 * tank_w
+    c.set_params(t2); c.step(3)
+    c.state_restore()
+    c.step(5); c.advect(); c.sort(); c.density(); c.relax(); c.sort(); c.step(3)
+    b, ub = c.download(order=sph_b200.ORDER_CELL)
+    assert np.array_equal(ua, ub)
+    for f in ("x", "y", "v_x", "v_y"):
+        assert np.array_equal(a[f].view("u4"), b[f].view("u4")), f
+
+
+def check_clamped_impulses(make, make_oracle):
+    """A violent goo state -- every second particle thrown at up to 5 units/s against its neighbours -- in which the +-5
+    clamp of a pair's impulse (fluid.c:459) binds for many pairs: the trimmed candidate loop of k_advect must fall back
+    to its exact body for those rows and agree with the gather oracle's clamped impulses."""
+    z, t, tank_w, tank_h, h, _ = load_golden("goo_rect1508")
+    st = z["w300_state"].copy()
+    rng = np.random.default_rng(5)
+    st["v_x"] = np.where(np.arange(len(st)) % 2 == 0, 5.0, -5.0).astype("f4") * rng.uniform(0.5, 1.0, len(st)).astype("f4")
+    st["v_y"] = rng.uniform(-5, 5, len(st)).astype("f4")
+    b = make(tank_w, tank_h, h, len(st) + 64); o = make_oracle(tank_w, tank_h, h, len(st) + 64)
+    for s in (b, o):
+        s.set_params(t); s.upload(st)
+        s.advect(); s.sort()
+    a, ua = b.download(); r, ur = o.download()
+    assert np.array_equal(ua, ur)
+    # predicted positions = x + v dt: a unit of velocity error is dt = 8.3e-3 of position
+    assert np.abs(a["x"] - r["x"]).max() <= 1e-5 and np.abs(a["y"] - r["y"]).max() <= 1e-5
+    x, y, vx, vy = (st[f].astype("f8") for f in ("x", "y", "v_x", "v_y"))
+    dx = x[None, :] - x[:, None]; dy = y[None, :] - y[:, None]
+    rr = np.hypot(dx, dy); np.fill_diagonal(rr, np.inf)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        u = ((vx[:, None] - vx[None, :]) * dx + (vy[:, None] - vy[None, :]) * dy) / rr
+        imp = 0.5 * t.time_step * (1 - rr / h) * (t.sigma * u + t.beta * u * u)
+    binds = (rr <= h) & (u > 0) & ((np.abs(imp * dx / rr) > 2.5) | (np.abs(imp * dy / rr) > 2.5))
+    assert binds.sum() > 20, binds.sum()

@@ -19,6 +19,9 @@ def main():
     out, n_req, steps = sys.argv[1], int(sys.argv[2]), int(sys.argv[3])
     transport = sys.argv[4] if len(sys.argv) > 4 else "p2p"
     goo = len(sys.argv) > 5 and sys.argv[5] == "goo_stabilised"     # preset y with the stabilised viscosity gather
+    # "onex:E:policy": one exchange per step, neighbours meet every E steps, edge policy count / cost / time
+    onex = next((a for a in sys.argv[5:] if a.startswith("onex:")), None)
+    period, policy = (int(onex.split(":")[1]), onex.split(":")[2]) if onex else (1, "count")
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
     dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ["LOCAL_RANK"])))
@@ -30,7 +33,8 @@ def main():
     with torch.cuda.stream(stream):
         # (a one-exchange build of the library needs one more h of ghost layer with the stabilised gather)
         halo = 4.5 if goo and sph_b200.lib().sph_exchanges_per_step() == 1 else None
-        sim = SlabRunner(prob, t, rank, world, stream, transport=transport, halo_width=halo)
+        sim = SlabRunner(prob, t, rank, world, stream, transport=transport, halo_width=halo, exchange_period=period,
+                         exchanges_per_step=1 if onex else 0, balance_policy=policy)
         if goo:
             sim.ctx.set_viscosity_stabilisation(0.5)
         sim.init_lattice()

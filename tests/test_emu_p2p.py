@@ -26,7 +26,10 @@ def spin_timeout(monkeypatch):
 def test_peer_memory_slab_steps_equal_single_slab_bit_for_bit(built_lib, monkeypatch, world, goo, one_exchange, period):
     """period > 1 (sph_set_exchange_period): the graph of a step exists with and without the exchange kernel, and the
     message sequence numbers / buffer parity advance with the EXCHANGES, not with the steps."""
-    lib = build_emu(defines=("SPH_ONE_EXCHANGE=1",), name="libsph_emu_sph_one_exchange1.so") if one_exchange else build_emu()
+    # one exchange per step is a mode of the context (sph_config.exchanges_per_step = 1) or the default of a
+    # -DSPH_ONE_EXCHANGE=1 build: the cases with a period of 2 take the first route on the DEFAULT build
+    runtime_mode = one_exchange and period == 2
+    lib = build_emu(defines=("SPH_ONE_EXCHANGE=1",), name="libsph_emu_sph_one_exchange1.so") if one_exchange and not runtime_mode else build_emu()
     monkeypatch.setattr(sph_b200, "_lib", sph_b200._bind(C.CDLL(lib)))
     halo = (4.5 if goo else 3.5) * period if one_exchange else 2.0
     n_req, steps = 3000, 80
@@ -45,7 +48,7 @@ def test_peer_memory_slab_steps_equal_single_slab_bit_for_bit(built_lib, monkeyp
     for r in range(world):
         a, uid = lattice(prob, r)
         c = sph_b200.Context(prob["tank_w"], prob["tank_h"], prob["h"], 2 * len(a) + 4096, msg_capacity=2048,
-                             device=r, rank=r, nranks=world, halo_width=halo)
+                             device=r, rank=r, nranks=world, halo_width=halo, exchanges_per_step=1 if runtime_mode else 0)
         assert c.exchanges_per_step == (1 if one_exchange else 2)
         if period > 1:
             c.set_exchange_period(period)

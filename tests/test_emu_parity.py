@@ -15,6 +15,7 @@ import subprocess
 import numpy as np
 import pytest
 
+import parity_checks as pc
 import sph_b200
 import test_gpu_parity as gpu
 import test_zy_gpu_stabilised_and_feed as late
@@ -108,22 +109,8 @@ def test_results_do_not_depend_on_block_or_thread_order(built_lib, monkeypatch, 
 
 
 def test_state_snapshot_restores_the_same_future(built_lib):
-    """sph_state_save / sph_state_restore: the steps after a restore are the steps after the save, bit for bit (graph
-    and staged paths, a parameter change in between undone too)."""
-    from common import load_golden
-    z, t, tank_w, tank_h, h, _ = load_golden("block3000")
-    st = z["w150_state"]
-    c = sph_b200.Context(tank_w, tank_h, h, len(st) + 64)
-    ts = gpu.as_sph(t)
-    c.set_params(ts); c.upload(st); c.step(7)
-    c.state_save()
-    c.step(9)
-    a, ua = c.download(order=sph_b200.ORDER_CELL)
-    t2 = ts.copy(); t2.k = 0.5; t2.mover_center_x = 0.3 * tank_w
-    c.set_params(t2); c.step(3)
-    c.state_restore()
-    c.step(5); c.advect(); c.sort(); c.density(); c.relax(); c.sort(); c.step(3)
-    b, ub = c.download(order=sph_b200.ORDER_CELL)
-    assert np.array_equal(ua, ub)
-    for f in ("x", "y", "v_x", "v_y"):
-        assert np.array_equal(a[f].view("u4"), b[f].view("u4")), f
+    pc.check_state_snapshot(sph_b200.Context, gpu.as_sph)
+
+
+def test_clamped_impulses_take_the_exact_rows(built_lib):
+    pc.check_clamped_impulses(gpu.mk, gpu.make_oracle)
