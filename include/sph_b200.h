@@ -116,7 +116,9 @@ typedef struct sph_status {
     int max_bucket;              /* largest population of a reference bucket (cell of side h) in the current state */
     int bucket_overflow;         /* buckets above SPH_REF_MAX_BUCKET now, or sub-cells above it in any earlier sort
                                   * (the reference would have dropped particles, hash.c:160-165) */
-    int neighbor_overflow;       /* particles with > SPH_REF_MAX_NEIGHBORS forward neighbours */
+    int neighbor_overflow;       /* particles whose reference forward list (owner rule of hash.c:178-224) would exceed
+                                  * SPH_REF_MAX_NEIGHBORS in the current state; exact.  (Between a producing kernel and its
+                                  * sort: the density kernels' conservative running count instead.) */
     int capacity_overflow;       /* particles dropped because `capacity` was exceeded (fatal) */
     int msg_overflow;            /* entries that did not fit a neighbour message: a ghost is missing on the other side, or
                                   * an emigrant had to wait for the next exchange (it stays resident: nobody is lost) --

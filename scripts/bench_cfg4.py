@@ -35,7 +35,7 @@ def main():
     b.set_params(ts)
     n0 = b.init_lattice(prob)
     bufs = [torch.empty(2 * (n0 + 4096), dtype=torch.int16).pin_memory().numpy() for _ in range(2)]
-    phases, tickets, f = [], [], 0
+    phases, prev, f = [], None, 0
     for cyc in range(a.cycles):
         for preset in "abxy":
             torch.cuda.synchronize()
@@ -43,11 +43,12 @@ def main():
             for _ in range(a.frames_per_preset):
                 L.sph_host_mover_autopilot_ex(C.byref(ts), prob["tank_w"], prob["tank_h"], C.byref(gl_x), C.byref(direction), dx_gl)
                 L.sph_host_preset(C.byref(ts), preset.encode())
-                tickets.append(b.run_frame_async(ts, 4, bufs[f % 2]))
-                if f > 0:
-                    b.coords_wait(tickets[f - 1])
+                ticket = b.run_frame_async(ts, 4, bufs[f % 2])        # frame f goes in ...
+                if prev is not None:
+                    b.coords_wait(prev)                               # ... before frame f-1 is collected
+                prev = ticket
                 f += 1
-            b.coords_wait(tickets[-1]); tickets[-1] = None
+            b.coords_wait(prev); prev = None
             torch.cuda.synchronize()
             secs = time.perf_counter() - t0
             st = b.status()
@@ -55,7 +56,6 @@ def main():
                            "launches_per_frame": (b.launches - l0) / a.frames_per_preset, "max_bucket": st.max_bucket,
                            "bucket_overflow": st.bucket_overflow, "neighbor_overflow": st.neighbor_overflow,
                            "mean_neighbours": 2.0 * b.L.sph_get_pairs(b.h, None, 0) / n0})
-            tickets = [None] * f
     out, u = b.download()
     ok = bool(np.array_equal(u, np.arange(n0, dtype=u.dtype)) and np.all(np.isfinite(out["x"])) and np.all(np.abs(out["v_x"]) <= 5.0))
     total_steps = 4 * a.frames_per_preset * len(phases)

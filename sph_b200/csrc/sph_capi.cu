@@ -84,6 +84,7 @@ struct sph_ctx {
     int *cnt, *cell_start, *t_key, *t_slot, *ord_src, *ord_key;
     uint32_t *ord_uid;
     int *tile_total;                 // one population total per scan tile
+    int ntiles_max;
     unsigned char *send[2], *recv[2];
     unsigned char *xchg;             // exchange block for peer-memory mode (flags + 8 message buffers)
     void *peer[2];                   // neighbours' exchange blocks mapped with cudaIpcOpenMemHandle
@@ -249,6 +250,7 @@ extern "C" int sph_create(const sph_config *cfg, sph_ctx **out)
     CK(cudaMalloc(&ctx->ord_uid, cap * sizeof(uint32_t)));
     CK(cudaMalloc(&ctx->coords, cap * sizeof(short2)));
     const size_t ntiles_max = (ncell_max + SCAN_TILE - 1) / SCAN_TILE + 1;
+    ctx->ntiles_max = (int)ntiles_max;
     CK(cudaMalloc(&ctx->tile_total, ntiles_max * sizeof(int)));
     CK(cudaMemset(ctx->tile_total, 0, ntiles_max * sizeof(int)));
     CK(cudaMemset(ctx->cnt, 0, (ncell_max + 1) * sizeof(int)));
@@ -532,21 +534,24 @@ static int launch_sort(sph_ctx *ctx, int which, bool with_unpack = true, bool re
     if (ctx->cfg.nranks > 1 && with_unpack && (refresh || (!(ctx->one_x && which == 1) && ctx->cur_x))) {
         SPH_LAUNCH(k_unpack, ctx->unpack_grid, ctx->stream)(ctx->dp, ctx->counters, which, ctx->send[0], ctx->send[1],
                                                              ctx->recv[0], ctx->recv[1],
-                                                             sp, sq, su, ctx->cnt, ctx->t_key, ctx->t_slot, ctx->xt);
+                                                             sp, sq, su, ctx->cnt, ctx->t_key, ctx->t_slot, ctx->xt, ctx->tile_total);
         ctx->launches++;
     }
     // grids sized for the widest window (tile loops inside): a captured graph survives moving slab edges
     const int sgrid = std::max(1, std::min(ctx->scan_grid, SPH_GRID_MULT_SORT * 148));
+#if !SPH_TILE_ATOMICS
     SPH_LAUNCH(k_scan_totals, sgrid, ctx->stream)(ctx->dp, ctx->counters, ctx->cnt, ctx->tile_total);
+    ctx->launches++;
+#endif
     SPH_LAUNCH(k_scan_apply, sgrid, ctx->stream)(ctx->dp, ctx->counters, ctx->cnt, ctx->cell_start, ctx->tile_total,
                                                          ctx->cfg.nranks > 1 ? ctx->send[0] : nullptr,
                                                          ctx->cfg.nranks > 1 ? ctx->send[1] : nullptr,
                                                          (which == 1 && with_unpack && (refresh || ctx->cur_x)) ? 1 : 0);
     SPH_LAUNCH(k_scatter, ctx->sort_grid, ctx->stream)(ctx->counters, ctx->cell_start, ctx->t_key, ctx->t_slot, su,
-                                                          ctx->ord_uid, ctx->ord_src, ctx->ord_key);
+                                                          ctx->ord_uid, ctx->ord_src, ctx->ord_key, ctx->tile_total, ctx->ntiles_max);
     SPH_LAUNCH(k_reorder, ctx->sort_grid, ctx->stream)(ctx->dp, ctx->counters, ctx->cell_start, ctx->ord_key,
                                                           ctx->ord_uid, ctx->ord_src, sp, sq, dp, dq, du);
-    ctx->launches += 4;
+    ctx->launches += 3;
     ctx->hp.gx0 = ctx->hp.gx0_new;     // the scan kernel did the same on the device
     ctx->hp.wx = ctx->hp.wx_new;
     CK(cudaGetLastError());
@@ -633,14 +638,14 @@ static int launch_advect(sph_ctx *ctx)
         SPH_LAUNCH(k_coupling, ctx->grid_advect, ctx->stream)(ctx->dp, ctx->counters, ctx->P[0], ctx->Q[0], ctx->cell_start, ctx->coupling, ctx->ord_key);
         SPH_LAUNCH(k_advect<true>, ctx->grid_advect, ctx->stream)(ctx->dp, ctx->counters, ctx->P[0], ctx->Q[0], ctx->U[0],
                                                             ctx->cell_start, ctx->P[1], ctx->cnt, ctx->t_key, ctx->t_slot,
-                                                            ctx->send[0], ctx->send[1], ctx->coupling, ctx->dopt, ctx->cur_x ? 1 : 0, ctx->ord_key);
+                                                            ctx->send[0], ctx->send[1], ctx->coupling, ctx->dopt, ctx->cur_x ? 1 : 0, ctx->ord_key, ctx->tile_total);
         ctx->launches += 2;
         CK(cudaGetLastError());
         return SPH_OK;
     }
     SPH_LAUNCH(k_advect<false>, ctx->grid_advect, ctx->stream)(ctx->dp, ctx->counters, ctx->P[0], ctx->Q[0], ctx->U[0],
                                                          ctx->cell_start, ctx->P[1], ctx->cnt, ctx->t_key, ctx->t_slot,
-                                                         ctx->send[0], ctx->send[1], nullptr, nullptr, ctx->cur_x ? 1 : 0, ctx->ord_key);
+                                                         ctx->send[0], ctx->send[1], nullptr, nullptr, ctx->cur_x ? 1 : 0, ctx->ord_key, ctx->tile_total);
     ctx->launches++;
     CK(cudaGetLastError());
     return SPH_OK;
@@ -662,7 +667,7 @@ static int launch_relax(sph_ctx *ctx)
 {
     SPH_LAUNCH(k_relax, ctx->grid_relax, ctx->stream)(ctx->dp, ctx->counters, ctx->P[2], ctx->Q[1], ctx->U[1], ctx->dens,
                                                         ctx->cell_start, ctx->nmask, ctx->P[3], ctx->Q[2], ctx->cnt, ctx->t_key,
-                                                        ctx->t_slot, ctx->send[0], ctx->send[1], ctx->ord_key
+                                                        ctx->t_slot, ctx->send[0], ctx->send[1], ctx->ord_key, ctx->tile_total
 #if SPH_RELAX_PD4
                                                         , ctx->pd
 #endif
@@ -724,7 +729,7 @@ extern "C" int sph_refresh_ghosts(sph_ctx *ctx)
     if (ctx->stage != ST_READY) return fail(ctx, SPH_ERR_STATE, "sph_refresh_ghosts: state is not at a step boundary");
     if (ctx->cfg.nranks <= 1) return SPH_OK;
     SPH_LAUNCH(k_requeue, ctx->grid, ctx->stream)(ctx->dp, ctx->counters, ctx->P[0], ctx->Q[0], ctx->U[0], ctx->P[3], ctx->Q[2],
-                                                  ctx->U[1], ctx->cnt, ctx->t_key, ctx->t_slot, ctx->send[0], ctx->send[1]);
+                                                  ctx->U[1], ctx->cnt, ctx->t_key, ctx->t_slot, ctx->send[0], ctx->send[1], ctx->tile_total);
     ctx->launches++;
     CK(cudaGetLastError());
     ctx->stage = ST_REQUEUED;
@@ -833,7 +838,8 @@ static int ingest(sph_ctx *ctx, int n)
     for (int s = 0; s < 2; s++) CK(cudaMemsetAsync(ctx->send[s], 0, 16, ctx->stream));
     int rc = push_params(ctx);
     if (rc) return rc;
-    SPH_LAUNCH(k_bin_upload, ctx->grid, ctx->stream)(ctx->dp, ctx->counters, ctx->P[3], ctx->cnt, ctx->t_key, ctx->t_slot);
+    CK(cudaMemsetAsync(ctx->tile_total, 0, (size_t)ctx->ntiles_max * sizeof(int), ctx->stream));
+    SPH_LAUNCH(k_bin_upload, ctx->grid, ctx->stream)(ctx->dp, ctx->counters, ctx->P[3], ctx->cnt, ctx->t_key, ctx->t_slot, ctx->tile_total);
     ctx->launches++;
     // no neighbour messages belong to an upload: skip the unpack kernel
     if ((rc = launch_sort(ctx, 1, false))) return rc;
@@ -1042,6 +1048,22 @@ extern "C" int sph_get_status(sph_ctx *ctx, sph_status *out)
         out->bucket_overflow = std::max(hz[1], c[CN_BUCKET_OVER]);
     }
     out->neighbor_overflow = c[CN_NEIGH_OVER];
+    if (c[CN_NEIGH_OVER] > 0) {
+        // the hot path's count is conservative (full neighbour count, candidates past a row's mask taken as accepted) and
+        // cumulative; where the state is sorted, count the reference's forward lists of the CURRENT state exactly
+        float2 *dpos, *dq; uint32_t *duid; bool q_is_prev;
+        if (ctx->stage == ST_READY || ctx->stage == ST_SORTED1 || ctx->stage == ST_DENSITY) {
+            current_arrays(ctx, &dpos, &dq, &duid, &q_is_prev);
+            int *dstat = ctx->counters + CN_SPARE0;
+            int z = 0;
+            CK(cudaMemcpyAsync(dstat, &z, sizeof z, cudaMemcpyHostToDevice, ctx->stream));
+            SPH_LAUNCH(k_forward_overflow, ctx->grid, ctx->stream)(ctx->dp, ctx->counters, dpos, duid, ctx->cell_start, dstat);
+            ctx->launches++;
+            CK(cudaMemcpyAsync(&z, dstat, sizeof z, cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+            out->neighbor_overflow = z;
+        }
+    }
     out->capacity_overflow = c[CN_CAP_OVER];
     out->msg_overflow = c[CN_MSG_OVER];
     out->exchange_timeouts = c[CN_TIMEOUT_MSG];

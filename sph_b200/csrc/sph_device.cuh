@@ -151,6 +151,14 @@ __device__ __forceinline__ long long global_timer_ns()
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
+// one more entry in scan tile `tile`: one atomic per warp and tile (the lanes of a warp bin neighbouring particles,
+// nearly always into the same tile).  Called from divergent code: the lanes that arrive together form the group.
+__device__ __forceinline__ void tile_count_add(int *tile_total, int tile)
+{
+    const unsigned act = __activemask();
+    const unsigned same = __match_any_sync(act, tile);
+    if ((threadIdx.x & 31) == __ffs(same) - 1) atomicAdd(&tile_total[tile], __popc(same));
+}
 // FMNMX.NAN: a NaN operand wins, so that a running maximum also reports "not finite"
 __device__ __forceinline__ float max_nan(float a, float b)
 {

@@ -15,6 +15,14 @@
 #include "sph_device.cuh"
 
 #define SPH_THREADS 256
+#define SCAN_ITEMS 8
+#define SCAN_TILE (SPH_THREADS * SCAN_ITEMS)      // cells per tile of the prefix sum (k_scan_apply)
+// SPH_TILE_ATOMICS=1 (round 2): the kernels that bin a position also add it to its scan tile's total (one atomic per
+// warp and tile), so the prefix sum needs no pass of its own over the cell populations to form the tile totals:
+// k_scan_totals (5.5 us per sort at 1 M particles, latency-bound) disappears, the sort is three kernels instead of four.
+#ifndef SPH_TILE_ATOMICS
+#define SPH_TILE_ATOMICS 1
+#endif
 // resident blocks per SM the register allocation of each gather is held to (measured)
 #ifndef SPH_UNROLL
 #define SPH_UNROLL 4          // candidates per trip of the gather loops (loads issued together)
@@ -217,7 +225,8 @@ __device__ __forceinline__ void send_messages(const DevParams &P, int *counters,
 // bin a freshly produced position for the coming sort: key, arrival slot, cell population
 __device__ __forceinline__ void bin_position(int i, float2 p, int extra_bits, const DevParams &P,
                                              int *__restrict__ cnt, int *__restrict__ t_key,
-                                             int *__restrict__ t_slot, int *__restrict__ counters, bool keep = false)
+                                             int *__restrict__ t_slot, int *__restrict__ counters, int *__restrict__ tile_total,
+                                             bool keep = false)
 {
     int key = window_key_new(p, P);
     if (key == SPH_KEY_DROP && keep) key = window_key_clamped(p, P);
@@ -231,13 +240,16 @@ __device__ __forceinline__ void bin_position(int i, float2 p, int extra_bits, co
     }
     t_slot[i] = atomicAdd(&cnt[key], 1);
     t_key[i] = key | extra_bits;
+#if SPH_TILE_ATOMICS
+    tile_count_add(tile_total, key / SCAN_TILE);
+#endif
 }
 
 // The same with the store of the arrival slot left to the caller (SPH_PIPE): returns the slot, or -1 when the entry
 // was dropped.  The caller stores it an iteration later, so that no instruction waits for the atomic's round trip.
 __device__ __forceinline__ bool bin_position_deferred(int i, float2 p, int extra_bits, const DevParams &P,
                                                       int *__restrict__ cnt, int *__restrict__ t_key, int *__restrict__ counters,
-                                                      int &slot, bool keep = false)
+                                                      int *__restrict__ tile_total, int &slot, bool keep = false)
 {
     int key = window_key_new(p, P);
     if (key == SPH_KEY_DROP && keep) key = window_key_clamped(p, P);
@@ -248,6 +260,9 @@ __device__ __forceinline__ bool bin_position_deferred(int i, float2 p, int extra
     }
     t_key[i] = key | extra_bits;
     slot = atomicAdd(&cnt[key], 1);        // (the caller must not look at it before the next iteration)
+#if SPH_TILE_ATOMICS
+    tile_count_add(tile_total, key / SCAN_TILE);
+#endif
     return true;
 }
 
@@ -276,7 +291,7 @@ k_advect(const DevParams *__restrict__ Pp, int *__restrict__ counters,
          const int *__restrict__ cell_start,
          float2 *__restrict__ pos_pred, int *__restrict__ cnt, int *__restrict__ t_key, int *__restrict__ t_slot,
          unsigned char *send_l, unsigned char *send_r, const float *__restrict__ coupling, const DevOptions *__restrict__ Op,
-         int xstep, const int *__restrict__ ckey)
+         int xstep, const int *__restrict__ ckey, int *__restrict__ tile_total)
 {
     // xstep: neighbours exchange after this prediction (always, except in the one-exchange build with an exchange
     // period > 1, where between exchanges the ghosts are advanced here like everything else; see sph_set_exchange_period)
@@ -530,9 +545,9 @@ k_advect(const DevParams *__restrict__ Pp, int *__restrict__ counters,
         }
 #if SPH_PIPE
         if (slot_i >= 0) t_slot[slot_i] = slot_v;                       // the previous particle's: its atomic is back by now
-        slot_i = bin_position_deferred(i, np, extra, P, cnt, t_key, counters, slot_v, unsent) ? i : -1;
+        slot_i = bin_position_deferred(i, np, extra, P, cnt, t_key, counters, tile_total, slot_v, unsent) ? i : -1;
 #else
-        bin_position(i, np, extra, P, cnt, t_key, t_slot, counters, unsent);
+        bin_position(i, np, extra, P, cnt, t_key, t_slot, counters, tile_total, unsent);
 #endif
     }
 #if SPH_PIPE
@@ -634,7 +649,8 @@ __global__ void __launch_bounds__(SPH_THREADS)
 k_unpack(const DevParams *__restrict__ Pp, int *__restrict__ counters, int which,
          unsigned char *send_l, unsigned char *send_r, unsigned char *recv_l, unsigned char *recv_r,
          float2 *__restrict__ src_pos, float2 *__restrict__ src_q, uint32_t *__restrict__ src_uid,
-         int *__restrict__ cnt, int *__restrict__ t_key, int *__restrict__ t_slot, long long *__restrict__ xt)
+         int *__restrict__ cnt, int *__restrict__ t_key, int *__restrict__ t_slot, long long *__restrict__ xt,
+         int *__restrict__ tile_total)
 {
     pdl_enter();
     const DevParams P = *Pp;
@@ -718,7 +734,7 @@ k_unpack(const DevParams *__restrict__ Pp, int *__restrict__ counters, int which
         src_uid[idx] = u;
         // a ghost outside this slab's window is simply not needed (a slab parked outside the tank,
         // controls.c:405-426, still receives its neighbour's edge particles): same flag as an emigrant
-        bin_position(idx, p, (u & SPH_HALO_BIT) ? SPH_KEY_EMIG : 0, P, cnt, t_key, t_slot, counters);
+        bin_position(idx, p, (u & SPH_HALO_BIT) ? SPH_KEY_EMIG : 0, P, cnt, t_key, t_slot, counters, tile_total);
     }
     if (timer && P.p2p) {
         const long long tc3 = global_timer_ns();
@@ -742,9 +758,6 @@ k_unpack(const DevParams *__restrict__ Pp, int *__restrict__ counters, int which
 //     The reference silently drops particles above 100 per bucket (hash.c:160-165): the largest
 //     population seen is recorded so that this can be detected.
 // -------------------------------------------------------------------------------------------
-#define SCAN_ITEMS 8
-#define SCAN_TILE (SPH_THREADS * SCAN_ITEMS)
-
 __device__ __forceinline__ void scan_load_tile(const int *__restrict__ cnt, int base, int ncell, int (&v)[SCAN_ITEMS])
 {
     if (base + SCAN_ITEMS <= ncell) {
@@ -828,6 +841,19 @@ k_scan_apply(DevParams *__restrict__ Pp, int *__restrict__ counters, int *__rest
         int sum = 0;
 #pragma unroll
         for (int k = 0; k < SCAN_ITEMS; k++) sum += v[k];
+#if SPH_TILE_ATOMICS
+        {
+            // the bucket statistics k_scan_totals used to form (per sort-grid sub-cell: a sub-cell above 100 implies its
+            // reference bucket is; the exact bucket statistics are computed on demand by k_bucket_stats)
+            int mx = 0, over = 0;
+#pragma unroll
+            for (int k = 0; k < SCAN_ITEMS; k++) { mx = max(mx, v[k]); over += v[k] > 100; }
+            mx = __reduce_max_sync(0xffffffffu, mx);
+            over = __reduce_add_sync(0xffffffffu, over);
+            if (lane == 0 && mx > 0) atomicMax(&counters[CN_MAX_BUCKET], mx);
+            if (lane == 0 && over > 0) atomicAdd(&counters[CN_BUCKET_OVER], over);
+        }
+#endif
         int inc = sum;                                     // warp inclusive scan of the thread sums
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -892,10 +918,15 @@ k_scan_apply(DevParams *__restrict__ Pp, int *__restrict__ counters, int *__rest
 __global__ void __launch_bounds__(SPH_THREADS)
 k_scatter(const int *__restrict__ counters, const int *__restrict__ cell_start,
           const int *__restrict__ t_key, const int *__restrict__ t_slot, const uint32_t *__restrict__ src_uid,
-          uint32_t *__restrict__ ord_uid, int *__restrict__ ord_src, int *__restrict__ ord_key)
+          uint32_t *__restrict__ ord_uid, int *__restrict__ ord_src, int *__restrict__ ord_key,
+          int *__restrict__ tile_total, int ntiles_max)
 {
     pdl_enter();
     const int n = counters[CN_NSRC];
+#if SPH_TILE_ATOMICS
+    // the scan before this kernel has consumed the tile totals: clear them for the producers of the next sort
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < ntiles_max; t += gridDim.x * blockDim.x) tile_total[t] = 0;
+#endif
     for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) {
         const int key = t_key[s];
         if (key == SPH_KEY_DROP) continue;
@@ -1040,9 +1071,10 @@ k_density(const DevParams *__restrict__ Pp, int *__restrict__ counters,
 #if SPH_RELAX_PD4
         pd[i] = make_float4(p.x, p.y, d, dn);
 #endif
-        // a forward list cannot exceed the full neighbour count: cheap, conservative detection
-        // of the reference's 400-entry cap (hash.c:188,223)
-        if (nn > 400) atomicAdd(&counters[CN_NEIGH_OVER], 1);
+        // The reference's 400-entry cap is on a particle's FORWARD list (hash.c:188,223).  A forward list cannot exceed
+        // the full neighbour count, and candidates past a row's mask were counted as accepted: only a particle that
+        // fails this cheap, conservative test is counted again exactly, with the reference's owner rule (rare path).
+        if (nn > SPH_REF_MAX_NEIGHBORS) atomicAdd(&counters[CN_NEIGH_OVER], 1);      // (sph_get_status then counts exactly)
         cost += SPH_COST_BASE + nn;
     }
     pdl_done();
@@ -1063,7 +1095,7 @@ k_relax(const DevParams *__restrict__ Pp, int *__restrict__ counters,
         const sph_mask_t *__restrict__ nmask,
         float2 *__restrict__ pos_out, float2 *__restrict__ vel_out,
         int *__restrict__ cnt, int *__restrict__ t_key, int *__restrict__ t_slot,
-        unsigned char *send_l, unsigned char *send_r, const int *__restrict__ ckey SPH_PD4_CPARAM)
+        unsigned char *send_l, unsigned char *send_r, const int *__restrict__ ckey, int *__restrict__ tile_total SPH_PD4_CPARAM)
 {
     pdl_enter();
     const DevParams P = *Pp;
@@ -1325,9 +1357,9 @@ k_relax(const DevParams *__restrict__ Pp, int *__restrict__ counters,
         if (P.one_x) {
 #if SPH_PIPE
             if (slot_i >= 0) t_slot[slot_i] = slot_v;
-            slot_i = bin_position_deferred(i, np, ghost ? SPH_KEY_EMIG : 0, P, cnt, t_key, counters, slot_v, !ghost) ? i : -1;
+            slot_i = bin_position_deferred(i, np, ghost ? SPH_KEY_EMIG : 0, P, cnt, t_key, counters, tile_total, slot_v, !ghost) ? i : -1;
 #else
-            bin_position(i, np, ghost ? SPH_KEY_EMIG : 0, P, cnt, t_key, t_slot, counters, !ghost);
+            bin_position(i, np, ghost ? SPH_KEY_EMIG : 0, P, cnt, t_key, t_slot, counters, tile_total, !ghost);
 #endif
             continue;
         }
@@ -1346,9 +1378,9 @@ k_relax(const DevParams *__restrict__ Pp, int *__restrict__ counters,
 #if SPH_PIPE
         if (slot_i >= 0) t_slot[slot_i] = slot_v;                       // the previous particle's: its atomic is back by now
         // (a local outside the window can only be an emigrant that is still waiting for room in a message: kept)
-        slot_i = bin_position_deferred(i, np, 0, P, cnt, t_key, counters, slot_v, true) ? i : -1;
+        slot_i = bin_position_deferred(i, np, 0, P, cnt, t_key, counters, tile_total, slot_v, true) ? i : -1;
 #else
-        bin_position(i, np, 0, P, cnt, t_key, t_slot, counters, true);
+        bin_position(i, np, 0, P, cnt, t_key, t_slot, counters, tile_total, true);
 #endif
     }
 #if SPH_PIPE
@@ -1364,13 +1396,13 @@ k_relax(const DevParams *__restrict__ Pp, int *__restrict__ counters,
 // -------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(SPH_THREADS)
 k_bin_upload(const DevParams *__restrict__ Pp, int *__restrict__ counters, const float2 *__restrict__ pos,
-             int *__restrict__ cnt, int *__restrict__ t_key, int *__restrict__ t_slot)
+             int *__restrict__ cnt, int *__restrict__ t_key, int *__restrict__ t_slot, int *__restrict__ tile_total)
 {
     pdl_enter();
     const DevParams P = *Pp;
     const int n = counters[CN_NTOT];
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-        bin_position(i, pos[i], 0, P, cnt, t_key, t_slot, counters);
+        bin_position(i, pos[i], 0, P, cnt, t_key, t_slot, counters, tile_total);
 }
 
 // -------------------------------------------------------------------------------------------
@@ -1383,7 +1415,7 @@ k_requeue(const DevParams *__restrict__ Pp, int *__restrict__ counters,
           const float2 *__restrict__ pos, const float2 *__restrict__ vel, const uint32_t *__restrict__ uid,
           float2 *__restrict__ pos_out, float2 *__restrict__ vel_out, uint32_t *__restrict__ uid_out,
           int *__restrict__ cnt, int *__restrict__ t_key, int *__restrict__ t_slot,
-          unsigned char *send_l, unsigned char *send_r)
+          unsigned char *send_l, unsigned char *send_r, int *__restrict__ tile_total)
 {
     pdl_enter();
     const DevParams P = *Pp;
@@ -1407,7 +1439,7 @@ k_requeue(const DevParams *__restrict__ Pp, int *__restrict__ counters,
                 else atomicAdd(&counters[CN_MSG_OVER], 1);
             }
         }
-        bin_position(i, p, 0, P, cnt, t_key, t_slot, counters);
+        bin_position(i, p, 0, P, cnt, t_key, t_slot, counters, tile_total);
     }
 }
 
@@ -1502,6 +1534,42 @@ __global__ void k_bucket_stats(const DevParams *__restrict__ Pp, const int *__re
     mx = __reduce_max_sync(0xffffffffu, mx);
     over = __reduce_add_sync(0xffffffffu, over);
     if ((threadIdx.x & 31) == 0) { if (mx) atomicMax(&out[0], mx); if (over) atomicAdd(&out[1], over); }
+}
+
+// Particles whose REFERENCE forward list (hash.c:178-224: owner = earlier bucket slot in the same cell, else the cell
+// whose forward stencil holds the other; ghosts are appended to the local's list) would exceed its 400 entries, in the
+// current sorted state: the exact figure behind sph_status.neighbor_overflow (the density kernel only keeps a cheap
+// conservative count).
+__global__ void k_forward_overflow(const DevParams *__restrict__ Pp, const int *__restrict__ counters,
+                                   const float2 *__restrict__ pos, const uint32_t *__restrict__ uid,
+                                   const int *__restrict__ cell_start, int *__restrict__ out)
+{
+    pdl_enter();
+    const DevParams P = *Pp;
+    const int n = counters[CN_NTOT];
+    const float h2 = __fmul_rn(P.h, P.h);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        if (uid[i] & SPH_HALO_BIT) continue;
+        const float2 p = pos[i];
+        const uint32_t ui = uid[i] & SPH_UID_MASK;
+        const int gxi = cell_coord(p.x, P.cell_h), gyi = cell_coord(p.y, P.cell_h);
+        const Rows R = candidate_rows(p, P, cell_start);
+        int total = 0;
+        for (int d = 0; d < SPH_NROWS; d++) total += R.e[d] - R.b[d];
+        if (total <= SPH_REF_MAX_NEIGHBORS) continue;                  // cannot have more forward neighbours than candidates
+        int fwd = 0;
+        for (int d = 0; d < SPH_NROWS; d++)
+            for (int j = R.b[d]; j < R.e[d]; j++) {
+                if (j == i) continue;
+                const float2 q = pos[j];
+                if (dist2(p.x - q.x, p.y - q.y) > h2) continue;
+                const uint32_t uj = uid[j] & SPH_UID_MASK;
+                const int gxj = cell_coord(q.x, P.cell_h), gyj = cell_coord(q.y, P.cell_h);
+                const bool owner = (gxi == gxj && gyi == gyj) ? (ui < uj) : (gxi != gxj ? gxi < gxj : gyi < gyj);
+                if ((uid[j] & SPH_HALO_BIT) || owner) fwd++;
+            }
+        if (fwd > SPH_REF_MAX_NEIGHBORS) atomicAdd(out, 1);
+    }
 }
 
 __global__ void k_export_cells(const DevParams *__restrict__ Pp, const int *__restrict__ counters,

@@ -5,6 +5,7 @@
 #pragma once
 static inline float rcp_approx(float x) { return 1.0f / x; }
 static inline void prefetch_l1(const void *) {}
+static inline void tile_count_add(int *tile_total, int tile) { tile_total[tile] += 1; }   // (fibers of one OS thread: a plain add)
 static inline long long global_timer_ns() { return clock64(); }
 static inline float max_nan(float a, float b) { return (a != a || b != b) ? NAN : (a > b ? a : b); }
 struct f32x2 { float lo, hi; };

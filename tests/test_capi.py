@@ -31,6 +31,7 @@ def test_no_cpu_fallback(built_lib):
     if torch.cuda.is_available():
         pytest.skip("a GPU is present")
     import sph_b200
+    sph_b200._lib = None          # (an emulator test earlier in the same process may have rebound the module's library)
     with pytest.raises(sph_b200.SphError) as e:
         sph_b200.Context(15.0, 8.4375, 0.58, 2048)
     assert "-> 1" in str(e.value)

@@ -29,9 +29,9 @@ def test_bench_main_runs_end_to_end_on_the_emulator(built_lib, extra, gather):
     assert set(d["roofline"]) >= {"bound", "achieved", "peak", "unit", "frac", "traffic"}
     assert d["e2e"]["value"] > 0 and d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0
     assert "pipelined" in d["e2e"]["protocol"] and d["e2e"]["synchronous_value"] > 0 and "pipelined_error" not in d["e2e"]
-    # 11 launches per step (12 with the stabilised gather's extra pass) in the timed region, which repeats the block
+    # 9 launches per step (10 with the stabilised gather's extra pass) in the timed region, which repeats the block
     # of --steps steps until enough device time has been measured and reports the median block with its spread
     tr = d["config"]["timed_region"]
     assert tr["blocks"] >= 3 and tr["steps_per_block"] == 4 and len(tr["block_ms_min_p10_median_p90_max"]) == 5
-    assert d["gpu_launches"] == tr["blocks"] * 4 * (12 if gather.endswith("stabilised") else 11)
+    assert d["gpu_launches"] == tr["blocks"] * 4 * (10 if gather.endswith("stabilised") else 9)
     assert d["config"]["integrity"]["nobody_lost_or_duplicated"] and d["config"]["integrity"]["capacity_overflow"] == 0
