@@ -51,6 +51,12 @@ def launches(src, dst):
     print(open(dst).read())
 
 
+def short(name):
+    """'void k_advect<0>(const DevParams *, ...)' -> 'k_advect'"""
+    import re
+    return re.sub(r"<.*$", "", name.split("(")[0].replace("void ", "")).strip()
+
+
 def full(src, dst):
     out = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
@@ -58,7 +64,7 @@ def full(src, dst):
     idx = {h: i for i, h in enumerate(hdr)}
     with open(dst, "w") as f:
         w = csv.writer(f)
-        w.writerow(["metric", "unit"] + [r[idx["Kernel Name"]].split("(")[0] for r in rows[2:]])
+        w.writerow(["metric", "unit"] + [short(r[idx["Kernel Name"]]) for r in rows[2:]])
         for m in KEEP:
             if m in idx:
                 w.writerow([m, units[idx[m]]] + [r[idx[m]] for r in rows[2:]])
@@ -72,7 +78,7 @@ def full(src, dst):
     for r in rows[2:]:
         rd = float(r[idx["dram__bytes_read.sum"]]) * scale[units[idx["dram__bytes_read.sum"]]]
         wr = float(r[idx["dram__bytes_write.sum"]]) * scale[units[idx["dram__bytes_write.sum"]]]
-        t[r[idx["Kernel Name"]].split("(")[0]] = {"dram_bytes_per_launch": rd + wr, "n_particles": n, "source": os.path.basename(dst)}
+        t[short(r[idx["Kernel Name"]])] = {"dram_bytes_per_launch": rd + wr, "n_particles": n, "source": os.path.basename(dst)}
     json.dump(t, open(tj, "w"), indent=1)
 
 

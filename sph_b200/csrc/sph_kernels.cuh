@@ -41,6 +41,25 @@ constexpr int kGatherUnroll = SPH_UNROLL;     // (#pragma unroll takes a constan
 #ifndef SPH_PACKED_RELAX
 #define SPH_PACKED_RELAX 1
 #endif
+// SPH_TRIM=1 (default since round 2): k_advect's candidate loop applies a pair's half impulse with two FFMAs and
+// moves the reference's per-component +-5 clamp (fluid.c:459) into an exact redo of the rare rows in which it can
+// bind (see the kernel).  Measured: k_advect 86 -> 82 us on top of the packed loop.
+#ifndef SPH_TRIM
+#define SPH_TRIM 1
+#endif
+// SPH_PIPE=1 (from the per-instruction stall samples of round 2's call 2): the per-particle prologue and epilogue of
+// the gathers were a chain of dependent long-latency accesses -- uid, then position, then an IEEE division for the
+// cell, then the ten range bounds, (k_relax: then one mask per row), ..., then the atomic that hands out the arrival
+// slot and the store that waits for it -- and 18 % (k_advect) to 40 % (k_relax) of all stall samples sat on them.
+// With the flag: the sort-grid cell comes from the key the sort left behind (ord_key is constant inside a cell, so
+// ord_key[i] IS the key of sorted entry i: no division, no dependence on the position), the inputs of the thread's
+// next particle and the late inputs of this one are prefetched into L1, and the arrival slot is stored one iteration
+// later, when its atomic has long returned.  Same arithmetic, same results.  Measured on the B200 and REJECTED as a
+// default (0): k_advect 88 -> 84 us, but k_relax 66 -> 72 us (the stall samples on the prologue fell by a quarter, yet
+// the added prefetch traffic and code size cost more).
+#ifndef SPH_PIPE
+#define SPH_PIPE 0
+#endif
 // SPH_RELAX_PD4=1: k_density also writes (x, y, density, density_near) as one 16-byte record per entry and
 // k_relax's neighbour walk reads that record: one load and one address per neighbour instead of two.
 // Measured on the B200 in round 2 and REJECTED: k_relax 74 us against 67 (the extra 16 bytes per particle that

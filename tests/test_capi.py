@@ -89,3 +89,19 @@ def test_pdl_variant_builds_and_every_kernel_waits_before_it_reads(built_lib):
     base = subprocess.run(["cuobjdump", "-sass", built_lib], check=True, capture_output=True, text=True).stdout
     assert "ACQBULK" not in base and "PREEXIT" not in base
     os.remove(lib)
+
+
+def test_every_build_flag_tested_in_the_sources_has_a_default():
+    """An `#if SPH_X` whose macro is defined nowhere silently reads as 0 (round 2 lost the defaults of two flags to an
+    editing slip and shipped a slower kernel for a few commits): every SPH_ flag tested by the preprocessor in
+    sph_b200/csrc must have an `#ifndef SPH_X / #define SPH_X default` block (or a plain #define) in those sources."""
+    import glob
+    import re
+    root = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
+    src = "".join(open(f).read() for f in glob.glob(os.path.join(root, "sph_b200", "csrc", "*.cu*")) +
+                  glob.glob(os.path.join(root, "include", "*.h")))
+    used = set(re.findall(r"^\s*#\s*(?:if|elif)[^\n]*?\b(SPH_[A-Z0-9_]+)", src, re.M)) | \
+        set(m for line in re.findall(r"^\s*#\s*(?:if|elif)([^\n]*)", src, re.M) for m in re.findall(r"\bSPH_[A-Z0-9_]+", line))
+    defined = set(re.findall(r"^\s*#\s*define\s+(SPH_[A-Z0-9_]+)", src, re.M))
+    missing = sorted(u for u in used if u not in defined and u != "SPH_EMU")        # SPH_EMU: only the test suite defines it
+    assert not missing, missing
