@@ -329,8 +329,8 @@ class SlabRunner:
     def kernel_name(self, stage):
         return {"advect": "k_advect", "density": "k_density", "relax": "k_relax",
                 "exchange": "peer stores inside k_advect/k_relax" if self.transport == "p2p" else "nccl send/recv",
-                "sort1": "k_unpack+k_scan_totals+k_scan_apply+k_scatter+k_reorder",
-                "sort2": "k_unpack+k_scan_totals+k_scan_apply+k_scatter+k_reorder"}[stage]
+                "sort1": "k_unpack+k_scan_apply+k_scatter+k_reorder",
+                "sort2": "k_scan_apply+k_scatter+k_reorder"}[stage]
 
     def e2e(self, frames, flush_buf):
         """Frames with host buffers, pipelined like the reference's MPI_Isend of its frame (fluid.c:283-287, :354-365) and
