@@ -373,8 +373,8 @@ def main_ours(args):
         stats = sim.stats()
         mark("stats")
 
-    if world == 8 and not args.no_cfg3:
-        del sim
+    if (world == 8 or args.force_cfg3) and world > 1 and not args.no_cfg3:
+        # (the main section's simulation stays alive: its names and settings go into the line below)
         try:
             cfg3 = run_cfg3(sph_b200, rank, world, stream, args, flush_buf, barrier)
         except Exception as e:
@@ -558,7 +558,7 @@ def run_cfg3(sph_b200, rank, world, stream, args, flush_buf, barrier):
     import torch
     import torch.distributed as dist
     from sph_b200.slab import SlabRunner
-    n_per = 2_000_000
+    n_per = args.cfg3_particles
     prob = sph_b200.make_problem(n_per * world, tank_w=problem_dims(n_per * world, args.water_frac), water_frac=args.water_frac, nranks=world)
     t = sph_b200.default_params(prob["h"], prob["tank_w"], prob["tank_h"], args.preset)
     t.mover_center_x = 0.75 * prob["tank_w"]
@@ -742,6 +742,8 @@ def main():
     ap.add_argument("--max-repeats", type=int, default=400)
     ap.add_argument("--no-parity-check", action="store_true", help="N > 1: skip the small N-slab-vs-1-slab bit comparison before the timed region")
     ap.add_argument("--no-cfg3", action="store_true", help="--gpus 8: skip the second timed section on BASELINE config 3 (16 M particles)")
+    ap.add_argument("--force-cfg3", action="store_true", help="run that section at any N > 1 (to exercise the code path on fewer GPUs)")
+    ap.add_argument("--cfg3-particles", type=int, default=2_000_000, help="particles per GPU of that section (8 x 2 M = config 3's 16 M)")
     ap.add_argument("--balance", default="time", choices=["count", "cost", "time"],
                     help="slab edge policy at N > 1: each slab's measured device time between meetings (default), the reference's "
                          "particle counts (renderer.c:427-477), or the modelled work estimate; results are identical bit for bit")
