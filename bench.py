@@ -290,7 +290,7 @@ def main_ours(args):
             from sph_b200.slab import SlabRunner
             sim = SlabRunner(prob, t, rank, world, stream, capacity_factor=2.0, balance_policy=args.balance,
                              halo_width=args.halo_width, exchange_period=args.exchange_period,
-                             exchanges_per_step=args.exchanges_per_step)
+                             exchanges_per_step=args.exchanges_per_step, time_proportional=not args.time_fixed_step)
         if args.visc_stab is not None:                  # default: the library's (gamma 0.5 for blocks with dt*sigma >= 0.5)
             sim.ctx.set_viscosity_stabilisation(args.visc_stab)
         mark("created")
@@ -517,7 +517,7 @@ def slab_parity_check(sph_b200, rank, world, stream, args, n_req=None, steps=40)
         with torch.cuda.stream(stream):
             sim = SlabRunner(prob, t, rank, world, stream, capacity_factor=3.0, balance_policy=args.balance,
                              halo_width=args.halo_width, exchange_period=args.exchange_period,
-                             exchanges_per_step=args.exchanges_per_step)
+                             exchanges_per_step=args.exchanges_per_step, time_proportional=not args.time_fixed_step)
             sim.init_lattice()
             sim.run(steps)
             a, uid = sim.ctx.download()
@@ -566,7 +566,7 @@ def run_cfg3(sph_b200, rank, world, stream, args, flush_buf, barrier):
     with torch.cuda.stream(stream):
         sim = SlabRunner(prob, t, rank, world, stream, capacity_factor=2.0, balance_policy=args.balance,
                          halo_width=args.halo_width, exchange_period=args.exchange_period,
-                             exchanges_per_step=args.exchanges_per_step)
+                             exchanges_per_step=args.exchanges_per_step, time_proportional=not args.time_fixed_step)
         sim.init_lattice()
         sim.run(preroll + args.warmup)
         barrier()
@@ -729,6 +729,8 @@ def main():
     ap.add_argument("--visc-stab", type=float, default=None, metavar="GAMMA",
                     help="force the stabilised viscosity gather with this gamma for every block (0 = plain gather everywhere); "
                          "default: the library's own rule (gamma 0.5 where dt*sigma >= 0.5, i.e. the goo preset, DESIGN.md 5b)")
+    ap.add_argument("--time-fixed-step", action="store_true",
+                    help="--balance time with the reference's fixed edge step of h/8 per frame instead of a step proportional to the imbalance")
     ap.add_argument("--exchanges-per-step", type=int, default=1, choices=[1, 2],
                     help="N > 1: 2 = neighbours meet after the prediction and after the relaxation, like the reference (fluid.c:310-348); "
                          "1 = once, ghosts relaxed redundantly (default)")

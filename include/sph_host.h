@@ -45,6 +45,12 @@ void sph_host_balance(sph_tunable *master, int nactive, const int *counts, int t
  * for callers that balance on a work estimate (sph_copy_load) and want it tighter than +-6.7 %. */
 void sph_host_balance_ex(sph_tunable *master, int nactive, const int *counts, int total, float band_divisor);
 
+/* OPTIONAL edge policy on MEASURED slab times (sph_copy_work; not the reference's): every interior edge moves towards
+ * the slower of its two slabs by `gain` x the shift that would equalise their times, at most max_shift_h smoothing
+ * radii per call, keeping every slab at least min_width_h radii wide; dead band 0.5 %.  The particles do not depend on
+ * where the edges are, so this changes the schedule only. */
+void sph_host_balance_time(sph_tunable *master, int nactive, const int *busy, float gain, float max_shift_h, float min_width_h);
+
 /* The render rank's idle "autopilot" for the mover (renderer.c:513-531): per frame gl_x += 0.01 * dir,
  * direction flips outside [-1, 1], gl_y = sinf(3.14 * 5 * gl_x) / 10 - 0.6, then opengl_to_sim
  * (renderer.c:396-404).  Updates t->mover_center_{x,y}; *gl_x / *direction carry the state. */

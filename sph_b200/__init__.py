@@ -337,7 +337,7 @@ class Context:
 # C host layer (include/sph_host.h): start-up geometry, parameter model, slab load balancer
 # ------------------------------------------------------------------------------------------------
 HOST_SYMBOLS = ("sph_host_mover_autopilot", "sph_host_mover_autopilot_ex", "sph_host_spacing", "sph_host_default_params", "sph_host_preset", "sph_host_partition",
-                "sph_host_lattice", "sph_host_balance", "sph_host_balance_ex", "sph_host_remove_partition", "sph_host_add_partition")
+                "sph_host_lattice", "sph_host_balance", "sph_host_balance_ex", "sph_host_balance_time", "sph_host_remove_partition", "sph_host_add_partition")
 
 
 def _host():
@@ -411,6 +411,18 @@ def balance(edges, counts, h, nactive=None, band_divisor=15.0):
     c = np.asarray(counts, "i4")
     L.sph_host_balance_ex.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_float]
     L.sph_host_balance_ex(m, nactive, _p(c), int(c.sum()), float(band_divisor))
+    return [(float(m[r].node_start_x), float(m[r].node_end_x)) for r in range(n)]
+
+
+def balance_time(edges, busy, h, nactive=None, gain=0.5, max_shift_h=1.0, min_width_h=2.0):
+    """sph_host_balance_time: edges moved in proportion to the measured imbalance of adjacent slabs (not the reference's policy)."""
+    L = _host()
+    n = len(edges)
+    nactive = n if nactive is None else nactive
+    m = _edge_blocks(edges, h)
+    c = np.asarray(busy, "i4")
+    L.sph_host_balance_time.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_float, C.c_float, C.c_float]
+    L.sph_host_balance_time(m, nactive, _p(c), float(gain), float(max_shift_h), float(min_width_h))
     return [(float(m[r].node_start_x), float(m[r].node_end_x)) for r in range(n)]
 
 

@@ -135,6 +135,39 @@ void sph_host_balance_ex(sph_tunable *m, int nactive, const int *counts, int tot
     }
 }
 
+void sph_host_balance_time(sph_tunable *m, int nactive, const int *busy, float gain, float max_shift_h, float min_width_h)
+{
+    /* Not the reference's policy (that is sph_host_balance above).  Every interior edge moves towards the slower of
+     * its two slabs by `gain` times the shift that would equalise their measured times if a slab's time were
+     * proportional to its width: delta = gain (T_right - T_left) / (T_left / w_left + T_right / w_right),
+     * bounded by max_shift_h smoothing radii per call, never leaving a slab narrower than min_width_h radii, and left
+     * alone inside a dead band of 0.5 % of the pair's time.  Left to right, on the edges as they were on entry. */
+    const float h = m[0].smoothing_radius;
+    float len[64], shift[64];
+    if (nactive < 2 || nactive > 64) return;
+    for (int r = 0; r < nactive; r++) len[r] = slab_len(&m[r]);
+    for (int e = 0; e + 1 < nactive; e++) {          /* edge e: between slab e and slab e + 1 */
+        shift[e] = 0.0f;
+        const float tl = (float)busy[e], tr = (float)busy[e + 1];
+        if (tl <= 0.0f || tr <= 0.0f || len[e] <= 0.0f || len[e + 1] <= 0.0f) continue;
+        if (fabsf(tr - tl) <= 0.005f * (tl + tr)) continue;
+        float d = gain * (tr - tl) / (tl / len[e] + tr / len[e + 1]);     /* > 0: the right slab is slower, it shrinks */
+        const float cap = max_shift_h * h;
+        if (d > cap) d = cap;
+        if (d < -cap) d = -cap;
+        shift[e] = d;
+    }
+    for (int e = 0; e + 1 < nactive; e++) {
+        float d = shift[e];
+        /* widths after this and the neighbouring edges' moves must stay above the minimum */
+        const float left_after = len[e] + d - (e > 0 ? shift[e - 1] : 0.0f);
+        const float right_after = len[e + 1] - d + (e + 2 < nactive ? shift[e + 1] : 0.0f);
+        if (left_after < min_width_h * h || right_after < min_width_h * h) { shift[e] = 0.0f; continue; }
+    }
+    for (int e = 0; e + 1 < nactive; e++)
+        if (shift[e] != 0.0f) shift_edge(m, e, shift[e]);
+}
+
 void sph_host_mover_autopilot(sph_tunable *t, float tank_w, float tank_h, float *gl_x, int *direction)
 {
     sph_host_mover_autopilot_ex(t, tank_w, tank_h, gl_x, direction, 0.01f);

@@ -55,7 +55,7 @@ class SlabRunner:
     def __init__(self, prob, tunable, rank, world, stream=None, capacity_factor=2.0, backend=None,
                  msg_capacity=None, steps_per_frame=4, balance=True, group=None, transport="p2p",
                  async_counts=True, balance_policy="count", cost_band_divisor=40.0, halo_width=None, exchange_period=1,
-                 exchanges_per_step=0):
+                 exchanges_per_step=0, time_proportional=True):
         import torch
         import torch.distributed as dist
         self.torch, self.dist = torch, dist
@@ -64,6 +64,7 @@ class SlabRunner:
         assert balance_policy in ("count", "cost", "time")
         self.balance_policy, self.cost_band_divisor = balance_policy, cost_band_divisor
         self.time_band_divisor = 100.0      # "time" policy: a slab's measured time within 1 % of the mean is left alone
+        self.time_proportional = time_proportional
         self.costs = None
         self.sub_step = 0
         self.n_active = world            # slabs taking part (render_state->num_compute_procs_active)
@@ -204,7 +205,14 @@ class SlabRunner:
         if self.balance_policy == "time" and min(active) > 0:
             # same edge arithmetic, fed with each slab's MEASURED device time between its meetings (sph_copy_work):
             # whatever makes a slab slow -- denser fluid, more ghosts, a mover, a slower GPU -- it gives up columns
-            self.edges = sph_b200.balance(self.edges, busy, self.prob["h"], self.n_active, band_divisor=self.time_band_divisor)
+            if self.time_proportional:
+                # edges move in proportion to the measured imbalance of the two slabs they separate (converges in tens
+                # of frames; the reference's fixed h/8 per frame needs hundreds for a 10 % imbalance)
+                layer = (self.ctx.cfg.halo_width or 2.0) if self.exchanges == 1 else 2.0
+                self.edges = sph_b200.balance_time(self.edges, busy, self.prob["h"], self.n_active, gain=0.5, max_shift_h=2.0,
+                                                   min_width_h=max(2.0, layer))
+            else:
+                self.edges = sph_b200.balance(self.edges, busy, self.prob["h"], self.n_active, band_divisor=self.time_band_divisor)
         elif self.balance_policy == "cost":
             # same edge arithmetic, fed with the work estimate (scaled to stay far from int overflow)
             self.edges = sph_b200.balance(self.edges, [c >> 4 for c in costs], self.prob["h"], self.n_active,
