@@ -222,15 +222,19 @@ extern "C" int sph_create(const sph_config *cfg, sph_ctx **out)
     ctx->grid_relax = std::min<int>((int)((cap + SPH_THREADS - 1) / SPH_THREADS), prop.multiProcessorCount * SPH_GRID_RELAX);
     ctx->sort_grid = std::min<int>((int)((cap + SPH_THREADS - 1) / SPH_THREADS), prop.multiProcessorCount * SPH_GRID_MULT_SORT);
 
-    for (int i = 0; i < 4; i++) CK(cudaMalloc(&ctx->P[i], cap * sizeof(float2)));
-    for (int i = 0; i < 3; i++) CK(cudaMalloc(&ctx->Q[i], cap * sizeof(float2)));
+    // (SPH_PAIRMASK: a masked pair trip reads one entry past a candidate range and discards it; the entry must exist and
+    //  be finite, so the arrays the gathers read are padded and start out as zeros)
+    const size_t pad = 4;
+    for (int i = 0; i < 4; i++) { CK(cudaMalloc(&ctx->P[i], (cap + pad) * sizeof(float2))); CK(cudaMemset(ctx->P[i], 0, (cap + pad) * sizeof(float2))); }
+    for (int i = 0; i < 3; i++) { CK(cudaMalloc(&ctx->Q[i], (cap + pad) * sizeof(float2))); CK(cudaMemset(ctx->Q[i], 0, (cap + pad) * sizeof(float2))); }
     for (int i = 0; i < 2; i++) CK(cudaMalloc(&ctx->U[i], cap * sizeof(uint32_t)));
     CK(cudaMalloc(&ctx->dens, cap * sizeof(float2)));
     CK(cudaMalloc(&ctx->nmask, SPH_NROWS * cap * sizeof(sph_mask_t)));
 #if SPH_RELAX_PD4
     CK(cudaMalloc(&ctx->pd, cap * sizeof(float4)));
 #endif
-    CK(cudaMalloc(&ctx->coupling, cap * sizeof(float)));
+    CK(cudaMalloc(&ctx->coupling, (cap + pad) * sizeof(float)));
+    CK(cudaMemset(ctx->coupling, 0, (cap + pad) * sizeof(float)));
     CK(cudaMalloc(&ctx->dopt, sizeof(DevOptions)));
     {
         // Default: the stabilised viscosity gather engages by itself for parameter blocks with dt*sigma >= 0.5, i.e.
@@ -543,14 +547,26 @@ static int launch_sort(sph_ctx *ctx, int which, bool with_unpack = true, bool re
     SPH_LAUNCH(k_scan_totals, sgrid, ctx->stream)(ctx->dp, ctx->counters, ctx->cnt, ctx->tile_total);
     ctx->launches++;
 #endif
-    SPH_LAUNCH(k_scan_apply, sgrid, ctx->stream)(ctx->dp, ctx->counters, ctx->cnt, ctx->cell_start, ctx->tile_total,
+#if SPH_SCAN_FAST && SPH_TILE_ATOMICS
+#define SPH_K_SCAN k_scan_apply_fast
+#else
+#define SPH_K_SCAN k_scan_apply
+#endif
+    SPH_LAUNCH(SPH_K_SCAN, sgrid, ctx->stream)(ctx->dp, ctx->counters, ctx->cnt, ctx->cell_start, ctx->tile_total,
                                                          ctx->cfg.nranks > 1 ? ctx->send[0] : nullptr,
                                                          ctx->cfg.nranks > 1 ? ctx->send[1] : nullptr,
                                                          (which == 1 && with_unpack && (refresh || ctx->cur_x)) ? 1 : 0);
+#if SPH_SORT_SRC
+    SPH_LAUNCH(k_scatter_uid, ctx->sort_grid, ctx->stream)(ctx->counters, ctx->cell_start, ctx->t_key, ctx->t_slot, su,
+                                                              ctx->ord_uid, ctx->tile_total, ctx->ntiles_max);
+    SPH_LAUNCH(k_reorder_src, ctx->sort_grid, ctx->stream)(ctx->dp, ctx->counters, ctx->cell_start, ctx->t_key,
+                                                              ctx->ord_uid, su, sp, sq, dp, dq, du, ctx->ord_key);
+#else
     SPH_LAUNCH(k_scatter, ctx->sort_grid, ctx->stream)(ctx->counters, ctx->cell_start, ctx->t_key, ctx->t_slot, su,
                                                           ctx->ord_uid, ctx->ord_src, ctx->ord_key, ctx->tile_total, ctx->ntiles_max);
     SPH_LAUNCH(k_reorder, ctx->sort_grid, ctx->stream)(ctx->dp, ctx->counters, ctx->cell_start, ctx->ord_key,
                                                           ctx->ord_uid, ctx->ord_src, sp, sq, dp, dq, du);
+#endif
     ctx->launches += 3;
     ctx->hp.gx0 = ctx->hp.gx0_new;     // the scan kernel did the same on the device
     ctx->hp.wx = ctx->hp.wx_new;

@@ -15,7 +15,9 @@
 #include "sph_device.cuh"
 
 #define SPH_THREADS 256
-#define SCAN_ITEMS 8
+#ifndef SCAN_ITEMS
+#define SCAN_ITEMS 8           // (a multiple of 4: the tile is loaded and stored as int4)
+#endif
 #define SCAN_TILE (SPH_THREADS * SCAN_ITEMS)      // cells per tile of the prefix sum (k_scan_apply)
 // SPH_TILE_ATOMICS=1 (round 2): the kernels that bin a position also add it to its scan tile's total (one atomic per
 // warp and tile), so the prefix sum needs no pass of its own over the cell populations to form the tile totals:
@@ -24,6 +26,22 @@
 #define SPH_TILE_ATOMICS 1
 #endif
 // resident blocks per SM the register allocation of each gather is held to (measured)
+// SPH_SORT_SRC=1 (round 2, second half): the sort's last two kernels walk the SOURCE order.  k_scatter_uid stores only a
+// uid into its cell's range (arrival order); k_reorder_src then reads key, uid and payload of a source entry coalesced,
+// ranks the uid inside its cell (cells of population 1 -- most of them -- need no look at all) and stores the entry at
+// its final place.  The (uid, source, key) triple no longer round-trips through memory: 16 bytes per entry less, and the
+// payload loads no longer hang behind the load of their own index.  Two entries per thread and trip in both kernels.
+#ifndef SPH_SORT_SRC
+#define SPH_SORT_SRC 0
+#endif
+// SPH_SCAN_FAST=1: k_scan_apply asks for its tile's populations BEFORE it forms the tile's offset (the DRAM latency
+// overlaps the reduction), forms offset, warp totals and bucket statistics behind ONE barrier instead of four, issues
+// one statistics atomic per tile instead of one per warp, and neither reads nor clears the populations of a tile
+// whose total is zero (the air above the fluid: half the table in the dam-break).
+#ifndef SPH_SCAN_FAST
+#define SPH_SCAN_FAST 0
+#endif
+
 #ifndef SPH_UNROLL
 #define SPH_UNROLL 4          // candidates per trip of the gather loops (loads issued together)
 #endif
@@ -72,6 +90,28 @@ constexpr int kGatherUnroll = SPH_UNROLL;     // (#pragma unroll takes a constan
 // lanes, 53 M issued warp instructions against the walk's 37 M.
 #ifndef SPH_RELAX_BF
 #define SPH_RELAX_BF 0
+#endif
+// SPH_PAIRMASK=1: the packed candidate loops of k_advect (trimmed loop) / k_coupling / k_density take a row's LAST odd
+// candidate in a masked pair trip instead of a separate scalar loop: the pair's second slot then reads the entry just past
+// the range (allocated, finite: the arrays are zero-filled and padded at creation) and is excluded by a validity
+// predicate folded into the membership test, so it adds an exact zero.  The per-instruction counts of round 2's capture
+// showed every warp paying the 28-40 instructions of the left-over loop in every row (5 rows per particle: 12-13 % of
+// all instructions of k_advect / k_density).  Same operations in the same order for every real candidate.
+#ifndef SPH_PAIRMASK
+#define SPH_PAIRMASK 0
+#endif
+#if SPH_PAIRMASK && !(SPH_PACKED && SPH_TRIM)
+#error "SPH_PAIRMASK is written for the packed, trimmed loops"
+#endif
+// SPH_RELAX_RARE=1: k_relax's mask walk without the coincident-pair rules in its loop.  The walk's pair physics is
+// straight-line (no branch per neighbour, the neighbours of a trip interleave); a pair with r2 <= 1e-12 -- the only case
+// fluid.c:583-588 treats differently -- raises a flag, and a flagged particle is redone from its entry position by the
+// exact walk.  Same operations in the same order for every other particle.  SPH_RELAX_TRIP: neighbours per trip.
+#ifndef SPH_RELAX_RARE
+#define SPH_RELAX_RARE 0
+#endif
+#ifndef SPH_RELAX_TRIP
+#define SPH_RELAX_TRIP 2
 #endif
 #if SPH_RELAX_PD4
 #define SPH_PD4_PARAM , float4 *__restrict__ pd
@@ -395,7 +435,13 @@ k_advect(const DevParams *__restrict__ Pp, int *__restrict__ counters,
 #if SPH_PACKED
             f32x2 vv = pk2(vx, vy);
 #pragma unroll kPackedUnroll
+#if SPH_PAIRMASK
+            for (; j < je; j += 2) {
+                const bool v1 = j + 1 < je;                 // the row's last trip may hold one candidate only
+#else
             for (; j + 1 < je; j += 2) {
+                const bool v1 = true;
+#endif
                 const f32x2 d0 = sub2(ld2(pos + j), pp), d1 = sub2(ld2(pos + j + 1), pp);
                 const float2 s0 = unpk2(mul2(d0, d0)), s1 = unpk2(mul2(d1, d1));
                 const float r20 = __fadd_rn(s0.x, s0.y), r21 = __fadd_rn(s1.x, s1.y);
@@ -403,7 +449,7 @@ k_advect(const DevParams *__restrict__ Pp, int *__restrict__ counters,
                 const f32x2 rs = pk2(rsqrt_approx(r20), rsqrt_approx(r21));
                 const f32x2 u = mul2(pk2(__fadd_rn(m0.x, m0.y), __fadd_rn(m1.x, m1.y)), rs);
                 const float2 uu = unpk2(u);
-                const bool hit0 = (r20 <= h2) & (uu.x > 0.0f), hit1 = (r21 <= h2) & (uu.y > 0.0f);
+                const bool hit0 = (r20 <= h2) & (uu.x > 0.0f), hit1 = v1 & (r21 <= h2) & (uu.y > 0.0f);
                 const f32x2 nw = fma2(mul2(pk2(r20, r21), rs), hh2, nhdt2);          // -(1 - r/h) dt/2
                 f32x2 t = mul2(mul2(mul2(u, fma2(beta2, u, sigma2)), nw), rs);
                 if (STAB) {
@@ -418,6 +464,9 @@ k_advect(const DevParams *__restrict__ Pp, int *__restrict__ counters,
                 vv = fma2(pk2(t1, t1), d1, vv);
             }
             { const float2 v2 = unpk2(vv); vx = v2.x; vy = v2.y; }
+#endif
+#if !SPH_PAIRMASK
+#if SPH_PACKED
 #pragma unroll 1
             for (; j < je; j++) {      // at most one left over
 #else
@@ -439,6 +488,7 @@ k_advect(const DevParams *__restrict__ Pp, int *__restrict__ counters,
                 vx = fmaf(t, dx, vx);
                 vy = fmaf(t, dy, vy);
             }
+#endif
             if (!(tmax <= tlim)) {      // the clamp may bind in this row (or something was not finite): exact body
                 vx = vx_row; vy = vy_row;
 #pragma unroll 1
@@ -622,7 +672,13 @@ k_coupling(const DevParams *__restrict__ Pp, const int *__restrict__ counters,
             int j = R.b[d];
             const int je = R.e[d];
 #pragma unroll kPackedUnroll
+#if SPH_PAIRMASK
+            for (; j < je; j += 2) {
+                const bool v1 = j + 1 < je;
+#else
             for (; j + 1 < je; j += 2) {
+                const bool v1 = true;
+#endif
                 const f32x2 d0 = sub2(ld2(pos + j), pp), d1 = sub2(ld2(pos + j + 1), pp);
                 const float2 s0 = unpk2(mul2(d0, d0)), s1 = unpk2(mul2(d1, d1));
                 const float r20 = __fadd_rn(s0.x, s0.y), r21 = __fadd_rn(s1.x, s1.y);
@@ -632,8 +688,11 @@ k_coupling(const DevParams *__restrict__ Pp, const int *__restrict__ counters,
                 const float2 uu = unpk2(u);
                 const float2 cj = unpk2(mul2(mul2(fma2(mul2(pk2(r20, r21), rs), nh2, one2), dt2), fma2(beta2, u, sigma2)));
                 c += (r20 <= h2 && uu.x > 0.0f) ? cj.x : 0.0f;
-                c += (r21 <= h2 && uu.y > 0.0f) ? cj.y : 0.0f;
+                c += (v1 && r21 <= h2 && uu.y > 0.0f) ? cj.y : 0.0f;
             }
+#endif
+#if !SPH_PAIRMASK
+#if SPH_PACKED
 #pragma unroll 1
             for (; j < je; j++) {      // at most one left over
 #else
@@ -652,6 +711,7 @@ k_coupling(const DevParams *__restrict__ Pp, const int *__restrict__ counters,
                 const float cj = wdt * fmaf(P.beta, u_in, P.sigma);
                 c += hit ? cj : 0.0f;
             }
+#endif
         }
         coupling[i] = c;
     }
@@ -930,6 +990,193 @@ k_scan_apply(DevParams *__restrict__ Pp, int *__restrict__ counters, int *__rest
     pdl_done();
 }
 
+#if SPH_SCAN_FAST
+// K3' (SPH_SCAN_FAST): see the flag's comment at the top.  Same arguments and results as k_scan_apply.
+__global__ void __launch_bounds__(SPH_THREADS)
+k_scan_apply_fast(DevParams *__restrict__ Pp, int *__restrict__ counters, int *__restrict__ cnt, int *__restrict__ cell_start,
+                  const int *__restrict__ tile_total, unsigned char *send_l, unsigned char *send_r, int end_of_step)
+{
+    pdl_enter();
+    constexpr int NW = SPH_THREADS / 32;
+    __shared__ int s_inc[NW], s_part[NW], s_max[NW], s_over[NW];
+    const int ncell = Pp->wx_new * Pp->sort_rows;
+    const int ntiles = (ncell + SCAN_TILE - 1) / SCAN_TILE;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int base = tile * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+        // the tile's own total counts exactly the increments its cells received (bin_position adds to both): zero means
+        // every population of the tile is zero already
+        const bool occupied = tile_total[tile] != 0;
+        int v[SCAN_ITEMS];
+        if (occupied) scan_load_tile(cnt, base, ncell, v);
+        else {
+#pragma unroll
+            for (int k = 0; k < SCAN_ITEMS; k++) v[k] = 0;
+        }
+        int part = 0;                                      // all preceding totals, coalesced
+        for (int idx = threadIdx.x; idx < tile; idx += SPH_THREADS) part += tile_total[idx];
+        int sum = 0, mx = 0, over = 0;
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; k++) { sum += v[k]; mx = max(mx, v[k]); over += v[k] > 100; }
+        int inc = sum;                                     // warp inclusive scan of the thread sums
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        part = __reduce_add_sync(0xffffffffu, part);
+        mx = __reduce_max_sync(0xffffffffu, mx);
+        over = __reduce_add_sync(0xffffffffu, over);
+        if (lane == 31) s_inc[warp] = inc;
+        if (lane == 0) { s_part[warp] = part; s_max[warp] = mx; s_over[warp] = over; }
+        __syncthreads();
+        int prefix = 0, warp_off = 0, block_total = 0;
+#pragma unroll
+        for (int w = 0; w < NW; w++) {
+            prefix += s_part[w];
+            const int sw = s_inc[w];
+            if (w < warp) warp_off += sw;
+            block_total += sw;
+        }
+        if (threadIdx.x == 0 && occupied) {
+            int m = 0, o = 0;
+#pragma unroll
+            for (int w = 0; w < NW; w++) { m = max(m, s_max[w]); o += s_over[w]; }
+            if (m > 0) atomicMax(&counters[CN_MAX_BUCKET], m);
+            if (o > 0) atomicAdd(&counters[CN_BUCKET_OVER], o);
+        }
+        int run = prefix + warp_off + (inc - sum);
+        if (base + SCAN_ITEMS <= ncell) {
+            int4 *dst = reinterpret_cast<int4 *>(cell_start + base);
+            int4 *zero = reinterpret_cast<int4 *>(cnt + base);
+#pragma unroll
+            for (int k = 0; k < SCAN_ITEMS / 4; k++) {
+                int4 o;
+                o.x = run; run += v[4 * k];
+                o.y = run; run += v[4 * k + 1];
+                o.z = run; run += v[4 * k + 2];
+                o.w = run; run += v[4 * k + 3];
+                dst[k] = o;
+                if (occupied) zero[k] = make_int4(0, 0, 0, 0);
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < SCAN_ITEMS; k++) {
+                const int idx = base + k;
+                if (idx < ncell) { cell_start[idx] = run; if (occupied) cnt[idx] = 0; }
+                run += v[k];
+            }
+        }
+        if (tile == ntiles - 1 && threadIdx.x == SPH_THREADS - 1) {
+            const int total = prefix + block_total;
+            cell_start[ncell] = total;
+            counters[CN_NSRC] = counters[CN_NTOT] + counters[CN_EXTRA];
+            counters[CN_EXTRA] = 0;
+            counters[CN_NTOT] = total;
+            counters[CN_NLOCAL] = 0;
+            Pp->gx0 = Pp->gx0_new;
+            Pp->wx = Pp->wx_new;
+            if (send_l) { msg_hdr(send_l)[0] = 0; msg_hdr(send_l)[1] = 0; }
+            if (send_r) { msg_hdr(send_r)[0] = 0; msg_hdr(send_r)[1] = 0; }
+            if (end_of_step) counters[CN_STEP] += 1;
+        }
+        __syncthreads();                                   // the shared arrays are reused by the block's next tile
+    }
+    pdl_done();
+}
+#endif
+
+#if SPH_SORT_SRC
+// -------------------------------------------------------------------------------------------
+// K4' (SPH_SORT_SRC) a source entry's uid into its cell's range, at its arrival slot.
+// -------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(SPH_THREADS)
+k_scatter_uid(const int *__restrict__ counters, const int *__restrict__ cell_start,
+              const int *__restrict__ t_key, const int *__restrict__ t_slot, const uint32_t *__restrict__ src_uid,
+              uint32_t *__restrict__ ord_uid, int *__restrict__ tile_total, int ntiles_max)
+{
+    pdl_enter();
+    const int n = counters[CN_NSRC];
+    const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gstride = gridDim.x * blockDim.x;
+#if SPH_TILE_ATOMICS
+    for (int t = gtid; t < ntiles_max; t += gstride) tile_total[t] = 0;
+#endif
+    for (int s0 = gtid; s0 < n; s0 += 2 * gstride) {
+        const int s1 = s0 + gstride;
+        const bool two = s1 < n;
+        // level 1: six independent coalesced loads; level 2: two cell offsets; then two stores nobody waits for
+        const int key0 = t_key[s0], key1 = two ? t_key[s1] : SPH_KEY_DROP;
+        const bool on0 = key0 != SPH_KEY_DROP, on1 = key1 != SPH_KEY_DROP;
+        const int slot0 = on0 ? t_slot[s0] : 0, slot1 = on1 ? t_slot[s1] : 0;
+        const uint32_t u0 = src_uid[s0], u1 = two ? src_uid[s1] : 0u;
+        const int b0 = on0 ? cell_start[key0 & SPH_KEY_MASK] : 0, b1 = on1 ? cell_start[key1 & SPH_KEY_MASK] : 0;
+        if (on0) ord_uid[b0 + slot0] = u0 & SPH_UID_MASK;
+        if (on1) ord_uid[b1 + slot1] = u1 & SPH_UID_MASK;
+    }
+    pdl_done();
+}
+
+// -------------------------------------------------------------------------------------------
+// K5' (SPH_SORT_SRC) canonical order inside each cell (ascending uid, as K5) and the physical reorder, walking the
+//     source order: key, uid and payload of an entry are coalesced first-level loads.
+// -------------------------------------------------------------------------------------------
+__device__ __forceinline__ int rank_in_cell(const uint32_t *__restrict__ ord_uid, int b, int e, uint32_t um)
+{
+    int rank = 0;
+    if (e - b > 1)                                         // alone in its cell: nothing to look at
+        for (int k = b; k < e; k++) rank += ord_uid[k] < um;
+    return rank;
+}
+
+__global__ void __launch_bounds__(SPH_THREADS)
+k_reorder_src(const DevParams *__restrict__ Pp, int *__restrict__ counters, const int *__restrict__ cell_start,
+              const int *__restrict__ t_key, const uint32_t *__restrict__ ord_uid, const uint32_t *__restrict__ src_uid,
+              const float2 *__restrict__ src_pos, const float2 *__restrict__ src_q,
+              float2 *__restrict__ dst_pos, float2 *__restrict__ dst_q, uint32_t *__restrict__ dst_uid, int *__restrict__ dst_key)
+{
+    pdl_enter();
+    const int n = counters[CN_NSRC];
+    const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gstride = gridDim.x * blockDim.x;
+    int locals = 0;
+    for (int s0 = gtid; s0 < n; s0 += 2 * gstride) {
+        const int s1 = s0 + gstride;
+        const bool two = s1 < n;
+        const int key0 = t_key[s0], key1 = two ? t_key[s1] : SPH_KEY_DROP;
+        const bool on0 = key0 != SPH_KEY_DROP, on1 = key1 != SPH_KEY_DROP;
+        uint32_t u0 = src_uid[s0], u1 = two ? src_uid[s1] : 0u;
+        float2 p0 = make_float2(0.0f, 0.0f), q0 = p0, p1 = p0, q1 = p0;
+        if (on0) { p0 = src_pos[s0]; q0 = src_q[s0]; }
+        if (on1) { p1 = src_pos[s1]; q1 = src_q[s1]; }
+        const int c0 = key0 & SPH_KEY_MASK, c1 = key1 & SPH_KEY_MASK;
+        int b0 = 0, e0 = 0, b1 = 0, e1 = 0;
+        if (on0) { b0 = cell_start[c0]; e0 = cell_start[c0 + 1]; }
+        if (on1) { b1 = cell_start[c1]; e1 = cell_start[c1 + 1]; }
+        if (on0) {
+            if (key0 & SPH_KEY_EMIG) u0 |= SPH_HALO_BIT;
+            const int dst = b0 + rank_in_cell(ord_uid, b0, e0, u0 & SPH_UID_MASK);
+            dst_pos[dst] = p0; dst_q[dst] = q0; dst_uid[dst] = u0;
+#if SPH_PIPE
+            dst_key[dst] = c0;
+#endif
+            locals += !(u0 & SPH_HALO_BIT);
+        }
+        if (on1) {
+            if (key1 & SPH_KEY_EMIG) u1 |= SPH_HALO_BIT;
+            const int dst = b1 + rank_in_cell(ord_uid, b1, e1, u1 & SPH_UID_MASK);
+            dst_pos[dst] = p1; dst_q[dst] = q1; dst_uid[dst] = u1;
+#if SPH_PIPE
+            dst_key[dst] = c1;
+#endif
+            locals += !(u1 & SPH_HALO_BIT);
+        }
+    }
+    pdl_done();
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) locals += __shfl_xor_sync(0xffffffffu, locals, o);
+    if ((threadIdx.x & 31) == 0 && locals) atomicAdd(&counters[CN_NLOCAL], locals);
+}
+#endif
+
 // -------------------------------------------------------------------------------------------
 // K4  scatter (uid, source index) to cell_start[key] + arrival slot.  Arrival order inside a
 //     cell is whatever the atomics produced; K5 makes it canonical.
@@ -1045,11 +1292,17 @@ k_density(const DevParams *__restrict__ Pp, int *__restrict__ counters,
 #if SPH_PACKED
                 int j = jb;
 #pragma unroll kPackedUnroll
+#if SPH_PAIRMASK
+                for (; j < je; j += 2) {
+                    const bool v1 = j + 1 < je;
+#else
                 for (; j + 1 < je; j += 2) {
+                    const bool v1 = true;
+#endif
                     const f32x2 d0 = sub2(ld2(pos + j), pp), d1 = sub2(ld2(pos + j + 1), pp);
                     const float2 s0 = unpk2(mul2(d0, d0)), s1 = unpk2(mul2(d1, d1));
                     const float r20 = __fadd_rn(s0.x, s0.y), r21 = __fadd_rn(s1.x, s1.y);
-                    const bool in0 = r20 <= h2, in1 = r21 <= h2;
+                    const bool in0 = r20 <= h2, in1 = v1 & (r21 <= h2);
                     m |= in0 ? bit : (sph_mask_t)0;
                     bit += bit;
                     m |= in1 ? bit : (sph_mask_t)0;
@@ -1062,6 +1315,9 @@ k_density(const DevParams *__restrict__ Pp, int *__restrict__ counters,
                     d += ww.y;
                     dn = fmaf(ww.y, w1, dn);
                 }
+#endif
+#if !SPH_PAIRMASK
+#if SPH_PACKED
 #pragma unroll 1
                 for (; j < je; j++) {      // at most one left over
 #else
@@ -1082,6 +1338,7 @@ k_density(const DevParams *__restrict__ Pp, int *__restrict__ counters,
                     d += w2;
                     dn = fmaf(w2, w, dn);
                 }
+#endif
             }
             nmask[(size_t)dd * P.cap + i] = m;
             nn += sph_mask_popc(m) + max(e - b - SPH_MASK_BITS, 0);     // candidates past the mask count as accepted
@@ -1291,7 +1548,84 @@ k_relax(const DevParams *__restrict__ Pp, int *__restrict__ counters,
             }
         }
         };
-#if SPH_RELAX_BF
+#if SPH_RELAX_RARE && !SPH_RELAX_BF
+        {
+            float r2min = 1.0f;                      // smallest squared distance met (one FMNMX per neighbour)
+#if !SPH_PACKED_RELAX
+            const float x_in = x, y_in = y;
+#endif
+            // one listed neighbour, no special cases; `on` = false for the filler slots of a row's last trip
+            auto pair_fast = [&](float2 q, float2 dj, bool on) {
+#if SPH_PACKED_RELAX
+                const f32x2 dd = sub2(pk2(q.x, q.y), pp);
+                const float2 sq = unpk2(mul2(dd, dd));
+                const float r2 = __fadd_rn(sq.x, sq.y);
+                r2min = fminf(r2min, r2);
+                const float2 ab = unpk2(fma2(pk2(dj.x, dj.y), K12, AB0));
+                const float rs = rsqrt_approx(r2);
+                const float w = fmaxf(fmaf(-r2 * rs, h_recip, 1.0f), 0.0f);
+                float s = fmaf(ab.y, w, ab.x) * w * rs;
+                s = on ? s : 0.0f;
+                xy = fma2(pk2(-s, -s), dd, xy);
+#else
+                const float dx = q.x - p.x, dy = q.y - p.y;
+                const float r2 = dist2(dx, dy);
+                r2min = fminf(r2min, r2);
+                const float A = fmaf(dj.x, K1, Ai), B = fmaf(dj.y, K2, Bi);
+                const float rs = rsqrt_approx(r2);
+                const float w = fmaxf(fmaf(-r2 * rs, h_recip, 1.0f), 0.0f);
+                float s = fmaf(B, w, A) * w * rs;
+                s = on ? s : 0.0f;
+                x = fmaf(-s, dx, x);
+                y = fmaf(-s, dy, y);
+#endif
+            };
+#pragma unroll
+            for (int d = 0; d < SPH_NROWS; d++) {
+                const int b = R.b[d];
+                sph_mask_t m = nmask[(size_t)d * P.cap + i];
+                while (m) {
+                    int jj[SPH_RELAX_TRIP];
+                    bool on[SPH_RELAX_TRIP];
+                    on[0] = true;
+                    jj[0] = b + sph_mask_ffs(m) - 1;
+                    m &= m - 1;
+#pragma unroll
+                    for (int t = 1; t < SPH_RELAX_TRIP; t++) {
+                        on[t] = m != 0;
+                        jj[t] = on[t] ? b + sph_mask_ffs(m) - 1 : jj[0];      // (a filler repeats the trip's first neighbour)
+                        m &= m - 1;
+                    }
+                    float2 qq[SPH_RELAX_TRIP], dj[SPH_RELAX_TRIP];
+#pragma unroll
+                    for (int t = 0; t < SPH_RELAX_TRIP; t++) {
+#if SPH_RELAX_PD4
+                        const float4 r4 = pd[jj[t]];
+                        qq[t] = make_float2(r4.x, r4.y); dj[t] = make_float2(r4.z, r4.w);
+#else
+                        qq[t] = pos[jj[t]]; dj[t] = dens[jj[t]];
+#endif
+                    }
+#pragma unroll
+                    for (int t = 0; t < SPH_RELAX_TRIP; t++) pair_fast(qq[t], dj[t], on[t]);
+                }
+                // the rare candidates beyond those a mask covers
+                for (int j = b + SPH_MASK_BITS; j < R.e[d]; j++) {
+                    const float2 q = pos[j];
+                    if (dist2(q.x - p.x, q.y - p.y) > h2 || j == i) continue;
+                    pair(j, q, dens[j]);
+                }
+            }
+            if (!(r2min > 1.0001e-12f)) {            // a (nearly) coincident pair: redo this particle with the reference's rules
+#if SPH_PACKED_RELAX
+                xy = pp;
+#else
+                x = x_in; y = y_in;
+#endif
+                walk_all();
+            }
+        }
+#elif SPH_RELAX_BF
         // SPH_RELAX_BF=1 (round 2): the row's first SPH_MASK_BITS candidates in CANDIDATE order, branch-free: a
         // candidate whose acceptance bit is off loads nothing (predicated loads) and contributes an exact zero, so
         // values and order of the sum are the walk's, but the index of a neighbour is a loop counter instead of

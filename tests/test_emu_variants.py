@@ -125,3 +125,146 @@ def test_branch_free_relax_loop_redoes_particles_with_coincident_neighbours(buil
         outs.append(b.download()[0])
     for f in ("x", "y", "v_x", "v_y"):
         assert np.array_equal(outs[0][f].view("u4"), outs[1][f].view("u4")), f
+
+
+SORT_DEFS = ("SPH_SORT_SRC=1", "SPH_SCAN_FAST=1")
+
+
+def run_order(libpath, name, warm, steps, gamma, monkeypatch):
+    """like run(), returning the resident ORDER (uids as stored) after each sort as well"""
+    monkeypatch.setattr(sph_b200, "_lib", sph_b200._bind(C.CDLL(libpath)))
+    z, t, tank_w, tank_h, h, _ = load_golden(name)
+    st = z[f"w{warm}_state"]
+    c = sph_b200.Context(tank_w, tank_h, h, len(st) + 64)
+    c.set_params(as_sph(t)); c.set_viscosity_stabilisation(gamma); c.upload(st)
+    c.step(steps)
+    c.advect(); c.sort()
+    a, ua = c.download(order=sph_b200.ORDER_CELL, include_halo=True)
+    c.density(); c.relax(); c.sort()
+    b, ub = c.download(order=sph_b200.ORDER_CELL, include_halo=True)
+    s = c.status()
+    return a, ua, b, ub, tuple(getattr(s, f) for f, _ in s._fields_)
+
+
+@pytest.mark.parametrize("items", [8, 4])
+@pytest.mark.parametrize("name,warm,gamma", [("default1508", 400, 0.0), ("block3000", 150, 0.0), ("goo_rect1508", 300, 0.5)])
+def test_source_order_sort_is_bit_identical_in_the_emulator(built_lib, monkeypatch, name, warm, gamma, items):
+    """SPH_SORT_SRC=1 + SPH_SCAN_FAST=1: the sort's kernels restructured (uid-only scatter, reorder walking the source
+    order, one-barrier scan that skips empty tiles).  A sort has exactly one correct result -- cells in key order,
+    ascending uid inside a cell -- so order, payload and every counter must equal the default build's.
+    (items = 4: scan tiles of 1024 cells, so that these small tanks have several tiles and empty ones among them.)"""
+    base = build_emu()
+    var = build_emu(defines=SORT_DEFS + (("SCAN_ITEMS=4",) if items == 4 else ()), name="libsph_emu_sortsrc%d.so" % items)
+    r0 = run_order(base, name, warm, 12, gamma, monkeypatch)
+    r1 = run_order(var, name, warm, 12, gamma, monkeypatch)
+    for k in (0, 2):
+        for f in ("x", "y", "v_x", "v_y", "x_prev", "y_prev"):
+            if f in r0[k].dtype.names:
+                assert np.array_equal(r0[k][f].view("u4"), r1[k][f].view("u4")), (k, f)
+    assert np.array_equal(r0[1], r1[1]) and np.array_equal(r0[3], r1[3])
+    assert r0[4] == r1[4]
+
+
+def test_source_order_sort_on_the_hostile_soup(built_lib, monkeypatch):
+    """coincident particles, a corner pile (cells of > 32 entries: the rank loop matters), particles on the walls"""
+    from test_gpu_parity import Cuda
+    outs = []
+    for lib in (build_emu(), build_emu(defines=SORT_DEFS, name="libsph_emu_sortsrc8.so")):
+        monkeypatch.setattr(sph_b200, "_lib", sph_b200._bind(C.CDLL(lib)))
+        z, t, tank_w, tank_h, h, _ = load_golden("default1508")
+        rng = np.random.default_rng(11)
+        n = 1200
+        st = np.zeros(n, z["w400_state"].dtype)
+        st["x"] = rng.uniform(0, tank_w, n); st["y"] = rng.uniform(0, tank_h * 0.3, n)
+        st["x"][:200] = st["x"][200:400]; st["y"][:200] = st["y"][200:400]
+        st["x"][400:560] = rng.uniform(0, 0.4 * h, 160); st["y"][400:560] = rng.uniform(0, 0.4 * h, 160)
+        st["x"][560:600] = 0.0; st["y"][600:640] = 0.0
+        st["v_x"] = rng.uniform(-3, 3, n); st["v_y"] = rng.uniform(-3, 3, n)
+        st["x_prev"] = st["x"]; st["y_prev"] = st["y"]
+        b = Cuda(tank_w, tank_h, h, n + 64)
+        b.set_params(t); b.upload(st); b.step(6)
+        outs.append(b.download(order=sph_b200.ORDER_CELL))
+    assert np.array_equal(outs[0][1], outs[1][1])
+    for f in ("x", "y", "v_x", "v_y"):
+        assert np.array_equal(outs[0][0][f].view("u4"), outs[1][0][f].view("u4")), f
+
+
+@pytest.mark.parametrize("trip", [2, 3])
+@pytest.mark.parametrize("name,warm,gamma", [("default1508", 400, 0.0), ("block3000", 150, 0.0), ("goo_rect1508", 300, 0.5)])
+def test_relax_walk_with_the_rare_pairs_out_of_line_is_bit_identical_in_the_emulator(built_lib, monkeypatch, name, warm, gamma, trip):
+    """SPH_RELAX_RARE=1: the mask walk's pair physics without the coincident-pair rules; flagged particles are redone."""
+    base = build_emu()
+    var = build_emu(defines=("SPH_RELAX_RARE=1", "SPH_RELAX_TRIP=%d" % trip), name="libsph_emu_rare%d.so" % trip)
+    d0, a0 = run(base, name, warm, 12, gamma, monkeypatch)
+    d1, a1 = run(var, name, warm, 12, gamma, monkeypatch)
+    for f in ("x", "y", "v_x", "v_y"):
+        assert np.array_equal(a0[f].view("u4"), a1[f].view("u4")), ("after the step", f)
+
+
+def test_relax_walk_with_the_rare_pairs_out_of_line_redoes_coincident_particles(built_lib, monkeypatch):
+    """the hostile soup again: 200 coincident pairs, a corner pile with rows longer than a mask, particles on the walls"""
+    from test_gpu_parity import Cuda
+    outs = []
+    for lib in (build_emu(), build_emu(defines=("SPH_RELAX_RARE=1", "SPH_RELAX_TRIP=2"), name="libsph_emu_rare2.so")):
+        monkeypatch.setattr(sph_b200, "_lib", sph_b200._bind(C.CDLL(lib)))
+        z, t, tank_w, tank_h, h, _ = load_golden("default1508")
+        rng = np.random.default_rng(11)
+        n = 1200
+        st = np.zeros(n, z["w400_state"].dtype)
+        st["x"] = rng.uniform(0, tank_w, n); st["y"] = rng.uniform(0, tank_h * 0.3, n)
+        st["x"][:200] = st["x"][200:400]; st["y"][:200] = st["y"][200:400]
+        st["x"][400:560] = rng.uniform(0, 0.4 * h, 160); st["y"][400:560] = rng.uniform(0, 0.4 * h, 160)
+        st["x"][560:600] = 0.0; st["y"][600:640] = 0.0
+        st["v_x"] = rng.uniform(-3, 3, n); st["v_y"] = rng.uniform(-3, 3, n)
+        st["x_prev"] = st["x"]; st["y_prev"] = st["y"]
+        b = Cuda(tank_w, tank_h, h, n + 64)
+        b.set_params(t); b.upload(st); b.step(6)
+        outs.append(b.download()[0])
+    for f in ("x", "y", "v_x", "v_y"):
+        assert np.array_equal(outs[0][f].view("u4"), outs[1][f].view("u4")), f
+
+
+ALL_R2B = ("SPH_PAIRMASK=1", "SPH_RELAX_RARE=1", "SPH_SORT_SRC=1", "SPH_SCAN_FAST=1")
+
+
+@pytest.mark.parametrize("defs,tag", [(("SPH_PAIRMASK=1",), "pm"), (ALL_R2B, "r2b")])
+@pytest.mark.parametrize("name,warm,gamma", [("default1508", 400, 0.0), ("block3000", 150, 0.0), ("goo_rect1508", 300, 0.5), ("gas1508", 200, 0.5)])
+def test_masked_pair_trips_are_bit_identical_in_the_emulator(built_lib, monkeypatch, name, warm, gamma, defs, tag):
+    """SPH_PAIRMASK=1: a row's odd last candidate rides in a masked pair trip (k_advect, k_coupling, k_density) instead of
+    a scalar left-over loop.  The masked slot adds an exact zero, so densities, masks (through the relaxation they
+    drive), positions and velocities must equal the default build's -- alone and together with the round's other
+    restructurings (r2b)."""
+    base = build_emu()
+    var = build_emu(defines=defs, name="libsph_emu_%s.so" % tag)
+    d0, a0 = run(base, name, warm, 12, gamma, monkeypatch)
+    d1, a1 = run(var, name, warm, 12, gamma, monkeypatch)
+    for f in ("density", "density_near", "x", "y"):
+        assert np.array_equal(d0[f].view("u4"), d1[f].view("u4")), ("density stage", f)
+    for f in ("x", "y", "v_x", "v_y"):
+        assert np.array_equal(a0[f].view("u4"), a1[f].view("u4")), ("after the step", f)
+
+
+def test_all_round2b_variants_on_the_hostile_soup(built_lib, monkeypatch):
+    """coincident pairs, a corner pile, particles on the walls, through every restructured loop at once; capacity
+    exactly the particle count, so the masked slot of the very last range reads the padding"""
+    from test_gpu_parity import Cuda
+    outs = []
+    for lib in (build_emu(), build_emu(defines=ALL_R2B, name="libsph_emu_r2b.so")):
+        monkeypatch.setattr(sph_b200, "_lib", sph_b200._bind(C.CDLL(lib)))
+        z, t, tank_w, tank_h, h, _ = load_golden("default1508")
+        rng = np.random.default_rng(11)
+        n = 1200
+        st = np.zeros(n, z["w400_state"].dtype)
+        st["x"] = rng.uniform(0, tank_w, n); st["y"] = rng.uniform(0, tank_h * 0.3, n)
+        st["x"][:200] = st["x"][200:400]; st["y"][:200] = st["y"][200:400]
+        st["x"][400:560] = rng.uniform(0, 0.4 * h, 160); st["y"][400:560] = rng.uniform(0, 0.4 * h, 160)
+        st["x"][560:600] = 0.0; st["y"][600:640] = 0.0
+        st["x"][640:660] = tank_w - 0.001; st["y"][640:660] = tank_h - 0.001      # the very last cell of the table
+        st["v_x"] = rng.uniform(-3, 3, n); st["v_y"] = rng.uniform(-3, 3, n)
+        st["x_prev"] = st["x"]; st["y_prev"] = st["y"]
+        b = Cuda(tank_w, tank_h, h, n)
+        b.set_params(t); b.upload(st); b.step(6)
+        outs.append(b.download(order=sph_b200.ORDER_CELL))
+    assert np.array_equal(outs[0][1], outs[1][1])
+    for f in ("x", "y", "v_x", "v_y"):
+        assert np.array_equal(outs[0][0][f].view("u4"), outs[1][0][f].view("u4")), f
