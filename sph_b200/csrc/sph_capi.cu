@@ -46,7 +46,7 @@ template <class... A> static PdlLauncher<A...> pdl_launcher(void (*k)(A...), int
 #define SPH_GRID_MULT 8          // blocks per SM of the gather kernels (0: one block per 256 entries of capacity)
 #endif
 #ifndef SPH_GRID_ADVECT
-#define SPH_GRID_ADVECT (SPH_GRID_MULT > 0 ? SPH_GRID_MULT : 1 << 20)
+#define SPH_GRID_ADVECT (SPH_GRID_MULT > 0 ? 2 * SPH_GRID_MULT : 1 << 20)
 #endif
 #ifndef SPH_GRID_DENSITY
 #define SPH_GRID_DENSITY (SPH_GRID_MULT > 0 ? 2 * SPH_GRID_MULT : 1 << 20)
@@ -83,6 +83,7 @@ struct sph_ctx {
     float visc_gamma, visc_min_dt_sigma;
     int *cnt, *cell_start, *t_key, *t_slot, *ord_src, *ord_key;
     uint32_t *ord_uid;
+    float4 *pv;                      // SPH_ADVECT_PV4: (x, y, vx, vy) of the resident entries after sort 2
     int *tile_total;                 // one population total per scan tile
     int ntiles_max;
     unsigned char *send[2], *recv[2];
@@ -233,6 +234,10 @@ extern "C" int sph_create(const sph_config *cfg, sph_ctx **out)
 #if SPH_RELAX_PD4
     CK(cudaMalloc(&ctx->pd, cap * sizeof(float4)));
 #endif
+#if SPH_ADVECT_PV4
+    CK(cudaMalloc(&ctx->pv, (cap + pad) * sizeof(float4)));
+    CK(cudaMemset(ctx->pv, 0, (cap + pad) * sizeof(float4)));
+#endif
     CK(cudaMalloc(&ctx->coupling, (cap + pad) * sizeof(float)));
     CK(cudaMemset(ctx->coupling, 0, (cap + pad) * sizeof(float)));
     CK(cudaMalloc(&ctx->dopt, sizeof(DevOptions)));
@@ -341,7 +346,7 @@ extern "C" void sph_destroy(sph_ctx *ctx)
     for (int i = 0; i < 2; i++) cudaFree(ctx->U[i]);
     cudaFree(ctx->dens); cudaFree(ctx->nmask); cudaFree(ctx->cnt); cudaFree(ctx->cell_start); cudaFree(ctx->t_key);
     cudaFree(ctx->t_slot); cudaFree(ctx->ord_src); cudaFree(ctx->ord_key); cudaFree(ctx->ord_uid); cudaFree(ctx->coords);
-    cudaFree(ctx->tile_total); cudaFree(ctx->counters); cudaFree(ctx->dp);
+    cudaFree(ctx->pv); cudaFree(ctx->tile_total); cudaFree(ctx->counters); cudaFree(ctx->dp);
     for (int s = 0; s < 2; s++) { cudaFree(ctx->send[s]); cudaFree(ctx->recv[s]); }
     for (int s = 0; s < 2; s++) if (ctx->peer[s]) cudaIpcCloseMemHandle(ctx->peer[s]);
     cudaFree(ctx->xchg); cudaFree(ctx->xt);
@@ -560,7 +565,11 @@ static int launch_sort(sph_ctx *ctx, int which, bool with_unpack = true, bool re
     SPH_LAUNCH(k_scatter_uid, ctx->sort_grid, ctx->stream)(ctx->counters, ctx->cell_start, ctx->t_key, ctx->t_slot, su,
                                                               ctx->ord_uid, ctx->tile_total, ctx->ntiles_max);
     SPH_LAUNCH(k_reorder_src, ctx->sort_grid, ctx->stream)(ctx->dp, ctx->counters, ctx->cell_start, ctx->t_key,
-                                                              ctx->ord_uid, su, sp, sq, dp, dq, du, ctx->ord_key);
+                                                              ctx->ord_uid, su, sp, sq, dp, dq, du, ctx->ord_key
+#if SPH_ADVECT_PV4
+                                                              , which == 1 ? ctx->pv : nullptr
+#endif
+                                                              );
 #else
     SPH_LAUNCH(k_scatter, ctx->sort_grid, ctx->stream)(ctx->counters, ctx->cell_start, ctx->t_key, ctx->t_slot, su,
                                                           ctx->ord_uid, ctx->ord_src, ctx->ord_key, ctx->tile_total, ctx->ntiles_max);
@@ -648,20 +657,25 @@ extern "C" int sph_exchange_due(sph_ctx *ctx)
 }
 
 
+#if SPH_ADVECT_PV4
+#define SPH_PV4_ARG , ctx->pv
+#else
+#define SPH_PV4_ARG
+#endif
 static int launch_advect(sph_ctx *ctx)
 {
     if (stabilised(ctx)) {
         SPH_LAUNCH(k_coupling, ctx->grid_advect, ctx->stream)(ctx->dp, ctx->counters, ctx->P[0], ctx->Q[0], ctx->cell_start, ctx->coupling, ctx->ord_key);
         SPH_LAUNCH(k_advect<true>, ctx->grid_advect, ctx->stream)(ctx->dp, ctx->counters, ctx->P[0], ctx->Q[0], ctx->U[0],
                                                             ctx->cell_start, ctx->P[1], ctx->cnt, ctx->t_key, ctx->t_slot,
-                                                            ctx->send[0], ctx->send[1], ctx->coupling, ctx->dopt, ctx->cur_x ? 1 : 0, ctx->ord_key, ctx->tile_total);
+                                                            ctx->send[0], ctx->send[1], ctx->coupling, ctx->dopt, ctx->cur_x ? 1 : 0, ctx->ord_key, ctx->tile_total SPH_PV4_ARG);
         ctx->launches += 2;
         CK(cudaGetLastError());
         return SPH_OK;
     }
     SPH_LAUNCH(k_advect<false>, ctx->grid_advect, ctx->stream)(ctx->dp, ctx->counters, ctx->P[0], ctx->Q[0], ctx->U[0],
                                                          ctx->cell_start, ctx->P[1], ctx->cnt, ctx->t_key, ctx->t_slot,
-                                                         ctx->send[0], ctx->send[1], nullptr, nullptr, ctx->cur_x ? 1 : 0, ctx->ord_key, ctx->tile_total);
+                                                         ctx->send[0], ctx->send[1], nullptr, nullptr, ctx->cur_x ? 1 : 0, ctx->ord_key, ctx->tile_total SPH_PV4_ARG);
     ctx->launches++;
     CK(cudaGetLastError());
     return SPH_OK;
@@ -924,6 +938,9 @@ extern "C" int sph_state_restore(sph_ctx *ctx)
     ctx->have_queued = false;
     ctx->force_x = true;
     for (int s = 0; s < 2; s++) CK(cudaMemsetAsync(ctx->send[s], 0, 16, ctx->stream));
+#if SPH_ADVECT_PV4
+    SPH_LAUNCH(k_interleave, ctx->sort_grid, ctx->stream)(ctx->counters, ctx->P[0], ctx->Q[0], ctx->pv);
+#endif
     return push_params(ctx);
 }
 

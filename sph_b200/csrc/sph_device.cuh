@@ -188,6 +188,20 @@ __device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) { f32x2 r; asm("sub.rn.f
 __device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 __device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
 __device__ __forceinline__ f32x2 ld2(const float2 *p) { return *reinterpret_cast<const f32x2 *>(p); }
+// Asynchronous global -> shared copies (LDGSTS): the per-particle inputs of a thread's NEXT particle travel into a
+// shared-memory slot of its own while the thread works through the current one (SPH_ASYNC, sph_kernels.cuh).  No register
+// is held and no warp waits for them; cp_async_wait<1>() returns when all but the most recently committed group of this
+// thread have landed, and a thread only ever reads the slots it filled itself, so no barrier is involved.
+__device__ __forceinline__ void cp_async4(void *smem, const void *g)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void *smem, const void *g)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 // Programmatic dependent launch (build variant -DSPH_PDL=1; default off, then this is empty and the machine code
 // of every kernel is unchanged).  Every kernel of the library starts with pdl_enter(): it waits until the grid
 // before it in the stream has completed and its memory is visible -- nothing a predecessor wrote, *Pp and the

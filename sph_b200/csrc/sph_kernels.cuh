@@ -16,7 +16,7 @@
 
 #define SPH_THREADS 256
 #ifndef SCAN_ITEMS
-#define SCAN_ITEMS 8           // (a multiple of 4: the tile is loaded and stored as int4)
+#define SCAN_ITEMS 4           // (a multiple of 4: the tile is loaded and stored as int4)
 #endif
 #define SCAN_TILE (SPH_THREADS * SCAN_ITEMS)      // cells per tile of the prefix sum (k_scan_apply)
 // SPH_TILE_ATOMICS=1 (round 2): the kernels that bin a position also add it to its scan tile's total (one atomic per
@@ -32,14 +32,14 @@
 // its final place.  The (uid, source, key) triple no longer round-trips through memory: 16 bytes per entry less, and the
 // payload loads no longer hang behind the load of their own index.  Two entries per thread and trip in both kernels.
 #ifndef SPH_SORT_SRC
-#define SPH_SORT_SRC 0
+#define SPH_SORT_SRC 1
 #endif
 // SPH_SCAN_FAST=1: k_scan_apply asks for its tile's populations BEFORE it forms the tile's offset (the DRAM latency
 // overlaps the reduction), forms offset, warp totals and bucket statistics behind ONE barrier instead of four, issues
 // one statistics atomic per tile instead of one per warp, and neither reads nor clears the populations of a tile
 // whose total is zero (the air above the fluid: half the table in the dam-break).
 #ifndef SPH_SCAN_FAST
-#define SPH_SCAN_FAST 0
+#define SPH_SCAN_FAST 1
 #endif
 
 #ifndef SPH_UNROLL
@@ -90,6 +90,55 @@ constexpr int kGatherUnroll = SPH_UNROLL;     // (#pragma unroll takes a constan
 // lanes, 53 M issued warp instructions against the walk's 37 M.
 #ifndef SPH_RELAX_BF
 #define SPH_RELAX_BF 0
+#endif
+// SPH_ASYNC (bit mask: 1 k_advect, 2 k_relax, 4 k_density): the per-particle inputs of a thread's next particle are
+// copied global -> shared asynchronously (cp.async, LDGSTS) while it works on the current one.  The stall samples of the
+// r2_final capture (profiles/r2_final_source_regions.md) put 19 % (k_advect) and 38 % (k_relax) of all samples on a chain
+// of dependent per-particle loads -- uid, then position, then one acceptance mask per row, then the previous position
+// -- each a full memory round trip that only other warps could hide; prefetching them into L1 (SPH_PIPE) did not help.
+// SPH_DEFER=1: the store of a particle's arrival slot waits for its atomic until the thread's next particle is done
+// (5 % of the samples sat on that store).
+#ifndef SPH_ASYNC
+#define SPH_ASYNC 2         // (measured: staging pays in k_relax only, profiles/r2_variants.md)
+#endif
+#ifndef SPH_DEFER
+#define SPH_DEFER 0
+#endif
+// SPH_PREFETCH (same bit mask; needs the matching SPH_ASYNC bit): when a thread has finished a particle it forms the
+// candidate rows of its NEXT one (whose position is already in its staging slot) and asks for the first and last line
+// of each row towards L1.  The candidate loads of the gathers hit L1 73-83 % of the time; what misses is the first
+// touch of a row by a block, and a warp that meets one in a trip waits an L2 round trip with 8 warps per scheduler to
+// cover it.
+#ifndef SPH_PREFETCH
+#define SPH_PREFETCH 0
+#endif
+#if (SPH_PREFETCH & ~SPH_ASYNC) != 0
+#error "SPH_PREFETCH needs the same bits in SPH_ASYNC (the next particle's position comes from its staging slot)"
+#endif
+#define SPH_DEFER_SLOT (SPH_PIPE || SPH_DEFER)
+// SPH_KEYROWS=1: a particle's candidate rows from the cell key its sort assigned (one more 4-byte load per particle)
+// instead of from its position: no IEEE divisions in the prologue of the three gathers (about 60 of its 100-110
+// instructions), and the ten cell_start loads no longer wait for them.  This is the first part of SPH_PIPE on its own.
+#ifndef SPH_KEYROWS
+#define SPH_KEYROWS 0
+#endif
+#define SPH_ROWS_FROM_KEY (SPH_PIPE || SPH_KEYROWS)
+// SPH_ADVECT_PV4=1 (needs SPH_SORT_SRC): the reorder of sort 2 also writes (x, y, vx, vy) records, and k_advect's candidate
+// loop reads one 16-byte record per candidate instead of a position and a velocity from two arrays: half the load
+// instructions and half the L1 tag look-ups of the loop (l1tex throughput, 45 % of peak, was its busiest unit after the
+// issue slots).  Same values, same arithmetic.
+#ifndef SPH_ADVECT_PV4
+#define SPH_ADVECT_PV4 0
+#endif
+#if SPH_ADVECT_PV4 && !(SPH_SORT_SRC && SPH_PACKED && SPH_TRIM)
+#error "SPH_ADVECT_PV4 is written for the source-order sort and the packed, trimmed loop"
+#endif
+#if SPH_ADVECT_PV4
+#define SPH_PV4_PARAM , float4 *__restrict__ pv
+#define SPH_PV4_CPARAM , const float4 *__restrict__ pv
+#else
+#define SPH_PV4_PARAM
+#define SPH_PV4_CPARAM
 #endif
 // SPH_PAIRMASK=1: the packed candidate loops of k_advect (trimmed loop) / k_coupling / k_density take a row's LAST odd
 // candidate in a masked pair trip instead of a separate scalar loop: the pair's second slot then reads the entry just past
@@ -205,6 +254,15 @@ __device__ __forceinline__ Rows candidate_rows_key(int key, const DevParams &P, 
         r.e[d] = __ldg(&cell_start[rb + c1 + 1]);
     }
     return r;
+}
+
+// first and last line of each candidate row towards L1 (rows span 1-2 lines of 128 bytes)
+template <class T>
+__device__ __forceinline__ void prefetch_rows(const Rows &R, const T *__restrict__ arr)
+{
+#pragma unroll
+    for (int d = 0; d < SPH_NROWS; d++)
+        if (R.e[d] > R.b[d]) { prefetch_l1(arr + R.b[d]); prefetch_l1(arr + R.e[d] - 1); }
 }
 
 // -------------------------------------------------------------------------------------------
@@ -350,7 +408,7 @@ k_advect(const DevParams *__restrict__ Pp, int *__restrict__ counters,
          const int *__restrict__ cell_start,
          float2 *__restrict__ pos_pred, int *__restrict__ cnt, int *__restrict__ t_key, int *__restrict__ t_slot,
          unsigned char *send_l, unsigned char *send_r, const float *__restrict__ coupling, const DevOptions *__restrict__ Op,
-         int xstep, const int *__restrict__ ckey, int *__restrict__ tile_total)
+         int xstep, const int *__restrict__ ckey, int *__restrict__ tile_total SPH_PV4_CPARAM)
 {
     // xstep: neighbours exchange after this prediction (always, except in the one-exchange build with an exchange
     // period > 1, where between exchanges the ghosts are advanced here like everything else; see sph_set_exchange_period)
@@ -364,13 +422,40 @@ k_advect(const DevParams *__restrict__ Pp, int *__restrict__ counters,
     const float h_recip = __fdiv_rn(1.0f, P.h);
     const float h2 = __fmul_rn(P.h, P.h);
     if (blockIdx.x == 0 && threadIdx.x == 0) { counters[CN_MAX_BUCKET] = 0; counters[CN_COST] = 0; }
-#if SPH_PIPE
+#if SPH_ROWS_FROM_KEY
     const float inv_wx = 1.0f / (float)P.wx;
+#endif
+#if SPH_DEFER_SLOT
     int slot_i = -1, slot_v = 0;                                        // arrival slot whose store is still owed
+#endif
+#if SPH_ASYNC & 1
+    // staging slots of this thread: [buffer][thread]
+    __shared__ uint32_t s_uid[2][SPH_THREADS];
+    __shared__ float2 s_pos[2][SPH_THREADS], s_vel[2][SPH_THREADS];
+    const int gstride = gridDim.x * blockDim.x;
+    int buf = 0;
+    {
+        const int i0 = blockIdx.x * blockDim.x + threadIdx.x;
+        if (i0 < n) { cp_async4(&s_uid[0][threadIdx.x], uid + i0); cp_async8(&s_pos[0][threadIdx.x], pos + i0); cp_async8(&s_vel[0][threadIdx.x], vel + i0); }
+        cp_async_commit();
+    }
 #endif
 
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+#if SPH_ASYNC & 1
+        {
+            const int nx = i + gstride;
+            if (nx < n) { cp_async4(&s_uid[buf ^ 1][threadIdx.x], uid + nx); cp_async8(&s_pos[buf ^ 1][threadIdx.x], pos + nx); cp_async8(&s_vel[buf ^ 1][threadIdx.x], vel + nx); }
+            cp_async_commit();
+            cp_async_wait<1>();                                         // this particle's copies (the group before) have landed
+        }
+        const uint32_t u = s_uid[buf][threadIdx.x];
+        const float2 p = s_pos[buf][threadIdx.x];
+        const float2 v0 = s_vel[buf][threadIdx.x];
+        buf ^= 1;
+#else
         const uint32_t u = uid[i];
+#endif
 #if SPH_PIPE
         // all of this particle's inputs are requested before the first of them is looked at
         const float2 p = pos[i];
@@ -383,14 +468,17 @@ k_advect(const DevParams *__restrict__ Pp, int *__restrict__ counters,
 #endif
         // ghosts are replaced at every exchange; in the one-exchange mode there are steps without one (exchange period > 1),
         // in which a ghost is advanced here like everything else
+#if SPH_KEYROWS && !SPH_PIPE
+        const int key_i = ckey[i];
+#endif
         const bool ghost = (u & SPH_HALO_BIT) != 0;
         if (ghost && (xstep || !P.one_x)) { t_key[i] = SPH_KEY_DROP; continue; }
-#if !SPH_PIPE
+#if !SPH_PIPE && !(SPH_ASYNC & 1)
         const float2 p = pos[i];
         const float2 v0 = vel[i];
 #endif
         float vx = v0.x, vy = v0.y + gdt;                               // apply_gravity
-#if SPH_PIPE
+#if SPH_ROWS_FROM_KEY
         const Rows R = candidate_rows_key(key_i, P, inv_wx, cell_start);
 #else
         const Rows R = candidate_rows(p, P, cell_start);
@@ -442,10 +530,17 @@ k_advect(const DevParams *__restrict__ Pp, int *__restrict__ counters,
             for (; j + 1 < je; j += 2) {
                 const bool v1 = true;
 #endif
+#if SPH_ADVECT_PV4
+                const float4 c0 = pv[j], c1 = pv[j + 1];
+                const f32x2 d0 = sub2(pk2(c0.x, c0.y), pp), d1 = sub2(pk2(c1.x, c1.y), pp);
+                const f32x2 w0 = sub2(v0p, pk2(c0.z, c0.w)), w1 = sub2(v0p, pk2(c1.z, c1.w));
+#else
                 const f32x2 d0 = sub2(ld2(pos + j), pp), d1 = sub2(ld2(pos + j + 1), pp);
+                const f32x2 w0 = sub2(v0p, ld2(vel + j)), w1 = sub2(v0p, ld2(vel + j + 1));
+#endif
                 const float2 s0 = unpk2(mul2(d0, d0)), s1 = unpk2(mul2(d1, d1));
                 const float r20 = __fadd_rn(s0.x, s0.y), r21 = __fadd_rn(s1.x, s1.y);
-                const float2 m0 = unpk2(mul2(sub2(v0p, ld2(vel + j)), d0)), m1 = unpk2(mul2(sub2(v0p, ld2(vel + j + 1)), d1));
+                const float2 m0 = unpk2(mul2(w0, d0)), m1 = unpk2(mul2(w1, d1));
                 const f32x2 rs = pk2(rsqrt_approx(r20), rsqrt_approx(r21));
                 const f32x2 u = mul2(pk2(__fadd_rn(m0.x, m0.y), __fadd_rn(m1.x, m1.y)), rs);
                 const float2 uu = unpk2(u);
@@ -612,14 +707,22 @@ k_advect(const DevParams *__restrict__ Pp, int *__restrict__ counters,
                 }
             }
         }
-#if SPH_PIPE
+#if SPH_DEFER_SLOT
         if (slot_i >= 0) t_slot[slot_i] = slot_v;                       // the previous particle's: its atomic is back by now
         slot_i = bin_position_deferred(i, np, extra, P, cnt, t_key, counters, tile_total, slot_v, unsent) ? i : -1;
 #else
         bin_position(i, np, extra, P, cnt, t_key, t_slot, counters, tile_total, unsent);
 #endif
+#if SPH_PREFETCH & 1
+        if (i + gstride < n) {
+            cp_async_wait<0>();                                         // (issued a whole particle ago)
+            const Rows Rn = candidate_rows(s_pos[buf][threadIdx.x], P, cell_start);
+            prefetch_rows(Rn, pos);
+            prefetch_rows(Rn, vel);
+        }
+#endif
     }
-#if SPH_PIPE
+#if SPH_DEFER_SLOT
     if (slot_i >= 0) t_slot[slot_i] = slot_v;
 #endif
     pdl_done();
@@ -648,16 +751,18 @@ k_coupling(const DevParams *__restrict__ Pp, const int *__restrict__ counters,
     const int n = counters[CN_NTOT];
     const float h_recip = __fdiv_rn(1.0f, P.h);
     const float h2 = __fmul_rn(P.h, P.h);
-#if SPH_PIPE
+#if SPH_ROWS_FROM_KEY
     const float inv_wx = 1.0f / (float)P.wx;
 #endif
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const float2 p = pos[i];
         const float2 v0 = vel[i];
         float c = 0.0f;
-#if SPH_PIPE
+#if SPH_ROWS_FROM_KEY
         const Rows R = candidate_rows_key(ckey[i], P, inv_wx, cell_start);
+#if SPH_PIPE
         { const int nx = i + gridDim.x * blockDim.x; if (nx < n) { prefetch_l1(pos + nx); prefetch_l1(vel + nx); prefetch_l1(ckey + nx); } }
+#endif
 #else
         const Rows R = candidate_rows(p, P, cell_start);
 #endif
@@ -852,6 +957,7 @@ __device__ __forceinline__ void scan_load_tile(const int *__restrict__ cnt, int 
     }
 }
 
+#if !SPH_TILE_ATOMICS
 __global__ void __launch_bounds__(SPH_THREADS)
 k_scan_totals(const DevParams *__restrict__ Pp, int *__restrict__ counters, const int *__restrict__ cnt,
               int *__restrict__ tile_total)
@@ -887,6 +993,9 @@ k_scan_totals(const DevParams *__restrict__ Pp, int *__restrict__ counters, cons
     pdl_done();
 }
 
+#endif
+
+#if !(SPH_SCAN_FAST && SPH_TILE_ATOMICS)
 __global__ void __launch_bounds__(SPH_THREADS)
 k_scan_apply(DevParams *__restrict__ Pp, int *__restrict__ counters, int *__restrict__ cnt, int *__restrict__ cell_start,
              const int *__restrict__ tile_total, unsigned char *send_l, unsigned char *send_r, int end_of_step)
@@ -989,6 +1098,8 @@ k_scan_apply(DevParams *__restrict__ Pp, int *__restrict__ counters, int *__rest
     }
     pdl_done();
 }
+
+#endif
 
 #if SPH_SCAN_FAST
 // K3' (SPH_SCAN_FAST): see the flag's comment at the top.  Same arguments and results as k_scan_apply.
@@ -1132,7 +1243,8 @@ __global__ void __launch_bounds__(SPH_THREADS)
 k_reorder_src(const DevParams *__restrict__ Pp, int *__restrict__ counters, const int *__restrict__ cell_start,
               const int *__restrict__ t_key, const uint32_t *__restrict__ ord_uid, const uint32_t *__restrict__ src_uid,
               const float2 *__restrict__ src_pos, const float2 *__restrict__ src_q,
-              float2 *__restrict__ dst_pos, float2 *__restrict__ dst_q, uint32_t *__restrict__ dst_uid, int *__restrict__ dst_key)
+              float2 *__restrict__ dst_pos, float2 *__restrict__ dst_q, uint32_t *__restrict__ dst_uid, int *__restrict__ dst_key
+              SPH_PV4_PARAM)
 {
     pdl_enter();
     const int n = counters[CN_NSRC];
@@ -1155,7 +1267,10 @@ k_reorder_src(const DevParams *__restrict__ Pp, int *__restrict__ counters, cons
             if (key0 & SPH_KEY_EMIG) u0 |= SPH_HALO_BIT;
             const int dst = b0 + rank_in_cell(ord_uid, b0, e0, u0 & SPH_UID_MASK);
             dst_pos[dst] = p0; dst_q[dst] = q0; dst_uid[dst] = u0;
-#if SPH_PIPE
+#if SPH_ADVECT_PV4
+            if (pv) pv[dst] = make_float4(p0.x, p0.y, q0.x, q0.y);
+#endif
+#if SPH_ROWS_FROM_KEY
             dst_key[dst] = c0;
 #endif
             locals += !(u0 & SPH_HALO_BIT);
@@ -1164,7 +1279,10 @@ k_reorder_src(const DevParams *__restrict__ Pp, int *__restrict__ counters, cons
             if (key1 & SPH_KEY_EMIG) u1 |= SPH_HALO_BIT;
             const int dst = b1 + rank_in_cell(ord_uid, b1, e1, u1 & SPH_UID_MASK);
             dst_pos[dst] = p1; dst_q[dst] = q1; dst_uid[dst] = u1;
-#if SPH_PIPE
+#if SPH_ADVECT_PV4
+            if (pv) pv[dst] = make_float4(p1.x, p1.y, q1.x, q1.y);
+#endif
+#if SPH_ROWS_FROM_KEY
             dst_key[dst] = c1;
 #endif
             locals += !(u1 & SPH_HALO_BIT);
@@ -1177,6 +1295,7 @@ k_reorder_src(const DevParams *__restrict__ Pp, int *__restrict__ counters, cons
 }
 #endif
 
+#if !SPH_SORT_SRC
 // -------------------------------------------------------------------------------------------
 // K4  scatter (uid, source index) to cell_start[key] + arrival slot.  Arrival order inside a
 //     cell is whatever the atomics produced; K5 makes it canonical.
@@ -1241,6 +1360,8 @@ k_reorder(const DevParams *__restrict__ Pp, int *__restrict__ counters, const in
     if ((threadIdx.x & 31) == 0 && locals) atomicAdd(&counters[CN_NLOCAL], locals);
 }
 
+#endif      // !SPH_SORT_SRC
+
 // -------------------------------------------------------------------------------------------
 // K6  calculate_density (fluid.c:527-539) over every pair within h, as a gather.
 //     Output: (density, density_near) per resident entry, ghosts included (their pressure is
@@ -1257,16 +1378,39 @@ k_density(const DevParams *__restrict__ Pp, int *__restrict__ counters,
     const float h_recip = __fdiv_rn(1.0f, P.h);
     const float h2 = __fmul_rn(P.h, P.h);
     int cost = 0;
-#if SPH_PIPE
+#if SPH_ROWS_FROM_KEY
     const float inv_wx = 1.0f / (float)P.wx;
 #endif
+#if SPH_ASYNC & 4
+    __shared__ float2 s_pos[2][SPH_THREADS];
+    const int gstride = gridDim.x * blockDim.x;
+    int buf = 0;
+    {
+        const int i0 = blockIdx.x * blockDim.x + threadIdx.x;
+        if (i0 < n) cp_async8(&s_pos[0][threadIdx.x], pos + i0);
+        cp_async_commit();
+    }
+#endif
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+#if SPH_ASYNC & 4
+        {
+            const int nx = i + gstride;
+            if (nx < n) cp_async8(&s_pos[buf ^ 1][threadIdx.x], pos + nx);
+            cp_async_commit();
+            cp_async_wait<1>();
+        }
+        const float2 p = s_pos[buf][threadIdx.x];
+        buf ^= 1;
+#else
         const float2 p = pos[i];
+#endif
         float d = 0.0f, dn = 0.0f;
         int nn = 0;
-#if SPH_PIPE
+#if SPH_ROWS_FROM_KEY
         const Rows R = candidate_rows_key(ckey[i], P, inv_wx, cell_start);
+#if SPH_PIPE
         { const int nx = i + gridDim.x * blockDim.x; if (nx < n) { prefetch_l1(pos + nx); prefetch_l1(ckey + nx); } }
+#endif
 #else
         const Rows R = candidate_rows(p, P, cell_start);
 #endif
@@ -1352,6 +1496,12 @@ k_density(const DevParams *__restrict__ Pp, int *__restrict__ counters,
         // fails this cheap, conservative test is counted again exactly, with the reference's owner rule (rare path).
         if (nn > SPH_REF_MAX_NEIGHBORS) atomicAdd(&counters[CN_NEIGH_OVER], 1);      // (sph_get_status then counts exactly)
         cost += SPH_COST_BASE + nn;
+#if SPH_PREFETCH & 4
+        if (i + gstride < n) {
+            cp_async_wait<0>();
+            prefetch_rows(candidate_rows(s_pos[buf][threadIdx.x], P, cell_start), pos);
+        }
+#endif
     }
     pdl_done();
     // work estimate of this slab (one atomic per warp per launch): input of the cost-based edge policy
@@ -1376,8 +1526,10 @@ k_relax(const DevParams *__restrict__ Pp, int *__restrict__ counters,
     pdl_enter();
     const DevParams P = *Pp;
     const int n = counters[CN_NTOT];
-#if SPH_PIPE
+#if SPH_ROWS_FROM_KEY
     const float inv_wx = 1.0f / (float)P.wx;
+#endif
+#if SPH_DEFER_SLOT
     int slot_i = -1, slot_v = 0;                                        // arrival slot whose store is still owed
 #endif
     const float dt = P.dt, dt2 = dt * dt;
@@ -1387,8 +1539,60 @@ k_relax(const DevParams *__restrict__ Pp, int *__restrict__ counters,
     const float K1 = dt2 * P.k, K2 = dt2 * P.k_near, Cs = dt2 * P.k_spring * h * 0.5f;
     if (blockIdx.x == 0 && threadIdx.x == 0) counters[CN_MAX_BUCKET] = 0;
 
+#if SPH_ASYNC & 2
+    // staging slots of this thread: [buffer][thread]; everything k_relax reads once per particle
+    __shared__ uint32_t s_uid[2][SPH_THREADS];
+    __shared__ float2 s_pos[2][SPH_THREADS], s_dens[2][SPH_THREADS], s_prev[2][SPH_THREADS];
+    __shared__ sph_mask_t s_mask[2][SPH_NROWS][SPH_THREADS];
+#if SPH_KEYROWS
+    __shared__ int s_key[2][SPH_THREADS];
+#endif
+    static_assert(sizeof(sph_mask_t) == 4, "the staging copies move 4-byte masks");
+    const int gstride = gridDim.x * blockDim.x;
+    int buf = 0;
+    auto stage = [&](int b, int k) {
+        cp_async4(&s_uid[b][threadIdx.x], uid + k);
+        cp_async8(&s_pos[b][threadIdx.x], pos + k);
+        cp_async8(&s_dens[b][threadIdx.x], dens + k);
+        cp_async8(&s_prev[b][threadIdx.x], prev + k);
+#if SPH_KEYROWS
+        cp_async4(&s_key[b][threadIdx.x], ckey + k);
+#endif
+#pragma unroll
+        for (int d = 0; d < SPH_NROWS; d++) cp_async4(&s_mask[b][d][threadIdx.x], nmask + (size_t)d * P.cap + k);
+    };
+    {
+        const int i0 = blockIdx.x * blockDim.x + threadIdx.x;
+        if (i0 < n) stage(0, i0);
+        cp_async_commit();
+    }
+#endif
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+#if SPH_ASYNC & 2
+        {
+            const int nx = i + gstride;
+            if (nx < n) stage(buf ^ 1, nx);
+            cp_async_commit();
+            cp_async_wait<1>();                                         // this particle's copies (the group before) have landed
+        }
+        const int cur = buf;
+        buf ^= 1;
+        const uint32_t u = s_uid[cur][threadIdx.x];
+        const float2 p = s_pos[cur][threadIdx.x];
+        const float2 di = s_dens[cur][threadIdx.x];
+#if SPH_KEYROWS && !SPH_PIPE
+        const int key_i = s_key[cur][threadIdx.x];
+#endif
+#define SPH_ROW_MASK(d) s_mask[cur][d][threadIdx.x]
+#define SPH_PREV_I s_prev[cur][threadIdx.x]
+#else
         const uint32_t u = uid[i];
+#if SPH_KEYROWS && !SPH_PIPE
+        const int key_i = ckey[i];
+#endif
+#define SPH_ROW_MASK(d) nmask[(size_t)(d) * P.cap + i]
+#define SPH_PREV_I prev[i]
+#endif
 #if SPH_PIPE
         const float2 p = pos[i];
         const float2 di = dens[i];
@@ -1398,8 +1602,10 @@ k_relax(const DevParams *__restrict__ Pp, int *__restrict__ counters,
         const bool ghost = (u & SPH_HALO_BIT) != 0;
         if (ghost && !P.one_x) { t_key[i] = SPH_KEY_DROP; continue; }
 #if !SPH_PIPE
+#if !(SPH_ASYNC & 2)
         const float2 p = pos[i];
         const float2 di = dens[i];
+#endif
 #else
         {
             // this particle's late inputs (the masks of the rows after the first, its previous position) and the
@@ -1424,7 +1630,7 @@ k_relax(const DevParams *__restrict__ Pp, int *__restrict__ counters,
         const float Ai = fmaf(K1, di.x - 2.0f * P.rest_density, Cs);
         const float Bi = K2 * di.y;
         float x = p.x, y = p.y;
-#if SPH_PIPE
+#if SPH_ROWS_FROM_KEY
         // (the reference cell of this particle is only needed by the coincident-pair rule: formed there)
 #define SPH_GXI cell_coord(p.x, P.cell_h)
 #define SPH_GYI cell_coord(p.y, P.cell_h)
@@ -1520,7 +1726,7 @@ k_relax(const DevParams *__restrict__ Pp, int *__restrict__ counters,
             //  against 68 -- it loads position AND density of ~50 candidates instead of ~22 neighbours,
             //  and L1 wavefronts, not instruction issue, then bound the kernel.)
             const int b = R.b[d];
-            sph_mask_t m = nmask[(size_t)d * P.cap + i];
+            sph_mask_t m = SPH_ROW_MASK(d);
             while (m) {
                 // two neighbours per trip, all four loads (position + density of each) issued up front:
                 // load latency was this kernel's top stall (profiles/r1_div2_full.csv, long_scoreboard);
@@ -1583,7 +1789,7 @@ k_relax(const DevParams *__restrict__ Pp, int *__restrict__ counters,
 #pragma unroll
             for (int d = 0; d < SPH_NROWS; d++) {
                 const int b = R.b[d];
-                sph_mask_t m = nmask[(size_t)d * P.cap + i];
+                sph_mask_t m = SPH_ROW_MASK(d);
                 while (m) {
                     int jj[SPH_RELAX_TRIP];
                     bool on[SPH_RELAX_TRIP];
@@ -1640,7 +1846,7 @@ k_relax(const DevParams *__restrict__ Pp, int *__restrict__ counters,
 #pragma unroll
             for (int d = 0; d < SPH_NROWS; d++) {
                 const int b = R.b[d];
-                sph_mask_t m = nmask[(size_t)d * P.cap + i];
+                sph_mask_t m = SPH_ROW_MASK(d);
 #pragma unroll 4
                 for (int j = b; m != 0; j++, m >>= 1) {
                     const bool on = (m & 1) != 0;
@@ -1703,12 +1909,12 @@ k_relax(const DevParams *__restrict__ Pp, int *__restrict__ counters,
         { const float2 a = unpk2(xy); x = a.x; y = a.y; }
 #endif
         float2 np = boundary(make_float2(x, y), P);                     // fluid.c:649
-        const float2 pv = prev[i];
+        const float2 pv = SPH_PREV_I;
         const float2 v = make_float2(clamp5(__fdiv_rn(np.x - pv.x, dt)), clamp5(__fdiv_rn(np.y - pv.y, dt)));
         pos_out[i] = np;
         vel_out[i] = v;
         if (P.one_x) {
-#if SPH_PIPE
+#if SPH_DEFER_SLOT
             if (slot_i >= 0) t_slot[slot_i] = slot_v;
             slot_i = bin_position_deferred(i, np, ghost ? SPH_KEY_EMIG : 0, P, cnt, t_key, counters, tile_total, slot_v, !ghost) ? i : -1;
 #else
@@ -1728,21 +1934,44 @@ k_relax(const DevParams *__restrict__ Pp, int *__restrict__ counters,
                 else atomicAdd(&counters[CN_MSG_OVER], 1);
             }
         }
-#if SPH_PIPE
+#if SPH_DEFER_SLOT
         if (slot_i >= 0) t_slot[slot_i] = slot_v;                       // the previous particle's: its atomic is back by now
         // (a local outside the window can only be an emigrant that is still waiting for room in a message: kept)
         slot_i = bin_position_deferred(i, np, 0, P, cnt, t_key, counters, tile_total, slot_v, true) ? i : -1;
 #else
         bin_position(i, np, 0, P, cnt, t_key, t_slot, counters, tile_total, true);
 #endif
+#if SPH_PREFETCH & 2
+        if (i + gstride < n) {
+            cp_async_wait<0>();
+            const Rows Rn = candidate_rows(s_pos[buf][threadIdx.x], P, cell_start);
+            prefetch_rows(Rn, pos);
+            prefetch_rows(Rn, dens);
+        }
+#endif
     }
-#if SPH_PIPE
+#if SPH_DEFER_SLOT
     if (slot_i >= 0) t_slot[slot_i] = slot_v;
 #endif
 #undef SPH_GXI
 #undef SPH_GYI
+#undef SPH_ROW_MASK
+#undef SPH_PREV_I
     pdl_done();
 }
+
+#if SPH_ADVECT_PV4
+// (x, y, vx, vy) records of the resident entries rebuilt from the two arrays (sph_state_restore)
+__global__ void __launch_bounds__(SPH_THREADS)
+k_interleave(const int *__restrict__ counters, const float2 *__restrict__ pos, const float2 *__restrict__ vel, float4 *__restrict__ pv)
+{
+    const int n = counters[CN_NTOT];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float2 p = pos[i], v = vel[i];
+        pv[i] = make_float4(p.x, p.y, v.x, v.y);
+    }
+}
+#endif
 
 // -------------------------------------------------------------------------------------------
 // upload helper: bin freshly uploaded particles (sph_upload)

@@ -22,3 +22,8 @@ static inline float rsqrt_approx(float x) { return 1.0f / sqrtf(x); }
 static inline float sqrt_approx(float x) { return sqrtf(x); }
 static inline void pdl_enter() {}   // launches of the emulator are already serialised
 static inline void pdl_done() {}
+// asynchronous copies land at once (a fiber only reads the slots it filled itself)
+static inline void cp_async4(void *smem, const void *g) { memcpy(smem, g, 4); }
+static inline void cp_async8(void *smem, const void *g) { memcpy(smem, g, 8); }
+static inline void cp_async_commit() {}
+template <int N> static inline void cp_async_wait() {}
