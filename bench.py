@@ -52,7 +52,7 @@ def measured_traffic(kernel, n_particles):
     return e["dram_bytes_per_launch"]
 
 
-def profiled_limiter(kernel, source="r2_final_full.csv", launch_seconds=None, sm_mhz=None, n_particles=None, sms=148):
+def profiled_limiter(kernel, source="r2b_full.csv", launch_seconds=None, sm_mhz=None, n_particles=None, sms=148):
     """What actually bounds `kernel` according to the last `ncu --set full` capture summarised under profiles/
     (NOT measured in this run): issue-slot utilisation, active lanes per instruction and DRAM throughput.  The
     HBM roofline fraction is small because these gathers are instruction-issue bound.

@@ -55,7 +55,7 @@ template <class... A> static PdlLauncher<A...> pdl_launcher(void (*k)(A...), int
 #define SPH_GRID_RELAX (SPH_GRID_MULT > 0 ? SPH_GRID_MULT : 1 << 20)
 #endif
 #ifndef SPH_GRID_MULT_SORT
-#define SPH_GRID_MULT_SORT 8     // blocks per SM of the sort's streaming kernels (scan, scatter, reorder)
+#define SPH_GRID_MULT_SORT 4     // blocks per SM of the sort's streaming kernels (scan, scatter, reorder; 4 entries per thread and trip)
 #endif
 
 enum { ST_READY = 0, ST_ADVECTED, ST_SORTED1, ST_DENSITY, ST_RELAXED, ST_REQUEUED };

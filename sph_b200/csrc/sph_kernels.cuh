@@ -115,7 +115,8 @@ constexpr int kGatherUnroll = SPH_UNROLL;     // (#pragma unroll takes a constan
 #if (SPH_PREFETCH & ~SPH_ASYNC) != 0
 #error "SPH_PREFETCH needs the same bits in SPH_ASYNC (the next particle's position comes from its staging slot)"
 #endif
-#define SPH_DEFER_SLOT (SPH_PIPE || SPH_DEFER)
+#define SPH_DEFER_ADVECT (SPH_PIPE || (SPH_DEFER & 1))      // (SPH_DEFER is a bit mask like SPH_ASYNC: 1 k_advect, 2 k_relax)
+#define SPH_DEFER_RELAX (SPH_PIPE || (SPH_DEFER & 2))
 // SPH_KEYROWS=1: a particle's candidate rows from the cell key its sort assigned (one more 4-byte load per particle)
 // instead of from its position: no IEEE divisions in the prologue of the three gathers (about 60 of its 100-110
 // instructions), and the ten cell_start loads no longer wait for them.  This is the first part of SPH_PIPE on its own.
@@ -157,10 +158,10 @@ constexpr int kGatherUnroll = SPH_UNROLL;     // (#pragma unroll takes a constan
 // fluid.c:583-588 treats differently -- raises a flag, and a flagged particle is redone from its entry position by the
 // exact walk.  Same operations in the same order for every other particle.  SPH_RELAX_TRIP: neighbours per trip.
 #ifndef SPH_RELAX_RARE
-#define SPH_RELAX_RARE 0
+#define SPH_RELAX_RARE 1
 #endif
 #ifndef SPH_RELAX_TRIP
-#define SPH_RELAX_TRIP 2
+#define SPH_RELAX_TRIP 3
 #endif
 #if SPH_RELAX_PD4
 #define SPH_PD4_PARAM , float4 *__restrict__ pd
@@ -425,7 +426,7 @@ k_advect(const DevParams *__restrict__ Pp, int *__restrict__ counters,
 #if SPH_ROWS_FROM_KEY
     const float inv_wx = 1.0f / (float)P.wx;
 #endif
-#if SPH_DEFER_SLOT
+#if SPH_DEFER_ADVECT
     int slot_i = -1, slot_v = 0;                                        // arrival slot whose store is still owed
 #endif
 #if SPH_ASYNC & 1
@@ -707,7 +708,7 @@ k_advect(const DevParams *__restrict__ Pp, int *__restrict__ counters,
                 }
             }
         }
-#if SPH_DEFER_SLOT
+#if SPH_DEFER_ADVECT
         if (slot_i >= 0) t_slot[slot_i] = slot_v;                       // the previous particle's: its atomic is back by now
         slot_i = bin_position_deferred(i, np, extra, P, cnt, t_key, counters, tile_total, slot_v, unsent) ? i : -1;
 #else
@@ -722,7 +723,7 @@ k_advect(const DevParams *__restrict__ Pp, int *__restrict__ counters,
         }
 #endif
     }
-#if SPH_DEFER_SLOT
+#if SPH_DEFER_ADVECT
     if (slot_i >= 0) t_slot[slot_i] = slot_v;
 #endif
     pdl_done();
@@ -1198,6 +1199,11 @@ k_scan_apply_fast(DevParams *__restrict__ Pp, int *__restrict__ counters, int *_
 #endif
 
 #if SPH_SORT_SRC
+// entries per thread and trip of the two kernels below: every load of a level is issued for all of them before the
+// first is looked at (the kernels are bound by the latency of three dependent levels, not by bytes)
+#ifndef SPH_SORT_ITEMS
+#define SPH_SORT_ITEMS 4          // (1 / 2 / 4 / 8 measured: profiles/r2_variants.md)
+#endif
 // -------------------------------------------------------------------------------------------
 // K4' (SPH_SORT_SRC) a source entry's uid into its cell's range, at its arrival slot.
 // -------------------------------------------------------------------------------------------
@@ -1207,22 +1213,33 @@ k_scatter_uid(const int *__restrict__ counters, const int *__restrict__ cell_sta
               uint32_t *__restrict__ ord_uid, int *__restrict__ tile_total, int ntiles_max)
 {
     pdl_enter();
+    constexpr int K = SPH_SORT_ITEMS;
     const int n = counters[CN_NSRC];
     const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gstride = gridDim.x * blockDim.x;
 #if SPH_TILE_ATOMICS
     for (int t = gtid; t < ntiles_max; t += gstride) tile_total[t] = 0;
 #endif
-    for (int s0 = gtid; s0 < n; s0 += 2 * gstride) {
-        const int s1 = s0 + gstride;
-        const bool two = s1 < n;
-        // level 1: six independent coalesced loads; level 2: two cell offsets; then two stores nobody waits for
-        const int key0 = t_key[s0], key1 = two ? t_key[s1] : SPH_KEY_DROP;
-        const bool on0 = key0 != SPH_KEY_DROP, on1 = key1 != SPH_KEY_DROP;
-        const int slot0 = on0 ? t_slot[s0] : 0, slot1 = on1 ? t_slot[s1] : 0;
-        const uint32_t u0 = src_uid[s0], u1 = two ? src_uid[s1] : 0u;
-        const int b0 = on0 ? cell_start[key0 & SPH_KEY_MASK] : 0, b1 = on1 ? cell_start[key1 & SPH_KEY_MASK] : 0;
-        if (on0) ord_uid[b0 + slot0] = u0 & SPH_UID_MASK;
-        if (on1) ord_uid[b1 + slot1] = u1 & SPH_UID_MASK;
+    for (int s0 = gtid; s0 < n; s0 += K * gstride) {
+        // level 1: 3 K independent coalesced loads; level 2: K cell offsets; then K stores nobody waits for
+        int key[K], slot[K], b[K];
+        uint32_t u[K];
+        bool on[K];
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            const int s = s0 + k * gstride;
+            key[k] = s < n ? t_key[s] : SPH_KEY_DROP;
+            u[k] = s < n ? src_uid[s] : 0u;
+        }
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            on[k] = key[k] != SPH_KEY_DROP;
+            slot[k] = on[k] ? t_slot[s0 + k * gstride] : 0;
+        }
+#pragma unroll
+        for (int k = 0; k < K; k++) b[k] = on[k] ? cell_start[key[k] & SPH_KEY_MASK] : 0;
+#pragma unroll
+        for (int k = 0; k < K; k++)
+            if (on[k]) ord_uid[b[k] + slot[k]] = u[k] & SPH_UID_MASK;
     }
     pdl_done();
 }
@@ -1247,45 +1264,46 @@ k_reorder_src(const DevParams *__restrict__ Pp, int *__restrict__ counters, cons
               SPH_PV4_PARAM)
 {
     pdl_enter();
+    constexpr int K = SPH_SORT_ITEMS;
     const int n = counters[CN_NSRC];
     const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gstride = gridDim.x * blockDim.x;
     int locals = 0;
-    for (int s0 = gtid; s0 < n; s0 += 2 * gstride) {
-        const int s1 = s0 + gstride;
-        const bool two = s1 < n;
-        const int key0 = t_key[s0], key1 = two ? t_key[s1] : SPH_KEY_DROP;
-        const bool on0 = key0 != SPH_KEY_DROP, on1 = key1 != SPH_KEY_DROP;
-        uint32_t u0 = src_uid[s0], u1 = two ? src_uid[s1] : 0u;
-        float2 p0 = make_float2(0.0f, 0.0f), q0 = p0, p1 = p0, q1 = p0;
-        if (on0) { p0 = src_pos[s0]; q0 = src_q[s0]; }
-        if (on1) { p1 = src_pos[s1]; q1 = src_q[s1]; }
-        const int c0 = key0 & SPH_KEY_MASK, c1 = key1 & SPH_KEY_MASK;
-        int b0 = 0, e0 = 0, b1 = 0, e1 = 0;
-        if (on0) { b0 = cell_start[c0]; e0 = cell_start[c0 + 1]; }
-        if (on1) { b1 = cell_start[c1]; e1 = cell_start[c1 + 1]; }
-        if (on0) {
-            if (key0 & SPH_KEY_EMIG) u0 |= SPH_HALO_BIT;
-            const int dst = b0 + rank_in_cell(ord_uid, b0, e0, u0 & SPH_UID_MASK);
-            dst_pos[dst] = p0; dst_q[dst] = q0; dst_uid[dst] = u0;
-#if SPH_ADVECT_PV4
-            if (pv) pv[dst] = make_float4(p0.x, p0.y, q0.x, q0.y);
-#endif
-#if SPH_ROWS_FROM_KEY
-            dst_key[dst] = c0;
-#endif
-            locals += !(u0 & SPH_HALO_BIT);
+    for (int s0 = gtid; s0 < n; s0 += K * gstride) {
+        int key[K], b[K], e[K];
+        uint32_t u[K];
+        float2 p[K], q[K];
+        bool on[K];
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            const int s = s0 + k * gstride;
+            key[k] = s < n ? t_key[s] : SPH_KEY_DROP;
+            u[k] = s < n ? src_uid[s] : 0u;
         }
-        if (on1) {
-            if (key1 & SPH_KEY_EMIG) u1 |= SPH_HALO_BIT;
-            const int dst = b1 + rank_in_cell(ord_uid, b1, e1, u1 & SPH_UID_MASK);
-            dst_pos[dst] = p1; dst_q[dst] = q1; dst_uid[dst] = u1;
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            const int s = s0 + k * gstride;
+            on[k] = key[k] != SPH_KEY_DROP;
+            p[k] = q[k] = make_float2(0.0f, 0.0f);
+            b[k] = e[k] = 0;
+            if (on[k]) {
+                p[k] = src_pos[s]; q[k] = src_q[s];
+                const int c = key[k] & SPH_KEY_MASK;
+                b[k] = cell_start[c]; e[k] = cell_start[c + 1];
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            if (!on[k]) continue;
+            if (key[k] & SPH_KEY_EMIG) u[k] |= SPH_HALO_BIT;
+            const int dst = b[k] + rank_in_cell(ord_uid, b[k], e[k], u[k] & SPH_UID_MASK);
+            dst_pos[dst] = p[k]; dst_q[dst] = q[k]; dst_uid[dst] = u[k];
 #if SPH_ADVECT_PV4
-            if (pv) pv[dst] = make_float4(p1.x, p1.y, q1.x, q1.y);
+            if (pv) pv[dst] = make_float4(p[k].x, p[k].y, q[k].x, q[k].y);
 #endif
 #if SPH_ROWS_FROM_KEY
-            dst_key[dst] = c1;
+            dst_key[dst] = key[k] & SPH_KEY_MASK;
 #endif
-            locals += !(u1 & SPH_HALO_BIT);
+            locals += !(u[k] & SPH_HALO_BIT);
         }
     }
     pdl_done();
@@ -1529,7 +1547,7 @@ k_relax(const DevParams *__restrict__ Pp, int *__restrict__ counters,
 #if SPH_ROWS_FROM_KEY
     const float inv_wx = 1.0f / (float)P.wx;
 #endif
-#if SPH_DEFER_SLOT
+#if SPH_DEFER_RELAX
     int slot_i = -1, slot_v = 0;                                        // arrival slot whose store is still owed
 #endif
     const float dt = P.dt, dt2 = dt * dt;
@@ -1914,7 +1932,7 @@ k_relax(const DevParams *__restrict__ Pp, int *__restrict__ counters,
         pos_out[i] = np;
         vel_out[i] = v;
         if (P.one_x) {
-#if SPH_DEFER_SLOT
+#if SPH_DEFER_RELAX
             if (slot_i >= 0) t_slot[slot_i] = slot_v;
             slot_i = bin_position_deferred(i, np, ghost ? SPH_KEY_EMIG : 0, P, cnt, t_key, counters, tile_total, slot_v, !ghost) ? i : -1;
 #else
@@ -1934,7 +1952,7 @@ k_relax(const DevParams *__restrict__ Pp, int *__restrict__ counters,
                 else atomicAdd(&counters[CN_MSG_OVER], 1);
             }
         }
-#if SPH_DEFER_SLOT
+#if SPH_DEFER_RELAX
         if (slot_i >= 0) t_slot[slot_i] = slot_v;                       // the previous particle's: its atomic is back by now
         // (a local outside the window can only be an emigrant that is still waiting for room in a message: kept)
         slot_i = bin_position_deferred(i, np, 0, P, cnt, t_key, counters, tile_total, slot_v, true) ? i : -1;
@@ -1950,7 +1968,7 @@ k_relax(const DevParams *__restrict__ Pp, int *__restrict__ counters,
         }
 #endif
     }
-#if SPH_DEFER_SLOT
+#if SPH_DEFER_RELAX
     if (slot_i >= 0) t_slot[slot_i] = slot_v;
 #endif
 #undef SPH_GXI

@@ -127,14 +127,25 @@ def test_branch_free_relax_loop_redoes_particles_with_coincident_neighbours(buil
         assert np.array_equal(outs[0][f].view("u4"), outs[1][f].view("u4")), f
 
 
-# the default build's sort since round 2's second half: uid-only scatter, reorder walking the source order, one-barrier
-# scan over 1024-cell tiles that skips empty tiles, k_relax inputs staged with cp.async; R2A = what round 2 shipped first
-SORT_DEFS = ("SPH_SORT_SRC=1", "SPH_SCAN_FAST=1")
-R2A = ("SPH_SORT_SRC=0", "SPH_SCAN_FAST=0", "SPH_ASYNC=0", "SCAN_ITEMS=8")
+# ---------------------------------------------------------------------------------------------------------------
+# Round 2, second half.  The default build changed (profiles/r2_variants.md): source-order sort (uid-only scatter,
+# reorder with coalesced payload loads, four entries per trip), one-barrier scan over 1024-cell tiles that skips empty
+# tiles, k_relax inputs staged one particle ahead (cp.async on the GPU, a plain copy here), k_relax's mask walk with the
+# coincident-pair rules out of line.  R2A = the build round 2 shipped first: every one of those switched back.
+# A sort has exactly one correct result (cells in key order, ascending uid inside a cell) and none of the other changes
+# touches an operation or its order, so resident order, payload bits and counters must be equal.
+# (Three emulator builds for the whole section: each costs ~10 s of the CPU suite.)
+# ---------------------------------------------------------------------------------------------------------------
+R2A = ("SPH_SORT_SRC=0", "SPH_SCAN_FAST=0", "SPH_ASYNC=0", "SCAN_ITEMS=8", "SPH_RELAX_RARE=0")
+# other sizes of the same machinery: 2048-cell tiles, two entries per sort trip, two neighbours per relax trip
+SIZES = ("SCAN_ITEMS=8", "SPH_SORT_ITEMS=2", "SPH_RELAX_TRIP=2")
+# everything that was measured and rejected, switched on together: masked pair trips, staged inputs in all three
+# gathers, deferred slot store, (x, y, vx, vy) candidate records, rows from the sort key, L1 prefetch of the next rows
+REJECTED = ("SPH_PAIRMASK=1", "SPH_ASYNC=7", "SPH_DEFER=3", "SPH_ADVECT_PV4=1", "SPH_KEYROWS=1", "SPH_PREFETCH=7")
 
 
 def run_order(libpath, name, warm, steps, gamma, monkeypatch):
-    """like run(), returning the resident ORDER (uids as stored) after each sort as well"""
+    """like run(), returning the resident ORDER (uids as stored, ghosts included) after each sort as well"""
     monkeypatch.setattr(sph_b200, "_lib", sph_b200._bind(C.CDLL(libpath)))
     z, t, tank_w, tank_h, h, _ = load_golden(name)
     st = z[f"w{warm}_state"]
@@ -143,200 +154,89 @@ def run_order(libpath, name, warm, steps, gamma, monkeypatch):
     c.step(steps)
     c.advect(); c.sort()
     a, ua = c.download(order=sph_b200.ORDER_CELL, include_halo=True)
-    c.density(); c.relax(); c.sort()
+    c.density()
+    d, _ = c.download(order=sph_b200.ORDER_CELL, include_halo=True)
+    c.relax(); c.sort()
     b, ub = c.download(order=sph_b200.ORDER_CELL, include_halo=True)
     s = c.status()
-    return a, ua, b, ub, tuple(getattr(s, f) for f, _ in s._fields_)
+    return a, ua, b, ub, tuple(getattr(s, f) for f, _ in s._fields_), d
 
 
-@pytest.mark.parametrize("name,warm,gamma,items", [("default1508", 400, 0.0, 4), ("block3000", 150, 0.0, 4), ("goo_rect1508", 300, 0.5, 4),
-                                                   ("block3000", 150, 0.0, 8)])
-def test_source_order_sort_is_bit_identical_in_the_emulator(built_lib, monkeypatch, name, warm, gamma, items):
-    """SPH_SORT_SRC=1 + SPH_SCAN_FAST=1: the sort's kernels restructured (uid-only scatter, reorder walking the source
-    order, one-barrier scan that skips empty tiles).  A sort has exactly one correct result -- cells in key order,
-    ascending uid inside a cell -- so order, payload and every counter must equal the default build's.
-    (items = 4: scan tiles of 1024 cells, so that these small tanks have several tiles and empty ones among them.)"""
-    base = build_emu(defines=R2A, name="libsph_emu_r2a.so")
-    var = build_emu(defines=SORT_DEFS + ("SCAN_ITEMS=%d" % items,), name="libsph_emu_sortsrc%d.so" % items)
-    r0 = run_order(base, name, warm, 12, gamma, monkeypatch)
-    r1 = run_order(var, name, warm, 12, gamma, monkeypatch)
+def same_run(r0, r1):
     for k in (0, 2):
-        for f in ("x", "y", "v_x", "v_y", "x_prev", "y_prev"):
-            if f in r0[k].dtype.names:
-                assert np.array_equal(r0[k][f].view("u4"), r1[k][f].view("u4")), (k, f)
+        for f in ("x", "y", "v_x", "v_y"):
+            assert np.array_equal(r0[k][f].view("u4"), r1[k][f].view("u4")), (k, f)
+    for f in ("density", "density_near"):
+        assert np.array_equal(r0[5][f].view("u4"), r1[5][f].view("u4")), f
     assert np.array_equal(r0[1], r1[1]) and np.array_equal(r0[3], r1[3])
     assert r0[4] == r1[4]
 
 
-def test_source_order_sort_on_the_hostile_soup(built_lib, monkeypatch):
-    """coincident particles, a corner pile (cells of > 32 entries: the rank loop matters), particles on the walls"""
+def soup(lib, monkeypatch, cap_extra=0):
+    """coincident pairs, a corner pile (cells of > 32 entries: rank loops, rows longer than a mask), particles on the
+    walls and in the very last cell of the table; capacity = particle count, so the last range ends at the padding"""
     from test_gpu_parity import Cuda
-    outs = []
-    for lib in (build_emu(defines=R2A, name="libsph_emu_r2a.so"), build_emu()):
-        monkeypatch.setattr(sph_b200, "_lib", sph_b200._bind(C.CDLL(lib)))
-        z, t, tank_w, tank_h, h, _ = load_golden("default1508")
-        rng = np.random.default_rng(11)
-        n = 1200
-        st = np.zeros(n, z["w400_state"].dtype)
-        st["x"] = rng.uniform(0, tank_w, n); st["y"] = rng.uniform(0, tank_h * 0.3, n)
-        st["x"][:200] = st["x"][200:400]; st["y"][:200] = st["y"][200:400]
-        st["x"][400:560] = rng.uniform(0, 0.4 * h, 160); st["y"][400:560] = rng.uniform(0, 0.4 * h, 160)
-        st["x"][560:600] = 0.0; st["y"][600:640] = 0.0
-        st["v_x"] = rng.uniform(-3, 3, n); st["v_y"] = rng.uniform(-3, 3, n)
-        st["x_prev"] = st["x"]; st["y_prev"] = st["y"]
-        b = Cuda(tank_w, tank_h, h, n + 64)
-        b.set_params(t); b.upload(st); b.step(6)
-        outs.append(b.download(order=sph_b200.ORDER_CELL))
-    assert np.array_equal(outs[0][1], outs[1][1])
+    monkeypatch.setattr(sph_b200, "_lib", sph_b200._bind(C.CDLL(lib)))
+    z, t, tank_w, tank_h, h, _ = load_golden("default1508")
+    rng = np.random.default_rng(11)
+    n = 1200
+    st = np.zeros(n, z["w400_state"].dtype)
+    st["x"] = rng.uniform(0, tank_w, n); st["y"] = rng.uniform(0, tank_h * 0.3, n)
+    st["x"][:200] = st["x"][200:400]; st["y"][:200] = st["y"][200:400]
+    st["x"][400:560] = rng.uniform(0, 0.4 * h, 160); st["y"][400:560] = rng.uniform(0, 0.4 * h, 160)
+    st["x"][560:600] = 0.0; st["y"][600:640] = 0.0
+    st["x"][640:660] = tank_w - 0.001; st["y"][640:660] = tank_h - 0.001
+    st["v_x"] = rng.uniform(-3, 3, n); st["v_y"] = rng.uniform(-3, 3, n)
+    st["x_prev"] = st["x"]; st["y_prev"] = st["y"]
+    b = Cuda(tank_w, tank_h, h, n + cap_extra)
+    b.set_params(t); b.upload(st); b.step(6)
+    return b.download(order=sph_b200.ORDER_CELL)
+
+
+def same_soup(a, b):
+    assert np.array_equal(a[1], b[1])
     for f in ("x", "y", "v_x", "v_y"):
-        assert np.array_equal(outs[0][0][f].view("u4"), outs[1][0][f].view("u4")), f
+        assert np.array_equal(a[0][f].view("u4"), b[0][f].view("u4")), f
 
 
-@pytest.mark.parametrize("trip", [2])
-@pytest.mark.parametrize("name,warm,gamma", [("block3000", 150, 0.0), ("goo_rect1508", 300, 0.5)])
-def test_relax_walk_with_the_rare_pairs_out_of_line_is_bit_identical_in_the_emulator(built_lib, monkeypatch, name, warm, gamma, trip):
-    """SPH_RELAX_RARE=1: the mask walk's pair physics without the coincident-pair rules; flagged particles are redone."""
-    base = build_emu()
-    var = build_emu(defines=("SPH_RELAX_RARE=1", "SPH_RELAX_TRIP=%d" % trip), name="libsph_emu_rare%d.so" % trip)
-    d0, a0 = run(base, name, warm, 12, gamma, monkeypatch)
-    d1, a1 = run(var, name, warm, 12, gamma, monkeypatch)
-    for f in ("x", "y", "v_x", "v_y"):
-        assert np.array_equal(a0[f].view("u4"), a1[f].view("u4")), ("after the step", f)
+@pytest.mark.parametrize("name,warm,gamma", [("default1508", 400, 0.0), ("block3000", 150, 0.0), ("goo_rect1508", 300, 0.5)])
+def test_default_build_equals_the_build_round_2_shipped_first(built_lib, monkeypatch, name, warm, gamma):
+    """(block3000 has 6240 sort cells = 7 scan tiles of the default build, the upper ones empty: the tile-skipping path)"""
+    same_run(run_order(build_emu(defines=R2A, name="libsph_emu_r2a.so"), name, warm, 12, gamma, monkeypatch),
+             run_order(build_emu(), name, warm, 12, gamma, monkeypatch))
 
 
-def test_relax_walk_with_the_rare_pairs_out_of_line_redoes_coincident_particles(built_lib, monkeypatch):
-    """the hostile soup again: 200 coincident pairs, a corner pile with rows longer than a mask, particles on the walls"""
-    from test_gpu_parity import Cuda
-    outs = []
-    for lib in (build_emu(), build_emu(defines=("SPH_RELAX_RARE=1", "SPH_RELAX_TRIP=2"), name="libsph_emu_rare2.so")):
-        monkeypatch.setattr(sph_b200, "_lib", sph_b200._bind(C.CDLL(lib)))
-        z, t, tank_w, tank_h, h, _ = load_golden("default1508")
-        rng = np.random.default_rng(11)
-        n = 1200
-        st = np.zeros(n, z["w400_state"].dtype)
-        st["x"] = rng.uniform(0, tank_w, n); st["y"] = rng.uniform(0, tank_h * 0.3, n)
-        st["x"][:200] = st["x"][200:400]; st["y"][:200] = st["y"][200:400]
-        st["x"][400:560] = rng.uniform(0, 0.4 * h, 160); st["y"][400:560] = rng.uniform(0, 0.4 * h, 160)
-        st["x"][560:600] = 0.0; st["y"][600:640] = 0.0
-        st["v_x"] = rng.uniform(-3, 3, n); st["v_y"] = rng.uniform(-3, 3, n)
-        st["x_prev"] = st["x"]; st["y_prev"] = st["y"]
-        b = Cuda(tank_w, tank_h, h, n + 64)
-        b.set_params(t); b.upload(st); b.step(6)
-        outs.append(b.download()[0])
-    for f in ("x", "y", "v_x", "v_y"):
-        assert np.array_equal(outs[0][f].view("u4"), outs[1][f].view("u4")), f
+def test_default_build_equals_the_build_round_2_shipped_first_on_the_hostile_soup(built_lib, monkeypatch):
+    """the coincident-pair rules live in the exact walk the straight-line loop falls back to"""
+    same_soup(soup(build_emu(defines=R2A, name="libsph_emu_r2a.so"), monkeypatch), soup(build_emu(), monkeypatch))
 
 
-ALL_R2B = ("SPH_PAIRMASK=1", "SPH_RELAX_RARE=1")
-
-
-@pytest.mark.parametrize("defs,tag", [(ALL_R2B, "r2b")])
-@pytest.mark.parametrize("name,warm,gamma", [("block3000", 150, 0.0), ("goo_rect1508", 300, 0.5)])
-def test_masked_pair_trips_are_bit_identical_in_the_emulator(built_lib, monkeypatch, name, warm, gamma, defs, tag):
-    """SPH_PAIRMASK=1: a row's odd last candidate rides in a masked pair trip (k_advect, k_coupling, k_density) instead of
-    a scalar left-over loop.  The masked slot adds an exact zero, so densities, masks (through the relaxation they
-    drive), positions and velocities must equal the default build's -- alone and together with the round's other
-    restructurings (r2b)."""
-    base = build_emu()
-    var = build_emu(defines=defs, name="libsph_emu_%s.so" % tag)
-    d0, a0 = run(base, name, warm, 12, gamma, monkeypatch)
-    d1, a1 = run(var, name, warm, 12, gamma, monkeypatch)
-    for f in ("density", "density_near", "x", "y"):
-        assert np.array_equal(d0[f].view("u4"), d1[f].view("u4")), ("density stage", f)
-    for f in ("x", "y", "v_x", "v_y"):
-        assert np.array_equal(a0[f].view("u4"), a1[f].view("u4")), ("after the step", f)
-
-
-def test_all_round2b_variants_on_the_hostile_soup(built_lib, monkeypatch):
-    """coincident pairs, a corner pile, particles on the walls, through every restructured loop at once; capacity
-    exactly the particle count, so the masked slot of the very last range reads the padding"""
-    from test_gpu_parity import Cuda
-    outs = []
-    for lib in (build_emu(defines=R2A, name="libsph_emu_r2a.so"), build_emu(defines=ALL_R2B, name="libsph_emu_r2b.so")):
-        monkeypatch.setattr(sph_b200, "_lib", sph_b200._bind(C.CDLL(lib)))
-        z, t, tank_w, tank_h, h, _ = load_golden("default1508")
-        rng = np.random.default_rng(11)
-        n = 1200
-        st = np.zeros(n, z["w400_state"].dtype)
-        st["x"] = rng.uniform(0, tank_w, n); st["y"] = rng.uniform(0, tank_h * 0.3, n)
-        st["x"][:200] = st["x"][200:400]; st["y"][:200] = st["y"][200:400]
-        st["x"][400:560] = rng.uniform(0, 0.4 * h, 160); st["y"][400:560] = rng.uniform(0, 0.4 * h, 160)
-        st["x"][560:600] = 0.0; st["y"][600:640] = 0.0
-        st["x"][640:660] = tank_w - 0.001; st["y"][640:660] = tank_h - 0.001      # the very last cell of the table
-        st["v_x"] = rng.uniform(-3, 3, n); st["v_y"] = rng.uniform(-3, 3, n)
-        st["x_prev"] = st["x"]; st["y_prev"] = st["y"]
-        b = Cuda(tank_w, tank_h, h, n)
-        b.set_params(t); b.upload(st); b.step(6)
-        outs.append(b.download(order=sph_b200.ORDER_CELL))
-    assert np.array_equal(outs[0][1], outs[1][1])
-    for f in ("x", "y", "v_x", "v_y"):
-        assert np.array_equal(outs[0][0][f].view("u4"), outs[1][0][f].view("u4")), f
+def test_tile_and_trip_sizes_do_not_matter(built_lib, monkeypatch):
+    var = build_emu(defines=SIZES, name="libsph_emu_sizes.so")
+    same_run(run_order(build_emu(), "block3000", 150, 12, 0.0, monkeypatch), run_order(var, "block3000", 150, 12, 0.0, monkeypatch))
+    same_soup(soup(build_emu(), monkeypatch), soup(var, monkeypatch))
 
 
 @pytest.mark.parametrize("name,warm,gamma", [("block3000", 150, 0.0), ("goo_rect1508", 300, 0.5)])
-def test_staged_inputs_and_deferred_slot_are_bit_identical_in_the_emulator(built_lib, monkeypatch, name, warm, gamma):
-    """SPH_ASYNC=7 + SPH_DEFER=1: per-particle inputs staged through shared memory one particle ahead (cp.async on the
-    GPU, a plain copy here) and the arrival-slot store deferred by one particle: the same values reach the same
-    arithmetic, so every bit and the resident order must equal the default build's."""
-    base = build_emu(defines=R2A, name="libsph_emu_r2a.so")
-    var = build_emu(defines=("SPH_ASYNC=7", "SPH_DEFER=1"), name="libsph_emu_async.so")
-    r0 = run_order(base, name, warm, 12, gamma, monkeypatch)
-    r1 = run_order(var, name, warm, 12, gamma, monkeypatch)
-    for k in (0, 2):
-        for f in ("x", "y", "v_x", "v_y"):
-            assert np.array_equal(r0[k][f].view("u4"), r1[k][f].view("u4")), (k, f)
-    assert np.array_equal(r0[1], r1[1]) and np.array_equal(r0[3], r1[3])
-    assert r0[4] == r1[4]
+def test_measured_and_rejected_variants_still_agree(built_lib, monkeypatch, name, warm, gamma):
+    """the A/B flags stay in the source with their numbers (profiles/r2_variants.md); they must keep building and
+    keep producing the default build's bits"""
+    var = build_emu(defines=REJECTED, name="libsph_emu_rejected.so")
+    same_run(run_order(build_emu(), name, warm, 12, gamma, monkeypatch), run_order(var, name, warm, 12, gamma, monkeypatch))
 
 
-R2B_FINAL = ("SPH_ADVECT_PV4=1",)
-
-
-@pytest.mark.parametrize("name,warm,gamma", [("block3000", 150, 0.0)])
-def test_interleaved_candidate_records_are_bit_identical_in_the_emulator(built_lib, monkeypatch, name, warm, gamma):
-    """SPH_ADVECT_PV4=1 on top of the source-order sort and the staged k_relax inputs: k_advect reads (x, y, vx, vy)
-    records written by sort 2's reorder.  Also through a save / restore (the records are rebuilt)."""
-    base = build_emu()
-    var = build_emu(defines=R2B_FINAL, name="libsph_emu_pv4.so")
-    r0 = run_order(base, name, warm, 12, gamma, monkeypatch)
-    r1 = run_order(var, name, warm, 12, gamma, monkeypatch)
-    for k in (0, 2):
-        for f in ("x", "y", "v_x", "v_y"):
-            assert np.array_equal(r0[k][f].view("u4"), r1[k][f].view("u4")), (k, f)
-    assert np.array_equal(r0[1], r1[1]) and np.array_equal(r0[3], r1[3])
-    # save, run on, restore, run again: same result as the first time
+def test_rejected_variants_on_the_soup_and_through_a_restore(built_lib, monkeypatch):
+    var = build_emu(defines=REJECTED, name="libsph_emu_rejected.so")
+    same_soup(soup(build_emu(), monkeypatch), soup(var, monkeypatch))
+    # SPH_ADVECT_PV4 keeps (x, y, vx, vy) records beside the arrays: rebuilt by sph_state_restore
     monkeypatch.setattr(sph_b200, "_lib", sph_b200._bind(C.CDLL(var)))
-    z, t, tank_w, tank_h, h, _ = load_golden(name)
-    st = z[f"w{warm}_state"]
+    z, t, tank_w, tank_h, h, _ = load_golden("block3000")
+    st = z["w150_state"]
     c = sph_b200.Context(tank_w, tank_h, h, len(st) + 64)
-    c.set_params(as_sph(t)); c.set_viscosity_stabilisation(gamma); c.upload(st)
+    c.set_params(as_sph(t)); c.upload(st)
     c.step(3); c.state_save(); c.step(5)
     a, _ = c.download()
     c.state_restore(); c.step(5)
     b, _ = c.download()
     for f in ("x", "y", "v_x", "v_y"):
         assert np.array_equal(a[f].view("u4"), b[f].view("u4")), f
-
-
-@pytest.mark.parametrize("name,warm,gamma", [("goo_rect1508", 300, 0.5)])
-def test_rows_from_the_sort_key_are_bit_identical_in_the_emulator(built_lib, monkeypatch, name, warm, gamma):
-    """SPH_KEYROWS=1 (with the source-order sort and the staged k_relax inputs): candidate rows from the cell key"""
-    base = build_emu()
-    var = build_emu(defines=("SPH_KEYROWS=1",), name="libsph_emu_keyrows.so")
-    r0 = run_order(base, name, warm, 12, gamma, monkeypatch)
-    r1 = run_order(var, name, warm, 12, gamma, monkeypatch)
-    for k in (0, 2):
-        for f in ("x", "y", "v_x", "v_y"):
-            assert np.array_equal(r0[k][f].view("u4"), r1[k][f].view("u4")), (k, f)
-    assert np.array_equal(r0[1], r1[1]) and np.array_equal(r0[3], r1[3])
-
-
-def test_row_prefetch_build_is_bit_identical_in_the_emulator(built_lib, monkeypatch):
-    """SPH_PREFETCH=7 (+ SPH_ASYNC=7): prefetches change no value; the build must run and agree"""
-    base = build_emu()
-    var = build_emu(defines=("SPH_ASYNC=7", "SPH_PREFETCH=7"), name="libsph_emu_pf.so")
-    r0 = run_order(base, "block3000", 150, 12, 0.0, monkeypatch)
-    r1 = run_order(var, "block3000", 150, 12, 0.0, monkeypatch)
-    for k in (0, 2):
-        for f in ("x", "y", "v_x", "v_y"):
-            assert np.array_equal(r0[k][f].view("u4"), r1[k][f].view("u4")), (k, f)
