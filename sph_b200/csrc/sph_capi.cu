@@ -52,10 +52,13 @@ template <class... A> static PdlLauncher<A...> pdl_launcher(void (*k)(A...), int
 #define SPH_GRID_DENSITY (SPH_GRID_MULT > 0 ? 2 * SPH_GRID_MULT : 1 << 20)
 #endif
 #ifndef SPH_GRID_RELAX
-#define SPH_GRID_RELAX (SPH_GRID_MULT > 0 ? SPH_GRID_MULT : 1 << 20)
+#define SPH_GRID_RELAX (SPH_GRID_MULT > 0 ? 3 * SPH_GRID_MULT / 2 : 1 << 20)
 #endif
 #ifndef SPH_GRID_MULT_SORT
-#define SPH_GRID_MULT_SORT 4     // blocks per SM of the sort's streaming kernels (scan, scatter, reorder; 4 entries per thread and trip)
+#define SPH_GRID_MULT_SORT 4     // blocks per SM of the sort's scatter and reorder kernels (4 entries per thread and trip)
+#endif
+#ifndef SPH_GRID_MULT_SCAN
+#define SPH_GRID_MULT_SCAN 8     // blocks per SM of the scan (one 1024-cell tile per block and trip)
 #endif
 
 enum { ST_READY = 0, ST_ADVECTED, ST_SORTED1, ST_DENSITY, ST_RELAXED, ST_REQUEUED };
@@ -217,7 +220,7 @@ extern "C" int sph_create(const sph_config *cfg, sph_ctx **out)
 #else
     ctx->grid = (int)((cap + SPH_THREADS - 1) / SPH_THREADS);
 #endif
-    // per-kernel block counts (A/B of round 2: k_advect and k_density like 16 blocks per SM, k_relax 8)
+    // per-kernel block counts (A/B of round 2: k_advect and k_density like 16 blocks per SM, k_relax 12)
     ctx->grid_advect = std::min<int>((int)((cap + SPH_THREADS - 1) / SPH_THREADS), prop.multiProcessorCount * SPH_GRID_ADVECT);
     ctx->grid_density = std::min<int>((int)((cap + SPH_THREADS - 1) / SPH_THREADS), prop.multiProcessorCount * SPH_GRID_DENSITY);
     ctx->grid_relax = std::min<int>((int)((cap + SPH_THREADS - 1) / SPH_THREADS), prop.multiProcessorCount * SPH_GRID_RELAX);
@@ -547,7 +550,7 @@ static int launch_sort(sph_ctx *ctx, int which, bool with_unpack = true, bool re
         ctx->launches++;
     }
     // grids sized for the widest window (tile loops inside): a captured graph survives moving slab edges
-    const int sgrid = std::max(1, std::min(ctx->scan_grid, SPH_GRID_MULT_SORT * 148));
+    const int sgrid = std::max(1, std::min(ctx->scan_grid, SPH_GRID_MULT_SCAN * 148));
 #if !SPH_TILE_ATOMICS
     SPH_LAUNCH(k_scan_totals, sgrid, ctx->stream)(ctx->dp, ctx->counters, ctx->cnt, ctx->tile_total);
     ctx->launches++;
