@@ -292,10 +292,15 @@ int sph_run_frame(sph_ctx *ctx, const sph_tunable *t, int steps, int16_t *xy_pai
  * stream copy the frame into xy_pairs (pinned host memory; untouched until collected) and returns a ticket
  * (0 or 1, alternating; at most two frames in flight) or a negative error.  sph_coords_wait(ticket) blocks until
  * that frame has arrived and returns its particle count, like sph_pack_coords.  A single slab copies exactly its
- * particles; a slab among others copies min(cap, capacity) entries, because its count is not known on the host
- * without a synchronisation.  sph_run_frame_async = sph_run_frame ending in sph_pack_coords_async. */
+ * particles; a slab among others, whose count is not known on the host without a synchronisation, copies the
+ * population of the last frame it collected plus an eighth (the whole buffer until it has collected one), and
+ * sph_coords_wait fetches the remainder in the rare frame in which the slab grew by more.  Each ticket has its own
+ * device-side frame: the compute stream never waits for a copy.  sph_coords_copied(ticket): entries of that frame
+ * that crossed to the host (for D2H accounting).  sph_run_frame_async = sph_run_frame ending in
+ * sph_pack_coords_async. */
 int sph_pack_coords_async(sph_ctx *ctx, int16_t *xy_pairs, int cap);
 int sph_coords_wait(sph_ctx *ctx, int ticket);
+int sph_coords_copied(sph_ctx *ctx, int ticket);
 int sph_run_frame_async(sph_ctx *ctx, const sph_tunable *t, int steps, int16_t *xy_pairs, int cap);
 
 /* kernels launched since the context was created (bench bookkeeping) */

@@ -61,7 +61,7 @@ C_ABI_SYMBOLS = (
     "sph_advect", "sph_sort", "sph_density", "sph_relax", "sph_step", "sph_exchange_buffers",
     "sph_set_neighbors", "sph_get_cells", "sph_get_pairs", "sph_get_forward_counts",
     "sph_pack_coords", "sph_launch_count", "sph_run_frame", "sph_p2p_local_handle", "sph_p2p_connect", "sph_copy_n_local", "sph_copy_load", "sph_init_lattice",
-    "sph_set_viscosity_stabilisation", "sph_pack_coords_async", "sph_coords_wait", "sph_run_frame_async",
+    "sph_set_viscosity_stabilisation", "sph_pack_coords_async", "sph_coords_wait", "sph_coords_copied", "sph_run_frame_async",
     "sph_exchanges_per_step", "sph_refresh_ghosts", "sph_exchange_via_host", "sph_set_exchange_period", "sph_exchange_due", "sph_get_exchange_times", "sph_state_save", "sph_state_restore", "sph_copy_work", "sph_ctx_exchanges_per_step",
 )
 
@@ -111,6 +111,7 @@ def _bind(L):
     L.sph_run_frame_async.argtypes = [C.c_void_p, C.POINTER(Tunable), C.c_int, C.c_void_p, C.c_int]
     L.sph_pack_coords_async.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
     L.sph_coords_wait.argtypes = [C.c_void_p, C.c_int]
+    L.sph_coords_copied.argtypes = [C.c_void_p, C.c_int]
     L.sph_init_lattice.argtypes = [C.c_void_p] + [C.c_float] * 4 + [C.c_int] * 3
     L.sph_copy_n_local.argtypes = [C.c_void_p, C.c_void_p]
     L.sph_copy_load.argtypes = [C.c_void_p, C.c_void_p]
@@ -229,6 +230,10 @@ class Context:
         if n < 0:
             self._ck(-n, "sph_coords_wait")
         return n
+
+    def coords_copied(self, ticket):
+        """Entries of that ticket's frame that crossed to the host (after coords_wait)."""
+        return int(self.L.sph_coords_copied(self.h, int(ticket)))
 
     def status(self):
         s = Status()

@@ -98,11 +98,14 @@ struct sph_ctx {
     cudaEvent_t stage_free;          // ... and the point in the stream after which they may be rewritten
     bool stage_busy;
     int unpack_grid;                 // k_unpack waits on the neighbour inside the kernel: grid must be fully co-resident
-    short2 *coords;
+    short2 *coords;                  // device-side frame of the synchronous feed and of ticket 0
+    short2 *coords1;                 // ... of ticket 1 (the asynchronous feed packs frame f while frame f-1 still drains)
     // asynchronous coordinate feed (sph_pack_coords_async): the copy of frame f drains on its own stream while the
     // steps of frame f+1 run, like the reference's MPI_Isend of its frame (fluid.c:283-287, :354-365)
     cudaStream_t copy_stream;
-    struct { cudaEvent_t packed, copied; int cap; bool pending; } feed[2];
+    struct { cudaEvent_t packed, copied; int cap; bool pending; int entries; int16_t *xy; } feed[2];
+    int feed_last_n;                 // a slab's population as of the last collected frame (0: none yet)
+    int feed_margin;                 // entries copied beyond feed_last_n * 9/8 (SPH_FEED_MARGIN_ENTRIES; tests make it negative)
     int *feed_cnt_dev;               // 2 x CN_COUNT: counters as they stood when the frame was packed
     int *feed_cnt_host;              // the same, in pinned host memory
     unsigned feed_seq;
@@ -261,6 +264,9 @@ extern "C" int sph_create(const sph_config *cfg, sph_ctx **out)
     CK(cudaMalloc(&ctx->ord_key, cap * sizeof(int)));
     CK(cudaMalloc(&ctx->ord_uid, cap * sizeof(uint32_t)));
     CK(cudaMalloc(&ctx->coords, cap * sizeof(short2)));
+    CK(cudaMalloc(&ctx->coords1, cap * sizeof(short2)));
+    ctx->feed_margin = 4096;
+    if (const char *fm = getenv("SPH_FEED_MARGIN_ENTRIES")) ctx->feed_margin = atoi(fm);
     const size_t ntiles_max = (ncell_max + SCAN_TILE - 1) / SCAN_TILE + 1;
     ctx->ntiles_max = (int)ntiles_max;
     CK(cudaMalloc(&ctx->tile_total, ntiles_max * sizeof(int)));
@@ -348,7 +354,7 @@ extern "C" void sph_destroy(sph_ctx *ctx)
     for (int i = 0; i < 3; i++) cudaFree(ctx->Q[i]);
     for (int i = 0; i < 2; i++) cudaFree(ctx->U[i]);
     cudaFree(ctx->dens); cudaFree(ctx->nmask); cudaFree(ctx->cnt); cudaFree(ctx->cell_start); cudaFree(ctx->t_key);
-    cudaFree(ctx->t_slot); cudaFree(ctx->ord_src); cudaFree(ctx->ord_key); cudaFree(ctx->ord_uid); cudaFree(ctx->coords);
+    cudaFree(ctx->t_slot); cudaFree(ctx->ord_src); cudaFree(ctx->ord_key); cudaFree(ctx->ord_uid); cudaFree(ctx->coords); cudaFree(ctx->coords1);
     cudaFree(ctx->pv); cudaFree(ctx->tile_total); cudaFree(ctx->counters); cudaFree(ctx->dp);
     for (int s = 0; s < 2; s++) { cudaFree(ctx->send[s]); cudaFree(ctx->recv[s]); }
     for (int s = 0; s < 2; s++) if (ctx->peer[s]) cudaIpcCloseMemHandle(ctx->peer[s]);
@@ -1130,21 +1136,32 @@ extern "C" int sph_pack_coords_async(sph_ctx *ctx, int16_t *xy, int cap)
     if (ctx->feed[k].pending) { fail(ctx, SPH_ERR_STATE, "sph_pack_coords_async: two frames in flight, collect one with sph_coords_wait"); return -SPH_ERR_STATE; }
     auto bail = [&](cudaError_t e) { snprintf(ctx->err, sizeof ctx->err, "pack_coords_async: %s", cudaGetErrorString(e)); return -SPH_ERR_CUDA; };
     cudaError_t e;
-    // one device-side buffer: the copy of the frame before must have drained before it is packed again
-    if (ctx->feed[k ^ 1].pending && (e = cudaStreamWaitEvent(ctx->stream, ctx->feed[k ^ 1].copied, 0))) return bail(e);
+    // one device-side frame per ticket: the compute stream never waits for a copy.  (Frame f-2's copy out of this
+    // buffer has drained: its ticket was collected, or this call would have been refused above.  Round 2's first build
+    // had ONE buffer and made the pack of frame f wait for the copy of frame f-1 -- on 8 GPUs, whose 12 MB frames share
+    // the host's memory, that wait was part of every frame.)
+    short2 *dcoords = k == 0 ? ctx->coords : ctx->coords1;
     if ((e = cudaMemsetAsync(ctx->counters + CN_COORDS, 0, sizeof(int), ctx->stream))) return bail(e);
-    SPH_LAUNCH(k_pack_coords, ctx->grid, ctx->stream)(ctx->dp, ctx->counters, dpos, duid, ctx->coords, ctx->cfg.capacity);
+    SPH_LAUNCH(k_pack_coords, ctx->grid, ctx->stream)(ctx->dp, ctx->counters, dpos, duid, dcoords, ctx->cfg.capacity);
     ctx->launches++;
     // the counters as they stand now (the next frame's sorts will rewrite them while the copy is still running)
     if ((e = cudaMemcpyAsync(ctx->feed_cnt_dev + k * CN_COUNT, ctx->counters, CN_COUNT * sizeof(int), cudaMemcpyDeviceToDevice, ctx->stream))) return bail(e);
     if ((e = cudaEventRecord(ctx->feed[k].packed, ctx->stream))) return bail(e);
     if ((e = cudaStreamWaitEvent(ctx->copy_stream, ctx->feed[k].packed, 0))) return bail(e);
-    // how many entries to bring over is not known on the host without a synchronisation: a single slab keeps
-    // the count of its upload; a slab among others may have gained particles, so its whole buffer travels
-    const int entries = std::min(cap, ctx->cfg.nranks == 1 ? ctx->n_uploaded : ctx->cfg.capacity);
+    // how many entries to bring over is not known on the host without a synchronisation: a single slab keeps the
+    // count of its upload; a slab among others copies the population of the last frame it collected plus an eighth
+    // (plus a margin), and sph_coords_wait fetches the rest in the rare frame in which the slab grew by more than that
+    // (until a frame has been collected the whole buffer travels)
+    int entries = ctx->cfg.capacity;
+    if (ctx->cfg.nranks == 1) entries = ctx->n_uploaded;
+    else if (ctx->feed_last_n > 0)
+        entries = (int)std::min<long long>(ctx->cfg.capacity, std::max<long long>(0, (long long)ctx->feed_last_n + ctx->feed_last_n / 8 + ctx->feed_margin));
+    entries = std::min(cap, entries);
     if ((e = cudaMemcpyAsync(ctx->feed_cnt_host + k * CN_COUNT, ctx->feed_cnt_dev + k * CN_COUNT, CN_COUNT * sizeof(int), cudaMemcpyDeviceToHost, ctx->copy_stream))) return bail(e);
-    if (entries > 0 && (e = cudaMemcpyAsync(xy, ctx->coords, (size_t)entries * sizeof(short2), cudaMemcpyDeviceToHost, ctx->copy_stream))) return bail(e);
+    if (entries > 0 && (e = cudaMemcpyAsync(xy, dcoords, (size_t)entries * sizeof(short2), cudaMemcpyDeviceToHost, ctx->copy_stream))) return bail(e);
     if ((e = cudaEventRecord(ctx->feed[k].copied, ctx->copy_stream))) return bail(e);
+    ctx->feed[k].entries = entries;
+    ctx->feed[k].xy = xy;
     ctx->feed[k].cap = cap;
     ctx->feed[k].pending = true;
     ctx->feed_seq++;
@@ -1160,7 +1177,26 @@ extern "C" int sph_coords_wait(sph_ctx *ctx, int ticket)
     cudaError_t e = cudaEventSynchronize(ctx->feed[ticket].copied);
     ctx->feed[ticket].pending = false;
     if (e) { snprintf(ctx->err, sizeof ctx->err, "coords_wait: %s", cudaGetErrorString(e)); return -SPH_ERR_CUDA; }
-    return ctx->feed_cnt_host[ticket * CN_COUNT + CN_NLOCAL];
+    const int n = ctx->feed_cnt_host[ticket * CN_COUNT + CN_NLOCAL];
+    const int want = std::min(n, ctx->feed[ticket].cap), have = ctx->feed[ticket].entries;
+    if (want > have) {
+        // the slab grew by more than the estimate allowed for: the rest of the frame is still in this ticket's device
+        // buffer (nothing packs into it before the ticket is collected)
+        const short2 *dcoords = ticket == 0 ? ctx->coords : ctx->coords1;
+        e = cudaMemcpy(ctx->feed[ticket].xy + 2 * (size_t)have, dcoords + have, (size_t)(want - have) * sizeof(short2), cudaMemcpyDeviceToHost);
+        if (e) { snprintf(ctx->err, sizeof ctx->err, "coords_wait (remainder): %s", cudaGetErrorString(e)); return -SPH_ERR_CUDA; }
+        ctx->feed[ticket].entries = want;
+    }
+    ctx->feed_last_n = n;
+    return n;
+}
+
+// entries of the frame of `ticket` that crossed to the host (after sph_coords_wait: what the asynchronous copy brought
+// plus what the wait had to fetch); for the D2H accounting of a bench
+extern "C" int sph_coords_copied(sph_ctx *ctx, int ticket)
+{
+    if (!ctx || ticket < 0 || ticket > 1) return -SPH_ERR_ARG;
+    return ctx->feed[ticket].entries;
 }
 
 extern "C" int sph_pack_coords(sph_ctx *ctx, int16_t *xy, int cap)

@@ -340,8 +340,10 @@ class SlabRunner:
                 "sort1": "k_unpack+k_scan_apply+k_scatter+k_reorder",
                 "sort2": "k_scan_apply+k_scatter+k_reorder"}[stage]
 
-    def e2e(self, frames, flush_buf):
-        """Frames with host buffers, pipelined like the reference's MPI_Isend of its frame (fluid.c:283-287, :354-365) and
+    def e2e(self, frames, flush_buf, block=None):
+        """(In blocks of `block` frames that each start from the state of state_save(), restored outside the clock: the
+        frames then are the steps the bench's timed blocks time.)
+        Frames with host buffers, pipelined like the reference's MPI_Isend of its frame (fluid.c:283-287, :354-365) and
         like the single-GPU bench: per frame a parameter block H2D (queued by the rebalancer, lands at the last sub-step),
         4 steps, the slab's int16 coordinates D2H into pinned memory; frame f is collected after frame f+1 has been
         submitted.  One host clock per rank around all frames (the bench takes the max over ranks).  The synchronous
@@ -350,6 +352,9 @@ class SlabRunner:
         bufs = [torch.empty(2 * self.capacity, dtype=torch.int16).pin_memory().numpy() for _ in range(2)]
         c = self.ctx
         # synchronous protocol (a few frames are enough for the comparison figure)
+        block = max(1, min(block or frames, frames))
+        self.state_save()                              # the state every block starts from: the one e2e() was called in
+        restore = True
         sync_frames = max(3, min(frames, 12))
         secs_sync, n = 0.0, 0
         for f in range(sync_frames + 1):
@@ -367,26 +372,35 @@ class SlabRunner:
             for f in range(2):
                 self.run(self.steps_per_frame)
                 c.coords_wait(c.pack_coords_async(bufs[f]))
-            torch.cuda.synchronize()
-            self.dist.barrier()
-            tickets = []
-            t0 = time.perf_counter()
-            for f in range(frames):
-                self.run(self.steps_per_frame)
-                tickets.append(c.pack_coords_async(bufs[f % 2]))
-                if f > 0:
-                    n = c.coords_wait(tickets[f - 1])
-            n = c.coords_wait(tickets[-1])
-            secs = time.perf_counter() - t0
+            secs, done, copied = 0.0, 0, 0
+            while done < frames:
+                if restore:
+                    self.state_restore()
+                torch.cuda.synchronize()
+                self.dist.barrier()
+                tickets = []
+                t0 = time.perf_counter()
+                for f in range(block):
+                    self.run(self.steps_per_frame)
+                    tickets.append(c.pack_coords_async(bufs[f % 2]))
+                    if f > 0:
+                        n = c.coords_wait(tickets[f - 1])
+                        copied += c.coords_copied(tickets[f - 1])
+                n = c.coords_wait(tickets[-1])
+                copied += c.coords_copied(tickets[-1])
+                secs += time.perf_counter() - t0
+                done += block
+            secs *= frames / done                      # (per `frames` frames, like the synchronous figure)
             # the last frame must be what the synchronous call packs from the same state (a slab packs its particles in
             # the order an atomic cursor hands out: compare as sets of coordinate pairs)
-            last = bufs[(frames - 1) % 2][:2 * n].reshape(n, 2).copy()
+            last = bufs[(block - 1) % 2][:2 * n].reshape(n, 2).copy()
             ref = c.pack_coords()
             key = lambda a: np_.sort(a[:, 0].astype("i4") * 65536 + a[:, 1].astype("i4"))
             if len(ref) == n and np_.array_equal(key(last), key(ref)):
-                # a slab does not know its population on the host without a stall: its whole coordinate buffer travels
+                # a slab does not know its population on the host without a stall: the population of the last collected
+                # frame plus an eighth travels (sph_pack_coords_async); counted from what the library copied
                 out = {"seconds": secs, "steps": self.steps_per_frame * frames, "h2d_per_step": 64 / self.steps_per_frame,
-                       "d2h_per_step": 4 * self.capacity / self.steps_per_frame, "pipelined": True,
+                       "d2h_per_step": 4 * copied / (self.steps_per_frame * done), "pipelined": True,
                        "sync_seconds": secs_sync * frames / sync_frames}
             else:
                 out["pipelined_error"] = "last frame differs from the synchronous feed"

@@ -61,12 +61,29 @@ def main():
         if s % 20 == 19:
             st = sim.ctx.status()
             history.append((st.n_local, st.n_halo, sim.edges[rank][0], sim.edges[rank][1]))
+    e2e = None
+    if os.environ.get("SPH_EMU_E2E"):
+        # bench.py's end-to-end leg on slabs (SlabRunner.e2e: blocks of frames that each start from the restored state,
+        # synchronous and pipelined protocols), with the CUDA-only calls of torch stubbed: protocol and bookkeeping, not time
+        import torch
+        torch.cuda.synchronize = lambda *a: None
+        torch.Tensor.pin_memory = lambda self: self
+        sim.state_save()
+        outs = []
+        for _ in range(2):      # twice, as bench.py does it (restore, then the leg): both must end in the same state
+            sim.state_restore()
+            e2e = sim.e2e(4, torch.zeros(16, dtype=torch.uint8), block=2)
+            outs.append(sim.ctx.download())
+        same = all(np.array_equal(outs[0][0][f].view("u4"), outs[1][0][f].view("u4")) for f in ("x", "y", "v_x", "v_y")) \
+            and np.array_equal(outs[0][1], outs[1][1])
+        e2e = dict(e2e, repeatable=bool(same))
     a, uid = sim.ctx.download()
     st = sim.ctx.status()
     np.savez(f"{out}.rank{rank}.npz", state=a, uid=uid, history=np.array(history, "f8"),
              overflow=np.array([st.capacity_overflow, st.msg_overflow]), edges=np.array(sim.edges, "f8"),
              costs=np.array(sim.costs if sim.costs is not None else [], "f8"), exchanges=np.array([sim.exchanges]),
-             n_exchanges=np.array([getattr(sim, "n_exchanges", 0)]))
+             n_exchanges=np.array([getattr(sim, "n_exchanges", 0)]),
+             e2e=np.array([repr(e2e)]))
     dist.barrier()
     dist.destroy_process_group()
 
