@@ -25,16 +25,16 @@
 #ifndef SPH_TILE_ATOMICS
 #define SPH_TILE_ATOMICS 1
 #endif
-// resident blocks per SM the register allocation of each gather is held to (measured)
-// SPH_SORT_SRC=1 (round 2, second half): the sort's last two kernels walk the SOURCE order.  k_scatter_uid stores only a
+// SPH_SORT_SRC=1 (default since round 2's second half; measured, profiles/r2_variants.md: 35 -> 30.6 us per sort, 27.7
+// with the grids and trip sizes below): the sort's last two kernels walk the SOURCE order.  k_scatter_uid stores only a
 // uid into its cell's range (arrival order); k_reorder_src then reads key, uid and payload of a source entry coalesced,
 // ranks the uid inside its cell (cells of population 1 -- most of them -- need no look at all) and stores the entry at
 // its final place.  The (uid, source, key) triple no longer round-trips through memory: 16 bytes per entry less, and the
-// payload loads no longer hang behind the load of their own index.  Two entries per thread and trip in both kernels.
+// payload loads no longer hang behind the load of their own index.  SPH_SORT_ITEMS entries per thread and trip.
 #ifndef SPH_SORT_SRC
 #define SPH_SORT_SRC 1
 #endif
-// SPH_SCAN_FAST=1: k_scan_apply asks for its tile's populations BEFORE it forms the tile's offset (the DRAM latency
+// SPH_SCAN_FAST=1 (default, same series): k_scan_apply asks for its tile's populations BEFORE it forms the tile's offset (the DRAM latency
 // overlaps the reduction), forms offset, warp totals and bucket statistics behind ONE barrier instead of four, issues
 // one statistics atomic per tile instead of one per warp, and neither reads nor clears the populations of a tile
 // whose total is zero (the air above the fluid: half the table in the dam-break).
@@ -171,6 +171,8 @@ constexpr int kGatherUnroll = SPH_UNROLL;     // (#pragma unroll takes a constan
 #define SPH_PD4_CPARAM
 #endif
 constexpr int kPackedUnroll = SPH_UNROLL / 2 > 0 ? SPH_UNROLL / 2 : 1;
+// resident blocks per SM the register allocation of each gather is held to (measured, DESIGN.md 8: 64 / 40 / 64
+// registers; 5 blocks of k_advect or k_relax spill and lose, profiles/r2_variants.md)
 #ifndef SPH_BLOCKS_ADVECT
 #define SPH_BLOCKS_ADVECT 4
 #endif
