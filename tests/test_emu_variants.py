@@ -136,12 +136,14 @@ def test_branch_free_relax_loop_redoes_particles_with_coincident_neighbours(buil
 # touches an operation or its order, so resident order, payload bits and counters must be equal.
 # (Three emulator builds for the whole section: each costs ~10 s of the CPU suite.)
 # ---------------------------------------------------------------------------------------------------------------
-R2A = ("SPH_SORT_SRC=0", "SPH_SCAN_FAST=0", "SPH_ASYNC=0", "SCAN_ITEMS=8", "SPH_RELAX_RARE=0")
+from emu.build_emu import VARIANTS  # noqa: E402  (one list of defines per library name: conftest prebuilds them side by side)
+
+R2A = VARIANTS["libsph_emu_r2a.so"]
 # other sizes of the same machinery: 2048-cell tiles, two entries per sort trip, two neighbours per relax trip
-SIZES = ("SCAN_ITEMS=8", "SPH_SORT_ITEMS=2", "SPH_RELAX_TRIP=2")
+SIZES = VARIANTS["libsph_emu_sizes.so"]
 # everything that was measured and rejected, switched on together: masked pair trips, staged inputs in all three
 # gathers, deferred slot store, (x, y, vx, vy) candidate records, rows from the sort key, L1 prefetch of the next rows
-REJECTED = ("SPH_PAIRMASK=1", "SPH_ASYNC=7", "SPH_DEFER=3", "SPH_ADVECT_PV4=1", "SPH_KEYROWS=1", "SPH_PREFETCH=7")
+REJECTED = VARIANTS["libsph_emu_rejected.so"]
 
 
 def run_order(libpath, name, warm, steps, gamma, monkeypatch):
