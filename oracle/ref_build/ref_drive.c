@@ -41,6 +41,7 @@
 #include <string.h>
 #include <sys/prctl.h>
 #include <sys/wait.h>
+#include <time.h>
 #include <unistd.h>
 
 #include "mpi.h"
@@ -56,7 +57,16 @@ static struct {
     FILE *out;
     volatile double *shared;     /* --ranks K: world size, written by rank 0's stub; [8 + 2r], [9 + 2r]: first edges of rank r */
     int rank, ranks, wobble;
+    double t_first, t_last;      /* when frame frames_wanted / 5 and the last frame arrived (the "timing:" line) */
+    int f_first;
 } R;
+
+static double now_s(void)
+{
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
 
 static void r_bcast(void *buf, size_t bytes)
 {
@@ -95,6 +105,9 @@ static void r_from_compute(const void *buf, size_t bytes, int tag)
         fwrite(&pairs, 4, 1, R.out);
         fwrite(buf, 4, (size_t)pairs, R.out);
         R.frames_seen++;
+        /* what the route costs per frame (4 steps + the frame's message), start-up and the first fifth left out */
+        if (R.frames_seen == R.frames_wanted / 5 + 1) { R.t_first = now_s(); R.f_first = R.frames_seen; }
+        R.t_last = now_s();
     } else {
         fprintf(stderr, "ref_drive: unexpected message to the render rank: tag %d, %zu bytes\n", tag, bytes);
         exit(3);
@@ -229,6 +242,9 @@ int main(int argc, char **argv)
     if (explicit) printf("explicit transport calls: %ld\n", explicit_calls);
 
     fclose(R.out);
+    if (R.frames_seen > R.f_first && R.f_first > 0)
+        printf("timing: rank %d of %d: frames %d..%d in %.6f s = %.2f us per step (4 steps per frame, fluid.c:105)\n", R.rank, ranks,
+               R.f_first, R.frames_seen, R.t_last - R.t_first, 1e6 * (R.t_last - R.t_first) / (4.0 * (R.frames_seen - R.f_first)));
     printf("ref_drive: %d frames of %d particles, world %.4f x %.4f -> %s\n", R.frames_seen, R.n_global,
            R.world[0], R.world[1], out);
     return R.frames_seen == R.frames_wanted ? 0 : 4;
