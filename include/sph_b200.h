@@ -216,7 +216,10 @@ int sph_step(sph_ctx *ctx, int n);
 /* ---- slab exchange (communication.c:120-450): device-side message buffers ---- */
 /* Message layout: 16-byte header {int n_migrants, n_halo, 0, 0} then records.  The
  * pack is fused into advect/relax, the unpack into sort; a transport only moves bytes.
- * which = 0: after advect (migrants + predicted-position halo), 1: after relax (pos+vel halo). */
+ * which = 0: after advect (migrants + predicted-position halo), 1: after relax (pos+vel halo).
+ * Results equal the one-slab run's bit for bit as long as no particle is displaced further than (halo_width - 1) h past
+ * its slab's edge within one step: ordinary motion is clamped to 0.07 h per step; only a mover teleported into the
+ * fluid beside an edge can do that ("The condition"; a valid but decomposition-dependent step follows). */
 int sph_exchange_buffers(sph_ctx *ctx, int which, void **send_left, void **recv_left,
                          void **send_right, void **recv_right, size_t *bytes);
 /* The same exchange for a host whose transport moves HOST memory (plain MPI_Sendrecv, sockets): the library stages

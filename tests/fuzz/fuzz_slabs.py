@@ -1,0 +1,155 @@
+"""TEST INFRASTRUCTURE -- randomised slab runs on the kernel-source emulator against ONE slab, bit for bit.
+
+Per seed: 2-4 slabs in one process (message buffers copied by hand), two exchanges per step or one exchange every 1 / 2
+steps, 1500-6000 particles, block or full tank, per frame a new parameter block (another preset now and then, the mover
+somewhere else, sphere / rectangle) and slab edges moved by up to h.  WALK=1: the mover walks at most h per frame and axis
+(the regime in which N slabs == 1 slab is guaranteed, DESIGN.md 6 "The condition"); without it the mover is teleported
+across the tank every frame, which is how that condition was found.     [WALK=1] python tests/fuzz/fuzz_slabs.py FIRST_SEED COUNT [debug]
+(tests/test_emu_fuzz.py runs a few fixed seeds with WALK=1.)"""
+import ctypes as C
+import os
+import random
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path[:0] = [os.path.dirname(os.path.dirname(HERE)), os.path.dirname(HERE)]
+import sph_b200 as sph  # noqa: E402
+from emu.build_emu import build  # noqa: E402
+
+sph._lib = sph._bind(C.CDLL(build()))
+
+
+DEBUG = False
+HIST = []
+
+
+def run(seed, frames=14):
+    rng = random.Random(seed)
+    K = rng.choice([2, 3, 4])
+    onex = rng.choice([0, 1, 2])          # 0: two exchanges per step; 1 / 2: one exchange every 1 / 2 steps
+    n_req = rng.choice([1500, 3000, 6000])
+    water = rng.choice([0.5, 1.0])
+    tank_w = 15.0 * float(np.sqrt(n_req / (1500.0 * water)))
+    prob = sph.make_problem(n_req, tank_w=tank_w, water_frac=water, nranks=K)
+    p1 = sph.make_problem(n_req, tank_w=tank_w, water_frac=water)
+    h = prob["h"]
+    preset = rng.choice(["x", "a", "b"])
+    layer = 2.0 if onex == 0 else 3.5 * onex
+    t0 = sph.default_params(h, prob["tank_w"], prob["tank_h"], preset)
+    t0.mover_center_x = rng.random() * prob["tank_w"]; t0.mover_center_y = rng.random() * prob["tank_h"]
+    edges = [(s, e) for (_, _, s, e) in prob["slabs"]]
+    if min(e - s for s, e in edges) < (layer + 0.6) * h:
+        return "skipped (slabs narrower than the layer)"
+    ctxs = []
+    for r in range(K):
+        c = sph.Context(prob["tank_w"], prob["tank_h"], h, 2 * prob["n_global"] + 4096, msg_capacity=4096, rank=r, nranks=K,
+                        halo_width=0.0 if onex == 0 else layer, exchanges_per_step=1 if onex else 0)
+        if onex == 2:
+            c.set_exchange_period(2)
+        t = t0.copy(); t.node_start_x, t.node_end_x = edges[r]
+        c.set_params(t); c.init_lattice(prob, r)
+        ctxs.append(c)
+    one = sph.Context(p1["tank_w"], p1["tank_h"], h, p1["n_global"] + 64)
+    one.set_params(t0); one.init_lattice(p1)
+
+    def exchange(which):
+        bufs = [[np.ctypeslib.as_array((C.c_ubyte * nb).from_address(p)) for p in ptrs]
+                for ptrs, nb in (c.exchange_pointers(which) for c in ctxs)]
+        # order of a slab's pointers: send_l, recv_l, send_r, recv_r
+        for r in range(K - 1):
+            bufs[r + 1][1][:] = bufs[r][2]
+            bufs[r][3][:] = bufs[r + 1][0]
+
+    tcur = t0.copy()
+    for f in range(frames):
+        for sub in range(4):
+            if sub == 3:
+                # the frame's parameter block: mover somewhere else, maybe another preset, edges moved
+                ev = rng.random()
+                tcur = tcur.copy()
+                if ev < 0.3:
+                    pr = sph.default_params(h, prob["tank_w"], prob["tank_h"], rng.choice(["x", "a", "b"]))
+                    for fld in ("k", "k_near", "k_spring", "sigma", "beta", "rest_density", "g"):
+                        setattr(tcur, fld, getattr(pr, fld))
+                if os.environ.get("WALK"):
+                    # a mover that walks: at most 1 h per frame and axis (8 x the autopilot's step at the default size)
+                    tcur.mover_center_x = min(max(tcur.mover_center_x + (2 * rng.random() - 1) * h, 0.0), prob["tank_w"])
+                    tcur.mover_center_y = min(max(tcur.mover_center_y + (2 * rng.random() - 1) * h, 0.0), prob["tank_h"])
+                else:
+                    tcur.mover_center_x = rng.random() * prob["tank_w"]; tcur.mover_center_y = rng.random() * prob["tank_h"]
+                if os.environ.get("NOMOVER"):
+                    tcur.mover_center_y = -100.0
+                if rng.random() < 0.2:
+                    tcur.mover_type = bytes([rng.choice([0, 1])]) if isinstance(tcur.mover_type, bytes) else tcur.mover_type
+                new = list(edges)
+                for r in range(K - 1):
+                    d = rng.choice([0, 0, 1, -1, 2, -2, 8, -8]) * 0.125 * h
+                    e = new[r][1] + d
+                    if e - new[r][0] >= (layer + 0.6) * h and new[r + 1][1] - e >= (layer + 0.6) * h:
+                        new[r] = (new[r][0], e); new[r + 1] = (e, new[r + 1][1])
+                HIST.append([(round(a / h, 3), round(b / h, 3)) for a, b in new])
+                edges = new
+                for r, c in enumerate(ctxs):
+                    t = tcur.copy(); t.node_start_x, t.node_end_x = edges[r]
+                    c.queue_params(t)
+                one.queue_params(tcur)
+            for c in ctxs:
+                c.advect()
+            if all(c.exchange_due for c in ctxs) if onex else True:
+                exchange(0)
+            for c in ctxs:
+                c.sort(); c.density(); c.relax()
+            if onex == 0:
+                exchange(1)
+            for c in ctxs:
+                c.sort()
+            one.step(1)
+            if DEBUG:
+                parts = [c.download() for c in ctxs]
+                uid = np.concatenate([p[1] for p in parts]); state = np.concatenate([p[0] for p in parts])
+                ref, ru = one.download()
+                order = np.argsort(uid)
+                if len(uid) != len(ru):
+                    print("frame", f, "sub", sub, "count differs", len(uid), len(ru)); return "debug stop"
+                d = np.nonzero((state["x"][order].view("u4") != ref["x"].view("u4")) | (state["y"][order].view("u4") != ref["y"].view("u4")))[0]
+                if len(d):
+                    print("frame", f, "sub", sub, "first divergence:", len(d), "particles; edges", [(round(a / h, 3), round(b / h, 3)) for a, b in edges])
+                    print("x/h of the differing particles:", np.round(ref["x"][d] / h, 3)[:20])
+                    owner = np.concatenate([np.full(len(p[1]), r) for r, p in enumerate(parts)])[order][d]
+                    print("owners:", owner[:20], "uids", ru[d][:20])
+                    print("y/h:", np.round(ref["y"][d] / h, 3)[:20])
+                    print("dx:", (state["x"][order][d] - ref["x"][d])[:10])
+                    print("mover", tcur.mover_center_x / h, tcur.mover_center_y / h, tcur.mover_type, "hist", HIST[-3:])
+                    return "debug stop"
+    parts = [c.download() for c in ctxs]
+    uid = np.concatenate([p[1] for p in parts]); state = np.concatenate([p[0] for p in parts])
+    ref, ru = one.download()
+    bad = [(c.status().capacity_overflow, c.status().msg_overflow) for c in ctxs]
+    assert len(uid) == len(ru) and np.array_equal(np.sort(uid), ru), ("lost or duplicated", len(uid), len(ru), bad)
+    order = np.argsort(uid)
+    for fld in ("x", "y", "v_x", "v_y"):
+        if not np.array_equal(state[fld][order].view("u4"), ref[fld].view("u4")):
+            nbad = int((state[fld][order].view("u4") != ref[fld].view("u4")).sum())
+            raise AssertionError(f"{fld} differs for {nbad} particles; K={K} onex={onex} n={n_req} water={water} preset={preset} overflow={bad}")
+    for c in ctxs:
+        c.close()
+    one.close()
+    return f"ok K={K} onex={onex} n={n_req} water={water} overflow={bad}"
+
+
+if __name__ == "__main__":
+    s0, n = int(sys.argv[1]), int(sys.argv[2])
+    DEBUG = len(sys.argv) > 3
+    failed = 0
+    for seed in range(s0, s0 + n):
+        try:
+            print("seed", seed, run(seed), flush=True)
+        except AssertionError as e:
+            failed += 1
+            print("seed", seed, "FAIL", str(e)[:500], flush=True)
+        except sph.SphError as e:
+            failed += 1
+            print("seed", seed, "SphError", str(e)[:300], flush=True)
+    sys.exit(1 if failed else 0)

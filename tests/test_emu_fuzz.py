@@ -1,0 +1,23 @@
+"""A few fixed seeds of the two randomised harnesses under tests/fuzz/ (kernel-source emulator, no GPU): call sequences
+against the C ABI's host logic, and slab runs with a walking mover, moving edges and changing presets against one slab.
+More seeds by hand: python tests/fuzz/fuzz_api.py 0 40; WALK=1 python tests/fuzz/fuzz_slabs.py 0 60."""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def test_random_call_sequences_leave_the_simulation_intact(built_lib):
+    r = subprocess.run([sys.executable, os.path.join(HERE, "fuzz", "fuzz_api.py"), "100", "2"], capture_output=True, text=True,
+                       timeout=600, env=dict(os.environ, FUZZ_OPS="30"))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert r.stdout.count(" ok") == 2
+
+
+def test_random_slab_runs_with_a_walking_mover_equal_one_slab_bit_for_bit(built_lib):
+    # seeds 5-10: 2, 3 and 4 slabs; two exchanges per step, one per step, one every two steps
+    r = subprocess.run([sys.executable, os.path.join(HERE, "fuzz", "fuzz_slabs.py"), "5", "6"], capture_output=True, text=True,
+                       timeout=600, env=dict(os.environ, WALK="1"))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert r.stdout.count(" ok ") == 6, r.stdout

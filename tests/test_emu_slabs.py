@@ -241,3 +241,84 @@ def test_bench_e2e_leg_on_emulated_slabs(tmp_path, built_lib, monkeypatch, margi
         #  the default margin of 4096 entries dominates at this size)
         lo, hi = (4500, 7500) if margin else (7000, 10500)        # (three slabs: ~4000 particles each)
         assert lo < out["d2h_per_step"] < hi, out
+
+
+@pytest.mark.parametrize("exchanges", [2, 1])
+def test_slabs_equal_one_slab_while_no_particle_is_thrown_past_the_ghost_layer(built_lib, monkeypatch, exchanges):
+    """The condition behind "N slabs == 1 slab bit for bit" (DESIGN.md 6), pinned from both sides.  Ordinary motion is
+    bounded by the velocity clamp (0.07 h per step, fluid.c:613-625); the one unbounded displacement on the path is the
+    mover's push-out (fluid.c:663-685).  A sphere of radius 3.4 h whose centre sits 1 h beyond a slab edge throws the
+    particles between the edge and its centre 2.4 h deep into the neighbour's slab.  If the mover ARRIVES at a walk (1 h per
+    frame: 8 x the render rank's autopilot step, renderer.c:513-531) the fluid gives way ahead of it and the slabs stay
+    bit-identical to one slab; if it is teleported into the fluid in a single step (a mouse click, controls.c), particles are
+    thrown further than the ghost layer reaches, their owner relaxes them for one step without their new neighbours, and a
+    few come out differently from the one-slab run -- as they do in the reference, whose halo is h wide
+    (communication.c:137-140).  Nobody is lost, nothing overflows."""
+    import sph_b200
+    from emu.backend import use_emulator
+    monkeypatch.setattr(sph_b200, "_lib", sph_b200._lib)      # use_emulator() rebinds the module's library: undone after the test
+    sph = use_emulator()
+    n_req = 6000
+    tank_w = 15.0 * float(np.sqrt(n_req / 1500.0))
+    prob, p1 = sph.make_problem(n_req, tank_w=tank_w, nranks=2), sph.make_problem(n_req, tank_w=tank_w)
+    h = prob["h"]
+    edges = [(s, e) for (_, _, s, e) in prob["slabs"]]
+
+    def run(jump_h):
+        t0 = sph.default_params(h, prob["tank_w"], prob["tank_h"], "x")
+        radius = 0.5 * t0.mover_width
+        assert radius > 3.2 * h
+        t0.mover_center_x = edges[0][1] + h
+        t0.mover_center_y = -2.0 * radius                    # below the floor: touches nothing yet
+        ctxs = []
+        for r in range(2):
+            c = sph.Context(prob["tank_w"], prob["tank_h"], h, 2 * prob["n_global"] + 4096, msg_capacity=4096, rank=r, nranks=2,
+                            halo_width=0.0 if exchanges == 2 else 3.5, exchanges_per_step=0 if exchanges == 2 else 1)
+            t = t0.copy(); t.node_start_x, t.node_end_x = edges[r]
+            c.set_params(t); c.init_lattice(prob, r)
+            ctxs.append(c)
+        one = sph.Context(p1["tank_w"], p1["tank_h"], h, p1["n_global"] + 64)
+        one.set_params(t0); one.init_lattice(p1)
+
+        def exchange(which):
+            bufs = [[np.ctypeslib.as_array((sph.C.c_ubyte * nb).from_address(p)) for p in ptrs]
+                    for ptrs, nb in (c.exchange_pointers(which) for c in ctxs)]
+            bufs[1][1][:] = bufs[0][2]
+            bufs[0][3][:] = bufs[1][0]
+
+        tcur = t0.copy()
+        for frame in range(10):
+            for sub in range(4):
+                if sub == 3 and frame >= 4:                  # the frame's parameter block (fluid.c:293-294)
+                    tcur = tcur.copy()
+                    tcur.mover_center_y = min(tcur.mover_center_y + jump_h * h, 0.3 * prob["tank_h"])
+                    for r, c in enumerate(ctxs):
+                        t = tcur.copy(); t.node_start_x, t.node_end_x = edges[r]
+                        c.queue_params(t)
+                    one.queue_params(tcur)
+                for c in ctxs:
+                    c.advect()
+                exchange(0)
+                for c in ctxs:
+                    c.sort(); c.density(); c.relax()
+                if exchanges == 2:
+                    exchange(1)
+                for c in ctxs:
+                    c.sort()
+                one.step(1)
+        parts = [c.download() for c in ctxs]
+        uid = np.concatenate([p[1] for p in parts]); state = np.concatenate([p[0] for p in parts])
+        ref, ru = one.download()
+        assert np.array_equal(np.sort(uid), ru), "particles lost or duplicated"
+        for c in ctxs:
+            st = c.status()
+            assert st.capacity_overflow == 0 and st.msg_overflow == 0
+        o = np.argsort(uid)
+        d = np.maximum(np.abs(state["x"][o] - ref["x"]), np.abs(state["y"][o] - ref["y"])) / h
+        moved = float(np.abs(ref["y"] - sph.lattice(p1)[0]["y"]).max() / h)
+        return int((d > 0).sum()), float(d.max()), moved
+
+    differing, worst, moved = run(1.0)
+    assert differing == 0 and moved > 1.0, (differing, worst, moved)         # the mover did plough through the fluid
+    differing, worst, _ = run(100.0)
+    assert 0 < differing < 0.05 * prob["n_global"] and worst < 1.0, (differing, worst)
