@@ -1,4 +1,4 @@
-# Build every tuning variant of scripts/gpu_round2_first.sh into sph_b200/variants/ (run HERE, before gpurun: the .so
+# Build every tuning variant of scripts/calls/gpu_round2_first.sh into sph_b200/variants/ (run HERE, before gpurun: the .so
 # files travel with the snapshot).  ~7 s each.
 set -e
 python -m sph_b200.build --variant packed -DSPH_PACKED=1

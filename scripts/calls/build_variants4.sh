@@ -1,5 +1,5 @@
 # Round 2, second half: A/B list of the restructurings written after the per-instruction counts of the r2_final capture
-# (run HERE before gpurun; scripts/gpu_r2b_call1.sh times them)
+# (run HERE before gpurun; scripts/calls/gpu_r2b_call1.sh times them)
 set -e
 S="-DSPH_SORT_SRC=1 -DSPH_SCAN_FAST=1"
 python -m sph_b200.build --variant scanfast -DSPH_SCAN_FAST=1

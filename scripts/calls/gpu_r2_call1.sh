@@ -1,5 +1,5 @@
 # Round 2, GPU call 1 (one box): full GPU suite WITHOUT -x (every failure visible), then the A/B of all build variants.
-#   bash scripts/build_variants.sh && /usr/local/graft/bin/gpurun --timeout 1500 -- 'bash scripts/gpu_r2_call1.sh'
+#   bash scripts/calls/build_variants.sh && /usr/local/graft/bin/gpurun --timeout 1500 -- 'bash scripts/calls/gpu_r2_call1.sh'
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/r2c1_smi.txt
 timeout 1000 python -m pytest tests -m gpu -q -rA 2>&1 | tail -120 > gpurun_out/r2c1_gpu_tests.txt

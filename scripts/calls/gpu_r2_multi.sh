@@ -1,5 +1,5 @@
 # Round 2, multi-GPU A/B: the two-exchange build against the one-exchange build with exchange periods 1, 2, 4
-#   /usr/local/graft/bin/gpurun --gpus 2 --timeout 1200 -- 'NGPU=2 bash scripts/gpu_r2_multi.sh'
+#   /usr/local/graft/bin/gpurun --gpus 2 --timeout 1200 -- 'NGPU=2 bash scripts/calls/gpu_r2_multi.sh'
 mkdir -p gpurun_out
 N=${NGPU:-2}
 cp sph_b200/libsph_b200.so /tmp/base.so

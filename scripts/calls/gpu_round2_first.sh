@@ -1,9 +1,9 @@
 # First GPU call of round 2 (one box, ~15 min): everything that was written after round 1's GPU budget ran out.
-#   /usr/local/graft/bin/gpurun --timeout 1500 -- 'bash scripts/gpu_round2_first.sh'
+#   /usr/local/graft/bin/gpurun --timeout 1500 -- 'bash scripts/calls/gpu_round2_first.sh'
 # 1. the GPU suite (first hardware run of k_coupling / k_advect<true> and of the stabilised-viscosity tests)
 # 2. A/B of the packed-FP32 builds against the default (tight parity tests + short bench each)
 # 3. cost of the stabilised viscosity pass on the goo preset
-# Build the variants BEFORE calling gpurun (they travel as .so files): bash scripts/build_variants.sh, i.e.
+# Build the variants BEFORE calling gpurun (they travel as .so files): bash scripts/calls/build_variants.sh, i.e.
 #   python -m sph_b200.build --variant packed -DSPH_PACKED=1
 #   python -m sph_b200.build --variant packed_relax -DSPH_PACKED=1 -DSPH_PACKED_RELAX=1
 #   python -m sph_b200.build --variant packed_b3 -DSPH_PACKED=1 -DSPH_BLOCKS_ADVECT=3     # no spills, fewer warps

@@ -1,7 +1,7 @@
 # Multi-GPU A/B of round 2: the shipped two-exchange build against the one-exchange build (ghosts relaxed
 # redundantly, neighbours meet once per step), each with the reference's count-based edge policy and with the
 # cost-based one.  Build the variant first:  python -m sph_b200.build --variant onex -DSPH_ONE_EXCHANGE=1
-#   /usr/local/graft/bin/gpurun --gpus 8 --timeout 1500 -- 'NGPU=8 bash scripts/gpu_round2_multi.sh'
+#   /usr/local/graft/bin/gpurun --gpus 8 --timeout 1500 -- 'NGPU=8 bash scripts/calls/gpu_round2_multi.sh'
 mkdir -p gpurun_out
 N=${NGPU:-2}
 cp sph_b200/libsph_b200.so /tmp/base.so
