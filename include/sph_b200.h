@@ -103,7 +103,9 @@ typedef struct sph_config {
     int msg_capacity;        /* max particles in one neighbour message (halo or migrants) */
     int device;              /* CUDA device ordinal */
     int rank, nranks;        /* slab index / number of slabs; nranks == 1: no exchange */
-    float halo_width;        /* ghost-layer width in units of h; 0 -> default 2.0 */
+    float halo_width;        /* ghost-layer width in units of h; 0 -> default 2.0 (3.5 with one exchange per step).  With two
+                              * exchanges per step, the stabilised viscosity gather (goo) and a mover that moves, ask for 3:
+                              * its coupling sums are one more pair pass, which leaves the 2 h layer no margin (below) */
     void *stream;            /* cudaStream_t to run on, or NULL for a private stream */
     int exchanges_per_step;  /* slabs: 2 = neighbours meet after the prediction and after the relaxation (ghost layer 2 h);
                               * 1 = once, the ghosts are relaxed redundantly (layer >= 3.5 h; sph_set_exchange_period makes it
@@ -178,7 +180,8 @@ int sph_set_edges(sph_ctx *ctx, float node_start_x, float node_end_x);
 int sph_set_viscosity_stabilisation(sph_ctx *ctx, float gamma, float min_dt_sigma);
 
 /* ---- state ---- */
-/* Snapshot of the whole resident state at a step boundary in DEVICE memory (one slot), and its restoration: the
+/* Snapshot of the whole resident state at a step boundary -- particles, cell tables, counters AND the parameter block
+ * in force (a block set after the snapshot is undone by the restore) -- in DEVICE memory (one slot), and its restoration: the
  * same steps can be run again (a benchmark timing identical work repeatedly; a host that rewinds).  On slabs all
  * ranks save and restore together; the first step after a restore is an exchange step. */
 int sph_state_save(sph_ctx *ctx);
@@ -218,8 +221,10 @@ int sph_step(sph_ctx *ctx, int n);
  * pack is fused into advect/relax, the unpack into sort; a transport only moves bytes.
  * which = 0: after advect (migrants + predicted-position halo), 1: after relax (pos+vel halo).
  * Results equal the one-slab run's bit for bit as long as no particle is displaced further than (halo_width - 1) h past
- * its slab's edge within one step: ordinary motion is clamped to 0.07 h per step; only a mover teleported into the
- * fluid beside an edge can do that ("The condition"; a valid but decomposition-dependent step follows). */
+ * its slab's edge within one step ((halo_width - 2) h while the stabilised viscosity gather is engaged): ordinary
+ * motion is clamped to 0.07 h per step; only the mover's push-out can do that -- a mover teleported into the fluid
+ * beside an edge, or, with the stabilised gather on the default 2 h layer, any moving mover on an edge
+ * ("The condition"; a valid but decomposition-dependent step follows). */
 int sph_exchange_buffers(sph_ctx *ctx, int which, void **send_left, void **recv_left,
                          void **send_right, void **recv_right, size_t *bytes);
 /* The same exchange for a host whose transport moves HOST memory (plain MPI_Sendrecv, sockets): the library stages

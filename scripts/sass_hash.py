@@ -35,10 +35,15 @@ def kernel_hashes(lib):
 
 
 def short(name):
-    """k_advect<false> is the plain kernel (the default path): it keeps the name it had before it became a template"""
+    """k_advect<false, false> is the plain kernel (the default path): it keeps the name it had before it became a
+    template; <true, false> is the stabilised gather's, "k_advect<true>" in the records; the HOLD instantiations
+    (a slab's steps between two exchanges, added after the round-2b capture) are "...+hold"."""
     d = subprocess.run(["c++filt", name], capture_output=True, text=True).stdout.strip()
-    d = re.sub(r"^void ", "", d)
-    return d.split("(")[0].replace("<false>", "")
+    d = re.sub(r"^void ", "", d).split("(")[0]
+    m = re.fullmatch(r"k_advect<(true|false), (true|false)>", d)
+    if m:
+        d = "k_advect" + ("<true>" if m.group(1) == "true" else "") + ("+hold" if m.group(2) == "true" else "")
+    return d.replace("<false>", "")
 
 
 if __name__ == "__main__":

@@ -671,18 +671,26 @@ extern "C" int sph_exchange_due(sph_ctx *ctx)
 #else
 #define SPH_PV4_ARG
 #endif
+// (function pointers: a template argument list with a comma cannot pass through the SPH_LAUNCH macro)
+static constexpr auto k_advect_plain = k_advect<false>, k_advect_stab = k_advect<true>;
+static constexpr auto k_advect_plain_hold = k_advect<false, true>, k_advect_stab_hold = k_advect<true, true>;
+
 static int launch_advect(sph_ctx *ctx)
 {
+    // a slab's step between two exchanges: the instantiation that keeps waiting emigrants resident (k_advect, HOLD)
+    const bool hold = ctx->cfg.nranks > 1 && !ctx->cur_x;
     if (stabilised(ctx)) {
         SPH_LAUNCH(k_coupling, ctx->grid_advect, ctx->stream)(ctx->dp, ctx->counters, ctx->P[0], ctx->Q[0], ctx->cell_start, ctx->coupling, ctx->ord_key);
-        SPH_LAUNCH(k_advect<true>, ctx->grid_advect, ctx->stream)(ctx->dp, ctx->counters, ctx->P[0], ctx->Q[0], ctx->U[0],
+        const auto advect_stab = hold ? k_advect_stab_hold : k_advect_stab;
+        SPH_LAUNCH(advect_stab, ctx->grid_advect, ctx->stream)(ctx->dp, ctx->counters, ctx->P[0], ctx->Q[0], ctx->U[0],
                                                             ctx->cell_start, ctx->P[1], ctx->cnt, ctx->t_key, ctx->t_slot,
                                                             ctx->send[0], ctx->send[1], ctx->coupling, ctx->dopt, ctx->cur_x ? 1 : 0, ctx->ord_key, ctx->tile_total SPH_PV4_ARG);
         ctx->launches += 2;
         CK(cudaGetLastError());
         return SPH_OK;
     }
-    SPH_LAUNCH(k_advect<false>, ctx->grid_advect, ctx->stream)(ctx->dp, ctx->counters, ctx->P[0], ctx->Q[0], ctx->U[0],
+    const auto advect_plain = hold ? k_advect_plain_hold : k_advect_plain;
+    SPH_LAUNCH(advect_plain, ctx->grid_advect, ctx->stream)(ctx->dp, ctx->counters, ctx->P[0], ctx->Q[0], ctx->U[0],
                                                          ctx->cell_start, ctx->P[1], ctx->cnt, ctx->t_key, ctx->t_slot,
                                                          ctx->send[0], ctx->send[1], nullptr, nullptr, ctx->cur_x ? 1 : 0, ctx->ord_key, ctx->tile_total SPH_PV4_ARG);
     ctx->launches++;

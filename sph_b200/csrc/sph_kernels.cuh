@@ -403,8 +403,15 @@ __device__ __forceinline__ float stab_scale(float t, float gci, float gamma, con
     }
 }
 
-// STAB: the stabilised viscosity gather (k_coupling below); false = the plain gather, the default
-template <bool STAB>
+// STAB: the stabilised viscosity gather (k_coupling below); false = the plain gather, the default.
+// HOLD: the instantiation launched for a slab's steps BETWEEN two exchanges (exchange period > 1): nobody can be handed
+// over in such a step, so a local outside the slab's window -- an emigrant still waiting for room in a message: a parked
+// slab, or one that has just given half of itself away, holds more of them than one message takes -- stays resident
+// (binned into the nearest window cell) instead of being dropped.  Found by tests/fuzz/fuzz_slabs.py: a slab parked
+// under an exchange period of 2 lost whatever it had not sent yet in the first step without an exchange.  A separate
+// instantiation so that the machine code of every other step (all of a single slab's, and every exchange step) is
+// exactly the code that was measured and profiled (profiles/r2b_sass_hashes.json).
+template <bool STAB, bool HOLD = false>
 __global__ void __launch_bounds__(SPH_THREADS, SPH_BLOCKS_ADVECT)
 k_advect(const DevParams *__restrict__ Pp, int *__restrict__ counters,
          const float2 *__restrict__ pos, const float2 *__restrict__ vel, const uint32_t *__restrict__ uid,
@@ -710,11 +717,12 @@ k_advect(const DevParams *__restrict__ Pp, int *__restrict__ counters,
                 }
             }
         }
+        const bool keep = HOLD ? !ghost : unsent;                       // (HOLD steps never exchange: `unsent` stays false)
 #if SPH_DEFER_ADVECT
         if (slot_i >= 0) t_slot[slot_i] = slot_v;                       // the previous particle's: its atomic is back by now
-        slot_i = bin_position_deferred(i, np, extra, P, cnt, t_key, counters, tile_total, slot_v, unsent) ? i : -1;
+        slot_i = bin_position_deferred(i, np, extra, P, cnt, t_key, counters, tile_total, slot_v, keep) ? i : -1;
 #else
-        bin_position(i, np, extra, P, cnt, t_key, t_slot, counters, tile_total, unsent);
+        bin_position(i, np, extra, P, cnt, t_key, t_slot, counters, tile_total, keep);
 #endif
 #if SPH_PREFETCH & 1
         if (i + gstride < n) {

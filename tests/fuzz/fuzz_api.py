@@ -45,12 +45,21 @@ def run(seed, nops=40):
     sbuf = np.zeros(2 * cap, "i2")
     pending = []          # tickets in flight on A
     saved = False
+    queued = False        # a queued parameter block has not landed yet (it lands inside the next step)
     log = []
-    tcur = t.copy()
+    tcur = t.copy()       # the latest block handed to the library (set, queued or carried by a frame)
+    tforce = t.copy()     # the block in force (a queued block is not, until a step has run)
+    tq = None
     for k in range(nops):
         op = rng.choice(["step", "stages", "frame", "frame_async", "wait", "pack", "pack_async", "status", "download", "pairs",
                          "save", "restore", "set_params", "queue", "frame_none", "cells", "fwd"])
         log.append(op)
+        if os.environ.get("FUZZ_LOG"):
+            print(k, op, flush=True)
+        if op in ("step", "stages", "frame", "frame_async", "frame_none"):
+            landed = True
+        else:
+            landed = False
         try:
             if op == "step":
                 n = rng.randint(1, 5)
@@ -60,6 +69,8 @@ def run(seed, nops=40):
                 def noise():
                     for _ in range(rng.randint(0, 2)):
                         o = rng.choice(["status", "pack", "download", "pairs", "cells", "fwd", "save", "restore", "set_same", "queue_mid", "step_mid", "pack_async"])
+                        if os.environ.get("FUZZ_LOG"):
+                            print("   noise", o, flush=True)
                         try:
                             if o == "status": A.status()
                             elif o == "pack": A.pack_coords()
@@ -69,7 +80,7 @@ def run(seed, nops=40):
                             elif o == "fwd": A.forward_counts()
                             elif o == "save": A.state_save(); raise AssertionError("state_save accepted in mid-step")
                             elif o == "restore" and saved: A.state_restore(); raise AssertionError("state_restore accepted in mid-step")
-                            elif o == "set_same": A.set_params(tcur)
+                            elif o == "set_same" and not was_queued: A.set_params(tforce)      # (a no-op only while nothing is queued)
                             elif o == "step_mid": A.step(1); raise AssertionError("sph_step accepted in mid-step")
                             elif o == "pack_async" and len(pending) < 2:
                                 idx = 1 - pending[-1][2] if pending else 0
@@ -77,6 +88,7 @@ def run(seed, nops=40):
                                 pending.append((tk, bufs[idx], idx, None))
                         except sph_b200.SphError:
                             pass
+                was_queued = queued
                 A.advect(); noise(); A.sort(); noise(); A.density(); noise(); A.relax(); noise(); A.sort()
                 Bc.step(1)
             elif op == "frame":
@@ -129,18 +141,31 @@ def run(seed, nops=40):
                     assert "queued parameter block" in str(e), e
                     continue
                 Bc.state_save(); saved = True
+                t_saved = tforce.copy()
             elif op == "restore":
                 if saved:
                     A.state_restore(); Bc.state_restore()
+                    tcur = t_saved.copy(); tforce = t_saved.copy()       # the snapshot holds the parameter block in force too
+                    queued = False
             elif op == "set_params":
                 tcur = tcur.copy(); tcur.k = 0.2 + 0.1 * rng.random(); tcur.mover_center_x = prob["tank_w"] * rng.random()
                 A.set_params(tcur); Bc.set_params(tcur)
+                tforce = tcur.copy()
             elif op == "queue":
                 tcur = tcur.copy(); tcur.sigma = 20.0 * rng.random(); tcur.mover_center_y = prob["tank_h"] * rng.random()
                 A.queue_params(tcur); Bc.queue_params(tcur)
+                queued = True; tq = tcur.copy()
         except sph_b200.SphError as e:
             print("seed", seed, "op", k, op, "SphError", e, "log", log[-8:])
             raise
+        if landed:
+            if queued:
+                tforce = tq.copy()
+            if op in ("frame", "frame_async"):
+                tforce = tcur.copy()             # the frame's own block landed in its last step
+            queued = False
+        if os.environ.get("FUZZ_CHECK"):
+            assert same(A, Bc), ("state differs after op", k, op)
     while pending:
         tk, buf, idx, ref = pending.pop(0)
         n = A.coords_wait(tk)

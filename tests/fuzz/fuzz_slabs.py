@@ -40,7 +40,10 @@ def run(seed, frames=14):
     goo = EXTRA and rng.random() < 0.35                  # preset y: the stabilised viscosity gather, one more h of layer per step
     presets = ["y"] if goo else ["x", "a", "b"]
     preset = rng.choice(presets)
-    layer = 2.0 if onex == 0 else (4.5 if goo else 3.5) * onex
+    # (two exchanges per step: the default layer of 2 h is exact for particles that stay inside their slab between two
+    #  migrations, but the stabilised gather's coupling sums are one more pair pass -- with it the layer has no room for a
+    #  particle the mover pushes across an edge; 3 h gives it one h)
+    layer = (3.0 if goo else 2.0) if onex == 0 else (4.5 if goo else 3.5) * onex
     elastic = EXTRA and K >= 3 and rng.random() < 0.4    # the last slab is parked and re-added on the way (controls.c:405-455)
     msg_cap = rng.choice([4096, 600]) if EXTRA and elastic else 4096
     n_active = K
@@ -52,7 +55,7 @@ def run(seed, frames=14):
     ctxs = []
     for r in range(K):
         c = sph.Context(prob["tank_w"], prob["tank_h"], h, 2 * prob["n_global"] + 4096, msg_capacity=msg_cap, rank=r, nranks=K,
-                        halo_width=0.0 if onex == 0 else layer, exchanges_per_step=1 if onex else 0)
+                        halo_width=(layer if goo else 0.0) if onex == 0 else layer, exchanges_per_step=1 if onex else 0)
         if onex == 2:
             c.set_exchange_period(2)
         t = t0.copy(); t.node_start_x, t.node_end_x = edges[r]

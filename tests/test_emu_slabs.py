@@ -322,3 +322,62 @@ def test_slabs_equal_one_slab_while_no_particle_is_thrown_past_the_ghost_layer(b
     assert differing == 0 and moved > 1.0, (differing, worst, moved)         # the mover did plough through the fluid
     differing, worst, _ = run(100.0)
     assert 0 < differing < 0.05 * prob["n_global"] and worst < 1.0, (differing, worst)
+
+
+def test_parked_slab_keeps_its_waiting_emigrants_between_two_exchanges(built_lib, monkeypatch):
+    """Exchange period 2 (the multi-GPU bench's default) and a slab that is parked (controls.c:405-426) with more
+    particles than one message takes: the emigrants that wait for the next exchange must survive the step in between,
+    in which nobody is handed over.  Found by tests/fuzz/fuzz_slabs.py: the prediction kernel of such a step dropped
+    every local outside the slab's window -- all that the parked slab had not sent yet (792 of 6068 particles in the run
+    that showed it), reported as capacity_overflow.  Those steps now run the HOLD instantiation of k_advect."""
+    import sph_b200
+    from emu.backend import use_emulator
+    monkeypatch.setattr(sph_b200, "_lib", sph_b200._lib)      # use_emulator() rebinds the module's library: undone after the test
+    sph = use_emulator()
+    K, n_req, period = 3, 6000, 2
+    tank_w = 15.0 * float(np.sqrt(n_req / 1500.0))
+    prob = sph.make_problem(n_req, tank_w=tank_w, nranks=K)
+    h = prob["h"]
+    edges = [(s, e) for (_, _, s, e) in prob["slabs"]]
+    t0 = sph.default_params(h, prob["tank_w"], prob["tank_h"], "x")
+    t0.mover_center_y = -10.0 * prob["tank_h"]               # out of the way
+    ctxs = []
+    for r in range(K):
+        c = sph.Context(prob["tank_w"], prob["tank_h"], h, 2 * prob["n_global"] + 4096, msg_capacity=1400, rank=r, nranks=K,
+                        halo_width=3.5 * period, exchanges_per_step=1)
+        c.set_exchange_period(period)
+        t = t0.copy(); t.node_start_x, t.node_end_x = edges[r]
+        c.set_params(t); c.init_lattice(prob, r)
+        ctxs.append(c)
+    assert ctxs[K - 1].status().n_local > 1400               # more than one message takes
+
+    def exchange():
+        bufs = [[np.ctypeslib.as_array((sph.C.c_ubyte * nb).from_address(p)) for p in ptrs]
+                for ptrs, nb in (c.exchange_pointers(0) for c in ctxs)]
+        for r in range(K - 1):
+            bufs[r + 1][1][:] = bufs[r][2]
+            bufs[r][3][:] = bufs[r + 1][0]
+
+    n_active, populations = K, []
+    for step in range(24):
+        if step == 7:                                         # the frame's parameter block parks the last slab
+            edges, n_active = sph.remove_partition(edges, h, n_active)
+            for r, c in enumerate(ctxs):
+                t = t0.copy(); t.node_start_x, t.node_end_x = edges[r]; t.active = bytes([1 if r < n_active else 0])
+                c.queue_params(t)
+        for c in ctxs:
+            c.advect()
+        if all(c.exchange_due for c in ctxs):
+            exchange()
+        else:
+            assert not any(c.exchange_due for c in ctxs)
+        for c in ctxs:
+            c.sort(); c.density(); c.relax(); c.sort()
+        populations.append(ctxs[K - 1].status().n_local)
+    uid = np.concatenate([c.download()[1] for c in ctxs])
+    assert np.array_equal(np.sort(uid), np.arange(prob["n_global"])), (len(uid), populations)      # nobody lost, nobody duplicated
+    assert all(c.status().capacity_overflow == 0 for c in ctxs)
+    assert ctxs[K - 1].status().msg_overflow > 0             # emigrants did have to wait ...
+    waiting = [p for p in populations[7:] if 0 < p < populations[6]]
+    assert len(waiting) >= 2, populations                    # ... through at least one step without an exchange
+    assert populations[-1] == 0, populations                 # and the parked slab did drain
