@@ -1,6 +1,6 @@
 """A few fixed seeds of the two randomised harnesses under tests/fuzz/ (kernel-source emulator, no GPU): call sequences
-against the C ABI's host logic, and slab runs with a walking mover, moving edges and changing presets against one slab.
-More seeds by hand: python tests/fuzz/fuzz_api.py 0 40; WALK=1 python tests/fuzz/fuzz_slabs.py 0 60."""
+against the C ABI's host logic, slab runs with a walking mover, moving edges and changing presets against one slab.
+More seeds by hand: python tests/fuzz/fuzz_api.py 0 40; WALK=1 python tests/fuzz/fuzz_slabs.py 0 60; python tests/fuzz/fuzz_p2p.py 0 40."""
 import os
 import subprocess
 import sys
@@ -21,3 +21,10 @@ def test_random_slab_runs_with_a_walking_mover_equal_one_slab_bit_for_bit(built_
                        timeout=600, env=dict(os.environ, WALK="1"))
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert r.stdout.count(" ok ") == 6, r.stdout
+
+
+def test_random_scripts_through_the_peer_memory_protocol_equal_one_slab(built_lib):
+    # seeds 103-108: 2 and 3 emulated devices; sph_step in pieces, queued blocks, snapshots / restores at barriers, a parked slab
+    r = subprocess.run([sys.executable, os.path.join(HERE, "fuzz", "fuzz_p2p.py"), "103", "6"], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert r.stdout.count(" ok ") >= 4, r.stdout
