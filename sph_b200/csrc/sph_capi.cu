@@ -97,6 +97,7 @@ struct sph_ctx {
     DevParams *stage_dp;             // pinned: the two parameter blocks a captured queued-parameter step copies in
     cudaEvent_t stage_free;          // ... and the point in the stream after which they may be rewritten
     bool stage_busy;
+    bool dens_seen = false;          // a density pass has run since the last upload (its running count primes sph_get_status)
     int unpack_grid;                 // k_unpack waits on the neighbour inside the kernel: grid must be fully co-resident
     short2 *coords;                  // device-side frame of the synchronous feed and of ticket 0
     short2 *coords1;                 // ... of ticket 1 (the asynchronous feed packs frame f while frame f-1 still drains)
@@ -700,6 +701,7 @@ static int launch_advect(sph_ctx *ctx)
 
 static int launch_density(sph_ctx *ctx)
 {
+    ctx->dens_seen = true;
     SPH_LAUNCH(k_density, ctx->grid_density, ctx->stream)(ctx->dp, ctx->counters, ctx->P[2], ctx->cell_start, ctx->dens, ctx->nmask, ctx->ord_key
 #if SPH_RELAX_PD4
                                                    , ctx->pd
@@ -892,6 +894,7 @@ static int ingest(sph_ctx *ctx, int n)
     if ((rc = launch_sort(ctx, 1, false))) return rc;
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->stage = ST_READY;
+    ctx->dens_seen = false;
     ctx->n_uploaded = n;
     ctx->force_x = true;          // a fresh upload has no ghosts
     return SPH_OK;
@@ -1098,7 +1101,8 @@ extern "C" int sph_get_status(sph_ctx *ctx, sph_status *out)
         out->bucket_overflow = std::max(hz[1], c[CN_BUCKET_OVER]);
     }
     out->neighbor_overflow = c[CN_NEIGH_OVER];
-    if (c[CN_NEIGH_OVER] > 0) {
+    // (a freshly uploaded state has not been through a density pass: nothing has primed the running count yet)
+    if (c[CN_NEIGH_OVER] > 0 || !ctx->dens_seen) {
         // the hot path's count is conservative (full neighbour count, candidates past a row's mask taken as accepted) and
         // cumulative; where the state is sorted, count the reference's forward lists of the CURRENT state exactly
         float2 *dpos, *dq; uint32_t *duid; bool q_is_prev;

@@ -1,0 +1,136 @@
+"""TEST INFRASTRUCTURE -- random particle soups through the emulated CUDA path against the gather oracle, stage by stage.
+
+Per seed: a non-physical state -- uniform or clustered positions (clusters dense enough that a candidate row holds far
+more than the 32 entries of a neighbour mask and that reference buckets / forward lists overflow), coincident and
+nearly coincident pairs, particles exactly on the walls, random velocities up to the clamp -- under a random preset
+(goo with the stabilised gather included) with a sphere or rectangle mover somewhere in the soup.  Two steps; after
+every stage: same uid order, positions / velocities within a few ulps of the tank (the oracle runs the same algorithm
+in the same summation order; the emulator's MUFU stand-ins are exact where the GPU's are approximate, so this is a
+check of the LOGIC -- ranges, masks, rare paths -- not of the arithmetic), neighbour sets and overflow reports equal.
+    python tests/fuzz/fuzz_soup.py FIRST_SEED COUNT"""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path[:0] = [os.path.dirname(os.path.dirname(HERE)), os.path.dirname(HERE)]
+import sph_b200  # noqa: E402
+from common import DENSITY_REL, ULPS_POS, ulp32  # noqa: E402
+from emu.build_emu import build  # noqa: E402
+from oracle.oracle import PARTICLE, GatherOracle, default_tunable  # noqa: E402
+from test_gpu_parity import as_sph  # noqa: E402
+
+sph_b200._lib = sph_b200._bind(C.CDLL(build()))
+
+
+def soup(rng, n, tank_w, tank_h, h):
+    a = np.zeros(n, PARTICLE)
+    kind = rng.integers(0, 3)
+    if kind == 0:
+        x = rng.uniform(0, tank_w, n); y = rng.uniform(0, tank_h, n)
+    else:
+        k = int(rng.integers(1, 6))
+        c = rng.uniform(0.1, 0.9, (k, 2)) * [tank_w, tank_h]
+        spread = rng.choice([0.15, 0.5, 2.0]) * h              # 0.15 h: hundreds of particles within one h
+        w = rng.integers(0, k, n)
+        x = c[w, 0] + rng.normal(0, spread, n); y = c[w, 1] + rng.normal(0, spread, n)
+    x = np.clip(x, 0, tank_w - 0.002).astype("f4"); y = np.clip(y, 0, tank_h - 0.002).astype("f4")
+    m = int(rng.integers(0, 12))                               # coincident and nearly coincident pairs
+    for _ in range(m):
+        i, j = rng.integers(0, n, 2)
+        x[j] = x[i]; y[j] = y[i]
+        # (not next to x == 0: a separation that is a DENORMAL squares to zero, r = 0, and the reference's own
+        #  imp * d / r (fluid.c:453-455) is inf * 0 * inf = NaN there whenever u = +inf; the gather oracle reproduces that
+        #  NaN and loses the pair, the CUDA path treats r == 0 as "no impulse" -- seeds 155 / 185 of the first series)
+        if rng.random() < 0.5 and x[j] > 1e-3:
+            x[j] = np.nextafter(x[j], np.float32(np.inf))
+    for _ in range(int(rng.integers(0, 8))):                   # exactly on a wall
+        i = rng.integers(0, n)
+        if rng.random() < 0.5:
+            x[i] = 0.0
+        else:
+            y[i] = 0.0
+    a["x"], a["y"] = x, y
+    vmax = rng.choice([0.5, 3.0, 5.0])
+    a["v_x"] = rng.uniform(-vmax, vmax, n); a["v_y"] = rng.uniform(-vmax, vmax, n)
+    a["x_prev"], a["y_prev"] = a["x"], a["y"]
+    a["id"] = np.arange(n)
+    return a
+
+
+def run(seed):
+    rng = np.random.default_rng(seed)
+    n = int(rng.choice([300, 1500, 4000]))
+    tank_w = float(rng.choice([6.0, 15.0, 31.0])); tank_h = tank_w * 9.0 / 16.0
+    preset = str(rng.choice(["x", "a", "b", "y"]))
+    t = default_tunable(0.580948, tank_w, tank_h, preset)
+    h = t.smoothing_radius
+    t.mover_center_x = float(rng.uniform(0, tank_w)); t.mover_center_y = float(rng.uniform(0, tank_h))
+    t.mover_type = bytes([int(rng.integers(0, 2))])
+    if rng.random() < 0.3:
+        t.mover_width = float(rng.uniform(0.5, 4.0)); t.mover_height = float(rng.uniform(0.5, 4.0))
+    a = soup(rng, n, tank_w, tank_h, h)
+    stab = preset == "y"
+    b = sph_b200.Context(tank_w, tank_h, h, n + 64)
+    o = GatherOracle(tank_w, tank_h, h, n + 64)
+    if stab:
+        b.set_viscosity_stabilisation(0.5); o.set_viscosity_stabilisation(0.5)
+    else:
+        b.set_viscosity_stabilisation(0.0)
+    b.set_params(as_sph(t)); o.set_params(t)
+    b.upload(a); o.upload(a)
+    tol = ULPS_POS * ulp32(tank_w)
+    tag = f"n={n} tank={tank_w} preset={preset}"
+    dense = False
+    for s in range(2):
+        if s == 1 and dense:
+            break            # thousands of neighbours per particle: one step's ulps become anything in the next
+        if s == 0:
+            # identical inputs: neighbour sets, the reference's forward lists (owner rule of hash.c:178-224) and the
+            # overflow reports must be EQUAL (after a step positions differ by ulps, and a pair at r2 == h2 may flip)
+            assert np.array_equal(b.pairs(), o.pairs()), ("pairs", tag)
+            (fu, fc), (gu, gc) = b.forward_counts(), o.forward_counts()
+            ob, oo = np.argsort(fu), np.argsort(gu)
+            assert np.array_equal(fu[ob], gu[oo]) and np.array_equal(fc[ob], gc[oo]), ("forward counts", tag)
+            sb, so = b.status(), o.status()
+            # (bucket_overflow is a flag with a count in it -- buckets above the cap now, or sub-cells above it in an
+            #  earlier sort; the oracle accumulates: only zero / non-zero is comparable)
+            assert (sb.max_bucket, sb.bucket_overflow > 0) == (so.max_bucket, so.bucket_overflow > 0), ("bucket report", tag)
+            dense = sb.max_bucket > 100
+            assert sb.neighbor_overflow == int((fc > 400).sum()), ("neighbor_overflow", tag, sb.neighbor_overflow, int((fc > 400).sum()))
+        b.advect(); o.advect(); b.sort(); o.sort()
+        x, ux = b.download(); r, ur = o.download()
+        assert np.array_equal(ux, ur), ("uids after advect", s, tag)
+        grow = 512 ** s      # (a dense soup amplifies rounding differences by far more per step than a fluid does)
+        assert np.abs(x["x"] - r["x"]).max() <= tol * grow and np.abs(x["y"] - r["y"]).max() <= tol * grow, \
+            ("advect", s, tag, float(np.abs(x["x"] - r["x"]).max() / tol), float(np.abs(x["y"] - r["y"]).max() / tol))
+        b.density(); o.density()
+        x, _ = b.download(); r, _ = o.download()
+        assert np.abs(x["density"] - r["density"]).max() <= DENSITY_REL * max(1.0, float(r["density"].max())) * grow, ("density", s, tag)
+        b.relax(); o.relax(); b.sort(); o.sort()
+        x, ux = b.download(); r, ur = o.download()
+        assert np.array_equal(ux, ur), ("uids after relax", s, tag)
+        # dense clusters: hundreds of neighbours per particle, displacements of many h per step -- relative bound
+        scale = max(1.0, float(np.abs(r["x"] - a["x"][np.argsort(a["id"])][: len(r)]).max() / max(tank_w, 1e-6)) * 64)
+        ex, ey = float(np.abs(x["x"] - r["x"]).max()), float(np.abs(x["y"] - r["y"]).max())
+        assert ex <= tol * grow * scale and ey <= tol * grow * scale, ("relax", s, tag, ex / tol, ey / tol, scale)
+    st = b.status()
+    b.close()
+    return f"ok {tag} max_bucket={st.max_bucket} bucket_over={st.bucket_overflow} neigh_over={st.neighbor_overflow}"
+
+
+if __name__ == "__main__":
+    s0, cnt = int(sys.argv[1]), int(sys.argv[2])
+    failed = 0
+    for seed in range(s0, s0 + cnt):
+        try:
+            print("seed", seed, run(seed), flush=True)
+        except AssertionError as e:
+            failed += 1
+            print("seed", seed, "FAIL", str(e)[:600], flush=True)
+        except sph_b200.SphError as e:
+            failed += 1
+            print("seed", seed, "SphError", str(e)[:300], flush=True)
+    sys.exit(1 if failed else 0)

@@ -28,3 +28,10 @@ def test_random_scripts_through_the_peer_memory_protocol_equal_one_slab(built_li
     r = subprocess.run([sys.executable, os.path.join(HERE, "fuzz", "fuzz_p2p.py"), "103", "6"], capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert r.stdout.count(" ok ") >= 4, r.stdout
+
+
+def test_random_soups_against_the_gather_oracle(built_lib):
+    # seeds 0-7: uniform and clustered soups, all presets, both mover types
+    r = subprocess.run([sys.executable, os.path.join(HERE, "fuzz", "fuzz_soup.py"), "0", "8"], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert r.stdout.count(" ok ") == 8, r.stdout

@@ -114,3 +114,32 @@ def test_state_snapshot_restores_the_same_future(built_lib):
 
 def test_clamped_impulses_take_the_exact_rows(built_lib):
     pc.check_clamped_impulses(gpu.mk, gpu.make_oracle)
+
+
+def test_status_of_a_fresh_upload_counts_the_forward_lists_exactly(built_lib):
+    """sph_status.neighbor_overflow is documented as exact for the current sorted state.  The exact count used to run only
+    once a density pass had raised its conservative running count, so a state that had just been uploaded reported 0
+    whatever it held (found by tests/fuzz/fuzz_soup.py: 2315 particles with forward lists above the reference's 400
+    entries, hash.c:188,223, reported as none).  Emulator only: the fix is host logic around a kernel the GPU suite runs."""
+    from oracle.oracle import PARTICLE, GatherOracle, default_tunable
+    rng = np.random.default_rng(7)
+    n, tank_w = 3000, 15.0
+    tank_h = tank_w * 9.0 / 16.0
+    t = default_tunable(0.580948, tank_w, tank_h, "x")
+    h = t.smoothing_radius
+    a = np.zeros(n, PARTICLE)
+    a["x"] = np.clip(0.5 * tank_w + rng.normal(0, 0.5 * h, n), 0, tank_w - 0.002)       # one cluster: ~1000 particles within h
+    a["y"] = np.clip(0.5 * tank_h + rng.normal(0, 0.5 * h, n), 0, tank_h - 0.002)
+    a["x_prev"], a["y_prev"], a["id"] = a["x"], a["y"], np.arange(n)
+    b = sph_b200.Context(tank_w, tank_h, h, n + 64)
+    b.set_params(gpu.as_sph(t)); b.upload(a)
+    o = GatherOracle(tank_w, tank_h, h, n + 64)
+    o.set_params(t); o.upload(a)
+    (fu, fc), (gu, gc) = b.forward_counts(), o.forward_counts()
+    assert np.array_equal(fc[np.argsort(fu)], gc[np.argsort(gu)])
+    want = int((gc > 400).sum())
+    assert want > 100
+    assert b.status().neighbor_overflow == want
+    b.step(1)                                                    # and it stays exact once the running count is primed
+    fu, fc = b.forward_counts()
+    assert b.status().neighbor_overflow == int((fc > 400).sum())
