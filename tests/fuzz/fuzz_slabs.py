@@ -100,7 +100,7 @@ def run(seed, frames=14):
                 elif elastic and f == 9:
                     new, n_active = sph.add_partition(new, h, n_active)
                 for r in range(n_active - 1):
-                    d = rng.choice([0, 0, 1, -1, 2, -2, 8, -8]) * 0.125 * h
+                    d = rng.choice([0, 0, 1, -1, 2, -2, 8, -8, 16, -16]) * 0.125 * h      # (the time-proportional policy moves an edge by up to 2 h per frame)
                     e = new[r][1] + d
                     if e - new[r][0] >= (layer + 0.6) * h and new[r + 1][1] - e >= (layer + 0.6) * h:
                         new[r] = (new[r][0], e); new[r + 1] = (e, new[r + 1][1])
@@ -172,6 +172,11 @@ if __name__ == "__main__":
             failed += 1
             print("seed", seed, "FAIL", str(e)[:500], flush=True)
         except sph.SphError as e:
+            if "narrower than the ghost layer" in str(e):
+                # (a slab split in half by add_partition can come out narrower than the layer of its exchange mode: the
+                #  library refuses to step, as documented -- not a finding)
+                print("seed", seed, "skipped (the library refused a slab narrower than its ghost layer)", flush=True)
+                continue
             failed += 1
             print("seed", seed, "SphError", str(e)[:300], flush=True)
     sys.exit(1 if failed else 0)
