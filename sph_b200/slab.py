@@ -241,7 +241,17 @@ class SlabRunner:
         """Split the last active slab in half and hand the right half to the next parked rank
         (controls.c:429-455).  Call on every rank at the same step."""
         import sph_b200
-        self.edges, self.n_active = sph_b200.add_partition(self.edges, self.prob["h"], self.n_active)
+        edges, n_active = sph_b200.add_partition(self.edges, self.prob["h"], self.n_active)
+        if self.exchanges == 1:
+            # one exchange per step: an interior slab narrower than the ghost layer makes the library refuse to step
+            # (SPH_ERR_STATE) -- on that one rank, while its neighbours wait for it.  Same arithmetic on every rank:
+            # refuse here, everywhere at once.
+            layer = (self.ctx.cfg.halo_width or 3.5) * self.prob["h"]
+            narrow = [r for r in range(1, n_active - 1) if edges[r][1] - edges[r][0] < layer]
+            if narrow:
+                raise ValueError(f"add_partition: slab {narrow[0]} would be narrower than the ghost layer of this exchange mode "
+                                 f"({(edges[narrow[0]][1] - edges[narrow[0]][0]) / self.prob['h']:.1f} h < {layer / self.prob['h']:.1f} h)")
+        self.edges, self.n_active = edges, n_active
         self._queue_edges()
 
     # -------------------------------------------------------------------------------- simulation
