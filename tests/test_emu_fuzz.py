@@ -35,3 +35,14 @@ def test_random_soups_against_the_gather_oracle(built_lib):
     r = subprocess.run([sys.executable, os.path.join(HERE, "fuzz", "fuzz_soup.py"), "0", "8"], capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert r.stdout.count(" ok ") == 8, r.stdout
+
+
+def test_reference_whole_program_under_a_random_user(built_lib):
+    # seeds 0-2: 2 and 3 compute ranks, presets and remove / add_partition pressed at random frames
+    from test_ref_drive import WORLD_GPU
+    import pytest
+    if not os.path.exists(WORLD_GPU):
+        pytest.skip("oracle/_ref not built")
+    r = subprocess.run([sys.executable, os.path.join(HERE, "fuzz", "fuzz_world.py"), "0", "3"], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert r.stdout.count(" ok ") == 3, r.stdout
