@@ -41,6 +41,10 @@ def run(seed):
     if min(e - s for s, e in edges) < (layer + 0.6) * h:
         return "skipped (slabs narrower than the layer)"
     elastic = K == 3 and rng.random() < 0.4
+    # a parked slab with more particles than a message takes: its emigrants wait, also through the steps between two
+    # exchanges (the HOLD instantiation of k_advect); such a run is no longer the one-slab run -- conservation only
+    small = elastic and rng.random() < 0.5
+    msg_cap = 700 if small else 4096
     t0 = sph.default_params(h, prob["tank_w"], prob["tank_h"], "y" if goo else rng.choice(["x", "a", "b"]))
     t0.mover_center_x = rng.random() * prob["tank_w"]; t0.mover_center_y = rng.random() * prob["tank_h"]
 
@@ -79,7 +83,7 @@ def run(seed):
 
     ctxs = []
     for r in range(K):
-        c = sph.Context(prob["tank_w"], prob["tank_h"], h, 2 * prob["n_global"] + 4096, msg_capacity=4096, device=r, rank=r, nranks=K,
+        c = sph.Context(prob["tank_w"], prob["tank_h"], h, 2 * prob["n_global"] + 4096, msg_capacity=msg_cap, device=r, rank=r, nranks=K,
                         halo_width=(layer if goo else 0.0) if E == 0 else layer, exchanges_per_step=1 if E else 0)
         if E > 1:
             c.set_exchange_period(E)
@@ -134,16 +138,16 @@ def run(seed):
     ref, ru = one.download()
     bad = [(c.status().capacity_overflow, c.status().msg_overflow, c.status().exchange_timeouts) for c in ctxs]
     assert len(uid) == len(ru) and np.array_equal(np.sort(uid), ru), ("lost or duplicated", len(uid), len(ru), bad)
-    assert all(b == (0, 0, 0) for b in bad), bad
+    assert all((b[0], b[2]) == (0, 0) for b in bad) and (small or all(b[1] == 0 for b in bad)), bad
     order = np.argsort(uid)
-    for fld in ("x", "y", "v_x", "v_y"):
+    for fld in () if small else ("x", "y", "v_x", "v_y"):
         if not np.array_equal(state[fld][order].view("u4"), ref[fld].view("u4")):
             nbad = int((state[fld][order].view("u4") != ref[fld].view("u4")).sum())
             raise AssertionError(f"{fld} differs for {nbad} particles; K={K} E={E} n={n_req} goo={goo} elastic={elastic} script={[s[0] + (str(s[1]) if s[0] == 'step' else '') for s in script]}")
     for c in ctxs:
         c.close()
     one.close()
-    return f"ok K={K} E={E} n={n_req} water={water} goo={goo} elastic={elastic} steps={total} ops={len(script)}"
+    return f"ok K={K} E={E} n={n_req} water={water} goo={goo} elastic={elastic} msg_cap={msg_cap} waited={sum(b[1] for b in bad)} steps={total} ops={len(script)}"
 
 
 if __name__ == "__main__":
