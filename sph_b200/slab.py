@@ -40,14 +40,21 @@ def keep_slabs_wider_than(old, new, min_width, nactive):
     would shrink an interior slab below `min_width`.  Pure arithmetic on identical inputs: every rank gets the same
     answer."""
     out = [list(e) for e in new]
-    for r in range(nactive - 1):                       # the edge between slab r and slab r+1
-        if out[r][1] == old[r][1]:
-            continue
-        shrunk = r if out[r][1] < old[r][1] else r + 1
-        interior = 0 < shrunk < nactive - 1
-        if interior and out[shrunk][1] - out[shrunk][0] < min_width:
-            out[r][1] = old[r][1]
-            out[r + 1][0] = old[r + 1][0]
+    # (undoing one edge's move changes the width its neighbours' moves leave of the slab between them: repeated until
+    #  nothing is undone any more -- one pass let a slab through that both of its edges had been moving along with)
+    for _ in range(nactive):
+        undone = False
+        for r in range(nactive - 1):                   # the edge between slab r and slab r+1
+            if out[r][1] == old[r][1]:
+                continue
+            shrunk = r if out[r][1] < old[r][1] else r + 1
+            interior = 0 < shrunk < nactive - 1
+            if interior and out[shrunk][1] - out[shrunk][0] < min_width:
+                out[r][1] = old[r][1]
+                out[r + 1][0] = old[r + 1][0]
+                undone = True
+        if not undone:
+            break
     return [tuple(e) for e in out]
 
 

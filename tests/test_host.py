@@ -184,3 +184,32 @@ def test_time_proportional_edge_policy_never_leaves_a_slab_narrower_than_the_min
             edges = new
             busy = [max(1, int(b * rng.uniform(0.8, 1.25))) for b in busy]
     assert moved > 1000
+
+
+def test_edge_filter_of_the_one_exchange_modes_holds_for_random_layouts():
+    """slab.keep_slabs_wider_than behind the reference's balancer (h/8 per frame, renderer.c:427-477) on random layouts and
+    random counts: no interior slab ever gets narrower than the ghost layer.  One pass over the edges was not enough -- a
+    slab whose two edges had both been moving right came out 0.05 h too narrow once the second move was undone (1 of
+    93 000 calls of a randomised check); the filter now repeats until nothing is undone."""
+    import random
+    import sph_b200
+    from sph_b200.slab import keep_slabs_wider_than
+    h = 0.58
+    calls = 0
+    for seed in list(range(300)) + [2267]:
+        rng = random.Random(seed)
+        K = rng.randint(3, 8)
+        W = rng.uniform(40, 300) * h
+        layer = rng.choice([3.5, 4.5, 7.0])
+        cuts = sorted(rng.uniform(0, W) for _ in range(K - 1))
+        edges = [(a, b) for a, b in zip([0.0] + cuts, cuts + [W])]
+        if min(b - a for a, b in edges[1:-1]) < layer * h:
+            continue
+        for _ in range(40):
+            counts = [rng.randint(0, 4000) for _ in range(K)]
+            new = keep_slabs_wider_than(edges, sph_b200.balance(edges, counts, h, K), layer * h, K)
+            assert all(new[r][1] == new[r + 1][0] for r in range(K - 1))
+            assert all(b - a >= layer * h - 1e-5 for a, b in new[1:-1]), (seed, [(b - a) / h for a, b in edges], [(b - a) / h for a, b in new])
+            edges = new
+            calls += 1
+    assert calls > 3000
