@@ -213,3 +213,63 @@ def test_edge_filter_of_the_one_exchange_modes_holds_for_random_layouts():
             edges = new
             calls += 1
     assert calls > 3000
+
+
+def test_balancer_and_partition_controls_match_the_compiled_reference_functions(built_lib):
+    """check_partition_left (renderer.c:427-477), remove_partition and add_partition (controls.c:405-455) as COMPILED from
+    the reference (oracle/_ref/libref_full.so, the unmodified renderer.c / controls.c), called on a render_t built here,
+    against sph_host_balance / sph_host_remove_partition / sph_host_add_partition: random layouts of 1-8 slabs, random
+    counts, sequences of 30 calls -- every edge float for float, the number of active slabs too.  (The other balance tests
+    compare with restatements; a run of 90 000 such calls found no difference.)"""
+    import random
+    import sph_b200
+    ref = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "oracle", "_ref", "libref_full.so")
+    if not os.path.exists(ref):
+        pytest.skip("oracle/_ref not built")
+    R = C.CDLL(ref)
+    T = sph_b200.Tunable
+
+    class Render(C.Structure):          # the leading members of render_t (renderer.h:44-61)
+        _fields_ = [("sim_width", C.c_float), ("sim_height", C.c_float), ("screen_width", C.c_float), ("screen_height", C.c_float),
+                    ("selected_parameter", C.c_int), ("node_params", C.c_void_p), ("master_params", C.c_void_p),
+                    ("num_compute_procs", C.c_int), ("num_compute_procs_active", C.c_int), ("rest", C.c_char * 64)]
+    assert Render.master_params.offset == 32 and Render.num_compute_procs_active.offset == 44
+    h = 0.580948
+
+    def reference(edges, nactive, fn, counts=None):
+        K = len(edges)
+        m = (T * K)()
+        for r, (s, e) in enumerate(edges):
+            m[r].smoothing_radius = h; m[r].node_start_x = s; m[r].node_end_x = e
+        rs = Render(); rs.master_params = rs.node_params = C.addressof(m); rs.num_compute_procs = K; rs.num_compute_procs_active = nactive
+        if fn == "balance":
+            R.check_partition_left(C.byref(rs), (C.c_int * K)(*counts), C.c_int(sum(counts)))
+        else:
+            getattr(R, fn + "_partition")(C.byref(rs))
+        return [(float(m[r].node_start_x), float(m[r].node_end_x)) for r in range(K)], rs.num_compute_procs_active
+
+    calls = 0
+    for seed in range(150):
+        rng = random.Random(seed)
+        K = rng.randint(1, 8)
+        W = rng.uniform(10, 300)
+        cuts = sorted(rng.uniform(0, W) for _ in range(K - 1))
+        edges = [(float(np.float32(a)), float(np.float32(b))) for a, b in zip([0.0] + cuts, cuts + [W])]
+        nactive = K
+        for _ in range(30):
+            op = rng.choice(["balance"] * 6 + ["remove", "add"])
+            if op == "balance":
+                counts = [rng.randint(0, 3000) * 2 if r < nactive else 0 for r in range(K)]     # coordinate counts, renderer.c:280,290
+                want, wn = reference(edges, nactive, op, counts)
+                got, gn = sph_b200.balance(edges, counts, h, nactive), nactive
+            elif op == "remove":
+                want, wn = reference(edges, nactive, op)
+                got, gn = sph_b200.remove_partition(edges, h, nactive)
+            else:
+                want, wn = reference(edges, nactive, op)
+                got, gn = sph_b200.add_partition(edges, h, nactive)
+            assert gn == wn, (seed, op)
+            assert [tuple(np.float32(x) for x in e) for e in got] == [tuple(np.float32(x) for x in e) for e in want], (seed, op, edges)
+            edges, nactive = got, gn
+            calls += 1
+    assert calls == 4500
