@@ -273,3 +273,30 @@ def test_balancer_and_partition_controls_match_the_compiled_reference_functions(
             edges, nactive = got, gn
             calls += 1
     assert calls == 4500
+
+
+def test_presets_match_the_compiled_reference_functions(built_lib):
+    """set_fluid_x / y / a / b of the compiled controls.c (controls.c:344-401) applied to a parameter block against
+    sph_host_preset on the same block: all 64 bytes."""
+    import sph_b200
+    ref = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "oracle", "_ref", "libref_full.so")
+    if not os.path.exists(ref):
+        pytest.skip("oracle/_ref not built")
+    R = C.CDLL(ref)
+    L = C.CDLL(built_lib)
+
+    class Render(C.Structure):          # the leading members of render_t (renderer.h:44-61)
+        _fields_ = [("sim_width", C.c_float), ("sim_height", C.c_float), ("screen_width", C.c_float), ("screen_height", C.c_float),
+                    ("selected_parameter", C.c_int), ("node_params", C.c_void_p), ("master_params", C.c_void_p),
+                    ("num_compute_procs", C.c_int), ("num_compute_procs_active", C.c_int), ("rest", C.c_char * 64)]
+    for before in "xyab":
+        for which in "xyab":
+            m = (sph_b200.Tunable * 2)()
+            for r in range(2):
+                m[r] = sph_b200.default_params(0.58, 15.0, 8.4375, before)
+            mine = sph_b200.default_params(0.58, 15.0, 8.4375, before)
+            rs = Render(); rs.master_params = rs.node_params = C.addressof(m); rs.num_compute_procs = rs.num_compute_procs_active = 2
+            getattr(R, "set_fluid_" + which)(C.byref(rs))
+            assert L.sph_host_preset(C.byref(mine), C.c_char(which.encode())) == 0
+            for r in range(2):
+                assert bytes(C.string_at(C.addressof(m[r]), 64)) == bytes(C.string_at(C.addressof(mine), 64)), (before, which, r)
