@@ -3,7 +3,7 @@
 Per seed: 2-4 slabs in one process (message buffers copied by hand), two exchanges per step or one exchange every 1 / 2
 steps, 1500-6000 particles, block or full tank, per frame a new parameter block (another preset now and then, the mover
 somewhere else, sphere / rectangle) and slab edges moved by up to h.  EXTRA=1 adds the goo preset (stabilised viscosity
-gather), a last slab that is parked and re-added, small message capacities and an exchange period of 4.  WALK=1: the mover walks at most h per frame and axis
+gather), a last slab that is parked and re-added, small message capacities and an exchange period of 4.  WALK=1: the mover walks at most h per frame and axis and keeps its shape
 (the regime in which N slabs == 1 slab is guaranteed, DESIGN.md 6 "The condition"); without it the mover is teleported
 across the tank every frame, which is how that condition was found; such runs are only checked for conservation (nobody
 lost or duplicated, no capacity overflow).     [WALK=1] python tests/fuzz/fuzz_slabs.py FIRST_SEED COUNT [debug]
@@ -93,7 +93,13 @@ def run(seed, frames=14):
                 if os.environ.get("NOMOVER"):
                     tcur.mover_center_y = -100.0
                 if rng.random() < 0.2:
-                    tcur.mover_type = bytes([rng.choice([0, 1])]) if isinstance(tcur.mover_type, bytes) else tcur.mover_type
+                    shape = bytes([rng.choice([0, 1])])
+                    # (WALK=1 keeps the shape: a sphere that turns into the square around it appears, in one step, up
+                    #  to 0.41 of its radius deep inside the fluid at the corners -- the same event as a teleported
+                    #  mover, DESIGN.md 6 "The condition"; seed 80070: 4 particles beside an edge differ by ulps after
+                    #  the switch, 422 at the end.  The reference never changes mover_type at run time, fluid.c:100.)
+                    if not (os.environ.get("KEEPSHAPE") or os.environ.get("WALK")):
+                        tcur.mover_type = shape if isinstance(tcur.mover_type, bytes) else tcur.mover_type
                 new = list(edges)
                 if elastic and f == 3:
                     new, n_active = sph.remove_partition(new, h, n_active)
