@@ -53,7 +53,12 @@ void sph_host_balance_time(sph_tunable *master, int nactive, const int *busy, fl
 
 /* The render rank's idle "autopilot" for the mover (renderer.c:513-531): per frame gl_x += 0.01 * dir,
  * direction flips outside [-1, 1], gl_y = sinf(3.14 * 5 * gl_x) / 10 - 0.6, then opengl_to_sim
- * (renderer.c:396-404).  Updates t->mover_center_{x,y}; *gl_x / *direction carry the state. */
+ * (renderer.c:396-404).  Updates t->mover_center_{x,y}; *gl_x / *direction carry the state.
+ * The reference does not keep gl_x: every frame it forms it again from the mover's centre (sim_to_opengl,
+ * renderer.c:494: x / (tank_w / 2) - 1).  A caller that does the same before each call gets the compiled reference's
+ * trajectory BIT FOR BIT (tests/test_host.py, 1200 frames against update_inactive_state of the unmodified renderer.c);
+ * with *gl_x carried over, the rounding of that round trip is absent and a reversal at gl_x = +-1 can fall one frame
+ * later: the same path, shifted by two frames from there on. */
 void sph_host_mover_autopilot(sph_tunable *t, float tank_w, float tank_h, float *gl_x, int *direction);
 /* The same path with the per-frame step as a parameter.  The reference's 0.01 GL units are 0.075 simulation units
  * per frame in ITS tank (width 15, fluid.c:119), 2.25 units/s against the +-5 velocity clamp (fluid.c:613-625).  In a

@@ -300,3 +300,49 @@ def test_presets_match_the_compiled_reference_functions(built_lib):
             assert L.sph_host_preset(C.byref(mine), C.c_char(which.encode())) == 0
             for r in range(2):
                 assert bytes(C.string_at(C.addressof(m[r]), 64)) == bytes(C.string_at(C.addressof(mine), 64)), (before, which, r)
+
+
+def test_autopilot_matches_the_compiled_reference_when_gl_x_is_rederived(built_lib):
+    """update_inactive_state of the compiled renderer.c (renderer.c:491-531: the mover's idle path, which also resets the
+    preset and the mover size every frame) against sph_host_mover_autopilot, 1200 frames (six reversals) in three tank
+    sizes: bit-identical mover centres when the caller forms gl_x from the centre before each call, as the reference
+    does (renderer.c:494); with gl_x carried over the path is the same up to the frame at which it reverses."""
+    import sph_b200
+    ref = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "oracle", "_ref", "libref_full.so")
+    if not os.path.exists(ref):
+        pytest.skip("oracle/_ref not built")
+    R = C.CDLL(ref)
+    L = C.CDLL(built_lib)
+
+    class Render(C.Structure):          # render_t (renderer.h:44-61)
+        _fields_ = [("sim_width", C.c_float), ("sim_height", C.c_float), ("screen_width", C.c_float), ("screen_height", C.c_float),
+                    ("selected_parameter", C.c_int), ("node_params", C.c_void_p), ("master_params", C.c_void_p),
+                    ("num_compute_procs", C.c_int), ("num_compute_procs_active", C.c_int), ("show_dividers", C.c_bool),
+                    ("pause", C.c_bool), ("quit_mode", C.c_bool), ("last_activity_time", C.c_double),
+                    ("exit_menu_state", C.c_void_p), ("return_value", C.c_int), ("liquid", C.c_bool)]
+    f32 = np.float32
+    for tank_w in (15.0, 41.7, 387.3):
+        tank_h = float(f32(tank_w) / f32(16.0 / 9.0))
+        m = (sph_b200.Tunable * 1)()
+        m[0] = sph_b200.default_params(0.58, tank_w, tank_h, "b")
+        rs = Render(); rs.sim_width = tank_w; rs.sim_height = tank_h; rs.master_params = rs.node_params = C.addressof(m)
+        rs.num_compute_procs = rs.num_compute_procs_active = 1
+        mine = sph_b200.default_params(0.58, tank_w, tank_h, "b")
+        kept = sph_b200.default_params(0.58, tank_w, tank_h, "b")
+        gl_kept = C.c_float(f32(kept.mover_center_x) / (f32(tank_w) * f32(0.5)) - f32(1.0)); d_kept = C.c_int(1)
+        d = C.c_int(1)
+        far = 0.0
+        for frame in range(1200):
+            R.update_inactive_state(C.byref(rs))
+            gl = C.c_float(f32(mine.mover_center_x) / (f32(tank_w) * f32(0.5)) - f32(1.0))
+            L.sph_host_mover_autopilot(C.byref(mine), C.c_float(tank_w), C.c_float(tank_h), C.byref(gl), C.byref(d))
+            assert (m[0].mover_center_x, m[0].mover_center_y) == (mine.mover_center_x, mine.mover_center_y), (tank_w, frame)
+            L.sph_host_mover_autopilot(C.byref(kept), C.c_float(tank_w), C.c_float(tank_h), C.byref(gl_kept), C.byref(d_kept))
+            far = max(far, abs(kept.mover_center_x - m[0].mover_center_x) / tank_w)
+        # carried over: never further from the reference's path than a few frames' travel (0.005 of the width per frame)
+        assert far <= 6 * 0.005 + 1e-6, (tank_w, far)
+        # (the idle path also puts the fluid back to preset x and the mover to 2 x 2: controls.c:344-357, :333-338)
+        want = sph_b200.default_params(0.58, tank_w, tank_h, "x")
+        assert L.sph_host_preset(C.byref(mine), C.c_char(b"x")) == 0
+        for fld in ("k", "k_near", "k_spring", "sigma", "beta", "rest_density", "g"):
+            assert getattr(m[0], fld) == getattr(want, fld) == getattr(mine, fld), fld
