@@ -53,6 +53,35 @@ torch.cuda.Event = Event
 torch.cuda.stream = lambda s: contextlib.nullcontext()
 torch.cuda.current_device = lambda: 0
 
+_tensor = torch.tensor
+torch.tensor = lambda *a, device=None, **k: _tensor(*a, **k)
+
+if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+    # several ranks (python -m torch.distributed.run ... run_bench_emulated.py --gpus N): gloo instead of NCCL, every rank's
+    # slab on the emulator with host message buffers that torch.distributed moves (the "collective" transport of
+    # SlabRunner; the peer-memory protocol itself is exercised by tests/test_emu_p2p.py).  What this executes is
+    # bench.py's own N > 1 path: parity pre-check, time-balanced edges, exchange period, reductions over ranks, the
+    # per-slab table, the config-3 section, JSON assembly.
+    import torch.distributed as dist
+
+    import sph_b200.slab as slab
+    from emu.backend import EmuSlab
+
+    os.environ.setdefault("SPH_EMU_DEFINES", "SPH_ONE_EXCHANGE=1")
+    _init = dist.init_process_group
+    dist.init_process_group = lambda backend=None, device_id=None, **k: _init("gloo", **k)
+    _slab_init = slab.SlabRunner.__init__
+
+    def _emulated_slab(self, prob, tunable, rank, world, stream=None, capacity_factor=2.0, backend=None, **k):
+        hw = k.get("halo_width")
+        if not hw and int(k.get("exchange_period", 1)) > 1:
+            hw = (4.5 if tunable.time_step * tunable.sigma >= 0.5 else 3.5) * int(k["exchange_period"])
+        os.environ["SPH_EMU_HALO_WIDTH"] = str(hw or 0)
+        k.pop("exchanges_per_step", None)          # (the emulator backend is the one-exchange build)
+        _slab_init(self, prob, tunable, rank, world, stream=None, capacity_factor=capacity_factor, backend=EmuSlab, **k)
+
+    slab.SlabRunner.__init__ = _emulated_slab
+
 import bench  # noqa: E402
 
 if __name__ == "__main__":

@@ -35,3 +35,41 @@ def test_bench_main_runs_end_to_end_on_the_emulator(built_lib, extra, gather):
     assert tr["blocks"] >= 3 and tr["steps_per_block"] == 4 and len(tr["block_ms_min_p10_median_p90_max"]) == 5
     assert d["gpu_launches"] == tr["blocks"] * 4 * (10 if gather.endswith("stabilised") else 9)
     assert d["config"]["integrity"]["nobody_lost_or_duplicated"] and d["config"]["integrity"]["capacity_overflow"] == 0
+
+
+def _free_port():
+    import socket
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+@pytest.mark.parametrize("world,extra", [(2, []), (3, ["--force-cfg3", "--cfg3-particles", "2000"])])
+def test_bench_main_runs_as_several_ranks_on_emulated_slabs(built_lib, world, extra):
+    """The command the driver's scaling run launches -- torch.distributed.run, one rank per GPU, bench.py --gpus N -- from
+    argv to JSON line on emulated slabs over gloo: the parity pre-check (N slabs against one, 40 k particles), the
+    exchange period, time-balanced edges, the reductions over ranks, the per-slab table, integrity counters and (forced
+    at N = 3) the config-3 section that --gpus 8 adds.  Found on the way: the roofline's dominant "kernel" was taken over
+    all stage times, "exchange" included -- a KeyError whenever the collective transport's send/recv was the longest stage."""
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr", "127.0.0.1",
+           "--master-port", str(_free_port()), os.path.join(HERE, "emu", "run_bench_emulated.py"), "--gpus", str(world),
+           "--particles", "3000", "--steps", "4", "--warmup", "3", "--preroll", "8", "--no-cpu-baseline", "--min-timed-ms", "50"] + extra
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-3000:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1, "exactly one JSON line, printed by rank 0"
+    d = json.loads(lines[0])
+    assert all(k in d for k in CONTRACT), [k for k in CONTRACT if k not in d]
+    assert d["n_gpus"] == world and d["scaling"] == "weak" and d["value"] > 0 and d["e2e"]["value"] > 0
+    c = d["config"]
+    assert c["slab_parity"]["result"] == "bit-identical" and c["slab_parity"]["slabs"] == world
+    assert c["integrity"]["nobody_lost_or_duplicated"] and c["integrity"]["capacity_overflow"] == 0 and c["integrity"]["exchange_timeouts"] == 0
+    assert c["exchange_period_steps"] == 2 and c["parallelism"] == f"slab{world}"
+    per_slab = [v for k, v in c.items() if k.startswith("per_slab_")][0]
+    assert len(per_slab) == world and sum(row[0] for row in per_slab) == c["integrity"]["particles_resident"]
+    assert d["roofline"]["kernel"].startswith("k_")
+    if extra:
+        c3 = c["cfg3_16m"]
+        assert "failed" not in c3 and c3["value"] > 0 and c3["particles_resident"] == c3["particles_created"] and c3["capacity_overflow"] == 0
+    else:
+        assert "cfg3_16m" not in c
