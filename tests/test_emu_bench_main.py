@@ -73,3 +73,19 @@ def test_bench_main_runs_as_several_ranks_on_emulated_slabs(built_lib, world, ex
         assert "failed" not in c3 and c3["value"] > 0 and c3["particles_resident"] == c3["particles_created"] and c3["capacity_overflow"] == 0
     else:
         assert "cfg3_16m" not in c
+
+
+def test_smoke_entry_point_runs_on_the_emulator(built_lib, monkeypatch, capsys):
+    """__graft_entry__.smoke() -- the driver's first call on the B200 -- with the binding pointed at the emulator: its
+    three comparisons (gather oracle at rounding level, reference restatement and live reference within the one-step
+    tolerance) and its status checks execute here before they do there."""
+    import ctypes as C
+
+    import sph_b200
+    from emu.build_emu import build as build_emu
+    sys.path.insert(0, os.path.dirname(HERE))
+    import __graft_entry__ as entry
+    monkeypatch.setattr(sph_b200, "_lib", sph_b200._bind(C.CDLL(build_emu())))
+    entry.smoke()
+    out = capsys.readouterr().out
+    assert "smoke ok: n=1508" in out
