@@ -90,3 +90,27 @@ def test_smoke_entry_point_runs_on_the_emulator(built_lib, monkeypatch, capsys):
     entry.smoke()
     out = capsys.readouterr().out
     assert "smoke ok: n=1508" in out
+
+
+@pytest.mark.parametrize("world", [1, 2])
+def test_reference_arm_prints_one_line_from_rank_zero(world):
+    """bench.py --impl reference, as the driver launches it (under torch.distributed.run for N > 1: rank 0 alone runs the
+    reference's CPU implementation and prints, the others exit 0): contract keys, impl, a cpu_baseline of kind
+    "reference" that describes this run, an e2e object with zero copies."""
+    ref = os.path.join(HERE, "..", "oracle", "_ref", "sph_ref_run")
+    if not os.path.exists(ref):
+        pytest.skip("oracle/_ref not built")
+    bench = os.path.join(HERE, "..", "bench.py")
+    tail = ["--impl", "reference", "--gpus", str(world), "--steps", "2", "--warmup", "3", "--particles", "3000", "--preroll", "5"]
+    cmd = [sys.executable, bench] + tail if world == 1 else \
+        [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr", "127.0.0.1",
+         "--master-port", str(_free_port()), bench] + tail
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "particle-steps/sec" and d["n_gpus"] == world and d["higher_is_better"] is True
+    assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["value"] == d["value"] > 0 and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert f"{3000 * world} particles requested" in d["config"]["workload"]
