@@ -169,7 +169,16 @@ void sph_host_balance_time(sph_tunable *m, int nactive, const int *busy, float g
             if (d == 0.0f) continue;
             const float left_after = len[e] + d - (e > 0 ? shift[e - 1] : 0.0f);
             const float right_after = len[e + 1] - d + (e + 2 < nactive ? shift[e + 1] : 0.0f);
-            if (left_after < min_width_h * h || right_after < min_width_h * h) { shift[e] = 0.0f; withdrawn = 1; }
+            /* ... and so must what the move leaves of the OLD extent of the slab it eats into.  In the step in which
+             * the new edges land, the slab on the other side of that slab still holds what is being handed over: a slab
+             * whose two edges move the same way keeps its width, but if its old and new extents overlap by less than
+             * the ghost layer, the strip its neighbour needs as ghosts is owned, for that one step, by the neighbour's
+             * neighbour (soak run 93072 of tests/fuzz/fuzz_slabs.py: a slab 2.75 h wide, both edges 2 h to the left, 23
+             * particles beside the new edge differ by ulps from the one-slab run). */
+            const float left_kept = len[e] + (d < 0.0f ? d : 0.0f);
+            const float right_kept = len[e + 1] - (d > 0.0f ? d : 0.0f);
+            if (left_after < min_width_h * h || right_after < min_width_h * h ||
+                left_kept < min_width_h * h || right_kept < min_width_h * h) { shift[e] = 0.0f; withdrawn = 1; }
         }
         if (!withdrawn) break;
     }

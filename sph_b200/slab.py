@@ -49,7 +49,11 @@ def keep_slabs_wider_than(old, new, min_width, nactive):
                 continue
             shrunk = r if out[r][1] < old[r][1] else r + 1
             interior = 0 < shrunk < nactive - 1
-            if interior and out[shrunk][1] - out[shrunk][0] < min_width:
+            # (what the move leaves of the slab's OLD extent counts as well: in the step in which the new edges land the
+            #  strip its other neighbour needs as ghosts must already be this slab's -- a slab whose two edges move the
+            #  same way keeps its width while its old and new extents drift apart; sph_host_balance_time has the same rule)
+            kept = out[r][1] - old[r][0] if shrunk == r else old[r + 1][1] - out[r][1]
+            if interior and (out[shrunk][1] - out[shrunk][0] < min_width or kept < min_width):
                 out[r][1] = old[r][1]
                 out[r + 1][0] = old[r + 1][0]
                 undone = True

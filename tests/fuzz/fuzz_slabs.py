@@ -108,7 +108,12 @@ def run(seed, frames=14):
                 for r in range(n_active - 1):
                     d = rng.choice([0, 0, 1, -1, 2, -2, 8, -8, 16, -16]) * 0.125 * h      # (the time-proportional policy moves an edge by up to 2 h per frame)
                     e = new[r][1] + d
-                    if e - new[r][0] >= (layer + 0.6) * h and new[r + 1][1] - e >= (layer + 0.6) * h:
+                    # (a slab keeps (layer + 0.6) h of its new AND of its old extent: with less than a layer of overlap
+                    #  between the two, the ghosts its neighbour needs in the step the edges land are still owned by the
+                    #  slab beyond -- seed 93072 of the first soak: 2.75 h wide, both edges 2 h to the left; the library's
+                    #  own policies have the rule since, sph_host_balance_time / slab.keep_slabs_wider_than)
+                    if e - new[r][0] >= (layer + 0.6) * h and new[r + 1][1] - e >= (layer + 0.6) * h and \
+                            e - edges[r][0] >= (layer + 0.6) * h and edges[r + 1][1] - e >= (layer + 0.6) * h:
                         new[r] = (new[r][0], e); new[r + 1] = (e, new[r + 1][1])
                 HIST.append([(round(a / h, 3), round(b / h, 3)) for a, b in new])
                 edges = new

@@ -381,3 +381,81 @@ def test_parked_slab_keeps_its_waiting_emigrants_between_two_exchanges(built_lib
     waiting = [p for p in populations[7:] if 0 < p < populations[6]]
     assert len(waiting) >= 2, populations                    # ... through at least one step without an exchange
     assert populations[-1] == 0, populations                 # and the parked slab did drain
+
+
+def test_a_slab_must_keep_a_layer_of_its_old_extent_when_both_of_its_edges_move(built_lib, monkeypatch):
+    """The second half of the condition behind "N slabs == 1 slab" (DESIGN.md 6), pinned from both sides: in the step in
+    which new edges land, a slab's neighbour needs as ghosts a strip that must already be that slab's.  Three slabs, the
+    middle one 2.75 h wide, two exchanges per step (2 h layer), both of its edges moved 2 h to the left in one parameter
+    block: its width stays, but its old and new extents overlap by 0.75 h only -- most of what the right slab needs as
+    ghosts is, for that one step, still owned by the LEFT slab, which is not its neighbour; a few particles beside the
+    new edge come out ulps away from the one-slab run (soak run 93072 of tests/fuzz/fuzz_slabs.py).  With the middle
+    slab 4.25 h wide (layer + move, and a quarter) the same move is bit-identical.  sph_host_balance_time and
+    slab.keep_slabs_wider_than refuse the first move since (tests/test_host.py); nobody is lost either way."""
+    import sph_b200
+    from emu.backend import use_emulator
+    monkeypatch.setattr(sph_b200, "_lib", sph_b200._lib)      # use_emulator() rebinds the module's library: undone after the test
+    sph = use_emulator()
+    n_req = 3000
+    tank_w = 15.0 * float(np.sqrt(n_req / 750.0))
+    p1 = sph.make_problem(n_req, tank_w=tank_w, water_frac=0.5)
+    h = p1["h"]
+    a0, uid0 = sph.lattice(p1)
+
+    def run(width_h):
+        t0 = sph.default_params(h, p1["tank_w"], p1["tank_h"], "x")
+        # a sphere that sits in the fluid from the start, across the edges that will move: it stirs the lattice (on the
+        # undisturbed lattice the missing ghosts are exactly h away from the nearest local and weigh nothing)
+        t0.mover_center_x = 12.5 * h; t0.mover_center_y = 0.5 * p1["tank_h"]
+        left = 14.5 * h - width_h * h
+        edges = [(0.0, left), (left, 14.5 * h), (14.5 * h, p1["tank_w"])]
+        ctxs = []
+        for r in range(3):
+            c = sph.Context(p1["tank_w"], p1["tank_h"], h, 2 * p1["n_global"] + 4096, msg_capacity=4096, rank=r, nranks=3)
+            t = t0.copy(); t.node_start_x, t.node_end_x = edges[r]
+            c.set_params(t)
+            mine = (a0["x"] >= edges[r][0]) & (a0["x"] < edges[r][1]) if r < 2 else a0["x"] >= edges[r][0]
+            c.upload(a0[mine], uid0[mine])
+            ctxs.append(c)
+        one = sph.Context(p1["tank_w"], p1["tank_h"], h, p1["n_global"] + 64)
+        one.set_params(t0); one.upload(a0, uid0)
+
+        def exchange(which):
+            bufs = [[np.ctypeslib.as_array((sph.C.c_ubyte * nb).from_address(p)) for p in ptrs]
+                    for ptrs, nb in (c.exchange_pointers(which) for c in ctxs)]
+            for r in range(2):
+                bufs[r + 1][1][:] = bufs[r][2]
+                bufs[r][3][:] = bufs[r + 1][0]
+
+        for frame in range(9):
+            for sub in range(4):
+                if sub == 3 and frame == 6:                  # one parameter block: both edges of the middle slab 2 h to the left
+                    edges = [(0.0, edges[0][1] - 2.0 * h), (edges[1][0] - 2.0 * h, edges[1][1] - 2.0 * h), (edges[2][0] - 2.0 * h, edges[2][1])]
+                    for r, c in enumerate(ctxs):
+                        t = t0.copy(); t.node_start_x, t.node_end_x = edges[r]
+                        c.queue_params(t)
+                    one.queue_params(t0)
+                for c in ctxs:
+                    c.advect()
+                exchange(0)
+                for c in ctxs:
+                    c.sort(); c.density(); c.relax()
+                exchange(1)
+                for c in ctxs:
+                    c.sort()
+                one.step(1)
+        parts = [c.download() for c in ctxs]
+        uid = np.concatenate([p[1] for p in parts]); state = np.concatenate([p[0] for p in parts])
+        ref, ru = one.download()
+        assert np.array_equal(np.sort(uid), ru), "particles lost or duplicated"
+        for c in ctxs:
+            st = c.status()
+            assert st.capacity_overflow == 0 and st.msg_overflow == 0
+        o = np.argsort(uid)
+        d = np.maximum(np.abs(state["x"][o] - ref["x"]), np.abs(state["y"][o] - ref["y"])) / h
+        return int((d > 0).sum()), float(d.max())
+
+    differing, worst = run(4.25)
+    assert differing == 0, (differing, worst)
+    differing, worst = run(2.75)
+    assert 0 < differing < 0.2 * p1["n_global"] and worst < 1e-2, (differing, worst)

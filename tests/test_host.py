@@ -180,6 +180,14 @@ def test_time_proportional_edge_policy_never_leaves_a_slab_narrower_than_the_min
             assert abs(new[0][0]) < 1e-6 and abs(new[-1][1] - W) < 1e-3 and all(new[r][1] == new[r + 1][0] for r in range(K - 1))
             assert all(b - a >= layer * h - 1e-4 for a, b in new), (seed, [(b - a) / h for a, b in edges], [(b - a) / h for a, b in new], busy)
             assert all(abs(new[r][1] - edges[r][1]) <= 2.0 * h + 1e-4 for r in range(K - 1))
+            # ... and every slab keeps a layer of its OLD extent (a slab whose two edges move the same way keeps its
+            # width while its old and new extents drift apart: in the step the edges land, its neighbour's ghosts would
+            # still be owned by the slab beyond -- soak run 93072 of tests/fuzz/fuzz_slabs.py)
+            for r in range(K - 1):
+                if new[r][1] < edges[r][1]:
+                    assert new[r][1] - edges[r][0] >= layer * h - 1e-4, (seed, r, "left slab", (new[r][1] - edges[r][0]) / h)
+                elif new[r][1] > edges[r][1]:
+                    assert edges[r + 1][1] - new[r][1] >= layer * h - 1e-4, (seed, r, "right slab", (edges[r + 1][1] - new[r][1]) / h)
             moved += new != edges
             edges = new
             busy = [max(1, int(b * rng.uniform(0.8, 1.25))) for b in busy]
