@@ -47,7 +47,9 @@ void sph_host_balance_ex(sph_tunable *master, int nactive, const int *counts, in
 
 /* OPTIONAL edge policy on MEASURED slab times (sph_copy_work; not the reference's): every interior edge moves towards
  * the slower of its two slabs by `gain` x the shift that would equalise their times, at most max_shift_h smoothing
- * radii per call, keeping every slab at least min_width_h radii wide; dead band 0.5 %.  The particles do not depend on
+ * radii per call, keeping every slab at least min_width_h radii wide AND at least min_width_h radii of its extent
+ * before the call (a slab whose two edges move the same way must still own, in the step the edges land, the ghosts its
+ * neighbour needs: DESIGN.md 6); dead band 0.5 %.  The particles do not depend on
  * where the edges are, so this changes the schedule only. */
 void sph_host_balance_time(sph_tunable *master, int nactive, const int *busy, float gain, float max_shift_h, float min_width_h);
 
