@@ -162,7 +162,11 @@ int sph_set_params(sph_ctx *ctx, const sph_tunable *t);
  * advect stage, which is where the reference's MPI_Scatterv lands (fluid.c:279-310). */
 int sph_queue_params(sph_ctx *ctx, const sph_tunable *t);
 /* Slab edges only (node_start_x / node_end_x); used by migration and halo selection.  On a slab only at a step
- * boundary (SPH_ERR_STATE otherwise; see sph_set_params). */
+ * boundary (SPH_ERR_STATE otherwise; see sph_set_params).  Where the edges are never changes a result, with one
+ * condition on how far they MOVE at once: a slab must keep a ghost layer (halo_width) of the extent it had before the
+ * move, so that the strip its neighbour needs as ghosts in that step is already its own (DESIGN.md 6;
+ * sph_host_balance_time enforces it, the reference's h/8 per frame cannot violate it).  Applies to the edges carried
+ * by sph_set_params / sph_queue_params as well. */
 int sph_set_edges(sph_ctx *ctx, float node_start_x, float node_end_x);
 
 /* Stabilised viscosity gather (not in the reference).  DEFAULT: gamma = 0.5, min_dt_sigma = 0.5, i.e. it
