@@ -459,3 +459,70 @@ def test_a_slab_must_keep_a_layer_of_its_old_extent_when_both_of_its_edges_move(
     assert differing == 0, (differing, worst)
     differing, worst = run(2.75)
     assert 0 < differing < 0.2 * p1["n_global"] and worst < 1e-2, (differing, worst)
+
+
+def test_a_mover_resting_on_a_wall_beside_an_edge_walks_particles_across_it_after_the_migration(built_lib, monkeypatch):
+    """A third face of the condition behind "N slabs == 1 slab" (DESIGN.md 6), pinned from both sides.  A sphere that
+    stands in the fluid from the start is harmless (the first prediction's boundary pass throws what it covers BEFORE
+    that step's migration) -- unless it also rests on a WALL next to a slab edge: a particle under it is pushed out
+    radially, i.e. below the floor, the tank clamp (fluid.c:656-744) puts it back on the floor INSIDE the sphere, and the
+    next boundary pass -- the relaxation's, after the migration -- pushes it out again, now almost horizontally: it walks
+    along the floor to the sphere's rim, across the edge and 2.5 h beyond it, while it still belongs to the slab it came
+    from, whose ghost layer (2 h) does not reach its new neighbours.  Soak runs 401053 / 420879 / 430956 of
+    tests/fuzz/fuzz_slabs.py (3 of 4000): 16 particles ulps away from the one-slab run in the second step.  The same
+    sphere 8 h above the floor: bit-identical.  Nobody is lost either way."""
+    import sph_b200
+    from emu.backend import use_emulator
+    monkeypatch.setattr(sph_b200, "_lib", sph_b200._lib)      # use_emulator() rebinds the module's library: undone after the test
+    sph = use_emulator()
+    n_req = 6000
+    tank_w = 15.0 * float(np.sqrt(n_req / 750.0))
+    prob = sph.make_problem(n_req, tank_w=tank_w, water_frac=0.5, nranks=2)
+    p1 = sph.make_problem(n_req, tank_w=tank_w, water_frac=0.5)
+    h = prob["h"]
+    edges = [(s, e) for (_, _, s, e) in prob["slabs"]]
+    assert abs(edges[0][1] / h - 18.0) < 1e-3
+
+    def run(my_h):
+        t0 = sph.default_params(h, prob["tank_w"], prob["tank_h"], "b")
+        t0.mover_center_x = 15.694 * h; t0.mover_center_y = my_h * h      # 2.3 h left of the edge
+        ctxs = []
+        for r in range(2):
+            c = sph.Context(prob["tank_w"], prob["tank_h"], h, 2 * prob["n_global"] + 4096, msg_capacity=4096, rank=r, nranks=2)
+            t = t0.copy(); t.node_start_x, t.node_end_x = edges[r]
+            c.set_params(t); c.init_lattice(prob, r)
+            ctxs.append(c)
+        one = sph.Context(p1["tank_w"], p1["tank_h"], h, p1["n_global"] + 64)
+        one.set_params(t0); one.init_lattice(p1)
+
+        def exchange(which):
+            bufs = [[np.ctypeslib.as_array((sph.C.c_ubyte * nb).from_address(p)) for p in ptrs]
+                    for ptrs, nb in (c.exchange_pointers(which) for c in ctxs)]
+            bufs[1][1][:] = bufs[0][2]
+            bufs[0][3][:] = bufs[1][0]
+
+        for step in range(2):
+            for c in ctxs:
+                c.advect()
+            exchange(0)
+            for c in ctxs:
+                c.sort(); c.density(); c.relax()
+            exchange(1)
+            for c in ctxs:
+                c.sort()
+            one.step(1)
+        parts = [c.download() for c in ctxs]
+        uid = np.concatenate([p[1] for p in parts]); state = np.concatenate([p[0] for p in parts])
+        ref, ru = one.download()
+        assert np.array_equal(np.sort(uid), ru), "particles lost or duplicated"
+        for c in ctxs:
+            st = c.status()
+            assert st.capacity_overflow == 0 and st.msg_overflow == 0
+        o = np.argsort(uid)
+        d = np.maximum(np.abs(state["x"][o] - ref["x"]), np.abs(state["y"][o] - ref["y"])) / h
+        return int((d > 0).sum()), float(d.max())
+
+    differing, worst = run(8.0)
+    assert differing == 0, (differing, worst)
+    differing, worst = run(0.989)
+    assert 0 < differing < 100 and worst < 1e-2, (differing, worst)
